@@ -1135,3 +1135,11 @@ int afxo_condition(const float* pcm, int channels, int nframes, int src_rate, in
   free(S.data); analyser_free(&A);
   return len;
 }
+
+/* single-function exports used by the KAT tests (TestStatistics.cpp:16-113) */
+double afxo_sum(const double* x, int n) { return st_sum(x, n); }
+double afxo_mean(const double* x, int n) { return st_mean(x, n); }
+double afxo_median(const double* x, int n) { return st_median(x, n); }
+double afxo_gmean(const double* x, int n) { return st_gmean(x, n); }
+double afxo_min(const double* x, int n) { double m = n > 0 ? x[0] : 0.0; for (int i = 1; i < n; ++i) m = x[i] < m ? x[i] : m; return m; }
+double afxo_max(const double* x, int n) { double m = n > 0 ? x[0] : 0.0; for (int i = 1; i < n; ++i) m = x[i] > m ? x[i] : m; return m; }

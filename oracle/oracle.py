@@ -39,7 +39,8 @@ def lib():
         L.afxo_peaks.restype = C.c_int
         L.afxo_peaks.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         for name in ("afxo_variance", "afxo_centroid", "afxo_spread", "afxo_skewness",
-                     "afxo_kurtosis", "afxo_flatness"):
+                     "afxo_kurtosis", "afxo_flatness", "afxo_sum", "afxo_mean", "afxo_median",
+                     "afxo_gmean", "afxo_min", "afxo_max"):
             f = getattr(L, name)
             f.restype = C.c_double
             f.argtypes = [C.c_void_p, C.c_int]
@@ -95,6 +96,11 @@ def condition(pcm: np.ndarray, src_rate: int = 44100, sample_rate: int = 44100, 
     ln = L.afxo_condition(planar.ctypes.data, ch, n, src_rate, sample_rate, fft_size, data.ctypes.data,
                           cap, C.byref(off), C.byref(pk), C.byref(rms))
     return data[:ln].copy(), off.value, pk.value, rms.value
+
+
+def scalar_stat(name: str, x) -> float:
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    return float(getattr(lib(), "afxo_" + name)(x.ctypes.data if len(x) else None, len(x)))
 
 
 def stats13(x) -> np.ndarray:
