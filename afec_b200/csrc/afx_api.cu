@@ -1,0 +1,671 @@
+// C ABI of libafec_b200.so (include/afec_b200.h): context, per-batch planning, staging and the
+// kernel schedule.  Host code here only builds data-independent tables and plans (window, mel
+// filters, twiddles, chunk / frame-slot tables); every sample-dependent operation runs on the GPU.
+#include "afx_common.cuh"
+#include "../../include/afec_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#define CHUNK 8192
+
+static thread_local std::string g_create_error;
+
+// growable device / pinned buffers ------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct afx_ctx {
+  afx_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  AfxParams P;
+  DevBuf tables;                      // all constant tables in one allocation
+  DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf,
+         d_stats, d_header, d_plan, d_scratch;
+  PinBuf h_results_cache, h_plan_cache;   // recycled between batches
+  std::vector<double> zeros;          // backing store of the all-zero series
+  std::string error;
+  bool debug_times = false;
+  std::mutex mu;
+  int max_frame_cap = 0;
+};
+
+struct KernelTime { const char* name; cudaEvent_t a, b; };
+
+struct afx_batch {
+  afx_ctx* ctx = nullptr;
+  int n_files = 0;
+  std::vector<afx_file> in;
+  std::vector<AfxFile> files;
+  std::vector<AfxState> state_host;
+  // plan
+  std::vector<int> src_chunk_file, src_chunk_start, dst_chunk_file, dst_chunk_start, rs_chunk_file, rs_chunk_start;
+  struct CopyRun { const unsigned char* host; size_t dev_off; size_t bytes; };
+  std::vector<CopyRun> runs;
+  size_t pcm_bytes = 0; long long mono_samples = 0, mono_src_samples = 0;
+  int TF = 0, TFr = 0;
+  PinBuf h_plan;                      // pinned staging of file table + chunk tables
+  PinBuf h_results;                   // pinned results
+  // host result layout (offsets in doubles inside h_results)
+  size_t o_header = 0, o_state = 0, o_fs = 0, o_fsr = 0, o_fv = 0, o_stats = 0, total_doubles = 0;
+  AfxBatchDev dev;
+  AfxCondPlan cond;
+  cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  bool uploaded = false, computed = false, downloaded = false;
+  long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  std::vector<KernelTime> ktimes;
+};
+
+static int fail(afx_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+  char buf[512];
+  if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(buf, sizeof(buf), "%s", what);
+  if (c) c->error = buf; else g_create_error = buf;
+  return code;
+}
+#define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, AFX_ERR_CUDA, what, e_); } while (0)
+
+// reference rounding helpers (CoreTypes/Export/InlineMath.inl:758-761, 823-826)
+static int d2i_round(double v) { return (int)(v + (std::signbit(v) ? -0.5 : 0.5)); }
+static int f2i_round(float v) { return (int)(v + (std::signbit(v) ? -0.5f : 0.5f)); }
+static int ms_to_samples(int sr, float ms) { return f2i_round((float)sr / 1000.0f * ms); }
+static double db_to_lin(double v) { if (v == 0.0) return 1.0; if (v > -200.0) return std::exp(v * (std::log(10.0) / 20.0)); return 0.0; }
+
+// LibXtract init.c:237-378, equal gain, called as (N/2 bins, nyquist = sr/2, 20..15500 Hz, 14 filters)
+static void build_mel(std::vector<double>& tab, int nbins, double nyquist, double fmin, double fmax, int nf)
+{
+  tab.assign((size_t)nf * nbins, 0.0);
+  const int M = nbins >> 1;
+  std::vector<double> mel_peak(nf + 2), lin_peak(nf + 2); std::vector<int> fft_peak(nf + 2);
+  const double mel_max = 1127 * std::log(1 + fmax / 700), mel_min = 1127 * std::log(1 + fmin / 700);
+  const double bw = (mel_max - mel_min) / nf;
+  mel_peak[0] = mel_min; lin_peak[0] = fmin; fft_peak[0] = (int)(lin_peak[0] / nyquist * M);
+  for (int n = 1; n < nf + 2; ++n) {
+    mel_peak[n] = mel_peak[n - 1] + bw;
+    lin_peak[n] = 700 * (std::exp(mel_peak[n] / 1127) - 1);
+    fft_peak[n] = (int)(lin_peak[n] / nyquist * M);
+  }
+  int i = 0;
+  for (int n = 0; n < nf; ++n) {
+    double* row = tab.data() + (size_t)n * nbins;
+    double inc = (n == 0) ? 1.0 / fft_peak[n] : 1.0 / (fft_peak[n] - fft_peak[n - 1]);
+    double val = 0;
+    for (; i <= fft_peak[n]; ++i) { row[i] = val; val += inc; }
+    inc = 1.0 / (fft_peak[n + 1] - fft_peak[n]);
+    val = 0;
+    for (i = fft_peak[n + 1]; i > fft_peak[n]; --i) { row[i] = val; val += inc; }
+  }
+}
+
+// libresample filterkit.c:67-113 + resample.c:113-116 (float copy of one Kaiser-windowed sinc wing)
+static double rs_izero(double x)
+{
+  double sum = 1, u = 1, halfx = x / 2.0; int n = 1;
+  do { double t = halfx / (double)n; n += 1; t *= t; u *= t; sum += u; } while (u >= 1E-21 * sum);
+  return sum;
+}
+static void build_rs_wing(std::vector<float>& imp)
+{
+  const int nwing = 4096 * 34 / 2;
+  std::vector<double> c(nwing);
+  const double frq = 0.5 * 0.90, beta = 6, pi = 3.14159265358979232846;
+  c[0] = 2.0 * frq;
+  for (int i = 1; i < nwing; ++i) { const double t = pi * (double)i / 4096.0; c[i] = std::sin(2.0 * t * frq) / t; }
+  const double ibeta = 1.0 / rs_izero(beta), inm1 = 1.0 / ((double)(nwing - 1));
+  for (int i = 1; i < nwing; ++i) {
+    const double t = (double)i * inm1; double t1 = 1.0 - t * t; t1 = (t1 < 0 ? 0 : t1);
+    c[i] *= rs_izero(beta * std::sqrt(t1)) * ibeta;
+  }
+  imp.resize(nwing);
+  for (int i = 0; i < nwing; ++i) imp[i] = (float)c[i];
+}
+
+extern "C" int afx_abi_version(void) { return AFX_ABI_VERSION; }
+
+extern "C" const char* afx_last_error(const afx_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
+{
+  afx_ctx* ctx = nullptr;
+  if (!cfg || !out) return fail(nullptr, AFX_ERR_ARG, "afx_create: null argument");
+  *out = nullptr;
+  if (cfg->sample_rate != 44100 || cfg->fft_size != 2048)
+    return fail(nullptr, AFX_ERR_ARG, "afx_create: only sample_rate 44100 / fft_size 2048 are supported (Crawler.cpp:41-43)");
+  if (cfg->hop_size < 256 || cfg->hop_size > 2048 || (cfg->hop_size % 256) != 0)
+    return fail(nullptr, AFX_ERR_ARG, "afx_create: hop_size must be a multiple of 256 in [256, 2048]");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) return fail(nullptr, AFX_ERR_CUDA, "afx_create: no CUDA device (no CPU fallback exists)", e);
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, AFX_ERR_ARG, "afx_create: bad device ordinal");
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, AFX_ERR_CUDA, "cudaSetDevice", e);
+
+  ctx = new afx_ctx();
+  ctx->cfg = *cfg; ctx->device = cfg->device;
+  ctx->debug_times = getenv("AFX_DEBUG_KERNEL_TIMES") && atoi(getenv("AFX_DEBUG_KERNEL_TIMES")) != 0;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete ctx; return fail(nullptr, AFX_ERR_CUDA, "cudaStreamCreate", e); }
+
+  AfxParams& P = ctx->P;
+  memset(&P, 0, sizeof(P));
+  const int sr = cfg->sample_rate, N = cfg->fft_size, H = cfg->hop_size;
+  P.sr = sr; P.N = N; P.H = H;
+  // SampleAnalyser.cpp:171-175 -- FrequenciesPerBin is an integer division (= 21)
+  const double fpb = (double)(sr / N);
+  P.first_bin = d2i_round(20.0 / fpb);
+  const int last_bin = d2i_round(15500.0 / fpb);
+  P.nbins = last_bin - P.first_bin + 1;
+  static const double b14[14] = { 50.0, 100.0, 200.0, 400.0, 630.0, 920.0, 1270.0, 1720.0, 2320.0, 3150.0, 4400.0, 6400.0, 9500.0, 15500.0 };
+  static const double b28[28] = { 50.0, 100.0, 150.0, 200.0, 300.0, 400.0, 510.0, 630.0, 770.0, 920.0, 1080.0, 1270.0, 1480.0, 1720.0,
+    2000.0, 2320.0, 2700.0, 3150.0, 3700.0, 4400.0, 5300.0, 6400.0, 7700.0, 9500.0, 12000.0, 15500.0, 19000.0, 22050.0 };
+  { // SampleAnalyser.cpp:2084-2100, 2134-2241: bins are consumed cumulatively from first_bin
+    int cur = P.first_bin;
+    for (int b = 0; b < 14; ++b) {
+      const int s = (b == 0) ? P.first_bin : d2i_round(b14[b - 1] / fpb);
+      const int en = d2i_round(b14[b] / fpb);
+      int nb = en - s + 1; if (nb > N / 2 - cur) nb = N / 2 - cur;
+      P.band14_start[b] = cur; P.band14_n[b] = nb;
+      int nei = (int)(0.3 * nb); if (nei < 1) nei = 1;
+      P.band14_nei[b] = nei;
+      cur += nb;
+    }
+  }
+  for (int b = 0; b < 28; ++b) {   // SampleAnalyser.cpp:2026-2045
+    int s = d2i_round((b == 0) ? (double)P.first_bin : b28[b - 1] / fpb);
+    int en = d2i_round(b28[b] / fpb); if (en > N / 2) en = N / 2;
+    if (s >= N / 2) { s = 0; en = 0; }
+    P.band28_s[b] = s; P.band28_e[b] = en;
+  }
+  P.wh_decay = std::pow(0.001, (double)((float)H / (float)sr) / 22.0);       // awhitening.c:84-86, SA.cpp:44
+  P.env_coef = std::pow(0.01, (1000.0 / (8.0 * (double)sr)));                // Envelopes.cpp:66-69, SA.cpp:69
+  P.silence_floor_amp = (double)32768.0f * db_to_lin(-48.0);                 // SA.cpp:648-649
+  P.eff_floor[0] = db_to_lin(-48.0); P.eff_floor[1] = db_to_lin(-24.0); P.eff_floor[2] = db_to_lin(-12.0);
+  P.analysis_cap = ms_to_samples(sr, 1000 * 20);                             // SA.cpp:37, 760-761
+  P.ac_min_period = ms_to_samples(sr, 0.8f); P.ac_width = ms_to_samples(sr, 12.0f);   // SA.cpp:2318-2324
+
+  // ---- constant tables ----
+  std::vector<double> window(N), rwindow(AFX_RFFT), mel, dct(14 * 14);
+  std::vector<double> tw2048(2 * 2048), tw512(2 * 512);
+  std::vector<float> imp;
+  const double pi = 3.14159265358979323846;
+  for (int n = 0; n < N; ++n) window[n] = (0.5 * (1.0 - std::cos(2.0 * pi * (double)n / (double)(N - 1)))) * 2.0;   // window.c:67-76, SA.cpp:178-181
+  for (int i = 0; i < AFX_RFFT; ++i) rwindow[i] = 0.5 * (1.0 - std::cos(6.2831853071795864769252867665590 * (double)i * (1.0 / (double)(AFX_RFFT - 1))));  // Fourier.cpp:545-551
+  build_mel(mel, N / 2, sr / 2, 20.0, 15500.0, 14);
+  for (int n = 0; n < 14; ++n) for (int m = 1; m <= 14; ++m) dct[n * 14 + (m - 1)] = std::cos(pi * (n / (double)14) * (m - 0.5));   // vector.c:372-391
+  for (int k = 0; k < 2048; ++k) { tw2048[2 * k] = std::cos(-2.0 * pi * k / 2048.0); tw2048[2 * k + 1] = std::sin(-2.0 * pi * k / 2048.0); }
+  for (int k = 0; k < 512; ++k) { tw512[2 * k] = std::cos(-2.0 * pi * k / 512.0); tw512[2 * k + 1] = std::sin(-2.0 * pi * k / 512.0); }
+  build_rs_wing(imp);
+
+  size_t off = 0;
+  auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_win = place(window.size() * 8), o_rwin = place(rwindow.size() * 8), o_mel = place(mel.size() * 8),
+    o_dct = place(dct.size() * 8), o_tw = place(tw2048.size() * 8), o_tw5 = place(tw512.size() * 8), o_imp = place(imp.size() * 4);
+  e = ctx->tables.reserve(off);
+  if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMalloc(tables)", e); }
+  unsigned char* base = (unsigned char*)ctx->tables.p;
+  cudaMemcpy(base + o_win, window.data(), window.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_rwin, rwindow.data(), rwindow.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_mel, mel.data(), mel.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_dct, dct.data(), dct.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_tw, tw2048.data(), tw2048.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_tw5, tw512.data(), tw512.size() * 8, cudaMemcpyHostToDevice);
+  e = cudaMemcpy(base + o_imp, imp.data(), imp.size() * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMemcpy(tables)", e); }
+  P.t.window = (const double*)(base + o_win); P.t.rwindow = (const double*)(base + o_rwin);
+  P.t.mel = (const double*)(base + o_mel); P.t.dct = (const double*)(base + o_dct);
+  P.t.tw2048 = (const double2*)(base + o_tw); P.t.tw512 = (const double2*)(base + o_tw5);
+  P.t.rs_imp = (const float*)(base + o_imp);
+
+  ctx->max_frame_cap = (P.analysis_cap - AFX_RFFT) / AFX_RHOP + 2;
+  ctx->zeros.assign(ctx->max_frame_cap, 0.0);
+  *out = ctx;
+  return AFX_OK;
+}
+
+extern "C" void afx_destroy(afx_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  DevBuf* bufs[] = { &ctx->tables, &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
+    &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch };
+  for (DevBuf* b : bufs) b->release();
+  ctx->h_results_cache.release(); ctx->h_plan_cache.release();
+  delete ctx;
+}
+
+extern "C" int afx_host_alloc(afx_ctx* ctx, uint64_t bytes, void** out)
+{
+  if (!ctx || !out) return AFX_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault), "cudaHostAlloc");
+  return AFX_OK;
+}
+extern "C" int afx_host_free(afx_ctx* ctx, void* p)
+{
+  if (!ctx) return AFX_ERR_ARG;
+  if (p) CK(cudaFreeHost(p), "cudaFreeHost");
+  return AFX_OK;
+}
+
+// ---- batch planning ------------------------------------------------------------------------------
+extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_files, afx_batch** out)
+{
+  if (!ctx || !out || (n_files > 0 && !files) || n_files < 0) return fail(ctx, AFX_ERR_ARG, "afx_batch_create: bad arguments");
+  *out = nullptr;
+  const AfxParams& P = ctx->P;
+  afx_batch* b = new afx_batch();
+  b->ctx = ctx; b->n_files = n_files;
+  b->in.assign(files, files + n_files);
+  b->files.resize(n_files);
+  size_t pcm_off = 0; long long mono_off = 0, src_off = 0; long long tf = 0, tfr = 0;
+  const unsigned char* run_end = nullptr;
+  for (int i = 0; i < n_files; ++i) {
+    const afx_file& f = files[i];
+    AfxFile& d = b->files[i];
+    memset(&d, 0, sizeof(d));
+    d.channels = f.channels; d.src_rate = f.src_rate; d.format = f.format; d.bit_depth = f.bit_depth; d.file_size = f.file_size;
+    d.status = AFX_FILE_OK;
+    if (f.channels < 1 || f.channels > 8) d.status = AFX_FILE_BAD_CHANNELS;          // SA.cpp:472-477
+    else if (f.nframes <= 0 || !f.pcm) d.status = AFX_FILE_EMPTY;                     // SA.cpp:479-482
+    else if (f.nframes > 0x7fffffffLL / 8 || f.src_rate <= 0 || (f.format != AFX_PCM_I16 && f.format != AFX_PCM_F32)) {
+      delete b; return fail(ctx, AFX_ERR_ARG, "afx_batch_create: unsupported file description");
+    }
+    d.frame_off = (int)tf; d.rframe_off = (int)tfr; d.mono_off = mono_off; d.src_off = src_off; d.pcm_off = (long long)pcm_off;
+    if (d.status != AFX_FILE_OK) continue;
+    d.nframes_src = (int)f.nframes;
+    const double speed = (double)f.src_rate / (double)P.sr;                            // SA.cpp:563-573
+    d.n = d.nframes_src;
+    if (speed != 1.0) { int nn = d2i_round(d.nframes_src / speed); d.n = nn < 1 ? 1 : nn; }
+    // upper bounds for the conditioned length: len <= max(n + N/2, N)
+    long long lmax = std::max<long long>((long long)d.n + P.N / 2, P.N);
+    if (lmax > P.analysis_cap) lmax = P.analysis_cap;
+    d.frame_cap = (int)((lmax - P.N) / P.H + 1);
+    d.rframe_cap = (int)((lmax - AFX_RFFT) / AFX_RHOP + 1);
+    tf += d.frame_cap; tfr += d.rframe_cap;
+    // PCM packing: keep host-contiguous files contiguous on the device so they move in one copy
+    const size_t bps = (f.format == AFX_PCM_I16) ? 2 : 4;
+    const size_t bytes = (size_t)f.nframes * f.channels * bps;
+    const unsigned char* hp = (const unsigned char*)f.pcm;
+    if (run_end == hp && (pcm_off % bps) == 0 && !b->runs.empty()) {
+      b->runs.back().bytes += bytes;
+    } else {
+      pcm_off = (pcm_off + 15) & ~(size_t)15;
+      b->runs.push_back({ hp, pcm_off, bytes });
+    }
+    d.pcm_off = (long long)pcm_off;
+    pcm_off += bytes; run_end = hp + bytes;
+    mono_off += ((long long)d.n + 3) & ~3LL;
+    d.mono_off = mono_off - (((long long)d.n + 3) & ~3LL);
+    if (speed != 1.0) { d.src_off = src_off; src_off += ((long long)d.nframes_src + 3) & ~3LL; }
+    for (int s = 0; s < d.nframes_src; s += CHUNK) { b->src_chunk_file.push_back(i); b->src_chunk_start.push_back(s); }
+    for (int s = 0; s < d.n; s += CHUNK) {
+      b->dst_chunk_file.push_back(i); b->dst_chunk_start.push_back(s);
+      if (speed != 1.0) { b->rs_chunk_file.push_back(i); b->rs_chunk_start.push_back(s); }
+    }
+    if (tf > 0x7fffffffLL || tfr > 0x7fffffffLL) { delete b; return fail(ctx, AFX_ERR_ARG, "afx_batch_create: batch too large (frame slots overflow int32)"); }
+  }
+  b->pcm_bytes = pcm_off; b->mono_samples = mono_off; b->mono_src_samples = src_off;
+  b->TF = (int)tf; b->TFr = (int)tfr;
+
+  // host result layout
+  size_t o = 0;
+  b->o_header = o; o += (size_t)n_files * AFX_N_HEADER;
+  b->o_stats = o; o += (size_t)n_files * AFX_N_SERIES * AFX_N_STATS;
+  b->o_fs = o; o += (size_t)AFX_N_FS_MAIN * b->TF;
+  b->o_fsr = o; o += (size_t)2 * b->TFr;
+  b->o_fv = o; o += (size_t)AFX_FV_STRIDE * b->TF;
+  b->o_state = o; o += ((size_t)n_files * sizeof(AfxState) + 7) / 8;
+  b->total_doubles = o;
+  *out = b;
+  return AFX_OK;
+}
+
+static void take_cached(PinBuf& dst, PinBuf& cache, size_t bytes)
+{
+  if (cache.p && cache.cap >= bytes) { dst = cache; cache.p = nullptr; cache.cap = 0; }
+}
+static void give_back(PinBuf& src, PinBuf& cache)
+{
+  if (!src.p) return;
+  if (!cache.p || cache.cap < src.cap) { cache.release(); cache = src; src.p = nullptr; src.cap = 0; }
+  else src.release();
+}
+
+extern "C" int afx_batch_upload(afx_batch* b)
+{
+  if (!b) return AFX_ERR_ARG;
+  afx_ctx* ctx = b->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  const int n = b->n_files;
+  if (!b->ev[0]) for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&b->ev[i]), "cudaEventCreate");
+
+  // device buffers
+  const size_t TF = (size_t)b->TF, TFr = (size_t)b->TFr;
+  const unsigned feat = ctx->cfg.features;
+  CK(ctx->d_pcm.reserve(b->pcm_bytes + 16), "cudaMalloc(pcm)");
+  CK(ctx->d_mono.reserve((size_t)(b->mono_samples + 8) * 4), "cudaMalloc(mono)");
+  if (b->mono_src_samples) CK(ctx->d_mono_src.reserve((size_t)(b->mono_src_samples + 8) * 4), "cudaMalloc(mono_src)");
+  CK(ctx->d_files.reserve((size_t)(n + 1) * sizeof(AfxFile)), "cudaMalloc(files)");
+  CK(ctx->d_state.reserve((size_t)(n + 1) * sizeof(AfxState)), "cudaMalloc(state)");
+  CK(ctx->d_mag.reserve((TF + 1) * AFX_NBIN * 8), "cudaMalloc(mag)");
+  CK(ctx->d_cent.reserve((TF + 1) * 8), "cudaMalloc(cent)");
+  CK(ctx->d_fs.reserve((TF + 1) * AFX_N_FS_MAIN * 8), "cudaMalloc(fs)");
+  CK(ctx->d_fsr.reserve((TFr + 1) * 2 * 8), "cudaMalloc(fsr)");
+  if (feat & AFX_FEAT_BANDS) CK(ctx->d_fv.reserve((TF + 1) * AFX_FV_STRIDE * 8), "cudaMalloc(fv)");
+  if (feat & AFX_FEAT_RHYTHM) {
+    CK(ctx->d_rpolar.reserve((TFr + 1) * AFX_RROW * 4), "cudaMalloc(rpolar)");
+    CK(ctx->d_rodf.reserve((TFr + 1) * 2 * 4), "cudaMalloc(rodf)");
+    CK(ctx->d_scratch.reserve((TFr + 1) * 2 * 2 * 8 + 1024), "cudaMalloc(scratch)");
+  }
+  CK(ctx->d_stats.reserve((size_t)(n + 1) * AFX_N_SERIES * AFX_N_STATS * 8), "cudaMalloc(stats)");
+  CK(ctx->d_header.reserve((size_t)(n + 1) * AFX_N_HEADER * 8), "cudaMalloc(header)");
+
+  // plan tables -> one pinned block -> one H2D copy
+  const size_t nsc = b->src_chunk_file.size(), ndc = b->dst_chunk_file.size(), nrc = b->rs_chunk_file.size();
+  size_t po = 0;
+  auto place = [&](size_t bytes) { size_t o = po; po += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t p_files = place((size_t)n * sizeof(AfxFile));
+  const size_t p_scf = place(nsc * 4), p_scs = place(nsc * 4), p_dcf = place(ndc * 4), p_dcs = place(ndc * 4),
+    p_rcf = place(nrc * 4), p_rcs = place(nrc * 4);
+  take_cached(b->h_plan, ctx->h_plan_cache, po);
+  CK(b->h_plan.reserve(po + 256), "cudaHostAlloc(plan)");
+  CK(ctx->d_plan.reserve(po + 256), "cudaMalloc(plan)");
+  unsigned char* hp = (unsigned char*)b->h_plan.p;
+  if (n) memcpy(hp + p_files, b->files.data(), (size_t)n * sizeof(AfxFile));
+  if (nsc) { memcpy(hp + p_scf, b->src_chunk_file.data(), nsc * 4); memcpy(hp + p_scs, b->src_chunk_start.data(), nsc * 4); }
+  if (ndc) { memcpy(hp + p_dcf, b->dst_chunk_file.data(), ndc * 4); memcpy(hp + p_dcs, b->dst_chunk_start.data(), ndc * 4); }
+  if (nrc) { memcpy(hp + p_rcf, b->rs_chunk_file.data(), nrc * 4); memcpy(hp + p_rcs, b->rs_chunk_start.data(), nrc * 4); }
+
+  CK(cudaEventRecord(b->ev[0], ctx->stream), "cudaEventRecord");
+  CK(cudaMemcpyAsync(ctx->d_plan.p, hp, po, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(plan)");
+  b->h2d_bytes = (long long)po;
+  for (const auto& r : b->runs) {
+    CK(cudaMemcpyAsync((unsigned char*)ctx->d_pcm.p + r.dev_off, r.host, r.bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(pcm)");
+    b->h2d_bytes += (long long)r.bytes;
+  }
+  CK(cudaEventRecord(b->ev[1], ctx->stream), "cudaEventRecord");
+
+  unsigned char* dp = (unsigned char*)ctx->d_plan.p;
+  AfxBatchDev& D = b->dev;
+  memset(&D, 0, sizeof(D));
+  D.n_files = n; D.TF = b->TF; D.TFr = b->TFr;
+  D.pcm = (const unsigned char*)ctx->d_pcm.p; D.mono = (float*)ctx->d_mono.p; D.mono_src = (float*)ctx->d_mono_src.p;
+  D.files = (const AfxFile*)(dp + p_files); D.state = (AfxState*)ctx->d_state.p;
+  D.mag = (double*)ctx->d_mag.p; D.cent_full = (double*)ctx->d_cent.p; D.fs = (double*)ctx->d_fs.p; D.fsr = (double*)ctx->d_fsr.p;
+  D.fv = (double*)ctx->d_fv.p; D.rpolar = (float*)ctx->d_rpolar.p; D.rodf = (float*)ctx->d_rodf.p;
+  D.stats = (double*)ctx->d_stats.p; D.header = (double*)ctx->d_header.p; D.scratch = (double*)ctx->d_scratch.p;
+  AfxCondPlan& C = b->cond;
+  memset(&C, 0, sizeof(C));
+  C.src_chunk_file = (const int*)(dp + p_scf); C.src_chunk_start = (const int*)(dp + p_scs); C.n_src_chunks = (int)nsc;
+  C.dst_chunk_file = (const int*)(dp + p_dcf); C.dst_chunk_start = (const int*)(dp + p_dcs); C.n_dst_chunks = (int)ndc;
+  C.rs_chunk_file = (const int*)(dp + p_rcf); C.rs_chunk_start = (const int*)(dp + p_rcs); C.n_rs_chunks = (int)nrc;
+  b->uploaded = true;
+  return AFX_OK;
+}
+
+static void ktime_begin(afx_batch* b, const char* name)
+{
+  if (!b->ctx->debug_times) return;
+  KernelTime k; k.name = name;
+  cudaEventCreate(&k.a); cudaEventCreate(&k.b);
+  cudaEventRecord(k.a, b->ctx->stream);
+  b->ktimes.push_back(k);
+}
+static void ktime_end(afx_batch* b)
+{
+  if (!b->ctx->debug_times) return;
+  cudaEventRecord(b->ktimes.back().b, b->ctx->stream);
+}
+
+extern "C" int afx_batch_compute(afx_batch* b)
+{
+  if (!b) return AFX_ERR_ARG;
+  afx_ctx* ctx = b->ctx;
+  if (!b->uploaded) return fail(ctx, AFX_ERR_STATE, "afx_batch_compute: upload first");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  const unsigned feat = ctx->cfg.features;
+  for (auto& k : b->ktimes) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
+  b->ktimes.clear();
+  b->launches = 0;
+  CK(cudaEventRecord(b->ev[2], ctx->stream), "cudaEventRecord");
+  ktime_begin(b, "condition"); afx_launch_condition_plan(ctx->P, b->dev, b->cond, ctx->stream, &b->launches); ktime_end(b);
+  if (feat & (AFX_FEAT_SPECTRAL | AFX_FEAT_AMPLITUDE | AFX_FEAT_PEAKS | AFX_FEAT_BANDS | AFX_FEAT_PITCH)) {
+    ktime_begin(b, "spectrum"); afx_launch_spectrum(ctx->P, b->dev, feat, ctx->stream, &b->launches); ktime_end(b);
+  }
+#ifdef AFX_HAVE_PEAKS
+  if (feat & AFX_FEAT_PEAKS) { ktime_begin(b, "peaks"); afx_launch_peaks(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+#endif
+#ifdef AFX_HAVE_BANDS
+  if (feat & AFX_FEAT_BANDS) { ktime_begin(b, "bands"); afx_launch_bands(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+#endif
+#ifdef AFX_HAVE_PITCH
+  if (feat & AFX_FEAT_PITCH) { ktime_begin(b, "pitch"); afx_launch_pitch(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+#endif
+#ifdef AFX_HAVE_AUTOCORR
+  if (feat & AFX_FEAT_AUTOCORR) { ktime_begin(b, "autocorr"); afx_launch_autocorr(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+#endif
+#ifdef AFX_HAVE_RHYTHM
+  if (feat & AFX_FEAT_RHYTHM) { ktime_begin(b, "rhythm"); afx_launch_rhythm(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+#endif
+#ifdef AFX_HAVE_STATS
+  if (feat & AFX_FEAT_STATS) { ktime_begin(b, "stats"); afx_launch_stats(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+#endif
+  CK(cudaEventRecord(b->ev[3], ctx->stream), "cudaEventRecord");
+  CK(cudaGetLastError(), "kernel launch");
+  b->computed = true;
+  return AFX_OK;
+}
+
+// fs rows produced by a feature mask, as [begin, end) ranges
+static void fs_row_ranges(unsigned feat, std::vector<std::pair<int, int>>& out)
+{
+  bool have[AFX_N_FS_MAIN] = { false };
+  if (feat & AFX_FEAT_AMPLITUDE) for (int r = 0; r < 4; ++r) have[r] = true;
+  if (feat & AFX_FEAT_SPECTRAL) { for (int r = 4; r <= 10; ++r) have[r] = true; have[FS_SPEC_FLUX] = true; }
+  if (feat & AFX_FEAT_PEAKS) have[FS_SPEC_COMPLEXITY] = true;
+  if (feat & AFX_FEAT_BANDS) have[FS_SPEC_CONTRAST] = true;
+  if (feat & AFX_FEAT_PITCH) { have[FS_F0] = have[FS_F0_CONF] = have[FS_F0_FAILSAFE] = true; }
+  if (feat & AFX_FEAT_AUTOCORR) have[FS_AUTOCORR] = true;
+  int r = 0;
+  while (r < AFX_N_FS_MAIN) {
+    if (!have[r]) { ++r; continue; }
+    int e = r; while (e < AFX_N_FS_MAIN && have[e]) ++e;
+    out.push_back({ r, e }); r = e;
+  }
+}
+
+extern "C" int afx_batch_download(afx_batch* b)
+{
+  if (!b) return AFX_ERR_ARG;
+  afx_ctx* ctx = b->ctx;
+  if (!b->computed) return fail(ctx, AFX_ERR_STATE, "afx_batch_download: compute first");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  const unsigned feat = ctx->cfg.features;
+  const size_t bytes = b->total_doubles * 8 + 64;
+  if (!b->h_results.p) take_cached(b->h_results, ctx->h_results_cache, bytes);
+  CK(b->h_results.reserve(bytes), "cudaHostAlloc(results)");
+  double* H = (double*)b->h_results.p;
+  const int n = b->n_files; const size_t TF = (size_t)b->TF, TFr = (size_t)b->TFr;
+  b->d2h_bytes = 0;
+  CK(cudaEventRecord(b->ev[4], ctx->stream), "cudaEventRecord");
+  auto cp = [&](void* dst, const void* src, size_t nbytes) -> cudaError_t {
+    if (!nbytes) return cudaSuccess;
+    b->d2h_bytes += (long long)nbytes;
+    return cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream);
+  };
+  CK(cp(H + b->o_header, b->dev.header, (size_t)n * AFX_N_HEADER * 8), "D2H header");
+  CK(cp(H + b->o_state, b->dev.state, (size_t)n * sizeof(AfxState)), "D2H state");
+  if (feat & AFX_FEAT_STATS) CK(cp(H + b->o_stats, b->dev.stats, (size_t)n * AFX_N_SERIES * AFX_N_STATS * 8), "D2H stats");
+  std::vector<std::pair<int, int>> rr; fs_row_ranges(feat, rr);
+  for (auto& r : rr) CK(cp(H + b->o_fs + (size_t)r.first * TF, b->dev.fs + (size_t)r.first * TF, (size_t)(r.second - r.first) * TF * 8), "D2H fs");
+  if (feat & AFX_FEAT_RHYTHM) CK(cp(H + b->o_fsr, b->dev.fsr, 2 * TFr * 8), "D2H fsr");
+  if (feat & AFX_FEAT_BANDS) CK(cp(H + b->o_fv, b->dev.fv, TF * AFX_FV_STRIDE * 8), "D2H fv");
+  CK(cudaEventRecord(b->ev[5], ctx->stream), "cudaEventRecord");
+  b->downloaded = true;
+  return AFX_OK;
+}
+
+extern "C" int afx_batch_sync(afx_batch* b)
+{
+  if (!b) return AFX_ERR_ARG;
+  afx_ctx* ctx = b->ctx;
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  return AFX_OK;
+}
+
+extern "C" int afx_analyze(afx_ctx* ctx, const afx_file* files, int32_t n_files, afx_batch** out)
+{
+  int rc = afx_batch_create(ctx, files, n_files, out);
+  if (rc != AFX_OK) return rc;
+  afx_batch* b = *out;
+  if ((rc = afx_batch_upload(b)) != AFX_OK || (rc = afx_batch_compute(b)) != AFX_OK ||
+      (rc = afx_batch_download(b)) != AFX_OK || (rc = afx_batch_sync(b)) != AFX_OK) {
+    afx_batch_free(b); *out = nullptr; return rc;
+  }
+  return AFX_OK;
+}
+
+extern "C" int afx_batch_result(const afx_batch* b, int32_t i, afx_file_result* out)
+{
+  if (!b || !out || i < 0 || i >= b->n_files) return AFX_ERR_ARG;
+  if (!b->downloaded) return fail(b->ctx, AFX_ERR_STATE, "afx_batch_result: download + sync first");
+  memset(out, 0, sizeof(*out));
+  const AfxFile& f = b->files[i];
+  out->status = f.status;
+  const double* H = (const double*)b->h_results.p;
+  out->header = H + b->o_header + (size_t)i * AFX_N_HEADER;
+  if (f.status != AFX_FILE_OK) return AFX_OK;
+  const AfxState* st = reinterpret_cast<const AfxState*>(H + b->o_state) + i;
+  out->n_frames = st->F; out->n_rhythm_frames = st->Fr;
+  const unsigned feat = b->ctx->cfg.features;
+  std::vector<std::pair<int, int>> rr; fs_row_ranges(feat, rr);
+  const size_t TF = (size_t)b->TF, TFr = (size_t)b->TFr;
+  for (auto& r : rr) for (int s = r.first; s < r.second; ++s) out->fs[s] = H + b->o_fs + (size_t)s * TF + f.frame_off;
+  if (feat & AFX_FEAT_SPECTRAL) {   // constant-zero series (degenerate in the reference)
+    out->fs[FS_SPEC_INHARM] = out->fs[FS_TRISTIM1] = out->fs[FS_TRISTIM2] = out->fs[FS_TRISTIM3] = b->ctx->zeros.data();
+  }
+  if (feat & AFX_FEAT_RHYTHM) for (int s = 0; s < 2; ++s) out->fs[AFX_N_FS_MAIN + s] = H + b->o_fsr + (size_t)s * TFr + f.rframe_off;
+  if (feat & AFX_FEAT_BANDS) {
+    static const int offs[AFX_N_FV] = { FV_RMS, FV_FLATNESS, FV_FLUX, FV_COMPLEXITY, FV_CONTRAST, FV_BANDS28, FV_CEPSTRUM };
+    static const int nbv[AFX_N_FV] = { 14, 14, 14, 14, 14, 28, 14 };
+    for (int v = 0; v < AFX_N_FV; ++v) out->fv[v] = H + b->o_fv + (size_t)offs[v] * TF + (size_t)f.frame_off * nbv[v];
+  }
+  if (feat & AFX_FEAT_STATS) out->stats = H + b->o_stats + (size_t)i * AFX_N_SERIES * AFX_N_STATS;
+  return AFX_OK;
+}
+
+extern "C" void afx_batch_free(afx_batch* b)
+{
+  if (!b) return;
+  afx_ctx* ctx = b->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    give_back(b->h_results, ctx->h_results_cache);
+    give_back(b->h_plan, ctx->h_plan_cache);
+  }
+  for (int i = 0; i < 6; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+  for (auto& k : b->ktimes) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
+  delete b;
+}
+
+extern "C" int afx_batch_timings(const afx_batch* b, float* up, float* comp, float* down)
+{
+  if (!b) return AFX_ERR_ARG;
+  cudaSetDevice(b->ctx->device);
+  float v;
+  if (up) { *up = 0; if (b->uploaded && cudaEventElapsedTime(&v, b->ev[0], b->ev[1]) == cudaSuccess) *up = v; }
+  if (comp) { *comp = 0; if (b->computed && cudaEventElapsedTime(&v, b->ev[2], b->ev[3]) == cudaSuccess) *comp = v; }
+  if (down) { *down = 0; if (b->downloaded && cudaEventElapsedTime(&v, b->ev[4], b->ev[5]) == cudaSuccess) *down = v; }
+  return AFX_OK;
+}
+
+extern "C" int afx_batch_counters(const afx_batch* b, int64_t* launches, int64_t* h2d, int64_t* d2h, int64_t* frames, int64_t* rframes)
+{
+  if (!b) return AFX_ERR_ARG;
+  if (launches) *launches = b->launches;
+  if (h2d) *h2d = b->h2d_bytes;
+  if (d2h) *d2h = b->d2h_bytes;
+  long long F = 0, Fr = 0;
+  if (b->downloaded) {
+    const AfxState* st = reinterpret_cast<const AfxState*>((const double*)b->h_results.p + b->o_state);
+    for (int i = 0; i < b->n_files; ++i) if (b->files[i].status == 0) { F += st[i].F; Fr += st[i].Fr; }
+  }
+  if (frames) *frames = F;
+  if (rframes) *rframes = Fr;
+  return AFX_OK;
+}
+
+extern "C" int afx_batch_kernel_times(const afx_batch* b, const char** names, float* ms, int32_t cap)
+{
+  if (!b) return AFX_ERR_ARG;
+  cudaSetDevice(b->ctx->device);
+  int n = 0;
+  for (const auto& k : b->ktimes) {
+    if (n >= cap) break;
+    float v = 0; cudaEventElapsedTime(&v, k.a, k.b);
+    if (names) names[n] = k.name;
+    if (ms) ms[n] = v;
+    ++n;
+  }
+  return n;
+}
+
+extern "C" int64_t afx_batch_conditioned(const afx_batch* b, int32_t i, double* out, int64_t cap)
+{
+  if (!b || i < 0 || i >= b->n_files) return AFX_ERR_ARG;
+  afx_ctx* ctx = b->ctx;
+  if (!b->computed) return fail(ctx, AFX_ERR_STATE, "afx_batch_conditioned: compute first");
+  cudaSetDevice(ctx->device);
+  AfxState st;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return AFX_ERR_CUDA;
+  if (cudaMemcpy(&st, b->dev.state + i, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) return AFX_ERR_CUDA;
+  if (b->files[i].status != 0) return 0;
+  if (!out || cap < st.len) return st.len;
+  double* d = nullptr;
+  if (cudaMalloc(&d, (size_t)st.len * 8) != cudaSuccess) return AFX_ERR_NOMEM;
+  afx_launch_materialise(b->dev.mono + b->files[i].mono_off, b->dev.state + i, d, st.len, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaMemcpy(out, d, (size_t)st.len * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return st.len;
+}

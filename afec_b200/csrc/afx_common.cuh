@@ -1,0 +1,256 @@
+// Shared device-side types and helpers of libafec_b200 (sm_100a).
+//
+// Data layout in HBM for one batch (see DESIGN.md "Data layout"):
+//   pcm      raw interleaved PCM of every file, packed in submission order
+//   mono     float32 mono signal at the analysis rate (after downmix / resample), per file
+//   files    AfxFile[n_files]       host-built descriptor table
+//   state    AfxState[n_files]      device-computed conditioning result
+//   mag      double [TF][1024]      magnitude spectra of all main frames (TF = sum of frame caps)
+//   fs       double [22][TF]        framed scalars on the main grid (series-major -> coalesced)
+//   fsr      double [2][TFr]        onset series on the rhythm grid
+//   fv       double 7 x [TF][nb]    framed vectors (5 x 14 sub-bands, 28 bands, 14 cepstrum), one array each
+//   stats    double [n_files][136][13]
+//   header   double [n_files][32]
+// The conditioned signal mData (SampleAnalyser.cpp:698-718) is never materialised: frames read
+// the float32 mono buffer through mdata() which applies trim, padding and normalisation.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define AFX_NFFT 2048
+#define AFX_NBIN 1024
+#define AFX_RFFT 512
+#define AFX_RHOP 128
+#define AFX_RBINS 255
+#define AFX_RROW 512        // floats per rhythm frame row: mag[0..255], dc, nyq, pad | phase[256..511]
+#define AFX_FV_STRIDE 112
+
+// fs series ids (order of afec_b200/layout.py FRAMED_SCALARS)
+enum {
+  FS_AMP_SILENCE = 0, FS_AMP_PEAK, FS_AMP_RMS, FS_AMP_ENV,
+  FS_SPEC_RMS, FS_SPEC_CENTROID, FS_SPEC_ROLLOFF, FS_SPEC_SPREAD, FS_SPEC_SKEW, FS_SPEC_KURT,
+  FS_SPEC_FLATNESS, FS_SPEC_INHARM, FS_SPEC_COMPLEXITY, FS_SPEC_CONTRAST, FS_SPEC_FLUX,
+  FS_F0, FS_F0_CONF, FS_F0_FAILSAFE, FS_TRISTIM1, FS_TRISTIM2, FS_TRISTIM3, FS_AUTOCORR,
+  FS_ONSETS_COMPLEX, FS_ONSETS_PERC
+};
+// fv: seven arrays [TF][nbands]; array v starts at fv + FV_x * TF (FV_x = cumulative band count)
+enum { FV_RMS = 0, FV_FLATNESS = 14, FV_FLUX = 28, FV_COMPLEXITY = 42, FV_CONTRAST = 56, FV_BANDS28 = 70, FV_CEPSTRUM = 98 };
+// header slots
+enum {
+  H_FILE_SIZE = 0, H_FILE_LENGTH, H_FILE_RATE, H_FILE_CHANNELS, H_FILE_BITS,
+  H_EFF48, H_EFF24, H_EFF12, H_ANALYZATION_OFFSET,
+  H_RC_COUNT, H_RC_CONTRAST, H_RC_FREQ, H_RC_STRENGTH, H_RC_TEMPO, H_RC_TEMPO_CONF,
+  H_RP_COUNT, H_RP_CONTRAST, H_RP_FREQ, H_RP_STRENGTH, H_RP_TEMPO, H_RP_TEMPO_CONF,
+  H_FINAL_TEMPO, H_FINAL_TEMPO_CONF, H_PEAK, H_RMS, H_DATA_OFFSET, H_DATA_LEN
+};
+
+struct AfxFile {            // host-built, one per file
+  long long pcm_off;        // byte offset of the file's interleaved PCM in the device pcm buffer
+  long long mono_off;       // sample offset into the mono buffer
+  long long src_off;        // sample offset into the pre-resample mono buffer (resampled files only)
+  int nframes_src;          // frames per channel as decoded
+  int n;                    // samples at the analysis rate (== nframes_src unless resampled)
+  int channels, src_rate, format, bit_depth;
+  long long file_size;
+  int frame_off, frame_cap; // main frame slots [frame_off, frame_off + frame_cap)
+  int rframe_off, rframe_cap;
+  int status;               // AFX_FILE_*
+  int pad;
+};
+
+struct AfxState {           // device-computed, one per file (SampleAnalyser.cpp:610-718)
+  unsigned int maxabs_bits; // max |x| as float bits (non-negative floats order like ints)
+  int first, last;          // first / last sample above the -48 dB floor (n / -1 when none)
+  int eff_first[3], eff_last[3];
+  double sumsq;             // sum (x/32768)^2
+  double fs;                // FinalScaling = Amplification / 32768
+  double amp;
+  int lead, audible, start_off, len;
+  int L, F, Fr, data_offset;
+};
+
+struct AfxTables {          // per-context constant tables in device memory
+  const double* window;     // [2048] Hann * 2
+  const double2* tw2048;    // [2048] exp(-2 pi i k / 2048)
+  const double2* tw512;     // [512]  exp(-2 pi i k / 512)
+  const double* rwindow;    // [512] rhythm Hann
+  const double* mel;        // [14][1024]
+  const double* dct;        // [14][14] cos(pi n/14 (m+0.5)), row n
+  const float* rs_imp;      // [69632] resampler wing
+};
+
+struct AfxParams {
+  int sr, N, H;
+  int first_bin, nbins;     // 1, 738
+  int band14_start[14], band14_n[14], band14_nei[14];
+  int band28_s[28], band28_e[28];
+  double wh_decay, env_coef, silence_floor_amp;   // silence floor in 16-bit range (SA.cpp:648-649)
+  double eff_floor[3];
+  int analysis_cap;         // 882000
+  int ac_min_period, ac_width;   // 35, 529
+  AfxTables t;
+};
+
+// ---------------------------------------------------------------------------------------------
+// the conditioned signal (reference: TSampleData::mData) as a function of the mono buffer
+__device__ __forceinline__ double mdata(const float* __restrict__ mono, const AfxState& st, int i)
+{
+  const int j = i - st.start_off;
+  return (j >= 0 && j < st.audible) ? (double)__ldg(mono + st.lead + j) * st.fs : 0.0;
+}
+
+// locate the file owning global slot `slot` in a prefix table off[] (off[i] = first slot of file i,
+// file i owns [off_i, off_i + cap_i)); binary search over AfxFile entries
+__device__ __forceinline__ int find_file_by_frame(const AfxFile* __restrict__ files, int n_files, int slot)
+{
+  int lo = 0, hi = n_files - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (files[mid].frame_off <= slot) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+__device__ __forceinline__ int find_file_by_rframe(const AfxFile* __restrict__ files, int n_files, int slot)
+{
+  int lo = 0, hi = n_files - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (files[mid].rframe_off <= slot) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp / block reductions (all threads of the block must call; blockDim.x multiple of 32, <= 1024)
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// K simultaneous block-wide sums; scratch must hold K * 32 doubles.  Result broadcast to all threads.
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double* scratch)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();   // scratch may still be read from a previous call
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) scratch[k * 32 + wid] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double t = (lane < nw) ? scratch[k * 32 + lane] : 0.0;
+    v[k] = warp_sum(t);
+  }
+}
+__device__ __forceinline__ double block_max(double v, double* scratch)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  double t = (lane < nw) ? scratch[lane] : -1.0e308;
+  return warp_max(t);
+}
+__device__ __forceinline__ int block_sum_i(int v, int* scratch)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum_i(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  int t = (lane < nw) ? scratch[lane] : 0;
+  return warp_sum_i(t);
+}
+__device__ __forceinline__ int block_min_i(int v, int* scratch)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  int t = (lane < nw) ? scratch[lane] : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t = min(t, __shfl_xor_sync(0xffffffffu, t, o));
+  return t;
+}
+
+// TAudioMath::LinToDb(double), AudioTypes/Export/AudioMath.inl:55-70 (MEpsilon is a float literal)
+__device__ __forceinline__ double lin_to_db(double v)
+{
+  if (v == 1.0) return 0.0;
+  if (v > (double)1e-12f) return log(v) * (20.0 / 2.302585092994045684);
+  return -200.0;
+}
+// SFlatnessDb, SampleAnalyser.cpp:129-133, from a mean and a geometric mean
+__device__ __forceinline__ double flatness_db(double mean, double gmean)
+{
+  const double fl = (mean == 0.0) ? 0.0 : gmean / mean;
+  return fmin(lin_to_db(fl) / -60.0, 1.0);
+}
+
+// split a positive double into mantissa in [0.5, 1) and exponent, for overflow-free products
+__device__ __forceinline__ void mul_frexp(double& mant, int& ex, double v)
+{
+  int e;
+  mant *= frexp(v, &e);
+  ex += e;
+  if (mant < 0x1p-512) { mant *= 0x1p512; ex -= 512; }
+}
+
+// kernel launchers (one per translation unit); all asynchronous on `s`
+struct AfxBatchDev {
+  int n_files, TF, TFr;
+  const unsigned char* pcm;
+  float* mono;
+  float* mono_src;
+  const AfxFile* files;
+  AfxState* state;
+  double* mag;        // [TF][1024]
+  double* cent_full;  // [TF] centroid of mag[0..1023] (failsafe f0)
+  double* fs;         // [22][TF]
+  double* fsr;        // [2][TFr]
+  double* fv;         // 7 arrays [TF][nb], array v at fv + FV_x * TF
+  float* rpolar;      // [TFr][512]
+  float* rodf;        // [2][TFr] raw onset functions
+  double* stats;      // [n_files][136][13]
+  double* header;     // [n_files][32]
+  double* scratch;    // rhythm back-end workspace
+};
+
+struct RsBlock { double t0; int out0; int nout; long long in0; };   // in0: source index of X[0] (may be negative)
+struct AfxCondPlan {       // device arrays built by the host for one batch
+  const int* src_chunk_file; const int* src_chunk_start; int n_src_chunks;   // chunks over source frames
+  const int* dst_chunk_file; const int* dst_chunk_start; int n_dst_chunks;   // chunks over analysis-rate samples
+  const int* rs_chunk_file; const int* rs_chunk_start; int n_rs_chunks;      // same, resampled files only
+  const RsBlock* rs_blocks; const int* rs_blk_file; const double* rs_times; const long long* rs_time_off; int n_rs_blocks;
+};
+void afx_launch_condition_plan(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s, long long* launches);
+void afx_launch_materialise(const float* mono, const AfxState* st, double* out, int len, cudaStream_t s);
+void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, long long* launches);
+void afx_launch_peaks(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
+void afx_launch_bands(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
+void afx_launch_pitch(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
+void afx_launch_autocorr(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
+void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
+void afx_launch_stats(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);

@@ -1,0 +1,315 @@
+// K1: PCM conditioning -- the tail of TSampleAnalyser::LoadSample
+// (Source/Crawler/FeatureExtraction/Source/SampleAnalyser.cpp:531-719) for a whole batch.
+//
+//   k_downmix   : interleaved int16 / float32 -> float32 mono, (sum of channels) * (1/C) in float32
+//                 exactly as SA.cpp:535-548, fused with the peak / sum-of-squares reduction
+//                 (SA.cpp:612-631) for files that need no resampling
+//   k_resample  : libresample HQ restatement for files with src_rate != 44100 (SA.cpp:563-607)
+//   k_reduce    : peak / sum-of-squares for resampled files
+//   k_amp       : Amplification, FinalScaling (SA.cpp:630-637)
+//   k_trim      : first / last sample above the -48 dB floor (SA.cpp:648-669)
+//   k_layout    : lead / trail / padding / frame counts (SA.cpp:681-701, 760-764, 814, 991)
+//   k_eff       : effective length at -48 / -24 / -12 dB (SA.cpp:1715-1756)
+//   k_header    : file properties and scalar outputs (SA.cpp:734-754)
+//
+// All passes stream each sample once, coalesced; they are HBM-bound (bytes in DESIGN.md).
+#include "afx_common.cuh"
+#include "../../include/afec_b200.h"
+
+#define CHUNK 8192          // samples per CTA
+#define CT 256
+
+__device__ __forceinline__ float load_mono(const unsigned char* __restrict__ pcm, const AfxFile& f, int i)
+{
+  // SA.cpp:535-548: dst = ch0; dst += ch[c] (c = 1..C-1); dst *= 1.0f / C    -- all float32
+  const int C = f.channels;
+  float acc;
+  if (f.format == AFX_PCM_I16) {
+    const short* p = reinterpret_cast<const short*>(pcm + f.pcm_off) + (long long)i * C;
+    acc = (float)p[0];
+    for (int c = 1; c < C; ++c) acc = __fadd_rn(acc, (float)p[c]);
+  } else {
+    const float* p = reinterpret_cast<const float*>(pcm + f.pcm_off) + (long long)i * C;
+    acc = p[0];
+    for (int c = 1; c < C; ++c) acc = __fadd_rn(acc, p[c]);
+  }
+  if (C > 1) acc = __fmul_rn(acc, __fdiv_rn(1.0f, (float)C));
+  return acc;
+}
+
+__device__ __forceinline__ void reduce_peak_sumsq(float amax, double ssq, AfxState* st, double* scratch)
+{
+  double v[1] = { ssq };
+  block_sum<1>(v, scratch);
+  const double m = block_max((double)amax, scratch);
+  if (threadIdx.x == 0) {
+    atomicMax(&st->maxabs_bits, __float_as_uint((float)m));
+    atomicAdd(&st->sumsq, v[0]);
+  }
+}
+
+__global__ void __launch_bounds__(CT) k_downmix(AfxBatchDev B, const int* __restrict__ chunk_file,
+                                               const int* __restrict__ chunk_start, int analysis_rate)
+{
+  __shared__ double scratch[64];
+  const int fi = chunk_file[blockIdx.x];
+  const AfxFile f = B.files[fi];
+  if (f.status != 0) return;
+  const int start = chunk_start[blockIdx.x];
+  const int end = min(start + CHUNK, f.nframes_src);
+  const bool resampled = (f.src_rate != analysis_rate);
+  float* dst = resampled ? (B.mono_src + f.src_off) : (B.mono + f.mono_off);
+  float amax = 0.0f;
+  double ssq = 0.0;
+  for (int i = start + threadIdx.x; i < end; i += CT) {
+    const float v = load_mono(B.pcm, f, i);
+    dst[i] = v;
+    amax = fmaxf(amax, fabsf(v));
+    const double q = (double)(v / 32768.0f);
+    ssq += q * q;
+  }
+  if (!resampled) reduce_peak_sumsq(amax, ssq, B.state + fi, scratch);
+}
+
+// peak / sum of squares over the analysis-rate signal of resampled files (chunks over f.n)
+__global__ void __launch_bounds__(CT) k_reduce(AfxBatchDev B, const int* __restrict__ chunk_file,
+                                              const int* __restrict__ chunk_start)
+{
+  __shared__ double scratch[64];
+  const int fi = chunk_file[blockIdx.x];
+  const AfxFile f = B.files[fi];
+  if (f.status != 0) return;
+  const int start = chunk_start[blockIdx.x];
+  const int end = min(start + CHUNK, f.n);
+  const float* src = B.mono + f.mono_off;
+  float amax = 0.0f;
+  double ssq = 0.0;
+  for (int i = start + threadIdx.x; i < end; i += CT) {
+    const float v = src[i];
+    amax = fmaxf(amax, fabsf(v));
+    const double q = (double)(v / 32768.0f);
+    ssq += q * q;
+  }
+  reduce_peak_sumsq(amax, ssq, B.state + fi, scratch);
+}
+
+// ---- libresample HQ restatement (3rdParty/Resample/Dist/src) -------------------------------------
+// One thread per output sample.  The output-sample time stamps (a double accumulator advanced by
+// repeated "+= 1/factor" inside 4096-sample input blocks, resample.c:230-300 / resamplesubs.c:97-119)
+// are data independent; the host replays that recurrence once per distinct (rate, length) pair and
+// uploads, per block, the start time, the first output index and the input offset.  Inside a block a
+// thread reproduces its stamp by the same repeated additions in chunks of 64 from checkpoints.
+
+__global__ void __launch_bounds__(128) k_resample(AfxBatchDev B, AfxTables T, const RsBlock* __restrict__ blocks,
+                                                  const int* __restrict__ blk_file, const double* __restrict__ times,
+                                                  const long long* __restrict__ time_off, int n_blocks, int analysis_rate)
+{
+  const int bi = blockIdx.x;
+  if (bi >= n_blocks) return;
+  const RsBlock rb = blocks[bi];
+  const AfxFile f = B.files[blk_file[bi]];
+  const double factor = (double)analysis_rate / (double)f.src_rate;
+  const float* __restrict__ src = B.mono_src + f.src_off;
+  float* __restrict__ dst = B.mono + f.mono_off;
+  const float* __restrict__ imp = T.rs_imp;
+  const int nwing = 4096 * 34 / 2;
+  const int nsrc = f.nframes_src;
+  float lpscl = 1.0f;
+  if (factor < 1) lpscl = (float)((double)lpscl * factor);
+  double dh = factor * 4096.0; if (dh > 4096.0) dh = 4096.0;
+  const double* tt = times + time_off[bi];
+  for (int k = threadIdx.x; k < rb.nout; k += blockDim.x) {
+    const int o = rb.out0 + k;
+    if (o >= f.n) break;
+    const double t = tt[k];
+    const double fl = floor(t);
+    const double lph = t - fl, rph = 1.0 - lph;
+    const long long xi = rb.in0 + (long long)fl;   // source index of X[(int)t]
+    float v;
+    if (factor >= 1) {
+      // lrsFilterUp, filterkit.c:115-164, no coefficient interpolation
+      float vl = 0.0f, vr = 0.0f;
+      { double ph = lph * 4096.0; int h = (int)ph; long long x = xi;
+        while (h < nwing) { const float s = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vl = __fadd_rn(vl, __fmul_rn(imp[h], s)); h += 4096; x -= 1; } }
+      { double ph = rph * 4096.0; int h = (int)ph; long long x = xi + 1; const int end = nwing - 1;
+        if (ph == 0) h += 4096;
+        while (h < end) { const float s = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vr = __fadd_rn(vr, __fmul_rn(imp[h], s)); h += 4096; x += 1; } }
+      v = __fadd_rn(vl, vr);
+    } else {
+      // lrsFilterUD, filterkit.c:166-215
+      float vl = 0.0f, vr = 0.0f;
+      { double ho = lph * dh; long long x = xi;
+        while ((int)ho < nwing) { const float s = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vl = __fadd_rn(vl, __fmul_rn(imp[(int)ho], s)); ho += dh; x -= 1; } }
+      { double ho = rph * dh; long long x = xi + 1; const int end = nwing - 1;
+        if (rph == 0) ho += dh;
+        while ((int)ho < end) { const float s = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vr = __fadd_rn(vr, __fmul_rn(imp[(int)ho], s)); ho += dh; x += 1; } }
+      v = __fadd_rn(vl, vr);
+    }
+    dst[o] = __fmul_rn(v, lpscl);
+  }
+}
+
+// ---- Amplification / FinalScaling -------------------------------------------------------------
+__global__ void k_amp(AfxBatchDev B)
+{
+  const int fi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fi >= B.n_files) return;
+  AfxState* st = B.state + fi;
+  const double maxamp = (double)__uint_as_float(st->maxabs_bits);
+  const double amp = (maxamp > (double)1e-12f) ? 32768.0 / maxamp : 1.0;   // SA.cpp:636-637
+  st->amp = amp;
+  st->fs = amp / 32768.0;                                                  // SA.cpp:712
+}
+
+__global__ void __launch_bounds__(CT) k_trim(AfxBatchDev B, const int* __restrict__ chunk_file,
+                                            const int* __restrict__ chunk_start, double floor_amp)
+{
+  __shared__ int scratch[32];
+  const int fi = chunk_file[blockIdx.x];
+  const AfxFile f = B.files[fi];
+  if (f.status != 0) return;
+  const int start = chunk_start[blockIdx.x];
+  if (start >= f.n) return;
+  const int end = min(start + CHUNK, f.n);
+  const float* src = B.mono + f.mono_off;
+  const double amp = B.state[fi].amp;
+  int first = 0x7fffffff, last = -1;
+  for (int i = start + threadIdx.x; i < end; i += CT) {
+    if (fabs(amp * (double)src[i]) > floor_amp) { first = min(first, i); last = max(last, i); }
+  }
+  first = block_min_i(first, scratch);
+  last = -block_min_i(-last, scratch);
+  if (threadIdx.x == 0) {
+    if (first != 0x7fffffff) atomicMin(&B.state[fi].first, first);
+    if (last >= 0) atomicMax(&B.state[fi].last, last);
+  }
+}
+
+__global__ void k_layout(AfxBatchDev B, AfxParams P)
+{
+  const int fi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fi >= B.n_files) return;
+  const AfxFile f = B.files[fi];
+  AfxState* st = B.state + fi;
+  if (f.status != 0) { st->F = 0; st->Fr = 0; st->len = 0; st->audible = 0; return; }
+  const int n = f.n;
+  // SA.cpp:651-669: lead = first sample above the floor (n if none); the trailing scan stops at lead
+  const int first = st->first < n ? st->first : n;
+  const int lead = first;
+  int trail = 0;
+  if (lead < n) { const int last = st->last > lead ? st->last : lead; trail = n - 1 - last; }
+  const int audible = n - lead - trail;
+  int end_off = 0, start_off = 0;                                          // SA.cpp:685-696
+  if ((audible % P.N) < P.N / 2) end_off += P.N / 2;
+  if (audible + end_off < P.N) start_off = P.N - audible - end_off;
+  st->lead = lead; st->audible = audible; st->start_off = start_off;
+  st->len = audible + start_off + end_off;
+  st->data_offset = -lead + start_off;                                     // SA.cpp:701
+  const int L = st->len < P.analysis_cap ? st->len : P.analysis_cap;       // SA.cpp:760-764
+  st->L = L;
+  int F = (L >= P.N) ? (L - P.N) / P.H + 1 : 0;
+  int Fr = (L >= AFX_RFFT) ? (L - AFX_RFFT) / AFX_RHOP + 1 : 0;
+  if (F > f.frame_cap) F = f.frame_cap;      // cannot happen (caps are upper bounds); keeps writes in range
+  if (Fr > f.rframe_cap) Fr = f.rframe_cap;
+  st->F = F; st->Fr = Fr;
+  for (int k = 0; k < 3; ++k) { st->eff_first[k] = 0x7fffffff; st->eff_last[k] = -1; }
+}
+
+__global__ void __launch_bounds__(CT) k_eff(AfxBatchDev B, const int* __restrict__ chunk_file,
+                                           const int* __restrict__ chunk_start, AfxParams P)
+{
+  __shared__ int scratch[32];
+  const int fi = chunk_file[blockIdx.x];
+  const AfxFile f = B.files[fi];
+  if (f.status != 0) return;
+  const AfxState st = B.state[fi];
+  // chunk over the mono index space; only the audible region [lead, lead + audible) maps into mData
+  int start = chunk_start[blockIdx.x];
+  int end = min(start + CHUNK, f.n);
+  start = max(start, st.lead); end = min(end, st.lead + st.audible);
+  if (start >= end) return;      // uniform per block
+  const float* src = B.mono + f.mono_off;
+  int first[3] = { 0x7fffffff, 0x7fffffff, 0x7fffffff }, last[3] = { -1, -1, -1 };
+  for (int i = start + threadIdx.x; i < end; i += CT) {
+    const double v = fabs((double)src[i] * st.fs);
+    const int idx = i - st.lead + st.start_off;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) if (v > P.eff_floor[k]) { first[k] = min(first[k], idx); last[k] = max(last[k], idx); }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int a = block_min_i(first[k], scratch);
+    const int b = -block_min_i(-last[k], scratch);
+    if (threadIdx.x == 0) {
+      if (a != 0x7fffffff) atomicMin(&B.state[fi].eff_first[k], a);
+      if (b >= 0) atomicMax(&B.state[fi].eff_last[k], b);
+    }
+  }
+}
+
+// TAudioMath::SamplesToMs, AudioTypes/Export/AudioMath.inl:134-137 (float32 math)
+__device__ __forceinline__ float samples_to_ms(int sr, int samples)
+{
+  return __fdiv_rn((float)samples, __fdiv_rn((float)sr, 1000.0f));
+}
+
+__global__ void k_header(AfxBatchDev B, AfxParams P)
+{
+  const int fi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fi >= B.n_files) return;
+  const AfxFile f = B.files[fi];
+  const AfxState st = B.state[fi];
+  double* H = B.header + (size_t)fi * AFX_N_HEADER;
+  for (int k = 0; k < AFX_N_HEADER; ++k) H[k] = 0.0;
+  if (f.status != 0) return;
+  H[H_FILE_SIZE] = (double)f.file_size;
+  H[H_FILE_LENGTH] = (double)samples_to_ms(f.src_rate, f.nframes_src) / 1000.0;   // SA.cpp:741-742
+  H[H_FILE_RATE] = f.src_rate; H[H_FILE_CHANNELS] = f.channels; H[H_FILE_BITS] = f.bit_depth;
+  H[H_ANALYZATION_OFFSET] = (double)samples_to_ms(P.sr, st.data_offset) / 1000.0; // SA.cpp:748-749
+  for (int k = 0; k < 3; ++k) {                                                   // SA.cpp:1731-1754
+    const int len = st.len;
+    const int first = st.eff_first[k] < len ? st.eff_first[k] : len;
+    int trail = 0;
+    if (first < len) { const int last = st.eff_last[k] > first ? st.eff_last[k] : first; trail = len - 1 - last; }
+    H[H_EFF48 + k] = (double)samples_to_ms(P.sr, len - first - trail) / 1000.0;
+  }
+  const double maxamp = (double)__uint_as_float(st.maxabs_bits);
+  H[H_PEAK] = (double)(float)fmin(1.0, maxamp / 32768.0);                         // SA.cpp:634
+  H[H_RMS] = (double)(float)fmin(1.0, sqrt(st.sumsq / (double)f.n));              // SA.cpp:618-619
+  H[H_DATA_OFFSET] = st.data_offset; H[H_DATA_LEN] = st.len;
+}
+
+__global__ void k_state_init(AfxBatchDev B)
+{
+  const int fi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fi >= B.n_files) return;
+  AfxState* st = B.state + fi;
+  st->maxabs_bits = 0u; st->sumsq = 0.0; st->first = 0x7fffffff; st->last = -1;
+}
+
+// debug / parity: materialise mData of one file
+__global__ void k_materialise(const float* mono, const AfxState* st, double* out, int len)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) out[i] = mdata(mono, *st, i);
+}
+void afx_launch_materialise(const float* mono, const AfxState* st, double* out, int len, cudaStream_t s)
+{
+  k_materialise<<<(len + 255) / 256, 256, 0, s>>>(mono, st, out, len);
+}
+
+void afx_launch_condition_plan(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s, long long* launches)
+{
+  const int fb = (B.n_files + 127) / 128;
+  k_state_init<<<fb, 128, 0, s>>>(B); ++*launches;
+  if (C.n_src_chunks > 0) { k_downmix<<<C.n_src_chunks, CT, 0, s>>>(B, C.src_chunk_file, C.src_chunk_start, P.sr); ++*launches; }
+  if (C.n_rs_blocks > 0) {
+    k_resample<<<C.n_rs_blocks, 128, 0, s>>>(B, P.t, C.rs_blocks, C.rs_blk_file, C.rs_times, C.rs_time_off, C.n_rs_blocks, P.sr); ++*launches;
+    k_reduce<<<C.n_rs_chunks, CT, 0, s>>>(B, C.rs_chunk_file, C.rs_chunk_start); ++*launches;
+  }
+  k_amp<<<fb, 128, 0, s>>>(B); ++*launches;
+  if (C.n_dst_chunks > 0) { k_trim<<<C.n_dst_chunks, CT, 0, s>>>(B, C.dst_chunk_file, C.dst_chunk_start, P.silence_floor_amp); ++*launches; }
+  k_layout<<<fb, 128, 0, s>>>(B, P); ++*launches;
+  if (C.n_dst_chunks > 0) { k_eff<<<C.n_dst_chunks, CT, 0, s>>>(B, C.dst_chunk_file, C.dst_chunk_start, P); ++*launches; }
+  k_header<<<fb, 128, 0, s>>>(B, P); ++*launches;
+}

@@ -1,0 +1,146 @@
+/*
+ * afec_b200.h -- C ABI of libafec_b200.so, the B200 (sm_100a) implementation of AFEC's
+ * low-level descriptor hot path.
+ *
+ * What it replaces in the reference (emuell/AFEC), file:line relative to the reference root:
+ *   - the PCM conditioning tail of TSampleAnalyser::LoadSample
+ *       Source/Crawler/FeatureExtraction/Source/SampleAnalyser.cpp:531-719
+ *   - TSampleAnalyser::AnalyzeLowLevelDescriptors           SampleAnalyser.cpp:723-1066
+ *   - every Calc* helper it calls                            SampleAnalyser.cpp:1715-2412
+ *   - TStatistics::Calc for the per-file temporal statistics Statistics.cpp:12-90
+ * The caller keeps file decoding (TAudioFile / TAudioStream::ReadSamples) and the descriptor
+ * sink (TSampleDescriptorPool::InsertSample): it hands decoded PCM in, and gets the values of
+ * TSampleDescriptors' low-level members back (Export/SampleDescriptors.h:396-466).
+ *
+ * There is no CPU fallback: every entry point that computes fails with AFX_ERR_CUDA when no
+ * usable device is present.
+ *
+ * Plain C: pointers and sizes only.  All functions return AFX_OK (0) or a negative error code;
+ * afx_last_error() gives the message of the last failure on that context.
+ */
+#ifndef AFEC_B200_H_
+#define AFEC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFX_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------ */
+#define AFX_OK 0
+#define AFX_ERR_ARG (-1)        /* bad argument */
+#define AFX_ERR_CUDA (-2)       /* CUDA runtime failure / no device: the batch's files failed to analyse */
+#define AFX_ERR_NOMEM (-3)
+#define AFX_ERR_STATE (-4)      /* call sequence violated */
+
+/* per-file status (afx_file_result.status) -- mirrors the reference's load-time rejections,
+ * SampleAnalyser.cpp:472-482 */
+#define AFX_FILE_OK 0
+#define AFX_FILE_BAD_CHANNELS 1 /* "Unsupported audio file channel layout" (channels outside 1..8) */
+#define AFX_FILE_EMPTY 2        /* "Sample file is empty, probably failed to read." */
+
+/* ---- PCM formats -------------------------------------------------------------------------- */
+/* Both are INTERLEAVED frames.  I16 is converted as (float)value, F32 is taken as is: the
+ * reference's decoders hand LoadSample float32 in 16-bit range (+-32768),
+ * Source/Core/CoreFileFormats/Export/SampleConverter.h:446-449. */
+#define AFX_PCM_I16 0
+#define AFX_PCM_F32 1
+
+/* ---- feature groups (afx_config.features) --------------------------------------------- */
+#define AFX_FEAT_SPECTRAL (1u << 0)  /* window+FFT+magnitude, spectral rms/centroid/spread/skew/kurt/rolloff/flatness/flux */
+#define AFX_FEAT_AMPLITUDE (1u << 1) /* amplitude silence/peak/rms/envelope */
+#define AFX_FEAT_PEAKS (1u << 2)     /* whitening + peak spectrum -> spectral_complexity */
+#define AFX_FEAT_BANDS (1u << 3)     /* 14 sub-band features, spectral_contrast, 28 frequency bands, 14 cepstrum bands */
+#define AFX_FEAT_PITCH (1u << 4)     /* f0, f0_confidence, failsafe_f0 (YIN fast) */
+#define AFX_FEAT_AUTOCORR (1u << 5)  /* auto_correlation */
+#define AFX_FEAT_RHYTHM (1u << 6)    /* onset functions + rhythm scalars */
+#define AFX_FEAT_STATS (1u << 7)     /* 13 statistics per series */
+#define AFX_FEAT_ALL 0xFFu           /* the full low-level set (`Crawler --level low`) */
+
+typedef struct afx_ctx afx_ctx;
+typedef struct afx_batch afx_batch;
+
+typedef struct afx_config {
+  int32_t device;       /* CUDA device ordinal */
+  int32_t sample_rate;  /* TSampleAnalyser ctor args, Export/SampleAnalyser.h:33-36; Crawler.cpp:41-43 */
+  int32_t fft_size;     /*   only 44100 / 2048 are supported (the Crawler's compile-time values) */
+  int32_t hop_size;     /*   any hop with fft_size % hop == 0 (1024 default, 512 in BASELINE config 2) */
+  uint32_t features;    /* AFX_FEAT_* mask; AFX_FEAT_ALL for a drop-in afec-ll.db */
+  uint32_t reserved;
+} afx_config;
+
+/* one decoded file, as TSampleAnalyser::LoadSample sees it after ReadSamples (SampleAnalyser.cpp:484-528) */
+typedef struct afx_file {
+  const void* pcm;      /* interleaved frames; may be pageable or from afx_host_alloc (pinned) */
+  int64_t nframes;      /* sample frames per channel */
+  int32_t channels;
+  int32_t src_rate;     /* != sample_rate -> resampled like libresample HQ (SampleAnalyser.cpp:563-607) */
+  int32_t format;       /* AFX_PCM_* */
+  int32_t bit_depth;    /* file property only (file_bit_depth_R) */
+  int64_t file_size;    /* file property only (file_size_R) */
+} afx_file;
+
+/* number of entries of afx_file_result.header / series; order = Descriptors(kLowLevelDescriptors),
+ * SampleDescriptors.cpp:154-203.  Names are listed in afec_b200/layout.py and host/afx_names.h. */
+#define AFX_N_HEADER 32
+#define AFX_N_FS 24          /* framed scalars; the first AFX_N_FS_MAIN run on the main frame grid */
+#define AFX_N_FS_MAIN 22
+#define AFX_N_FV 7           /* framed vectors: 5 x 14 sub-bands, 28 frequency bands, 14 cepstrum bands */
+#define AFX_N_STATS 13
+#define AFX_N_SERIES 136     /* 24 + 5*14 + 28 + 14 */
+
+typedef struct afx_file_result {
+  int32_t status;            /* AFX_FILE_* */
+  int32_t n_frames;          /* F : main frames (fft_size / hop_size grid) */
+  int32_t n_rhythm_frames;   /* Fr: 512 / 128 grid */
+  int32_t reserved;
+  const double* header;      /* [AFX_N_HEADER] scalars */
+  const double* fs[AFX_N_FS];/* fs[s][frame]; s < 22 -> n_frames values, s = 22, 23 -> n_rhythm_frames */
+  const double* fv[AFX_N_FV];/* fv[v][frame * nbands(v) + band] */
+  const double* stats;       /* [AFX_N_SERIES][AFX_N_STATS] */
+} afx_file_result;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int afx_abi_version(void);
+int afx_create(const afx_config* cfg, afx_ctx** out);
+void afx_destroy(afx_ctx* ctx);
+const char* afx_last_error(const afx_ctx* ctx);   /* ctx may be NULL: last afx_create failure */
+
+/* pinned host memory for decode threads (ring slots); H2D copies from it are asynchronous */
+int afx_host_alloc(afx_ctx* ctx, uint64_t bytes, void** out);
+int afx_host_free(afx_ctx* ctx, void* p);
+
+/* ---- batches ------------------------------------------------------------------------------ */
+/* The stages may be called one by one (upload / compute / download are asynchronous on the
+ * context's stream), or all at once through afx_analyze().  PCM memory must stay valid until
+ * afx_batch_upload() has been followed by afx_batch_sync() (or afx_analyze() returned). */
+int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_files, afx_batch** out);
+int afx_batch_upload(afx_batch* b);     /* host -> device copies of the PCM + file table */
+int afx_batch_compute(afx_batch* b);    /* all kernels of the configured feature set */
+int afx_batch_download(afx_batch* b);   /* device -> pinned host copies of every result array */
+int afx_batch_sync(afx_batch* b);       /* wait for everything issued so far */
+int afx_analyze(afx_ctx* ctx, const afx_file* files, int32_t n_files, afx_batch** out); /* all of the above */
+int afx_batch_result(const afx_batch* b, int32_t file_index, afx_file_result* out);
+void afx_batch_free(afx_batch* b);
+
+/* ---- measurement helpers ---------------------------------------------------------------------- */
+/* device time (ms, CUDA events on the context's stream) of the last upload / compute / download */
+int afx_batch_timings(const afx_batch* b, float* upload_ms, float* compute_ms, float* download_ms);
+/* number of kernels launched by the last afx_batch_compute() and bytes moved by upload / download */
+int afx_batch_counters(const afx_batch* b, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes,
+                       int64_t* main_frames, int64_t* rhythm_frames);
+/* per-kernel device time of the last compute (only when the context was created with
+ * AFX_DEBUG_KERNEL_TIMES=1 in the environment); returns the number of entries written */
+int afx_batch_kernel_times(const afx_batch* b, const char** names, float* ms, int32_t cap);
+
+/* debugging / parity: copy the conditioned signal (the reference's TSampleData::mData,
+ * SampleAnalyser.cpp:698-718) of one file back to the host.  Returns its length. */
+int64_t afx_batch_conditioned(const afx_batch* b, int32_t file_index, double* out, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFEC_B200_H_ */

@@ -284,7 +284,7 @@ static float* rs_design(int nwing)
   double* c = (double*)malloc(sizeof(double) * nwing);
   const double frq = 0.5 * 0.90, beta = 6;
   c[0] = 2.0 * frq;
-  for (int i = 1; i < nwing; ++i) { const double t = kPi * (double)i / (double)RS_NPC; c[i] = sin(2.0 * t * frq) / t; }
+  for (int i = 1; i < nwing; ++i) { const double t = 3.14159265358979232846 /* resample_defs.h:30, sic */ * (double)i / (double)RS_NPC; c[i] = sin(2.0 * t * frq) / t; }
   const double ibeta = 1.0 / rs_izero(beta), inm1 = 1.0 / ((double)(nwing - 1));
   for (int i = 1; i < nwing; ++i) {
     const double t = (double)i * inm1; double t1 = 1.0 - t * t; t1 = (t1 < 0 ? 0 : t1);

@@ -1,0 +1,148 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference goldens.
+Run on the B200 box: python -m pytest tests -m gpu."""
+import numpy as np
+import pytest
+
+import golden_io
+import parity
+from afec_b200 import api, layout, synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = golden_io.load()
+
+SPECTRAL = ["spectral_rms", "spectral_centroid", "spectral_rolloff", "spectral_spread", "spectral_skewness",
+            "spectral_kurtosis", "spectral_flatness", "spectral_flux", "spectral_inharmonicity",
+            "tristimulus1", "tristimulus2", "tristimulus3"]
+AMPLITUDE = ["amplitude_silence", "amplitude_peak", "amplitude_rms", "amplitude_envelope"]
+GROUPS = {
+    api.FEAT_SPECTRAL: SPECTRAL,
+    api.FEAT_AMPLITUDE: AMPLITUDE,
+    api.FEAT_PEAKS: ["spectral_complexity"],
+    api.FEAT_BANDS: ["spectral_contrast", "spectral_rms_bands", "spectral_flatness_bands", "spectral_flux_bands",
+                     "spectral_complexity_bands", "spectral_contrast_bands", "frequency_bands", "cepstrum_bands"],
+    api.FEAT_PITCH: ["f0", "f0_confidence", "failsafe_f0"],
+    api.FEAT_AUTOCORR: ["auto_correlation"],
+    api.FEAT_RHYTHM: ["rhythm_complex_onsets", "rhythm_percussive_onsets"],
+}
+
+
+def implemented_features() -> int:
+    """Feature groups compiled into the library (all of them once the path is complete)."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", api.LIB_PATH], capture_output=True, text=True).stdout
+    feats = api.FEAT_SPECTRAL | api.FEAT_AMPLITUDE
+    for flag, sym in ((api.FEAT_PEAKS, "afx_launch_peaks"), (api.FEAT_BANDS, "afx_launch_bands"),
+                      (api.FEAT_PITCH, "afx_launch_pitch"), (api.FEAT_AUTOCORR, "afx_launch_autocorr"),
+                      (api.FEAT_RHYTHM, "afx_launch_rhythm"), (api.FEAT_STATS, "afx_launch_stats")):
+        if sym in out:
+            feats |= flag
+    return feats
+
+
+def series_for(features: int):
+    names = []
+    for flag, ns in GROUPS.items():
+        if features & flag:
+            names += ns
+    return names
+
+
+@pytest.fixture(scope="module")
+def feats():
+    return implemented_features()
+
+
+@pytest.fixture(scope="module")
+def analysers(feats):
+    cache = {}
+
+    def get(hop):
+        if hop not in cache:
+            cache[hop] = api.SampleAnalyser(44100, 2048, hop, features=feats)
+        return cache[hop]
+    yield get
+    for a in cache.values():
+        a.close()
+
+
+def check(got, want, feats, **kw):
+    full = (feats & api.FEAT_ALL) == api.FEAT_ALL
+    errs = parity.compare(got, want, only_series=None if full else series_for(feats),
+                          check_stats=full, check_header=full, **kw)
+    assert not errs, "\n".join(errs[:25])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_reference_vectors(analysers, feats, case):
+    """CUDA path vs vectors produced by the unmodified reference (tests/golden/make_golden.py)."""
+    if case["rate"] != 44100 and not hasattr(api, "HAVE_RESAMPLE"):
+        pytest.skip("resampler not built yet")
+    got = analysers(case["hop"]).analyze_pcm([case["pcm"]], [case["rate"]])[0]
+    check(got, case["ref"], feats)
+
+
+@pytest.mark.parametrize("hop", [1024, 512])
+def test_batch_vs_oracle(analysers, feats, oracle_lib, hop):
+    """A mixed batch (ragged lengths, stereo, tiny, silent) in ONE call vs the oracle file by file."""
+    pcms = [synth.one_shot(400 + i, 0.3 + 0.4 * i) for i in range(6)]
+    pcms.append(synth.one_shot(410, 0.9, channels=2))
+    pcms.append(synth.one_shot(411, 0.02))
+    pcms.append(np.zeros(30000, dtype=np.int16))
+    pcms.append(synth.one_shot(412, 21.5))                 # crosses the 20 s cap
+    pcms.append(synth.one_shot(413, 0.7, channels=5).astype(np.float32))   # float32 input path
+    rates = [44100] * len(pcms)
+    got = analysers(hop).analyze_pcm(pcms, rates)
+    for g, p in zip(got, pcms):
+        want = oracle_lib.analyze(p, hop=hop, file_size=44 + p.size * p.itemsize)
+        check(g, want, feats)
+
+
+def test_conditioning_bit_exact(analysers, oracle_lib):
+    """mData (SampleAnalyser.cpp:698-718) must be bit-identical: integer trim / pad + one multiply."""
+    pcms = [synth.one_shot(500 + i, 0.2 + 0.3 * i, channels=1 + (i % 3)) for i in range(5)]
+    pcms.append(np.zeros(5000, dtype=np.int16))
+    an = analysers(1024)
+    b = an.batch(pcms, [44100] * len(pcms)).run()
+    for i, p in enumerate(pcms):
+        data, off, pk, rms = oracle_lib.condition(p)
+        got = b.conditioned(i)
+        assert got.shape == data.shape
+        assert np.array_equal(got, data)
+        r = b.result(i)
+        assert r.header[layout.HEADER_NAMES.index("data_offset")] == off
+        assert r.header[layout.HEADER_NAMES.index("peak_value")] == pk
+        assert abs(r.header[layout.HEADER_NAMES.index("rms_value")] - rms) <= 1e-6 * max(rms, 1e-9)
+    b.free()
+
+
+def test_rejected_files_do_not_poison_batch(analysers, feats, oracle_lib):
+    """SampleAnalyser.cpp:472-482: bad channel count / empty file fail alone; neighbours still analyse."""
+    good = synth.one_shot(600, 0.5)
+    pcms = [good, np.zeros((100, 9), dtype=np.int16), np.zeros((0,), dtype=np.int16), good]
+    got = analysers(1024).analyze_pcm(pcms, [44100] * 4)
+    assert got[1].status == 1 and got[2].status == 2
+    want = oracle_lib.analyze(good, file_size=44 + good.size * 2)
+    check(got[0], want, feats)
+    check(got[3], want, feats)
+
+
+def test_empty_batch(analysers):
+    assert analysers(1024).analyze_pcm([], []) == []
+
+
+def test_large_batch_properties(analysers, feats):
+    """Size-independent properties at bench scale: identical files give identical rows; results do not
+    depend on batch composition or order."""
+    base = [synth.one_shot(700 + i, 1.0 + 0.1 * i) for i in range(8)]
+    pcms = [base[i % 8] for i in range(512)]
+    an = analysers(512)
+    got = an.analyze_pcm(pcms, [44100] * len(pcms))
+    solo = an.analyze_pcm(base, [44100] * 8)
+    for i, g in enumerate(got):
+        s = solo[i % 8]
+        assert (g.F, g.Fr) == (s.F, s.Fr)
+        for a, b in zip(g.fs, s.fs):
+            assert np.array_equal(a, b)
+        for a, b in zip(g.fv, s.fv):
+            assert np.array_equal(a, b)
