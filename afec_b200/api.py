@@ -23,7 +23,7 @@ EXPORTS = [
     "afx_abi_version", "afx_create", "afx_destroy", "afx_last_error", "afx_host_alloc", "afx_host_free",
     "afx_batch_create", "afx_batch_upload", "afx_batch_compute", "afx_batch_download", "afx_batch_sync",
     "afx_analyze", "afx_batch_result", "afx_batch_free", "afx_batch_timings", "afx_batch_counters",
-    "afx_batch_kernel_times", "afx_batch_conditioned",
+    "afx_batch_kernel_times", "afx_batch_conditioned", "afx_measure_fp64_peak",
 ]
 
 
@@ -80,6 +80,7 @@ def load_library():
     L.afx_batch_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int32]
     L.afx_batch_conditioned.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     L.afx_batch_conditioned.restype = C.c_int64
+    L.afx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -247,6 +248,11 @@ class SampleAnalyser:
         out = [b.result(i) for i in range(b.n_files)]
         b.free()
         return out
+
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double()
+        self._check(self._L.afx_measure_fp64_peak(self._ctx, C.byref(v)))
+        return v.value
 
     def pinned(self, nbytes: int) -> PinnedArena:
         return PinnedArena(self, nbytes)

@@ -669,3 +669,40 @@ extern "C" int64_t afx_batch_conditioned(const afx_batch* b, int32_t i, double* 
   cudaFree(d);
   return st.len;
 }
+
+// ---- FP64 FMA peak (roofline denominator) -----------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters)
+{
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+
+extern "C" int afx_measure_fp64_peak(afx_ctx* ctx, double* tflops)
+{
+  if (!ctx || !tflops) return AFX_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device), "cudaGetDeviceProperties");
+  double* d = nullptr;
+  CK(cudaMalloc(&d, 8), "cudaMalloc");
+  const int blocks = prop.multiProcessorCount * 8, iters = 20000;
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(a, ctx->stream);
+    k_fp64_peak<<<blocks, 256, 0, ctx->stream>>>(d, iters);
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    const double fl = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+    if (rep > 0 && ms > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+  *tflops = best;
+  return AFX_OK;
+}

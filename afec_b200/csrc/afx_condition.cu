@@ -300,6 +300,7 @@ void afx_launch_materialise(const float* mono, const AfxState* st, double* out, 
 
 void afx_launch_condition_plan(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s, long long* launches)
 {
+  if (B.n_files <= 0) return;
   const int fb = (B.n_files + 127) / 128;
   k_state_init<<<fb, 128, 0, s>>>(B); ++*launches;
   if (C.n_src_chunks > 0) { k_downmix<<<C.n_src_chunks, CT, 0, s>>>(B, C.src_chunk_file, C.src_chunk_start, P.sr); ++*launches; }

@@ -136,6 +136,10 @@ int afx_batch_counters(const afx_batch* b, int64_t* kernel_launches, int64_t* h2
  * AFX_DEBUG_KERNEL_TIMES=1 in the environment); returns the number of entries written */
 int afx_batch_kernel_times(const afx_batch* b, const char** names, float* ms, int32_t cap);
 
+/* measured FP64 FMA throughput of the device (TFLOP/s), the denominator of the compute roofline
+ * (MEASURED_PEAKS.json only holds HBM and bf16 tensor peaks) */
+int afx_measure_fp64_peak(afx_ctx* ctx, double* tflops);
+
 /* debugging / parity: copy the conditioned signal (the reference's TSampleData::mData,
  * SampleAnalyser.cpp:698-718) of one file back to the host.  Returns its length. */
 int64_t afx_batch_conditioned(const afx_batch* b, int32_t file_index, double* out, int64_t cap);
