@@ -1,0 +1,137 @@
+// K5: per-file temporal aggregation -- TStatistics::Calc (Statistics.cpp:12-90) over each of the 136
+// series of a file (24 framed scalars, 5 x 14 sub-band series, 28 frequency bands, 14 cepstrum bands;
+// SampleAnalyser.cpp:2402-2412, SampleDescriptors.h:212-230, 327-355).
+//
+// A segmented reduction: one warp per (file, series); the series are segments of the batch-wide
+// descriptor arrays (frame_off / rframe_off give the segment start, F / Fr its length).  Thirteen
+// statistics per segment: min, max, lower median (Statistics.cpp:316-413, here an 8-pass MSD radix
+// select on order-preserving 64-bit keys), mean, geometric mean, variance (/n), the reference's
+// index-weighted centroid / spread, its "value minus centroid over spread" skewness / kurtosis,
+// flatness = gmean / mean, and mean / variance of |x[i+1] - x[i]|.
+#include "afx_common.cuh"
+#include "../../include/afec_b200.h"
+
+#define SW 8            // warps per CTA
+
+__device__ __forceinline__ unsigned long long order_key(double x)
+{
+  const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_to_double(unsigned long long k)
+{
+  const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+
+__global__ void __launch_bounds__(SW * 32) k_stats(AfxBatchDev B, AfxParams P)
+{
+  __shared__ int hist[SW][256];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * SW + wid;
+  const int fi = (int)(gw / AFX_N_SERIES), s = (int)(gw % AFX_N_SERIES);
+  if (fi >= B.n_files) return;
+  const AfxFile f = B.files[fi];
+  double* out = B.stats + ((size_t)fi * AFX_N_SERIES + s) * AFX_N_STATS;
+  if (f.status != 0) { if (lane < AFX_N_STATS) out[lane] = 0.0; return; }
+  const AfxState* st = B.state + fi;
+  const size_t TF = (size_t)B.TF;
+  const double* x; int n, stride;
+  if (s < AFX_N_FS_MAIN) { x = B.fs + (size_t)s * TF + f.frame_off; n = st->F; stride = 1; }
+  else if (s < AFX_N_FS) { x = B.fsr + (size_t)(s - AFX_N_FS_MAIN) * B.TFr + f.rframe_off; n = st->Fr; stride = 1; }
+  else {
+    int b = s - AFX_N_FS, off, nb;
+    if (b < 70) { off = (b / 14) * 14; nb = 14; b = b % 14; }
+    else if (b < 98) { off = FV_BANDS28; nb = 28; b -= 70; }
+    else { off = FV_CEPSTRUM; nb = 14; b -= 98; }
+    x = B.fv + (size_t)off * TF + (size_t)f.frame_off * nb + b; n = st->F; stride = nb;
+  }
+  double r[AFX_N_STATS];
+#pragma unroll
+  for (int k = 0; k < AFX_N_STATS; ++k) r[k] = 0.0;
+  if (n == 1) { const double v = x[0]; r[0] = v; r[1] = v; r[3] = v; }
+  if (n > 1) {
+    // ---- pass 1 -------------------------------------------------------------------------------------
+    double sum = 0, sj = 0, sd = 0, mn = 1.0e308, mx = -1.0e308, mant = 1.0; int ex = 0;
+    for (int i = lane; i < n; i += 32) {
+      const double v = x[(size_t)i * stride];
+      sum += v; sj += (double)i * v; mn = fmin(mn, v); mx = fmax(mx, v);
+      mul_frexp(mant, ex, fabs(v) + 1e-20);
+      if (i + 1 < n) sd += fabs(x[(size_t)(i + 1) * stride] - v);
+    }
+    double ls = log(mant) + (double)ex * 0.693147180559945309417;
+    sum = warp_sum(sum); sj = warp_sum(sj); sd = warp_sum(sd); ls = warp_sum(ls);
+    mn = -warp_max(-mn); mx = warp_max(mx);
+    const double dn = (double)n;
+    const double mean = sum / dn;
+    const double gmean = exp(ls / dn);
+    const double cen = (sum == 0.0) ? 0.0 : sj / sum;
+    const double dmean = (n > 2) ? sd / (double)(n - 1) : 0.0;
+    // ---- pass 2 -------------------------------------------------------------------------------------
+    double var = 0, sp = 0, dvar = 0;
+    for (int i = lane; i < n; i += 32) {
+      const double v = x[(size_t)i * stride];
+      var += (v - mean) * (v - mean);
+      const double d = (double)i - cen; sp += d * d * v;
+      if (n > 2 && i + 1 < n) { const double q = fabs(x[(size_t)(i + 1) * stride] - v) - dmean; dvar += q * q; }
+    }
+    var = warp_sum(var); sp = warp_sum(sp); dvar = warp_sum(dvar);
+    const double spread = (sum == 0.0) ? 0.0 : sp / sum;
+    // ---- pass 3 -------------------------------------------------------------------------------------
+    double sk = 0, ku = 0;
+    const bool have = fabs(spread) > (double)1e-12f;
+    if (have) for (int i = lane; i < n; i += 32) {
+      const double d = (x[(size_t)i * stride] - cen) / spread; const double d2 = d * d;
+      sk += d2 * d; ku += d2 * d2;
+    }
+    sk = warp_sum(sk); ku = warp_sum(ku);
+    // ---- lower median: MSD radix select of rank (n-1)/2 ------------------------------------------------
+    unsigned long long prefix = 0ull, pmask = 0ull;
+    int k = (n - 1) / 2;
+    int* h = hist[wid];
+    for (int byte = 7; byte >= 0; --byte) {
+      for (int q = lane; q < 256; q += 32) h[q] = 0;
+      __syncwarp();
+      const int sh = byte * 8;
+      for (int i = lane; i < n; i += 32) {
+        const unsigned long long key = order_key(x[(size_t)i * stride]);
+        if ((key & pmask) == prefix) atomicAdd(&h[(int)((key >> sh) & 0xff)], 1);
+      }
+      __syncwarp();
+      // each lane owns 8 consecutive buckets
+      int c[8]; int tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { c[q] = h[lane * 8 + q]; tot += c[q]; }
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int pv = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += pv; }
+      const int excl = inc - tot;
+      int digit = -1, newk = 0;
+      if (k >= excl && k < inc) {
+        int run = excl;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { if (digit < 0 && k < run + c[q]) { digit = lane * 8 + q; newk = k - run; } run += c[q]; }
+      }
+      const unsigned ball = __ballot_sync(0xffffffffu, digit >= 0);
+      const int src = __ffs(ball) - 1;
+      digit = __shfl_sync(0xffffffffu, digit, src); newk = __shfl_sync(0xffffffffu, newk, src);
+      prefix |= ((unsigned long long)digit) << sh; pmask |= 0xffull << sh; k = newk;
+      __syncwarp();
+    }
+    r[0] = mn; r[1] = mx; r[2] = key_to_double(prefix); r[3] = mean; r[4] = gmean; r[5] = var / dn;
+    r[6] = cen; r[7] = spread; r[8] = have ? sk / dn : 0.0; r[9] = have ? ku / dn - 3.0 : 0.0;
+    r[10] = (mean == 0.0) ? 0.0 : gmean / mean;
+    r[11] = dmean; r[12] = (n > 2) ? dvar / (double)(n - 1) : 0.0;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < AFX_N_STATS; ++q) out[q] = r[q];
+  }
+}
+
+void afx_launch_stats(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
+{
+  if (B.n_files <= 0) return;
+  const long long warps = (long long)B.n_files * AFX_N_SERIES;
+  k_stats<<<(unsigned)((warps + SW - 1) / SW), SW * 32, 0, s>>>(B, P); ++*launches;
+}

@@ -67,10 +67,10 @@ def compare(got: layout.FileResult, want: layout.FileResult, skip_series=(), onl
             idx = np.argwhere(bad)[0]
             errs.append("%s: %d/%d values differ, first at %s: %r != %r" % (
                 n, nb, bad.size, idx.tolist(), a[tuple(idx)], b[tuple(idx)]))
-    if check_stats and only_series is None:
+    if check_stats:
         for si, (n, x) in enumerate(_series_iter(want)):
             base = n.split("[")[0]
-            if base in skip_series:
+            if base in skip_series or (only_series is not None and base not in only_series):
                 continue
             a, b = got.stats[si], want.stats[si]
             ok = close(a, b)
