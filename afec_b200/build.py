@@ -44,8 +44,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src = os.path.join(CSRC, s)
         obj = os.path.join(CSRC, s[:-3] + ".o")
         objs.append(obj)
-        if force or _stale(obj, [src] + headers):
-            jobs.append([NVCC] + ARCH + FLAGS + defs + ["-c", src, "-o", obj])
+        cmd = [NVCC] + ARCH + FLAGS + defs + ["-c", src, "-o", obj]
+        stamp = obj + ".cmd"
+        old = open(stamp).read() if os.path.exists(stamp) else ""
+        if force or _stale(obj, [src] + headers) or old != " ".join(cmd):
+            jobs.append(cmd)
+            with open(stamp, "w") as f:
+                f.write(" ".join(cmd))
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
