@@ -18,6 +18,7 @@ AFX_PCM_I16, AFX_PCM_F32 = 0, 1
 FEAT_SPECTRAL, FEAT_AMPLITUDE, FEAT_PEAKS, FEAT_BANDS = 1, 2, 4, 8
 FEAT_PITCH, FEAT_AUTOCORR, FEAT_RHYTHM, FEAT_STATS = 16, 32, 64, 128
 FEAT_ALL = 0xFF
+HAVE_RESAMPLE = True   # k_resample + host block plan (libresample HQ restatement)
 
 EXPORTS = [
     "afx_abi_version", "afx_create", "afx_destroy", "afx_last_error", "afx_host_alloc", "afx_host_free",

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -46,14 +47,23 @@ struct PinBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// data-independent replay of libresample's block / time bookkeeping for one (rate, length) pair
+struct RsShape {
+  std::vector<RsBlock> blocks;   // chk_off relative to chk
+  std::vector<double> chk;       // every 64th output time stamp of each block
+  int produced = 0;              // output samples libresample delivers (<= the requested count)
+};
+
 struct afx_ctx {
   afx_config cfg;
   int device = 0;
   cudaStream_t stream = nullptr;
   AfxParams P;
   DevBuf tables;                      // all constant tables in one allocation
-  DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf,
+  DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf, d_rpost,
          d_stats, d_header, d_plan, d_scratch;
+  std::map<std::pair<int, int>, std::shared_ptr<RsShape>> rs_cache;
+  long long group_frames = 393216, group_rframes = 3145728;   // per-launch scratch bound: 3 GB mag, 6 GB rpolar
   PinBuf h_results_cache, h_plan_cache;   // recycled between batches
   std::vector<double> zeros;          // backing store of the all-zero series
   std::string error;
@@ -72,6 +82,11 @@ struct afx_batch {
   std::vector<AfxState> state_host;
   // plan
   std::vector<int> src_chunk_file, src_chunk_start, dst_chunk_file, dst_chunk_start, rs_chunk_file, rs_chunk_start;
+  std::vector<RsBlock> rs_blocks; std::vector<int> rs_blk_file; std::vector<double> rs_chk;
+  struct Tail { long long off; long long count; }; std::vector<Tail> rs_tails;   // mono samples libresample never writes
+  struct Group { int file0, nfiles, slot0, nslots, rslot0, nrslots; };
+  std::vector<Group> groups;
+  int max_gslots = 0, max_grslots = 0, max_fr = 0;
   struct CopyRun { const unsigned char* host; size_t dev_off; size_t bytes; };
   std::vector<CopyRun> runs;
   size_t pcm_bytes = 0; long long mono_samples = 0, mono_src_samples = 0;
@@ -153,6 +168,49 @@ static void build_rs_wing(std::vector<float>& imp)
   for (int i = 0; i < nwing; ++i) imp[i] = (float)c[i];
 }
 
+// resample.c:80-164 (open, high quality) + :170-337 (process, lastFlag = 1) + resamplesubs.c:30-123: the
+// block structure and the time accumulator do not depend on the samples, so they are replayed here once per
+// (source rate, length) and the filter sums run on the GPU (k_resample).
+static std::shared_ptr<RsShape> rs_plan(int in_len, int src_rate, int sr, int out_len)
+{
+  auto sh = std::make_shared<RsShape>();
+  const double speed = (double)src_rate / (double)sr, factor = 1.0 / speed;
+  const int nmult = 35;
+  const double inv = 1.0 / factor;
+  const unsigned xoff = (unsigned)(((nmult + 1) / 2.0) * (inv > 1.0 ? inv : 1.0) + 10);
+  const unsigned xsize = (2 * xoff + 10 > 4096) ? 2 * xoff + 10 : 4096;
+  unsigned xread = xoff;
+  double time = (double)xoff;
+  const double dt = 1.0 / factor;
+  int used = 0, outc = 0;
+  long long in0 = -(long long)xoff;
+  for (;;) {
+    int len = (int)(xsize - xread);
+    if (len >= in_len - used) len = in_len - used;
+    used += len; xread += len;
+    const int nx = (used == in_len) ? (int)(xread - xoff) : (int)(xread - 2 * xoff);
+    if (nx <= 0) break;
+    RsBlock rb; rb.out0 = outc; rb.in0 = in0; rb.chk_off = (long long)sh->chk.size();
+    int nout = 0;
+    double t = time; const double end_time = t + nx;
+    while (t < end_time) { if ((nout & 63) == 0) sh->chk.push_back(t); ++nout; t += dt; }
+    time = t;
+    time -= nx; unsigned xp = xoff + nx;
+    const unsigned ncreep = (unsigned)((int)time - (int)xoff);
+    if (ncreep) { time -= ncreep; xp += ncreep; }
+    const unsigned shift = xp - xoff;
+    const unsigned nreuse = xread - shift;
+    int ncopy = out_len - outc; if (ncopy > nout) ncopy = nout;
+    rb.nout = ncopy;
+    if (ncopy > 0) sh->blocks.push_back(rb);
+    outc += ncopy;
+    in0 += shift; xread = nreuse;
+    if (ncopy < nout) break;
+  }
+  sh->produced = outc;
+  return sh;
+}
+
 extern "C" int afx_abi_version(void) { return AFX_ABI_VERSION; }
 
 extern "C" const char* afx_last_error(const afx_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
@@ -216,6 +274,14 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   P.analysis_cap = ms_to_samples(sr, 1000 * 20);                             // SA.cpp:37, 760-761
   P.ac_min_period = ms_to_samples(sr, 0.8f); P.ac_width = ms_to_samples(sr, 12.0f);   // SA.cpp:2318-2324
 
+  // rhythm constants: OnsetDetector.cpp:106-111 (relax 25 s), :296, :318 (normalisation), CannyWindow.cpp:27-48
+  P.r_relax = (float)(std::exp((-2.30258509 * (float)AFX_RHOP) / (25.0f * (float)sr)));
+  P.r_norm_power = 2560.f / (float)((AFX_RBINS + 2) * AFX_RFFT);
+  P.r_norm_complex = (float)(231.70475 / std::pow((double)AFX_RFFT, 1.5));
+  for (int i = -12; i < 13; ++i) P.canny[i + 12] = (double)i / (16.0 * 16.0) * std::exp(-1.0 * (i * i) / (2.0 * 16.0 * 16.0));
+  if (getenv("AFX_GROUP_FRAMES")) ctx->group_frames = std::max(1LL, atoll(getenv("AFX_GROUP_FRAMES")));
+  if (getenv("AFX_GROUP_RFRAMES")) ctx->group_rframes = std::max(1LL, atoll(getenv("AFX_GROUP_RFRAMES")));
+
   // ---- constant tables ----
   std::vector<double> window(N), rwindow(AFX_RFFT), mel, dct(14 * 14);
   std::vector<double> tw2048(2 * 2048), tw512(2 * 512);
@@ -261,7 +327,7 @@ extern "C" void afx_destroy(afx_ctx* ctx)
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   DevBuf* bufs[] = { &ctx->tables, &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
-    &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch };
+    &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch };
   for (DevBuf* b : bufs) b->release();
   ctx->h_results_cache.release(); ctx->h_plan_cache.release();
   delete ctx;
@@ -293,6 +359,14 @@ extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_f
   b->files.resize(n_files);
   size_t pcm_off = 0; long long mono_off = 0, src_off = 0; long long tf = 0, tfr = 0;
   const unsigned char* run_end = nullptr;
+  std::map<const RsShape*, long long> shape_pool;     // shape -> offset of its checkpoints in rs_chk
+  afx_batch::Group g = { 0, 0, 0, 0, 0, 0 };
+  auto close_group = [&]() {
+    if (g.nfiles > 0) {
+      b->groups.push_back(g);
+      b->max_gslots = std::max(b->max_gslots, g.nslots); b->max_grslots = std::max(b->max_grslots, g.nrslots);
+    }
+  };
   for (int i = 0; i < n_files; ++i) {
     const afx_file& f = files[i];
     AfxFile& d = b->files[i];
@@ -305,7 +379,7 @@ extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_f
       delete b; return fail(ctx, AFX_ERR_ARG, "afx_batch_create: unsupported file description");
     }
     d.frame_off = (int)tf; d.rframe_off = (int)tfr; d.mono_off = mono_off; d.src_off = src_off; d.pcm_off = (long long)pcm_off;
-    if (d.status != AFX_FILE_OK) continue;
+    if (d.status != AFX_FILE_OK) { if (g.nfiles > 0) ++g.nfiles; else { g.file0 = i; g.nfiles = 1; g.slot0 = (int)tf; g.rslot0 = (int)tfr; } continue; }
     d.nframes_src = (int)f.nframes;
     const double speed = (double)f.src_rate / (double)P.sr;                            // SA.cpp:563-573
     d.n = d.nframes_src;
@@ -315,6 +389,13 @@ extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_f
     if (lmax > P.analysis_cap) lmax = P.analysis_cap;
     d.frame_cap = (int)((lmax - P.N) / P.H + 1);
     d.rframe_cap = (int)((lmax - AFX_RFFT) / AFX_RHOP + 1);
+    if (g.nfiles > 0 && (g.nslots + d.frame_cap > ctx->group_frames || g.nrslots + d.rframe_cap > ctx->group_rframes)) {
+      close_group();
+      g.nfiles = 0;
+    }
+    if (g.nfiles == 0) { g.file0 = i; g.slot0 = (int)tf; g.rslot0 = (int)tfr; g.nslots = 0; g.nrslots = 0; }
+    ++g.nfiles; g.nslots += d.frame_cap; g.nrslots += d.rframe_cap;
+    b->max_fr = std::max(b->max_fr, d.rframe_cap);
     tf += d.frame_cap; tfr += d.rframe_cap;
     // PCM packing: keep host-contiguous files contiguous on the device so they move in one copy
     const size_t bps = (f.format == AFX_PCM_I16) ? 2 : 4;
@@ -330,7 +411,27 @@ extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_f
     pcm_off += bytes; run_end = hp + bytes;
     mono_off += ((long long)d.n + 3) & ~3LL;
     d.mono_off = mono_off - (((long long)d.n + 3) & ~3LL);
-    if (speed != 1.0) { d.src_off = src_off; src_off += ((long long)d.nframes_src + 3) & ~3LL; }
+    if (speed != 1.0) {
+      d.src_off = src_off; src_off += ((long long)d.nframes_src + 3) & ~3LL;
+      std::shared_ptr<RsShape> sh;
+      {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto key = std::make_pair(f.src_rate, d.nframes_src);
+        auto it = ctx->rs_cache.find(key);
+        if (it == ctx->rs_cache.end()) {
+          if (ctx->rs_cache.size() > 256) ctx->rs_cache.clear();
+          it = ctx->rs_cache.emplace(key, rs_plan(d.nframes_src, f.src_rate, P.sr, d.n)).first;
+        }
+        sh = it->second;
+      }
+      auto pit = shape_pool.find(sh.get());
+      if (pit == shape_pool.end()) {
+        pit = shape_pool.emplace(sh.get(), (long long)b->rs_chk.size()).first;
+        b->rs_chk.insert(b->rs_chk.end(), sh->chk.begin(), sh->chk.end());
+      }
+      for (RsBlock rb : sh->blocks) { rb.chk_off += pit->second; b->rs_blocks.push_back(rb); b->rs_blk_file.push_back(i); }
+      if (sh->produced < d.n) b->rs_tails.push_back({ d.mono_off + sh->produced, (long long)d.n - sh->produced });
+    }
     for (int s = 0; s < d.nframes_src; s += CHUNK) { b->src_chunk_file.push_back(i); b->src_chunk_start.push_back(s); }
     for (int s = 0; s < d.n; s += CHUNK) {
       b->dst_chunk_file.push_back(i); b->dst_chunk_start.push_back(s);
@@ -338,6 +439,7 @@ extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_f
     }
     if (tf > 0x7fffffffLL || tfr > 0x7fffffffLL) { delete b; return fail(ctx, AFX_ERR_ARG, "afx_batch_create: batch too large (frame slots overflow int32)"); }
   }
+  close_group();
   b->pcm_bytes = pcm_off; b->mono_samples = mono_off; b->mono_src_samples = src_off;
   b->TF = (int)tf; b->TFr = (int)tfr;
 
@@ -382,15 +484,17 @@ extern "C" int afx_batch_upload(afx_batch* b)
   if (b->mono_src_samples) CK(ctx->d_mono_src.reserve((size_t)(b->mono_src_samples + 8) * 4), "cudaMalloc(mono_src)");
   CK(ctx->d_files.reserve((size_t)(n + 1) * sizeof(AfxFile)), "cudaMalloc(files)");
   CK(ctx->d_state.reserve((size_t)(n + 1) * sizeof(AfxState)), "cudaMalloc(state)");
-  CK(ctx->d_mag.reserve((TF + 1) * AFX_NBIN * 8), "cudaMalloc(mag)");
+  const size_t GS = (size_t)b->max_gslots, GR = (size_t)b->max_grslots;
+  CK(ctx->d_mag.reserve((GS + 1) * AFX_NBIN * 8), "cudaMalloc(mag)");
   CK(ctx->d_cent.reserve((TF + 1) * 8), "cudaMalloc(cent)");
   CK(ctx->d_fs.reserve((TF + 1) * AFX_N_FS_MAIN * 8), "cudaMalloc(fs)");
   CK(ctx->d_fsr.reserve((TFr + 1) * 2 * 8), "cudaMalloc(fsr)");
   if (feat & AFX_FEAT_BANDS) CK(ctx->d_fv.reserve((TF + 1) * AFX_FV_STRIDE * 8), "cudaMalloc(fv)");
   if (feat & AFX_FEAT_RHYTHM) {
-    CK(ctx->d_rpolar.reserve((TFr + 1) * AFX_RROW * 4), "cudaMalloc(rpolar)");
+    CK(ctx->d_rpolar.reserve((GR + 1) * AFX_RROW * 4), "cudaMalloc(rpolar)");
     CK(ctx->d_rodf.reserve((TFr + 1) * 2 * 4), "cudaMalloc(rodf)");
-    CK(ctx->d_scratch.reserve((TFr + 1) * 2 * 2 * 8 + 1024), "cudaMalloc(scratch)");
+    CK(ctx->d_rpost.reserve((TFr + 1) * 2 * 4), "cudaMalloc(rpost)");
+    CK(ctx->d_scratch.reserve((GR + 1) * 4 * 8 + 1024), "cudaMalloc(scratch)");
   }
   CK(ctx->d_stats.reserve((size_t)(n + 1) * AFX_N_SERIES * AFX_N_STATS * 8), "cudaMalloc(stats)");
   CK(ctx->d_header.reserve((size_t)(n + 1) * AFX_N_HEADER * 8), "cudaMalloc(header)");
@@ -402,6 +506,8 @@ extern "C" int afx_batch_upload(afx_batch* b)
   const size_t p_files = place((size_t)n * sizeof(AfxFile));
   const size_t p_scf = place(nsc * 4), p_scs = place(nsc * 4), p_dcf = place(ndc * 4), p_dcs = place(ndc * 4),
     p_rcf = place(nrc * 4), p_rcs = place(nrc * 4);
+  const size_t nrb = b->rs_blocks.size(), nck = b->rs_chk.size();
+  const size_t p_rb = place(nrb * sizeof(RsBlock)), p_rbf = place(nrb * 4), p_chk = place(nck * 8);
   take_cached(b->h_plan, ctx->h_plan_cache, po);
   CK(b->h_plan.reserve(po + 256), "cudaHostAlloc(plan)");
   CK(ctx->d_plan.reserve(po + 256), "cudaMalloc(plan)");
@@ -410,6 +516,8 @@ extern "C" int afx_batch_upload(afx_batch* b)
   if (nsc) { memcpy(hp + p_scf, b->src_chunk_file.data(), nsc * 4); memcpy(hp + p_scs, b->src_chunk_start.data(), nsc * 4); }
   if (ndc) { memcpy(hp + p_dcf, b->dst_chunk_file.data(), ndc * 4); memcpy(hp + p_dcs, b->dst_chunk_start.data(), ndc * 4); }
   if (nrc) { memcpy(hp + p_rcf, b->rs_chunk_file.data(), nrc * 4); memcpy(hp + p_rcs, b->rs_chunk_start.data(), nrc * 4); }
+  if (nrb) { memcpy(hp + p_rb, b->rs_blocks.data(), nrb * sizeof(RsBlock)); memcpy(hp + p_rbf, b->rs_blk_file.data(), nrb * 4); }
+  if (nck) memcpy(hp + p_chk, b->rs_chk.data(), nck * 8);
 
   CK(cudaEventRecord(b->ev[0], ctx->stream), "cudaEventRecord");
   CK(cudaMemcpyAsync(ctx->d_plan.p, hp, po, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(plan)");
@@ -427,13 +535,16 @@ extern "C" int afx_batch_upload(afx_batch* b)
   D.pcm = (const unsigned char*)ctx->d_pcm.p; D.mono = (float*)ctx->d_mono.p; D.mono_src = (float*)ctx->d_mono_src.p;
   D.files = (const AfxFile*)(dp + p_files); D.state = (AfxState*)ctx->d_state.p;
   D.mag = (double*)ctx->d_mag.p; D.cent_full = (double*)ctx->d_cent.p; D.fs = (double*)ctx->d_fs.p; D.fsr = (double*)ctx->d_fsr.p;
-  D.fv = (double*)ctx->d_fv.p; D.rpolar = (float*)ctx->d_rpolar.p; D.rodf = (float*)ctx->d_rodf.p;
+  D.fv = (double*)ctx->d_fv.p; D.rpolar = (float*)ctx->d_rpolar.p; D.rodf = (float*)ctx->d_rodf.p; D.rpost = (float*)ctx->d_rpost.p;
+  D.max_fr = b->max_fr;
   D.stats = (double*)ctx->d_stats.p; D.header = (double*)ctx->d_header.p; D.scratch = (double*)ctx->d_scratch.p;
   AfxCondPlan& C = b->cond;
   memset(&C, 0, sizeof(C));
   C.src_chunk_file = (const int*)(dp + p_scf); C.src_chunk_start = (const int*)(dp + p_scs); C.n_src_chunks = (int)nsc;
   C.dst_chunk_file = (const int*)(dp + p_dcf); C.dst_chunk_start = (const int*)(dp + p_dcs); C.n_dst_chunks = (int)ndc;
   C.rs_chunk_file = (const int*)(dp + p_rcf); C.rs_chunk_start = (const int*)(dp + p_rcs); C.n_rs_chunks = (int)nrc;
+  C.rs_blocks = (const RsBlock*)(dp + p_rb); C.rs_blk_file = (const int*)(dp + p_rbf); C.rs_times = (const double*)(dp + p_chk);
+  C.n_rs_blocks = (int)nrb;
   b->uploaded = true;
   return AFX_OK;
 }
@@ -464,25 +575,31 @@ extern "C" int afx_batch_compute(afx_batch* b)
   b->ktimes.clear();
   b->launches = 0;
   CK(cudaEventRecord(b->ev[2], ctx->stream), "cudaEventRecord");
+  for (const auto& t : b->rs_tails)   // samples past what libresample delivers stay 0 (SA.cpp:579-580: zero-initialised buffer)
+    CK(cudaMemsetAsync((float*)ctx->d_mono.p + t.off, 0, (size_t)t.count * 4, ctx->stream), "cudaMemsetAsync(mono tail)");
   ktime_begin(b, "condition"); afx_launch_condition_plan(ctx->P, b->dev, b->cond, ctx->stream, &b->launches); ktime_end(b);
-  if (feat & (AFX_FEAT_SPECTRAL | AFX_FEAT_AMPLITUDE | AFX_FEAT_PEAKS | AFX_FEAT_BANDS | AFX_FEAT_PITCH)) {
-    ktime_begin(b, "spectrum"); afx_launch_spectrum(ctx->P, b->dev, feat, ctx->stream, &b->launches); ktime_end(b);
-  }
+  for (const auto& g : b->groups) {
+    AfxBatchDev D = b->dev;
+    D.file0 = g.file0; D.g_files = g.nfiles; D.slot0 = g.slot0; D.g_slots = g.nslots; D.rslot0 = g.rslot0; D.g_rslots = g.nrslots;
+    if (feat & (AFX_FEAT_SPECTRAL | AFX_FEAT_AMPLITUDE | AFX_FEAT_PEAKS | AFX_FEAT_BANDS | AFX_FEAT_PITCH)) {
+      ktime_begin(b, "spectrum"); afx_launch_spectrum(ctx->P, D, feat, ctx->stream, &b->launches); ktime_end(b);
+    }
 #ifdef AFX_HAVE_PEAKS
-  if (feat & AFX_FEAT_PEAKS) { ktime_begin(b, "peaks"); afx_launch_peaks(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+    if (feat & AFX_FEAT_PEAKS) { ktime_begin(b, "peaks"); afx_launch_peaks(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
 #endif
 #ifdef AFX_HAVE_BANDS
-  if (feat & AFX_FEAT_BANDS) { ktime_begin(b, "bands"); afx_launch_bands(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+    if (feat & AFX_FEAT_BANDS) { ktime_begin(b, "bands"); afx_launch_bands(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
 #endif
 #ifdef AFX_HAVE_PITCH
-  if (feat & AFX_FEAT_PITCH) { ktime_begin(b, "pitch"); afx_launch_pitch(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+    if (feat & AFX_FEAT_PITCH) { ktime_begin(b, "pitch"); afx_launch_pitch(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
 #endif
 #ifdef AFX_HAVE_AUTOCORR
-  if (feat & AFX_FEAT_AUTOCORR) { ktime_begin(b, "autocorr"); afx_launch_autocorr(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+    if (feat & AFX_FEAT_AUTOCORR) { ktime_begin(b, "autocorr"); afx_launch_autocorr(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
 #endif
 #ifdef AFX_HAVE_RHYTHM
-  if (feat & AFX_FEAT_RHYTHM) { ktime_begin(b, "rhythm"); afx_launch_rhythm(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+    if (feat & AFX_FEAT_RHYTHM) { ktime_begin(b, "rhythm"); afx_launch_rhythm(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
 #endif
+  }
 #ifdef AFX_HAVE_STATS
   if (feat & AFX_FEAT_STATS) { ktime_begin(b, "stats"); afx_launch_stats(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
 #endif
@@ -640,11 +757,17 @@ extern "C" int afx_batch_kernel_times(const afx_batch* b, const char** names, fl
   if (!b) return AFX_ERR_ARG;
   cudaSetDevice(b->ctx->device);
   int n = 0;
+  std::vector<std::pair<const char*, float>> agg;     // one entry per kernel group, summed over the launch groups
   for (const auto& k : b->ktimes) {
-    if (n >= cap) break;
     float v = 0; cudaEventElapsedTime(&v, k.a, k.b);
-    if (names) names[n] = k.name;
-    if (ms) ms[n] = v;
+    bool found = false;
+    for (auto& a : agg) if (!strcmp(a.first, k.name)) { a.second += v; found = true; break; }
+    if (!found) agg.push_back({ k.name, v });
+  }
+  for (const auto& a : agg) {
+    if (n >= cap) break;
+    if (names) names[n] = a.first;
+    if (ms) ms[n] = a.second;
     ++n;
   }
   return n;

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(AT) k_autocorr(AfxBatchDev B, AfxParams P)
   __shared__ int s_file;
 
   const int tid = threadIdx.x;
-  const int slot = blockIdx.x;
+  const int slot = B.slot0 + blockIdx.x;
   if (tid == 0) s_file = find_file_by_frame(B.files, B.n_files, slot);
   __syncthreads();
   const int fi = s_file;
@@ -82,6 +82,6 @@ __global__ void __launch_bounds__(AT) k_autocorr(AfxBatchDev B, AfxParams P)
 
 void afx_launch_autocorr(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
-  if (B.TF <= 0) return;
-  k_autocorr<<<B.TF, AT, 0, s>>>(B, P); ++*launches;
+  if (B.g_slots <= 0) return;
+  k_autocorr<<<B.g_slots, AT, 0, s>>>(B, P); ++*launches;
 }

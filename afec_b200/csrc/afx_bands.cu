@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(BT) k_bands(AfxBatchDev B, AfxParams P)
   __shared__ int s_file;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int slot = blockIdx.x;
+  const int slot = B.slot0 + blockIdx.x;
   if (tid == 0) s_file = find_file_by_frame(B.files, B.n_files, slot);
   __syncthreads();
   const int fi = s_file;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(BT) k_bands(AfxBatchDev B, AfxParams P)
   const int t = slot - f.frame_off;
   if (f.status != 0 || t >= B.state[fi].F) return;
   const size_t TF = (size_t)B.TF;
-  const double* g = B.mag + (size_t)slot * AFX_NBIN;
+  const double* g = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
   const double* gp = (t > 0) ? g - AFX_NBIN : g;              // SampleAnalyser.cpp:936-940
   for (int k = tid; k < AFX_NBIN; k += BT) {
     const double m = g[k];
@@ -141,6 +141,6 @@ __global__ void __launch_bounds__(BT) k_bands(AfxBatchDev B, AfxParams P)
 
 void afx_launch_bands(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
-  if (B.TF <= 0) return;
-  k_bands<<<B.TF, BT, 0, s>>>(B, P); ++*launches;
+  if (B.g_slots <= 0) return;
+  k_bands<<<B.g_slots, BT, 0, s>>>(B, P); ++*launches;
 }

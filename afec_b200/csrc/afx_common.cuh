@@ -89,6 +89,9 @@ struct AfxParams {
   double eff_floor[3];
   int analysis_cap;         // 882000
   int ac_min_period, ac_width;   // 35, 529
+  // rhythm front / back end (OnsetDetector.cpp:106-111, 280-322; RhythmTracker.cpp:17-40; CannyWindow.cpp:27-80)
+  float r_relax, r_norm_complex, r_norm_power;
+  double canny[25];         // taps -12 .. +12 (the convolution uses -12 .. +11)
   AfxTables t;
 };
 
@@ -221,29 +224,35 @@ __device__ __forceinline__ void mul_frexp(double& mant, int& ex, double v)
 // kernel launchers (one per translation unit); all asynchronous on `s`
 struct AfxBatchDev {
   int n_files, TF, TFr;
+  // the frame-level kernels run group by group (whole files) so that the per-frame scratch (mag, rpolar,
+  // scratch) is bounded: this launch covers files [file0, file0 + g_files), main frame slots
+  // [slot0, slot0 + g_slots) and rhythm frame slots [rslot0, rslot0 + g_rslots)
+  int file0, g_files, slot0, g_slots, rslot0, g_rslots;
   const unsigned char* pcm;
   float* mono;
   float* mono_src;
   const AfxFile* files;
   AfxState* state;
-  double* mag;        // [TF][1024]
+  double* mag;        // [g_slots][1024]   (group scratch, indexed by slot - slot0)
   double* cent_full;  // [TF] centroid of mag[0..1023] (failsafe f0)
   double* fs;         // [22][TF]
   double* fsr;        // [2][TFr]
   double* fv;         // 7 arrays [TF][nb], array v at fv + FV_x * TF
-  float* rpolar;      // [TFr][512]
+  float* rpolar;      // [g_rslots][512]   (group scratch, indexed by rslot - rslot0)
   float* rodf;        // [2][TFr] raw onset functions
+  float* rpost;       // [2][TFr] onset functions minus their running median
   double* stats;      // [n_files][136][13]
   double* header;     // [n_files][32]
-  double* scratch;    // rhythm back-end workspace
+  double* scratch;    // [g_rslots][4] rhythm back-end workspace (group scratch)
+  int max_fr;         // largest rhythm frame capacity of any file in the batch
 };
 
-struct RsBlock { double t0; int out0; int nout; long long in0; };   // in0: source index of X[0] (may be negative)
+struct RsBlock { int out0; int nout; long long in0; long long chk_off; };   // in0: source index of X[0] (may be negative); chk_off: first time checkpoint
 struct AfxCondPlan {       // device arrays built by the host for one batch
   const int* src_chunk_file; const int* src_chunk_start; int n_src_chunks;   // chunks over source frames
   const int* dst_chunk_file; const int* dst_chunk_start; int n_dst_chunks;   // chunks over analysis-rate samples
   const int* rs_chunk_file; const int* rs_chunk_start; int n_rs_chunks;      // same, resampled files only
-  const RsBlock* rs_blocks; const int* rs_blk_file; const double* rs_times; const long long* rs_time_off; int n_rs_blocks;
+  const RsBlock* rs_blocks; const int* rs_blk_file; const double* rs_times; int n_rs_blocks;   // rs_times: every 64th output time stamp
 };
 void afx_launch_condition_plan(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s, long long* launches);
 void afx_launch_materialise(const float* mono, const AfxState* st, double* out, int len, cudaStream_t s);

@@ -97,18 +97,20 @@ __global__ void __launch_bounds__(CT) k_reduce(AfxBatchDev B, const int* __restr
 // One thread per output sample.  The output-sample time stamps (a double accumulator advanced by
 // repeated "+= 1/factor" inside 4096-sample input blocks, resample.c:230-300 / resamplesubs.c:97-119)
 // are data independent; the host replays that recurrence once per distinct (rate, length) pair and
-// uploads, per block, the start time, the first output index and the input offset.  Inside a block a
-// thread reproduces its stamp by the same repeated additions in chunks of 64 from checkpoints.
+// uploads, per block, the first output index, the input offset and every 64th time stamp.  A thread
+// reproduces its own stamp from the nearest checkpoint by the same repeated additions (<= 63).
 
 __global__ void __launch_bounds__(128) k_resample(AfxBatchDev B, AfxTables T, const RsBlock* __restrict__ blocks,
                                                   const int* __restrict__ blk_file, const double* __restrict__ times,
-                                                  const long long* __restrict__ time_off, int n_blocks, int analysis_rate)
+                                                  int n_blocks, int analysis_rate)
 {
   const int bi = blockIdx.x;
   if (bi >= n_blocks) return;
   const RsBlock rb = blocks[bi];
   const AfxFile f = B.files[blk_file[bi]];
-  const double factor = (double)analysis_rate / (double)f.src_rate;
+  const double speed = (double)f.src_rate / (double)analysis_rate;   // SA.cpp:563
+  const double factor = 1.0 / speed;                                  // SA.cpp:584-590
+  const double dt = 1.0 / factor;                                     // resamplesubs.c:44, 90
   const float* __restrict__ src = B.mono_src + f.src_off;
   float* __restrict__ dst = B.mono + f.mono_off;
   const float* __restrict__ imp = T.rs_imp;
@@ -117,11 +119,12 @@ __global__ void __launch_bounds__(128) k_resample(AfxBatchDev B, AfxTables T, co
   float lpscl = 1.0f;
   if (factor < 1) lpscl = (float)((double)lpscl * factor);
   double dh = factor * 4096.0; if (dh > 4096.0) dh = 4096.0;
-  const double* tt = times + time_off[bi];
+  const double* chk = times + rb.chk_off;
   for (int k = threadIdx.x; k < rb.nout; k += blockDim.x) {
     const int o = rb.out0 + k;
     if (o >= f.n) break;
-    const double t = tt[k];
+    double t = chk[k >> 6];
+    for (int q = 0; q < (k & 63); ++q) t = __dadd_rn(t, dt);   // the block's own repeated additions
     const double fl = floor(t);
     const double lph = t - fl, rph = 1.0 - lph;
     const long long xi = rb.in0 + (long long)fl;   // source index of X[(int)t]
@@ -305,7 +308,7 @@ void afx_launch_condition_plan(const AfxParams& P, const AfxBatchDev& B, const A
   k_state_init<<<fb, 128, 0, s>>>(B); ++*launches;
   if (C.n_src_chunks > 0) { k_downmix<<<C.n_src_chunks, CT, 0, s>>>(B, C.src_chunk_file, C.src_chunk_start, P.sr); ++*launches; }
   if (C.n_rs_blocks > 0) {
-    k_resample<<<C.n_rs_blocks, 128, 0, s>>>(B, P.t, C.rs_blocks, C.rs_blk_file, C.rs_times, C.rs_time_off, C.n_rs_blocks, P.sr); ++*launches;
+    k_resample<<<C.n_rs_blocks, 128, 0, s>>>(B, P.t, C.rs_blocks, C.rs_blk_file, C.rs_times, C.n_rs_blocks, P.sr); ++*launches;
     k_reduce<<<C.n_rs_chunks, CT, 0, s>>>(B, C.rs_chunk_file, C.rs_chunk_start); ++*launches;
   }
   k_amp<<<fb, 128, 0, s>>>(B); ++*launches;

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(YT) k_pitch(AfxBatchDev B, AfxParams P)
   __shared__ int s_file;
 
   const int tid = threadIdx.x;
-  const int slot = blockIdx.x;
+  const int slot = B.slot0 + blockIdx.x;
   if (tid == 0) s_file = find_file_by_frame(B.files, B.n_files, slot);
   __syncthreads();
   const int fi = s_file;
@@ -181,9 +181,9 @@ __global__ void __launch_bounds__(YT) k_pitch(AfxBatchDev B, AfxParams P)
 
 void afx_launch_pitch(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
-  if (B.TF <= 0) return;
+  if (B.g_slots <= 0) return;
   static bool attr_set = false;
   const int smem = 2 * YN * (int)sizeof(double2) + (YN + 8) * (int)sizeof(double);
   if (!attr_set) { cudaFuncSetAttribute(k_pitch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-  k_pitch<<<B.TF, YT, smem, s>>>(B, P); ++*launches;
+  k_pitch<<<B.g_slots, YT, smem, s>>>(B, P); ++*launches;
 }

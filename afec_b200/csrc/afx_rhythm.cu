@@ -1,0 +1,506 @@
+// K7: rhythm -- the 512 / 128 onset front end and the per-file back end.
+//
+// Reference: TSampleAnalyser::AnalyzeLowLevelDescriptors rhythm part (SampleAnalyser.cpp:983-1048),
+// TRhythmTracker (Source/Crawler/FeatureExtraction/Source/RhythmTracker.cpp:46-117 front end,
+// :121-660 back end), TOnsetFftProcessor / TOnsetDetector (Source/Core/AudioTypes/Source/
+// OnsetDetector.cpp:96-243, 371-590), TCannyWindow (CannyWindow.cpp:27-80) and aubio's beat tracker
+// (3rdParty/Aubio/Dist/src/tempo/beattracking.c:59-110, 126-262, 286-410, 424-441; mathutils.c:652-666).
+//
+// The reference walks the rhythm frames of a file one by one, but only three things really are
+// sequential: the per-bin whitening peak memory, the onset min-gap state machine and the valley
+// tracking of the contrast measure.  Everything else is a function of a few neighbouring frames and is
+// computed frame-parallel over the whole batch:
+//
+//   k_rhythm_polar   (warp per frame)  Hann(512) x frame -> 512-pt real FFT (FP64) -> float32 polar row
+//                                      [mag 0..254 | dc | phase 0..254] (bins 0..254 + Re[0]; quirk: the
+//                                      "Nyquist" slot of the reference is Im[0] == 0)
+//   k_rhythm_whiten  (thread per file x bin, sequential over frames) adaptive-max whitening, in place
+//   k_rhythm_odf     (warp per frame)  rectified complex-domain and power onset functions from rows
+//                                      t, t-1, t-2; float32 operation order of the reference
+//   k_rhythm_median  (warp per frame)  running median of the last 69 ODF values -> post = odf - median
+//   k_rhythm_back    (CTA per file)    min-gap peak picker -> onset series, onset count, Canny
+//                                      sharpening + z-score, peak strength / frequency / contrast, beat
+//                                      tracker (ACF, comb filterbank, Rayleigh weighting), tempo heuristics
+#include "afx_fft.cuh"
+#include "../../include/afec_b200.h"
+
+#define RPW 8              // frames (warps) per CTA in the frame-parallel kernels
+#define MEDSPAN 69         // int(44100 * 0.2 / 128 + 0.5), OnsetDetector.cpp:280-282
+#define BT_THREADS 256
+
+// OnsetDetector.cpp:19-23 (float32; explicit rn intrinsics keep nvcc from contracting to FMA)
+__device__ __forceinline__ float phase_rewrap(float p)
+{
+  const float pi = (float)3.14159265358979323846, twopi = (float)6.2831853071795864769252867665590,
+    inv2pi = (float)0.15915494309189533576888376337251;
+  if (p > -pi && p < pi) return p;
+  const float k = __fadd_rn(1.f, floorf(__fmul_rn(__fsub_rn(-pi, p), inv2pi)));
+  return __fadd_rn(p, __fmul_rn(twopi, k));
+}
+
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RPW * 32) k_rhythm_polar(AfxBatchDev B, AfxParams P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double2* a = reinterpret_cast<double2*>(smem_raw) + wid * 512;
+  double2* b = a + 256;
+  const int rel = blockIdx.x * RPW + wid;
+  if (rel >= B.g_rslots) return;               // warp-uniform; only __syncwarp below
+  const int slot = B.rslot0 + rel;
+  const int fi = find_file_by_rframe(B.files, B.n_files, slot);
+  const AfxFile f = B.files[fi];
+  const int t = slot - f.rframe_off;
+  if (f.status != 0 || t >= B.state[fi].Fr) return;
+  const AfxState st = B.state[fi];
+  const float* __restrict__ mono = B.mono + f.mono_off;
+  const double* __restrict__ win = P.t.rwindow;
+  const int n0 = t * AFX_RHOP;
+  for (int m = lane; m < 256; m += 32) {
+    const double x0 = mdata(mono, st, n0 + 2 * m), x1 = mdata(mono, st, n0 + 2 * m + 1);
+    a[m] = make_double2(__ldg(win + 2 * m) * x0, __ldg(win + 2 * m + 1) * x1);   // OnsetDetector.cpp:119-120
+  }
+  __syncwarp();
+  double2* Z = fft_pow4<256, AFX_RFFT, true>(a, b, P.t.tw512, lane, 32);
+  float* row = B.rpolar + (size_t)rel * AFX_RROW;
+  for (int k = lane; k < 256; k += 32) {
+    const double2 zk = Z[k], zm = cconj(Z[(256 - k) & 255]);
+    const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y + zm.y));
+    const double2 D = make_double2(0.5 * (zk.x - zm.x), 0.5 * (zk.y - zm.y));
+    const double2 O = make_double2(D.y, -D.x);
+    double2 X = cadd(E, cmul(__ldg(P.t.tw512 + k), O));
+    if (k == 0) { X.y = 0.0; row[255] = (float)X.x; }                             // mDC, OnsetDetector.cpp:146
+    if (k < AFX_RBINS) {
+      row[k] = (float)sqrt(X.x * X.x + X.y * X.y);                                // :136-155
+      row[256 + k] = (float)atan2(X.y, X.x);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// adaptive-max whitening (OnsetDetector.cpp:193-243): psp is a per-bin recurrence over the file's frames
+__global__ void __launch_bounds__(256) k_rhythm_whiten(AfxBatchDev B, AfxParams P)
+{
+  const int fi = B.file0 + blockIdx.x;
+  const AfxFile f = B.files[fi];
+  if (f.status != 0) return;
+  const int Fr = B.state[fi].Fr;
+  if (Fr <= 0) return;
+  float* col = B.rpolar + (size_t)(f.rframe_off - B.rslot0) * AFX_RROW + threadIdx.x;   // 0..254 bins, 255 dc
+  const double relax = (double)P.r_relax, wfloor = (double)0.1f;
+  double psp = 0.0;
+  float v = col[0];
+  for (int t = 0; t < Fr; ++t) {
+    const float vn = (t + 1 < Fr) ? col[(size_t)(t + 1) * AFX_RROW] : 0.0f;   // prefetch
+    double a = (double)fabsf(v);
+    if (a < psp) a = __dadd_rn(a, __dmul_rn(__dsub_rn(psp, a), relax));
+    psp = a;
+    col[(size_t)t * AFX_RROW] = __fdiv_rn(v, (float)(wfloor > psp ? wfloor : psp));
+    v = vn;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// onset functions (OnsetDetector.cpp:371-547): kFunctionRComplex and kFunctionPower
+__global__ void __launch_bounds__(RPW * 32) k_rhythm_odf(AfxBatchDev B, AfxParams P)
+{
+  __shared__ float smag[RPW][256];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rel = blockIdx.x * RPW + wid;
+  if (rel >= B.g_rslots) return;
+  const int slot = B.rslot0 + rel;
+  const int fi = find_file_by_rframe(B.files, B.n_files, slot);
+  const AfxFile f = B.files[fi];
+  const int t = slot - f.rframe_off;
+  if (f.status != 0 || t >= B.state[fi].Fr) return;
+  const float* r0 = B.rpolar + (size_t)rel * AFX_RROW;
+  const float* r1 = r0 - AFX_RROW;      // valid when t >= 1
+  const float* r2 = r0 - 2 * AFX_RROW;  // valid when t >= 2
+  double total = 0.0;
+  for (int i = lane; i < 256; i += 32) {
+    const float m = r0[i];
+    smag[wid][i] = m;
+    if (i >= AFX_RBINS) continue;
+    const float cur = fabsf(m);
+    const float pm = (t >= 1) ? fabsf(r1[i]) : 0.0f;
+    if (cur > 0.01f && !(cur < pm)) {
+      const float yp = (t >= 1) ? r1[256 + i] : 0.0f;
+      const float yp2 = (t >= 2) ? r2[256 + i] : 0.0f;
+      const float ypd = (t >= 1) ? phase_rewrap(__fsub_rn(yp, yp2)) : 0.0f;
+      const float pred = __fadd_rn(yp, ypd);
+      const float dev = __fsub_rn(pred, r0[256 + i]);
+      const float c = cosf(phase_rewrap(dev));
+      const float q = __fsub_rn(__fadd_rn(__fmul_rn(pm, pm), __fmul_rn(cur, cur)), __fmul_rn(__fmul_rn(pm, cur), c));
+      total += (double)sqrtf(q);
+    }
+  }
+  total = warp_sum(total);
+  __syncwarp();
+  if (lane == 0) {
+    const float dc = smag[wid][255];
+    float v = __fadd_rn(__fmul_rn(0.0f, 0.0f), __fmul_rn(dc, dc));          // nyq^2 + dc^2, :388-396
+    for (int i = 0; i < AFX_RBINS; ++i) { const float m = smag[wid][i]; v = __fadd_rn(v, __fmul_rn(m, m)); }
+    B.rodf[slot] = __fmul_rn((float)total, P.r_norm_complex);
+    B.rodf[(size_t)B.TFr + slot] = __fmul_rn(v, P.r_norm_power);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// median removal (OnsetDetector.cpp:551-575): post = odf[t] - median(odf[t-68 .. t]), zeros before the file
+__global__ void __launch_bounds__(RPW * 32) k_rhythm_median(AfxBatchDev B)
+{
+  __shared__ float w[RPW][2][96];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rel = blockIdx.x * RPW + wid;
+  if (rel >= B.g_rslots) return;
+  const int slot = B.rslot0 + rel;
+  const int fi = find_file_by_rframe(B.files, B.n_files, slot);
+  const AfxFile f = B.files[fi];
+  const int t = slot - f.rframe_off;
+  if (f.status != 0 || t >= B.state[fi].Fr) return;
+  for (int ty = 0; ty < 2; ++ty) {
+    const float* odf = B.rodf + (size_t)ty * B.TFr + slot;
+    for (int j = lane; j < 96; j += 32) w[wid][ty][j] = (j < MEDSPAN && t - j >= 0) ? odf[-j] : 0.0f;
+  }
+  __syncwarp();
+  for (int ty = 0; ty < 2; ++ty) {
+    const float* x = w[wid][ty];
+    float med = 0.0f; bool have = false;
+    for (int j = lane; j < MEDSPAN; j += 32) {
+      const float v = x[j];
+      int rank = 0;
+      for (int k = 0; k < MEDSPAN; ++k) { const float u = x[k]; rank += (u < v || (u == v && k < j)) ? 1 : 0; }
+      if (rank == (MEDSPAN - 1) / 2) { med = v; have = true; }
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, have);
+    med = __shfl_sync(0xffffffffu, med, ball ? (__ffs(ball) - 1) : 0);
+    if (lane == 0) B.rpost[(size_t)ty * B.TFr + slot] = __fsub_rn(x[0], med);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// back end helpers
+__device__ __forceinline__ unsigned long long rb_order_key(double x)
+{
+  const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double rb_key_to_double(unsigned long long k)
+{
+  const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+
+// k-th smallest (0-based) of s[0..n) by an 8-pass MSD radix select; all threads call, result broadcast
+__device__ double block_select(const double* s, int n, int k, int* hist, int* ctl)
+{
+  unsigned long long prefix = 0ull, pmask = 0ull;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int byte = 7; byte >= 0; --byte) {
+    for (int q = tid; q < 256; q += blockDim.x) hist[q] = 0;
+    __syncthreads();
+    const int sh = byte * 8;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const unsigned long long key = rb_order_key(s[i]);
+      if ((key & pmask) == prefix) atomicAdd(&hist[(int)((key >> sh) & 0xff)], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      int c[8]; int tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { c[q] = hist[lane * 8 + q]; tot += c[q]; }
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int pv = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += pv; }
+      const int excl = inc - tot;
+      if (k >= excl && k < inc) {
+        int run = excl, digit = -1, newk = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { if (digit < 0 && k < run + c[q]) { digit = lane * 8 + q; newk = k - run; } run += c[q]; }
+        ctl[0] = digit; ctl[1] = newk;
+      }
+    }
+    __syncthreads();
+    prefix |= ((unsigned long long)ctl[0]) << sh; pmask |= 0xffull << sh; k = ctl[1];
+    __syncthreads();
+  }
+  return rb_key_to_double(prefix);
+}
+
+// TAudioMath::SamplesToMs / MsToSamples, AudioMath.inl:127-137 (float32)
+__device__ __forceinline__ float r_samples_to_ms(int sr, int samples) { return __fdiv_rn((float)samples, __fdiv_rn((float)sr, 1000.0f)); }
+__device__ __forceinline__ int r_ms_to_samples(int sr, float ms)
+{
+  const float v = __fmul_rn(__fdiv_rn((float)sr, 1000.0f), ms);
+  return (int)__fadd_rn(v, signbit(v) ? -0.5f : 0.5f);
+}
+
+// RhythmTracker.cpp:502-555
+__device__ double r_guess_beats(double min_bpm, double dur)
+{
+  const double beat = 60.0 / min_bpm, bar = 4.0 * beat;
+  if (dur < beat) return 0.0;
+  if (dur < bar) {
+    for (int div = 2; div >= 1; div /= 2) { const double d = (4.0 / (double)div) * beat; if (4 % div == 0 && dur < d) return (double)(float)(4.0 / (double)div); }
+    return 4.0;
+  }
+  for (int bars = 1; bars <= 8; bars *= 2) { const double nb = 4.0 * bars; if (dur / nb < beat) return (double)(float)nb; }
+  return 0.0;
+}
+
+// RhythmTracker.cpp:559-603
+__device__ double r_onset_match_conf(int sr, const double* raw, int n, double off_s, double nbeats, double tempo, double thr)
+{
+  const int off = r_ms_to_samples(sr, (float)(off_s * 1000));
+  const double spb = 60.0 / tempo * sr;
+  const int range = (int)(spb / 32) / AFX_RHOP;
+  double strength = 0;
+  for (int i = 0; i < nbeats * 2; ++i) {
+    const int t = (int)(i * spb / 2.0) + off;
+    const int idx = ((t + AFX_RHOP / 2) / AFX_RHOP);
+    double peak = 0.0;
+    for (int j = idx - range; j < idx + range; ++j) if (j >= 0 && j < n) peak = peak > raw[j] ? peak : raw[j];
+    if (peak >= thr) strength += 1.0;
+  }
+  const double v = strength / (nbeats * 2) * 2.0;
+  return v < 1.0 ? v : 1.0;
+}
+
+// block-wide sum / max of one double (blockDim.x == BT_THREADS); result broadcast
+__device__ __forceinline__ double rb_sum(double v, double* scr) { double a[1] = { v }; block_sum<1>(a, scr); return a[0]; }
+
+__global__ void __launch_bounds__(BT_THREADS) k_rhythm_back(AfxBatchDev B, AfxParams P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double scr[64];
+  __shared__ int hist[256];
+  __shared__ int ctl[4];
+  __shared__ double res[2][2];      // [type][tempo, confidence]
+
+  const int tid = threadIdx.x;
+  const int fi = B.file0 + blockIdx.x;
+  const AfxFile f = B.files[fi];
+  if (f.status != 0) return;
+  const int n = B.state[fi].Fr;
+  if (n <= 0) return;
+  const int cap = B.max_fr;
+  double* s = reinterpret_cast<double*>(smem_raw);                        // [cap] sharpened onsets
+  unsigned char* lm = reinterpret_cast<unsigned char*>(s + cap);          // [cap] local-maximum flags
+  unsigned* bits = reinterpret_cast<unsigned*>(lm + ((cap + 15) & ~15));  // [(cap + 31) / 32] candidate mask
+  const int nw = (n + 31) >> 5;
+  double* H = B.header + (size_t)fi * AFX_N_HEADER;
+  double* gs = B.scratch + (size_t)(f.rframe_off - B.rslot0) * 4;
+  const int fcap = f.rframe_cap;
+  const size_t TFr = (size_t)B.TFr;
+
+  for (int ty = 0; ty < 2; ++ty) {
+    const float* post = B.rpost + (size_t)ty * TFr + f.rframe_off;
+    double* raw = B.fsr + (size_t)ty * TFr + f.rframe_off;
+    double* sharp = gs + (size_t)ty * fcap;
+    double* acf = gs + (size_t)2 * fcap;
+    double* acfout = gs + (size_t)3 * fcap;
+    const float thr_f = ty ? 0.8f : 0.2f;                                 // RhythmTracker.cpp:17-40
+    const double thr_d = ty ? 0.8 : 0.2;
+    const int mingap = ty ? 41 : 21;                                      // int(44100 * {0.12, 0.06} / 128 + .5)
+
+    // ---- min-gap peak picker (OnsetDetector.cpp:577-590): candidates in parallel, gaps sequentially ----
+    for (int w = tid; w < nw; w += BT_THREADS) {
+      unsigned m = 0;
+      for (int q = 0; q < 32; ++q) {
+        const int t = w * 32 + q;
+        if (t < n) {
+          const float p = post[t], pp = (t > 0) ? post[t - 1] : 0.0f;
+          if (p > thr_f && pp <= thr_f) m |= 1u << q;
+          raw[t] = 0.0;
+        }
+      }
+      bits[w] = m;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      while (t < n) {
+        int w = t >> 5;
+        unsigned m = bits[w] & (0xffffffffu << (t & 31));
+        while (!m && ++w < nw) m = bits[w];
+        if (!m) break;
+        t = w * 32 + __ffs(m) - 1;
+        raw[t] = (double)post[t];                                        // RhythmTracker.cpp:105-115
+        t += mingap + 1;
+      }
+    }
+    __syncthreads();
+
+    // ---- onset count (RhythmTracker.cpp:121-134) and Canny convolution (CannyWindow.cpp:50-66) ----
+    int cnt = 0;
+    for (int i = tid; i < n; i += BT_THREADS) {
+      cnt += (raw[i] > thr_d) ? 1 : 0;
+      double sum = 0.0;
+      for (int sh = -12; sh < 12; ++sh) { const int j = i + sh; if (j >= 0 && j < n) sum = __dadd_rn(sum, __dmul_rn(raw[j], P.canny[sh + 12])); }
+      s[i] = sum;
+    }
+    cnt = block_sum_i(cnt, hist);
+    __syncthreads();
+    // z-score, rectified (CannyWindow.cpp:68-80)
+    double a = 0.0;
+    for (int i = tid; i < n; i += BT_THREADS) a += s[i];
+    const double mean = (n >= 2) ? rb_sum(a, scr) / (double)n : s[0];
+    a = 0.0;
+    for (int i = tid; i < n; i += BT_THREADS) { const double d = s[i] - mean; a += d * d; }
+    const double var = (n >= 2) ? rb_sum(a, scr) / (double)n : 0.0;
+    __syncthreads();
+    if (var > 0.0) {
+      const double sd = sqrt(var);
+      for (int i = tid; i < n; i += BT_THREADS) { const double v = (s[i] - mean) / sd; s[i] = v > 0.0 ? v : 0.0; }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += BT_THREADS) sharp[i] = s[i];
+
+    // ---- peaks of the sharpened function (RhythmTracker.cpp:623-659): strength, frequency ----
+    a = 0.0; int np = 0; double tot = 0.0;
+    for (int i = tid; i < n; i += BT_THREADS) {
+      const double v = s[i];
+      tot += v;
+      bool is_max = true;
+      const int lo = max(0, i - 24), hi = min(n - 1, i + 24);
+      for (int j = lo; j <= hi; ++j) if (s[j] > v) { is_max = false; break; }
+      lm[i] = is_max ? 1 : 0;
+      if (v > 0.1 && is_max) { a += v; ++np; }
+    }
+    const double psum = rb_sum(a, scr);
+    np = block_sum_i(np, hist);
+    const double total_mean = (n >= 2) ? rb_sum(tot, scr) / (double)n : s[0];
+
+    // ---- contrast (RhythmTracker.cpp:392-480): 85th percentile threshold, peaks vs preceding valleys ----
+    const double pthr = block_select(s, n, (int)(85.0 / 100.0 * (n - 1)), hist, ctl);
+    if (tid == 0) {
+      double ps = 0, vs = 0; int pc = 0, vpos = 0; double vval = pthr;
+      for (int i = 0; i < n; ++i) {
+        const double v = s[i];
+        if (v < vval) { vpos = i; vval = v; }
+        if (v < pthr) continue;
+        if (lm[i]) { ps += v; vs += s[vpos]; ++pc; vval = v; }
+      }
+      const double pmean = pc ? ps / pc : 0.0, vmean = (pc ? vs / pc : 0.0) + 0.0001;
+      double* Hh = H + H_RC_COUNT + 6 * ty;
+      Hh[0] = (double)cnt;
+      Hh[1] = (pmean != 0.0) ? -1.0 * pow(pmean / vmean, 1.0 / log(total_mean + 0.0001)) : 0.0;
+      Hh[2] = (double)np / (double)n * (double)AFX_RHOP / (double)AFX_RFFT;        // SA.cpp:1012-1016
+      double st = np ? (psum / np) / 4.0 : 0.0;                                      // SA.cpp:1018-1027
+      Hh[3] = st < 0.0 ? 0.0 : (st > 1.0 ? 1.0 : st);
+      Hh[4] = 0.0; Hh[5] = 0.0;
+      res[ty][0] = 0.0; res[ty][1] = 0.0;
+    }
+    __syncthreads();
+
+    // ---- tempo: one fresh aubio beat tracker pass over the whole vector (RhythmTracker.cpp:155-230) ----
+    if (cnt >= 4) {
+      const int winlen = n, laglen = winlen / 4;
+      // autocorrelation (mathutils.c:652-666); lags i and winlen-1-i are paired for balance
+      for (int i = tid; i < (winlen + 1) / 2; i += BT_THREADS) {
+        const int i2 = winlen - 1 - i;
+        double t1 = 0.0, t2 = 0.0;
+        for (int j = i; j < winlen; ++j) t1 = fma(s[j - i], s[j], t1);
+        if (i2 != i) for (int j = i2; j < winlen; ++j) t2 = fma(s[j - i2], s[j], t2);
+        acf[i] = t1 / (double)(winlen - i);
+        if (i2 != i) acf[i2] = t2 / (double)(winlen - i2);
+      }
+      __syncthreads();
+      // comb filterbank (beattracking.c:167-177) + Rayleigh weighting (:104-107, 180)
+      const double rp_d = 60. * (double)P.sr / 120. / (double)AFX_RHOP;
+      double lsum = 0.0, lmax = 0.0;
+      for (int i = tid; i < laglen; i += BT_THREADS) {
+        double v = 0.0;
+        if (i >= 1 && i < laglen - 1)
+          for (int aa = 1; aa <= 4; ++aa) for (int b = 1; b < 2 * aa; ++b) v += acf[i * aa + b - 1] * 1. / (2. * aa - 1.);
+        v *= ((double)(i + 1.) / (rp_d * rp_d)) * exp((-((double)(i + 1.) * (double)(i + 1.)) / (2. * rp_d * rp_d)));
+        acfout[i] = v;
+        lsum += v; lmax = fmax(lmax, v);
+      }
+      const double asum = rb_sum(lsum, scr);
+      const double gmax = block_max(lmax, scr);           // >= 0: the reference's running maximum starts at 0
+      int li = -1;
+      for (int i = tid; i < laglen; i += BT_THREADS) if (acfout[i] == gmax) li = i;   // ties -> last index (mathutils.c:267-283)
+      const int maxi_raw = -block_min_i(-li, hist);
+      __syncthreads();
+      if (tid == 0) {
+        const int maxi = maxi_raw < 0 ? 0 : maxi_raw;
+        double rp;
+        if (maxi > 0 && maxi < laglen - 1) {
+          const double s0 = acfout[maxi - 1], s1 = acfout[maxi], s2 = acfout[maxi + 1];
+          rp = maxi + .5 * (s0 - s2) / (s0 - 2. * s1 + s2);
+        } else rp = (double)(unsigned)rp_d;
+        double bp = rp;                                     // beattracking.c:286-410, first call: gp == 0
+        while (0 < bp && bp < 25) bp = bp * 2;
+        double tempo = 0.0;
+        if (bp != 0) tempo = 60. / (((double)AFX_RHOP * bp) / (double)P.sr);
+        double conf = 0.0;                                  // beattracking.c:432-441, mathutils.c:508-517
+        if (asum != 0.) {
+          double qm = 0.;
+          if (!(rp >= laglen || rp < 0.)) {
+            const unsigned idx = (unsigned)(rp - .5) + 1;
+            if ((double)idx == rp) qm = acfout[idx];
+            else { const double x0 = acfout[idx - 1], x1 = acfout[idx], x2 = acfout[idx + 1]; qm = x1 - .25 * (x0 - x2) * (rp - idx); }
+          }
+          conf = qm / asum;
+        }
+        conf = conf * 16.0; conf = conf < 0.0 ? 0.0 : (conf > 1.0 ? 1.0 : conf);
+        if (tempo < 20.0 || tempo > 300.0) { tempo = 0.0; conf = 0.0; }
+        else { while (tempo < 80.0) tempo *= 2.0; while (tempo >= 200.0) tempo /= 2.0; }
+        H[H_RC_COUNT + 6 * ty + 4] = tempo; H[H_RC_COUNT + 6 * ty + 5] = conf;
+        res[ty][0] = tempo; res[ty][1] = conf;
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- final tempo: the more confident onset type + duration heuristics (RhythmTracker.cpp:234-325) ----
+  if (tid == 0) {
+    const int w = (res[1][1] > res[0][1]) ? 1 : 0;
+    const double tempo_in = res[w][0], conf_in = res[w][1];
+    double tempo = 0.0, conf = 0.0;
+    if (tempo_in != 0) {
+      const double* sharp = gs + (size_t)w * fcap;
+      const double* raw = B.fsr + (size_t)w * TFr + f.rframe_off;
+      const double thr = w == 0 ? 0.2 : 0.8;
+      const double dur_s = (double)__fdiv_rn(r_samples_to_ms(f.src_rate, f.nframes_src), 1000.0f);   // SA.cpp:1031-1040
+      const double off_s = (double)__fdiv_rn(r_samples_to_ms(f.src_rate, B.state[fi].data_offset), 1000.0f);
+      tempo = tempo_in; conf = conf_in;
+      const double spb = 60.0 / tempo * P.sr;
+      int last = n - 1;
+      while (last > 0 && sharp[last] < 0.1) --last;
+      const double ns = (double)(last * AFX_RHOP);
+      if (ns < spb * 3) { tempo = 0.0; conf = 0.0; }
+      else {
+        const double nb = r_guess_beats(80, dur_s);
+        if (nb >= 4 && nb <= 16) {
+          const double gbpm = nb / (dur_s / 60);
+          const double delay = (double)r_samples_to_ms(P.sr, AFX_RHOP / 2) / 1000.0;
+          const double gc = r_onset_match_conf(P.sr, raw, n, off_s + delay, nb, gbpm, thr);
+          if ((gc > 0.5) || (conf < 0.1 && gc > 0.1) || (conf < 0.5 && fabs(gbpm - tempo) < 10)) { tempo = gbpm; conf = 0.5 > gc ? 0.5 : gc; }
+        }
+      }
+    }
+    H[H_FINAL_TEMPO] = tempo; H[H_FINAL_TEMPO_CONF] = conf;
+  }
+}
+
+void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
+{
+  if (B.g_files <= 0 || B.g_rslots <= 0) return;
+  static bool attr_set = false;
+  const int smem_polar = RPW * 512 * (int)sizeof(double2);
+  const int cap = B.max_fr;
+  const int smem_back = cap * 8 + ((cap + 15) & ~15) + ((cap + 31) / 32) * 4 + 16;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_rhythm_polar, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_polar);
+    cudaFuncSetAttribute(k_rhythm_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  const int fb = (B.g_rslots + RPW - 1) / RPW;
+  k_rhythm_polar<<<fb, RPW * 32, smem_polar, s>>>(B, P); ++*launches;
+  k_rhythm_whiten<<<B.g_files, 256, 0, s>>>(B, P); ++*launches;
+  k_rhythm_odf<<<fb, RPW * 32, 0, s>>>(B, P); ++*launches;
+  k_rhythm_median<<<fb, RPW * 32, 0, s>>>(B); ++*launches;
+  k_rhythm_back<<<B.g_files, BT_THREADS, smem_back, s>>>(B, P); ++*launches;
+}

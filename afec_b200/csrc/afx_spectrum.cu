@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(ST) k_spectrum(AfxBatchDev B, AfxParams P, uns
   __shared__ int s_file;
 
   const int tid = threadIdx.x;
-  const int slot = blockIdx.x;
+  const int slot = B.slot0 + blockIdx.x;
   if (tid == 0) s_file = find_file_by_frame(B.files, B.n_files, slot);
   __syncthreads();
   const int fi = s_file;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(ST) k_spectrum(AfxBatchDev B, AfxParams P, uns
   // ---- FFT (1024 complex, 5 radix-4 passes) + real unpack + magnitude / N -----------------------
   double2* Z = fft_pow4<AFX_NBIN, AFX_NFFT, false>(bufA, bufB, P.t.tw2048, tid, ST);
   double* mag = reinterpret_cast<double*>(Z == bufA ? bufB : bufA);
-  double* gmag = B.mag + (size_t)slot * AFX_NBIN;
+  double* gmag = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
   for (int k = tid; k < AFX_NBIN; k += ST) {
     const double2 zk = Z[k], zm = cconj(Z[(AFX_NBIN - k) & (AFX_NBIN - 1)]);
     const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y + zm.y));
@@ -188,13 +188,13 @@ __global__ void __launch_bounds__(ST) k_spectrum(AfxBatchDev B, AfxParams P, uns
 __global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P)
 {
   const int lane = threadIdx.x & 31;
-  const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (slot >= B.TF) return;
+  const int slot = B.slot0 + blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (slot >= B.slot0 + B.g_slots) return;
   const int fi = find_file_by_frame(B.files, B.n_files, slot);
   const AfxFile f = B.files[fi];
   const int t = slot - f.frame_off;
   if (f.status != 0 || t >= B.state[fi].F) return;
-  const double* a = B.mag + (size_t)slot * AFX_NBIN + P.first_bin;
+  const double* a = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN + P.first_bin;
   const double* b = (t > 0) ? a - AFX_NBIN : a;
   double s1 = 0, s2 = 0, s11 = 0, s12 = 0, s22 = 0;
   for (int j = lane; j < P.nbins; j += 32) {
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P)
 
 void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, long long* launches)
 {
-  if (B.TF <= 0) return;
-  k_spectrum<<<B.TF, ST, 0, s>>>(B, P, features); ++*launches;
-  k_flux<<<(B.TF + 7) / 8, 256, 0, s>>>(B, P); ++*launches;
+  if (B.g_slots <= 0) return;
+  k_spectrum<<<B.g_slots, ST, 0, s>>>(B, P, features); ++*launches;
+  k_flux<<<(B.g_slots + 7) / 8, 256, 0, s>>>(B, P); ++*launches;
 }

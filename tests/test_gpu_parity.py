@@ -146,3 +146,42 @@ def test_large_batch_properties(analysers, feats):
             assert np.array_equal(a, b)
         for a, b in zip(g.fv, s.fv):
             assert np.array_equal(a, b)
+
+
+def test_launch_groups_do_not_change_results(feats, monkeypatch):
+    """The frame-level kernels run group by group over a bounded scratch (afx_api.cu); results must not
+    depend on where the group boundaries fall."""
+    pcms = [synth.one_shot(800 + i, 0.4 + 0.35 * i) for i in range(7)]
+    pcms.insert(3, np.zeros((0,), dtype=np.int16))           # a rejected file inside a group
+    rates = [44100] * len(pcms)
+    whole = api.SampleAnalyser(44100, 2048, 1024, features=feats)
+    want = whole.analyze_pcm(pcms, rates)
+    whole.close()
+    monkeypatch.setenv("AFX_GROUP_FRAMES", "60")
+    monkeypatch.setenv("AFX_GROUP_RFRAMES", "500")
+    split = api.SampleAnalyser(44100, 2048, 1024, features=feats)
+    got = split.analyze_pcm(pcms, rates)
+    split.close()
+    for g, w in zip(got, want):
+        assert g.status == w.status and (g.F, g.Fr) == (w.F, w.Fr)
+        assert np.array_equal(g.header, w.header)
+        for a, b in zip(g.fs + g.fv, w.fs + w.fv):
+            assert np.array_equal(a, b)
+        assert np.array_equal(g.stats, w.stats)
+
+
+def test_resampled_batch_vs_oracle(analysers, feats, oracle_lib):
+    """Files at other rates go through the libresample restatement (SampleAnalyser.cpp:563-607)."""
+    cases = [(synth.one_shot(900, 0.5, rate=96000, channels=2), 96000), (synth.one_shot(901, 0.6, rate=22050), 22050),
+             (synth.one_shot(902, 0.7, rate=48000), 48000), (synth.one_shot(903, 0.5), 44100),
+             (synth.one_shot(904, 0.3, rate=8000), 8000), (synth.one_shot(900, 0.5, rate=96000, channels=2), 96000)]
+    an = analysers(1024)
+    b = an.batch([c[0] for c in cases], [c[1] for c in cases]).run()
+    for i, (p, r) in enumerate(cases):
+        data, off, pk, rms = oracle_lib.condition(p, src_rate=r)
+        got = b.conditioned(i)
+        assert got.shape == data.shape
+        assert np.array_equal(got, data), "resampled + conditioned signal of case %d differs" % i
+        want = oracle_lib.analyze(p, src_rate=r, file_size=44 + p.size * 2)
+        check(b.result(i), want, feats)
+    b.free()
