@@ -65,7 +65,39 @@ def build(force: bool = False, verbose: bool = False) -> str:
             list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
         run([NVCC] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs + ["-cudart", "static"])
+    build_host(force=force or bool(jobs), verbose=verbose)
     return LIB
+
+
+HOST = os.path.join(HERE, "host")
+HOST_LIB = os.path.join(HOST, "libafec_b200_host.so")
+CRAWLER = os.path.join(HOST, "afec-b200-crawler")
+HOST_SOURCES = ["descriptors.cpp", "sqlite_pool.cpp", "wav_reader.cpp", "gpu_analyser.cpp", "capi.cpp"]
+SQLITE = "/usr/lib/x86_64-linux-gnu/libsqlite3.so.0"
+
+
+def build_host(force: bool = False, verbose: bool = False):
+    """C++ host adapter (reference extractor interface + afec-ll.db sink) and the crawler executable."""
+    srcs = [os.path.join(HOST, s) for s in HOST_SOURCES]
+    deps = srcs + [os.path.join(HOST, h) for h in os.listdir(HOST) if h.endswith(".h")] + [
+        os.path.join(os.path.dirname(HERE), "include", "afec_b200.h"), LIB, os.path.abspath(__file__)]
+    cxx = os.environ.get("CXX", "g++")
+    common = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-pthread"]
+    rpath = ["-Wl,-rpath,$ORIGIN/../csrc", "-Wl,-rpath,$ORIGIN"]
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0 or verbose:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("host build failed: " + cmd[-1])
+
+    if force or _stale(HOST_LIB, deps):
+        run([cxx] + common + ["-shared", "-o", HOST_LIB] + srcs + ["-L" + CSRC, "-lafec_b200", SQLITE] + rpath)
+    if force or _stale(CRAWLER, deps + [os.path.join(HOST, "crawler_main.cpp"), HOST_LIB]):
+        run([cxx] + common + ["-o", CRAWLER, os.path.join(HOST, "crawler_main.cpp"), "-L" + HOST, "-lafec_b200_host",
+                              "-L" + CSRC, "-lafec_b200", SQLITE] + rpath)
+    return HOST_LIB
 
 
 if __name__ == "__main__":

@@ -1,0 +1,79 @@
+// Small C entry points over the host classes, for language bindings and tests (ctypes).
+#include "afx_host.h"
+
+#include <cstring>
+
+using namespace afec;
+
+extern "C" {
+
+// number of columns and the CREATE TABLE column list ("name TYPE,name TYPE,...")
+int afxh_schema(char* out, int cap)
+{
+  std::string s;
+  const auto cols = TSqliteSampleDescriptorPool::ColumnNamesAndTypes();
+  for (size_t i = 0; i < cols.size(); ++i) { if (i) s += ","; s += cols[i]; }
+  if (out && cap > 0) { strncpy(out, s.c_str(), (size_t)cap - 1); out[cap - 1] = 0; }
+  return (int)s.size();
+}
+
+// write one row from flat arrays laid out like afx_file_result (header[32], fs concatenated, fv concatenated,
+// stats[136][13]) -- lets the sink be tested without a GPU.  status_reason != NULL writes a failed row.
+int afxh_write_row(const char* db, const char* base_path, const char* filename, const char* file_type,
+                   int n_frames, int n_rhythm_frames, const double* header, const double* fs, const double* fv,
+                   const double* stats, const char* failed_reason)
+{
+  try {
+    TSqliteSampleDescriptorPool pool;
+    if (!pool.Open(db)) return -1;
+    if (base_path && *base_path) pool.SetBasePath(base_path);
+    if (failed_reason) { pool.InsertFailedSample(filename, failed_reason); return 0; }
+    TSampleDescriptors d;
+    d.mFileName = filename; d.mFileType = file_type ? file_type : "";
+    d.mFrames = n_frames; d.mRhythmFrames = n_rhythm_frames;
+    memcpy(d.mHeader, header, sizeof(d.mHeader));
+    const double* p = fs;
+    for (int s = 0; s < AFX_N_FS; ++s) { const int n = s < AFX_N_FS_MAIN ? n_frames : n_rhythm_frames; d.mFramedScalars[s].assign(p, p + n); p += n; }
+    p = fv;
+    for (int v = 0; v < AFX_N_FV; ++v) { const size_t n = (size_t)n_frames * kFramedVectorBands[v]; d.mFramedVectors[v].assign(p, p + n); p += n; }
+    memcpy(d.mStats, stats, sizeof(d.mStats));
+    pool.InsertSample(filename, d);
+    return 0;
+  } catch (const std::exception&) { return -2; }
+}
+
+// run the batched extractor over a list of files; returns failed count or < 0
+int afxh_extract_files(const char* db, const char* base_path, const char* const* files, int n_files, int hop,
+                       const int* devices, int n_devices, int slots_per_device, double* audio_seconds, double* seconds,
+                       long long* main_frames)
+{
+  try {
+    TSqliteSampleDescriptorPool pool;
+    if (!pool.Open(db)) return -1;
+    if (base_path && *base_path) pool.SetBasePath(base_path);
+    std::vector<int> dev(devices, devices + n_devices);
+    TGpuSampleAnalyser an(44100, 2048, hop, dev, slots_per_device);
+    std::vector<std::string> names(files, files + n_files);
+    std::mutex lock; TGpuSampleAnalyser::TProgress pr;
+    const int failed = an.ExtractBatch(names, &pool, lock, &pr);
+    if (audio_seconds) *audio_seconds = pr.mAudioSeconds;
+    if (seconds) *seconds = pr.mSeconds;
+    if (main_frames) *main_frames = pr.mMainFrames;
+    return failed;
+  } catch (const std::exception&) { return -2; }
+}
+
+// TSampleAnalyser::Extract on one file (single-file entry point)
+int afxh_extract_one(const char* db, const char* filename, int hop, int device)
+{
+  try {
+    TSqliteSampleDescriptorPool pool;
+    if (!pool.Open(db)) return -1;
+    TGpuSampleAnalyser an(44100, 2048, hop, std::vector<int>(1, device), 1);
+    std::mutex lock;
+    an.Extract(filename, &pool, lock);
+    return 0;
+  } catch (const std::exception&) { return -2; }
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// afec-b200-crawler: a minimal stand-in for `Crawler -l low -o afec-ll.db <paths...>` (Crawler.cpp:136-386,
+// 566-760) that drives the GPU path: collect files, build the change list against the database's modtimes
+// (Crawler.cpp:934-998), analyse in batches on the listed devices, write afec-ll.db.
+// Only the low-level set is produced (classification stays with the reference's host tools) and only WAV is
+// decoded here (FLAC / Ogg / MP3 decoding is the reference's CoreFileFormats, outside this path).
+#include "afx_host.h"
+
+#include <algorithm>
+#include <csignal>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dirent.h>
+#include <map>
+#include <sys/stat.h>
+
+using namespace afec;
+
+static volatile bool sAbort = false;
+static void on_sigint(int) { sAbort = true; }
+
+static bool is_dir(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
+static bool has_audio_ext(const std::string& p)
+{
+  std::string e = ExtractFileExtension(p);
+  std::transform(e.begin(), e.end(), e.begin(), ::tolower);
+  return e == "wav";
+}
+static void collect(const std::string& path, std::vector<std::string>& out)
+{
+  if (!is_dir(path)) { if (has_audio_ext(path)) out.push_back(path); return; }
+  DIR* d = opendir(path.c_str());
+  if (!d) return;
+  std::vector<std::string> names;
+  while (dirent* e = readdir(d)) { if (e->d_name[0] != '.') names.push_back(e->d_name); }
+  closedir(d);
+  std::sort(names.begin(), names.end());
+  for (const auto& n : names) collect(path + (path.back() == '/' ? "" : "/") + n, out);
+}
+static std::string abs_path(const std::string& p)
+{
+  char buf[4096];
+  return realpath(p.c_str(), buf) ? std::string(buf) : p;
+}
+
+int main(int argc, char** argv)
+{
+  std::string out_db = "afec-ll.db", level = "low";
+  int hop = 1024, slots = 2; std::vector<int> devices(1, 0); std::vector<std::string> paths;
+  bool quiet = false;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(1); } return argv[++i]; };
+    if (a == "-o" || a == "--out") out_db = next();
+    else if (a == "-l" || a == "--level") level = next();
+    else if (a == "-j" || a == "--jobs") slots = std::max(1, atoi(next().c_str()));
+    else if (a == "--hop") hop = atoi(next().c_str());
+    else if (a == "--devices") { devices.clear(); std::string s = next(); size_t p = 0; while (p <= s.size()) { size_t q = s.find(',', p); if (q == std::string::npos) q = s.size(); if (q > p) devices.push_back(atoi(s.substr(p, q - p).c_str())); p = q + 1; } }
+    else if (a == "-q") quiet = true;
+    else if (a == "-h" || a == "--help") {
+      printf("usage: %s [-l low] [-o afec-ll.db] [-j slots-per-gpu] [--hop 1024] [--devices 0,1,..] <file-or-dir>...\n", argv[0]);
+      return 0;
+    } else if (!a.empty() && a[0] == '-') { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
+    else paths.push_back(a);
+  }
+  if (level != "low") { fprintf(stderr, "only --level low runs on the GPU path (high-level classification stays with the reference Crawler)\n"); return 1; }
+  if (paths.empty()) { fprintf(stderr, "no input paths\n"); return 1; }
+  signal(SIGINT, on_sigint);
+  try {
+    std::vector<std::string> files;
+    for (const auto& p : paths) collect(abs_path(p), files);
+    TSqliteSampleDescriptorPool pool;
+    const std::string db_abs = abs_path(out_db).empty() ? out_db : out_db;
+    if (!pool.Open(db_abs)) { fprintf(stderr, "failed to open database %s\n", out_db.c_str()); return 1; }
+    // file names are stored relative to the database's directory when every input lives below it
+    // (SqliteSampleDescriptorPool.cpp:1164-1188; Crawler.cpp:610-640)
+    {
+      std::string dir = abs_path(out_db);
+      const size_t s = dir.find_last_of('/');
+      dir = (s == std::string::npos) ? abs_path(".") : dir.substr(0, s);
+      if (dir.empty() || dir.back() != '/') dir += '/';
+      bool all_below = !files.empty();
+      for (const auto& f : files) if (f.compare(0, dir.size(), dir) != 0) { all_below = false; break; }
+      if (all_below) pool.SetBasePath(dir);
+    }
+    // change list: new or modified files are (re)analysed, vanished ones removed
+    std::map<std::string, int> known;
+    for (const auto& e : pool.SampleModificationDates()) known[e.first] = e.second;
+    std::vector<std::string> todo, gone;
+    for (const auto& f : files) { auto it = known.find(f); if (it == known.end() || it->second < ModificationStatTime(f)) todo.push_back(f); if (it != known.end()) known.erase(it); }
+    for (const auto& e : known) gone.push_back(e.first);
+    if (!gone.empty()) pool.RemoveSamples(gone);
+    if (!quiet) printf("%zu files found, %zu to analyse, %zu removed\n", files.size(), todo.size(), gone.size());
+    if (todo.empty()) return 0;
+    TGpuSampleAnalyser analyser(44100, 2048, hop, devices, slots);
+    std::mutex lock; TGpuSampleAnalyser::TProgress pr;
+    const int failed = analyser.ExtractBatch(todo, &pool, lock, &pr, &sAbort);
+    if (!quiet) printf("{\"files\": %lld, \"failed\": %d, \"main_frames\": %lld, \"rhythm_frames\": %lld, \"audio_seconds\": %.3f, \"seconds\": %.4f, \"audio_hours_per_s\": %.4f}\n",
+                       (long long)pr.mFiles, failed, (long long)pr.mMainFrames, (long long)pr.mRhythmFrames, pr.mAudioSeconds, pr.mSeconds,
+                       pr.mSeconds > 0 ? pr.mAudioSeconds / 3600.0 / pr.mSeconds : 0.0);
+    return sAbort ? 2 : 0;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+}

@@ -1,0 +1,45 @@
+// Minimal declarations of the public SQLite C API used by the descriptor pool.  The image ships
+// libsqlite3.so.0 (3.45) but no development header, and the reference tree's own copy is part of the
+// reference (not copied): these prototypes restate the documented, ABI-stable interface.
+#ifndef AFX_SQLITE3_MIN_H_
+#define AFX_SQLITE3_MIN_H_
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct sqlite3 sqlite3;
+typedef struct sqlite3_stmt sqlite3_stmt;
+typedef long long sqlite3_int64;
+typedef void (*sqlite3_destructor_type)(void*);
+#define SQLITE_OK 0
+#define SQLITE_ROW 100
+#define SQLITE_DONE 101
+#define SQLITE_OPEN_READONLY 0x00000001
+#define SQLITE_OPEN_READWRITE 0x00000002
+#define SQLITE_OPEN_CREATE 0x00000004
+#define SQLITE_STATIC ((sqlite3_destructor_type)0)
+#define SQLITE_TRANSIENT ((sqlite3_destructor_type)-1)
+int sqlite3_open_v2(const char* filename, sqlite3** db, int flags, const char* vfs);
+int sqlite3_close(sqlite3*);
+int sqlite3_busy_timeout(sqlite3*, int ms);
+int sqlite3_exec(sqlite3*, const char* sql, int (*cb)(void*, int, char**, char**), void*, char** errmsg);
+void sqlite3_free(void*);
+const char* sqlite3_errmsg(sqlite3*);
+int sqlite3_prepare_v2(sqlite3*, const char* sql, int nbyte, sqlite3_stmt** stmt, const char** tail);
+int sqlite3_bind_null(sqlite3_stmt*, int);
+int sqlite3_bind_int(sqlite3_stmt*, int, int);
+int sqlite3_bind_int64(sqlite3_stmt*, int, sqlite3_int64);
+int sqlite3_bind_double(sqlite3_stmt*, int, double);
+int sqlite3_bind_text(sqlite3_stmt*, int, const char*, int n, sqlite3_destructor_type);
+int sqlite3_bind_blob(sqlite3_stmt*, int, const void*, int n, sqlite3_destructor_type);
+int sqlite3_step(sqlite3_stmt*);
+int sqlite3_reset(sqlite3_stmt*);
+int sqlite3_clear_bindings(sqlite3_stmt*);
+int sqlite3_finalize(sqlite3_stmt*);
+int sqlite3_column_count(sqlite3_stmt*);
+const unsigned char* sqlite3_column_text(sqlite3_stmt*, int);
+int sqlite3_column_int(sqlite3_stmt*, int);
+sqlite3_int64 sqlite3_column_int64(sqlite3_stmt*, int);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,274 @@
+// afec-ll.db writer: the reference's TSqliteSampleDescriptorPool for the low-level descriptor set.
+// Reference: SqliteSampleDescriptorPool.cpp:1116-1350 (open / schema / version handling), :1551-1578
+// (modification dates), :1582-1651 (InsertSample), :1655-1685 (InsertFailedSample), :1696-1733 (remove);
+// Database.cpp:337-351 (pragmas).  One behavioural extension: BeginBulk / EndBulk wrap many inserts in
+// one transaction (the reference commits one per file); rows and bytes are identical.
+#include "afx_host.h"
+#include "sqlite3_min.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace afec {
+
+struct TSqliteSampleDescriptorPool::Impl {
+  sqlite3* db = nullptr;
+  sqlite3_stmt* insert = nullptr;
+  sqlite3_stmt* insert_failed = nullptr;
+  std::string file;
+  int bulk = 0;
+  std::vector<unsigned char> blob;
+};
+
+static void check(sqlite3* db, int rc, const char* what)
+{
+  if (rc != SQLITE_OK && rc != SQLITE_DONE && rc != SQLITE_ROW)
+    throw TReadableException(std::string("Database error (") + what + "): " + (db ? sqlite3_errmsg(db) : "?"));
+}
+static void exec(sqlite3* db, const std::string& sql)
+{
+  char* err = nullptr;
+  const int rc = sqlite3_exec(db, sql.c_str(), nullptr, nullptr, &err);
+  if (rc != SQLITE_OK) { std::string m = err ? err : "?"; sqlite3_free(err); throw TReadableException("Database error: " + m + " in '" + sql.substr(0, 80) + "'"); }
+}
+static long long scalar_int(sqlite3* db, const std::string& sql)
+{
+  sqlite3_stmt* st = nullptr;
+  check(db, sqlite3_prepare_v2(db, sql.c_str(), -1, &st, nullptr), "prepare");
+  long long v = 0;
+  if (sqlite3_step(st) == SQLITE_ROW) v = sqlite3_column_int64(st, 0);
+  sqlite3_finalize(st);
+  return v;
+}
+
+std::vector<std::string> TSqliteSampleDescriptorPool::ColumnNamesAndTypes()
+{
+  // Descriptors(kLowLevelDescriptors) x Values(): "<name>_<R|S|VR|VVR> <type>" (SqliteSampleDescriptorPool.cpp:1313-1350)
+  std::vector<std::string> c = { "filename TEXT PRIMARY KEY", "modtime INTEGER", "status TEXT", "file_type_S TEXT" };
+  static const char* const kHeaderTypes[9] = { "INTEGER", "REAL", "INTEGER", "INTEGER", "INTEGER", "REAL", "REAL", "REAL", "REAL" };
+  for (int i = 0; i < 9; ++i) c.push_back(std::string(kHeaderNames[i]) + "_R " + kHeaderTypes[i]);
+  auto framed = [&](int s) {
+    c.push_back(std::string(kFramedScalarNames[s]) + "_VR BLOB");
+    for (int k = 0; k < AFX_N_STATS; ++k) c.push_back(std::string(kFramedScalarNames[s]) + "_" + kStatNames[k] + "_R REAL");
+  };
+  for (int s = 0; s < AFX_N_FS_MAIN; ++s) framed(s);
+  for (int t = 0; t < 2; ++t) {                       // onsets + the six scalars of each onset type
+    framed(AFX_N_FS_MAIN + t);
+    for (int k = 0; k < 6; ++k) c.push_back(std::string(kHeaderNames[9 + 6 * t + k]) + "_R REAL");
+  }
+  c.push_back("rhythm_final_tempo_R REAL"); c.push_back("rhythm_final_tempo_confidence_R REAL");
+  for (int v = 0; v < AFX_N_FV; ++v) {
+    c.push_back(std::string(kFramedVectorNames[v]) + "_VVR BLOB");
+    for (int k = 0; k < AFX_N_STATS; ++k) c.push_back(std::string(kFramedVectorNames[v]) + "_" + kStatNames[k] + "_VR BLOB");
+  }
+  return c;
+}
+
+TSqliteSampleDescriptorPool::TSqliteSampleDescriptorPool() : mImpl(new Impl()) {}
+TSqliteSampleDescriptorPool::~TSqliteSampleDescriptorPool() { Close(); }
+
+void TSqliteSampleDescriptorPool::Close()
+{
+  Impl& I = *mImpl;
+  if (!I.db) return;
+  if (I.bulk) { try { exec(I.db, "COMMIT"); } catch (...) {} I.bulk = 0; }
+  if (I.insert) sqlite3_finalize(I.insert);
+  if (I.insert_failed) sqlite3_finalize(I.insert_failed);
+  I.insert = I.insert_failed = nullptr;
+  sqlite3_close(I.db);
+  I.db = nullptr;
+}
+
+static bool open_db(sqlite3** db, const std::string& name, bool ro)
+{
+  const int flags = ro ? SQLITE_OPEN_READONLY : (SQLITE_OPEN_READWRITE | SQLITE_OPEN_CREATE);
+  if (sqlite3_open_v2(name.c_str(), db, flags, nullptr) != SQLITE_OK) { if (*db) sqlite3_close(*db); *db = nullptr; return false; }
+  sqlite3_busy_timeout(*db, 60000);
+  if (!ro) {                                            // Database.cpp:337-351
+    exec(*db, "PRAGMA encoding = utf8;");
+    exec(*db, "PRAGMA journal_mode = WAL;");
+    exec(*db, "PRAGMA synchronous = NORMAL;");
+  }
+  return true;
+}
+
+bool TSqliteSampleDescriptorPool::Open(const std::string& DatabaseName, bool ReadOnly)
+{
+  Close();
+  Impl& I = *mImpl;
+  I.file = DatabaseName;
+  if (!open_db(&I.db, DatabaseName, ReadOnly)) return false;
+  if (ReadOnly) return true;
+  // InitializeDatabase, SqliteSampleDescriptorPool.cpp:1224-1366
+  bool create = false;
+  if (scalar_int(I.db, "SELECT count(name) FROM sqlite_master WHERE type='table' AND name='assets'") != 1) create = true;
+  else {
+    const int version = (int)scalar_int(I.db, "PRAGMA user_version");
+    if (version > kCurrentVersion)
+      throw TReadableException("Unknown database version: " + std::to_string(version) + ". The database maybe got created by a newer version of the crawler.");
+    if (version < kCurrentVersion) {                    // older layout: drop everything and start over
+      create = true;
+      sqlite3_close(I.db); I.db = nullptr;
+      const bool deleted = (unlink(DatabaseName.c_str()) == 0);
+      unlink((DatabaseName + "-wal").c_str()); unlink((DatabaseName + "-shm").c_str());
+      if (!open_db(&I.db, DatabaseName, false)) throw TReadableException("Failed to (re)open the database file for upgrading.");
+      if (!deleted) { try { exec(I.db, "DROP table 'assets'"); exec(I.db, "VACUUM"); } catch (...) {} }
+    }
+  }
+  if (create) {
+    exec(I.db, "BEGIN");
+    exec(I.db, "PRAGMA user_version = '" + std::to_string((int)kCurrentVersion) + "'");
+    std::string sql = "CREATE TABLE assets(";
+    const std::vector<std::string> cols = ColumnNamesAndTypes();
+    for (size_t i = 0; i < cols.size(); ++i) { if (i) sql += ","; sql += cols[i]; }
+    sql += ")";
+    exec(I.db, sql);
+    exec(I.db, "COMMIT");
+  }
+  return true;
+}
+
+void TSqliteSampleDescriptorPool::SetBasePath(const std::string& BasePath)
+{
+  mBasePath = BasePath;
+  if (!mBasePath.empty() && mBasePath.back() != '/') mBasePath += '/';
+}
+
+std::string TSqliteSampleDescriptorPool::RelativeFilenamePath(const std::string& FileName) const
+{
+  if (!mBasePath.empty() && FileName.compare(0, mBasePath.size(), mBasePath) == 0) return FileName.substr(mBasePath.size());
+  return FileName;
+}
+
+bool TSqliteSampleDescriptorPool::IsEmpty() const { return NumberOfSamples() == 0; }
+int TSqliteSampleDescriptorPool::NumberOfSamples() const
+{
+  return mImpl->db ? (int)scalar_int(mImpl->db, "SELECT count(*) FROM assets") : 0;
+}
+
+std::vector<std::pair<std::string, int>> TSqliteSampleDescriptorPool::SampleModificationDates() const
+{
+  std::vector<std::pair<std::string, int>> ret;
+  sqlite3_stmt* st = nullptr;
+  check(mImpl->db, sqlite3_prepare_v2(mImpl->db, "SELECT filename, modtime FROM assets", -1, &st, nullptr), "prepare");
+  while (sqlite3_step(st) == SQLITE_ROW) {
+    std::string name = (const char*)sqlite3_column_text(st, 0);
+    if (!mBasePath.empty() && name.compare(0, mBasePath.size(), mBasePath) != 0) name = mBasePath + name;
+    ret.push_back({ name, sqlite3_column_int(st, 1) });
+  }
+  sqlite3_finalize(st);
+  return ret;
+}
+
+void TSqliteSampleDescriptorPool::BeginBulk() { if (mImpl->bulk++ == 0) exec(mImpl->db, "BEGIN"); }
+void TSqliteSampleDescriptorPool::EndBulk() { if (mImpl->bulk > 0 && --mImpl->bulk == 0) exec(mImpl->db, "COMMIT"); }
+
+void TSqliteSampleDescriptorPool::InsertSample(const std::string& FileName, const TSampleDescriptors& R)
+{
+  Impl& I = *mImpl;
+  if (!I.db) throw TReadableException("Database is not open");
+  const std::vector<std::string> cols = ColumnNamesAndTypes();
+  if (!I.insert) {
+    std::string sql = "INSERT OR REPLACE into assets(", q;
+    for (size_t i = 0; i < cols.size(); ++i) {
+      if (i) { sql += ","; q += ","; }
+      sql += cols[i].substr(0, cols[i].find(' ')); q += "?";
+    }
+    sql += ") values(" + q + ")";
+    check(I.db, sqlite3_prepare_v2(I.db, sql.c_str(), -1, &I.insert, nullptr), "prepare insert");
+  }
+  sqlite3_stmt* st = I.insert;
+  const std::string rel = RelativeFilenamePath(FileName);
+  const bool own_txn = (I.bulk == 0);
+  if (own_txn) exec(I.db, "BEGIN");
+  try {
+    int p = 1;
+    sqlite3_bind_text(st, p++, rel.c_str(), -1, SQLITE_TRANSIENT);
+    sqlite3_bind_int(st, p++, ModificationStatTime(FileName));
+    sqlite3_bind_text(st, p++, "succeeded", -1, SQLITE_STATIC);
+    sqlite3_bind_text(st, p++, R.mFileType.c_str(), -1, SQLITE_TRANSIENT);
+    sqlite3_bind_int(st, p++, (int)R.mHeader[0]);        // file_size
+    sqlite3_bind_double(st, p++, R.mHeader[1]);          // file_length
+    sqlite3_bind_int(st, p++, (int)R.mHeader[2]);
+    sqlite3_bind_int(st, p++, (int)R.mHeader[3]);
+    sqlite3_bind_int(st, p++, (int)R.mHeader[4]);
+    for (int k = 5; k < 9; ++k) sqlite3_bind_double(st, p++, R.mHeader[k]);
+    auto framed = [&](int s) {
+      PackVR(I.blob, R.mFramedScalars[s].data(), R.mFramedScalars[s].size());
+      sqlite3_bind_blob(st, p++, I.blob.data(), (int)I.blob.size(), SQLITE_TRANSIENT);
+      for (int k = 0; k < AFX_N_STATS; ++k) sqlite3_bind_double(st, p++, R.mStats[s][k]);
+    };
+    for (int s = 0; s < AFX_N_FS_MAIN; ++s) framed(s);
+    for (int t = 0; t < 2; ++t) {
+      framed(AFX_N_FS_MAIN + t);
+      for (int k = 0; k < 6; ++k) sqlite3_bind_double(st, p++, R.mHeader[9 + 6 * t + k]);
+    }
+    sqlite3_bind_double(st, p++, R.mHeader[21]); sqlite3_bind_double(st, p++, R.mHeader[22]);
+    int series = AFX_N_FS;
+    for (int v = 0; v < AFX_N_FV; ++v) {
+      const int nb = kFramedVectorBands[v];
+      PackVVR(I.blob, R.mFramedVectors[v].data(), (size_t)R.mFrames, (size_t)nb);
+      sqlite3_bind_blob(st, p++, I.blob.data(), (int)I.blob.size(), SQLITE_TRANSIENT);
+      double col[28];
+      for (int k = 0; k < AFX_N_STATS; ++k) {
+        for (int b = 0; b < nb; ++b) col[b] = R.mStats[series + b][k];
+        PackVR(I.blob, col, (size_t)nb);
+        sqlite3_bind_blob(st, p++, I.blob.data(), (int)I.blob.size(), SQLITE_TRANSIENT);
+      }
+      series += nb;
+    }
+    const int rc = sqlite3_step(st);
+    sqlite3_reset(st); sqlite3_clear_bindings(st);
+    check(I.db, rc, "insert");
+    if (own_txn) exec(I.db, "COMMIT");
+  } catch (...) {
+    sqlite3_reset(st); sqlite3_clear_bindings(st);
+    if (own_txn) { try { exec(I.db, "ROLLBACK"); } catch (...) {} }
+    throw;
+  }
+}
+
+void TSqliteSampleDescriptorPool::InsertFailedSample(const std::string& FileName, const std::string& Reason)
+{
+  Impl& I = *mImpl;
+  if (!I.db) throw TReadableException("Database is not open");
+  if (!I.insert_failed)
+    check(I.db, sqlite3_prepare_v2(I.db, "INSERT OR REPLACE into assets(filename, modtime, status) values (?,?,?)", -1, &I.insert_failed, nullptr), "prepare");
+  sqlite3_stmt* st = I.insert_failed;
+  const std::string rel = RelativeFilenamePath(FileName), status = "error: " + Reason;
+  const bool own_txn = (I.bulk == 0);
+  if (own_txn) exec(I.db, "BEGIN");
+  sqlite3_bind_text(st, 1, rel.c_str(), -1, SQLITE_TRANSIENT);
+  sqlite3_bind_int(st, 2, ModificationStatTime(FileName));
+  sqlite3_bind_text(st, 3, status.c_str(), -1, SQLITE_TRANSIENT);
+  const int rc = sqlite3_step(st);
+  sqlite3_reset(st); sqlite3_clear_bindings(st);
+  if (own_txn) exec(I.db, (rc == SQLITE_DONE) ? "COMMIT" : "ROLLBACK");
+  check(I.db, rc, "insert failed sample");
+}
+
+void TSqliteSampleDescriptorPool::RemoveSample(const std::string& FileName) { RemoveSamples(std::vector<std::string>(1, FileName)); }
+
+void TSqliteSampleDescriptorPool::RemoveSamples(const std::vector<std::string>& FileNames)
+{
+  Impl& I = *mImpl;
+  sqlite3_stmt* st = nullptr;
+  // the reference matches with a case-folding MATCH operator; Linux file names are case sensitive: '='
+  check(I.db, sqlite3_prepare_v2(I.db, "DELETE from assets WHERE filename = ?", -1, &st, nullptr), "prepare delete");
+  size_t i = 0;
+  while (i < FileNames.size()) {                          // batches of 100, :1713-1725
+    exec(I.db, "BEGIN");
+    for (int k = 0; k < 100 && i < FileNames.size(); ++k, ++i) {
+      const std::string rel = RelativeFilenamePath(FileNames[i]);
+      sqlite3_bind_text(st, 1, rel.c_str(), -1, SQLITE_TRANSIENT);
+      sqlite3_step(st); sqlite3_reset(st);
+    }
+    exec(I.db, "COMMIT");
+  }
+  sqlite3_finalize(st);
+}
+
+}  // namespace afec

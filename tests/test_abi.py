@@ -55,3 +55,13 @@ def test_bad_config_rejected(lib_path):
                 api.AfxConfig(0, 44100, 2048, 1000, 0xFF, 0)):
         assert L.afx_create(ctypes.byref(cfg), ctypes.byref(ctx)) == -1
         assert b"afx_create" in L.afx_last_error(None)
+
+
+def test_host_adapter_library_loads(lib_path):
+    """The C++ host adapter (reference extractor interface + sqlite sink) links against the CUDA library
+    and exports its C entry points; the crawler executable exists."""
+    from afec_b200 import build
+    host = ctypes.CDLL(build.HOST_LIB)
+    for s in ("afxh_schema", "afxh_write_row", "afxh_extract_files", "afxh_extract_one"):
+        assert hasattr(host, s), "missing export " + s
+    assert os.access(build.CRAWLER, os.X_OK)

@@ -1,0 +1,111 @@
+"""The host-side sink (afec_b200/host: TSqliteSampleDescriptorPool, msgpack packing) against a database
+written by the unmodified reference (tests/golden/ref_ll.db).  No GPU needed: rows are fed from the CPU
+oracle's values through afxh_write_row."""
+import ctypes as C
+import os
+import sqlite3
+
+import msgpack
+import numpy as np
+import pytest
+
+import db_cases
+import dbcompare
+from afec_b200 import build as afx_build
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_ll.db")
+
+
+@pytest.fixture(scope="module")
+def host():
+    afx_build.build()
+    L = C.CDLL(afx_build.HOST_LIB)
+    L.afxh_schema.argtypes = [C.c_char_p, C.c_int]
+    L.afxh_write_row.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_char_p]
+    return L
+
+
+def test_schema_is_the_reference_schema(host):
+    n = host.afxh_schema(None, 0)
+    buf = C.create_string_buffer(n + 1)
+    host.afxh_schema(buf, n + 1)
+    ours = "CREATE TABLE assets(" + buf.value.decode() + ")"
+    _, ref_sql, _ = dbcompare.rows(GOLDEN)
+    assert ours == ref_sql
+    assert ours.count(",") + 1 == 461
+
+
+def write_oracle_row(host, oracle_lib, db, directory, name, pcm, rate):
+    path = os.path.join(directory, name)
+    r = oracle_lib.analyze(pcm, src_rate=rate, file_size=os.path.getsize(path))
+    fs = np.concatenate([np.ravel(a) for a in r.fs]) if r.fs else np.zeros(0)
+    fv = np.concatenate([np.ravel(a) for a in r.fv]) if r.fv else np.zeros(0)
+    hdr = np.ascontiguousarray(r.header, dtype=np.float64)
+    st = np.ascontiguousarray(r.stats, dtype=np.float64)
+    rc = host.afxh_write_row(db.encode(), (directory + "/").encode(), path.encode(), b"wav", r.F, r.Fr,
+                             hdr.ctypes.data, fs.ctypes.data, fv.ctypes.data, st.ctypes.data, None)
+    assert rc == 0
+
+
+def test_rows_match_reference_database(host, oracle_lib, tmp_path):
+    d = str(tmp_path)
+    db_cases.write_files(d)
+    db = os.path.join(d, "afec-ll.db")
+    for name, c in db_cases.cases().items():
+        if isinstance(c, bytes):
+            rc = host.afxh_write_row(db.encode(), (d + "/").encode(), os.path.join(d, name).encode(), None, 0, 0,
+                                     None, None, None, None, b"Sample failed to load: Not a valid WAV file.")
+            assert rc == 0
+        else:
+            write_oracle_row(host, oracle_lib, db, d, name, c[0], c[1])
+    got, sql, pragmas = dbcompare.rows(db)
+    want, ref_sql, _ = dbcompare.rows(GOLDEN)
+    assert sql == ref_sql
+    assert pragmas == {"user_version": 2, "encoding": "UTF-8", "journal_mode": "wal"}
+    assert set(got) == set(want)
+    for name in want:
+        errs = dbcompare.compare_row(got[name], want[name])
+        assert not errs, name + ":\n" + "\n".join(errs[:20])
+    # file names are stored relative to the base path, modtime is the file's mtime
+    c = sqlite3.connect(db)
+    names = sorted(r[0] for r in c.execute("select filename from assets"))
+    assert names == sorted(db_cases.cases())
+    mt = c.execute("select modtime from assets where filename='kick.wav'").fetchone()[0]
+    assert mt == int(os.stat(os.path.join(d, "kick.wav")).st_mtime)
+    assert c.execute("select count(*) from assets where status!='succeeded'").fetchone()[0] == 1
+    c.close()
+
+
+def test_msgpack_blobs_are_bit_exact(host, oracle_lib, tmp_path):
+    """VR / VVR BLOBs decode to exactly the doubles that went in; sizes follow msgpack-c's array16 / fixarray rules."""
+    d = str(tmp_path)
+    db_cases.write_files(d)
+    db = os.path.join(d, "x.db")
+    pcm, rate = db_cases.cases()["kick.wav"]
+    write_oracle_row(host, oracle_lib, db, d, "kick.wav", pcm, rate)
+    r = oracle_lib.analyze(pcm, src_rate=rate, file_size=os.path.getsize(os.path.join(d, "kick.wav")))
+    c = sqlite3.connect(db)
+    blob, vv, vstat = c.execute("select spectral_centroid_VR, frequency_bands_VVR, cepstrum_bands_mean_VR from assets").fetchone()
+    assert len(blob) == 3 + 9 * r.F and blob[0] == 0xdc
+    assert np.array_equal(np.array(msgpack.unpackb(blob)), r.series("spectral_centroid"))
+    assert np.array_equal(np.array(msgpack.unpackb(vv)), r.series("frequency_bands"))
+    assert len(vstat) == 1 + 9 * 14 and vstat[0] == 0x9e
+    assert np.array_equal(np.array(msgpack.unpackb(vstat)), r.series_stats("cepstrum_bands")[:, 3])
+    c.close()
+
+
+def test_old_database_versions_are_rebuilt_and_newer_refused(host, tmp_path):
+    """SqliteSampleDescriptorPool.cpp:1239-1300: user_version < 2 -> dropped and recreated, > 2 -> refused."""
+    db = str(tmp_path / "old.db")
+    c = sqlite3.connect(db)
+    c.execute("create table assets(filename text primary key, junk integer)")
+    c.execute("insert into assets values('x', 1)")
+    c.execute("pragma user_version = 1")
+    c.commit(); c.close()
+    rc = host.afxh_write_row(db.encode(), b"", b"/nonexistent/f.wav", None, 0, 0, None, None, None, None, b"Sample failed to load: x")
+    assert rc == 0
+    c = sqlite3.connect(db)
+    assert c.execute("pragma user_version").fetchone()[0] == 2
+    assert [r[0] for r in c.execute("select filename from assets")] == ["/nonexistent/f.wav"]
+    c.execute("pragma user_version = 3"); c.commit(); c.close()
+    assert host.afxh_write_row(db.encode(), b"", b"/nonexistent/g.wav", None, 0, 0, None, None, None, None, b"x") == -2
