@@ -24,7 +24,7 @@ EXPORTS = [
     "afx_abi_version", "afx_create", "afx_destroy", "afx_last_error", "afx_host_alloc", "afx_host_free",
     "afx_batch_create", "afx_batch_upload", "afx_batch_compute", "afx_batch_download", "afx_batch_sync",
     "afx_analyze", "afx_batch_result", "afx_batch_free", "afx_batch_timings", "afx_batch_counters",
-    "afx_batch_kernel_times", "afx_batch_conditioned", "afx_measure_fp64_peak",
+    "afx_batch_kernel_times", "afx_batch_conditioned", "afx_measure_fp64_peak", "afx_debug_fft",
 ]
 
 
@@ -82,6 +82,7 @@ def load_library():
     L.afx_batch_conditioned.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     L.afx_batch_conditioned.restype = C.c_int64
     L.afx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.afx_debug_fft.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -254,6 +255,15 @@ class SampleAnalyser:
         v = C.c_double()
         self._check(self._L.afx_measure_fp64_peak(self._ctx, C.byref(v)))
         return v.value
+
+    def debug_fft(self, x: np.ndarray) -> np.ndarray:
+        """Forward FFT of complex128 rows [batch, n] (n = 256 / 1024 / 2048) through the kernels' FFT core."""
+        a = np.ascontiguousarray(x, dtype=np.complex128)
+        if a.ndim == 1:
+            a = a[None, :]
+        out = np.empty_like(a)
+        self._check(self._L.afx_debug_fft(self._ctx, a.shape[1], a.shape[0], a.ctypes.data, out.ctypes.data))
+        return out
 
     def pinned(self, nbytes: int) -> PinnedArena:
         return PinnedArena(self, nbytes)

@@ -793,6 +793,24 @@ extern "C" int64_t afx_batch_conditioned(const afx_batch* b, int32_t i, double* 
   return st.len;
 }
 
+// ---- test hook: the FFT core on caller data -------------------------------------------------------------
+int afx_debug_fft_launch(int n, int batch, const double2* in, double2* out, const double2* tw2048, cudaStream_t s);
+extern "C" int afx_debug_fft(afx_ctx* ctx, int32_t n, int32_t batch, const double* in, double* out)
+{
+  if (!ctx || !in || !out || batch <= 0 || (n != 256 && n != 1024 && n != 2048)) return fail(ctx, AFX_ERR_ARG, "afx_debug_fft: bad arguments");
+  cudaSetDevice(ctx->device);
+  const size_t bytes = (size_t)n * batch * 16;
+  double2 *di = nullptr, *dout = nullptr;
+  CK(cudaMalloc(&di, bytes), "cudaMalloc"); CK(cudaMalloc(&dout, bytes), "cudaMalloc");
+  cudaMemcpy(di, in, bytes, cudaMemcpyHostToDevice);
+  afx_debug_fft_launch(n, batch, di, dout, ctx->P.t.tw2048, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(di); cudaFree(dout);
+  if (e != cudaSuccess) return fail(ctx, AFX_ERR_CUDA, "afx_debug_fft", e);
+  return AFX_OK;
+}
+
 // ---- FP64 FMA peak (roofline denominator) -----------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters)
 {

@@ -7,27 +7,50 @@
 // with itself for lags 0..528 (R[i] = sum_{j < 529-i} x[j] x[j+i]), normalise by R[0] and report the
 // largest coefficient at lags >= period / 2.
 //
-// One CTA of 288 threads per frame; lags i and width-1-i are paired so every thread sums ~width+1
-// products.  The window (<= 1024 + 35 + 1024 + 1 samples are searched, 529 correlated) sits in
-// shared memory as FP64.
+// One WARP per frame, 8 frames per CTA, no block-wide barrier.  The two searches read the signal
+// straight from global memory in 32-sample steps (they nearly always stop in the first step); only the
+// 529-sample window goes to shared memory.  The 140k multiply-adds per frame are register tiled: a lane
+// owns 9 consecutive lags and slides a 9-sample window along j, so every pair of shared-memory loads
+// feeds 9 DFMAs (the FP64 pipe, not shared memory, is the limit); lag groups g and G-1-g are paired so
+// that all lanes carry the same number of products.
 #include "afx_common.cuh"
 
-#define AT 288
-#define AC_SPAN (1024 + 64 + 1024 + 8)
+#define AW 8                // warps (frames) per CTA
+#define AL 9                // lags per lane task
+#define AC_MAXW 544         // >= ac_width (529) + AL, multiple of 8
 
-__global__ void __launch_bounds__(AT) k_autocorr(AfxBatchDev B, AfxParams P)
+// returns max(R[i]) over the group's lags i with lo <= i < width; the group holding lag 0 also reports R[0]
+__device__ __forceinline__ double ac_group(const double* __restrict__ x, int width, int g, int lo, double& r0)
 {
-  __shared__ double xs[AC_SPAN];
-  __shared__ double R[544];
-  __shared__ int iscr[32];
-  __shared__ double dscr[32];
-  __shared__ int s_file;
+  const int i0 = g * AL;
+  const int nj = width - i0;            // products of the group's first lag; later lags read the zero padding
+  double acc[AL], w[AL];
+#pragma unroll
+  for (int q = 0; q < AL; ++q) { acc[q] = 0.0; w[q] = x[i0 + q]; }
+  for (int j = 0; j < nj; ++j) {
+    const double a = x[j];
+#pragma unroll
+    for (int q = 0; q < AL; ++q) acc[q] = fma(a, w[q], acc[q]);
+#pragma unroll
+    for (int q = 0; q < AL - 1; ++q) w[q] = w[q + 1];
+    w[AL - 1] = x[j + i0 + AL];
+  }
+  if (g == 0) r0 = acc[0];
+  double best = 0.0;
+#pragma unroll
+  for (int q = 0; q < AL; ++q) if (i0 + q < width && i0 + q >= lo) best = fmax(best, acc[q]);
+  return best;
+}
 
-  const int tid = threadIdx.x;
-  const int slot = B.slot0 + blockIdx.x;
-  if (tid == 0) s_file = find_file_by_frame(B.files, B.n_files, slot);
-  __syncthreads();
-  const int fi = s_file;
+__global__ void __launch_bounds__(AW * 32) k_autocorr(AfxBatchDev B, AfxParams P)
+{
+  __shared__ double xs[AW][AC_MAXW + 2 * AL + 8];
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rel = blockIdx.x * AW + wid;
+  if (rel >= B.g_slots) return;                    // warp-uniform; only warp-level sync below
+  const int slot = B.slot0 + rel;
+  const int fi = find_file_by_frame(B.files, B.n_files, slot);
   const AfxFile f = B.files[fi];
   const AfxState st = B.state[fi];
   const int t = slot - f.frame_off;
@@ -35,53 +58,56 @@ __global__ void __launch_bounds__(AT) k_autocorr(AfxBatchDev B, AfxParams P)
   const int n0 = t * P.H;
   const float* __restrict__ mono = B.mono + f.mono_off;
   int remaining = st.len - n0;                                   // SampleAnalyser.cpp:943
-  const int span = min(remaining, AC_SPAN);
-  for (int k = tid; k < span; k += AT) xs[k] = mdata(mono, st, n0 + k);
-  __syncthreads();
-
   const int max_seek = P.N / 2;
+
   // first rising pair (SampleAnalyser.cpp:2331-2341)
-  int cand = 0x7fffffff;
-  { const int lim = min(remaining, max_seek) - 1;
-    for (int i = tid; i < lim; i += AT) if (xs[i + 1] > xs[i]) { cand = i; break; } }
-  cand = block_min_i(cand, iscr);
   int start = 0;
-  if (cand != 0x7fffffff) { start = cand; remaining -= cand; }
+  {
+    const int lim = min(remaining, max_seek) - 1;
+    for (int base = 0; base < lim; base += 32) {
+      const int i = base + lane;
+      const bool hit = (i < lim) && (mdata(mono, st, n0 + i + 1) > mdata(mono, st, n0 + i));
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) { start = base + __ffs(m) - 1; remaining -= start; break; }
+    }
+  }
   // next rising pair at least min_period later (SampleAnalyser.cpp:2344-2356)
   const int seek_off = min(remaining, P.ac_min_period);
-  int cand2 = 0x7fffffff;
-  { const int lim = min(remaining - seek_off, max_seek) - 1;
-    for (int i = tid; i < lim; i += AT) if (xs[start + seek_off + i + 1] > xs[start + seek_off + i]) { cand2 = i; break; } }
-  cand2 = block_min_i(cand2, iscr);
-  const int period = (cand2 != 0x7fffffff) ? seek_off + cand2 : seek_off;
+  int period = seek_off;
+  {
+    const int lim = min(remaining - seek_off, max_seek) - 1;
+    const int o = n0 + start + seek_off;
+    for (int base = 0; base < lim; base += 32) {
+      const int i = base + lane;
+      const bool hit = (i < lim) && (mdata(mono, st, o + i + 1) > mdata(mono, st, o + i));
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) { period = seek_off + base + __ffs(m) - 1; break; }
+    }
+  }
   double* out = B.fs + (size_t)FS_AUTOCORR * B.TF + slot;
-  if (!remaining || period >= remaining) { if (tid == 0) *out = 0.0; return; }   // :2361-2365
+  if (!remaining || period >= remaining) { if (lane == 0) *out = 0.0; return; }   // :2361-2365
 
   const int width = min(remaining, P.ac_width);
-  const double* x = xs + start;
-  // lags tid and width-1-tid
-  for (int lag = tid; lag < (width + 1) / 2; lag += AT) {
-    const int lag2 = width - 1 - lag;
-    double a = 0.0, b = 0.0;
-    const int na = width - lag, nb = width - lag2;
-    for (int j = 0; j < na; ++j) a = fma(x[j], x[j + lag], a);
-    if (lag2 != lag) for (int j = 0; j < nb; ++j) b = fma(x[j], x[j + lag2], b);
-    R[lag] = a;
-    if (lag2 != lag) R[lag2] = b;
+  double* x = xs[wid];
+  for (int k = lane; k < AC_MAXW + 2 * AL + 8; k += 32) x[k] = (k < width) ? mdata(mono, st, n0 + start + k) : 0.0;
+  __syncwarp();
+
+  const int G = (width + AL - 1) / AL;             // lag groups; the last one may be partial (zero padded)
+  const int lo = period / 2;
+  double r0 = 0.0, best = 0.0;                     // the result is floored at 0 (Autocorrelation.cpp:96-103)
+  for (int g = lane; g < (G + 1) / 2; g += 32) {
+    best = fmax(best, ac_group(x, width, g, lo, r0));
+    const int g2 = G - 1 - g;
+    if (g2 != g) best = fmax(best, ac_group(x, width, g2, lo, r0));
   }
-  __syncthreads();
-  const double r0 = R[0];
-  double best = 0.0;
-  for (int i = period / 2 + tid; i < width; i += AT) {
-    const double v = (r0 != 0) ? R[i] / r0 : R[i];
-    best = fmax(best, v);
-  }
-  best = block_max(best, dscr);
-  if (tid == 0) *out = best;
+  best = warp_max(best);
+  r0 = __shfl_sync(0xffffffffu, r0, 0);            // lane 0 owns group 0
+  // normalisation by R[0] > 0 is monotonic, so max_i (R[i] / R[0]) == (max_i R[i]) / R[0] exactly
+  if (lane == 0) *out = (r0 != 0) ? best / r0 : best;
 }
 
 void afx_launch_autocorr(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  k_autocorr<<<B.g_slots, AT, 0, s>>>(B, P); ++*launches;
+  k_autocorr<<<(B.g_slots + AW - 1) / AW, AW * 32, 0, s>>>(B, P); ++*launches;
 }

@@ -12,17 +12,19 @@
 //   f0 = 0 when the 2048-sample level is below -48 dB; confidence = clip((1 - yin'[(uint)period]) / 0.25).
 //   failsafe_f0 = f0 if f0 > 0 and confidence > 0.2, else sr/N * centroid(mag[0..1023]) for audible hops.
 //
-// One CTA of 256 threads per frame.  The zero-padded first half a and the full frame b are transformed
-// together as z = a + i b (one 2048-point complex FFT), split into A and B, and conj(A) B goes back
-// through the same forward kernel (r = Re FFT(conj(P)) / N).  64 KB of ping-pong FFT buffers + 16 KB of
-// prefix sums in dynamic shared memory.
-#include "afx_fft.cuh"
+// One CTA of 128 threads per frame.  The zero-padded first half a and the full frame b are transformed
+// together as z = a + i b by ONE 2048-point complex FFT (register-blocked radix 16 x 16 x 8, afx_fft16.cuh),
+// split into A and B, and conj(conj(A) B) goes through the same forward transform (r = Re FFT(conj(P)) / N).
+// Shared memory: one padded 2048-point FFT buffer (34 KB), prefix sums of squares (17 KB), yin' (9 KB).
+#include "afx_fft16.cuh"
 
-#define YT 256
+#define YT 128
 #define YN 2048
 #define YW 1024
+#define PAD16(i) ((i) + ((i) >> 4))
+#define PAD8(i) ((i) + ((i) >> 3))
 
-// exclusive prefix sum across the block of one double per thread (256 threads); returns prefix, total in *tot
+// exclusive prefix sum across the block of one double per thread (YT threads); returns prefix, total in *tot
 __device__ __forceinline__ double block_scan_excl(double v, double* scratch, double* tot)
 {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -33,31 +35,18 @@ __device__ __forceinline__ double block_scan_excl(double v, double* scratch, dou
   if (lane == 31) scratch[wid] = inc;
   __syncthreads();
   double base = 0.0, total = 0.0;
+#pragma unroll
   for (int w = 0; w < (YT >> 5); ++w) { const double s = scratch[w]; if (w < wid) base += s; total += s; }
   if (tot) *tot = total;
   return base + inc - v;
 }
 
-__device__ __forceinline__ double2* fft2048(double2* a, double2* b, const double2* __restrict__ tw, int tid)
-{
-  stockham_r2_pass<YN, YN>(a, b, 1, tw, tid, YT);
-  __syncthreads();
-  double2* src = b; double2* dst = a;
-#pragma unroll 1
-  for (int p = 2; p < YN; p <<= 2) {
-    stockham_r4_pass<YN, YN>(src, dst, p, tw, tid, YT);
-    __syncthreads();
-    double2* t = src; src = dst; dst = t;
-  }
-  return src;
-}
-
 __global__ void __launch_bounds__(YT) k_pitch(AfxBatchDev B, AfxParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* bufA = reinterpret_cast<double2*>(smem_raw);
-  double2* bufB = bufA + YN;
-  double* S = reinterpret_cast<double*>(bufB + YN);      // [2049] prefix sums of squares
+  double2* buf = reinterpret_cast<double2*>(smem_raw);                 // [2048 + 128]
+  double* S = reinterpret_cast<double*>(buf + YN + YN / 16);           // [PAD16(2048) + 1] prefix sums of squares
+  double* yin = S + (YN + YN / 16 + 8);                                // [PAD8(1024)]
   __shared__ double scratch[32];
   __shared__ int iscr[32];
   __shared__ int s_file;
@@ -73,76 +62,84 @@ __global__ void __launch_bounds__(YT) k_pitch(AfxBatchDev B, AfxParams P)
   if (f.status != 0 || t >= st.F) return;
   const int n0 = t * P.H;
   const float* __restrict__ mono = B.mono + f.mono_off;
+  FftSyncBlock sync;
 
-  // ---- load 8 consecutive samples per thread, prefix sums of squares, pack z = a + i b -----------
-  double x[8]; double loc = 0.0;
+  // ---- prefix sums of squares: 16 consecutive samples per thread ---------------------------------
+  {
+    double x[16]; double loc = 0.0;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) { x[q] = mdata(mono, st, n0 + 8 * tid + q); loc += x[q] * x[q]; }
-  double total;
-  double pre = block_scan_excl(loc, scratch, &total);
-  if (tid == 0) S[0] = 0.0;
+    for (int q = 0; q < 16; ++q) { x[q] = mdata(mono, st, n0 + 16 * tid + q); loc += x[q] * x[q]; }
+    double pre = block_scan_excl(loc, scratch, nullptr);
+    if (tid == 0) S[0] = 0.0;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    pre += x[q] * x[q];
-    S[8 * tid + q + 1] = pre;
-    const int m = 8 * tid + q;
-    bufA[m] = make_double2(m < YW ? x[q] : 0.0, x[q]);
+    for (int q = 0; q < 16; ++q) { pre += x[q] * x[q]; S[PAD16(16 * tid + q + 1)] = pre; }
   }
-  __syncthreads();
 
-  // ---- forward FFT, split, conj(conj(A) B), forward FFT again --------------------------------------
-  double2* Z = fft2048(bufA, bufB, P.t.tw2048, tid);
-  double2* O = (Z == bufA) ? bufB : bufA;
-  for (int k = tid; k < YN; k += YT) {
-    const double2 zk = Z[k], zn = cconj(Z[(YN - k) & (YN - 1)]);
+  // ---- z = a + i b, strided per thread as the FFT wants it; forward FFT --------------------------------
+  double2 v[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int m = tid + YT * r;
+    const double xv = mdata(mono, st, n0 + m);
+    v[r] = make_double2(m < YW ? xv : 0.0, xv);
+  }
+  fft16_run<YN, YN>(v, buf, P.t.tw2048, tid, sync);
+  // split into A (transform of a) and B (of b), O = conj(conj(A) B); every thread builds its own 16 inputs
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int k = tid + YT * r;
+    const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((YN - k) & (YN - 1))];
+    const double2 zn = make_double2(zc.x, -zc.y);
     const double2 A = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y + zn.y));
     const double2 D = make_double2(0.5 * (zk.x - zn.x), 0.5 * (zk.y - zn.y));
     const double2 Bc = make_double2(D.y, -D.x);                  // D / i
-    const double2 Pk = cmul(cconj(A), Bc);
-    O[k] = cconj(Pk);
+    const double2 Pk = f_mul(make_double2(A.x, -A.y), Bc);
+    v[r] = make_double2(Pk.x, -Pk.y);
+  }
+  __syncthreads();                                               // all reads of buf done before it is rewritten
+  fft16_run<YN, YN>(v, buf, P.t.tw2048, tid, sync);
+
+  // ---- difference function (elementwise, tau = tid + 128 c) ------------------------------------------
+  const double sW = S[PAD16(YW)];
+#pragma unroll
+  for (int c = 0; c < YW / YT; ++c) {
+    const int tau = tid + YT * c;
+    const double sq = (S[PAD16(tau + YW)] - S[PAD16(tau)]) + sW;
+    yin[PAD8(tau)] = sq - buf[FFT_PHYS(tau)].x * (1.0 / YN);
   }
   __syncthreads();
-  double2* Rr = fft2048(O, Z, P.t.tw2048, tid);
-  double* yin = reinterpret_cast<double*>(Rr == bufA ? bufB : bufA);   // the free buffer
-
-  // ---- difference function, cumulative-mean normalisation -----------------------------------------
-  double y[4]; double ysum = 0.0;
-  const double sW = S[YW];
+  // ---- cumulative-mean normalisation: 8 consecutive tau per thread ---------------------------------------
+  double y[8]; double ysum = 0.0;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int tau = 4 * tid + q;
-    const double sq = (S[tau + YW] - S[tau]) + sW;
-    y[q] = sq - Rr[tau].x * (1.0 / YN);
-    if (tau >= 1) ysum += y[q];
-  }
-  __syncthreads();        // everyone done reading Rr before yin (aliases the other buffer: safe) -- keeps phases tidy
+  for (int q = 0; q < 8; ++q) { y[q] = yin[PAD8(8 * tid + q)]; if (8 * tid + q >= 1) ysum += y[q]; }
   double run = block_scan_excl(ysum, scratch, nullptr);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int tau = 4 * tid + q;
-    double v;
-    if (tau == 0) v = 1.0;
-    else { run += y[q]; v = (run != 0.0) ? y[q] * ((double)tau / run) : 1.0; }
-    y[q] = v;
-    yin[tau] = v;
+  for (int q = 0; q < 8; ++q) {
+    const int tau = 8 * tid + q;
+    double vv;
+    if (tau == 0) vv = 1.0;
+    else { run += y[q]; vv = (run != 0.0) ? y[q] * ((double)tau / run) : 1.0; }
+    y[q] = vv;
+    yin[PAD8(tau)] = vv;
   }
   __syncthreads();
 
   // ---- first dip below the tolerance, else the last global minimum ---------------------------------
   int cand = 0x7fffffff;
 #pragma unroll
-  for (int q = 3; q >= 0; --q) {
-    const int p = 4 * tid + q;
-    if (p >= 2 && p <= YW - 4 && y[q] < 0.75 && y[q] < yin[p + 1]) cand = p;
+  for (int q = 7; q >= 0; --q) {
+    const int p = 8 * tid + q;
+    const double nxt = (q < 7) ? y[q + 1] : yin[PAD8(min(p + 1, YW - 1))];
+    if (p >= 2 && p <= YW - 4 && y[q] < 0.75 && y[q] < nxt) cand = p;
   }
   cand = block_min_i(cand, iscr);
   int pos;
   if (cand != 0x7fffffff) pos = cand;
   else {
     // argmin with ties -> last index (mathutils.c:250-258)
-    double mv = y[0]; int mi = 4 * tid;
+    double mv = y[0]; int mi = 8 * tid;
 #pragma unroll
-    for (int q = 1; q < 4; ++q) if (!(mv < y[q])) { mv = y[q]; mi = 4 * tid + q; }
+    for (int q = 1; q < 8; ++q) if (!(mv < y[q])) { mv = y[q]; mi = 8 * tid + q; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double ov = __shfl_xor_sync(0xffffffffu, mv, o); const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
@@ -158,18 +155,18 @@ __global__ void __launch_bounds__(YT) k_pitch(AfxBatchDev B, AfxParams P)
   if (tid == 0) {
     double period;
     if (pos == 0 || pos == YW - 1) period = (double)pos;          // mathutils.c:494-506
-    else { const double s0 = yin[pos - 1], s1 = yin[pos], s2 = yin[pos + 1]; period = pos + .5 * (s0 - s2) / (s0 - 2. * s1 + s2); }
+    else { const double s0 = yin[PAD8(pos - 1)], s1 = yin[PAD8(pos)], s2 = yin[PAD8(pos + 1)]; period = pos + .5 * (s0 - s2) / (s0 - 2. * s1 + s2); }
     unsigned peak_pos = 0;
     if (period == period && period >= 0.0 && period < (double)YW) peak_pos = (unsigned)period;
     double pitch = (period > 0.0) ? (double)P.sr / (period + 0.) : 0.0;                  // pitch.c:450-462
-    const bool silent_frame = (10.0 * log10(S[YN] / (double)YN) < -48.0);                // pitch.c:399-407
+    const bool silent_frame = (10.0 * log10(S[PAD16(YN)] / (double)YN) < -48.0);         // pitch.c:399-407
     if (silent_frame) pitch = 0.0;
-    double conf = (1.0 - yin[peak_pos]) / 0.25;                                          // SA.cpp:887-889
+    double conf = (1.0 - yin[PAD8(peak_pos)]) / 0.25;                                    // SA.cpp:887-889
     conf = conf < 0.0 ? 0.0 : (conf > 1.0 ? 1.0 : conf);
     double fsafe = 0.0;                                                                  // SA.cpp:897-916
     if (pitch > 0.0 && conf > 0.2) fsafe = pitch;
     else {
-      const bool silent_hop = (10.0 * log10(S[P.H] / (double)P.H) < -48.0);
+      const bool silent_hop = (10.0 * log10(S[PAD16(P.H)] / (double)P.H) < -48.0);
       if (!silent_hop) { const double c = B.cent_full[slot]; fsafe = (double)P.sr / (double)P.N * (c > 0.0 ? c : 0.0); }
     }
     const size_t TF = (size_t)B.TF;
@@ -183,7 +180,7 @@ void afx_launch_pitch(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, 
 {
   if (B.g_slots <= 0) return;
   static bool attr_set = false;
-  const int smem = 2 * YN * (int)sizeof(double2) + (YN + 8) * (int)sizeof(double);
+  const int smem = (YN + YN / 16) * (int)sizeof(double2) + (YN + YN / 16 + 8) * (int)sizeof(double) + (YW + YW / 8 + 8) * (int)sizeof(double);
   if (!attr_set) { cudaFuncSetAttribute(k_pitch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
   k_pitch<<<B.g_slots, YT, smem, s>>>(B, P); ++*launches;
 }

@@ -144,6 +144,11 @@ int afx_measure_fp64_peak(afx_ctx* ctx, double* tflops);
  * SampleAnalyser.cpp:698-718) of one file back to the host.  Returns its length. */
 int64_t afx_batch_conditioned(const afx_batch* b, int32_t file_index, double* out, int64_t cap);
 
+/* debugging / parity: forward complex FFT (exp(-i), unscaled) of `batch` interleaved re/im sequences of
+ * n = 256, 1024 or 2048 points through the kernels' own FFT core -- the known-answer hook that plays the
+ * role of the reference's TAudioTypesTest::Fourier (Source/Core/AudioTypes/Test/TestFourier.cpp:12-84). */
+int afx_debug_fft(afx_ctx* ctx, int32_t n, int32_t batch, const double* in, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,9 @@
+import sys, numpy as np
+sys.path.insert(0, '.')
+from afec_b200 import api, synth
+pcms = synth.tiled_corpus(400, 16, seconds=3.0, seed0=0)
+an = api.SampleAnalyser(44100, 2048, 1024, features=api.FEAT_ALL)
+b = an.batch(pcms, [44100]*len(pcms))
+b.upload(); b.compute(); b.compute(); b.sync()
+print(b.timings())
+b.free(); an.close()

@@ -185,3 +185,20 @@ def test_resampled_batch_vs_oracle(analysers, feats, oracle_lib):
         want = oracle_lib.analyze(p, src_rate=r, file_size=44 + p.size * 2)
         check(b.result(i), want, feats)
     b.free()
+
+
+@pytest.mark.parametrize("n", [256, 1024, 2048])
+def test_fft_core_known_answers(analysers, n):
+    """The register-blocked FFT core vs numpy: random data, an impulse, a pure tone, and the round trip
+    conj(FFT(conj(FFT(x)))) / n == x (the properties TestFourier.cpp:16-83 checks on the reference FFT)."""
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((5, n)) + 1j * rng.standard_normal((5, n))
+    x[1] = 0; x[1, 3] = 1.0
+    x[2] = np.exp(2j * np.pi * 17 * np.arange(n) / n)
+    x[3] = rng.standard_normal(n)                      # real input
+    an = analysers(1024)
+    X = an.debug_fft(x)
+    ref = np.fft.fft(x, axis=1)
+    assert np.max(np.abs(X - ref)) <= 1e-11 * max(1.0, np.max(np.abs(ref)))
+    back = np.conj(an.debug_fft(np.conj(X))) / n
+    assert np.max(np.abs(back - x)) <= 1e-12 * max(1.0, np.max(np.abs(x)))
