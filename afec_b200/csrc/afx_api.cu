@@ -290,6 +290,11 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   for (int n = 0; n < N; ++n) window[n] = (0.5 * (1.0 - std::cos(2.0 * pi * (double)n / (double)(N - 1)))) * 2.0;   // window.c:67-76, SA.cpp:178-181
   for (int i = 0; i < AFX_RFFT; ++i) rwindow[i] = 0.5 * (1.0 - std::cos(6.2831853071795864769252867665590 * (double)i * (1.0 / (double)(AFX_RFFT - 1))));  // Fourier.cpp:545-551
   build_mel(mel, N / 2, sr / 2, 20.0, 15500.0, 14);
+  for (int q = 0; q < 14; ++q) {
+    int lo = N / 2, hi = -1;
+    for (int k = 0; k < N / 2; ++k) if (mel[(size_t)q * (N / 2) + k] != 0.0) { if (k < lo) lo = k; hi = k; }
+    P.mel_lo[q] = lo; P.mel_hi[q] = hi;
+  }
   for (int n = 0; n < 14; ++n) for (int m = 1; m <= 14; ++m) dct[n * 14 + (m - 1)] = std::cos(pi * (n / (double)14) * (m - 0.5));   // vector.c:372-391
   for (int k = 0; k < 2048; ++k) { tw2048[2 * k] = std::cos(-2.0 * pi * k / 2048.0); tw2048[2 * k + 1] = std::sin(-2.0 * pi * k / 2048.0); }
   for (int k = 0; k < 512; ++k) { tw512[2 * k] = std::cos(-2.0 * pi * k / 512.0); tw512[2 * k + 1] = std::sin(-2.0 * pi * k / 512.0); }

@@ -1,29 +1,197 @@
-// K4: band projections of the magnitude spectrum, one CTA (256 threads) per main frame.
+// K4: band projections of the magnitude spectrum, one CTA (8 warps) per main frame, no block-wide sort.
 //
 //   * 14 sub-bands (SampleAnalyser.cpp:2067-2260): rms, flatness (dB scaled), flux (Pearson correlation
 //     with the previous frame), complexity (strict local maxima above 0.25 x band max) and contrast
 //     -(peakMean / valleyMean)^(1 / ln(mean)) from the sorted band; spectral_contrast = mean of the 14
 //   * 28 "frequency bands" (SampleAnalyser.cpp:2007-2048): sum of squared magnitudes
 //   * 14 cepstrum bands (SampleAnalyser.cpp:2052-2063; LibXtract vector.c:350-391): 14 triangular mel
-//     filters -> log -> unnormalised DCT-II.  The filters only cover bins 0..359 (quirk: they are laid
-//     over 512 of the 1024 bins), so the dense 14 x 1024 contraction is evaluated on its support.
+//     filters -> log -> unnormalised DCT-II, each filter evaluated on its non-zero support only (the
+//     filters cover bins 1..358: they are laid over 512 of the 1024 bins -- quirk).
 //
-// The in-band sort is ONE block-wide bitonic sort of all 1024 bins keyed by (band id, value): bins
-// outside the 14 bands carry id 15 and sink to the end, band b ends up sorted at [start_b - first_bin, ..).
+// Each sub-band belongs to one warp that keeps the band in registers.  The reference sorts every band to
+// average its lowest / highest 30 %; a sum over the k smallest values only needs the k-th order statistic
+// v:  sum = sum_{x < v} x + (k - #{x < v}) v  (ties carry the same value, so the result is that of the
+// sort).  Order statistics come from an exact MSB-first bisection on the 64-bit patterns of the (non-negative)
+// magnitudes with 32-bit integer compares and warp vote/reduce -- the FP64 pipe is left to the arithmetic.
+// Bands of <= 32 bins rank their elements against each other with shuffles instead.
 #include "afx_common.cuh"
 
 #define BT 256
-#define MEL_SUPPORT 360
 
-__global__ void __launch_bounds__(BT) k_bands(AfxBatchDev B, AfxParams P)
+__device__ __forceinline__ double warp_sum_d(double v) { return warp_sum(v); }
+
+// raw per-band sums handed from the band's warp to the epilogue lane
+struct BandRaw { double s1, s2, s11, s12, s22, ls, x0, lo_sum, hi_sum; int cplx, pad; };
+
+// per-band epilogue (one lane per band, all 14 in lock step so the pow / log / exp chains run once)
+__device__ __forceinline__ double band_write(AfxBatchDev& B, size_t TF, int slot, int b, int n, int nei, const BandRaw& r)
 {
-  __shared__ double mag[AFX_NBIN];
-  __shared__ double prev[AFX_NBIN];
-  __shared__ double srt[AFX_NBIN];
-  __shared__ unsigned char sid[AFX_NBIN];
+  const double dn = (double)n;
+  const double mean = (n >= 2) ? r.s1 / dn : r.s1;          // TStatistics::Mean, Statistics.cpp:249-266
+  const double gmean = (n >= 2) ? exp(r.ls / dn) : r.x0;    // TStatistics::GeometricMean :417-455
+  const size_t o = (size_t)slot * 14 + b;
+  B.fv[(size_t)FV_RMS * TF + o] = sqrt(r.s11 / dn);
+  B.fv[(size_t)FV_FLATNESS * TF + o] = flatness_db(mean, gmean);
+  const double m1 = r.s1 / dn, m2 = r.s2 / dn;
+  const double den2 = (r.s11 - m1 * m1 * dn) * (r.s22 - m2 * m2 * dn);
+  const double num = r.s12 - (m1 * m2 * dn);
+  B.fv[(size_t)FV_FLUX * TF + o] = (fabs(den2) > (double)1e-12f) ? num / sqrt(den2) : 0.0;
+  B.fv[(size_t)FV_COMPLEXITY * TF + o] = (double)r.cplx;
+  const double valley = r.lo_sum / nei + 1e-30, peak = r.hi_sum / nei + 1e-30;      // SampleAnalyser.cpp:2199-2232
+  const double c = -1.0 * pow(peak / valley, 1.0 / log(mean + 1e-30));
+  B.fv[(size_t)FV_CONTRAST * TF + o] = c;
+  return c;
+}
+
+// One sub-band on one warp, C = ceil(n / 32) elements per lane.
+template <int C>
+__device__ __forceinline__ void subband(const AfxParams& P, int b, const double* __restrict__ g,
+                                        const double* __restrict__ gp, int lane, BandRaw* raw)
+{
+  const int s0 = P.band14_start[b], n = P.band14_n[b], nei = P.band14_nei[b];
+  double x[C]; unsigned hi[C], lo[C];
+  double s1 = 0, s2 = 0, s11 = 0, s12 = 0, s22 = 0, mx = 0.0, mant = 1.0; int ex = 0;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int k = lane + 32 * c;
+    const bool valid = k < n;
+    const double xv = valid ? g[s0 + k] : 0.0, yv = valid ? gp[s0 + k] : 0.0;
+    x[c] = xv;
+    const unsigned long long u = valid ? (unsigned long long)__double_as_longlong(xv) : 0xffffffffffffffffull;
+    hi[c] = (unsigned)(u >> 32); lo[c] = (unsigned)u;
+    if (valid) {
+      s12 += xv * yv; s1 += xv; s11 += xv * xv; s2 += yv; s22 += yv * yv;
+      mx = fmax(mx, xv);
+      mul_frexp_pos(mant, ex, fabs(xv) + 1e-20);
+    }
+  }
+  double ls = log(mant) + (double)ex * 0.693147180559945309417;
+  s1 = warp_sum(s1); s2 = warp_sum(s2); s11 = warp_sum(s11); s12 = warp_sum(s12); s22 = warp_sum(s22);
+  ls = warp_sum(ls); mx = warp_max(mx);
+  const double thr = mx * 0.25;
+  int cplx = 0;
+  if (thr > 0.0) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int k = lane + 32 * c, q = s0 + k;
+      if (k < n && x[c] > thr && q > 0 && q < AFX_NBIN - 1 && x[c] > g[q - 1] && x[c] > g[q + 1]) ++cplx;
+    }
+  }
+  cplx = __reduce_add_sync(0xffffffffu, cplx);
+
+  double lo_sum = 0.0, hi_sum = 0.0;
+  if (C == 1) {
+    // rank by shuffles: #less and #less-or-equal of every element; the element whose interval holds rank r is the r-th
+    int less = 0, leq = 0;
+    for (int j = 0; j < n; ++j) {
+      const unsigned oh = __shfl_sync(0xffffffffu, hi[0], j), ol = __shfl_sync(0xffffffffu, lo[0], j);
+      const bool lt = (oh < hi[0]) || (oh == hi[0] && ol < lo[0]);
+      const bool eq = (oh == hi[0]) && (ol == lo[0]);
+      less += lt ? 1 : 0; leq += (lt || eq) ? 1 : 0;
+    }
+    const bool valid = lane < n;
+    const int r1 = nei - 1, r2 = n - nei;
+    const unsigned m1 = __ballot_sync(0xffffffffu, valid && less <= r1 && r1 < leq);
+    const unsigned m2 = __ballot_sync(0xffffffffu, valid && less <= r2 && r2 < leq);
+    const int l1 = __ffs(m1) - 1, l2 = __ffs(m2) - 1;
+    const double v1 = __shfl_sync(0xffffffffu, x[0], l1), v2 = __shfl_sync(0xffffffffu, x[0], l2);
+    const int less1 = __shfl_sync(0xffffffffu, less, l1), leq2 = __shfl_sync(0xffffffffu, leq, l2);
+    lo_sum = warp_sum((valid && x[0] < v1) ? x[0] : 0.0) + (double)(nei - less1) * v1;
+    hi_sum = warp_sum((valid && x[0] > v2) ? x[0] : 0.0) + (double)(nei - (n - leq2)) * v2;
+  } else {
+    // Exact MSB-first bisection on the 64-bit patterns.  Select 1 looks for a threshold with exactly `nei`
+    // elements below it (then the sum of those elements IS the sum of the nei smallest), select 2 for one with
+    // exactly n - nei below it; each stops as soon as a trial splits the band that way, which takes about
+    // log2(spread / gap) steps once the bits common to the whole band are skipped.  Only when equal values
+    // straddle the split does a select run to the last bit; it then ends on the order statistic v of rank
+    // r (0-based) and the sum is  sum_{x < v} x + (k - #{x < v}) v.
+    const int r1 = nei - 1, r2 = n - nei;
+    unsigned mnh = 0xffffffffu, mxh = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) if (lane + 32 * c < n) { mnh = min(mnh, hi[c]); mxh = max(mxh, hi[c]); }
+    mnh = __reduce_min_sync(0xffffffffu, mnh); mxh = __reduce_max_sync(0xffffffffu, mxh);
+    const int top = 31 - __clz((mnh ^ mxh) | 1u);          // highest bit in which the high words differ (0 if equal)
+    const unsigned common = (top >= 31) ? 0u : (mxh & ~((2u << top) - 1u));
+    unsigned p1h = common, p2h = common, p1l = 0, p2l = 0;
+    bool done1 = false, done2 = false;                       // exact split found: threshold = (t?h, t?l)
+    unsigned t1h = 0, t1l = 0, t2h = 0, t2l = 0;
+    for (int bit = top; bit >= 0 && !(done1 && done2); --bit) {
+      const unsigned a1 = p1h | (1u << bit), a2 = p2h | (1u << bit);
+      int c1 = 0, c2 = 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { c1 += (hi[c] < a1) ? 1 : 0; c2 += (hi[c] < a2) ? 1 : 0; }
+      c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2);
+      if (!done1) { if (c1 == nei) { done1 = true; t1h = a1; t1l = 0; } else if (c1 <= r1) p1h = a1; }
+      if (!done2) { if (c2 == r2) { done2 = true; t2h = a2; t2l = 0; } else if (c2 <= r2) p2h = a2; }
+    }
+    if (!(done1 && done2)) {
+      int b1 = 0, b2 = 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { b1 += (hi[c] < p1h) ? 1 : 0; b2 += (hi[c] < p2h) ? 1 : 0; }
+      b1 = __reduce_add_sync(0xffffffffu, b1); b2 = __reduce_add_sync(0xffffffffu, b2);
+      for (int bit = 31; bit >= 0 && !(done1 && done2); --bit) {
+        const unsigned a1 = p1l | (1u << bit), a2 = p2l | (1u << bit);
+        int c1 = 0, c2 = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          c1 += (hi[c] == p1h && lo[c] < a1) ? 1 : 0;
+          c2 += (hi[c] == p2h && lo[c] < a2) ? 1 : 0;
+        }
+        c1 = b1 + __reduce_add_sync(0xffffffffu, c1); c2 = b2 + __reduce_add_sync(0xffffffffu, c2);
+        if (!done1) { if (c1 == nei) { done1 = true; t1h = p1h; t1l = a1; } else if (c1 <= r1) p1l = a1; }
+        if (!done2) { if (c2 == r2) { done2 = true; t2h = p2h; t2l = a2; } else if (c2 <= r2) p2l = a2; }
+      }
+    }
+    // thresholds as 64-bit patterns: an exact split, else the order statistic itself
+    const unsigned long long T1 = done1 ? (((unsigned long long)t1h << 32) | t1l) : (((unsigned long long)p1h << 32) | p1l);
+    const unsigned long long T2 = done2 ? (((unsigned long long)t2h << 32) | t2l) : (((unsigned long long)p2h << 32) | p2l);
+    int nl = 0, nge = 0, ngt = 0; double sl = 0.0, sge = 0.0, sgt = 0.0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const unsigned long long u = ((unsigned long long)hi[c] << 32) | lo[c];
+      const bool valid = (lane + 32 * c) < n;
+      if (valid && u < T1) { ++nl; sl += x[c]; }
+      if (valid && u >= T2) { ++nge; sge += x[c]; }
+      if (valid && u > T2) { ++ngt; sgt += x[c]; }
+    }
+    nl = __reduce_add_sync(0xffffffffu, nl); nge = __reduce_add_sync(0xffffffffu, nge); ngt = __reduce_add_sync(0xffffffffu, ngt);
+    sl = warp_sum(sl); sge = warp_sum(sge); sgt = warp_sum(sgt);
+    lo_sum = done1 ? sl : sl + (double)(nei - nl) * __longlong_as_double((long long)T1);
+    hi_sum = done2 ? sge : sgt + (double)(nei - ngt) * __longlong_as_double((long long)T2);
+    (void)nge;
+  }
+  const double x0 = __shfl_sync(0xffffffffu, x[0], 0);
+  if (lane == 0) {
+    BandRaw& r = raw[b];
+    r.s1 = s1; r.s2 = s2; r.s11 = s11; r.s12 = s12; r.s22 = s22; r.ls = ls; r.x0 = x0; r.lo_sum = lo_sum; r.hi_sum = hi_sum; r.cplx = cplx;
+  }
+}
+
+__device__ __forceinline__ void mel_energy(const AfxParams& P, int q, const double* __restrict__ g, int lane, double* lg)
+{
+  const double* row = P.t.mel + (size_t)q * AFX_NBIN;
+  double e = 0.0;
+  for (int k = P.mel_lo[q] + lane; k <= P.mel_hi[q]; k += 32) e += g[k] * __ldg(row + k);
+  e = warp_sum(e);
+  if (lane == 0) lg[q] = e;
+}
+
+__device__ __forceinline__ void bands28(AfxBatchDev& B, const AfxParams& P, size_t TF, int slot, int b0, int b1,
+                                        const double* __restrict__ g, int lane)
+{
+  for (int b = b0; b < b1; ++b) {
+    double s = 0.0;
+    for (int k = P.band28_s[b] + lane; k < P.band28_e[b]; k += 32) { const double m = g[k]; s += m * m; }
+    s = warp_sum(s);
+    if (lane == 0) B.fv[(size_t)FV_BANDS28 * TF + (size_t)slot * 28 + b] = s;
+  }
+}
+
+__global__ void __launch_bounds__(BT, 4) k_bands(AfxBatchDev B, AfxParams P)
+{
+  __shared__ BandRaw raw[14];
   __shared__ double lg[16];
   __shared__ double contrast[16];
-  __shared__ double bmean[16];
   __shared__ int s_file;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -35,104 +203,36 @@ __global__ void __launch_bounds__(BT) k_bands(AfxBatchDev B, AfxParams P)
   const int t = slot - f.frame_off;
   if (f.status != 0 || t >= B.state[fi].F) return;
   const size_t TF = (size_t)B.TF;
-  const double* g = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
-  const double* gp = (t > 0) ? g - AFX_NBIN : g;              // SampleAnalyser.cpp:936-940
-  for (int k = tid; k < AFX_NBIN; k += BT) {
-    const double m = g[k];
-    mag[k] = m; prev[k] = gp[k]; srt[k] = m; sid[k] = 15;
-  }
-  __syncthreads();
-  if (tid < 14) { const int s = P.band14_start[tid], n = P.band14_n[tid]; for (int k = 0; k < n; ++k) sid[s + k] = (unsigned char)tid; }
+  const double* __restrict__ g = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
+  const double* __restrict__ gp = (t > 0) ? g - AFX_NBIN : g;              // SampleAnalyser.cpp:936-940
 
-  // ---- 28 frequency bands: warp w takes bands w, w+8, ... ----------------------------------------
-  for (int b = wid; b < 28; b += 8) {
-    double s = 0.0;
-    for (int k = P.band28_s[b] + lane; k < P.band28_e[b]; k += 32) s += mag[k] * mag[k];
-    s = warp_sum(s);
-    if (lane == 0) B.fv[(size_t)FV_BANDS28 * TF + (size_t)slot * 28 + b] = s;
-  }
-  // ---- mel filter energies -> log ------------------------------------------------------------------
-  for (int q = wid; q < 14; q += 8) {
-    const double* row = P.t.mel + (size_t)q * AFX_NBIN;
-    double e = 0.0;
-    for (int k = lane; k < MEL_SUPPORT; k += 32) e += mag[k] * __ldg(row + k);
-    e = warp_sum(e);
-    if (lane == 0) lg[q] = log(e < 2e-42 ? 2e-42 : e);        // XTRACT_LOG_LIMIT
-  }
-  // ---- 14 sub-bands: sums, flux, complexity --------------------------------------------------------
-  for (int b = wid; b < 14; b += 8) {
-    const int s0 = P.band14_start[b], n = P.band14_n[b];
-    double s1 = 0, s2 = 0, s11 = 0, s12 = 0, s22 = 0, mx = 0.0, mant = 1.0; int ex = 0;
-    for (int k = lane; k < n; k += 32) {
-      const double x = mag[s0 + k], y = prev[s0 + k];
-      s12 += x * y; s1 += x; s11 += x * x; s2 += y; s22 += y * y;
-      mx = fmax(mx, x);
-      mul_frexp(mant, ex, fabs(x) + 1e-20);
-    }
-    double ls = log(mant) + (double)ex * 0.693147180559945309417;
-    s1 = warp_sum(s1); s2 = warp_sum(s2); s11 = warp_sum(s11); s12 = warp_sum(s12); s22 = warp_sum(s22);
-    ls = warp_sum(ls); mx = warp_max(mx);
-    const double thr = mx * 0.25;
-    int cplx = 0;
-    if (thr > 0.0) for (int k = lane; k < n; k += 32) {
-      const int q = s0 + k;
-      const double x = mag[q];
-      if (x > thr && q > 0 && q < AFX_NBIN - 1 && x > mag[q - 1] && x > mag[q + 1]) ++cplx;
-    }
-    cplx = warp_sum_i(cplx);
-    if (lane == 0) {
-      const double dn = (double)n;
-      const double mean = (n >= 2) ? s1 / dn : s1;            // TStatistics::Mean, Statistics.cpp:249-266
-      const double gmean = (n >= 2) ? exp(ls / dn) : mag[s0]; // TStatistics::GeometricMean :417-455
-      bmean[b] = mean;
-      const size_t o = (size_t)slot * 14 + b;
-      B.fv[(size_t)FV_RMS * TF + o] = sqrt(s11 / dn);
-      B.fv[(size_t)FV_FLATNESS * TF + o] = flatness_db(mean, gmean);
-      const double m1 = s1 / dn, m2 = s2 / dn;
-      const double den2 = (s11 - m1 * m1 * dn) * (s22 - m2 * m2 * dn);
-      const double num = s12 - (m1 * m2 * dn);
-      B.fv[(size_t)FV_FLUX * TF + o] = (fabs(den2) > (double)1e-12f) ? num / sqrt(den2) : 0.0;
-      B.fv[(size_t)FV_COMPLEXITY * TF + o] = (double)cplx;
-    }
+  // ---- phase 1: every warp owns sub-bands (+ a share of the mel / 28-band sums), results to shared memory ----
+  switch (wid) {
+    case 7: subband<9>(P, 13, g, gp, lane, raw); break;
+    case 6: subband<5>(P, 12, g, gp, lane, raw); break;
+    case 5: subband<3>(P, 11, g, gp, lane, raw); mel_energy(P, 12, g, lane, lg); mel_energy(P, 13, g, lane, lg); break;
+    case 4: subband<2>(P, 10, g, gp, lane, raw); subband<2>(P, 9, g, gp, lane, raw); break;
+    default: {
+      // warps 0..3: the nine bands of <= 32 bins (one code instance, looped), the mel energies and the 28 bands
+      const int first = (wid == 3) ? 7 : (wid == 2) ? 5 : (wid == 1) ? 2 : 0;
+      const int last = (wid == 3) ? 8 : (wid == 2) ? 6 : (wid == 1) ? 4 : 1;
+      for (int b = last; b >= first; --b) subband<1>(P, b, g, gp, lane, raw);
+      if (wid >= 2) { for (int q = (wid == 3 ? 8 : 0); q < (wid == 3 ? 12 : 8); ++q) mel_energy(P, q, g, lane, lg); }
+      else bands28(B, P, TF, slot, wid == 1 ? 14 : 0, wid == 1 ? 28 : 14, g, lane);
+    } break;
   }
   __syncthreads();
-  // ---- DCT of the log mel energies (vector.c:372-391) ----------------------------------------------
+  // ---- phase 2: one lane per band / per mel filter for the transcendental epilogues ------------------------
+  if (tid < 14) contrast[tid] = band_write(B, TF, slot, tid, P.band14_n[tid], P.band14_nei[tid], raw[tid]);
+  else if (tid >= 32 && tid < 46) { const double e = lg[tid - 32]; lg[tid - 32] = log(e < 2e-42 ? 2e-42 : e); }   // XTRACT_LOG_LIMIT
+  __syncthreads();
+  // ---- phase 3: DCT of the log mel energies (vector.c:372-391) and the mean contrast -------------------------
   if (tid < 14) {
     double a = 0.0;
     for (int m = 0; m < 14; ++m) a += lg[m] * __ldg(P.t.dct + tid * 14 + m);
     B.fv[(size_t)FV_CEPSTRUM * TF + (size_t)slot * 14 + tid] = a;
   }
-  // ---- bitonic sort of (band id, value), ascending ---------------------------------------------------
-  for (int k2 = 2; k2 <= AFX_NBIN; k2 <<= 1) {
-    for (int j = k2 >> 1; j > 0; j >>= 1) {
-      for (int q = tid; q < AFX_NBIN / 2; q += BT) {
-        const int a = ((q & ~(j - 1)) << 1) | (q & (j - 1));   // lower index of the pair
-        const int c = a | j;
-        const bool up = ((a & k2) == 0);
-        const unsigned char ia = sid[a], ic = sid[c];
-        const double va = srt[a], vc = srt[c];
-        const bool gt = (ia > ic) || (ia == ic && va > vc);
-        if (gt == up) { srt[a] = vc; srt[c] = va; sid[a] = ic; sid[c] = ia; }
-      }
-      __syncthreads();
-    }
-  }
-  // ---- contrast (SampleAnalyser.cpp:2199-2232) --------------------------------------------------------
-  for (int b = wid; b < 14; b += 8) {
-    const int pos = P.band14_start[b] - P.first_bin, n = P.band14_n[b], nei = P.band14_nei[b];
-    double lo = 0.0, hi = 0.0;
-    for (int k = lane; k < nei && k < n; k += 32) lo += srt[pos + k];
-    for (int k = lane; k < nei; k += 32) hi += srt[pos + n - 1 - k];
-    lo = warp_sum(lo); hi = warp_sum(hi);
-    if (lane == 0) {
-      const double valley = lo / nei + 1e-30, peak = hi / nei + 1e-30;
-      const double c = -1.0 * pow(peak / valley, 1.0 / log(bmean[b] + 1e-30));
-      contrast[b] = c;
-      B.fv[(size_t)FV_CONTRAST * TF + (size_t)slot * 14 + b] = c;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
+  if (tid == 32) {
     double s = 0.0;
     for (int b = 0; b < 14; ++b) s += contrast[b];
     B.fs[(size_t)FS_SPEC_CONTRAST * TF + slot] = s / 14.0;

@@ -85,6 +85,7 @@ struct AfxParams {
   int first_bin, nbins;     // 1, 738
   int band14_start[14], band14_n[14], band14_nei[14];
   int band28_s[28], band28_e[28];
+  int mel_lo[14], mel_hi[14];   // non-zero support [lo, hi] of each mel filter row
   double wh_decay, env_coef, silence_floor_amp;   // silence floor in 16-bit range (SA.cpp:648-649)
   double eff_floor[3];
   int analysis_cap;         // 882000
@@ -218,6 +219,16 @@ __device__ __forceinline__ void mul_frexp(double& mant, int& ex, double v)
   int e;
   mant *= frexp(v, &e);
   ex += e;
+  if (mant < 0x1p-512) { mant *= 0x1p512; ex -= 512; }
+}
+
+// same for a NORMAL positive double (callers add 1e-20 first, Statistics.cpp:424): the exponent is peeled off
+// with integer ops on the high word instead of the general frexp()
+__device__ __forceinline__ void mul_frexp_pos(double& mant, int& ex, double v)
+{
+  const int hi = __double2hiint(v), lo = __double2loint(v);
+  ex += ((hi >> 20) & 0x7ff) - 1022;
+  mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, lo);
   if (mant < 0x1p-512) { mant *= 0x1p512; ex -= 512; }
 }
 

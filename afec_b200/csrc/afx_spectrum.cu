@@ -6,80 +6,94 @@
 // kurtosis, rolloff, flatness, flux) with TStatistics (Statistics.cpp:459-638) and LibXtract
 // (scalar.c:472-493, 624-636).
 //
-// One CTA of 256 threads per frame.  Shared memory: two 1024-point complex ping-pong buffers
-// (32 KB); the magnitude spectrum aliases the buffer the last FFT pass did not write.
-#include "afx_fft.cuh"
+// 64 threads per frame, 4 frames per CTA; a frame group synchronises on its own named barrier.  The real
+// frame is packed as 1024 complex points (even samples -> re, odd -> im) and goes through the register-blocked
+// radix 16 x 16 x 4 transform of afx_fft16.cuh; every thread then owns bins tid, tid + 64, ... for the
+// magnitude and the order-free sums, and 12 consecutive analysis bins for the rolloff prefix sums.
+#include "afx_fft16.cuh"
 #include "../../include/afec_b200.h"
 
-#define ST 256
+#define SG 64               // threads per frame
+#define SF 4                // frames per CTA
 
-__global__ void __launch_bounds__(ST) k_spectrum(AfxBatchDev B, AfxParams P, unsigned features)
+// sum of K doubles over the 64 threads of a frame group; xch = K * 2 doubles of the group's shared scratch.
+// Two barriers: the scratch is free for reuse on return.
+template <int K, class Sync>
+__device__ __forceinline__ void group_sum(double (&v)[K], double* xch, int gt, Sync sync)
 {
-  __shared__ double2 bufA[AFX_NBIN];
-  __shared__ double2 bufB[AFX_NBIN];
-  __shared__ double scratch[8 * 32];
-  __shared__ int s_file;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  if ((gt & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) xch[k * 2 + (gt >> 5)] = v[k];
+  }
+  sync();
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = xch[k * 2] + xch[k * 2 + 1];
+  sync();
+}
+template <class Sync>
+__device__ __forceinline__ double group_max(double v, double* xch, int gt, Sync sync)
+{
+  v = warp_max(v);
+  if ((gt & 31) == 0) xch[gt >> 5] = v;
+  sync();
+  v = fmax(xch[0], xch[1]);
+  sync();
+  return v;
+}
 
-  const int tid = threadIdx.x;
-  const int slot = B.slot0 + blockIdx.x;
-  if (tid == 0) s_file = find_file_by_frame(B.files, B.n_files, slot);
-  __syncthreads();
-  const int fi = s_file;
+__global__ void __launch_bounds__(SG * SF) k_spectrum(AfxBatchDev B, AfxParams P, unsigned features)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int g = threadIdx.x / SG, gt = threadIdx.x % SG, lane = gt & 31, gw = gt >> 5;
+  double2* buf = reinterpret_cast<double2*>(smem_raw) + g * (AFX_NBIN + AFX_NBIN / 16);   // FFT buffer, later mag[1024]
+  double* xch = reinterpret_cast<double*>(reinterpret_cast<double2*>(smem_raw) + SF * (AFX_NBIN + AFX_NBIN / 16)) + g * 16;
+
+  const int rel = blockIdx.x * SF + g;
+  if (rel >= B.g_slots) return;                      // group-uniform; only the group's named barrier is used below
+  const int slot = B.slot0 + rel;
+  const int fi = find_file_by_frame(B.files, B.n_files, slot);
   const AfxFile f = B.files[fi];
   const AfxState st = B.state[fi];
   const int t = slot - f.frame_off;
   if (f.status != 0 || t >= st.F) return;
   const int n0 = t * P.H;
   const float* __restrict__ mono = B.mono + f.mono_off;
-  const double* __restrict__ win = P.t.window;
+  const double2* __restrict__ win2 = reinterpret_cast<const double2*>(P.t.window);
   const int TF = B.TF;
+  FftSyncNamed<SG> sync{ 1 + g };
 
-  // ---- load, window, pack (even -> re, odd -> im); hop-slice energy and peak on the way -------
-  double e_hop = 0.0, pk_hop = 0.0;
-  for (int m = tid; m < AFX_NBIN; m += ST) {
-    const double x0 = mdata(mono, st, n0 + 2 * m), x1 = mdata(mono, st, n0 + 2 * m + 1);
-    bufA[m] = make_double2(x0 * __ldg(win + 2 * m), x1 * __ldg(win + 2 * m + 1));
-    if (2 * m < P.H) { e_hop += x0 * x0 + x1 * x1; pk_hop = fmax(pk_hop, fmax(fabs(x0), fabs(x1))); }
-  }
-  __syncthreads();
-
-  // ---- amplitude features of the hop slice (SA.cpp:865-873) ------------------------------------
+  // ---- amplitude features of the hop slice (SA.cpp:865-873): H / 64 consecutive samples per thread --------
   if (features & AFX_FEAT_AMPLITUDE) {
-    double v[1] = { e_hop };
-    block_sum<1>(v, scratch);
-    const double pk = block_max(pk_hop, scratch);
-    // one-pole envelope (Envelopes.inl:14-18) as a scan of affine maps s -> A s + B
-    const int per = P.H / ST;                 // samples per thread (hop is a multiple of 256)
+    const int per = P.H / SG;                         // 4, 8, 16 or 32 (hop is a multiple of 256)
     const double c = P.env_coef;
-    double xs[8];
-    double A = 1.0, Bv = 0.0;
+    // one-pole envelope (Envelopes.inl:14-18) as a scan of affine maps s -> A s + Bv
+    double A = 1.0, Bv = 0.0, e_hop = 0.0, pk_hop = 0.0;
     for (int q = 0; q < per; ++q) {
-      xs[q] = fabs(mdata(mono, st, n0 + tid * per + q));
-      Bv = xs[q] + c * (Bv - xs[q]);
+      const double xv = mdata(mono, st, n0 + gt * per + q), a = fabs(xv);
+      e_hop += xv * xv; pk_hop = fmax(pk_hop, a);
+      Bv = a + c * (Bv - a);
       A *= c;
     }
-    // inclusive scan over threads
-    const int lane = tid & 31, wid = tid >> 5;
-    double sA = A, sB = Bv;
+    double sA = A, sB = Bv;                           // inclusive scan inside the warp
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const double pA = __shfl_up_sync(0xffffffffu, sA, o), pB = __shfl_up_sync(0xffffffffu, sB, o);
       if (lane >= o) { sB = sA * pB + sB; sA = sA * pA; }
     }
-    __syncthreads();
-    if (lane == 31) { scratch[wid] = sA; scratch[32 + wid] = sB; }
-    __syncthreads();
-    // state entering this warp = composition of all previous warps applied to 0
-    double s_in = 0.0;
-    for (int w = 0; w < wid; ++w) s_in = scratch[w] * s_in + scratch[32 + w];
-    // state entering this thread
+    if (lane == 31 && gw == 0) { xch[4] = sA; xch[5] = sB; }
+    double ev[1] = { e_hop };
+    group_sum<1>(ev, xch, gt, sync);                  // also publishes xch[4..5] (first barrier inside)
+    double s_in = (gw == 1) ? xch[5] : 0.0;           // state entering the second warp = first warp's map applied to 0
     const double pA = __shfl_up_sync(0xffffffffu, sA, 1), pB = __shfl_up_sync(0xffffffffu, sB, 1);
     if (lane > 0) s_in = pA * s_in + pB;
     double env = s_in, emax = 0.0;
-    for (int q = 0; q < per; ++q) { env = xs[q] + c * (env - xs[q]); emax = fmax(emax, env); }
-    emax = block_max(emax, scratch);
-    if (tid == 0) {
-      const double level = v[0] / (double)P.H;
+    for (int q = 0; q < per; ++q) { const double a = fabs(mdata(mono, st, n0 + gt * per + q)); env = a + c * (env - a); emax = fmax(emax, env); }
+    const double pk = group_max(pk_hop, xch, gt, sync);
+    emax = group_max(emax, xch, gt, sync);
+    if (gt == 0) {
+      const double level = ev[0] / (double)P.H;
       B.fs[(size_t)FS_AMP_SILENCE * TF + slot] = (10.0 * log10(level) < -48.0) ? 1.0 : 0.0;   // mathutils.c:606-615
       B.fs[(size_t)FS_AMP_PEAK * TF + slot] = pk;
       const double r = sqrt(level);
@@ -88,82 +102,93 @@ __global__ void __launch_bounds__(ST) k_spectrum(AfxBatchDev B, AfxParams P, uns
     }
   }
 
-  // ---- FFT (1024 complex, 5 radix-4 passes) + real unpack + magnitude / N -----------------------
-  double2* Z = fft_pow4<AFX_NBIN, AFX_NFFT, false>(bufA, bufB, P.t.tw2048, tid, ST);
-  double* mag = reinterpret_cast<double*>(Z == bufA ? bufB : bufA);
-  double* gmag = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
-  for (int k = tid; k < AFX_NBIN; k += ST) {
-    const double2 zk = Z[k], zm = cconj(Z[(AFX_NBIN - k) & (AFX_NBIN - 1)]);
+  // ---- load, window, pack (even -> re, odd -> im) in the FFT's strided order; transform ---------------------
+  double2 v[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int m = gt + SG * r;
+    const double2 w = __ldg(win2 + m);
+    v[r] = make_double2(mdata(mono, st, n0 + 2 * m) * w.x, mdata(mono, st, n0 + 2 * m + 1) * w.y);
+  }
+  fft16_run<AFX_NBIN, AFX_NFFT>(v, buf, P.t.tw2048, gt, sync);
+
+  // ---- real unpack + magnitude / N for bins gt + 64 c (Fourier.cpp:266-271, AudioMath.cpp:497-504) ---------
+  double m16[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int k = gt + SG * c;
+    const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((AFX_NBIN - k) & (AFX_NBIN - 1))];
+    const double2 zm = make_double2(zc.x, -zc.y);
     const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y + zm.y));
     const double2 D = make_double2(0.5 * (zk.x - zm.x), 0.5 * (zk.y - zm.y));
     const double2 O = make_double2(D.y, -D.x);                 // D / i
-    const double2 X = cadd(E, cmul(__ldg(P.t.tw2048 + k), O));
-    const double m = sqrt(X.x * X.x + X.y * X.y) * (1.0 / AFX_NFFT);   // Fourier.cpp:266-271, AudioMath.cpp:497-504
-    mag[k] = m;
-    gmag[k] = m;
+    const double2 X = f_add(E, f_mul(__ldg(P.t.tw2048 + k), O));
+    m16[c] = sqrt(X.x * X.x + X.y * X.y) * (1.0 / AFX_NFFT);
   }
-  __syncthreads();
-
-  // ---- spectral scalars on bins first_bin .. first_bin + nbins - 1 -----------------------------------
-  const int nb = P.nbins, fb = P.first_bin;
-  const int j0 = 3 * tid;                       // three consecutive analysis bins per thread
-  double m3[3];
+  double* gmag = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
+  sync();                                            // everyone has read Z before buf becomes the magnitude array
+  double* mag = reinterpret_cast<double*>(buf);
 #pragma unroll
-  for (int q = 0; q < 3; ++q) m3[q] = (j0 + q < nb) ? mag[fb + j0 + q] : 0.0;
+  for (int c = 0; c < 16; ++c) { const int k = gt + SG * c; mag[k] = m16[c]; gmag[k] = m16[c]; }
 
+  // ---- order-free sums over the analysis window (bins first_bin .. first_bin + nbins - 1) and all bins -----
+  const int nb = P.nbins, fb = P.first_bin;
   double acc[6] = { 0, 0, 0, 0, 0, 0 };        // S1, S2, SJ, log-sum, full S, full SJ
   double mant = 1.0; int ex = 0;
 #pragma unroll
-  for (int q = 0; q < 3; ++q) if (j0 + q < nb) {
-    acc[0] += m3[q]; acc[1] += m3[q] * m3[q]; acc[2] += (double)(j0 + q) * m3[q];
-    mul_frexp(mant, ex, fabs(m3[q]) + 1e-20);            // Statistics.cpp:417-455
+  for (int c = 0; c < 16; ++c) {
+    const int k = gt + SG * c, j = k - fb;
+    const double m = m16[c];
+    acc[4] += m; acc[5] += (double)k * m;
+    if (j >= 0 && j < nb) {
+      acc[0] += m; acc[1] += m * m; acc[2] += (double)j * m;
+      mul_frexp_pos(mant, ex, fabs(m) + 1e-20);               // Statistics.cpp:417-455
+    }
   }
   acc[3] = log(mant) + (double)ex * 0.693147180559945309417;
-  for (int k = tid; k < AFX_NBIN; k += ST) { acc[4] += mag[k]; acc[5] += (double)k * mag[k]; }
-  block_sum<6>(acc, scratch);
+  group_sum<6>(acc, xch, gt, sync);                  // (its first barrier also publishes mag[])
   const double S1 = acc[0];
   const double cen = (S1 == 0.0) ? 0.0 : acc[2] / S1;                          // Statistics.cpp:459-477
-
   double sp[1] = { 0.0 };
 #pragma unroll
-  for (int q = 0; q < 3; ++q) if (j0 + q < nb) { const double d = (double)(j0 + q) - cen; sp[0] += d * d * m3[q]; }
-  block_sum<1>(sp, scratch);
+  for (int c = 0; c < 16; ++c) { const int j = gt + SG * c - fb; if (j >= 0 && j < nb) { const double d = (double)j - cen; sp[0] += d * d * m16[c]; } }
+  group_sum<1>(sp, xch, gt, sync);
   const double spread = (S1 == 0.0) ? 0.0 : sp[0] / S1;                        // Statistics.cpp:486-506
-
   double sk[2] = { 0.0, 0.0 };
   const bool have_sk = fabs(spread) > (double)1e-12f;                          // Statistics.cpp:510-554
   if (have_sk) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) if (j0 + q < nb) { const double d = (m3[q] - cen) / spread; const double d2 = d * d; sk[0] += d2 * d; sk[1] += d2 * d2; }
+    for (int c = 0; c < 16; ++c) { const int j = gt + SG * c - fb; if (j >= 0 && j < nb) { const double d = (m16[c] - cen) / spread; const double d2 = d * d; sk[0] += d2 * d; sk[1] += d2 * d2; } }
   }
-  block_sum<2>(sk, scratch);
+  group_sum<2>(sk, xch, gt, sync);
 
-  // rolloff (LibXtract scalar.c:472-493): count of prefixes below 85 % of the total
-  const double pivot = S1 * (85.0 / 100.0);
-  double loc = m3[0] + m3[1] + m3[2];
+  // ---- rolloff (LibXtract scalar.c:472-493): count of prefixes below 85 % of the total; 12 bins per thread ---
   {
-    const int lane = tid & 31, wid = tid >> 5;
+    const double pivot = S1 * (85.0 / 100.0);
+    const int j0 = 12 * gt;
+    double m12[12], loc = 0.0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) { m12[q] = (j0 + q < nb) ? mag[fb + j0 + q] : 0.0; loc += m12[q]; }
     double inc = loc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const double pv = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += pv; }
-    __syncthreads();
-    if (lane == 31) scratch[wid] = inc;
-    __syncthreads();
-    double base = 0.0;
-    for (int w = 0; w < wid; ++w) base += scratch[w];
-    double pre = base + inc - loc;              // exclusive prefix = sum of bins before j0
+    if (lane == 31 && gw == 0) xch[0] = inc;
+    sync();
+    double pre = ((gw == 1) ? xch[0] : 0.0) + inc - loc;      // exclusive prefix = sum of bins before j0
     int cnt = 0;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) if (j0 + q < nb) { cnt += (pre < pivot) ? 1 : 0; pre += m3[q]; }
-    int* iscr = reinterpret_cast<int*>(scratch + 64);
-    cnt = block_sum_i(cnt, iscr);
-    if (tid == 0) {
-      const double r = (double)cnt * (double)(P.sr / (P.N / 2));              // SA.cpp:1892: 44100 / 1024 = 43
+    for (int q = 0; q < 12; ++q) if (j0 + q < nb) { cnt += (pre < pivot) ? 1 : 0; pre += m12[q]; }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    int* ix = reinterpret_cast<int*>(xch + 2);
+    if (lane == 0) ix[gw] = cnt;
+    sync();
+    if (gt == 0) {
+      const double r = (double)(ix[0] + ix[1]) * (double)(P.sr / (P.N / 2));   // SA.cpp:1892: 44100 / 1024 = 43
       B.fs[(size_t)FS_SPEC_ROLLOFF * TF + slot] = r;
     }
   }
 
-  if (tid == 0) {
+  if (gt == 0) {
     const double n = (double)nb;
     const double rms = sqrt(acc[1] / n);
     B.fs[(size_t)FS_SPEC_RMS * TF + slot] = (rms != rms) ? 0.0 : rms;
@@ -214,6 +239,9 @@ __global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P)
 void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  k_spectrum<<<B.g_slots, ST, 0, s>>>(B, P, features); ++*launches;
+  static bool attr_set = false;
+  const int smem = SF * (AFX_NBIN + AFX_NBIN / 16) * (int)sizeof(double2) + SF * 16 * (int)sizeof(double);
+  if (!attr_set) { cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+  k_spectrum<<<(B.g_slots + SF - 1) / SF, SG * SF, smem, s>>>(B, P, features); ++*launches;
   k_flux<<<(B.g_slots + 7) / 8, 256, 0, s>>>(B, P); ++*launches;
 }
