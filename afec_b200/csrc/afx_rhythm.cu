@@ -21,7 +21,7 @@
 //   k_rhythm_back    (CTA per file)    min-gap peak picker -> onset series, onset count, Canny
 //                                      sharpening + z-score, peak strength / frequency / contrast, beat
 //                                      tracker (ACF, comb filterbank, Rayleigh weighting), tempo heuristics
-#include "afx_fft.cuh"
+#include "afx_fft16.cuh"
 #include "../../include/afec_b200.h"
 
 #define RPW 8              // frames (warps) per CTA in the frame-parallel kernels
@@ -39,36 +39,44 @@ __device__ __forceinline__ float phase_rewrap(float p)
 }
 
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RPW * 32) k_rhythm_polar(AfxBatchDev B, AfxParams P)
+// 16 threads per rhythm frame (256-point packed transform = radix 16 x 16 in registers), two frames per warp
+#define PF 8                // frames per CTA (4 warps)
+__global__ void __launch_bounds__(PF * 16) k_rhythm_polar(AfxBatchDev B, AfxParams P)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double2* a = reinterpret_cast<double2*>(smem_raw) + wid * 512;
-  double2* b = a + 256;
-  const int rel = blockIdx.x * RPW + wid;
-  if (rel >= B.g_rslots) return;               // warp-uniform; only __syncwarp below
-  const int slot = B.rslot0 + rel;
+  __shared__ double2 sbuf[PF][256 + 16];
+  const int h = threadIdx.x >> 4, ht = threadIdx.x & 15;
+  double2* buf = sbuf[h];
+  const int rel = blockIdx.x * PF + h;
+  const bool in_range = rel < B.g_rslots;
+  const int slot = B.rslot0 + (in_range ? rel : 0);
   const int fi = find_file_by_rframe(B.files, B.n_files, slot);
   const AfxFile f = B.files[fi];
   const int t = slot - f.rframe_off;
-  if (f.status != 0 || t >= B.state[fi].Fr) return;
   const AfxState st = B.state[fi];
+  const bool live = in_range && f.status == 0 && t < st.Fr;   // both halves of a warp run the transform (warp-wide sync)
   const float* __restrict__ mono = B.mono + f.mono_off;
-  const double* __restrict__ win = P.t.rwindow;
+  const double2* __restrict__ win2 = reinterpret_cast<const double2*>(P.t.rwindow);
   const int n0 = t * AFX_RHOP;
-  for (int m = lane; m < 256; m += 32) {
-    const double x0 = mdata(mono, st, n0 + 2 * m), x1 = mdata(mono, st, n0 + 2 * m + 1);
-    a[m] = make_double2(__ldg(win + 2 * m) * x0, __ldg(win + 2 * m + 1) * x1);   // OnsetDetector.cpp:119-120
+  double2 v[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int m = ht + 16 * r;
+    const double2 w = __ldg(win2 + m);
+    const double x0 = live ? mdata(mono, st, n0 + 2 * m) : 0.0, x1 = live ? mdata(mono, st, n0 + 2 * m + 1) : 0.0;
+    v[r] = make_double2(w.x * x0, w.y * x1);                                        // OnsetDetector.cpp:119-120
   }
-  __syncwarp();
-  double2* Z = fft_pow4<256, AFX_RFFT, true>(a, b, P.t.tw512, lane, 32);
+  fft16_run<256, AFX_RFFT>(v, buf, P.t.tw512, ht, FftSyncWarp());
+  if (!live) return;
   float* row = B.rpolar + (size_t)rel * AFX_RROW;
-  for (int k = lane; k < 256; k += 32) {
-    const double2 zk = Z[k], zm = cconj(Z[(256 - k) & 255]);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int k = ht + 16 * c;
+    const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((256 - k) & 255)];
+    const double2 zm = make_double2(zc.x, -zc.y);
     const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y + zm.y));
     const double2 D = make_double2(0.5 * (zk.x - zm.x), 0.5 * (zk.y - zm.y));
     const double2 O = make_double2(D.y, -D.x);
-    double2 X = cadd(E, cmul(__ldg(P.t.tw512 + k), O));
+    double2 X = f_add(E, f_mul(__ldg(P.t.tw512 + k), O));
     if (k == 0) { X.y = 0.0; row[255] = (float)X.x; }                             // mDC, OnsetDetector.cpp:146
     if (k < AFX_RBINS) {
       row[k] = (float)sqrt(X.x * X.x + X.y * X.y);                                // :136-155
@@ -89,14 +97,24 @@ __global__ void __launch_bounds__(256) k_rhythm_whiten(AfxBatchDev B, AfxParams 
   float* col = B.rpolar + (size_t)(f.rframe_off - B.rslot0) * AFX_RROW + threadIdx.x;   // 0..254 bins, 255 dc
   const double relax = (double)P.r_relax, wfloor = (double)0.1f;
   double psp = 0.0;
-  float v = col[0];
-  for (int t = 0; t < Fr; ++t) {
-    const float vn = (t + 1 < Fr) ? col[(size_t)(t + 1) * AFX_RROW] : 0.0f;   // prefetch
-    double a = (double)fabsf(v);
-    if (a < psp) a = __dadd_rn(a, __dmul_rn(__dsub_rn(psp, a), relax));
-    psp = a;
-    col[(size_t)t * AFX_RROW] = __fdiv_rn(v, (float)(wfloor > psp ? wfloor : psp));
-    v = vn;
+  constexpr int D = 8;                        // rows in flight per thread: the recurrence is latency bound otherwise
+  float nxt[D];
+#pragma unroll
+  for (int q = 0; q < D; ++q) nxt[q] = (q < Fr) ? col[(size_t)q * AFX_RROW] : 0.0f;
+  for (int t0 = 0; t0 < Fr; t0 += D) {
+    float cur[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) { cur[q] = nxt[q]; nxt[q] = (t0 + D + q < Fr) ? col[(size_t)(t0 + D + q) * AFX_RROW] : 0.0f; }
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      if (t0 + q < Fr) {
+        const float v = cur[q];
+        double a = (double)fabsf(v);
+        if (a < psp) a = __dadd_rn(a, __dmul_rn(__dsub_rn(psp, a), relax));
+        psp = a;
+        col[(size_t)(t0 + q) * AFX_RROW] = __fdiv_rn(v, (float)(wfloor > psp ? wfloor : psp));
+      }
+    }
   }
 }
 
@@ -104,7 +122,7 @@ __global__ void __launch_bounds__(256) k_rhythm_whiten(AfxBatchDev B, AfxParams 
 // onset functions (OnsetDetector.cpp:371-547): kFunctionRComplex and kFunctionPower
 __global__ void __launch_bounds__(RPW * 32) k_rhythm_odf(AfxBatchDev B, AfxParams P)
 {
-  __shared__ float smag[RPW][256];
+  __shared__ __align__(16) float smag[RPW][256];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int rel = blockIdx.x * RPW + wid;
   if (rel >= B.g_rslots) return;
@@ -119,7 +137,7 @@ __global__ void __launch_bounds__(RPW * 32) k_rhythm_odf(AfxBatchDev B, AfxParam
   double total = 0.0;
   for (int i = lane; i < 256; i += 32) {
     const float m = r0[i];
-    smag[wid][i] = m;
+    smag[wid][i] = (i < AFX_RBINS) ? __fmul_rn(m, m) : m;       // squares for the power function; [255] keeps dc
     if (i >= AFX_RBINS) continue;
     const float cur = fabsf(m);
     const float pm = (t >= 1) ? fabsf(r1[i]) : 0.0f;
@@ -139,42 +157,76 @@ __global__ void __launch_bounds__(RPW * 32) k_rhythm_odf(AfxBatchDev B, AfxParam
   if (lane == 0) {
     const float dc = smag[wid][255];
     float v = __fadd_rn(__fmul_rn(0.0f, 0.0f), __fmul_rn(dc, dc));          // nyq^2 + dc^2, :388-396
-    for (int i = 0; i < AFX_RBINS; ++i) { const float m = smag[wid][i]; v = __fadd_rn(v, __fmul_rn(m, m)); }
+    const float4* sq4 = reinterpret_cast<const float4*>(smag[wid]);        // the reference adds bin by bin, in order
+#pragma unroll 4
+    for (int i = 0; i < 63; ++i) { const float4 q = sq4[i]; v = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(v, q.x), q.y), q.z), q.w); }
+    { const float4 q = sq4[63]; v = __fadd_rn(__fadd_rn(__fadd_rn(v, q.x), q.y), q.z); }
     B.rodf[slot] = __fmul_rn((float)total, P.r_norm_complex);
     B.rodf[(size_t)B.TFr + slot] = __fmul_rn(v, P.r_norm_power);
   }
 }
 
 // -------------------------------------------------------------------------------------------------
-// median removal (OnsetDetector.cpp:551-575): post = odf[t] - median(odf[t-68 .. t]), zeros before the file
-__global__ void __launch_bounds__(RPW * 32) k_rhythm_median(AfxBatchDev B)
+// median removal (OnsetDetector.cpp:551-575): post = odf[t] - median(odf[t-68 .. t]), zeros before the file.
+// The windows of consecutive frames differ by one value, so a thread walks a chunk of frames with the sorted
+// window held in 69 REGISTERS and replaces the outgoing value by the incoming one with two branch-free
+// compare/select sweeps (static indices only): ~300 FP32 ops per frame instead of 69 x 69 comparisons.
+// A chunk that starts inside a file first replays the 68 frames before it.
+#define ML 128             // frames per chunk
+#define MED_INF __int_as_float(0x7f800000)
+
+__device__ __forceinline__ void med_replace(float (&s)[MEDSPAN], float out, float in)
 {
-  __shared__ float w[RPW][2][96];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int rel = blockIdx.x * RPW + wid;
-  if (rel >= B.g_rslots) return;
-  const int slot = B.rslot0 + rel;
-  const int fi = find_file_by_rframe(B.files, B.n_files, slot);
-  const AfxFile f = B.files[fi];
-  const int t = slot - f.rframe_off;
-  if (f.status != 0 || t >= B.state[fi].Fr) return;
-  for (int ty = 0; ty < 2; ++ty) {
-    const float* odf = B.rodf + (size_t)ty * B.TFr + slot;
-    for (int j = lane; j < 96; j += 32) w[wid][ty][j] = (j < MEDSPAN && t - j >= 0) ? odf[-j] : 0.0f;
-  }
-  __syncwarp();
-  for (int ty = 0; ty < 2; ++ty) {
-    const float* x = w[wid][ty];
-    float med = 0.0f; bool have = false;
-    for (int j = lane; j < MEDSPAN; j += 32) {
-      const float v = x[j];
-      int rank = 0;
-      for (int k = 0; k < MEDSPAN; ++k) { const float u = x[k]; rank += (u < v || (u == v && k < j)) ? 1 : 0; }
-      if (rank == (MEDSPAN - 1) / 2) { med = v; have = true; }
+  // drop one copy of `out`: everything at or after its first position moves down by one
+#pragma unroll
+  for (int i = 0; i < MEDSPAN - 1; ++i) s[i] = (s[i] < out) ? s[i] : s[i + 1];
+  s[MEDSPAN - 1] = MED_INF;
+  // insert `in`: s'[i] = max(r[i-1], min(r[i], in))
+#pragma unroll
+  for (int i = MEDSPAN - 1; i > 0; --i) s[i] = fmaxf(s[i - 1], fminf(s[i], in));
+  s[0] = fminf(s[0], in);
+}
+
+__global__ void __launch_bounds__(64) k_rhythm_median(AfxBatchDev B)
+{
+  const int nchunks = (B.g_rslots + ML - 1) / ML;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= 2 * nchunks) return;
+  const int ty = gid & 1, chunk = gid >> 1;
+  const float* __restrict__ odf = B.rodf + (size_t)ty * B.TFr;
+  float* __restrict__ post = B.rpost + (size_t)ty * B.TFr;
+  int slot = B.rslot0 + chunk * ML;
+  const int s_end = min(slot + ML, B.rslot0 + B.g_rslots);
+  int fi = find_file_by_rframe(B.files, B.n_files, slot);
+  float s[MEDSPAN];
+  while (slot < s_end && fi < B.n_files) {
+    const AfxFile f = B.files[fi];
+    const int Fr = (f.status == 0) ? B.state[fi].Fr : 0;
+    const int file_end = f.rframe_off + f.rframe_cap;
+    int t = slot - f.rframe_off;
+    if (t >= 0 && t < Fr) {
+      const float* x = odf + f.rframe_off;
+      float* y = post + f.rframe_off;
+      bool primed = false;
+      if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < MEDSPAN; ++i) s[i] = 0.0f;         // the detector's history starts as zeros
+        primed = true;
+      } else {
+#pragma unroll
+        for (int i = 0; i < MEDSPAN; ++i) s[i] = MED_INF;
+        for (int j = t - (MEDSPAN - 1); j < t; ++j) med_replace(s, MED_INF, j >= 0 ? x[j] : 0.0f);
+      }
+      for (; t < Fr && slot < s_end; ++t, ++slot) {
+        const float out = primed ? ((t >= MEDSPAN) ? x[t - MEDSPAN] : 0.0f) : MED_INF;
+        primed = true;
+        const float in = x[t];
+        med_replace(s, out, in);
+        y[t] = __fsub_rn(in, s[(MEDSPAN - 1) / 2]);
+      }
     }
-    const unsigned ball = __ballot_sync(0xffffffffu, have);
-    med = __shfl_sync(0xffffffffu, med, ball ? (__ffs(ball) - 1) : 0);
-    if (lane == 0) B.rpost[(size_t)ty * B.TFr + slot] = __fsub_rn(x[0], med);
+    if (slot < file_end) slot = file_end;      // unused capacity slots of this file
+    ++fi;
   }
 }
 
@@ -489,18 +541,16 @@ void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s,
 {
   if (B.g_files <= 0 || B.g_rslots <= 0) return;
   static bool attr_set = false;
-  const int smem_polar = RPW * 512 * (int)sizeof(double2);
   const int cap = B.max_fr;
   const int smem_back = cap * 8 + ((cap + 15) & ~15) + ((cap + 31) / 32) * 4 + 16;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_rhythm_polar, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_polar);
     cudaFuncSetAttribute(k_rhythm_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_set = true;
   }
   const int fb = (B.g_rslots + RPW - 1) / RPW;
-  k_rhythm_polar<<<fb, RPW * 32, smem_polar, s>>>(B, P); ++*launches;
+  k_rhythm_polar<<<(B.g_rslots + PF - 1) / PF, PF * 16, 0, s>>>(B, P); ++*launches;
   k_rhythm_whiten<<<B.g_files, 256, 0, s>>>(B, P); ++*launches;
   k_rhythm_odf<<<fb, RPW * 32, 0, s>>>(B, P); ++*launches;
-  k_rhythm_median<<<fb, RPW * 32, 0, s>>>(B); ++*launches;
+  { const int nchunks = (B.g_rslots + ML - 1) / ML; k_rhythm_median<<<(2 * nchunks + 63) / 64, 64, 0, s>>>(B); ++*launches; }
   k_rhythm_back<<<B.g_files, BT_THREADS, smem_back, s>>>(B, P); ++*launches;
 }
