@@ -41,7 +41,7 @@ __device__ __forceinline__ double block_scan_excl(double v, double* scratch, dou
   return base + inc - v;
 }
 
-__global__ void __launch_bounds__(YT) k_pitch(AfxBatchDev B, AfxParams P)
+__global__ void __launch_bounds__(YT, 3) k_pitch(AfxBatchDev B, AfxParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* buf = reinterpret_cast<double2*>(smem_raw);                 // [2048 + 128]

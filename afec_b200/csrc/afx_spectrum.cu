@@ -43,7 +43,7 @@ __device__ __forceinline__ double group_max(double v, double* xch, int gt, Sync 
   return v;
 }
 
-__global__ void __launch_bounds__(SG * SF) k_spectrum(AfxBatchDev B, AfxParams P, unsigned features)
+__global__ void __launch_bounds__(SG * SF, 3) k_spectrum(AfxBatchDev B, AfxParams P, unsigned features)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int g = threadIdx.x / SG, gt = threadIdx.x % SG, lane = gt & 31, gw = gt >> 5;
