@@ -60,7 +60,7 @@ struct afx_ctx {
   cudaStream_t stream = nullptr;
   AfxParams P;
   DevBuf tables;                      // all constant tables in one allocation
-  DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf, d_rpost,
+  DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf, d_rpost, d_bandraw, d_slotmap,
          d_stats, d_header, d_plan, d_scratch;
   std::map<std::pair<int, int>, std::shared_ptr<RsShape>> rs_cache;
   long long group_frames = 393216, group_rframes = 3145728;   // per-launch scratch bound: 3 GB mag, 6 GB rpolar
@@ -299,11 +299,17 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   for (int k = 0; k < 2048; ++k) { tw2048[2 * k] = std::cos(-2.0 * pi * k / 2048.0); tw2048[2 * k + 1] = std::sin(-2.0 * pi * k / 2048.0); }
   for (int k = 0; k < 512; ++k) { tw512[2 * k] = std::cos(-2.0 * pi * k / 512.0); tw512[2 * k + 1] = std::sin(-2.0 * pi * k / 512.0); }
   build_rs_wing(imp);
+  // FFT pass twiddles in access order (afx_fft16.cuh)
+  std::vector<double> ft2(2 * 15 * 16), ft3a(2 * 3 * 256), ft3b(2 * 7 * 256);
+  for (int r = 1; r < 16; ++r) for (int k = 0; k < 16; ++k) { const double a = -2.0 * pi * (double)(r * k) / 256.0; ft2[2 * ((r - 1) * 16 + k)] = std::cos(a); ft2[2 * ((r - 1) * 16 + k) + 1] = std::sin(a); }
+  for (int r = 1; r < 4; ++r) for (int j = 0; j < 256; ++j) { const double a = -2.0 * pi * (double)(r * j) / 1024.0; ft3a[2 * ((r - 1) * 256 + j)] = std::cos(a); ft3a[2 * ((r - 1) * 256 + j) + 1] = std::sin(a); }
+  for (int r = 1; r < 8; ++r) for (int j = 0; j < 256; ++j) { const double a = -2.0 * pi * (double)(r * j) / 2048.0; ft3b[2 * ((r - 1) * 256 + j)] = std::cos(a); ft3b[2 * ((r - 1) * 256 + j) + 1] = std::sin(a); }
 
   size_t off = 0;
   auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_win = place(window.size() * 8), o_rwin = place(rwindow.size() * 8), o_mel = place(mel.size() * 8),
-    o_dct = place(dct.size() * 8), o_tw = place(tw2048.size() * 8), o_tw5 = place(tw512.size() * 8), o_imp = place(imp.size() * 4);
+    o_dct = place(dct.size() * 8), o_tw = place(tw2048.size() * 8), o_tw5 = place(tw512.size() * 8), o_imp = place(imp.size() * 4),
+    o_ft2 = place(ft2.size() * 8), o_ft3a = place(ft3a.size() * 8), o_ft3b = place(ft3b.size() * 8);
   e = ctx->tables.reserve(off);
   if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMalloc(tables)", e); }
   unsigned char* base = (unsigned char*)ctx->tables.p;
@@ -313,12 +319,16 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   cudaMemcpy(base + o_dct, dct.data(), dct.size() * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(base + o_tw, tw2048.data(), tw2048.size() * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(base + o_tw5, tw512.data(), tw512.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_ft2, ft2.data(), ft2.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_ft3a, ft3a.data(), ft3a.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_ft3b, ft3b.data(), ft3b.size() * 8, cudaMemcpyHostToDevice);
   e = cudaMemcpy(base + o_imp, imp.data(), imp.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMemcpy(tables)", e); }
   P.t.window = (const double*)(base + o_win); P.t.rwindow = (const double*)(base + o_rwin);
   P.t.mel = (const double*)(base + o_mel); P.t.dct = (const double*)(base + o_dct);
   P.t.tw2048 = (const double2*)(base + o_tw); P.t.tw512 = (const double2*)(base + o_tw5);
   P.t.rs_imp = (const float*)(base + o_imp);
+  P.t.fft_t2 = (const double2*)(base + o_ft2); P.t.fft_t3_1024 = (const double2*)(base + o_ft3a); P.t.fft_t3_2048 = (const double2*)(base + o_ft3b);
 
   ctx->max_frame_cap = (P.analysis_cap - AFX_RFFT) / AFX_RHOP + 2;
   ctx->zeros.assign(ctx->max_frame_cap, 0.0);
@@ -332,7 +342,7 @@ extern "C" void afx_destroy(afx_ctx* ctx)
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   DevBuf* bufs[] = { &ctx->tables, &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
-    &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch };
+    &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch };
   for (DevBuf* b : bufs) b->release();
   ctx->h_results_cache.release(); ctx->h_plan_cache.release();
   delete ctx;
@@ -492,9 +502,13 @@ extern "C" int afx_batch_upload(afx_batch* b)
   const size_t GS = (size_t)b->max_gslots, GR = (size_t)b->max_grslots;
   CK(ctx->d_mag.reserve((GS + 1) * AFX_NBIN * 8), "cudaMalloc(mag)");
   CK(ctx->d_cent.reserve((TF + 1) * 8), "cudaMalloc(cent)");
+  CK(ctx->d_slotmap.reserve((TF + TFr + 2) * 4), "cudaMalloc(slotmap)");
   CK(ctx->d_fs.reserve((TF + 1) * AFX_N_FS_MAIN * 8), "cudaMalloc(fs)");
   CK(ctx->d_fsr.reserve((TFr + 1) * 2 * 8), "cudaMalloc(fsr)");
-  if (feat & AFX_FEAT_BANDS) CK(ctx->d_fv.reserve((TF + 1) * AFX_FV_STRIDE * 8), "cudaMalloc(fv)");
+  if (feat & AFX_FEAT_BANDS) {
+    CK(ctx->d_fv.reserve((TF + 1) * AFX_FV_STRIDE * 8), "cudaMalloc(fv)");
+    CK(ctx->d_bandraw.reserve((GS + 1) * 154 * 8), "cudaMalloc(bandraw)");
+  }
   if (feat & AFX_FEAT_RHYTHM) {
     CK(ctx->d_rpolar.reserve((GR + 1) * AFX_RROW * 4), "cudaMalloc(rpolar)");
     CK(ctx->d_rodf.reserve((TFr + 1) * 2 * 4), "cudaMalloc(rodf)");
@@ -540,7 +554,8 @@ extern "C" int afx_batch_upload(afx_batch* b)
   D.pcm = (const unsigned char*)ctx->d_pcm.p; D.mono = (float*)ctx->d_mono.p; D.mono_src = (float*)ctx->d_mono_src.p;
   D.files = (const AfxFile*)(dp + p_files); D.state = (AfxState*)ctx->d_state.p;
   D.mag = (double*)ctx->d_mag.p; D.cent_full = (double*)ctx->d_cent.p; D.fs = (double*)ctx->d_fs.p; D.fsr = (double*)ctx->d_fsr.p;
-  D.fv = (double*)ctx->d_fv.p; D.rpolar = (float*)ctx->d_rpolar.p; D.rodf = (float*)ctx->d_rodf.p; D.rpost = (float*)ctx->d_rpost.p;
+  D.fv = (double*)ctx->d_fv.p; D.rpolar = (float*)ctx->d_rpolar.p; D.rodf = (float*)ctx->d_rodf.p; D.rpost = (float*)ctx->d_rpost.p; D.bandraw = (double*)ctx->d_bandraw.p;
+  D.slot_file = (const int*)ctx->d_slotmap.p; D.rslot_file = (const int*)ctx->d_slotmap.p + TF + 1;
   D.max_fr = b->max_fr;
   D.stats = (double*)ctx->d_stats.p; D.header = (double*)ctx->d_header.p; D.scratch = (double*)ctx->d_scratch.p;
   AfxCondPlan& C = b->cond;
@@ -799,7 +814,7 @@ extern "C" int64_t afx_batch_conditioned(const afx_batch* b, int32_t i, double* 
 }
 
 // ---- test hook: the FFT core on caller data -------------------------------------------------------------
-int afx_debug_fft_launch(int n, int batch, const double2* in, double2* out, const double2* tw2048, cudaStream_t s);
+int afx_debug_fft_launch(int n, int batch, const double2* in, double2* out, const AfxTables& T, cudaStream_t s);
 extern "C" int afx_debug_fft(afx_ctx* ctx, int32_t n, int32_t batch, const double* in, double* out)
 {
   if (!ctx || !in || !out || batch <= 0 || (n != 256 && n != 1024 && n != 2048)) return fail(ctx, AFX_ERR_ARG, "afx_debug_fft: bad arguments");
@@ -808,7 +823,7 @@ extern "C" int afx_debug_fft(afx_ctx* ctx, int32_t n, int32_t batch, const doubl
   double2 *di = nullptr, *dout = nullptr;
   CK(cudaMalloc(&di, bytes), "cudaMalloc"); CK(cudaMalloc(&dout, bytes), "cudaMalloc");
   cudaMemcpy(di, in, bytes, cudaMemcpyHostToDevice);
-  afx_debug_fft_launch(n, batch, di, dout, ctx->P.t.tw2048, ctx->stream);
+  afx_debug_fft_launch(n, batch, di, dout, ctx->P.t, ctx->stream);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost);
   cudaFree(di); cudaFree(dout);

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(AW * 32) k_autocorr(AfxBatchDev B, AfxParams P
   const int rel = blockIdx.x * AW + wid;
   if (rel >= B.g_slots) return;                    // warp-uniform; only warp-level sync below
   const int slot = B.slot0 + rel;
-  const int fi = find_file_by_frame(B.files, B.n_files, slot);
+  const int fi = B.slot_file[slot];
   const AfxFile f = B.files[fi];
   const AfxState st = B.state[fi];
   const int t = slot - f.frame_off;

@@ -1,4 +1,5 @@
-// K4: band projections of the magnitude spectrum, one CTA (8 warps) per main frame, no block-wide sort.
+// K4: band projections of the magnitude spectrum: a selection kernel (one warp per sub-band role and frame)
+// and an epilogue kernel (one lane per sub-band); no sort, no block-wide barrier.
 //
 //   * 14 sub-bands (SampleAnalyser.cpp:2067-2260): rms, flatness (dB scaled), flux (Pearson correlation
 //     with the previous frame), complexity (strict local maxima above 0.25 x band max) and contrast
@@ -21,7 +22,8 @@
 __device__ __forceinline__ double warp_sum_d(double v) { return warp_sum(v); }
 
 // raw per-band sums handed from the band's warp to the epilogue lane
-struct BandRaw { double s1, s2, s11, s12, s22, ls, x0, lo_sum, hi_sum; int cplx, pad; };
+struct BandRaw { double s1, s2, s11, s12, s22, ls, x0, lo_sum, hi_sum, cplx; };   // 10 doubles
+#define BR_STRIDE 154      // doubles per frame: 14 x BandRaw + 14 mel energies
 
 // per-band epilogue (one lane per band, all 14 in lock step so the pow / log / exp chains run once)
 __device__ __forceinline__ double band_write(AfxBatchDev& B, size_t TF, int slot, int b, int n, int nei, const BandRaw& r)
@@ -36,7 +38,7 @@ __device__ __forceinline__ double band_write(AfxBatchDev& B, size_t TF, int slot
   const double den2 = (r.s11 - m1 * m1 * dn) * (r.s22 - m2 * m2 * dn);
   const double num = r.s12 - (m1 * m2 * dn);
   B.fv[(size_t)FV_FLUX * TF + o] = (fabs(den2) > (double)1e-12f) ? num / sqrt(den2) : 0.0;
-  B.fv[(size_t)FV_COMPLEXITY * TF + o] = (double)r.cplx;
+  B.fv[(size_t)FV_COMPLEXITY * TF + o] = r.cplx;
   const double valley = r.lo_sum / nei + 1e-30, peak = r.hi_sum / nei + 1e-30;      // SampleAnalyser.cpp:2199-2232
   const double c = -1.0 * pow(peak / valley, 1.0 / log(mean + 1e-30));
   B.fv[(size_t)FV_CONTRAST * TF + o] = c;
@@ -163,7 +165,7 @@ __device__ __forceinline__ void subband(const AfxParams& P, int b, const double*
   const double x0 = __shfl_sync(0xffffffffu, x[0], 0);
   if (lane == 0) {
     BandRaw& r = raw[b];
-    r.s1 = s1; r.s2 = s2; r.s11 = s11; r.s12 = s12; r.s22 = s22; r.ls = ls; r.x0 = x0; r.lo_sum = lo_sum; r.hi_sum = hi_sum; r.cplx = cplx;
+    r.s1 = s1; r.s2 = s2; r.s11 = s11; r.s12 = s12; r.s22 = s22; r.ls = ls; r.x0 = x0; r.lo_sum = lo_sum; r.hi_sum = hi_sum; r.cplx = (double)cplx;
   }
 }
 
@@ -187,60 +189,75 @@ __device__ __forceinline__ void bands28(AfxBatchDev& B, const AfxParams& P, size
   }
 }
 
-__global__ void __launch_bounds__(BT, 4) k_bands(AfxBatchDev B, AfxParams P)
+// Phase A: grid (frames / 8, 8 roles).  All warps of a CTA run the SAME role (same code, same duration) on 8
+// different frames and never synchronise; the raw sums go to a per-frame scratch record in global memory.
+__global__ void __launch_bounds__(BT) k_bands_a(AfxBatchDev B, AfxParams P)
 {
-  __shared__ BandRaw raw[14];
-  __shared__ double lg[16];
-  __shared__ double contrast[16];
-  __shared__ int s_file;
-
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int slot = B.slot0 + blockIdx.x;
-  if (tid == 0) s_file = find_file_by_frame(B.files, B.n_files, slot);
-  __syncthreads();
-  const int fi = s_file;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rel = blockIdx.x * 8 + wid;
+  if (rel >= B.g_slots) return;
+  const int slot = B.slot0 + rel;
+  const int fi = B.slot_file[slot];
   const AfxFile f = B.files[fi];
   const int t = slot - f.frame_off;
   if (f.status != 0 || t >= B.state[fi].F) return;
   const size_t TF = (size_t)B.TF;
-  const double* __restrict__ g = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
+  const double* __restrict__ g = B.mag + (size_t)rel * AFX_NBIN;
   const double* __restrict__ gp = (t > 0) ? g - AFX_NBIN : g;              // SampleAnalyser.cpp:936-940
-
-  // ---- phase 1: every warp owns sub-bands (+ a share of the mel / 28-band sums), results to shared memory ----
-  switch (wid) {
+  BandRaw* raw = reinterpret_cast<BandRaw*>(B.bandraw + (size_t)rel * BR_STRIDE);
+  double* lg = B.bandraw + (size_t)rel * BR_STRIDE + 140;
+  const int role = blockIdx.y;
+  switch (role) {
     case 7: subband<9>(P, 13, g, gp, lane, raw); break;
     case 6: subband<5>(P, 12, g, gp, lane, raw); break;
     case 5: subband<3>(P, 11, g, gp, lane, raw); mel_energy(P, 12, g, lane, lg); mel_energy(P, 13, g, lane, lg); break;
     case 4: subband<2>(P, 10, g, gp, lane, raw); subband<2>(P, 9, g, gp, lane, raw); break;
     default: {
-      // warps 0..3: the nine bands of <= 32 bins (one code instance, looped), the mel energies and the 28 bands
-      const int first = (wid == 3) ? 7 : (wid == 2) ? 5 : (wid == 1) ? 2 : 0;
-      const int last = (wid == 3) ? 8 : (wid == 2) ? 6 : (wid == 1) ? 4 : 1;
+      // roles 0..3: the nine bands of <= 32 bins (one code instance, looped), the mel energies and the 28 bands
+      const int first = (role == 3) ? 7 : (role == 2) ? 5 : (role == 1) ? 2 : 0;
+      const int last = (role == 3) ? 8 : (role == 2) ? 6 : (role == 1) ? 4 : 1;
       for (int b = last; b >= first; --b) subband<1>(P, b, g, gp, lane, raw);
-      if (wid >= 2) { for (int q = (wid == 3 ? 8 : 0); q < (wid == 3 ? 12 : 8); ++q) mel_energy(P, q, g, lane, lg); }
-      else bands28(B, P, TF, slot, wid == 1 ? 14 : 0, wid == 1 ? 28 : 14, g, lane);
+      if (role >= 2) { for (int q = (role == 3 ? 8 : 0); q < (role == 3 ? 12 : 8); ++q) mel_energy(P, q, g, lane, lg); }
+      else bands28(B, P, TF, slot, role == 1 ? 14 : 0, role == 1 ? 28 : 14, g, lane);
     } break;
   }
-  __syncthreads();
-  // ---- phase 2: one lane per band / per mel filter for the transcendental epilogues ------------------------
-  if (tid < 14) contrast[tid] = band_write(B, TF, slot, tid, P.band14_n[tid], P.band14_nei[tid], raw[tid]);
-  else if (tid >= 32 && tid < 46) { const double e = lg[tid - 32]; lg[tid - 32] = log(e < 2e-42 ? 2e-42 : e); }   // XTRACT_LOG_LIMIT
-  __syncthreads();
-  // ---- phase 3: DCT of the log mel energies (vector.c:372-391) and the mean contrast -------------------------
-  if (tid < 14) {
-    double a = 0.0;
-    for (int m = 0; m < 14; ++m) a += lg[m] * __ldg(P.t.dct + tid * 14 + m);
-    B.fv[(size_t)FV_CEPSTRUM * TF + (size_t)slot * 14 + tid] = a;
+}
+
+// Phase B: 16 lanes per frame; lane j < 14 finishes sub-band j (the pow / log / exp chains run on full warps)
+// and takes the log of mel energy j; the DCT (vector.c:372-391) and the mean contrast go through shuffles.
+__global__ void __launch_bounds__(BT) k_bands_b(AfxBatchDev B, AfxParams P)
+{
+  const int j = threadIdx.x & 15;
+  const int rel = (blockIdx.x * BT + threadIdx.x) >> 4;
+  const bool in_range = rel < B.g_slots;
+  const int slot = B.slot0 + (in_range ? rel : 0);
+  const int fi = B.slot_file[slot];
+  const AfxFile f = B.files[fi];
+  const int t = slot - f.frame_off;
+  const bool live = in_range && f.status == 0 && t < B.state[fi].F;
+  const size_t TF = (size_t)B.TF;
+  double c = 0.0, lg = 0.0;
+  if (live && j < 14) {
+    const BandRaw r = reinterpret_cast<const BandRaw*>(B.bandraw + (size_t)rel * BR_STRIDE)[j];
+    c = band_write(B, TF, slot, j, P.band14_n[j], P.band14_nei[j], r);
+    const double e = B.bandraw[(size_t)rel * BR_STRIDE + 140 + j];
+    lg = log(e < 2e-42 ? 2e-42 : e);                       // XTRACT_LOG_LIMIT
   }
-  if (tid == 32) {
-    double s = 0.0;
-    for (int b = 0; b < 14; ++b) s += contrast[b];
-    B.fs[(size_t)FS_SPEC_CONTRAST * TF + slot] = s / 14.0;
+  double a = 0.0, csum = 0.0;
+#pragma unroll
+  for (int m = 0; m < 14; ++m) {
+    const double lm = __shfl_sync(0xffffffffu, lg, m, 16);
+    const double cm = __shfl_sync(0xffffffffu, c, m, 16);
+    if (j < 14) a += lm * __ldg(P.t.dct + j * 14 + m);
+    csum += cm;
   }
+  if (live && j < 14) B.fv[(size_t)FV_CEPSTRUM * TF + (size_t)slot * 14 + j] = a;
+  if (live && j == 0) B.fs[(size_t)FS_SPEC_CONTRAST * TF + slot] = csum / 14.0;
 }
 
 void afx_launch_bands(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  k_bands<<<B.g_slots, BT, 0, s>>>(B, P); ++*launches;
+  k_bands_a<<<dim3((B.g_slots + 7) / 8, 8), BT, 0, s>>>(B, P); ++*launches;
+  k_bands_b<<<(B.g_slots * 16 + BT - 1) / BT, BT, 0, s>>>(B, P); ++*launches;
 }

@@ -74,6 +74,10 @@ struct AfxTables {          // per-context constant tables in device memory
   const double* window;     // [2048] Hann * 2
   const double2* tw2048;    // [2048] exp(-2 pi i k / 2048)
   const double2* tw512;     // [512]  exp(-2 pi i k / 512)
+  // FFT pass twiddles laid out in access order (coalesced): afx_fft16.cuh
+  const double2* fft_t2;        // [15][16]  exp(-2 pi i r k / 256),  r = 1..15
+  const double2* fft_t3_1024;   // [3][256]  exp(-2 pi i r j / 1024), r = 1..3
+  const double2* fft_t3_2048;   // [7][256]  exp(-2 pi i r j / 2048), r = 1..7
   const double* rwindow;    // [512] rhythm Hann
   const double* mel;        // [14][1024]
   const double* dct;        // [14][14] cos(pi n/14 (m+0.5)), row n
@@ -199,6 +203,10 @@ __device__ __forceinline__ int block_min_i(int v, int* scratch)
   return t;
 }
 
+// aubio_silence_detection (mathutils.c:345-357, 606-615): 10 log10(mean square) < -48 dB.  log10 is monotonic,
+// so the test is a comparison of the mean square with 10^-4.8 (saves a serial double log10 per frame)
+#define AFX_SILENCE_LEVEL 1.5848931924611134e-05
+
 // TAudioMath::LinToDb(double), AudioTypes/Export/AudioMath.inl:55-70 (MEpsilon is a float literal)
 __device__ __forceinline__ double lin_to_db(double v)
 {
@@ -244,8 +252,11 @@ struct AfxBatchDev {
   float* mono_src;
   const AfxFile* files;
   AfxState* state;
+  const int* slot_file;   // [TF]  main frame slot -> file index (built on the device by k_slotmap)
+  const int* rslot_file;  // [TFr] rhythm frame slot -> file index
   double* mag;        // [g_slots][1024]   (group scratch, indexed by slot - slot0)
   double* cent_full;  // [TF] centroid of mag[0..1023] (failsafe f0)
+  double* bandraw;    // [g_slots][154] raw sub-band sums (14 x 10) + mel energies (14)   (group scratch)
   double* fs;         // [22][TF]
   double* fsr;        // [2][TFr]
   double* fv;         // 7 arrays [TF][nb], array v at fv + FV_x * TF

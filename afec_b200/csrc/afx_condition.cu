@@ -282,6 +282,16 @@ __global__ void k_header(AfxBatchDev B, AfxParams P)
   H[H_DATA_OFFSET] = st.data_offset; H[H_DATA_LEN] = st.len;
 }
 
+// slot -> file maps: every frame-level kernel starts from its slot index, one coalesced table look-up replaces a
+// 14-step dependent binary search over the file table
+__global__ void __launch_bounds__(256) k_slotmap(AfxBatchDev B, int* __restrict__ slot_file, int* __restrict__ rslot_file)
+{
+  const int fi = blockIdx.x;
+  const AfxFile f = B.files[fi];
+  for (int i = threadIdx.x; i < f.frame_cap; i += 256) slot_file[f.frame_off + i] = fi;
+  for (int i = threadIdx.x; i < f.rframe_cap; i += 256) rslot_file[f.rframe_off + i] = fi;
+}
+
 __global__ void k_state_init(AfxBatchDev B)
 {
   const int fi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,6 +316,7 @@ void afx_launch_condition_plan(const AfxParams& P, const AfxBatchDev& B, const A
   if (B.n_files <= 0) return;
   const int fb = (B.n_files + 127) / 128;
   k_state_init<<<fb, 128, 0, s>>>(B); ++*launches;
+  k_slotmap<<<B.n_files, 256, 0, s>>>(B, const_cast<int*>(B.slot_file), const_cast<int*>(B.rslot_file)); ++*launches;
   if (C.n_src_chunks > 0) { k_downmix<<<C.n_src_chunks, CT, 0, s>>>(B, C.src_chunk_file, C.src_chunk_start, P.sr); ++*launches; }
   if (C.n_rs_blocks > 0) {
     k_resample<<<C.n_rs_blocks, 128, 0, s>>>(B, P.t, C.rs_blocks, C.rs_blk_file, C.rs_times, C.n_rs_blocks, P.sr); ++*launches;

@@ -8,7 +8,8 @@
 //   output : X[j] at buf[FFT_PHYS(j)]           natural order, followed by a group sync
 //   buf    : N + N/16 double2 (one pad element per 16: keeps the stride-16 stores of the first pass and
 //            the stride-NT loads of the later passes on distinct banks)
-//   tw     : exp(-2 pi i j / TWN), TWN a multiple of N
+//   tw     : per-pass twiddle tables stored in the order the threads read them (FftTw), so a warp's twiddle
+//            load is one or two contiguous lines instead of up to 32 scattered ones
 //   sync   : functor synchronising the NT threads (__syncthreads, a named barrier or __syncwarp)
 //
 // A single buffer is enough: every pass first pulls its 16 inputs into registers, syncs, then writes.
@@ -89,9 +90,13 @@ struct FftSyncNamed {       // NT threads (a multiple of 32) sharing barrier `id
   __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(NT) : "memory"); }
 };
 
-template <int N, int TWN, class Sync>
-__device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict__ buf, const double2* __restrict__ tw,
-                                          int tid, Sync sync)
+struct FftTw {
+  const double2* t2;     // [15][16]     exp(-2 pi i r k / 256)
+  const double2* t3;     // [R - 1][256] exp(-2 pi i r j / N), R = 4 (N = 1024) or 8 (N = 2048); unused for N = 256
+};
+
+template <int N, class Sync>
+__device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict__ buf, const FftTw tw, int tid, Sync sync)
 {
   constexpr int NT = N / 16;
   static_assert(N == 256 || N == 1024 || N == 2048, "supported sizes");
@@ -106,9 +111,8 @@ __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict_
   sync();
   {
     const int k = tid & 15;
-    constexpr int step = TWN / 256;
 #pragma unroll
-    for (int r = 1; r < 16; ++r) v[r] = f_mul(v[r], __ldg(tw + (r * k) * step));
+    for (int r = 1; r < 16; ++r) v[r] = f_mul(v[r], __ldg(tw.t2 + (r - 1) * 16 + k));
     f_dft16(v);
     const int base = (tid - k) * 16 + k;
 #pragma unroll
@@ -123,12 +127,11 @@ __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict_
 #pragma unroll
       for (int r = 0; r < 4; ++r) v[4 * b + r] = buf[FFT_PHYS(tid + NT * b + r * 256)];
     sync();
-    constexpr int step = TWN / 1024;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int i = tid + NT * b;          // k = i (i < p = 256)
 #pragma unroll
-      for (int r = 1; r < 4; ++r) v[4 * b + r] = f_mul(v[4 * b + r], __ldg(tw + (r * i) * step));
+      for (int r = 1; r < 4; ++r) v[4 * b + r] = f_mul(v[4 * b + r], __ldg(tw.t3 + (r - 1) * 256 + i));
       f_r4(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) buf[FFT_PHYS(i + q * 256)] = v[4 * b + q];
@@ -140,12 +143,11 @@ __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict_
 #pragma unroll
       for (int r = 0; r < 8; ++r) v[8 * b + r] = buf[FFT_PHYS(tid + NT * b + r * 256)];
     sync();
-    constexpr int step = TWN / 2048;
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       const int i = tid + NT * b;
 #pragma unroll
-      for (int r = 1; r < 8; ++r) v[8 * b + r] = f_mul(v[8 * b + r], __ldg(tw + (r * i) * step));
+      for (int r = 1; r < 8; ++r) v[8 * b + r] = f_mul(v[8 * b + r], __ldg(tw.t3 + (r - 1) * 256 + i));
     }
     f_dft8<0>(v);
     f_dft8<8>(v);

@@ -49,13 +49,10 @@ __global__ void __launch_bounds__(YT, 3) k_pitch(AfxBatchDev B, AfxParams P)
   double* yin = S + (YN + YN / 16 + 8);                                // [PAD8(1024)]
   __shared__ double scratch[32];
   __shared__ int iscr[32];
-  __shared__ int s_file;
 
   const int tid = threadIdx.x;
   const int slot = B.slot0 + blockIdx.x;
-  if (tid == 0) s_file = find_file_by_frame(B.files, B.n_files, slot);
-  __syncthreads();
-  const int fi = s_file;
+  const int fi = B.slot_file[slot];
   const AfxFile f = B.files[fi];
   const AfxState st = B.state[fi];
   const int t = slot - f.frame_off;
@@ -64,26 +61,28 @@ __global__ void __launch_bounds__(YT, 3) k_pitch(AfxBatchDev B, AfxParams P)
   const float* __restrict__ mono = B.mono + f.mono_off;
   FftSyncBlock sync;
 
-  // ---- prefix sums of squares: 16 consecutive samples per thread ---------------------------------
-  {
-    double x[16]; double loc = 0.0;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { x[q] = mdata(mono, st, n0 + 16 * tid + q); loc += x[q] * x[q]; }
-    double pre = block_scan_excl(loc, scratch, nullptr);
-    if (tid == 0) S[0] = 0.0;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { pre += x[q] * x[q]; S[PAD16(16 * tid + q + 1)] = pre; }
-  }
-
-  // ---- z = a + i b, strided per thread as the FFT wants it; forward FFT --------------------------------
+  // ---- one coalesced pass over the frame: z = a + i b in the FFT's strided order, squares to shared memory ----
   double2 v[16];
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     const int m = tid + YT * r;
     const double xv = mdata(mono, st, n0 + m);
     v[r] = make_double2(m < YW ? xv : 0.0, xv);
+    S[PAD16(m)] = xv * xv;
   }
-  fft16_run<YN, YN>(v, buf, P.t.tw2048, tid, sync);
+  __syncthreads();
+  // ---- prefix sums of squares: 16 consecutive samples per thread (padded -> conflict free) -----------------
+  {
+    double q2[16]; double loc = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { q2[q] = S[PAD16(16 * tid + q)]; loc += q2[q]; }
+    double pre = block_scan_excl(loc, scratch, nullptr);      // its first barrier: every square has been read
+    if (tid == 0) S[0] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { pre += q2[q]; S[PAD16(16 * tid + q + 1)] = pre; }
+  }
+  const FftTw ftw = { P.t.fft_t2, P.t.fft_t3_2048 };
+  fft16_run<YN>(v, buf, ftw, tid, sync);
   // split into A (transform of a) and B (of b), O = conj(conj(A) B); every thread builds its own 16 inputs
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
@@ -97,7 +96,7 @@ __global__ void __launch_bounds__(YT, 3) k_pitch(AfxBatchDev B, AfxParams P)
     v[r] = make_double2(Pk.x, -Pk.y);
   }
   __syncthreads();                                               // all reads of buf done before it is rewritten
-  fft16_run<YN, YN>(v, buf, P.t.tw2048, tid, sync);
+  fft16_run<YN>(v, buf, ftw, tid, sync);
 
   // ---- difference function (elementwise, tau = tid + 128 c) ------------------------------------------
   const double sW = S[PAD16(YW)];
@@ -159,14 +158,14 @@ __global__ void __launch_bounds__(YT, 3) k_pitch(AfxBatchDev B, AfxParams P)
     unsigned peak_pos = 0;
     if (period == period && period >= 0.0 && period < (double)YW) peak_pos = (unsigned)period;
     double pitch = (period > 0.0) ? (double)P.sr / (period + 0.) : 0.0;                  // pitch.c:450-462
-    const bool silent_frame = (10.0 * log10(S[PAD16(YN)] / (double)YN) < -48.0);         // pitch.c:399-407
+    const bool silent_frame = (S[PAD16(YN)] / (double)YN) < AFX_SILENCE_LEVEL;         // pitch.c:399-407
     if (silent_frame) pitch = 0.0;
     double conf = (1.0 - yin[PAD8(peak_pos)]) / 0.25;                                    // SA.cpp:887-889
     conf = conf < 0.0 ? 0.0 : (conf > 1.0 ? 1.0 : conf);
     double fsafe = 0.0;                                                                  // SA.cpp:897-916
     if (pitch > 0.0 && conf > 0.2) fsafe = pitch;
     else {
-      const bool silent_hop = (10.0 * log10(S[PAD16(P.H)] / (double)P.H) < -48.0);
+      const bool silent_hop = (S[PAD16(P.H)] / (double)P.H) < AFX_SILENCE_LEVEL;
       if (!silent_hop) { const double c = B.cent_full[slot]; fsafe = (double)P.sr / (double)P.N * (c > 0.0 ? c : 0.0); }
     }
     const size_t TF = (size_t)B.TF;
@@ -179,8 +178,9 @@ __global__ void __launch_bounds__(YT, 3) k_pitch(AfxBatchDev B, AfxParams P)
 void afx_launch_pitch(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  static bool attr_set = false;
   const int smem = (YN + YN / 16) * (int)sizeof(double2) + (YN + YN / 16 + 8) * (int)sizeof(double) + (YW + YW / 8 + 8) * (int)sizeof(double);
-  if (!attr_set) { cudaFuncSetAttribute(k_pitch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+  // per launch: function attributes are per device, and one process may drive several devices
+  cudaFuncSetAttribute(k_pitch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_pitch, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   k_pitch<<<B.g_slots, YT, smem, s>>>(B, P); ++*launches;
 }

@@ -38,6 +38,29 @@ __device__ __forceinline__ float phase_rewrap(float p)
   return __fadd_rn(p, __fmul_rn(twopi, k));
 }
 
+// atan2 for the float32 phase column.  The reference computes atan2 in double and rounds to float
+// (OnsetDetector.cpp:136-155); the result only has to be right to well below a float ulp (2.4e-7 at pi), so one
+// division, an octant reduction to |w| <= tan(pi/8) and the Taylor series through w^21 (error < 7e-11) replace
+// libdevice's fully rounded double atan2 -- a third of its FP64 work.
+__device__ __forceinline__ double atan2_phase(double y, double x)
+{
+  const double ax = fabs(x), ay = fabs(y);
+  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  if (mx == 0.0) return 0.0;
+  const bool hi = mn > 0.41421356237309503 * mx;           // beyond pi/8: atan(z) = pi/4 + atan((z - 1) / (z + 1))
+  const double w = (hi ? mn - mx : mn) / (hi ? mn + mx : mx);
+  const double w2 = w * w;
+  double p = -1.0 / 21.0;
+  p = fma(p, w2, 1.0 / 19.0); p = fma(p, w2, -1.0 / 17.0); p = fma(p, w2, 1.0 / 15.0); p = fma(p, w2, -1.0 / 13.0);
+  p = fma(p, w2, 1.0 / 11.0); p = fma(p, w2, -1.0 / 9.0); p = fma(p, w2, 1.0 / 7.0); p = fma(p, w2, -1.0 / 5.0);
+  p = fma(p, w2, 1.0 / 3.0);
+  double r = fma(-(p * w2), w, w);                          // w - w^3 / 3 + ...
+  if (hi) r += 0.78539816339744830962;
+  if (ay > ax) r = 1.57079632679489661923 - r;
+  if (x < 0.0) r = 3.14159265358979323846 - r;
+  return (y < 0.0) ? -r : r;
+}
+
 // -------------------------------------------------------------------------------------------------
 // 16 threads per rhythm frame (256-point packed transform = radix 16 x 16 in registers), two frames per warp
 #define PF 8                // frames per CTA (4 warps)
@@ -49,7 +72,7 @@ __global__ void __launch_bounds__(PF * 16) k_rhythm_polar(AfxBatchDev B, AfxPara
   const int rel = blockIdx.x * PF + h;
   const bool in_range = rel < B.g_rslots;
   const int slot = B.rslot0 + (in_range ? rel : 0);
-  const int fi = find_file_by_rframe(B.files, B.n_files, slot);
+  const int fi = B.rslot_file[slot];
   const AfxFile f = B.files[fi];
   const int t = slot - f.rframe_off;
   const AfxState st = B.state[fi];
@@ -65,7 +88,7 @@ __global__ void __launch_bounds__(PF * 16) k_rhythm_polar(AfxBatchDev B, AfxPara
     const double x0 = live ? mdata(mono, st, n0 + 2 * m) : 0.0, x1 = live ? mdata(mono, st, n0 + 2 * m + 1) : 0.0;
     v[r] = make_double2(w.x * x0, w.y * x1);                                        // OnsetDetector.cpp:119-120
   }
-  fft16_run<256, AFX_RFFT>(v, buf, P.t.tw512, ht, FftSyncWarp());
+  fft16_run<256>(v, buf, FftTw{ P.t.fft_t2, nullptr }, ht, FftSyncWarp());
   if (!live) return;
   float* row = B.rpolar + (size_t)rel * AFX_RROW;
 #pragma unroll
@@ -80,7 +103,7 @@ __global__ void __launch_bounds__(PF * 16) k_rhythm_polar(AfxBatchDev B, AfxPara
     if (k == 0) { X.y = 0.0; row[255] = (float)X.x; }                             // mDC, OnsetDetector.cpp:146
     if (k < AFX_RBINS) {
       row[k] = (float)sqrt(X.x * X.x + X.y * X.y);                                // :136-155
-      row[256 + k] = (float)atan2(X.y, X.x);
+      row[256 + k] = (float)atan2_phase(X.y, X.x);
     }
   }
 }
@@ -127,7 +150,7 @@ __global__ void __launch_bounds__(RPW * 32) k_rhythm_odf(AfxBatchDev B, AfxParam
   const int rel = blockIdx.x * RPW + wid;
   if (rel >= B.g_rslots) return;
   const int slot = B.rslot0 + rel;
-  const int fi = find_file_by_rframe(B.files, B.n_files, slot);
+  const int fi = B.rslot_file[slot];
   const AfxFile f = B.files[fi];
   const int t = slot - f.rframe_off;
   if (f.status != 0 || t >= B.state[fi].Fr) return;
@@ -197,7 +220,7 @@ __global__ void __launch_bounds__(64) k_rhythm_median(AfxBatchDev B)
   float* __restrict__ post = B.rpost + (size_t)ty * B.TFr;
   int slot = B.rslot0 + chunk * ML;
   const int s_end = min(slot + ML, B.rslot0 + B.g_rslots);
-  int fi = find_file_by_rframe(B.files, B.n_files, slot);
+  int fi = B.rslot_file[slot];
   float s[MEDSPAN];
   while (slot < s_end && fi < B.n_files) {
     const AfxFile f = B.files[fi];
@@ -540,13 +563,9 @@ __global__ void __launch_bounds__(BT_THREADS) k_rhythm_back(AfxBatchDev B, AfxPa
 void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
   if (B.g_files <= 0 || B.g_rslots <= 0) return;
-  static bool attr_set = false;
   const int cap = B.max_fr;
   const int smem_back = cap * 8 + ((cap + 15) & ~15) + ((cap + 31) / 32) * 4 + 16;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_rhythm_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(k_rhythm_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);   // per device, see afx_pitch.cu
   const int fb = (B.g_rslots + RPW - 1) / RPW;
   k_rhythm_polar<<<(B.g_rslots + PF - 1) / PF, PF * 16, 0, s>>>(B, P); ++*launches;
   k_rhythm_whiten<<<B.g_files, 256, 0, s>>>(B, P); ++*launches;

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(SG * SF, 3) k_spectrum(AfxBatchDev B, AfxParam
   const int rel = blockIdx.x * SF + g;
   if (rel >= B.g_slots) return;                      // group-uniform; only the group's named barrier is used below
   const int slot = B.slot0 + rel;
-  const int fi = find_file_by_frame(B.files, B.n_files, slot);
+  const int fi = B.slot_file[slot];
   const AfxFile f = B.files[fi];
   const AfxState st = B.state[fi];
   const int t = slot - f.frame_off;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(SG * SF, 3) k_spectrum(AfxBatchDev B, AfxParam
     emax = group_max(emax, xch, gt, sync);
     if (gt == 0) {
       const double level = ev[0] / (double)P.H;
-      B.fs[(size_t)FS_AMP_SILENCE * TF + slot] = (10.0 * log10(level) < -48.0) ? 1.0 : 0.0;   // mathutils.c:606-615
+      B.fs[(size_t)FS_AMP_SILENCE * TF + slot] = (level < AFX_SILENCE_LEVEL) ? 1.0 : 0.0;   // mathutils.c:606-615
       B.fs[(size_t)FS_AMP_PEAK * TF + slot] = pk;
       const double r = sqrt(level);
       B.fs[(size_t)FS_AMP_RMS * TF + slot] = (r != r) ? 0.0 : r;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(SG * SF, 3) k_spectrum(AfxBatchDev B, AfxParam
     const double2 w = __ldg(win2 + m);
     v[r] = make_double2(mdata(mono, st, n0 + 2 * m) * w.x, mdata(mono, st, n0 + 2 * m + 1) * w.y);
   }
-  fft16_run<AFX_NBIN, AFX_NFFT>(v, buf, P.t.tw2048, gt, sync);
+  fft16_run<AFX_NBIN>(v, buf, FftTw{ P.t.fft_t2, P.t.fft_t3_1024 }, gt, sync);
 
   // ---- real unpack + magnitude / N for bins gt + 64 c (Fourier.cpp:266-271, AudioMath.cpp:497-504) ---------
   double m16[16];
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P)
   const int lane = threadIdx.x & 31;
   const int slot = B.slot0 + blockIdx.x * 8 + (threadIdx.x >> 5);
   if (slot >= B.slot0 + B.g_slots) return;
-  const int fi = find_file_by_frame(B.files, B.n_files, slot);
+  const int fi = B.slot_file[slot];
   const AfxFile f = B.files[fi];
   const int t = slot - f.frame_off;
   if (f.status != 0 || t >= B.state[fi].F) return;
@@ -239,9 +239,9 @@ __global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P)
 void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  static bool attr_set = false;
   const int smem = SF * (AFX_NBIN + AFX_NBIN / 16) * (int)sizeof(double2) + SF * 16 * (int)sizeof(double);
-  if (!attr_set) { cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+  cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device, see afx_pitch.cu
+  cudaFuncSetAttribute(k_spectrum, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   k_spectrum<<<(B.g_slots + SF - 1) / SF, SG * SF, smem, s>>>(B, P, features); ++*launches;
   k_flux<<<(B.g_slots + 7) / 8, 256, 0, s>>>(B, P); ++*launches;
 }
