@@ -604,11 +604,12 @@ extern "C" int afx_batch_compute(afx_batch* b)
     if (feat & (AFX_FEAT_SPECTRAL | AFX_FEAT_AMPLITUDE | AFX_FEAT_PEAKS | AFX_FEAT_BANDS | AFX_FEAT_PITCH)) {
       ktime_begin(b, "spectrum"); afx_launch_spectrum(ctx->P, D, feat, ctx->stream, &b->launches); ktime_end(b);
     }
-#ifdef AFX_HAVE_PEAKS
-    if (feat & AFX_FEAT_PEAKS) { ktime_begin(b, "peaks"); afx_launch_peaks(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
-#endif
 #ifdef AFX_HAVE_BANDS
     if (feat & AFX_FEAT_BANDS) { ktime_begin(b, "bands"); afx_launch_bands(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
+#endif
+    // peaks last among the users of the magnitude rows: its whitening pass overwrites them in place
+#ifdef AFX_HAVE_PEAKS
+    if (feat & AFX_FEAT_PEAKS) { ktime_begin(b, "peaks"); afx_launch_peaks(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
 #endif
 #ifdef AFX_HAVE_PITCH
     if (feat & AFX_FEAT_PITCH) { ktime_begin(b, "pitch"); afx_launch_pitch(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }

@@ -342,6 +342,29 @@ __device__ double r_onset_match_conf(int sr, const double* raw, int n, double of
 }
 
 // block-wide sum / max of one double (blockDim.x == BT_THREADS); result broadcast
+// nine consecutive lags of the beat tracker's autocorrelation (mathutils.c:652-666) on one thread: a sliding
+// 9-sample register window turns every pair of shared-memory loads into 9 DFMAs (same tiling as k_autocorr).
+// x must be readable (zero) up to index n + 17.
+#define RB_AL 9
+__device__ __forceinline__ void rb_acf_group(const double* __restrict__ x, int n, int g, double* __restrict__ acf)
+{
+  const int i0 = g * RB_AL;
+  const int nj = n - i0;
+  double acc[RB_AL], w[RB_AL];
+#pragma unroll
+  for (int q = 0; q < RB_AL; ++q) { acc[q] = 0.0; w[q] = x[i0 + q]; }
+  for (int j = 0; j < nj; ++j) {
+    const double a = x[j];
+#pragma unroll
+    for (int q = 0; q < RB_AL; ++q) acc[q] = fma(a, w[q], acc[q]);
+#pragma unroll
+    for (int q = 0; q < RB_AL - 1; ++q) w[q] = w[q + 1];
+    w[RB_AL - 1] = x[j + i0 + RB_AL];
+  }
+#pragma unroll
+  for (int q = 0; q < RB_AL; ++q) if (i0 + q < n) acf[i0 + q] = acc[q] / (double)(n - i0 - q);
+}
+
 __device__ __forceinline__ double rb_sum(double v, double* scr) { double a[1] = { v }; block_sum<1>(a, scr); return a[0]; }
 
 __global__ void __launch_bounds__(BT_THREADS) k_rhythm_back(AfxBatchDev B, AfxParams P)
@@ -360,7 +383,7 @@ __global__ void __launch_bounds__(BT_THREADS) k_rhythm_back(AfxBatchDev B, AfxPa
   if (n <= 0) return;
   const int cap = B.max_fr;
   double* s = reinterpret_cast<double*>(smem_raw);                        // [cap] sharpened onsets
-  unsigned char* lm = reinterpret_cast<unsigned char*>(s + cap);          // [cap] local-maximum flags
+  unsigned char* lm = reinterpret_cast<unsigned char*>(s + cap + 32);     // [cap] local-maximum flags (s is zero padded)
   unsigned* bits = reinterpret_cast<unsigned*>(lm + ((cap + 15) & ~15));  // [(cap + 31) / 32] candidate mask
   const int nw = (n + 31) >> 5;
   double* H = B.header + (size_t)fi * AFX_N_HEADER;
@@ -471,14 +494,16 @@ __global__ void __launch_bounds__(BT_THREADS) k_rhythm_back(AfxBatchDev B, AfxPa
     // ---- tempo: one fresh aubio beat tracker pass over the whole vector (RhythmTracker.cpp:155-230) ----
     if (cnt >= 4) {
       const int winlen = n, laglen = winlen / 4;
-      // autocorrelation (mathutils.c:652-666); lags i and winlen-1-i are paired for balance
-      for (int i = tid; i < (winlen + 1) / 2; i += BT_THREADS) {
-        const int i2 = winlen - 1 - i;
-        double t1 = 0.0, t2 = 0.0;
-        for (int j = i; j < winlen; ++j) t1 = fma(s[j - i], s[j], t1);
-        if (i2 != i) for (int j = i2; j < winlen; ++j) t2 = fma(s[j - i2], s[j], t2);
-        acf[i] = t1 / (double)(winlen - i);
-        if (i2 != i) acf[i2] = t2 / (double)(winlen - i2);
+      // autocorrelation (mathutils.c:652-666): register-tiled groups of 9 lags, groups g and G-1-g paired for balance
+      for (int i = n + tid; i < n + 32; i += BT_THREADS) s[i] = 0.0;
+      __syncthreads();
+      {
+        const int G = (winlen + RB_AL - 1) / RB_AL;
+        for (int g = tid; g < (G + 1) / 2; g += BT_THREADS) {
+          rb_acf_group(s, winlen, g, acf);
+          const int g2 = G - 1 - g;
+          if (g2 != g) rb_acf_group(s, winlen, g2, acf);
+        }
       }
       __syncthreads();
       // comb filterbank (beattracking.c:167-177) + Rayleigh weighting (:104-107, 180)
@@ -564,7 +589,7 @@ void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s,
 {
   if (B.g_files <= 0 || B.g_rslots <= 0) return;
   const int cap = B.max_fr;
-  const int smem_back = cap * 8 + ((cap + 15) & ~15) + ((cap + 31) / 32) * 4 + 16;
+  const int smem_back = (cap + 32) * 8 + ((cap + 15) & ~15) + ((cap + 31) / 32) * 4 + 16;
   cudaFuncSetAttribute(k_rhythm_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);   // per device, see afx_pitch.cu
   const int fb = (B.g_rslots + RPW - 1) / RPW;
   k_rhythm_polar<<<(B.g_rslots + PF - 1) / PF, PF * 16, 0, s>>>(B, P); ++*launches;
