@@ -58,6 +58,11 @@ struct afx_ctx {
   afx_config cfg;
   int device = 0;
   cudaStream_t stream = nullptr;
+  // side streams: the pitch, autocorrelation and rhythm chains only depend on the conditioned signal (pitch also on
+  // the spectrum's centroid), so they run beside the spectrum -> bands -> peaks chain and fill each other's idle pipes
+  cudaStream_t side[3] = { nullptr, nullptr, nullptr };
+  cudaEvent_t ev_fork = nullptr, ev_spec = nullptr, ev_join[3] = { nullptr, nullptr, nullptr };
+  bool multi_stream = true;
   AfxParams P;
   DevBuf tables;                      // all constant tables in one allocation
   DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf, d_rpost, d_bandraw, d_slotmap,
@@ -236,6 +241,11 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   ctx->debug_times = getenv("AFX_DEBUG_KERNEL_TIMES") && atoi(getenv("AFX_DEBUG_KERNEL_TIMES")) != 0;
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete ctx; return fail(nullptr, AFX_ERR_CUDA, "cudaStreamCreate", e); }
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) { e = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming); }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_spec, cudaEventDisableTiming);
+  if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaStreamCreate(side)", e); }
+  ctx->multi_stream = !ctx->debug_times && !(getenv("AFX_SINGLE_STREAM") && atoi(getenv("AFX_SINGLE_STREAM")) != 0);
 
   AfxParams& P = ctx->P;
   memset(&P, 0, sizeof(P));
@@ -341,6 +351,9 @@ extern "C" void afx_destroy(afx_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  for (int i = 0; i < 3; ++i) { if (ctx->side[i]) { cudaStreamSynchronize(ctx->side[i]); cudaStreamDestroy(ctx->side[i]); } if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_spec) cudaEventDestroy(ctx->ev_spec);
   DevBuf* bufs[] = { &ctx->tables, &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
     &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch };
   for (DevBuf* b : bufs) b->release();
@@ -390,7 +403,7 @@ extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_f
     d.status = AFX_FILE_OK;
     if (f.channels < 1 || f.channels > 8) d.status = AFX_FILE_BAD_CHANNELS;          // SA.cpp:472-477
     else if (f.nframes <= 0 || !f.pcm) d.status = AFX_FILE_EMPTY;                     // SA.cpp:479-482
-    else if (f.nframes > 0x7fffffffLL / 8 || f.src_rate <= 0 || (f.format != AFX_PCM_I16 && f.format != AFX_PCM_F32)) {
+    else if (f.nframes * f.channels > 0x7fffffffLL || f.src_rate <= 0 || (f.format != AFX_PCM_I16 && f.format != AFX_PCM_F32)) {
       delete b; return fail(ctx, AFX_ERR_ARG, "afx_batch_create: unsupported file description");
     }
     d.frame_off = (int)tf; d.rframe_off = (int)tfr; d.mono_off = mono_off; d.src_off = src_off; d.pcm_off = (long long)pcm_off;
@@ -598,28 +611,42 @@ extern "C" int afx_batch_compute(afx_batch* b)
   for (const auto& t : b->rs_tails)   // samples past what libresample delivers stay 0 (SA.cpp:579-580: zero-initialised buffer)
     CK(cudaMemsetAsync((float*)ctx->d_mono.p + t.off, 0, (size_t)t.count * 4, ctx->stream), "cudaMemsetAsync(mono tail)");
   ktime_begin(b, "condition"); afx_launch_condition_plan(ctx->P, b->dev, b->cond, ctx->stream, &b->launches); ktime_end(b);
+  const bool ms = ctx->multi_stream;
+  cudaStream_t s_main = ctx->stream;
+  cudaStream_t s_pitch = ms ? ctx->side[0] : s_main, s_ac = ms ? ctx->side[1] : s_main, s_rhythm = ms ? ctx->side[2] : s_main;
+  if (ms) {   // the side chains start once the conditioning is done
+    CK(cudaEventRecord(ctx->ev_fork, s_main), "cudaEventRecord");
+    for (int i = 0; i < 3; ++i) CK(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0), "cudaStreamWaitEvent");
+  }
   for (const auto& g : b->groups) {
     AfxBatchDev D = b->dev;
     D.file0 = g.file0; D.g_files = g.nfiles; D.slot0 = g.slot0; D.g_slots = g.nslots; D.rslot0 = g.rslot0; D.g_rslots = g.nrslots;
+    // every chain keeps to its own stream across groups, so the reuse of a chain's group scratch stays ordered
+#ifdef AFX_HAVE_AUTOCORR
+    if (feat & AFX_FEAT_AUTOCORR) { ktime_begin(b, "autocorr"); afx_launch_autocorr(ctx->P, D, s_ac, &b->launches); ktime_end(b); }
+#endif
+#ifdef AFX_HAVE_RHYTHM
+    if (feat & AFX_FEAT_RHYTHM) { ktime_begin(b, "rhythm"); afx_launch_rhythm(ctx->P, D, s_rhythm, &b->launches); ktime_end(b); }
+#endif
     if (feat & (AFX_FEAT_SPECTRAL | AFX_FEAT_AMPLITUDE | AFX_FEAT_PEAKS | AFX_FEAT_BANDS | AFX_FEAT_PITCH)) {
-      ktime_begin(b, "spectrum"); afx_launch_spectrum(ctx->P, D, feat, ctx->stream, &b->launches); ktime_end(b);
+      ktime_begin(b, "spectrum"); afx_launch_spectrum(ctx->P, D, feat, s_main, &b->launches); ktime_end(b);
     }
+#ifdef AFX_HAVE_PITCH
+    if (feat & AFX_FEAT_PITCH) {            // needs the spectrum's full-band centroid (fail-safe f0)
+      if (ms) { CK(cudaEventRecord(ctx->ev_spec, s_main), "cudaEventRecord"); CK(cudaStreamWaitEvent(s_pitch, ctx->ev_spec, 0), "cudaStreamWaitEvent"); }
+      ktime_begin(b, "pitch"); afx_launch_pitch(ctx->P, D, s_pitch, &b->launches); ktime_end(b);
+    }
+#endif
 #ifdef AFX_HAVE_BANDS
-    if (feat & AFX_FEAT_BANDS) { ktime_begin(b, "bands"); afx_launch_bands(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
+    if (feat & AFX_FEAT_BANDS) { ktime_begin(b, "bands"); afx_launch_bands(ctx->P, D, s_main, &b->launches); ktime_end(b); }
 #endif
     // peaks last among the users of the magnitude rows: its whitening pass overwrites them in place
 #ifdef AFX_HAVE_PEAKS
-    if (feat & AFX_FEAT_PEAKS) { ktime_begin(b, "peaks"); afx_launch_peaks(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
+    if (feat & AFX_FEAT_PEAKS) { ktime_begin(b, "peaks"); afx_launch_peaks(ctx->P, D, s_main, &b->launches); ktime_end(b); }
 #endif
-#ifdef AFX_HAVE_PITCH
-    if (feat & AFX_FEAT_PITCH) { ktime_begin(b, "pitch"); afx_launch_pitch(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
-#endif
-#ifdef AFX_HAVE_AUTOCORR
-    if (feat & AFX_FEAT_AUTOCORR) { ktime_begin(b, "autocorr"); afx_launch_autocorr(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
-#endif
-#ifdef AFX_HAVE_RHYTHM
-    if (feat & AFX_FEAT_RHYTHM) { ktime_begin(b, "rhythm"); afx_launch_rhythm(ctx->P, D, ctx->stream, &b->launches); ktime_end(b); }
-#endif
+  }
+  if (ms) {   // join before the statistics pass reads every series
+    for (int i = 0; i < 3; ++i) { CK(cudaEventRecord(ctx->ev_join[i], ctx->side[i]), "cudaEventRecord"); CK(cudaStreamWaitEvent(s_main, ctx->ev_join[i], 0), "cudaStreamWaitEvent"); }
   }
 #ifdef AFX_HAVE_STATS
   if (feat & AFX_FEAT_STATS) { ktime_begin(b, "stats"); afx_launch_stats(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }

@@ -346,7 +346,7 @@ __device__ double r_onset_match_conf(int sr, const double* raw, int n, double of
 // 9-sample register window turns every pair of shared-memory loads into 9 DFMAs (same tiling as k_autocorr).
 // x must be readable (zero) up to index n + 17.
 #define RB_AL 9
-__device__ __forceinline__ void rb_acf_group(const double* __restrict__ x, int n, int g, double* __restrict__ acf)
+__device__ __noinline__ void rb_acf_group(const double* __restrict__ x, int n, int g, double* __restrict__ acf)
 {
   const int i0 = g * RB_AL;
   const int nj = n - i0;

@@ -43,6 +43,9 @@ WORKLOADS = {
                  desc="configs[3] shard: full low-level descriptor set on 12.5k mixed-length (0.5-30 s) 44.1 kHz mono "
                       "int16 files per GPU (100k files at 8 GPUs)"),
 }
+WORKLOADS["long"] = dict(files_per_gpu=2, seconds=3600.0, min_seconds=None, hop=1024, features="all", rate=96000, channels=2,
+                         desc="configs[4] on one GPU: full low-level set on 1-hour 96 kHz stereo int16 files (fused downmix + "
+                              "libresample-exact 96k->44.1k resample dominate; analysis is capped at 20 s by the reference)")
 N_UNIQUE = 64            # distinct synthetic files, tiled to the workload size
 
 
@@ -99,22 +102,28 @@ class ClockSampler:
 
 
 def build_corpus(wl, rank):
-    """-> list of int16 mono arrays (tiled)."""
+    """-> list of int16 arrays (tiled)."""
+    if wl.get("rate", 44100) != 44100 or wl.get("channels", 1) != 1:
+        # long multi-channel files: a 30-s clip repeated to the requested duration
+        clip = synth.one_shot(7 + rank, 30.0, rate=wl["rate"], channels=wl["channels"])
+        reps = max(1, int(round(wl["seconds"] / 30.0)))
+        one = np.ascontiguousarray(np.tile(clip, (reps, 1)))
+        return [one for _ in range(wl["files_per_gpu"])]
     return synth.tiled_corpus(wl["files_per_gpu"], N_UNIQUE, seconds=wl["seconds"], seed0=1000 * rank,
                               min_seconds=wl["min_seconds"])
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_run(files_pcm, hop, threads, reps=1):
+def cpu_reference_run(files_pcm, hop, threads, reps=1, rate=44100):
     """Times the reference (or the port) on host cores over the given files.  Returns dict."""
     from oracle import oracle
-    audio_s = sum(len(p) for p in files_pcm) / 44100.0 * reps
+    audio_s = sum(len(p) for p in files_pcm) / float(rate) * reps
     if oracle.have_reference():
         with tempfile.TemporaryDirectory() as d:
             paths = []
             for i, p in enumerate(files_pcm):
                 path = os.path.join(d, "f%05d.wav" % i)
-                oracle.write_wav(path, p, 44100)
+                oracle.write_wav(path, p, rate)
                 paths.append(path)
             env = dict(os.environ, HOME=d)
             t0 = time.perf_counter()
@@ -130,7 +139,7 @@ def cpu_reference_run(files_pcm, hop, threads, reps=1):
         t0 = time.perf_counter()
         for _ in range(reps):
             for p in files_pcm:
-                oracle.analyze(p, hop=hop)
+                oracle.analyze(p, hop=hop, src_rate=rate)
         secs = time.perf_counter() - t0
         kind, threads = "port", 1
     return dict(seconds=secs, audio_hours_per_s=audio_s / 3600.0 / secs, kind=kind, cores=threads, audio_s=audio_s)
@@ -149,13 +158,15 @@ def run_reference_arm(args, wl, rank, world):
         return
     cores = os.cpu_count() or 1
     n_sample = reference_sample_files(wl, cores)
+    if wl["seconds"] >= 600:
+        n_sample = min(n_sample, wl["files_per_gpu"])          # hour-long files: minutes of CPU time each
     pcms = build_corpus(dict(wl, files_per_gpu=n_sample), 0)
     for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_reference_run(pcms[: max(4, cores // 2)], wl["hop"], cores)
+        cpu_reference_run(pcms[: max(4, cores // 2)], wl["hop"], cores, rate=wl.get("rate", 44100))
     secs, audio = 0.0, 0.0
     kind = "port"
     for _ in range(args.steps):
-        r = cpu_reference_run(pcms, wl["hop"], cores)
+        r = cpu_reference_run(pcms, wl["hop"], cores, rate=wl.get("rate", 44100))
         secs += r["seconds"]; audio += r["audio_s"]; kind = r["kind"]; used = r["cores"]
     value = audio / 3600.0 / secs
     line = {
@@ -180,6 +191,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--seconds", type=float, default=0.0, help="override file duration (debug)")
     ap.add_argument("--files", type=int, default=0, help="override files per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -190,6 +202,8 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.files:
         wl["files_per_gpu"] = args.files
+    if args.seconds:
+        wl["seconds"] = args.seconds
 
     if args.impl == "reference":
         run_reference_arm(args, wl, rank, world)
@@ -230,15 +244,16 @@ def main():
 
     # ---- synthetic decoded PCM in ONE pinned arena (what per-GPU decode threads would fill) ----
     pcms = build_corpus(wl, rank)
+    rate, nch = wl.get("rate", 44100), wl.get("channels", 1)
     total = sum(p.size for p in pcms)
     arena = an.pinned(total * 2)
     files, off = [], 0
     view = arena.array.view(np.int16)
     for p in pcms:
-        view[off:off + p.size] = p
-        files.append(api.AfxFile(arena.ptr + 2 * off, p.size, 1, 44100, api.AFX_PCM_I16, 16, 44 + 2 * p.size))
+        view[off:off + p.size] = p.reshape(-1)
+        files.append(api.AfxFile(arena.ptr + 2 * off, p.shape[0], nch, rate, api.AFX_PCM_I16, 16, 44 + 2 * p.size))
         off += p.size
-    audio_hours = total / 44100.0 / 3600.0
+    audio_hours = total / float(nch) / float(rate) / 3600.0
     files_arr = (api.AfxFile * len(files))(*files)
 
     def make_batch():
@@ -257,12 +272,19 @@ def main():
     b.sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_wait = time.perf_counter()
+    while not sampler.rows and time.perf_counter() - t_wait < 3.0:     # nvidia-smi needs ~1 s to deliver its first row:
+        b.compute(); b.sync()                                          # keep the GPU under the same load meanwhile
     barrier()
     dev_ms = 0.0
     for _ in range(args.steps):
         b.compute(); b.sync()
         dev_ms += b.timings()[1]
     barrier()
+    for _ in range(3):                                                 # a short timed region may end between two samples
+        if len(sampler.rows) >= 2:
+            break
+        b.compute(); b.sync()
     clocks = sampler.stop()
     b.download(); b.sync()
     cnt = b.counters()
@@ -278,7 +300,7 @@ def main():
     # Host pipeline as in afec_b200/host/gpu_analyser.cpp: E2E_SLOTS contexts (stream + device buffers each), one
     # host thread per slot; a step's files are cut into chunks that the slot threads claim in turn, so the H2D /
     # D2H copies of one chunk overlap the kernels of another.  ctypes releases the GIL inside the C calls.
-    E2E_SLOTS, E2E_CHUNKS = 3, 12
+    E2E_SLOTS, E2E_CHUNKS = 3, min(12, len(files))
     slots = [an] + [api.SampleAnalyser(44100, 2048, wl["hop"], device=local_rank, features=feats) for _ in range(E2E_SLOTS - 1)]
     bounds = [len(files) * i // E2E_CHUNKS for i in range(E2E_CHUNKS + 1)]
     chunk_arrs = [(api.AfxFile * (bounds[i + 1] - bounds[i]))(*files[bounds[i]:bounds[i + 1]]) for i in range(E2E_CHUNKS)]
@@ -395,7 +417,7 @@ def main():
         try:
             cores = os.cpu_count() or 1
             sample = pcms[: reference_sample_files(wl, cores)]
-            r = cpu_reference_run(sample, wl["hop"], cores)
+            r = cpu_reference_run(sample, wl["hop"], cores, rate=wl.get("rate", 44100))
             cpu = {"value": r["audio_hours_per_s"], "unit": "audio-hours/s", "cores": r["cores"], "kind": r["kind"],
                    "sample": "%d files (%.1f s audio), hop %d, %d host threads, FULL low-level set into a sqlite pool"
                              % (len(sample), r["audio_s"], wl["hop"], r["cores"]), "seconds": r["seconds"]}

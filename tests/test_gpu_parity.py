@@ -202,3 +202,21 @@ def test_fft_core_known_answers(analysers, n):
     assert np.max(np.abs(X - ref)) <= 1e-11 * max(1.0, np.max(np.abs(ref)))
     back = np.conj(an.debug_fft(np.conj(X))) / n
     assert np.max(np.abs(back - x)) <= 1e-12 * max(1.0, np.max(np.abs(x)))
+
+
+def test_long_resampled_stereo_file_vs_oracle(analysers, feats, oracle_lib):
+    """BASELINE config 5 in miniature: a 96 kHz stereo file longer than the 20 s analysis cap -- downmix,
+    libresample-exact resampling of ~2.3 M frames (hundreds of resampler blocks), trim over the whole file,
+    capped analysis (F = 860, Fr = 6887)."""
+    clip = synth.one_shot(31, 8.0, rate=96000, channels=2)
+    pcm = np.ascontiguousarray(np.tile(clip, (4, 1)))                   # 32 s
+    an = analysers(1024)
+    b = an.batch([pcm], [96000]).run()
+    data, off, pk, rms = oracle_lib.condition(pcm, src_rate=96000)
+    got = b.conditioned(0)
+    assert got.shape == data.shape and np.array_equal(got, data)
+    r = b.result(0)
+    assert (r.F, r.Fr) == (860, 6887)
+    want = oracle_lib.analyze(pcm, src_rate=96000, file_size=44 + pcm.size * 2)
+    check(r, want, feats)
+    b.free()
