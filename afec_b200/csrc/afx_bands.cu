@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(BT) k_bands_b(AfxBatchDev B, AfxParams P)
   for (int m = 0; m < 14; ++m) {
     const double lm = __shfl_sync(0xffffffffu, lg, m, 16);
     const double cm = __shfl_sync(0xffffffffu, c, m, 16);
-    if (j < 14) a += lm * __ldg(P.t.dct + j * 14 + m);
+    // separate rn multiply and add in the reference's m order: an all-equal input (silent frame) then cancels to
+    // the same last-bit residue as vector.c:381-386 instead of a different one
+    if (j < 14) a = __dadd_rn(a, __dmul_rn(lm, __ldg(P.t.dct + j * 14 + m)));
     csum += cm;
   }
   if (live && j < 14) B.fv[(size_t)FV_CEPSTRUM * TF + (size_t)slot * 14 + j] = a;

@@ -1,9 +1,17 @@
-import sys, numpy as np
+"""Small full-set batch for ncu: two warm computes, then ONE compute inside the NVTX range "prof"
+(ncu --nvtx --nvtx-include "prof/" captures just that one)."""
+import os, sys, numpy as np
 sys.path.insert(0, '.')
+import torch
 from afec_b200 import api, synth
-pcms = synth.tiled_corpus(400, 16, seconds=3.0, seed0=0)
-an = api.SampleAnalyser(44100, 2048, 1024, features=api.FEAT_ALL)
+hop = int(os.environ.get("PROF_HOP", "1024"))
+feats = api.FEAT_SPECTRAL if os.environ.get("PROF_FEATS") == "spectral" else api.FEAT_ALL
+pcms = synth.tiled_corpus(int(os.environ.get("PROF_FILES", "400")), 16, seconds=3.0, seed0=0)
+an = api.SampleAnalyser(44100, 2048, hop, features=feats)
 b = an.batch(pcms, [44100]*len(pcms))
 b.upload(); b.compute(); b.compute(); b.sync()
+torch.cuda.nvtx.range_push("prof")
+b.compute(); b.sync()
+torch.cuda.nvtx.range_pop()
 print(b.timings())
 b.free(); an.close()

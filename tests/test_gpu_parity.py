@@ -218,5 +218,5 @@ def test_long_resampled_stereo_file_vs_oracle(analysers, feats, oracle_lib):
     r = b.result(0)
     assert (r.F, r.Fr) == (860, 6887)
     want = oracle_lib.analyze(pcm, src_rate=96000, file_size=44 + pcm.size * 2)
-    check(r, want, feats)
+    check(r, want, feats, mdata=data)
     b.free()
