@@ -25,6 +25,8 @@ EXPORTS = [
     "afx_batch_create", "afx_batch_upload", "afx_batch_compute", "afx_batch_download", "afx_batch_sync",
     "afx_analyze", "afx_batch_result", "afx_batch_free", "afx_batch_timings", "afx_batch_counters",
     "afx_batch_kernel_times", "afx_batch_conditioned", "afx_measure_fp64_peak", "afx_debug_fft",
+    "afx_part_plan", "afx_part_sums_init", "afx_part_sums_merge", "afx_part_open", "afx_part_peak", "afx_part_trim",
+    "afx_part_effective", "afx_part_window", "afx_part_read", "afx_part_close", "afx_analyze_conditioned",
 ]
 
 
@@ -43,6 +45,15 @@ class AfxFileResult(C.Structure):
                 ("reserved", C.c_int32), ("header", C.POINTER(C.c_double)),
                 ("fs", C.POINTER(C.c_double) * layout.N_FS), ("fv", C.POINTER(C.c_double) * layout.N_FV),
                 ("stats", C.POINTER(C.c_double))]
+
+
+class AfxPart(C.Structure):
+    _fields_ = [("src_begin", C.c_int64), ("src_end", C.c_int64), ("out_begin", C.c_int64), ("out_end", C.c_int64)]
+
+
+class AfxPartSums(C.Structure):
+    _fields_ = [("maxabs", C.c_float), ("reserved", C.c_int32), ("sumsq", C.c_double), ("first", C.c_int64),
+                ("last", C.c_int64), ("eff_first", C.c_int64 * 3), ("eff_last", C.c_int64 * 3)]
 
 
 class AfxError(RuntimeError):
@@ -83,6 +94,22 @@ def load_library():
     L.afx_batch_conditioned.restype = C.c_int64
     L.afx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.afx_debug_fft.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.afx_part_plan.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(AfxPart)]
+    L.afx_part_sums_init.argtypes = [C.POINTER(AfxPartSums)]
+    L.afx_part_sums_init.restype = None
+    L.afx_part_sums_merge.argtypes = [C.POINTER(AfxPartSums), C.POINTER(AfxPartSums)]
+    L.afx_part_sums_merge.restype = None
+    L.afx_part_open.argtypes = [C.c_void_p, C.POINTER(AfxFile), C.POINTER(AfxPart), C.c_void_p, C.POINTER(C.c_void_p)]
+    L.afx_part_peak.argtypes = [C.c_void_p, C.POINTER(AfxPartSums)]
+    L.afx_part_trim.argtypes = [C.c_void_p, C.POINTER(AfxPartSums), C.POINTER(AfxPartSums)]
+    L.afx_part_effective.argtypes = [C.c_void_p, C.POINTER(AfxPartSums), C.POINTER(AfxPartSums)]
+    L.afx_part_window.argtypes = [C.c_void_p, C.POINTER(AfxFile), C.POINTER(AfxPartSums), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.afx_part_read.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    L.afx_part_read.restype = C.c_int64
+    L.afx_part_close.argtypes = [C.c_void_p]
+    L.afx_part_close.restype = None
+    L.afx_analyze_conditioned.argtypes = [C.c_void_p, C.POINTER(AfxFile), C.POINTER(AfxPartSums), C.c_void_p, C.c_int64, C.c_int64,
+                                          C.POINTER(C.c_void_p)]
     _lib = L
     return L
 

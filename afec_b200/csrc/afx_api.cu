@@ -1,8 +1,7 @@
 // C ABI of libafec_b200.so (include/afec_b200.h): context, per-batch planning, staging and the
 // kernel schedule.  Host code here only builds data-independent tables and plans (window, mel
 // filters, twiddles, chunk / frame-slot tables); every sample-dependent operation runs on the GPU.
-#include "afx_common.cuh"
-#include "../../include/afec_b200.h"
+#include "afx_internal.h"
 
 #include <algorithm>
 #include <cmath>
@@ -13,102 +12,16 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #define CHUNK 8192
 
 static thread_local std::string g_create_error;
 
-// growable device / pinned buffers ------------------------------------------------------------
-struct DevBuf {
-  void* p = nullptr; size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-struct PinBuf {
-  void* p = nullptr; size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr; cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-// data-independent replay of libresample's block / time bookkeeping for one (rate, length) pair
-struct RsShape {
-  std::vector<RsBlock> blocks;   // chk_off relative to chk
-  std::vector<double> chk;       // every 64th output time stamp of each block
-  int produced = 0;              // output samples libresample delivers (<= the requested count)
-};
-
-struct afx_ctx {
-  afx_config cfg;
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  // side streams: the pitch, autocorrelation and rhythm chains only depend on the conditioned signal (pitch also on
-  // the spectrum's centroid), so they run beside the spectrum -> bands -> peaks chain and fill each other's idle pipes
-  cudaStream_t side[3] = { nullptr, nullptr, nullptr };
-  cudaEvent_t ev_fork = nullptr, ev_spec = nullptr, ev_join[3] = { nullptr, nullptr, nullptr };
-  bool multi_stream = true;
-  AfxParams P;
-  DevBuf tables;                      // all constant tables in one allocation
-  DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf, d_rpost, d_bandraw, d_slotmap,
-         d_stats, d_header, d_plan, d_scratch;
-  std::map<std::pair<int, int>, std::shared_ptr<RsShape>> rs_cache;
-  long long group_frames = 393216, group_rframes = 3145728;   // per-launch scratch bound: 3 GB mag, 6 GB rpolar
-  PinBuf h_results_cache, h_plan_cache;   // recycled between batches
-  std::vector<double> zeros;          // backing store of the all-zero series
-  std::string error;
-  bool debug_times = false;
-  std::mutex mu;
-  int max_frame_cap = 0;
-};
-
-struct KernelTime { const char* name; cudaEvent_t a, b; };
-
-struct afx_batch {
-  afx_ctx* ctx = nullptr;
-  int n_files = 0;
-  std::vector<afx_file> in;
-  std::vector<AfxFile> files;
-  std::vector<AfxState> state_host;
-  // plan
-  std::vector<int> src_chunk_file, src_chunk_start, dst_chunk_file, dst_chunk_start, rs_chunk_file, rs_chunk_start;
-  std::vector<RsBlock> rs_blocks; std::vector<int> rs_blk_file; std::vector<double> rs_chk;
-  struct Tail { long long off; long long count; }; std::vector<Tail> rs_tails;   // mono samples libresample never writes
-  struct Group { int file0, nfiles, slot0, nslots, rslot0, nrslots; };
-  std::vector<Group> groups;
-  int max_gslots = 0, max_grslots = 0, max_fr = 0;
-  struct CopyRun { const unsigned char* host; size_t dev_off; size_t bytes; };
-  std::vector<CopyRun> runs;
-  size_t pcm_bytes = 0; long long mono_samples = 0, mono_src_samples = 0;
-  int TF = 0, TFr = 0;
-  PinBuf h_plan;                      // pinned staging of file table + chunk tables
-  PinBuf h_results;                   // pinned results
-  // host result layout (offsets in doubles inside h_results)
-  size_t o_header = 0, o_state = 0, o_fs = 0, o_fsr = 0, o_fv = 0, o_stats = 0, total_doubles = 0;
-  AfxBatchDev dev;
-  AfxCondPlan cond;
-  cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-  bool uploaded = false, computed = false, downloaded = false;
-  long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
-  std::vector<KernelTime> ktimes;
-};
-
-static int fail(afx_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
+static int fail(afx_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess);
+int afx_fail(afx_ctx* c, int code, const char* what, cudaError_t e) { return fail(c, code, what, e); }
+static int fail(afx_ctx* c, int code, const char* what, cudaError_t e)
 {
   char buf[512];
   if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
@@ -120,6 +33,7 @@ static int fail(afx_ctx* c, int code, const char* what, cudaError_t e = cudaSucc
 
 // reference rounding helpers (CoreTypes/Export/InlineMath.inl:758-761, 823-826)
 static int d2i_round(double v) { return (int)(v + (std::signbit(v) ? -0.5 : 0.5)); }
+int afx_reference_round(double v) { return d2i_round(v); }
 static int f2i_round(float v) { return (int)(v + (std::signbit(v) ? -0.5f : 0.5f)); }
 static int ms_to_samples(int sr, float ms) { return f2i_round((float)sr / 1000.0f * ms); }
 static double db_to_lin(double v) { if (v == 0.0) return 1.0; if (v > -200.0) return std::exp(v * (std::log(10.0) / 20.0)); return 0.0; }
@@ -207,7 +121,7 @@ static std::shared_ptr<RsShape> rs_plan(int in_len, int src_rate, int sr, int ou
     const unsigned nreuse = xread - shift;
     int ncopy = out_len - outc; if (ncopy > nout) ncopy = nout;
     rb.nout = ncopy;
-    if (ncopy > 0) sh->blocks.push_back(rb);
+    if (ncopy > 0) { sh->blocks.push_back(rb); sh->span.push_back(nx + 2 * (int)xoff + 2); }
     outc += ncopy;
     in0 += shift; xread = nreuse;
     if (ncopy < nout) break;
@@ -376,9 +290,29 @@ extern "C" int afx_host_free(afx_ctx* ctx, void* p)
 }
 
 // ---- batch planning ------------------------------------------------------------------------------
+// process-wide cache of the data-independent libresample replays, keyed by (analysis rate, source rate, length)
+std::shared_ptr<RsShape> afx_rs_shape(int sr, int in_len, int src_rate, int out_len)
+{
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int>, std::shared_ptr<RsShape>> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto key = std::make_tuple(sr, src_rate, in_len);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    if (cache.size() > 256) cache.clear();
+    it = cache.emplace(key, rs_plan(in_len, src_rate, sr, out_len)).first;
+  }
+  return it->second;
+}
+
 extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_files, afx_batch** out)
 {
-  if (!ctx || !out || (n_files > 0 && !files) || n_files < 0) return fail(ctx, AFX_ERR_ARG, "afx_batch_create: bad arguments");
+  return afx_batch_create_impl(ctx, files, n_files, nullptr, out);
+}
+
+int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, const AfxCondInput* cond, afx_batch** out)
+{
+  if (!ctx || !out || (n_files > 0 && !files) || n_files < 0 || (cond && n_files != 1)) return fail(ctx, AFX_ERR_ARG, "afx_batch_create: bad arguments");
   *out = nullptr;
   const AfxParams& P = ctx->P;
   afx_batch* b = new afx_batch();
@@ -402,7 +336,7 @@ extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_f
     d.channels = f.channels; d.src_rate = f.src_rate; d.format = f.format; d.bit_depth = f.bit_depth; d.file_size = f.file_size;
     d.status = AFX_FILE_OK;
     if (f.channels < 1 || f.channels > 8) d.status = AFX_FILE_BAD_CHANNELS;          // SA.cpp:472-477
-    else if (f.nframes <= 0 || !f.pcm) d.status = AFX_FILE_EMPTY;                     // SA.cpp:479-482
+    else if (f.nframes <= 0 || (!f.pcm && !cond)) d.status = AFX_FILE_EMPTY;          // SA.cpp:479-482
     else if (f.nframes * f.channels > 0x7fffffffLL || f.src_rate <= 0 || (f.format != AFX_PCM_I16 && f.format != AFX_PCM_F32)) {
       delete b; return fail(ctx, AFX_ERR_ARG, "afx_batch_create: unsupported file description");
     }
@@ -412,6 +346,7 @@ extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_f
     const double speed = (double)f.src_rate / (double)P.sr;                            // SA.cpp:563-573
     d.n = d.nframes_src;
     if (speed != 1.0) { int nn = d2i_round(d.nframes_src / speed); d.n = nn < 1 ? 1 : nn; }
+    d.src_end = d.nframes_src; d.dst_end = d.n; d.inject = -1;
     // upper bounds for the conditioned length: len <= max(n + N/2, N)
     long long lmax = std::max<long long>((long long)d.n + P.N / 2, P.N);
     if (lmax > P.analysis_cap) lmax = P.analysis_cap;
@@ -425,6 +360,18 @@ extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_f
     ++g.nfiles; g.nslots += d.frame_cap; g.nrslots += d.rframe_cap;
     b->max_fr = std::max(b->max_fr, d.rframe_cap);
     tf += d.frame_cap; tfr += d.rframe_cap;
+    if (cond) {
+      // conditioned elsewhere: the mono window goes straight into the mono buffer, addressed by its global sample index
+      if ((!cond->mono && cond->mono_count > 0) || cond->mono_count < 0 || cond->mono_begin < 0 || cond->mono_begin + cond->mono_count > d.n) {
+        delete b; return fail(ctx, AFX_ERR_ARG, "afx_analyze_conditioned: bad mono window");
+      }
+      if (cond->mono_count > 0) b->runs.push_back({ (const unsigned char*)cond->mono, (size_t)mono_off * 4, (size_t)cond->mono_count * 4, true });
+      d.mono_off = mono_off - cond->mono_begin;
+      mono_off += (cond->mono_count + 3) & ~3LL;
+      d.inject = (int)b->inject.size();
+      b->inject.push_back(cond->inj);
+      continue;
+    }
     // PCM packing: keep host-contiguous files contiguous on the device so they move in one copy
     const size_t bps = (f.format == AFX_PCM_I16) ? 2 : 4;
     const size_t bytes = (size_t)f.nframes * f.channels * bps;
@@ -433,7 +380,7 @@ extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_f
       b->runs.back().bytes += bytes;
     } else {
       pcm_off = (pcm_off + 15) & ~(size_t)15;
-      b->runs.push_back({ hp, pcm_off, bytes });
+      b->runs.push_back({ hp, pcm_off, bytes, false });
     }
     d.pcm_off = (long long)pcm_off;
     pcm_off += bytes; run_end = hp + bytes;
@@ -441,17 +388,7 @@ extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_f
     d.mono_off = mono_off - (((long long)d.n + 3) & ~3LL);
     if (speed != 1.0) {
       d.src_off = src_off; src_off += ((long long)d.nframes_src + 3) & ~3LL;
-      std::shared_ptr<RsShape> sh;
-      {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        auto key = std::make_pair(f.src_rate, d.nframes_src);
-        auto it = ctx->rs_cache.find(key);
-        if (it == ctx->rs_cache.end()) {
-          if (ctx->rs_cache.size() > 256) ctx->rs_cache.clear();
-          it = ctx->rs_cache.emplace(key, rs_plan(d.nframes_src, f.src_rate, P.sr, d.n)).first;
-        }
-        sh = it->second;
-      }
+      std::shared_ptr<RsShape> sh = afx_rs_shape(P.sr, d.nframes_src, f.src_rate, d.n);
       auto pit = shape_pool.find(sh.get());
       if (pit == shape_pool.end()) {
         pit = shape_pool.emplace(sh.get(), (long long)b->rs_chk.size()).first;
@@ -540,6 +477,7 @@ extern "C" int afx_batch_upload(afx_batch* b)
     p_rcf = place(nrc * 4), p_rcs = place(nrc * 4);
   const size_t nrb = b->rs_blocks.size(), nck = b->rs_chk.size();
   const size_t p_rb = place(nrb * sizeof(RsBlock)), p_rbf = place(nrb * 4), p_chk = place(nck * 8);
+  const size_t p_inj = place(b->inject.size() * sizeof(AfxInject));
   take_cached(b->h_plan, ctx->h_plan_cache, po);
   CK(b->h_plan.reserve(po + 256), "cudaHostAlloc(plan)");
   CK(ctx->d_plan.reserve(po + 256), "cudaMalloc(plan)");
@@ -550,12 +488,14 @@ extern "C" int afx_batch_upload(afx_batch* b)
   if (nrc) { memcpy(hp + p_rcf, b->rs_chunk_file.data(), nrc * 4); memcpy(hp + p_rcs, b->rs_chunk_start.data(), nrc * 4); }
   if (nrb) { memcpy(hp + p_rb, b->rs_blocks.data(), nrb * sizeof(RsBlock)); memcpy(hp + p_rbf, b->rs_blk_file.data(), nrb * 4); }
   if (nck) memcpy(hp + p_chk, b->rs_chk.data(), nck * 8);
+  if (!b->inject.empty()) memcpy(hp + p_inj, b->inject.data(), b->inject.size() * sizeof(AfxInject));
 
   CK(cudaEventRecord(b->ev[0], ctx->stream), "cudaEventRecord");
   CK(cudaMemcpyAsync(ctx->d_plan.p, hp, po, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(plan)");
   b->h2d_bytes = (long long)po;
   for (const auto& r : b->runs) {
-    CK(cudaMemcpyAsync((unsigned char*)ctx->d_pcm.p + r.dev_off, r.host, r.bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(pcm)");
+    unsigned char* dst = (unsigned char*)(r.to_mono ? ctx->d_mono.p : ctx->d_pcm.p) + r.dev_off;
+    CK(cudaMemcpyAsync(dst, r.host, r.bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(pcm)");
     b->h2d_bytes += (long long)r.bytes;
   }
   CK(cudaEventRecord(b->ev[1], ctx->stream), "cudaEventRecord");
@@ -566,6 +506,7 @@ extern "C" int afx_batch_upload(afx_batch* b)
   D.n_files = n; D.TF = b->TF; D.TFr = b->TFr;
   D.pcm = (const unsigned char*)ctx->d_pcm.p; D.mono = (float*)ctx->d_mono.p; D.mono_src = (float*)ctx->d_mono_src.p;
   D.files = (const AfxFile*)(dp + p_files); D.state = (AfxState*)ctx->d_state.p;
+  D.inject = b->inject.empty() ? nullptr : (const AfxInject*)(dp + p_inj);
   D.mag = (double*)ctx->d_mag.p; D.cent_full = (double*)ctx->d_cent.p; D.fs = (double*)ctx->d_fs.p; D.fsr = (double*)ctx->d_fsr.p;
   D.fv = (double*)ctx->d_fv.p; D.rpolar = (float*)ctx->d_rpolar.p; D.rodf = (float*)ctx->d_rodf.p; D.rpost = (float*)ctx->d_rpost.p; D.bandraw = (double*)ctx->d_bandraw.p;
   D.slot_file = (const int*)ctx->d_slotmap.p; D.rslot_file = (const int*)ctx->d_slotmap.p + TF + 1;

@@ -56,7 +56,16 @@ struct AfxFile {            // host-built, one per file
   int frame_off, frame_cap; // main frame slots [frame_off, frame_off + frame_cap)
   int rframe_off, rframe_cap;
   int status;               // AFX_FILE_*
+  int inject;               // >= 0: conditioning reductions come from AfxBatchDev::inject[inject] (long files conditioned in parts)
+  int src_end, dst_end;     // the conditioning passes stop here (== nframes_src / n, or the end of one part's range)
+};
+
+struct AfxInject {          // conditioning reductions of a whole file made elsewhere (afx_part.cu)
+  unsigned int maxabs_bits;
+  int first, last;
+  int eff_first[3], eff_last[3];
   int pad;
+  double sumsq;
 };
 
 struct AfxState {           // device-computed, one per file (SampleAnalyser.cpp:610-718)
@@ -251,6 +260,7 @@ struct AfxBatchDev {
   float* mono;
   float* mono_src;
   const AfxFile* files;
+  const AfxInject* inject;  // null unless a file of the batch was conditioned in parts
   AfxState* state;
   const int* slot_file;   // [TF]  main frame slot -> file index (built on the device by k_slotmap)
   const int* rslot_file;  // [TFr] rhythm frame slot -> file index
@@ -277,6 +287,9 @@ struct AfxCondPlan {       // device arrays built by the host for one batch
   const RsBlock* rs_blocks; const int* rs_blk_file; const double* rs_times; int n_rs_blocks;   // rs_times: every 64th output time stamp
 };
 void afx_launch_condition_plan(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s, long long* launches);
+void afx_launch_part_reduce(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s);
+void afx_launch_part_trim(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s);
+void afx_launch_part_eff(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s);
 void afx_launch_materialise(const float* mono, const AfxState* st, double* out, int len, cudaStream_t s);
 void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, long long* launches);
 void afx_launch_peaks(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);

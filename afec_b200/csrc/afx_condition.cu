@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(CT) k_downmix(AfxBatchDev B, const int* __rest
   const AfxFile f = B.files[fi];
   if (f.status != 0) return;
   const int start = chunk_start[blockIdx.x];
-  const int end = min(start + CHUNK, f.nframes_src);
+  const int end = min(start + CHUNK, f.src_end);
   const bool resampled = (f.src_rate != analysis_rate);
   float* dst = resampled ? (B.mono_src + f.src_off) : (B.mono + f.mono_off);
   float amax = 0.0f;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(CT) k_reduce(AfxBatchDev B, const int* __restr
   const AfxFile f = B.files[fi];
   if (f.status != 0) return;
   const int start = chunk_start[blockIdx.x];
-  const int end = min(start + CHUNK, f.n);
+  const int end = min(start + CHUNK, f.dst_end);
   const float* src = B.mono + f.mono_off;
   float amax = 0.0f;
   double ssq = 0.0;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(CT) k_trim(AfxBatchDev B, const int* __restric
   if (f.status != 0) return;
   const int start = chunk_start[blockIdx.x];
   if (start >= f.n) return;
-  const int end = min(start + CHUNK, f.n);
+  const int end = min(start + CHUNK, f.dst_end);
   const float* src = B.mono + f.mono_off;
   const double amp = B.state[fi].amp;
   int first = 0x7fffffff, last = -1;
@@ -238,6 +238,10 @@ __global__ void k_layout(AfxBatchDev B, AfxParams P)
   if (Fr > f.rframe_cap) Fr = f.rframe_cap;
   st->F = F; st->Fr = Fr;
   for (int k = 0; k < 3; ++k) { st->eff_first[k] = 0x7fffffff; st->eff_last[k] = -1; }
+  if (B.inject && f.inject >= 0) {
+    const AfxInject in = B.inject[f.inject];
+    for (int k = 0; k < 3; ++k) { st->eff_first[k] = in.eff_first[k]; st->eff_last[k] = in.eff_last[k]; }
+  }
 }
 
 __global__ void __launch_bounds__(CT) k_eff(AfxBatchDev B, const int* __restrict__ chunk_file,
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(CT) k_eff(AfxBatchDev B, const int* __restrict
   const AfxState st = B.state[fi];
   // chunk over the mono index space; only the audible region [lead, lead + audible) maps into mData
   int start = chunk_start[blockIdx.x];
-  int end = min(start + CHUNK, f.n);
+  int end = min(start + CHUNK, f.dst_end);
   start = max(start, st.lead); end = min(end, st.lead + st.audible);
   if (start >= end) return;      // uniform per block
   const float* src = B.mono + f.mono_off;
@@ -320,6 +324,11 @@ __global__ void k_state_init(AfxBatchDev B)
   if (fi >= B.n_files) return;
   AfxState* st = B.state + fi;
   st->maxabs_bits = 0u; st->sumsq = 0.0; st->first = 0x7fffffff; st->last = -1;
+  const int inj = B.files[fi].inject;
+  if (B.inject && inj >= 0) {
+    const AfxInject in = B.inject[inj];
+    st->maxabs_bits = in.maxabs_bits; st->sumsq = in.sumsq; st->first = in.first; st->last = in.last;
+  }
 }
 
 // debug / parity: materialise mData of one file
@@ -331,6 +340,25 @@ __global__ void k_materialise(const float* mono, const AfxState* st, double* out
 void afx_launch_materialise(const float* mono, const AfxState* st, double* out, int len, cudaStream_t s)
 {
   k_materialise<<<(len + 255) / 256, 256, 0, s>>>(mono, st, out, len);
+}
+
+// long files conditioned in parts (afx_part.cu): the same passes, phase by phase, over one part's ranges
+void afx_launch_part_reduce(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s)
+{
+  k_state_init<<<1, 128, 0, s>>>(B);
+  if (C.n_src_chunks > 0) k_downmix<<<C.n_src_chunks, CT, 0, s>>>(B, C.src_chunk_file, C.src_chunk_start, P.sr);
+  if (C.n_rs_blocks > 0) k_resample<<<C.n_rs_blocks, 128, 0, s>>>(B, P.t, C.rs_blocks, C.rs_blk_file, C.rs_times, C.n_rs_blocks, P.sr);
+  if (C.n_rs_chunks > 0) k_reduce<<<C.n_rs_chunks, CT, 0, s>>>(B, C.rs_chunk_file, C.rs_chunk_start);
+}
+void afx_launch_part_trim(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s)
+{
+  k_amp<<<1, 128, 0, s>>>(B);
+  if (C.n_dst_chunks > 0) k_trim<<<C.n_dst_chunks, CT, 0, s>>>(B, C.dst_chunk_file, C.dst_chunk_start, P.silence_floor_amp);
+}
+void afx_launch_part_eff(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s)
+{
+  k_layout<<<1, 128, 0, s>>>(B, P);
+  if (C.n_dst_chunks > 0) k_eff<<<C.n_dst_chunks, CT, 0, s>>>(B, C.dst_chunk_file, C.dst_chunk_start, P);
 }
 
 void afx_launch_condition_plan(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s, long long* launches)

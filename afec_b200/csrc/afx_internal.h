@@ -1,0 +1,113 @@
+// Host-side internals shared by the translation units that implement the C ABI (afx_api.cu, afx_part.cu):
+// growable buffers, the context and the batch.  Not part of the public interface (include/afec_b200.h).
+#pragma once
+#include "afx_common.cuh"
+#include "../../include/afec_b200.h"
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// growable device / pinned buffers ------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// data-independent replay of libresample's block / time bookkeeping for one (rate, length) pair
+struct RsShape {
+  std::vector<RsBlock> blocks;   // chk_off relative to chk
+  std::vector<double> chk;       // every 64th output time stamp of each block
+  std::vector<int> span;         // per block: source samples [in0, in0 + span) cover everything its filter sums read
+  int produced = 0;              // output samples libresample delivers (<= the requested count)
+};
+
+struct afx_ctx {
+  afx_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // side streams: the pitch, autocorrelation and rhythm chains only depend on the conditioned signal (pitch also on
+  // the spectrum's centroid), so they run beside the spectrum -> bands -> peaks chain and fill each other's idle pipes
+  cudaStream_t side[3] = { nullptr, nullptr, nullptr };
+  cudaEvent_t ev_fork = nullptr, ev_spec = nullptr, ev_join[3] = { nullptr, nullptr, nullptr };
+  bool multi_stream = true;
+  AfxParams P;
+  DevBuf tables;                      // all constant tables in one allocation
+  DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf, d_rpost, d_bandraw, d_slotmap,
+         d_stats, d_header, d_plan, d_scratch;
+  long long group_frames = 393216, group_rframes = 3145728;   // per-launch scratch bound: 3 GB mag, 6 GB rpolar
+  PinBuf h_results_cache, h_plan_cache;   // recycled between batches
+  std::vector<double> zeros;          // backing store of the all-zero series
+  std::string error;
+  bool debug_times = false;
+  std::mutex mu;
+  int max_frame_cap = 0;
+};
+
+struct KernelTime { const char* name; cudaEvent_t a, b; };
+
+struct afx_batch {
+  afx_ctx* ctx = nullptr;
+  int n_files = 0;
+  std::vector<afx_file> in;
+  std::vector<AfxFile> files;
+  std::vector<AfxState> state_host;
+  // plan
+  std::vector<int> src_chunk_file, src_chunk_start, dst_chunk_file, dst_chunk_start, rs_chunk_file, rs_chunk_start;
+  std::vector<RsBlock> rs_blocks; std::vector<int> rs_blk_file; std::vector<double> rs_chk;
+  struct Tail { long long off; long long count; }; std::vector<Tail> rs_tails;   // mono samples libresample never writes
+  struct Group { int file0, nfiles, slot0, nslots, rslot0, nrslots; };
+  std::vector<Group> groups;
+  int max_gslots = 0, max_grslots = 0, max_fr = 0;
+  struct CopyRun { const unsigned char* host; size_t dev_off; size_t bytes; bool to_mono; };
+  std::vector<AfxInject> inject;      // conditioning reductions made elsewhere (files conditioned in parts)
+  std::vector<CopyRun> runs;
+  size_t pcm_bytes = 0; long long mono_samples = 0, mono_src_samples = 0;
+  int TF = 0, TFr = 0;
+  PinBuf h_plan;                      // pinned staging of file table + chunk tables
+  PinBuf h_results;                   // pinned results
+  // host result layout (offsets in doubles inside h_results)
+  size_t o_header = 0, o_state = 0, o_fs = 0, o_fsr = 0, o_fv = 0, o_stats = 0, total_doubles = 0;
+  AfxBatchDev dev;
+  AfxCondPlan cond;
+  cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  bool uploaded = false, computed = false, downloaded = false;
+  long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+  std::vector<KernelTime> ktimes;
+};
+
+
+// shared helpers (afx_api.cu)
+int afx_fail(afx_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess);
+std::shared_ptr<RsShape> afx_rs_shape(int sr, int in_len, int src_rate, int out_len);   // cached libresample replay (process-wide)
+int afx_reference_round(double v);                                                            // TMath::d2iRound
+struct AfxCondInput {  // a file whose conditioning reductions were made elsewhere (afx_part.cu): the batch holds one such file
+  const float* mono;                  // analysis-rate mono samples [mono_begin, mono_begin + mono_count) of the file
+  long long mono_begin, mono_count;
+  AfxInject inj;
+};
+int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, const AfxCondInput* cond, afx_batch** out);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AFX_ABI_VERSION 1
+#define AFX_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------------ */
 #define AFX_OK 0
@@ -125,6 +125,54 @@ int afx_batch_sync(afx_batch* b);       /* wait for everything issued so far */
 int afx_analyze(afx_ctx* ctx, const afx_file* files, int32_t n_files, afx_batch** out); /* all of the above */
 int afx_batch_result(const afx_batch* b, int32_t file_index, afx_file_result* out);
 void afx_batch_free(afx_batch* b);
+
+/* ---- long files conditioned in parts ------------------------------------------------------------- */
+/* One long file (BASELINE config 5: 1-hour 96 kHz stereo) is cut into sample-range parts; each part is
+ * downmixed / resampled / reduced by its own context (its own GPU), and the per-file reductions that
+ * TSampleAnalyser::LoadSample makes over the whole file are combined BY THE CALLER between three phases
+ * (a handful of scalars: host reduce, or an all-reduce when the parts live in different processes):
+ *   afx_part_peak       max |x|, sum of squares            SampleAnalyser.cpp:612-631   combine: max, sum
+ *   afx_part_trim       first / last sample above -48 dB   SampleAnalyser.cpp:636-669   combine: min, max
+ *   afx_part_effective  -48 / -24 / -12 dB effective spans  SampleAnalyser.cpp:1715-1756 combine: min, max
+ * afx_part_sums_merge() is that combine: merging the outputs of ALL parts of a phase gives the global sums that
+ * the next phase takes as input (fields a phase does not compute are passed through so that they merge back to
+ * themselves).  The analysis itself reads at most the 20 s behind the trim point
+ * (SampleAnalyser.cpp:37, 760-764): afx_part_window() names those samples, afx_part_read() hands out the ones a
+ * part owns, and afx_analyze_conditioned() runs the regular kernel schedule on them.  Results are those of
+ * afx_analyze() on the whole file (bit-identical, except that the sum of squares adds in a different order). */
+typedef struct afx_part {
+  int64_t src_begin, src_end;   /* source frames the part needs, filter halo included: pcm_slice = frames [begin, end) */
+  int64_t out_begin, out_end;   /* analysis-rate samples the part produces */
+} afx_part;
+
+typedef struct afx_part_sums {
+  float maxabs;                 /* max |x|, 16-bit range */
+  int32_t reserved;
+  double sumsq;                 /* sum (x / 32768)^2 */
+  int64_t first, last;          /* analysis-rate sample indices; INT64_MAX / -1 when nothing is above the floor */
+  int64_t eff_first[3], eff_last[3];   /* conditioned-signal (mData) indices at -48 / -24 / -12 dB */
+} afx_part_sums;
+
+typedef struct afx_partjob afx_partjob;
+
+/* even split of a file into n_parts (cut at libresample block boundaries when src_rate != sample_rate);
+ * host-only arithmetic: needs no context and no device */
+int afx_part_plan(int32_t sample_rate, int64_t nframes, int32_t src_rate, int32_t n_parts, afx_part* out);
+void afx_part_sums_init(afx_part_sums* s);
+void afx_part_sums_merge(afx_part_sums* acc, const afx_part_sums* other);
+/* `whole` describes the whole file (nframes = all frames; its pcm member is ignored), pcm_slice holds the
+ * interleaved frames [part->src_begin, part->src_end) */
+int afx_part_open(afx_ctx* ctx, const afx_file* whole, const afx_part* part, const void* pcm_slice, afx_partjob** out);
+int afx_part_peak(afx_partjob* j, afx_part_sums* out);
+int afx_part_trim(afx_partjob* j, const afx_part_sums* global, afx_part_sums* out);
+int afx_part_effective(afx_partjob* j, const afx_part_sums* global, afx_part_sums* out);
+int afx_part_window(afx_ctx* ctx, const afx_file* whole, const afx_part_sums* global, int64_t* begin, int64_t* count);
+/* copies the samples of [begin, begin + count) this part owns to dst + (index - begin); returns how many */
+int64_t afx_part_read(afx_partjob* j, int64_t begin, int64_t count, float* dst);
+void afx_part_close(afx_partjob* j);
+/* mono = analysis-rate samples [mono_begin, mono_begin + mono_count) of the file (at least afx_part_window's) */
+int afx_analyze_conditioned(afx_ctx* ctx, const afx_file* whole, const afx_part_sums* global, const float* mono,
+                            int64_t mono_begin, int64_t mono_count, afx_batch** out);
 
 /* ---- measurement helpers ---------------------------------------------------------------------- */
 /* device time (ms, CUDA events on the context's stream) of the last upload / compute / download */
