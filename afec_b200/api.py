@@ -26,7 +26,7 @@ EXPORTS = [
     "afx_analyze", "afx_batch_result", "afx_batch_free", "afx_batch_timings", "afx_batch_counters",
     "afx_batch_kernel_times", "afx_batch_conditioned", "afx_measure_fp64_peak", "afx_debug_fft",
     "afx_part_plan", "afx_part_sums_init", "afx_part_sums_merge", "afx_part_open", "afx_part_peak", "afx_part_trim",
-    "afx_part_effective", "afx_part_window", "afx_part_read", "afx_part_close", "afx_analyze_conditioned",
+    "afx_part_effective", "afx_part_window", "afx_part_read", "afx_part_close", "afx_analyze_conditioned", "afx_debug_rs_plan_check",
 ]
 
 
@@ -110,6 +110,7 @@ def load_library():
     L.afx_part_close.restype = None
     L.afx_analyze_conditioned.argtypes = [C.c_void_p, C.POINTER(AfxFile), C.POINTER(AfxPartSums), C.c_void_p, C.c_int64, C.c_int64,
                                           C.POINTER(C.c_void_p)]
+    L.afx_debug_rs_plan_check.argtypes = [C.c_int32, C.c_int64, C.c_int32]
     _lib = L
     return L
 

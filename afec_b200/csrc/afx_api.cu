@@ -90,7 +90,70 @@ static void build_rs_wing(std::vector<float>& imp)
 // resample.c:80-164 (open, high quality) + :170-337 (process, lastFlag = 1) + resamplesubs.c:30-123: the
 // block structure and the time accumulator do not depend on the samples, so they are replayed here once per
 // (source rate, length) and the filter sums run on the GPU (k_resample).
-static std::shared_ptr<RsShape> rs_plan(int in_len, int src_rate, int sr, int out_len)
+//
+// The accumulator `t += dt` (resamplesubs.c:97-119) is replayed without walking every output sample: while t stays
+// inside one binade [2^e, 2^(e+1)) every double is a multiple of u = ulp(t), so fl(t + dt) = t + c with the
+// CONSTANT c = dt rounded to the grid u (round to nearest; an exact tie falls back to stepping) -- t advances
+// linearly and the k-th stamp is t + k c exactly.  Only the addition that crosses into the next binade (about 7
+// per 4096-sample block) is made in hardware.  Integers in units of 2^-80 keep the bookkeeping exact.  The result
+// is bit-identical to the step-by-step replay (rs_advance_stepwise; tests/test_longfile_host.py), at O(blocks)
+// instead of O(samples): 86 k blocks instead of 159 M additions for an hour of 96 kHz audio.
+typedef __int128 i128;
+#define RS_UNIT 80
+static inline i128 rs_to_fixed(double v) { return (i128)std::ldexp(v, RS_UNIT); }
+static inline double rs_from_fixed(i128 v) { return std::ldexp((double)v, -RS_UNIT); }
+
+// one block: stamps of outputs 0.. while t < end_time; pushes every 64th stamp; returns the count, t ends as the
+// accumulator after the last addition
+static int rs_advance_stepwise(double& t, double dt, double end_time, std::vector<double>& chk)
+{
+  int nout = 0;
+  while (t < end_time) { if ((nout & 63) == 0) chk.push_back(t); ++nout; t += dt; }
+  return nout;
+}
+
+static int rs_advance(double& t, double dt, double end_time, std::vector<double>& chk)
+{
+  if (!(dt >= 0x1p-20 && dt < 0x1p12 && t >= 1.0 && end_time < 0x1p40)) return rs_advance_stepwise(t, dt, end_time, chk);
+  const i128 DT = rs_to_fixed(dt), E = rs_to_fixed(end_time);
+  long long nout = 0;
+  while (t < end_time) {
+    int e; std::frexp(t, &e);                          // t in [2^(e-1), 2^e)
+    const i128 u = (i128)1 << (RS_UNIT + e - 53);      // ulp(t)
+    const i128 B = (i128)1 << (RS_UNIT + e);           // upper end of the binade
+    const i128 T = rs_to_fixed(t);
+    const i128 lo = DT & (u - 1), c = DT - lo + ((2 * lo > u) ? u : 0);   // u is a power of two
+    long long k = 0;
+    if (2 * lo != u && c > 0) {
+      // outputs j = 0..k-1 at T + j c: each must satisfy the loop test (T + j c < E) and its addition must stay
+      // inside the binade (T + j c + DT < B)
+      const i128 r1 = E - T, r2 = B - DT - T;
+      const i128 r = r1 < r2 ? r1 : r2;
+      if (r > 0) {                                      // k = ceil(r / c): a double estimate, corrected exactly
+        k = (long long)((double)r / (double)c);
+        while ((i128)k * c < r) ++k;
+        while (k > 0 && (i128)(k - 1) * c >= r) --k;
+      }
+    }
+    if (k > 0) {
+      const long long m0 = (nout + 63) & ~63LL;
+      if (m0 < nout + k) {
+        // stamps 64 outputs apart differ by 64 c: a multiple of u that keeps the sum inside the binade -> exact in double
+        double v = rs_from_fixed(T + (i128)(m0 - nout) * c);
+        const double step = rs_from_fixed(64 * c);
+        for (long long m = m0; m < nout + k; m += 64) { chk.push_back(v); v += step; }
+      }
+      t = rs_from_fixed(T + (i128)k * c);
+      nout += k;
+    } else {
+      if ((nout & 63) == 0) chk.push_back(t);          // the crossing (or tie) step, in hardware
+      ++nout; t += dt;
+    }
+  }
+  return (int)nout;
+}
+
+static std::shared_ptr<RsShape> rs_plan(int in_len, int src_rate, int sr, int out_len, bool stepwise = false)
 {
   auto sh = std::make_shared<RsShape>();
   const double speed = (double)src_rate / (double)sr, factor = 1.0 / speed;
@@ -103,6 +166,7 @@ static std::shared_ptr<RsShape> rs_plan(int in_len, int src_rate, int sr, int ou
   const double dt = 1.0 / factor;
   int used = 0, outc = 0;
   long long in0 = -(long long)xoff;
+  sh->chk.reserve((size_t)out_len / 64 + (size_t)in_len / 2048 + 64);
   for (;;) {
     int len = (int)(xsize - xread);
     if (len >= in_len - used) len = in_len - used;
@@ -110,9 +174,8 @@ static std::shared_ptr<RsShape> rs_plan(int in_len, int src_rate, int sr, int ou
     const int nx = (used == in_len) ? (int)(xread - xoff) : (int)(xread - 2 * xoff);
     if (nx <= 0) break;
     RsBlock rb; rb.out0 = outc; rb.in0 = in0; rb.chk_off = (long long)sh->chk.size();
-    int nout = 0;
     double t = time; const double end_time = t + nx;
-    while (t < end_time) { if ((nout & 63) == 0) sh->chk.push_back(t); ++nout; t += dt; }
+    const int nout = stepwise ? rs_advance_stepwise(t, dt, end_time, sh->chk) : rs_advance(t, dt, end_time, sh->chk);
     time = t;
     time -= nx; unsigned xp = xoff + nx;
     const unsigned ncreep = (unsigned)((int)time - (int)xoff);
@@ -121,13 +184,41 @@ static std::shared_ptr<RsShape> rs_plan(int in_len, int src_rate, int sr, int ou
     const unsigned nreuse = xread - shift;
     int ncopy = out_len - outc; if (ncopy > nout) ncopy = nout;
     rb.nout = ncopy;
-    if (ncopy > 0) { sh->blocks.push_back(rb); sh->span.push_back(nx + 2 * (int)xoff + 2); }
+    rb.span = nx + 2 * (int)xoff + 2; rb.pad = 0;
+    if (ncopy > 0) { sh->blocks.push_back(rb); sh->span.push_back(rb.span); sh->max_span = std::max(sh->max_span, rb.span); }
     outc += ncopy;
     in0 += shift; xread = nreuse;
     if (ncopy < nout) break;
   }
   sh->produced = outc;
   return sh;
+}
+
+// shared memory k_resample wants for one rate: the block's source span + one (index, coefficient) row per residue
+int afx_rs_smem_need(int sr, int src_rate, int span)
+{
+  int a = src_rate, b = sr;
+  while (b) { const int r = a % b; a = b; b = r; }
+  const long long q = sr / a;
+  const double speed = (double)src_rate / (double)sr;
+  const int tpw = (int)(17.0 * (speed > 1.0 ? speed : 1.0)) + 3, rl = (2 * tpw) | 1;
+  const long long need = (((long long)span * 4 + 15) & ~15LL) + q * 32 + q * rl * 4;   // span + RsRow[q] + float[q][rl]
+  return need <= 200 * 1024 ? (int)need : (int)std::min<long long>(200 * 1024, (((long long)span * 4 + 15) & ~15LL));
+}
+
+// test hook: 0 when the closed-form replay equals the step-by-step one bit for bit (blocks, spans, every checkpoint)
+extern "C" int afx_debug_rs_plan_check(int32_t sample_rate, int64_t nframes, int32_t src_rate)
+{
+  if (sample_rate <= 0 || src_rate <= 0 || nframes <= 0 || nframes > 0x7fffffffLL) return AFX_ERR_ARG;
+  const double speed = (double)src_rate / (double)sample_rate;
+  int n = d2i_round((double)(int)nframes / speed); if (n < 1) n = 1;
+  auto a = rs_plan((int)nframes, src_rate, sample_rate, n, false), b = rs_plan((int)nframes, src_rate, sample_rate, n, true);
+  if (a->produced != b->produced || a->blocks.size() != b->blocks.size() || a->chk.size() != b->chk.size() || a->span != b->span) return 1;
+  for (size_t i = 0; i < a->blocks.size(); ++i)
+    if (a->blocks[i].out0 != b->blocks[i].out0 || a->blocks[i].nout != b->blocks[i].nout || a->blocks[i].in0 != b->blocks[i].in0 ||
+        a->blocks[i].chk_off != b->blocks[i].chk_off) return 2;
+  if (!a->chk.empty() && memcmp(a->chk.data(), b->chk.data(), a->chk.size() * 8) != 0) return 3;
+  return 0;
 }
 
 extern "C" int afx_abi_version(void) { return AFX_ABI_VERSION; }
@@ -272,6 +363,7 @@ extern "C" void afx_destroy(afx_ctx* ctx)
     &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch };
   for (DevBuf* b : bufs) b->release();
   ctx->h_results_cache.release(); ctx->h_plan_cache.release();
+  for (auto& pb : ctx->part_pool) pb.release();
   delete ctx;
 }
 
@@ -395,6 +487,7 @@ int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, 
         b->rs_chk.insert(b->rs_chk.end(), sh->chk.begin(), sh->chk.end());
       }
       for (RsBlock rb : sh->blocks) { rb.chk_off += pit->second; b->rs_blocks.push_back(rb); b->rs_blk_file.push_back(i); }
+      if (!sh->blocks.empty()) b->rs_smem = std::max(b->rs_smem, afx_rs_smem_need(P.sr, f.src_rate, sh->max_span));
       if (sh->produced < d.n) b->rs_tails.push_back({ d.mono_off + sh->produced, (long long)d.n - sh->produced });
     }
     for (int s = 0; s < d.nframes_src; s += CHUNK) { b->src_chunk_file.push_back(i); b->src_chunk_start.push_back(s); }
@@ -518,7 +611,7 @@ extern "C" int afx_batch_upload(afx_batch* b)
   C.dst_chunk_file = (const int*)(dp + p_dcf); C.dst_chunk_start = (const int*)(dp + p_dcs); C.n_dst_chunks = (int)ndc;
   C.rs_chunk_file = (const int*)(dp + p_rcf); C.rs_chunk_start = (const int*)(dp + p_rcs); C.n_rs_chunks = (int)nrc;
   C.rs_blocks = (const RsBlock*)(dp + p_rb); C.rs_blk_file = (const int*)(dp + p_rbf); C.rs_times = (const double*)(dp + p_chk);
-  C.n_rs_blocks = (int)nrb;
+  C.n_rs_blocks = (int)nrb; C.rs_smem_bytes = b->rs_smem;
   b->uploaded = true;
   return AFX_OK;
 }

@@ -279,12 +279,13 @@ struct AfxBatchDev {
   int max_fr;         // largest rhythm frame capacity of any file in the batch
 };
 
-struct RsBlock { int out0; int nout; long long in0; long long chk_off; };   // in0: source index of X[0] (may be negative); chk_off: first time checkpoint
+struct RsBlock { int out0; int nout; long long in0; long long chk_off; int span; int pad; };   // in0: source index of X[0] (may be negative); chk_off: first time checkpoint; span: X[0 .. span) covers every sample the block's filter sums read
 struct AfxCondPlan {       // device arrays built by the host for one batch
   const int* src_chunk_file; const int* src_chunk_start; int n_src_chunks;   // chunks over source frames
   const int* dst_chunk_file; const int* dst_chunk_start; int n_dst_chunks;   // chunks over analysis-rate samples
   const int* rs_chunk_file; const int* rs_chunk_start; int n_rs_chunks;      // same, resampled files only
   const RsBlock* rs_blocks; const int* rs_blk_file; const double* rs_times; int n_rs_blocks;   // rs_times: every 64th output time stamp
+  int rs_smem_bytes;         // shared memory the resampler wants for this batch (source span + coefficient rows of the largest rate)
 };
 void afx_launch_condition_plan(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s, long long* launches);
 void afx_launch_part_reduce(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s);

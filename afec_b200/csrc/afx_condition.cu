@@ -116,16 +116,91 @@ __global__ void __launch_bounds__(CT) k_reduce(AfxBatchDev B, const int* __restr
 }
 
 // ---- libresample HQ restatement (3rdParty/Resample/Dist/src) -------------------------------------
-// One thread per output sample.  The output-sample time stamps (a double accumulator advanced by
-// repeated "+= 1/factor" inside 4096-sample input blocks, resample.c:230-300 / resamplesubs.c:97-119)
-// are data independent; the host replays that recurrence once per distinct (rate, length) pair and
-// uploads, per block, the first output index, the input offset and every 64th time stamp.  A thread
-// reproduces its own stamp from the nearest checkpoint by the same repeated additions (<= 63).
+// One CTA per libresample block (<= 4096 source samples, resample.c:230-300), one thread per output sample.
+// The output time stamps (a double accumulator advanced by repeated "+= 1/factor", resamplesubs.c:97-119) are
+// data independent; the host replays that recurrence once per distinct (rate, length) pair and uploads, per
+// block, the first output index, the input offset and every 64th time stamp.  A thread reproduces its own
+// stamp from the nearest checkpoint by the same repeated additions (<= 63).
+//
+// Coefficients.  Each output sums ~2 x 17 x max(1, speed) products with coefficients picked from the 69632-entry
+// Kaiser-sinc wing at indices (int)(frac(t) * dh + j * dh) that the reference forms by repeated double additions.
+// Done literally that is ~15 instructions per tap (double add, convert, bounds checks, two scattered loads) and
+// the kernel is issue bound.  For a rational rate ratio p / q the fractional parts of the stamps repeat every q
+// outputs, so the first q outputs of a block build, in shared memory, one row of coefficients per residue
+// k mod q, together with the row's stamp fraction and its MARGIN: the smallest distance of any of its running
+// indices ho_j to an integer.  A later output with the same residue has a fraction that differs by ~1e-13
+// (accumulated rounding of the stamps).  Its index sequence is then provably the row's when
+//     |frac' - frac| * dh + 2e-9  <  margin
+// (the two ho sequences start |frac' - frac| * dh (+ 1 ulp) apart and each of the <= 80 additions adds at most
+// half an ulp(2^17) = 7.3e-12 of divergence), and the output is a plain dot product of the row with the staged
+// source span: two shared loads, one multiply, one add per tap, in the reference's order.  Otherwise -- about
+// once per 10^9 taps, and for rows with a tiny margin -- the output walks the exact index sequence against the
+// table.  Results are bit-identical to the literal evaluation.  Rates whose rows do not fit in shared memory
+// (q * taps too large, e.g. 44101 Hz) take the literal path.
+#define RS_NWING (4096 * 34 / 2)
+#define RS_THREADS 512
 
-__global__ void __launch_bounds__(128) k_resample(AfxBatchDev B, AfxTables T, const RsBlock* __restrict__ blocks,
-                                                  const int* __restrict__ blk_file, const double* __restrict__ times,
-                                                  int n_blocks, int analysis_rate)
+struct RsRow { double lph; double margin; int nl, nr; int h0l, h0r; };   // margin < 0: never trust the row
+
+// literal evaluation (filterkit.c:115-215) against the staged source span xs[] (indexed like the block's X[])
+__device__ __forceinline__ float rs_output_exact(double t, double factor, double dh, float lpscl, const float* __restrict__ imp,
+                                                 const float* __restrict__ xs)
 {
+  const double fl = floor(t);
+  const double lph = t - fl, rph = 1.0 - lph;
+  const int xi = (int)fl;
+  float vl = 0.0f, vr = 0.0f;
+  if (factor >= 1) {
+    { double ph = lph * 4096.0; int h = (int)ph; int x = xi;
+      while (h < RS_NWING) { vl = __fadd_rn(vl, __fmul_rn(__ldg(imp + h), xs[x])); h += 4096; x -= 1; } }
+    { double ph = rph * 4096.0; int h = (int)ph; int x = xi + 1; const int end = RS_NWING - 1;
+      if (ph == 0) h += 4096;
+      while (h < end) { vr = __fadd_rn(vr, __fmul_rn(__ldg(imp + h), xs[x])); h += 4096; x += 1; } }
+  } else {
+    { double ho = lph * dh; int x = xi;
+      while ((int)ho < RS_NWING) { vl = __fadd_rn(vl, __fmul_rn(__ldg(imp + (int)ho), xs[x])); ho += dh; x -= 1; } }
+    { double ho = rph * dh; int x = xi + 1; const int end = RS_NWING - 1;
+      if (rph == 0) ho += dh;
+      while ((int)ho < end) { vr = __fadd_rn(vr, __fmul_rn(__ldg(imp + (int)ho), xs[x])); ho += dh; x += 1; } }
+  }
+  return __fmul_rn(__fadd_rn(vl, vr), lpscl);
+}
+
+__device__ __forceinline__ double rs_int_dist(double v) { const double f = v - floor(v); return fmin(f, 1.0 - f); }
+
+// coefficient row of one stamp: the literal index sequences, their tap counts and the margin
+__device__ __forceinline__ void rs_build_row(double t, double factor, double dh, const float* __restrict__ imp,
+                                             float* __restrict__ cl, float* __restrict__ cr, int tpw, RsRow* meta)
+{
+  const double fl = floor(t);
+  const double lph = t - fl, rph = 1.0 - lph;
+  RsRow m; m.lph = lph; m.margin = 1.0; m.nl = 0; m.nr = 0; m.h0l = 0; m.h0r = 0;
+  if (factor >= 1) {
+    // integer index steps: the row applies to every stamp with the same two starting indices (checked exactly)
+    { double ph = lph * 4096.0; int h = (int)ph; m.h0l = h;
+      while (h < RS_NWING && m.nl < tpw) { cl[m.nl++] = __ldg(imp + h); h += 4096; }
+      if (h < RS_NWING) m.margin = -1.0; }
+    { double ph = rph * 4096.0; int h = (int)ph; const int end = RS_NWING - 1; m.h0r = h;
+      if (ph == 0) h += 4096;
+      while (h < end && m.nr < tpw) { cr[m.nr++] = __ldg(imp + h); h += 4096; }
+      if (h < end) m.margin = -1.0; }
+  } else {
+    { double ho = lph * dh;
+      while ((int)ho < RS_NWING && m.nl < tpw) { m.margin = fmin(m.margin, rs_int_dist(ho)); cl[m.nl++] = __ldg(imp + (int)ho); ho += dh; }
+      if ((int)ho < RS_NWING) m.margin = -1.0; else m.margin = fmin(m.margin, rs_int_dist(ho)); }
+    { double ho = rph * dh; const int end = RS_NWING - 1;
+      if (rph == 0) ho += dh;
+      while ((int)ho < end && m.nr < tpw) { m.margin = fmin(m.margin, rs_int_dist(ho)); cr[m.nr++] = __ldg(imp + (int)ho); ho += dh; }
+      if ((int)ho < end) m.margin = -1.0; else m.margin = fmin(m.margin, rs_int_dist(ho)); }
+  }
+  *meta = m;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_resample(AfxBatchDev B, AfxTables T, const RsBlock* __restrict__ blocks,
+                                                         const int* __restrict__ blk_file, const double* __restrict__ times,
+                                                         int n_blocks, int analysis_rate, int smem_bytes)
+{
+  extern __shared__ __align__(16) unsigned char rs_smem[];
   const int bi = blockIdx.x;
   if (bi >= n_blocks) return;
   const RsBlock rb = blocks[bi];
@@ -136,41 +211,100 @@ __global__ void __launch_bounds__(128) k_resample(AfxBatchDev B, AfxTables T, co
   const float* __restrict__ src = B.mono_src + f.src_off;
   float* __restrict__ dst = B.mono + f.mono_off;
   const float* __restrict__ imp = T.rs_imp;
-  const int nwing = 4096 * 34 / 2;
   const int nsrc = f.nframes_src;
   float lpscl = 1.0f;
   if (factor < 1) lpscl = (float)((double)lpscl * factor);
   double dh = factor * 4096.0; if (dh > 4096.0) dh = 4096.0;
   const double* chk = times + rb.chk_off;
-  for (int k = threadIdx.x; k < rb.nout; k += blockDim.x) {
+
+  // rate ratio p / q in lowest terms: the stamps' fractional parts repeat every q outputs
+  int ga = f.src_rate, gb = analysis_rate;
+  while (gb) { const int r = ga % gb; ga = gb; gb = r; }
+  const int q = analysis_rate / ga;
+  const int tpw = (int)(17.0 * (speed > 1.0 ? speed : 1.0)) + 3;     // taps per wing, upper bound
+  const int rl = (2 * tpw) | 1;                                       // floats per row (odd: rows start on distinct banks)
+  const int span = rb.span;
+  const size_t o_meta = ((size_t)span * 4 + 15) & ~(size_t)15, o_rows = o_meta + (size_t)q * sizeof(RsRow);
+  float* xs = reinterpret_cast<float*>(rs_smem);                      // [span] source samples X[0 .. span)
+  RsRow* meta = reinterpret_cast<RsRow*>(rs_smem + o_meta);           // [q]
+  float* rows = reinterpret_cast<float*>(rs_smem + o_rows);           // [q][rl]: left wing at 0, right wing at tpw
+  const bool cached = o_rows + (size_t)q * rl * 4 <= (size_t)smem_bytes;
+  const bool staged = (size_t)span * 4 <= (size_t)smem_bytes;
+
+  if (staged) {
+    for (int i = threadIdx.x; i < span; i += RS_THREADS) { const long long x = rb.in0 + i; xs[i] = (x >= 0 && x < nsrc) ? src[x] : 0.0f; }
+  }
+  if (cached) {
+    for (int k = threadIdx.x; k < q && k < rb.nout; k += RS_THREADS) {
+      double t = chk[k >> 6];
+      for (int a = 0; a < (k & 63); ++a) t = __dadd_rn(t, dt);
+      rs_build_row(t, factor, dh, imp, rows + (size_t)k * rl, rows + (size_t)k * rl + tpw, tpw, meta + k);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < rb.nout; k += RS_THREADS) {
     const int o = rb.out0 + k;
     if (o >= f.n) break;
     double t = chk[k >> 6];
-    for (int q = 0; q < (k & 63); ++q) t = __dadd_rn(t, dt);   // the block's own repeated additions
-    const double fl = floor(t);
-    const double lph = t - fl, rph = 1.0 - lph;
-    const long long xi = rb.in0 + (long long)fl;   // source index of X[(int)t]
+    for (int a = 0; a < (k & 63); ++a) t = __dadd_rn(t, dt);         // the block's own repeated additions
     float v;
-    if (factor >= 1) {
-      // lrsFilterUp, filterkit.c:115-164, no coefficient interpolation
-      float vl = 0.0f, vr = 0.0f;
-      { double ph = lph * 4096.0; int h = (int)ph; long long x = xi;
-        while (h < nwing) { const float s = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vl = __fadd_rn(vl, __fmul_rn(imp[h], s)); h += 4096; x -= 1; } }
-      { double ph = rph * 4096.0; int h = (int)ph; long long x = xi + 1; const int end = nwing - 1;
-        if (ph == 0) h += 4096;
-        while (h < end) { const float s = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vr = __fadd_rn(vr, __fmul_rn(imp[h], s)); h += 4096; x += 1; } }
-      v = __fadd_rn(vl, vr);
-    } else {
-      // lrsFilterUD, filterkit.c:166-215
-      float vl = 0.0f, vr = 0.0f;
-      { double ho = lph * dh; long long x = xi;
-        while ((int)ho < nwing) { const float s = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vl = __fadd_rn(vl, __fmul_rn(imp[(int)ho], s)); ho += dh; x -= 1; } }
-      { double ho = rph * dh; long long x = xi + 1; const int end = nwing - 1;
-        if (rph == 0) ho += dh;
-        while ((int)ho < end) { const float s = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vr = __fadd_rn(vr, __fmul_rn(imp[(int)ho], s)); ho += dh; x += 1; } }
-      v = __fadd_rn(vl, vr);
+    bool done = false;
+    if (cached) {
+      const int r = k % q;
+      const RsRow m = meta[r];
+      const double fl = floor(t), lph = t - fl;
+      bool same;
+      if (factor >= 1) {
+        const double rph = 1.0 - lph;
+        same = m.margin >= 0.0 && (int)(lph * 4096.0) == m.h0l && (int)(rph * 4096.0) == m.h0r && ((rph * 4096.0 == 0) == ((1.0 - m.lph) * 4096.0 == 0));
+      } else {
+        same = (fabs(lph - m.lph) * dh + 2e-9 < m.margin) && ((lph == 0.0) == (m.lph == 0.0));
+      }
+      if (same) {
+        const float* __restrict__ cl = rows + (size_t)r * rl;
+        const float* __restrict__ cr = cl + tpw;
+        const int xi = (int)fl;
+        float vl = 0.0f, vr = 0.0f;
+        const float* __restrict__ xl = xs + xi;          // left wing walks down from X[xi], right wing up from X[xi + 1]
+        const float* __restrict__ xr = xs + xi + 1;
+        int j = 0;
+        for (; j + 4 <= m.nl; j += 4) {
+          vl = __fadd_rn(vl, __fmul_rn(cl[j], xl[-j]));         vl = __fadd_rn(vl, __fmul_rn(cl[j + 1], xl[-j - 1]));
+          vl = __fadd_rn(vl, __fmul_rn(cl[j + 2], xl[-j - 2])); vl = __fadd_rn(vl, __fmul_rn(cl[j + 3], xl[-j - 3]));
+        }
+        for (; j < m.nl; ++j) vl = __fadd_rn(vl, __fmul_rn(cl[j], xl[-j]));
+        for (j = 0; j + 4 <= m.nr; j += 4) {
+          vr = __fadd_rn(vr, __fmul_rn(cr[j], xr[j]));         vr = __fadd_rn(vr, __fmul_rn(cr[j + 1], xr[j + 1]));
+          vr = __fadd_rn(vr, __fmul_rn(cr[j + 2], xr[j + 2])); vr = __fadd_rn(vr, __fmul_rn(cr[j + 3], xr[j + 3]));
+        }
+        for (; j < m.nr; ++j) vr = __fadd_rn(vr, __fmul_rn(cr[j], xr[j]));
+        v = __fmul_rn(__fadd_rn(vl, vr), lpscl);
+        done = true;
+      }
     }
-    dst[o] = __fmul_rn(v, lpscl);
+    if (!done) {
+      if (staged) v = rs_output_exact(t, factor, dh, lpscl, imp, xs);
+      else {
+        // span larger than shared memory (never for the libresample block sizes): direct loads with bounds checks
+        const double fl = floor(t); const double lph = t - fl, rph = 1.0 - lph; const long long xi = rb.in0 + (long long)fl;
+        float vl = 0.0f, vr = 0.0f;
+        if (factor >= 1) {
+          { double ph = lph * 4096.0; int h = (int)ph; long long x = xi;
+            while (h < RS_NWING) { const float sv = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vl = __fadd_rn(vl, __fmul_rn(imp[h], sv)); h += 4096; x -= 1; } }
+          { double ph = rph * 4096.0; int h = (int)ph; long long x = xi + 1; const int end = RS_NWING - 1;
+            if (ph == 0) h += 4096;
+            while (h < end) { const float sv = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vr = __fadd_rn(vr, __fmul_rn(imp[h], sv)); h += 4096; x += 1; } }
+        } else {
+          { double ho = lph * dh; long long x = xi;
+            while ((int)ho < RS_NWING) { const float sv = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vl = __fadd_rn(vl, __fmul_rn(imp[(int)ho], sv)); ho += dh; x -= 1; } }
+          { double ho = rph * dh; long long x = xi + 1; const int end = RS_NWING - 1;
+            if (rph == 0) ho += dh;
+            while ((int)ho < end) { const float sv = (x >= 0 && x < nsrc) ? src[x] : 0.0f; vr = __fadd_rn(vr, __fmul_rn(imp[(int)ho], sv)); ho += dh; x += 1; } }
+        }
+        v = __fmul_rn(__fadd_rn(vl, vr), lpscl);
+      }
+    }
+    dst[o] = v;
   }
 }
 
@@ -342,12 +476,20 @@ void afx_launch_materialise(const float* mono, const AfxState* st, double* out, 
   k_materialise<<<(len + 255) / 256, 256, 0, s>>>(mono, st, out, len);
 }
 
+static void launch_resample(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s)
+{
+  int smem = C.rs_smem_bytes > 0 ? C.rs_smem_bytes : 64 * 1024;
+  if (smem > 200 * 1024) smem = 200 * 1024;
+  cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // per device, see afx_pitch.cu
+  k_resample<<<C.n_rs_blocks, RS_THREADS, smem, s>>>(B, P.t, C.rs_blocks, C.rs_blk_file, C.rs_times, C.n_rs_blocks, P.sr, smem);
+}
+
 // long files conditioned in parts (afx_part.cu): the same passes, phase by phase, over one part's ranges
 void afx_launch_part_reduce(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s)
 {
   k_state_init<<<1, 128, 0, s>>>(B);
   if (C.n_src_chunks > 0) k_downmix<<<C.n_src_chunks, CT, 0, s>>>(B, C.src_chunk_file, C.src_chunk_start, P.sr);
-  if (C.n_rs_blocks > 0) k_resample<<<C.n_rs_blocks, 128, 0, s>>>(B, P.t, C.rs_blocks, C.rs_blk_file, C.rs_times, C.n_rs_blocks, P.sr);
+  if (C.n_rs_blocks > 0) launch_resample(P, B, C, s);
   if (C.n_rs_chunks > 0) k_reduce<<<C.n_rs_chunks, CT, 0, s>>>(B, C.rs_chunk_file, C.rs_chunk_start);
 }
 void afx_launch_part_trim(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s)
@@ -369,7 +511,7 @@ void afx_launch_condition_plan(const AfxParams& P, const AfxBatchDev& B, const A
   k_slotmap<<<B.n_files, 256, 0, s>>>(B, const_cast<int*>(B.slot_file), const_cast<int*>(B.rslot_file)); ++*launches;
   if (C.n_src_chunks > 0) { k_downmix<<<C.n_src_chunks, CT, 0, s>>>(B, C.src_chunk_file, C.src_chunk_start, P.sr); ++*launches; }
   if (C.n_rs_blocks > 0) {
-    k_resample<<<C.n_rs_blocks, 128, 0, s>>>(B, P.t, C.rs_blocks, C.rs_blk_file, C.rs_times, C.n_rs_blocks, P.sr); ++*launches;
+    launch_resample(P, B, C, s); ++*launches;
     k_reduce<<<C.n_rs_chunks, CT, 0, s>>>(B, C.rs_chunk_file, C.rs_chunk_start); ++*launches;
   }
   k_amp<<<fb, 128, 0, s>>>(B); ++*launches;

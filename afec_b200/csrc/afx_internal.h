@@ -44,6 +44,15 @@ struct RsShape {
   std::vector<double> chk;       // every 64th output time stamp of each block
   std::vector<int> span;         // per block: source samples [in0, in0 + span) cover everything its filter sums read
   int produced = 0;              // output samples libresample delivers (<= the requested count)
+  int max_span = 0;
+};
+
+// device + pinned buffers of one part job (afx_part.cu); recycled through afx_ctx::part_pool so that a stream of
+// long files does not pay cudaMalloc / cudaFree per part
+struct PartBufs {
+  DevBuf pcm, mono_src, mono, tab, state;
+  PinBuf htab;
+  void release() { pcm.release(); mono_src.release(); mono.release(); tab.release(); state.release(); htab.release(); }
 };
 
 struct afx_ctx {
@@ -61,6 +70,7 @@ struct afx_ctx {
          d_stats, d_header, d_plan, d_scratch;
   long long group_frames = 393216, group_rframes = 3145728;   // per-launch scratch bound: 3 GB mag, 6 GB rpolar
   PinBuf h_results_cache, h_plan_cache;   // recycled between batches
+  std::vector<PartBufs> part_pool;        // recycled between part jobs
   std::vector<double> zeros;          // backing store of the all-zero series
   std::string error;
   bool debug_times = false;
@@ -82,7 +92,7 @@ struct afx_batch {
   struct Tail { long long off; long long count; }; std::vector<Tail> rs_tails;   // mono samples libresample never writes
   struct Group { int file0, nfiles, slot0, nslots, rslot0, nrslots; };
   std::vector<Group> groups;
-  int max_gslots = 0, max_grslots = 0, max_fr = 0;
+  int max_gslots = 0, max_grslots = 0, max_fr = 0, rs_smem = 0;
   struct CopyRun { const unsigned char* host; size_t dev_off; size_t bytes; bool to_mono; };
   std::vector<AfxInject> inject;      // conditioning reductions made elsewhere (files conditioned in parts)
   std::vector<CopyRun> runs;
@@ -104,6 +114,7 @@ struct afx_batch {
 // shared helpers (afx_api.cu)
 int afx_fail(afx_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess);
 std::shared_ptr<RsShape> afx_rs_shape(int sr, int in_len, int src_rate, int out_len);   // cached libresample replay (process-wide)
+int afx_rs_smem_need(int sr, int src_rate, int span);                                          // dynamic shared memory of k_resample
 int afx_reference_round(double v);                                                            // TMath::d2iRound
 struct AfxCondInput {  // a file whose conditioning reductions were made elsewhere (afx_part.cu): the batch holds one such file
   const float* mono;                  // analysis-rate mono samples [mono_begin, mono_begin + mono_count) of the file

@@ -31,14 +31,18 @@ struct afx_partjob {
   afx_part part;
   AfxFile file;
   AfxState st;
-  DevBuf d_pcm, d_mono_src, d_mono, d_tab, d_state;
+  PartBufs bufs;
   AfxBatchDev dev;
   AfxCondPlan plan;
   bool resampled = false;
   long long zero_from = -1, zero_count = 0;     // analysis-rate samples libresample never delivers (stay 0)
-  int phase = 0;
+  int phase = 0, rs_smem = 0;
   double own_sumsq = 0.0;                       // this part's share: every phase's output merges back to the global sums
-  void release() { d_pcm.release(); d_mono_src.release(); d_mono.release(); d_tab.release(); d_state.release(); }
+  void release()      // hand the buffers back to the context (caller holds ctx->mu)
+  {
+    if (ctx->part_pool.size() < 8) ctx->part_pool.push_back(bufs); else bufs.release();
+    bufs = PartBufs();
+  }
 };
 
 static int analysis_len(int sr, long long nframes, int src_rate)
@@ -123,6 +127,7 @@ extern "C" int afx_part_open(afx_ctx* ctx, const afx_file* whole, const afx_part
   cudaSetDevice(ctx->device);
   afx_partjob* j = new afx_partjob();
   j->ctx = ctx; j->part = *part;
+  if (!ctx->part_pool.empty()) { j->bufs = ctx->part_pool.back(); ctx->part_pool.pop_back(); }
   if (part->out_end > n) { delete j; return afx_fail(ctx, AFX_ERR_ARG, "afx_part_open: part exceeds the file"); }
   j->resampled = whole->src_rate != P.sr;
   const size_t bps = (whole->format == AFX_PCM_I16) ? 2 : 4;
@@ -154,6 +159,7 @@ extern "C" int afx_part_open(afx_ctx* ctx, const afx_file* whole, const afx_part
       for (long long c = c0; c < c1 && c < (long long)sh->chk.size(); ++c) chk.push_back(sh->chk[c]);
       blocks.push_back(rb); blkf.push_back(0);
       covered = rb.out0 + rb.nout;
+      j->rs_smem = std::max(j->rs_smem, afx_rs_smem_need(P.sr, f.src_rate, rb.span));
     }
     if (covered < part->out_end) { j->zero_from = covered; j->zero_count = part->out_end - covered; }   // SA.cpp:579-580
   }
@@ -161,36 +167,39 @@ extern "C" int afx_part_open(afx_ctx* ctx, const afx_file* whole, const afx_part
   auto place = [&](size_t bytes) { size_t o = po; po += (bytes + 255) & ~(size_t)255; return o; };
   const size_t p_file = place(sizeof(AfxFile)), p_scf = place(scf.size() * 4), p_scs = place(scs.size() * 4), p_dcf = place(dcf.size() * 4),
     p_dcs = place(dcs.size() * 4), p_rb = place(blocks.size() * sizeof(RsBlock)), p_rbf = place(blkf.size() * 4), p_chk = place(chk.size() * 8);
-  std::vector<unsigned char> tab(po + 256, 0);
-  memcpy(tab.data() + p_file, &f, sizeof(f));
-  if (!scf.empty()) { memcpy(tab.data() + p_scf, scf.data(), scf.size() * 4); memcpy(tab.data() + p_scs, scs.data(), scs.size() * 4); }
-  if (!dcf.empty()) { memcpy(tab.data() + p_dcf, dcf.data(), dcf.size() * 4); memcpy(tab.data() + p_dcs, dcs.data(), dcs.size() * 4); }
-  if (!blocks.empty()) { memcpy(tab.data() + p_rb, blocks.data(), blocks.size() * sizeof(RsBlock)); memcpy(tab.data() + p_rbf, blkf.data(), blkf.size() * 4); }
-  if (!chk.empty()) memcpy(tab.data() + p_chk, chk.data(), chk.size() * 8);
-
-  cudaError_t e = j->d_tab.reserve(po + 256);
-  if (e == cudaSuccess) e = j->d_state.reserve(sizeof(AfxState) * 2);
-  if (e == cudaSuccess) e = j->d_pcm.reserve(pcm_bytes + 64);
-  if (e == cudaSuccess) e = j->d_mono.reserve((size_t)((j->resampled ? no : ns) + 16) * 4);
-  if (e == cudaSuccess && j->resampled) e = j->d_mono_src.reserve((size_t)(ns + 16) * 4);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(j->d_tab.p, tab.data(), po, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess && pcm_bytes) e = cudaMemcpyAsync(j->d_pcm.p, pcm_slice, pcm_bytes, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);      // `tab` is pageable and goes out of scope
+  PartBufs& Bf = j->bufs;
+  cudaError_t e = Bf.htab.reserve(po + 256);
+  if (e == cudaSuccess) e = Bf.tab.reserve(po + 256);
+  if (e == cudaSuccess) e = Bf.state.reserve(sizeof(AfxState) * 2);
+  if (e == cudaSuccess) e = Bf.pcm.reserve(pcm_bytes + 64);
+  if (e == cudaSuccess) e = Bf.mono.reserve((size_t)((j->resampled ? no : ns) + 16) * 4);
+  if (e == cudaSuccess && j->resampled) e = Bf.mono_src.reserve((size_t)(ns + 16) * 4);
+  if (e == cudaSuccess) {
+    unsigned char* tab = (unsigned char*)Bf.htab.p;
+    memcpy(tab + p_file, &f, sizeof(f));
+    if (!scf.empty()) { memcpy(tab + p_scf, scf.data(), scf.size() * 4); memcpy(tab + p_scs, scs.data(), scs.size() * 4); }
+    if (!dcf.empty()) { memcpy(tab + p_dcf, dcf.data(), dcf.size() * 4); memcpy(tab + p_dcs, dcs.data(), dcs.size() * 4); }
+    if (!blocks.empty()) { memcpy(tab + p_rb, blocks.data(), blocks.size() * sizeof(RsBlock)); memcpy(tab + p_rbf, blkf.data(), blkf.size() * 4); }
+    if (!chk.empty()) memcpy(tab + p_chk, chk.data(), chk.size() * 8);
+    e = cudaMemcpyAsync(Bf.tab.p, tab, po, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  // asynchronous: afx_part_peak's read-back is the first wait (pcm_slice must stay valid until then)
+  if (e == cudaSuccess && pcm_bytes) e = cudaMemcpyAsync(Bf.pcm.p, pcm_slice, pcm_bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) { j->release(); delete j; return afx_fail(ctx, AFX_ERR_CUDA, "afx_part_open", e); }
 
-  unsigned char* dp = (unsigned char*)j->d_tab.p;
+  unsigned char* dp = (unsigned char*)Bf.tab.p;
   AfxBatchDev& D = j->dev;
   memset(&D, 0, sizeof(D));
   D.n_files = 1; D.g_files = 1;
-  D.pcm = (const unsigned char*)j->d_pcm.p; D.mono = (float*)j->d_mono.p; D.mono_src = (float*)j->d_mono_src.p;
-  D.files = (const AfxFile*)(dp + p_file); D.state = (AfxState*)j->d_state.p;
+  D.pcm = (const unsigned char*)Bf.pcm.p; D.mono = (float*)Bf.mono.p; D.mono_src = (float*)Bf.mono_src.p;
+  D.files = (const AfxFile*)(dp + p_file); D.state = (AfxState*)Bf.state.p;
   AfxCondPlan& C = j->plan;
   memset(&C, 0, sizeof(C));
   C.src_chunk_file = (const int*)(dp + p_scf); C.src_chunk_start = (const int*)(dp + p_scs); C.n_src_chunks = (int)scf.size();
   C.dst_chunk_file = (const int*)(dp + p_dcf); C.dst_chunk_start = (const int*)(dp + p_dcs); C.n_dst_chunks = (int)dcf.size();
   if (j->resampled) { C.rs_chunk_file = C.dst_chunk_file; C.rs_chunk_start = C.dst_chunk_start; C.n_rs_chunks = C.n_dst_chunks; }
   C.rs_blocks = (const RsBlock*)(dp + p_rb); C.rs_blk_file = (const int*)(dp + p_rbf); C.rs_times = (const double*)(dp + p_chk);
-  C.n_rs_blocks = (int)blocks.size();
+  C.n_rs_blocks = (int)blocks.size(); C.rs_smem_bytes = j->rs_smem;
   *out = j;
   return AFX_OK;
 }
@@ -218,7 +227,7 @@ extern "C" int afx_part_peak(afx_partjob* j, afx_part_sums* out)
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   if (j->zero_count > 0)
-    CKP(cudaMemsetAsync((float*)j->d_mono.p + (j->zero_from - j->part.out_begin), 0, (size_t)j->zero_count * 4, ctx->stream), "cudaMemsetAsync(mono tail)");
+    CKP(cudaMemsetAsync((float*)j->bufs.mono.p + (j->zero_from - j->part.out_begin), 0, (size_t)j->zero_count * 4, ctx->stream), "cudaMemsetAsync(mono tail)");
   afx_launch_part_reduce(ctx->P, j->dev, j->plan, ctx->stream);
   int rc = fetch_state(j);
   if (rc != AFX_OK) return rc;
@@ -296,7 +305,7 @@ extern "C" int64_t afx_part_read(afx_partjob* j, int64_t begin, int64_t count, f
   if (hi <= lo) return 0;
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
-  CKP(cudaMemcpyAsync(dst + (lo - begin), (const float*)j->d_mono.p + (lo - ob), (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(mono)");
+  CKP(cudaMemcpyAsync(dst + (lo - begin), (const float*)j->bufs.mono.p + (lo - ob), (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(mono)");
   CKP(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
   return hi - lo;
 }
@@ -306,7 +315,10 @@ extern "C" void afx_part_close(afx_partjob* j)
   if (!j) return;
   cudaSetDevice(j->ctx->device);
   cudaStreamSynchronize(j->ctx->stream);
-  j->release();
+  {
+    std::lock_guard<std::mutex> lk(j->ctx->mu);
+    j->release();
+  }
   delete j;
 }
 

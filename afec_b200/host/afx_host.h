@@ -126,6 +126,15 @@ public:
   int ExtractBatch(const std::vector<std::string>& FileNames, TSampleDescriptorPool* pPool, std::mutex& PoolLock,
                    TProgress* pProgress = nullptr, const volatile bool* pAbort = nullptr) const;
 
+  // Long files (BASELINE config 5): the decoded file is cut into NumParts sample-range parts (0 = one per device),
+  // part p is conditioned on slot p % slots -- its own GPU when the analyser was built over several devices --
+  // the per-file reductions are combined here on the host between the three phases, and the <= 20 s the reference
+  // analyses run on slot 0.  Same values as Analyze() (include/afec_b200.h, "long files conditioned in parts").
+  TSampleDescriptors AnalyzeInParts(const std::string& FileName, int NumParts = 0) const;
+  // Analyze() / Extract() route files with at least this many decoded PCM bytes through AnalyzeInParts when the
+  // analyser drives more than one device (0 disables)
+  void SetLongFileBytes(size_t Bytes) { mLongFileBytes = Bytes; }
+
   int SampleRate() const { return mSampleRate; }
   int FftFrameSize() const { return mFftFrameSize; }
   int HopFrameSize() const { return mHopFrameSize; }
@@ -137,6 +146,9 @@ private:
   int mSampleRate, mFftFrameSize, mHopFrameSize;
   size_t mMaxBatchBytes = (size_t)256 << 20;
   int mMaxBatchFiles = 2048;
+  size_t mLongFileBytes = (size_t)512 << 20;
+  int mNumDevices = 1;
+  TSampleDescriptors AnalyzeDecodedInParts(const std::string& FileName, const TDecodedAudio& Audio, int NumParts) const;
   std::vector<std::unique_ptr<Slot>> mSlots;
   mutable std::mutex mSingleLock;        // serialises Analyze()/Extract() on slot 0
 };

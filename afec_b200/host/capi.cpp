@@ -76,4 +76,21 @@ int afxh_extract_one(const char* db, const char* filename, int hop, int device)
   } catch (const std::exception&) { return -2; }
 }
 
+// one long file through the part path (TGpuSampleAnalyser::AnalyzeInParts) into the pool
+int afxh_extract_one_in_parts(const char* db, const char* filename, int hop, const int* devices, int n_devices, int n_parts)
+{
+  try {
+    TSqliteSampleDescriptorPool pool;
+    if (!pool.Open(db)) return -1;
+    TGpuSampleAnalyser an(44100, 2048, hop, std::vector<int>(devices, devices + n_devices), 1);
+    try {
+      const TSampleDescriptors d = an.AnalyzeInParts(filename, n_parts);
+      pool.InsertSample(filename, d);
+    } catch (const std::exception& e) {
+      pool.InsertFailedSample(filename, std::string("Sample failed to analyse: ") + e.what());
+    }
+    return 0;
+  } catch (const std::exception&) { return -2; }
+}
+
 }  // extern "C"

@@ -46,6 +46,7 @@ TGpuSampleAnalyser::TGpuSampleAnalyser(int SampleRate, int FftFrameSize, int Hop
       throw TReadableException(std::string("TGpuSampleAnalyser: ") + afx_last_error(nullptr));
     mSlots.push_back(std::move(slot));
   }
+  mNumDevices = (int)Devices.size();
 }
 
 TGpuSampleAnalyser::~TGpuSampleAnalyser() {}
@@ -66,10 +67,75 @@ static const char* file_status_message(int status)
   }
 }
 
+TSampleDescriptors TGpuSampleAnalyser::AnalyzeInParts(const std::string& FileName, int NumParts) const
+{
+  TDecodedAudio audio;
+  ReadWaveFile(FileName, audio);
+  return AnalyzeDecodedInParts(FileName, audio, NumParts);
+}
+
+TSampleDescriptors TGpuSampleAnalyser::AnalyzeDecodedInParts(const std::string& FileName, const TDecodedAudio& audio, int NumParts) const
+{
+  if (audio.mChannels < 1 || audio.mChannels > 8) throw TReadableException(file_status_message(AFX_FILE_BAD_CHANNELS));
+  if (audio.mFrames == 0) throw TReadableException(file_status_message(AFX_FILE_EMPTY));
+  std::lock_guard<std::mutex> lock(mSingleLock);
+  // one slot per device first (slots are laid out device-major), so parts spread over the GPUs
+  std::vector<Slot*> slots;
+  const int per_dev = (int)mSlots.size() / mNumDevices;
+  for (int d = 0; d < mNumDevices; ++d) slots.push_back(mSlots[(size_t)d * per_dev].get());
+  const int n_parts = NumParts > 0 ? NumParts : (int)slots.size();
+  std::vector<afx_part> parts((size_t)n_parts);
+  if (afx_part_plan(mSampleRate, audio.mFrames, audio.mSampleRate, n_parts, parts.data()) != AFX_OK)
+    throw TReadableException("afx_part_plan failed");
+  afx_file whole; describe(audio, nullptr, whole);
+  const size_t frame_bytes = (size_t)audio.mChannels * (audio.mFormat == AFX_PCM_I16 ? 2 : 4);
+  std::vector<afx_partjob*> jobs((size_t)n_parts, nullptr);
+  std::vector<afx_part_sums> sums((size_t)n_parts);
+  std::vector<std::string> errors((size_t)n_parts);
+  struct Closer { std::vector<afx_partjob*>& j; ~Closer() { for (auto* p : j) if (p) afx_part_close(p); } } closer{ jobs };
+  {
+    // phase A carries the bulk (H2D copy, downmix, resample): one thread per part so the GPUs work side by side
+    std::vector<std::thread> th;
+    for (int p = 0; p < n_parts; ++p) th.emplace_back([&, p]() {
+      Slot* S = slots[(size_t)p % slots.size()];
+      const unsigned char* slice = audio.mBytes.data() + (size_t)parts[p].src_begin * frame_bytes;
+      if (afx_part_open(S->ctx, &whole, &parts[p], slice, &jobs[p]) != AFX_OK || afx_part_peak(jobs[p], &sums[p]) != AFX_OK)
+        errors[p] = afx_last_error(S->ctx);
+    });
+    for (auto& t : th) t.join();
+  }
+  for (const auto& e : errors) if (!e.empty()) throw TReadableException(e);
+  auto combine = [&]() { afx_part_sums g; afx_part_sums_init(&g); for (const auto& s : sums) afx_part_sums_merge(&g, &s); return g; };
+  afx_part_sums g = combine();
+  for (int p = 0; p < n_parts; ++p)
+    if (afx_part_trim(jobs[p], &g, &sums[p]) != AFX_OK) throw TReadableException(afx_last_error(slots[(size_t)p % slots.size()]->ctx));
+  g = combine();
+  for (int p = 0; p < n_parts; ++p)
+    if (afx_part_effective(jobs[p], &g, &sums[p]) != AFX_OK) throw TReadableException(afx_last_error(slots[(size_t)p % slots.size()]->ctx));
+  g = combine();
+  Slot& S0 = *slots[0];
+  int64_t begin = 0, count = 0;
+  afx_part_window(S0.ctx, &whole, &g, &begin, &count);
+  std::vector<float> window((size_t)std::max<int64_t>(count, 1), 0.0f);
+  int64_t got = 0;
+  for (int p = 0; p < n_parts; ++p) { const int64_t r = afx_part_read(jobs[p], begin, count, window.data()); if (r > 0) got += r; }
+  if (got != count) throw TReadableException("long file: incomplete analysis window");
+  afx_batch* b = nullptr;
+  if (afx_analyze_conditioned(S0.ctx, &whole, &g, window.data(), begin, count, &b) != AFX_OK) throw TReadableException(afx_last_error(S0.ctx));
+  afx_file_result r;
+  afx_batch_result(b, 0, &r);
+  TSampleDescriptors out;
+  out.mFileName = FileName; out.mFileType = ExtractFileExtension(FileName);
+  out.Assign(r);
+  afx_batch_free(b);
+  return out;
+}
+
 TSampleDescriptors TGpuSampleAnalyser::Analyze(const std::string& FileName) const
 {
   TDecodedAudio audio;
   ReadWaveFile(FileName, audio);               // throws with the loader's message
+  if (mNumDevices > 1 && mLongFileBytes && audio.mBytes.size() >= mLongFileBytes) return AnalyzeDecodedInParts(FileName, audio, 0);
   std::lock_guard<std::mutex> lock(mSingleLock);
   Slot& S = *mSlots[0];
   afx_file f; describe(audio, audio.mBytes.data(), f);
@@ -102,6 +168,12 @@ void TGpuSampleAnalyser::Extract(const std::string& FileName, TSampleDescriptorP
   }
   TSampleDescriptors results;
   try {
+    if (mNumDevices > 1 && mLongFileBytes && audio.mBytes.size() >= mLongFileBytes) {
+      results = AnalyzeDecodedInParts(FileName, audio, 0);
+      const std::lock_guard<std::mutex> lock(PoolLock);
+      pPool->InsertSample(FileName, results);
+      return;
+    }
     std::lock_guard<std::mutex> lock(mSingleLock);
     Slot& S = *mSlots[0];
     afx_file f; describe(audio, audio.mBytes.data(), f);

@@ -161,7 +161,8 @@ int afx_part_plan(int32_t sample_rate, int64_t nframes, int32_t src_rate, int32_
 void afx_part_sums_init(afx_part_sums* s);
 void afx_part_sums_merge(afx_part_sums* acc, const afx_part_sums* other);
 /* `whole` describes the whole file (nframes = all frames; its pcm member is ignored), pcm_slice holds the
- * interleaved frames [part->src_begin, part->src_end) */
+ * interleaved frames [part->src_begin, part->src_end) and must stay valid until afx_part_peak() returned (the
+ * host -> device copy is asynchronous) */
 int afx_part_open(afx_ctx* ctx, const afx_file* whole, const afx_part* part, const void* pcm_slice, afx_partjob** out);
 int afx_part_peak(afx_partjob* j, afx_part_sums* out);
 int afx_part_trim(afx_partjob* j, const afx_part_sums* global, afx_part_sums* out);
@@ -196,6 +197,10 @@ int64_t afx_batch_conditioned(const afx_batch* b, int32_t file_index, double* ou
  * n = 256, 1024 or 2048 points through the kernels' own FFT core -- the known-answer hook that plays the
  * role of the reference's TAudioTypesTest::Fourier (Source/Core/AudioTypes/Test/TestFourier.cpp:12-84). */
 int afx_debug_fft(afx_ctx* ctx, int32_t n, int32_t batch, const double* in, double* out);
+
+/* debugging / parity: 0 when the closed-form replay of libresample's time accumulator (resamplesubs.c:97-119)
+ * used to plan the resampler kernel equals the step-by-step replay bit for bit; host arithmetic only */
+int afx_debug_rs_plan_check(int32_t sample_rate, int64_t nframes, int32_t src_rate);
 
 #ifdef __cplusplus
 }

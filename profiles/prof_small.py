@@ -6,9 +6,15 @@ import torch
 from afec_b200 import api, synth
 hop = int(os.environ.get("PROF_HOP", "1024"))
 feats = api.FEAT_SPECTRAL if os.environ.get("PROF_FEATS") == "spectral" else api.FEAT_ALL
-pcms = synth.tiled_corpus(int(os.environ.get("PROF_FILES", "400")), 16, seconds=3.0, seed0=0)
+rate = 44100
+if os.environ.get("PROF_LONG"):          # one 10-minute 96 kHz stereo file: the conditioning kernels of BASELINE configs[4]
+    rate = 96000
+    clip = synth.one_shot(7, 30.0, rate=rate, channels=2)
+    pcms = [np.ascontiguousarray(np.tile(clip, (20, 1)))]
+else:
+    pcms = synth.tiled_corpus(int(os.environ.get("PROF_FILES", "400")), 16, seconds=3.0, seed0=0)
 an = api.SampleAnalyser(44100, 2048, hop, features=feats)
-b = an.batch(pcms, [44100]*len(pcms))
+b = an.batch(pcms, [rate]*len(pcms))
 b.upload(); b.compute(); b.compute(); b.sync()
 torch.cuda.nvtx.range_push("prof")
 b.compute(); b.sync()

@@ -74,3 +74,31 @@ def test_single_file_extract_entry_point(tmp_path):
     for name in ("kick.wav", "_Not A Wavefile.wav"):
         errs = dbcompare.compare_row(got[name], want[name])
         assert not errs, "\n".join(errs[:20])
+
+
+def test_long_file_in_parts_writes_the_same_row(tmp_path):
+    """TGpuSampleAnalyser::AnalyzeInParts (the long-file path of the C++ adapter, BASELINE config 5): the row it writes
+    equals the row of the whole-file Extract() -- every BLOB byte for byte."""
+    import ctypes as C
+    import numpy as np
+    from afec_b200 import synth
+    from oracle import oracle
+    L = C.CDLL(afx_build.HOST_LIB)
+    L.afxh_extract_one.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    L.afxh_extract_one_in_parts.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]
+    d = str(tmp_path)
+    clip = synth.one_shot(41, 6.0, rate=96000, channels=2)
+    wav = os.path.join(d, "long_96k_stereo.wav")
+    oracle.write_wav(wav, np.ascontiguousarray(np.tile(clip, (4, 1))), 96000)
+    a, b = os.path.join(d, "whole.db"), os.path.join(d, "parts.db")
+    assert L.afxh_extract_one(a.encode(), wav.encode(), 1024, 0) == 0
+    dev = (C.c_int * 1)(0)
+    assert L.afxh_extract_one_in_parts(b.encode(), wav.encode(), 1024, dev, 1, 3) == 0
+    got, _, _ = dbcompare.rows(b)
+    want, _, _ = dbcompare.rows(a)
+    g, w = got["long_96k_stereo.wav"], want["long_96k_stereo.wav"]
+    assert w["status"] == "succeeded" and g["status"] == "succeeded"
+    for k in w:
+        if k == "modtime":
+            continue
+        assert g[k] == w[k], k

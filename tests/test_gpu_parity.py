@@ -220,3 +220,19 @@ def test_long_resampled_stereo_file_vs_oracle(analysers, feats, oracle_lib):
     want = oracle_lib.analyze(pcm, src_rate=96000, file_size=44 + pcm.size * 2)
     check(r, want, feats, mdata=data)
     b.free()
+
+
+@pytest.mark.parametrize("rate,seconds", [(48000, 6.0), (88200, 3.0), (32000, 4.0), (11025, 5.0), (192000, 2.0), (44101, 2.0),
+                                          (96000, 12.0), (22050, 9.0), (16000, 3.0), (47999, 1.0)])
+def test_resampler_bit_exact_across_rates(analysers, oracle_lib, rate, seconds):
+    """k_resample against the oracle's libresample restatement, bit for bit, over rate ratios p / q that exercise the
+    shared-memory coefficient rows (q = 147, 441, 1, 2, 4), several blocks per file, and ratios whose rows do not fit
+    (44101 / 44100, 47999 / 44100: the literal look-up)."""
+    pcm = synth.one_shot(1200 + rate % 97, seconds, rate=rate, channels=1 + (rate % 2))
+    an = analysers(1024)
+    b = an.batch([pcm], [rate]).run()
+    data, off, pk, rms = oracle_lib.condition(pcm, src_rate=rate)
+    got = b.conditioned(0)
+    b.free()
+    assert got.shape == data.shape
+    assert np.array_equal(got, data)

@@ -182,3 +182,12 @@ def test_two_ranks_gloo_protocol(tmp_path, oracle_lib):
     r = torch.load(out, weights_only=False)
     g = longfile.sums_from_array(r["g"])
     check_against_oracle(oracle_lib, long_mono(), g, r["win"], r["begin"])
+
+
+@pytest.mark.parametrize("nframes,rate", [(96000 * 600, 96000), (48000 * 60, 48000), (22050 * 100, 22050), (88200 * 60, 88200),
+                                          (32000 * 50, 32000), (8000 * 30, 8000), (11025 * 30, 11025), (192000 * 30, 192000),
+                                          (44101 * 30, 44101), (96000 * 10 + 17, 96000), (37, 96000), (100000, 47999)])
+def test_closed_form_time_replay_is_bit_exact(nframes, rate):
+    """The resampler plan's O(blocks) replay of libresample's `t += dt` accumulator (resamplesubs.c:97-119) equals the
+    step-by-step replay bit for bit: blocks, spans and every time checkpoint."""
+    assert api.load_library().afx_debug_rs_plan_check(44100, nframes, rate) == 0
