@@ -247,6 +247,7 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete ctx; return fail(nullptr, AFX_ERR_CUDA, "cudaStreamCreate", e); }
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) { e = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming); }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_spec, cudaEventDisableTiming);
   if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaStreamCreate(side)", e); }
@@ -357,6 +358,7 @@ extern "C" void afx_destroy(afx_ctx* ctx)
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   for (int i = 0; i < 3; ++i) { if (ctx->side[i]) { cudaStreamSynchronize(ctx->side[i]); cudaStreamDestroy(ctx->side[i]); } if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_spec) cudaEventDestroy(ctx->ev_spec);
   DevBuf* bufs[] = { &ctx->tables, &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,

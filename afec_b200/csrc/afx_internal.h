@@ -62,6 +62,7 @@ struct afx_ctx {
   // side streams: the pitch, autocorrelation and rhythm chains only depend on the conditioned signal (pitch also on
   // the spectrum's centroid), so they run beside the spectrum -> bands -> peaks chain and fill each other's idle pipes
   cudaStream_t side[3] = { nullptr, nullptr, nullptr };
+  cudaStream_t copy_stream = nullptr;   // H2D copies of part jobs: a later part uploads while an earlier one computes
   cudaEvent_t ev_fork = nullptr, ev_spec = nullptr, ev_join[3] = { nullptr, nullptr, nullptr };
   bool multi_stream = true;
   AfxParams P;

@@ -37,6 +37,7 @@ struct afx_partjob {
   bool resampled = false;
   long long zero_from = -1, zero_count = 0;     // analysis-rate samples libresample never delivers (stay 0)
   int phase = 0, rs_smem = 0;
+  cudaEvent_t ev_h2d = nullptr;                 // the slice and the tables are on the device
   double own_sumsq = 0.0;                       // this part's share: every phase's output merges back to the global sums
   void release()      // hand the buffers back to the context (caller holds ctx->mu)
   {
@@ -181,11 +182,14 @@ extern "C" int afx_part_open(afx_ctx* ctx, const afx_file* whole, const afx_part
     if (!dcf.empty()) { memcpy(tab + p_dcf, dcf.data(), dcf.size() * 4); memcpy(tab + p_dcs, dcs.data(), dcs.size() * 4); }
     if (!blocks.empty()) { memcpy(tab + p_rb, blocks.data(), blocks.size() * sizeof(RsBlock)); memcpy(tab + p_rbf, blkf.data(), blkf.size() * 4); }
     if (!chk.empty()) memcpy(tab + p_chk, chk.data(), chk.size() * 8);
-    e = cudaMemcpyAsync(Bf.tab.p, tab, po, cudaMemcpyHostToDevice, ctx->stream);
+    e = cudaMemcpyAsync(Bf.tab.p, tab, po, cudaMemcpyHostToDevice, ctx->copy_stream);
   }
-  // asynchronous: afx_part_peak's read-back is the first wait (pcm_slice must stay valid until then)
-  if (e == cudaSuccess && pcm_bytes) e = cudaMemcpyAsync(Bf.pcm.p, pcm_slice, pcm_bytes, cudaMemcpyHostToDevice, ctx->stream);
-  if (e != cudaSuccess) { j->release(); delete j; return afx_fail(ctx, AFX_ERR_CUDA, "afx_part_open", e); }
+  // asynchronous, on the context's copy stream: afx_part_peak makes the kernels wait for it, so a part opened
+  // early uploads while earlier parts compute (pcm_slice must stay valid until afx_part_peak returned)
+  if (e == cudaSuccess && pcm_bytes) e = cudaMemcpyAsync(Bf.pcm.p, pcm_slice, pcm_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&j->ev_h2d, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(j->ev_h2d, ctx->copy_stream);
+  if (e != cudaSuccess) { if (j->ev_h2d) cudaEventDestroy(j->ev_h2d); j->release(); delete j; return afx_fail(ctx, AFX_ERR_CUDA, "afx_part_open", e); }
 
   unsigned char* dp = (unsigned char*)Bf.tab.p;
   AfxBatchDev& D = j->dev;
@@ -226,6 +230,7 @@ extern "C" int afx_part_peak(afx_partjob* j, afx_part_sums* out)
   afx_ctx* ctx = j->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
+  CKP(cudaStreamWaitEvent(ctx->stream, j->ev_h2d, 0), "cudaStreamWaitEvent");
   if (j->zero_count > 0)
     CKP(cudaMemsetAsync((float*)j->bufs.mono.p + (j->zero_from - j->part.out_begin), 0, (size_t)j->zero_count * 4, ctx->stream), "cudaMemsetAsync(mono tail)");
   afx_launch_part_reduce(ctx->P, j->dev, j->plan, ctx->stream);
@@ -314,6 +319,7 @@ extern "C" void afx_part_close(afx_partjob* j)
 {
   if (!j) return;
   cudaSetDevice(j->ctx->device);
+  if (j->ev_h2d) { cudaEventSynchronize(j->ev_h2d); cudaEventDestroy(j->ev_h2d); }
   cudaStreamSynchronize(j->ctx->stream);
   {
     std::lock_guard<std::mutex> lk(j->ctx->mu);

@@ -1,6 +1,8 @@
 // Small C entry points over the host classes, for language bindings and tests (ctypes).
 #include "afx_host.h"
 
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 
 using namespace afec;
@@ -74,6 +76,32 @@ int afxh_extract_one(const char* db, const char* filename, int hop, int device)
     an.Extract(filename, &pool, lock);
     return 0;
   } catch (const std::exception&) { return -2; }
+}
+
+// sink throughput: insert n_rows synthetic rows of a file with `frames` main and `rframes` rhythm
+// frames, `bulk` rows per transaction; returns seconds (< 0 on error).  No GPU involved.
+double afxh_sink_bench(const char* db, int n_rows, int frames, int rframes, int bulk)
+{
+  try {
+    TSqliteSampleDescriptorPool pool;
+    if (!pool.Open(db)) return -1.0;
+    TSampleDescriptors d;
+    d.mFileType = "wav"; d.mFrames = frames; d.mRhythmFrames = rframes;
+    for (int s = 0; s < AFX_N_FS; ++s) { const int n = s < AFX_N_FS_MAIN ? frames : rframes; d.mFramedScalars[s].resize(n); for (int i = 0; i < n; ++i) d.mFramedScalars[s][i] = 0.001 * i + s; }
+    for (int v = 0; v < AFX_N_FV; ++v) { const size_t n = (size_t)frames * kFramedVectorBands[v]; d.mFramedVectors[v].resize(n); for (size_t i = 0; i < n; ++i) d.mFramedVectors[v][i] = 1e-3 * (double)i; }
+    for (int s = 0; s < AFX_N_SERIES; ++s) for (int k = 0; k < AFX_N_STATS; ++k) d.mStats[s][k] = s + 0.01 * k;
+    const auto t0 = std::chrono::steady_clock::now();
+    char name[64];
+    for (int i = 0; i < n_rows; ++i) {
+      if (bulk > 1 && i % bulk == 0) pool.BeginBulk();
+      snprintf(name, sizeof(name), "/nonexistent/f%07d.wav", i);
+      d.mFileName = name;
+      pool.InsertSample(name, d);
+      if (bulk > 1 && (i % bulk == bulk - 1 || i == n_rows - 1)) pool.EndBulk();
+    }
+    pool.Close();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  } catch (const std::exception&) { return -2.0; }
 }
 
 // one long file through the part path (TGpuSampleAnalyser::AnalyzeInParts) into the pool

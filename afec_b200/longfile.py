@@ -148,12 +148,15 @@ def analyze_in_parts(analysers, pcm: np.ndarray, rate: int, n_parts: int | None 
 
 
 def analyze_sharded(an, whole: api.AfxFile, part, pcm_slice, dist, analysis_rank: int = 0, job_factory=PartJob,
-                    group=None, device=None, finish=analyze_conditioned, window=window_of):
+                    group=None, device=None, finish=analyze_conditioned, window=window_of, job=None):
     """One process per part (torch.distributed, rank = part index).  Returns the analysis Batch on `analysis_rank`,
-    None elsewhere.  The only traffic: three all-gathers of a 112-byte record and a gather of the window pieces."""
+    None elsewhere.  The only traffic: three all-gathers of a 112-byte record and a gather of the window pieces.
+    `job`: a part job opened earlier (its host -> device copy is asynchronous, so the next file's part can be in
+    flight while this file goes through its phases)."""
     import torch
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    job = job_factory(an, whole, part, pcm_slice)
+    if job is None:
+        job = job_factory(an, whole, part, pcm_slice)
 
     def combine(mine: api.AfxPartSums) -> api.AfxPartSums:
         t = torch.from_numpy(sums_to_array(mine))

@@ -221,10 +221,17 @@ def run_long_sharded(args, wl, rank, local_rank, world):
 
     def step():
         frames = 0
+        nxt = None
         for k in range(n_files):
             if world > 1:
+                # the next file's part is opened (asynchronous H2D) before this file's host-mediated phases
                 p = (rank - k) % world
-                b = longfile.analyze_sharded(an, whole, parts[p], slices[p], dist, analysis_rank=k % world, device=dev)
+                job = nxt if nxt is not None else longfile.PartJob(an, whole, parts[p], slices[p])
+                nxt = None
+                if k + 1 < n_files:
+                    p1 = (rank - k - 1) % world
+                    nxt = longfile.PartJob(an, whole, parts[p1], slices[p1])
+                b = longfile.analyze_sharded(an, whole, parts[p], slices[p], dist, analysis_rank=k % world, device=dev, job=job)
             else:
                 jobs = [longfile.PartJob(an, whole, parts[p], slices[p]) for p in range(n_parts)]
                 g = longfile.merge_sums([j.peak() for j in jobs])
@@ -519,10 +526,16 @@ def main():
                      "algorithmic_flops_per_frame": flops_per_frame},
             "groups_ms": groups,
         }
+        # DRAM traffic of the dominant kernel group from the committed `ncu --set full` capture (bytes per main frame
+        # there x the frames of this launch); the capture is of the same kernels on a smaller batch of the same files
         prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(prof):
             with open(prof) as f:
-                roof["traffic"] = json.load(f).get(wl["features"], {}).get("dram_bytes_per_launch")
+                tr = json.load(f).get(wl["features"], {})
+            per_frame = tr.get("groups", {}).get(top, {}).get("dram_bytes_per_main_frame")
+            if per_frame and tr.get("hop") == wl["hop"]:
+                roof["traffic"] = per_frame * frames
+                roof["traffic_source"] = tr.get("source")
     except Exception as e:  # the roofline leg must not take the headline number down
         roof = {"bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
                 "traffic": None, "error": repr(e)}
