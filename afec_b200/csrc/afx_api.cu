@@ -325,7 +325,7 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_win = place(window.size() * 8), o_rwin = place(rwindow.size() * 8), o_mel = place(mel.size() * 8),
     o_dct = place(dct.size() * 8), o_tw = place(tw2048.size() * 8), o_tw5 = place(tw512.size() * 8), o_imp = place(imp.size() * 4),
-    o_ft2 = place(ft2.size() * 8), o_ft3a = place(ft3a.size() * 8), o_ft3b = place(ft3b.size() * 8);
+    o_ft2 = place(ft2.size() * 8), o_ft3a = place(ft3a.size() * 8), o_ft3b = place(ft3b.size() * 8), o_ctr = place(64 * 4);
   e = ctx->tables.reserve(off);
   if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMalloc(tables)", e); }
   unsigned char* base = (unsigned char*)ctx->tables.p;
@@ -344,6 +344,7 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   P.t.mel = (const double*)(base + o_mel); P.t.dct = (const double*)(base + o_dct);
   P.t.tw2048 = (const double2*)(base + o_tw); P.t.tw512 = (const double2*)(base + o_tw5);
   P.t.rs_imp = (const float*)(base + o_imp);
+  P.t.work_ctr = (unsigned int*)(base + o_ctr);
   P.t.fft_t2 = (const double2*)(base + o_ft2); P.t.fft_t3_1024 = (const double2*)(base + o_ft3a); P.t.fft_t3_2048 = (const double2*)(base + o_ft3b);
 
   ctx->max_frame_cap = (P.analysis_cap - AFX_RFFT) / AFX_RHOP + 2;

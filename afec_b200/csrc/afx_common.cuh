@@ -91,6 +91,7 @@ struct AfxTables {          // per-context constant tables in device memory
   const double* mel;        // [14][1024]
   const double* dct;        // [14][14] cos(pi n/14 (m+0.5)), row n
   const float* rs_imp;      // [69632] resampler wing
+  unsigned int* work_ctr;   // [64] work-claim counters of the persistent kernels (zeroed on the launching stream)
 };
 
 struct AfxParams {

@@ -95,7 +95,11 @@ struct FftTw {
   const double2* t3;     // [R - 1][256] exp(-2 pi i r j / N), R = 4 (N = 1024) or 8 (N = 2048); unused for N = 256
 };
 
-template <int N, class Sync>
+// TW_SMEM: the twiddle tables were copied to shared memory by the caller (plain loads instead of ld.global.nc)
+template <bool TW_SMEM>
+__device__ __forceinline__ double2 fft_tw_load(const double2* p) { return TW_SMEM ? *p : __ldg(p); }
+
+template <int N, class Sync, bool TW_SMEM = false>
 __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict__ buf, const FftTw tw, int tid, Sync sync)
 {
   constexpr int NT = N / 16;
@@ -112,7 +116,7 @@ __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict_
   {
     const int k = tid & 15;
 #pragma unroll
-    for (int r = 1; r < 16; ++r) v[r] = f_mul(v[r], __ldg(tw.t2 + (r - 1) * 16 + k));
+    for (int r = 1; r < 16; ++r) v[r] = f_mul(v[r], fft_tw_load<TW_SMEM>(tw.t2 + (r - 1) * 16 + k));
     f_dft16(v);
     const int base = (tid - k) * 16 + k;
 #pragma unroll
@@ -131,7 +135,7 @@ __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict_
     for (int b = 0; b < 4; ++b) {
       const int i = tid + NT * b;          // k = i (i < p = 256)
 #pragma unroll
-      for (int r = 1; r < 4; ++r) v[4 * b + r] = f_mul(v[4 * b + r], __ldg(tw.t3 + (r - 1) * 256 + i));
+      for (int r = 1; r < 4; ++r) v[4 * b + r] = f_mul(v[4 * b + r], fft_tw_load<TW_SMEM>(tw.t3 + (r - 1) * 256 + i));
       f_r4(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) buf[FFT_PHYS(i + q * 256)] = v[4 * b + q];
@@ -147,7 +151,7 @@ __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict_
     for (int b = 0; b < 2; ++b) {
       const int i = tid + NT * b;
 #pragma unroll
-      for (int r = 1; r < 8; ++r) v[8 * b + r] = f_mul(v[8 * b + r], __ldg(tw.t3 + (r - 1) * 256 + i));
+      for (int r = 1; r < 8; ++r) v[8 * b + r] = f_mul(v[8 * b + r], fft_tw_load<TW_SMEM>(tw.t3 + (r - 1) * 256 + i));
     }
     f_dft8<0>(v);
     f_dft8<8>(v);

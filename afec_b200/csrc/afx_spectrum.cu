@@ -12,6 +12,8 @@
 // magnitude and the order-free sums, and 12 consecutive analysis bins for the rolloff prefix sums.
 #include "afx_fft16.cuh"
 #include "../../include/afec_b200.h"
+#include <algorithm>
+#include <cstdlib>
 
 #define SG 64               // threads per frame
 #define SF 4                // frames per CTA
@@ -43,7 +45,7 @@ __device__ __forceinline__ double group_max(double v, double* xch, int gt, Sync 
   return v;
 }
 
-__global__ void __launch_bounds__(SG * SF, 3) k_spectrum(AfxBatchDev B, AfxParams P, unsigned features)
+__global__ void __launch_bounds__(SG * SF, 3) k_spectrum_old(AfxBatchDev B, AfxParams P, unsigned features)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int g = threadIdx.x / SG, gt = threadIdx.x % SG, lane = gt & 31, gw = gt >> 5;
@@ -208,6 +210,242 @@ __global__ void __launch_bounds__(SG * SF, 3) k_spectrum(AfxBatchDev B, AfxParam
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent form: one CTA per SM, NG frame groups of 64 threads, every group walks frame slots it claims from a
+// global counter (SCH at a time).  What this buys over one-CTA-per-4-frames:
+//   * the window, the two FFT twiddle tables and the real-unpack twiddles (40 KB) live in shared memory for the
+//     whole kernel -- with 3 x 70 KB of FFT buffers per SM only 28 KB of L1 are left and the tables used to miss
+//     half the time (ncu: 53 % L1 hit rate on global loads, long-scoreboard the top stall);
+//   * one CTA per SM leaves 96+ registers per thread: the 16 complex points and the 16 magnitudes of a thread
+//     stay in registers (the 80-register form spilled 110 loads/stores per frame to local memory);
+//   * the real unpack works on bin pairs (k, 1024 - k): X[k] = E + T, X[1024 - k] = conj(E - T) share E and
+//     T = W^k O, which halves the unpack arithmetic and the twiddle table (k <= 512).
+// A thread owns bins gt + 64 c (c = 0..7) and their mirrors 1024 - (gt + 64 c); the mirror of bin 0 would be the
+// Nyquist bin, which the magnitude spectrum does not hold (AudioMath.cpp:497-504), so that slot takes bin 512.
+#define SCH 4               // frame slots per claim
+
+template <int NG>
+struct SpecSmem {
+  static constexpr int BUF = AFX_NBIN + AFX_NBIN / 16;                 // double2 per group
+  static constexpr size_t o_t2 = (size_t)NG * BUF * sizeof(double2);  // [15][16]
+  static constexpr size_t o_t3 = o_t2 + 240 * sizeof(double2);        // [3][256]
+  static constexpr size_t o_tw = o_t3 + 768 * sizeof(double2);        // exp(-2 pi i k / 2048), k = 0..512 (padded to 528)
+  static constexpr size_t o_win = o_tw + 528 * sizeof(double2);       // [2048] Hann * 2
+  static constexpr size_t o_xch = o_win + AFX_NFFT * sizeof(double);  // [NG][24] reduction scratch
+  static constexpr size_t o_claim = o_xch + (size_t)NG * 24 * sizeof(double);   // [NG][2] claimed slot (double buffered)
+  static constexpr size_t bytes = o_claim + (size_t)NG * 2 * sizeof(int);
+};
+
+template <int NG>
+__global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParams P, unsigned features, unsigned int* __restrict__ work_ctr)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using L = SpecSmem<NG>;
+  const int g = threadIdx.x / SG, gt = threadIdx.x % SG, lane = gt & 31, gw = gt >> 5;
+  double2* buf = reinterpret_cast<double2*>(smem_raw) + g * L::BUF;   // FFT buffer, later mag[1024]
+  double2* s_t2 = reinterpret_cast<double2*>(smem_raw + L::o_t2);
+  double2* s_t3 = reinterpret_cast<double2*>(smem_raw + L::o_t3);
+  double2* s_tw = reinterpret_cast<double2*>(smem_raw + L::o_tw);
+  double2* s_win2 = reinterpret_cast<double2*>(smem_raw + L::o_win);
+  double* xch = reinterpret_cast<double*>(smem_raw + L::o_xch) + g * 24;
+  volatile int* claim = reinterpret_cast<int*>(smem_raw + L::o_claim) + g * 2;
+
+  for (int i = threadIdx.x; i < 240; i += SG * NG) s_t2[i] = __ldg(P.t.fft_t2 + i);
+  for (int i = threadIdx.x; i < 768; i += SG * NG) s_t3[i] = __ldg(P.t.fft_t3_1024 + i);
+  for (int i = threadIdx.x; i <= 512; i += SG * NG) s_tw[i] = __ldg(P.t.tw2048 + i);
+  for (int i = threadIdx.x; i < AFX_NBIN; i += SG * NG) s_win2[i] = __ldg(reinterpret_cast<const double2*>(P.t.window) + i);
+  __syncthreads();
+
+  const int TF = B.TF;
+  FftSyncNamed<SG> sync{ 1 + g };
+  for (int it = 0;; ++it) {
+    if (gt == 0) claim[it & 1] = (int)atomicAdd(work_ctr, (unsigned)SCH);
+    sync();
+    const int rel0 = claim[it & 1];
+    if (rel0 >= B.g_slots) break;                      // group-uniform
+    const int rel1 = min(rel0 + SCH, B.g_slots);
+    for (int rel = rel0; rel < rel1; ++rel) {
+  const int slot = B.slot0 + rel;
+  const int fi = B.slot_file[slot];
+  const AfxFile* __restrict__ fp = B.files + fi;
+  const AfxState st = B.state[fi];
+  const int t = slot - fp->frame_off;
+  if (fp->status != 0 || t >= st.F) continue;
+  const int n0 = t * P.H;
+  const float* __restrict__ mono = B.mono + fp->mono_off;
+
+  // ---- amplitude features of the hop slice (SA.cpp:865-873): H / 64 consecutive samples per thread --------
+  if (features & AFX_FEAT_AMPLITUDE) {
+    const int per = P.H / SG;                         // 4, 8, 16 or 32 (hop is a multiple of 256)
+    const double c = P.env_coef;
+    // one-pole envelope (Envelopes.inl:14-18) as a scan of affine maps s -> A s + Bv
+    double A = 1.0, Bv = 0.0, e_hop = 0.0, pk_hop = 0.0;
+    for (int q = 0; q < per; ++q) {
+      const double xv = mdata(mono, st, n0 + gt * per + q), a = fabs(xv);
+      e_hop += xv * xv; pk_hop = fmax(pk_hop, a);
+      Bv = a + c * (Bv - a);
+      A *= c;
+    }
+    double sA = A, sB = Bv;                           // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double pA = __shfl_up_sync(0xffffffffu, sA, o), pB = __shfl_up_sync(0xffffffffu, sB, o);
+      if (lane >= o) { sB = sA * pB + sB; sA = sA * pA; }
+    }
+    if (lane == 31 && gw == 0) { xch[4] = sA; xch[5] = sB; }
+    double ev[1] = { e_hop };
+    group_sum<1>(ev, xch, gt, sync);                  // also publishes xch[4..5] (first barrier inside)
+    double s_in = (gw == 1) ? xch[5] : 0.0;           // state entering the second warp = first warp's map applied to 0
+    const double pA = __shfl_up_sync(0xffffffffu, sA, 1), pB = __shfl_up_sync(0xffffffffu, sB, 1);
+    if (lane > 0) s_in = pA * s_in + pB;
+    double env = s_in, emax = 0.0;
+    for (int q = 0; q < per; ++q) { const double a = fabs(mdata(mono, st, n0 + gt * per + q)); env = a + c * (env - a); emax = fmax(emax, env); }
+    const double pk = group_max(pk_hop, xch, gt, sync);
+    emax = group_max(emax, xch, gt, sync);
+    if (gt == 0) {
+      const double level = ev[0] / (double)P.H;
+      B.fs[(size_t)FS_AMP_SILENCE * TF + slot] = (level < AFX_SILENCE_LEVEL) ? 1.0 : 0.0;   // mathutils.c:606-615
+      B.fs[(size_t)FS_AMP_PEAK * TF + slot] = pk;
+      const double r = sqrt(level);
+      B.fs[(size_t)FS_AMP_RMS * TF + slot] = (r != r) ? 0.0 : r;
+      B.fs[(size_t)FS_AMP_ENV * TF + slot] = emax;
+    }
+  }
+
+  // ---- load, window, pack (even -> re, odd -> im) in the FFT's strided order; transform ---------------------
+  double2 v[16];
+  {
+    const int j0 = n0 - st.start_off;                 // frame start relative to the first audible sample
+    const float* __restrict__ src = mono + st.lead + j0;
+    if (j0 >= 0 && j0 + AFX_NFFT <= st.audible) {     // whole frame inside the audible span (the common case)
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int m = gt + SG * r;
+        const double2 w = s_win2[m];
+        v[r] = make_double2(((double)__ldg(src + 2 * m) * st.fs) * w.x, ((double)__ldg(src + 2 * m + 1) * st.fs) * w.y);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int m = gt + SG * r;
+        const double2 w = s_win2[m];
+        v[r] = make_double2(mdata(mono, st, n0 + 2 * m) * w.x, mdata(mono, st, n0 + 2 * m + 1) * w.y);
+      }
+    }
+  }
+  fft16_run<AFX_NBIN, FftSyncNamed<SG>, true>(v, buf, FftTw{ s_t2, s_t3 }, gt, sync);
+
+  // ---- real unpack on bin pairs + magnitude / N (Fourier.cpp:266-271, AudioMath.cpp:497-504) ----------------
+  // with Zk = Z[k], Zc = conj(Z[1024 - k]):  2 E = Zk + Zc,  2 O = (Zk - Zc) / i,  2 X[k] = 2E + W^k 2O,
+  // 2 X[1024 - k] = conj(2E - W^k 2O); the halves are folded into the final scale
+  double m16[16];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int k = gt + SG * c;
+    const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((AFX_NBIN - k) & (AFX_NBIN - 1))];
+    const double2 E = make_double2(zk.x + zc.x, zk.y - zc.y);
+    const double2 O = make_double2(zk.y + zc.y, zc.x - zk.x);
+    const double2 T = f_mul(s_tw[k], O);
+    const double2 Xa = f_add(E, T), Xb = f_sub(E, T);
+    m16[c] = sqrt(Xa.x * Xa.x + Xa.y * Xa.y) * (0.5 / AFX_NFFT);
+    m16[8 + c] = sqrt(Xb.x * Xb.x + Xb.y * Xb.y) * (0.5 / AFX_NFFT);
+  }
+  if (gt == 0) { const double2 z = buf[FFT_PHYS(AFX_NBIN / 2)]; m16[8] = sqrt(z.x * z.x + z.y * z.y) * (1.0 / AFX_NFFT); }
+  const int kmir0 = (gt == 0) ? AFX_NBIN / 2 : AFX_NBIN - gt;          // bin held by m16[8]
+  double* gmag = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
+  sync();                                            // everyone has read Z before buf becomes the magnitude array
+  double* mag = reinterpret_cast<double*>(buf);
+  double acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };        // S1, S2, S3, S4, SJ, log-sum over the analysis window; full-band S, SJ
+  {
+    const double dgt = (double)gt;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int k = gt + SG * c, km = (c == 0) ? kmir0 : AFX_NBIN - k;
+      const double dk = dgt + (double)(SG * c), dkm = (c == 0) ? (double)kmir0 : (double)AFX_NBIN - dk;
+      mag[k] = m16[c]; gmag[k] = m16[c];
+      mag[km] = m16[8 + c]; gmag[km] = m16[8 + c];
+      acc[6] += m16[c] + m16[8 + c];
+      acc[7] = fma(dk, m16[c], fma(dkm, m16[8 + c], acc[7]));
+    }
+  }
+  sync();                                            // mag[] is complete
+
+  // ---- one pass over the analysis window (bins first_bin .. first_bin + nbins - 1, nbins <= 768): thread gt owns
+  // window bins j = gt + 64 c for the power sums and the 12 consecutive bins 12 gt .. 12 gt + 11 for the rolloff --------
+  const int nb = P.nbins, fb = P.first_bin;
+  const double dj0 = (double)gt;
+  double mj[12], m12[12], loc = 0.0;
+#pragma unroll
+  for (int c = 0; c < 12; ++c) mj[c] = (gt + SG * c < nb) ? mag[fb + gt + SG * c] : 0.0;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) { m12[q] = (12 * gt + q < nb) ? mag[fb + 12 * gt + q] : 0.0; loc += m12[q]; }
+  {
+    double mant = 1.0; int ex = 0;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) {
+      const double m = mj[c], m2 = m * m, jm = (dj0 + (double)(SG * c)) * m;
+      acc[0] += m; acc[1] += m2; acc[2] = fma(m2, m, acc[2]); acc[3] = fma(m2, m2, acc[3]); acc[4] += jm;
+      if (gt + SG * c < nb) mul_frexp_pos(mant, ex, fabs(m) + 1e-20);         // Statistics.cpp:417-455
+    }
+    acc[5] = log(mant) + (double)ex * 0.693147180559945309417;
+  }
+  double inc = loc;                                  // rolloff: inclusive scan of the 12-bin sums inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const double pv = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += pv; }
+  if (lane == 31 && gw == 0) xch[18] = inc;          // published by group_sum's first barrier
+  group_sum<8>(acc, xch, gt, sync);
+  const double S1 = acc[0];
+  const double cen = (S1 == 0.0) ? 0.0 : acc[4] / S1;                          // Statistics.cpp:459-477
+  double sp[1] = { 0.0 };
+#pragma unroll
+  for (int c = 0; c < 12; ++c) { const double d = (dj0 + (double)(SG * c)) - cen; sp[0] = fma(d * d, mj[c], sp[0]); }
+  {
+    // rolloff (LibXtract scalar.c:472-493): count of prefixes below 85 % of the total
+    const double pivot = S1 * (85.0 / 100.0);
+    double pre = ((gw == 1) ? xch[18] : 0.0) + inc - loc;     // exclusive prefix = sum of the window bins before 12 gt
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) if (12 * gt + q < nb) { cnt += (pre < pivot) ? 1 : 0; pre += m12[q]; }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) reinterpret_cast<int*>(xch + 19)[gw] = cnt;                // published by the next group_sum
+  }
+  group_sum<1>(sp, xch, gt, sync);
+  if (gt == 0) {
+    const int* ix = reinterpret_cast<const int*>(xch + 19);
+    const double n = (double)nb;
+    B.fs[(size_t)FS_SPEC_ROLLOFF * TF + slot] = (double)(ix[0] + ix[1]) * (double)(P.sr / (P.N / 2));   // SA.cpp:1892: 44100 / 1024 = 43
+    const double spread = (S1 == 0.0) ? 0.0 : sp[0] / S1;                      // Statistics.cpp:486-506
+    // skewness / kurtosis (Statistics.cpp:510-554): (1/n) sum ((m_j - cen) / spread)^p from the power sums S1..S4
+    // (binomial expansion; the terms cannot cancel to nothing because cen >= 1 > m_j except for spectra
+    // concentrated in the first two window bins, where all other bins contribute -cen each)
+    const bool have_sk = fabs(spread) > (double)1e-12f;
+    const double S2 = acc[1], S3 = acc[2], S4 = acc[3];
+    const double c2 = cen * cen, c3 = c2 * cen, c4 = c2 * c2;
+    const double mu3 = ((S3 - 3.0 * cen * S2) + 3.0 * c2 * S1) - n * c3;
+    const double mu4 = (((S4 - 4.0 * cen * S3) + 6.0 * c2 * S2) - 4.0 * c3 * S1) + n * c4;
+    const double s2 = spread * spread;
+    const double rms = sqrt(S2 / n);
+    B.fs[(size_t)FS_SPEC_RMS * TF + slot] = (rms != rms) ? 0.0 : rms;
+    B.fs[(size_t)FS_SPEC_CENTROID * TF + slot] = cen;
+    B.fs[(size_t)FS_SPEC_SPREAD * TF + slot] = spread;
+    B.fs[(size_t)FS_SPEC_SKEW * TF + slot] = have_sk ? mu3 / (s2 * spread) / n : 0.0;
+    B.fs[(size_t)FS_SPEC_KURT * TF + slot] = have_sk ? mu4 / (s2 * s2) / n - 3.0 : 0.0;
+    const double mean = S1 / n, gmean = exp(acc[5] / n);
+    const double fl = flatness_db(mean, gmean);
+    B.fs[(size_t)FS_SPEC_FLATNESS * TF + slot] = (fl != fl) ? 0.0 : fl;
+    B.cent_full[slot] = (acc[6] == 0.0) ? 0.0 : acc[7] / acc[6];
+    // degenerate in the reference (see oracle/afec_oracle.c, "harmonic spectrum"): always 0
+    B.fs[(size_t)FS_SPEC_INHARM * TF + slot] = 0.0;
+    B.fs[(size_t)FS_TRISTIM1 * TF + slot] = 0.0;
+    B.fs[(size_t)FS_TRISTIM2 * TF + slot] = 0.0;
+    B.fs[(size_t)FS_TRISTIM3 * TF + slot] = 0.0;
+  }
+  // no barrier here: the next frame's first shared-memory writes (xch[0..1, 4..5], the FFT buffer) touch nothing
+  // that is still read after the last group_sum (only xch[19], by thread 0)
+    }
+  }
+}
+
 // spectral flux = Pearson correlation with the previous frame's spectrum (first frame: itself),
 // Statistics.cpp:578-638, SA.cpp:936-940, 1919-1933.  One warp per frame, 8 frames per CTA.
 __global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P)
@@ -236,12 +474,34 @@ __global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P)
   }
 }
 
+template <int NG>
+static void launch_spectrum_p(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, int sms)
+{
+  const int smem = (int)SpecSmem<NG>::bytes;
+  cudaFuncSetAttribute(k_spectrum<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device, see afx_pitch.cu
+  const int groups_needed = (B.g_slots + SCH - 1) / SCH;
+  const int grid = std::max(1, std::min(sms, (groups_needed + NG - 1) / NG));
+  cudaMemsetAsync(P.t.work_ctr, 0, sizeof(unsigned int), s);
+  k_spectrum<NG><<<grid, SG * NG, smem, s>>>(B, P, features, P.t.work_ctr);
+}
+
 void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  const int smem = SF * (AFX_NBIN + AFX_NBIN / 16) * (int)sizeof(double2) + SF * 16 * (int)sizeof(double);
-  cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device, see afx_pitch.cu
-  cudaFuncSetAttribute(k_spectrum, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  k_spectrum<<<(B.g_slots + SF - 1) / SF, SG * SF, smem, s>>>(B, P, features); ++*launches;
+  static const int variant = getenv("AFX_SPEC_VARIANT") ? atoi(getenv("AFX_SPEC_VARIANT")) : 10;
+  if (variant == 0) {
+    const int smem = SF * (AFX_NBIN + AFX_NBIN / 16) * (int)sizeof(double2) + SF * 16 * (int)sizeof(double);
+    cudaFuncSetAttribute(k_spectrum_old, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_spectrum_old, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    k_spectrum_old<<<(B.g_slots + SF - 1) / SF, SG * SF, smem, s>>>(B, P, features); ++*launches;
+  } else {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (variant == 8) launch_spectrum_p<8>(P, B, features, s, sms);
+    else if (variant == 9) launch_spectrum_p<9>(P, B, features, s, sms);
+    else launch_spectrum_p<10>(P, B, features, s, sms);
+    ++*launches;
+  }
   k_flux<<<(B.g_slots + 7) / 8, 256, 0, s>>>(B, P); ++*launches;
 }
