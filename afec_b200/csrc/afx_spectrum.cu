@@ -18,6 +18,29 @@
 #define SG 64               // threads per frame
 #define SF 4                // frames per CTA
 
+// sqrt of a squared magnitude to ~2^-44 relative: MUFU.RSQ64H seed (2^-22) + one Newton step.  The full IEEE sqrt
+// costs twice the FP64 instructions and its last 8 bits are far below what the FFT's own rounding leaves intact.
+__device__ __noinline__ double sqrt_slow(double s) { return sqrt(s); }
+__device__ __forceinline__ double sqrt_mag(double s)
+{
+  if (!(s > 0x1p-900)) return sqrt_slow(s);          // zeros / subnormal squares: the seed instruction flushes them
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  const double r = s * y;
+  return fma(fma(-r, r, s), 0.5 * y, r);
+}
+
+// Pearson correlation from the window sums of two spectra (Statistics.cpp:604-638); explicit rounding steps so that
+// both kernels that call it produce the same bits
+__device__ __forceinline__ double flux_from_sums(double S1, double S2, double S1p, double S2p, double S12, double n)
+{
+  const double s1 = __ddiv_rn(S1, n), s2 = __ddiv_rn(S1p, n);
+  const double da = __dsub_rn(S2, __dmul_rn(__dmul_rn(s1, s1), n)), db = __dsub_rn(S2p, __dmul_rn(__dmul_rn(s2, s2), n));
+  const double den2 = __dmul_rn(da, db);
+  const double num = __dsub_rn(S12, __dmul_rn(__dmul_rn(s1, s2), n));
+  return (fabs(den2) > (double)1e-12f) ? __ddiv_rn(num, __dsqrt_rn(den2)) : 0.0;
+}
+
 // sum of K doubles over the 64 threads of a frame group; xch = K * 2 doubles of the group's shared scratch.
 // Two barriers: the scratch is free for reuse on return.
 template <int K, class Sync>
@@ -222,7 +245,7 @@ __global__ void __launch_bounds__(SG * SF, 3) k_spectrum_old(AfxBatchDev B, AfxP
 //     T = W^k O, which halves the unpack arithmetic and the twiddle table (k <= 512).
 // A thread owns bins gt + 64 c (c = 0..7) and their mirrors 1024 - (gt + 64 c); the mirror of bin 0 would be the
 // Nyquist bin, which the magnitude spectrum does not hold (AudioMath.cpp:497-504), so that slot takes bin 512.
-#define SCH 4               // frame slots per claim
+#define SCH 8               // frame slots per claim
 
 template <int NG>
 struct SpecSmem {
@@ -264,6 +287,7 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
     const int rel0 = claim[it & 1];
     if (rel0 >= B.g_slots) break;                      // group-uniform
     const int rel1 = min(rel0 + SCH, B.g_slots);
+    double S1p = 0.0, S2p = 0.0;                       // window sums of the previous frame of this chunk (flux)
     for (int rel = rel0; rel < rel1; ++rel) {
   const int slot = B.slot0 + rel;
   const int fi = B.slot_file[slot];
@@ -347,15 +371,15 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
     const double2 O = make_double2(zk.y + zc.y, zc.x - zk.x);
     const double2 T = f_mul(s_tw[k], O);
     const double2 Xa = f_add(E, T), Xb = f_sub(E, T);
-    m16[c] = sqrt(Xa.x * Xa.x + Xa.y * Xa.y) * (0.5 / AFX_NFFT);
-    m16[8 + c] = sqrt(Xb.x * Xb.x + Xb.y * Xb.y) * (0.5 / AFX_NFFT);
+    m16[c] = sqrt_mag(Xa.x * Xa.x + Xa.y * Xa.y) * (0.5 / AFX_NFFT);
+    m16[8 + c] = sqrt_mag(Xb.x * Xb.x + Xb.y * Xb.y) * (0.5 / AFX_NFFT);
   }
   if (gt == 0) { const double2 z = buf[FFT_PHYS(AFX_NBIN / 2)]; m16[8] = sqrt(z.x * z.x + z.y * z.y) * (1.0 / AFX_NFFT); }
   const int kmir0 = (gt == 0) ? AFX_NBIN / 2 : AFX_NBIN - gt;          // bin held by m16[8]
   double* gmag = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
   sync();                                            // everyone has read Z before buf becomes the magnitude array
   double* mag = reinterpret_cast<double*>(buf);
-  double acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };        // S1, S2, S3, S4, SJ, log-sum over the analysis window; full-band S, SJ
+  double acc[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };     // S1, S2, S3, S4, SJ, log-sum over the analysis window; full-band S, SJ; sum m * m_prev
   {
     const double dgt = (double)gt;
 #pragma unroll
@@ -374,26 +398,35 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
   // window bins j = gt + 64 c for the power sums and the 12 consecutive bins 12 gt .. 12 gt + 11 for the rolloff --------
   const int nb = P.nbins, fb = P.first_bin;
   const double dj0 = (double)gt;
-  double mj[12], m12[12], loc = 0.0;
+  // spectral flux (Statistics.cpp:578-638, SA.cpp:936-940, 1919-1933) = Pearson correlation with the previous
+  // frame's window.  Inside a chunk the previous row is the one this group wrote last iteration (read back through
+  // L2; its S1 / S2 are carried); a file's first frame correlates with itself; the first slot of a chunk is left to
+  // k_flux, which runs after this kernel over those slots only.
+  const bool flux_here = rel > rel0 || t == 0;
+  const bool flux_prev = rel > rel0 && t > 0;
+  double mj[12], pj[12], m12[12], loc = 0.0;
+#pragma unroll
+  for (int c = 0; c < 12; ++c) pj[c] = (flux_prev && gt + SG * c < nb) ? __ldcg(gmag - AFX_NBIN + fb + gt + SG * c) : 0.0;
 #pragma unroll
   for (int c = 0; c < 12; ++c) mj[c] = (gt + SG * c < nb) ? mag[fb + gt + SG * c] : 0.0;
-#pragma unroll
-  for (int q = 0; q < 12; ++q) { m12[q] = (12 * gt + q < nb) ? mag[fb + 12 * gt + q] : 0.0; loc += m12[q]; }
   {
     double mant = 1.0; int ex = 0;
 #pragma unroll
     for (int c = 0; c < 12; ++c) {
       const double m = mj[c], m2 = m * m, jm = (dj0 + (double)(SG * c)) * m;
-      acc[0] += m; acc[1] += m2; acc[2] = fma(m2, m, acc[2]); acc[3] = fma(m2, m2, acc[3]); acc[4] += jm;
+      acc[0] += m; acc[1] = fma(m, m, acc[1]); acc[2] = fma(m2, m, acc[2]); acc[3] = fma(m2, m2, acc[3]); acc[4] += jm;
+      acc[8] = fma(m, pj[c], acc[8]);
       if (gt + SG * c < nb) mul_frexp_pos(mant, ex, fabs(m) + 1e-20);         // Statistics.cpp:417-455
     }
     acc[5] = log(mant) + (double)ex * 0.693147180559945309417;
   }
+#pragma unroll
+  for (int q = 0; q < 12; ++q) { m12[q] = (12 * gt + q < nb) ? mag[fb + 12 * gt + q] : 0.0; loc += m12[q]; }
   double inc = loc;                                  // rolloff: inclusive scan of the 12-bin sums inside the warp
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const double pv = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += pv; }
   if (lane == 31 && gw == 0) xch[18] = inc;          // published by group_sum's first barrier
-  group_sum<8>(acc, xch, gt, sync);
+  group_sum<9>(acc, xch, gt, sync);
   const double S1 = acc[0];
   const double cen = (S1 == 0.0) ? 0.0 : acc[4] / S1;                          // Statistics.cpp:459-477
   double sp[1] = { 0.0 };
@@ -434,12 +467,15 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
     const double fl = flatness_db(mean, gmean);
     B.fs[(size_t)FS_SPEC_FLATNESS * TF + slot] = (fl != fl) ? 0.0 : fl;
     B.cent_full[slot] = (acc[6] == 0.0) ? 0.0 : acc[7] / acc[6];
+    if (flux_here)
+      B.fs[(size_t)FS_SPEC_FLUX * TF + slot] = flux_from_sums(S1, S2, flux_prev ? S1p : S1, flux_prev ? S2p : S2, flux_prev ? acc[8] : S2, n);
     // degenerate in the reference (see oracle/afec_oracle.c, "harmonic spectrum"): always 0
     B.fs[(size_t)FS_SPEC_INHARM * TF + slot] = 0.0;
     B.fs[(size_t)FS_TRISTIM1 * TF + slot] = 0.0;
     B.fs[(size_t)FS_TRISTIM2 * TF + slot] = 0.0;
     B.fs[(size_t)FS_TRISTIM3 * TF + slot] = 0.0;
   }
+  S1p = S1; S2p = acc[1];
   // no barrier here: the next frame's first shared-memory writes (xch[0..1, 4..5], the FFT buffer) touch nothing
   // that is still read after the last group_sum (only xch[19], by thread 0)
     }
@@ -447,31 +483,44 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
 }
 
 // spectral flux = Pearson correlation with the previous frame's spectrum (first frame: itself),
-// Statistics.cpp:578-638, SA.cpp:936-940, 1919-1933.  One warp per frame, 8 frames per CTA.
-__global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P)
+// Statistics.cpp:578-638, SA.cpp:936-940, 1919-1933.  64 threads per frame, 4 frames per CTA, with the summation
+// order of k_spectrum's fused flux (window bin j = gt + 64 c in c order, xor butterfly, warp 0 + warp 1), so a frame's
+// flux does not depend on which of the two kernels produced it.
+// `stride`: 1 = every slot; SCH = only the first slot of every chunk of the persistent k_spectrum (the others got
+// their flux there).
+__global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P, int stride)
 {
-  const int lane = threadIdx.x & 31;
-  const int slot = B.slot0 + blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (slot >= B.slot0 + B.g_slots) return;
-  const int fi = B.slot_file[slot];
-  const AfxFile f = B.files[fi];
-  const int t = slot - f.frame_off;
-  if (f.status != 0 || t >= B.state[fi].F) return;
-  const double* a = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN + P.first_bin;
-  const double* b = (t > 0) ? a - AFX_NBIN : a;
-  double s1 = 0, s2 = 0, s11 = 0, s12 = 0, s22 = 0;
-  for (int j = lane; j < P.nbins; j += 32) {
-    const double x = a[j], y = b[j];
-    s12 += x * y; s1 += x; s11 += x * x; s2 += y; s22 += y * y;
+  __shared__ double xs[4][5][2];
+  const int g = threadIdx.x >> 6, gt = threadIdx.x & 63, lane = gt & 31, gw = gt >> 5;
+  const int slot = B.slot0 + (blockIdx.x * 4 + g) * stride;
+  bool live = slot < B.slot0 + B.g_slots;
+  int t = 0;
+  if (live) {
+    const int fi = B.slot_file[slot];
+    t = slot - B.files[fi].frame_off;
+    live = B.files[fi].status == 0 && t < B.state[fi].F;
   }
-  s1 = warp_sum(s1); s2 = warp_sum(s2); s11 = warp_sum(s11); s12 = warp_sum(s12); s22 = warp_sum(s22);
+  double v[5] = { 0, 0, 0, 0, 0 };             // S1, S2, S1 prev, S2 prev, S12
+  if (live) {
+    const double* a = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN + P.first_bin;
+    const double* b = (t > 0) ? a - AFX_NBIN : a;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) {
+      const int j = gt + 64 * c;
+      const double x = (j < P.nbins) ? a[j] : 0.0, y = (j < P.nbins) ? b[j] : 0.0;
+      v[0] += x; v[1] = fma(x, x, v[1]); v[2] += y; v[3] = fma(y, y, v[3]); v[4] = fma(x, y, v[4]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) v[k] = warp_sum(v[k]);
   if (lane == 0) {
-    const double n = (double)P.nbins;
-    s1 = s1 / n; s2 = s2 / n;
-    const double den2 = (s11 - s1 * s1 * n) * (s22 - s2 * s2 * n);
-    const double num = s12 - (s1 * s2 * n);
-    B.fs[(size_t)FS_SPEC_FLUX * B.TF + slot] = (fabs(den2) > (double)1e-12f) ? num / sqrt(den2) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) xs[g][k][gw] = v[k];
   }
+  __syncthreads();
+  if (live && gt == 0)
+    B.fs[(size_t)FS_SPEC_FLUX * B.TF + slot] = flux_from_sums(xs[g][0][0] + xs[g][0][1], xs[g][1][0] + xs[g][1][1], xs[g][2][0] + xs[g][2][1],
+                                                              xs[g][3][0] + xs[g][3][1], xs[g][4][0] + xs[g][4][1], (double)P.nbins);
 }
 
 template <int NG>
@@ -503,5 +552,6 @@ void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned feat
     else launch_spectrum_p<10>(P, B, features, s, sms);
     ++*launches;
   }
-  k_flux<<<(B.g_slots + 7) / 8, 256, 0, s>>>(B, P); ++*launches;
+  const int stride = (variant == 0) ? 1 : SCH, nflux = (B.g_slots + stride - 1) / stride;
+  k_flux<<<(nflux + 3) / 4, 256, 0, s>>>(B, P, stride); ++*launches;
 }
