@@ -304,7 +304,7 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   std::vector<float> imp;
   const double pi = 3.14159265358979323846;
   for (int n = 0; n < N; ++n) window[n] = (0.5 * (1.0 - std::cos(2.0 * pi * (double)n / (double)(N - 1)))) * 2.0;   // window.c:67-76, SA.cpp:178-181
-  for (int i = 0; i < AFX_RFFT; ++i) rwindow[i] = 0.5 * (1.0 - std::cos(6.2831853071795864769252867665590 * (double)i * (1.0 / (double)(AFX_RFFT - 1))));  // Fourier.cpp:545-551
+  for (int i = 0; i < AFX_RFFT; ++i) rwindow[i] = 0.5 * (0.5 * (1.0 - std::cos(6.2831853071795864769252867665590 * (double)i * (1.0 / (double)(AFX_RFFT - 1)))));  // Fourier.cpp:545-551, pre-halved (exact): k_rhythm_polar's pair unpack yields 2 X[k]
   build_mel(mel, N / 2, sr / 2, 20.0, 15500.0, 14);
   for (int q = 0; q < 14; ++q) {
     int lo = N / 2, hi = -1;

@@ -87,7 +87,7 @@ struct AfxTables {          // per-context constant tables in device memory
   const double2* fft_t2;        // [15][16]  exp(-2 pi i r k / 256),  r = 1..15
   const double2* fft_t3_1024;   // [3][256]  exp(-2 pi i r j / 1024), r = 1..3
   const double2* fft_t3_2048;   // [7][256]  exp(-2 pi i r j / 2048), r = 1..7
-  const double* rwindow;    // [512] rhythm Hann
+  const double* rwindow;    // [512] rhythm Hann x 0.5 (see k_rhythm_polar)
   const double* mel;        // [14][1024]
   const double* dct;        // [14][14] cos(pi n/14 (m+0.5)), row n
   const float* rs_imp;      // [69632] resampler wing

@@ -39,32 +39,62 @@ __device__ __forceinline__ float phase_rewrap(float p)
 }
 
 // atan2 for the float32 phase column.  The reference computes atan2 in double and rounds to float
-// (OnsetDetector.cpp:136-155); the result only has to be right to well below a float ulp (2.4e-7 at pi), so one
-// division, an octant reduction to |w| <= tan(pi/8) and the Taylor series through w^21 (error < 7e-11) replace
-// libdevice's fully rounded double atan2 -- a third of its FP64 work.
+// (OnsetDetector.cpp:136-155); the result only has to be right to well below a float ulp (2.4e-7 at pi), so an
+// octant reduction to |w| <= tan(pi/8), one reciprocal-seeded division (MUFU.RCP64H + two Newton steps on the
+// quotient, ~1e-15) and the Taylor series through w^21 (error < 7e-11) replace libdevice's fully rounded double
+// atan2 -- a quarter of its FP64 work.  The FP64 constants sit in constant memory: as literals every use costs
+// two UMOVs, and this kernel is issue bound.
+__constant__ double c_at[16] = { -1.0 / 21.0, 1.0 / 19.0, -1.0 / 17.0, 1.0 / 15.0, -1.0 / 13.0, 1.0 / 11.0, -1.0 / 9.0, 1.0 / 7.0,
+                                 -1.0 / 5.0, 1.0 / 3.0, 0.41421356237309503, 0.78539816339744830962, 1.57079632679489661923,
+                                 3.14159265358979323846, 1.0, 0.5 };
 __device__ __forceinline__ double atan2_phase(double y, double x)
 {
   const double ax = fabs(x), ay = fabs(y);
-  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
-  if (mx == 0.0) return 0.0;
-  const bool hi = mn > 0.41421356237309503 * mx;           // beyond pi/8: atan(z) = pi/4 + atan((z - 1) / (z + 1))
-  const double w = (hi ? mn - mx : mn) / (hi ? mn + mx : mx);
+  const bool sw = ay > ax;
+  const double mx = sw ? ay : ax, mn = sw ? ax : ay;
+  const bool hi = mn > c_at[10] * mx;                       // beyond pi/8: atan(z) = pi/4 + atan((z - 1) / (z + 1))
+  const double num = hi ? mn - mx : mn;
+  double den = hi ? mn + mx : mx;
+  den = (mx == 0.0) ? c_at[14] : den;                       // atan2(0, 0) = 0: num is 0 there
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));   // den is 0 or far above the subnormals (float32 samples)
+  r = fma(fma(-den, r, c_at[14]), r, r);
+  const double q = num * r;
+  const double w = fma(fma(-den, q, num), r, q);
   const double w2 = w * w;
-  double p = -1.0 / 21.0;
-  p = fma(p, w2, 1.0 / 19.0); p = fma(p, w2, -1.0 / 17.0); p = fma(p, w2, 1.0 / 15.0); p = fma(p, w2, -1.0 / 13.0);
-  p = fma(p, w2, 1.0 / 11.0); p = fma(p, w2, -1.0 / 9.0); p = fma(p, w2, 1.0 / 7.0); p = fma(p, w2, -1.0 / 5.0);
-  p = fma(p, w2, 1.0 / 3.0);
-  double r = fma(-(p * w2), w, w);                          // w - w^3 / 3 + ...
-  if (hi) r += 0.78539816339744830962;
-  if (ay > ax) r = 1.57079632679489661923 - r;
-  if (x < 0.0) r = 3.14159265358979323846 - r;
-  return (y < 0.0) ? -r : r;
+  double p = c_at[0];
+#pragma unroll
+  for (int i = 1; i < 10; ++i) p = fma(p, w2, c_at[i]);
+  r = fma(-(p * w2), w, w);                                 // w - w^3 / 3 + ...
+  if (hi) r += c_at[11];
+  if (sw) r = c_at[12] - r;
+  if (x < 0.0) r = c_at[13] - r;
+  return __hiloint2double(__double2hiint(r) | (__double2hiint(y) & 0x80000000), __double2loint(r));   // copysign(r, y), r >= 0
+}
+// sqrt of a squared magnitude to ~2^-44 relative (MUFU.RSQ64H seed + one Newton step); the result is rounded to float.
+// s is exactly 0 or far above the subnormals (squares of sums of float32 samples)
+__device__ __forceinline__ double sqrt_mag_r(double s)
+{
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  y = (s > 0.0) ? y : 0.0;
+  const double r = s * y;
+  return fma(fma(-r, r, s), c_at[15] * y, r);
 }
 
 // -------------------------------------------------------------------------------------------------
-// 16 threads per rhythm frame (256-point packed transform = radix 16 x 16 in registers), two frames per warp
+// 16 threads per rhythm frame (256-point packed transform = radix 16 x 16 in registers), two frames per warp.
+// The real unpack works on bin pairs (k, 256 - k):  2 X[k] = E + T,  2 X[256 - k] = conj(E - T)  with
+// E = Z[k] + conj(Z[256 - k]),  T = W^k (Z[k] - conj(Z[256 - k])) / i;  the window table is pre-halved so that E + T
+// is X[k] itself.  The mirror of bin 0 is the Nyquist bin, which the polar row does not hold (quirk,
+// OnsetDetector.cpp:136-155), so that slot takes bin 128.
 #define PF 8                // frames per CTA (4 warps)
-__global__ void __launch_bounds__(PF * 16) k_rhythm_polar(AfxBatchDev B, AfxParams P)
+__device__ __forceinline__ void polar_store(float* __restrict__ row, int k, double2 X)
+{
+  row[k] = (float)sqrt_mag_r(fma(X.x, X.x, X.y * X.y));                           // OnsetDetector.cpp:136-155
+  row[256 + k] = (float)atan2_phase(X.y, X.x);
+}
+__global__ void __launch_bounds__(PF * 16, 5) k_rhythm_polar(AfxBatchDev B, AfxParams P)
 {
   __shared__ double2 sbuf[PF][256 + 16];
   const int h = threadIdx.x >> 4, ht = threadIdx.x & 15;
@@ -73,38 +103,54 @@ __global__ void __launch_bounds__(PF * 16) k_rhythm_polar(AfxBatchDev B, AfxPara
   const bool in_range = rel < B.g_rslots;
   const int slot = B.rslot0 + (in_range ? rel : 0);
   const int fi = B.rslot_file[slot];
-  const AfxFile f = B.files[fi];
-  const int t = slot - f.rframe_off;
+  const AfxFile* __restrict__ fp = B.files + fi;
+  const int t = slot - fp->rframe_off;
   const AfxState st = B.state[fi];
-  const bool live = in_range && f.status == 0 && t < st.Fr;   // both halves of a warp run the transform (warp-wide sync)
-  const float* __restrict__ mono = B.mono + f.mono_off;
+  const bool live = in_range && fp->status == 0 && t < st.Fr;   // both halves of a warp run the transform (warp-wide sync)
+  const float* __restrict__ mono = B.mono + fp->mono_off;
   const double2* __restrict__ win2 = reinterpret_cast<const double2*>(P.t.rwindow);
   const int n0 = t * AFX_RHOP;
   double2 v[16];
+  {
+    const int j0 = n0 - st.start_off;                 // frame start relative to the first audible sample
+    const float* __restrict__ src = mono + st.lead + j0;
+    if (live && j0 >= 0 && j0 + AFX_RFFT <= st.audible) {     // whole frame inside the audible span (the common case)
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int m = ht + 16 * r;
-    const double2 w = __ldg(win2 + m);
-    const double x0 = live ? mdata(mono, st, n0 + 2 * m) : 0.0, x1 = live ? mdata(mono, st, n0 + 2 * m + 1) : 0.0;
-    v[r] = make_double2(w.x * x0, w.y * x1);                                        // OnsetDetector.cpp:119-120
+      for (int r = 0; r < 16; ++r) {
+        const int m = ht + 16 * r;
+        const double2 w = __ldg(win2 + m);
+        v[r] = make_double2(w.x * ((double)__ldg(src + 2 * m) * st.fs), w.y * ((double)__ldg(src + 2 * m + 1) * st.fs));   // OnsetDetector.cpp:119-120
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int m = ht + 16 * r;
+        const double2 w = __ldg(win2 + m);
+        const double x0 = live ? mdata(mono, st, n0 + 2 * m) : 0.0, x1 = live ? mdata(mono, st, n0 + 2 * m + 1) : 0.0;
+        v[r] = make_double2(w.x * x0, w.y * x1);
+      }
+    }
   }
   fft16_run<256>(v, buf, FftTw{ P.t.fft_t2, nullptr }, ht, FftSyncWarp());
   if (!live) return;
   float* row = B.rpolar + (size_t)rel * AFX_RROW;
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const int k = ht + 16 * c;
+  for (int c = 0; c < 8; ++c) {
+    const int k = ht + 16 * c;                               // 0..127, mirror 256 - k
     const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((256 - k) & 255)];
-    const double2 zm = make_double2(zc.x, -zc.y);
-    const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y + zm.y));
-    const double2 D = make_double2(0.5 * (zk.x - zm.x), 0.5 * (zk.y - zm.y));
-    const double2 O = make_double2(D.y, -D.x);
-    double2 X = f_add(E, f_mul(__ldg(P.t.tw512 + k), O));
-    if (k == 0) { X.y = 0.0; row[255] = (float)X.x; }                             // mDC, OnsetDetector.cpp:146
-    if (k < AFX_RBINS) {
-      row[k] = (float)sqrt(X.x * X.x + X.y * X.y);                                // :136-155
-      row[256 + k] = (float)atan2_phase(X.y, X.x);
+    const double2 E = make_double2(zk.x + zc.x, zk.y - zc.y);
+    const double2 O = make_double2(zk.y + zc.y, zc.x - zk.x);
+    const double2 T = f_mul(__ldg(P.t.tw512 + k), O);
+    double2 Xa = f_add(E, T);
+    double2 Xb = make_double2(E.x - T.x, T.y - E.y);        // conj(E - T)
+    int kb = 256 - k;
+    if (c == 0 && ht == 0) {
+      Xa.y = 0.0; row[255] = (float)Xa.x;                    // mDC, OnsetDetector.cpp:146
+      const double2 z = buf[FFT_PHYS(128)];
+      Xb = make_double2(2.0 * z.x, -2.0 * z.y); kb = 128;
     }
+    if (kb < AFX_RBINS) polar_store(row, kb, Xb);
+    polar_store(row, k, Xa);
   }
 }
 
