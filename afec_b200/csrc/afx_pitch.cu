@@ -12,175 +12,276 @@
 //   f0 = 0 when the 2048-sample level is below -48 dB; confidence = clip((1 - yin'[(uint)period]) / 0.25).
 //   failsafe_f0 = f0 if f0 > 0 and confidence > 0.2, else sr/N * centroid(mag[0..1023]) for audible hops.
 //
-// One CTA of 128 threads per frame.  The zero-padded first half a and the full frame b are transformed
+// 128 threads per frame.  The zero-padded first half a and the full frame b are transformed
 // together as z = a + i b by ONE 2048-point complex FFT (register-blocked radix 16 x 16 x 8, afx_fft16.cuh),
 // split into A and B, and conj(conj(A) B) goes through the same forward transform (r = Re FFT(conj(P)) / N).
-// Shared memory: one padded 2048-point FFT buffer (34 KB), prefix sums of squares (17 KB), yin' (9 KB).
+// Shared memory: one padded 2048-point FFT buffer (34 KB) and yin' (9 KB).  The prefix sums of squares live in the FFT
+// buffer before the first transform: the windowed square sums sq[tau] they are needed for go to the yin array up front.
 #include "afx_fft16.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 #define YT 128
 #define YN 2048
 #define YW 1024
+#define YCH 4               // frame slots per claim
 #define PAD16(i) ((i) + ((i) >> 4))
 #define PAD8(i) ((i) + ((i) >> 3))
 
-// exclusive prefix sum across the block of one double per thread (YT threads); returns prefix, total in *tot
-__device__ __forceinline__ double block_scan_excl(double v, double* scratch, double* tot)
+// Persistent form (see afx_spectrum.cu): one CTA per SM, NG frame groups of 128 threads with a named barrier each,
+// frame slots claimed from a global counter.  The FFT twiddle tables (32 KB) stay in shared memory, and a group
+// PREFETCHES its next frame while it works on the current one: the slot -> file -> state -> samples chain of
+// dependent global loads was 39 % of the stall samples of the one-CTA-per-frame form (ncu, long scoreboard).
+template <int NG>
+struct PitchSmem {
+  static constexpr int BUF = YN + YN / 16;                             // double2 per group
+  static constexpr int YIN = YW + YW / 8 + 8;                          // doubles per group
+  static constexpr size_t group_bytes = (size_t)BUF * sizeof(double2) + (size_t)YIN * sizeof(double) + 40 * sizeof(double);
+  static constexpr size_t o_t2 = (size_t)NG * group_bytes;            // [15][16]
+  static constexpr size_t o_t3 = o_t2 + 240 * sizeof(double2);        // [7][256]
+  static constexpr size_t bytes = o_t3 + 7 * 256 * sizeof(double2);
+};
+
+// exclusive prefix sum over the 128 threads of a group; scratch: 4 doubles
+template <class Sync>
+__device__ __forceinline__ double group_scan_excl(double v, double* scratch, int tid, Sync sync)
 {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = tid & 31, wid = tid >> 5;
   double inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const double p = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += p; }
-  __syncthreads();
+  sync();
   if (lane == 31) scratch[wid] = inc;
-  __syncthreads();
-  double base = 0.0, total = 0.0;
+  sync();
+  double base = 0.0;
 #pragma unroll
-  for (int w = 0; w < (YT >> 5); ++w) { const double s = scratch[w]; if (w < wid) base += s; total += s; }
-  if (tot) *tot = total;
+  for (int w = 0; w < (YT >> 5) - 1; ++w) { const double sv = scratch[w]; if (w < wid) base += sv; }
   return base + inc - v;
 }
 
-__global__ void __launch_bounds__(YT, 3) k_pitch(AfxBatchDev B, AfxParams P)
+struct PitchNext {          // what a group knows about the frame it will work on next
+  int slot;                 // global slot, -1 = none
+  bool live;
+  double fs;
+  float x[16];              // raw mono samples tid + 128 r of the frame (0 outside the audible span)
+};
+
+template <int NG>
+__global__ void __launch_bounds__(YT * NG, 1) k_pitch(AfxBatchDev B, AfxParams P, unsigned int* __restrict__ work_ctr)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* buf = reinterpret_cast<double2*>(smem_raw);                 // [2048 + 128]
-  double* S = reinterpret_cast<double*>(buf + YN + YN / 16);           // [PAD16(2048) + 1] prefix sums of squares
-  double* yin = S + (YN + YN / 16 + 8);                                // [PAD8(1024)]
-  __shared__ double scratch[32];
-  __shared__ int iscr[32];
-
-  const int tid = threadIdx.x;
-  const int slot = B.slot0 + blockIdx.x;
-  const int fi = B.slot_file[slot];
-  const AfxFile f = B.files[fi];
-  const AfxState st = B.state[fi];
-  const int t = slot - f.frame_off;
-  if (f.status != 0 || t >= st.F) return;
-  const int n0 = t * P.H;
-  const float* __restrict__ mono = B.mono + f.mono_off;
-  FftSyncBlock sync;
-
-  // ---- one coalesced pass over the frame: z = a + i b in the FFT's strided order, squares to shared memory ----
-  double2 v[16];
-#pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int m = tid + YT * r;
-    const double xv = mdata(mono, st, n0 + m);
-    v[r] = make_double2(m < YW ? xv : 0.0, xv);
-    S[PAD16(m)] = xv * xv;
-  }
+  using L = PitchSmem<NG>;
+  const int g = threadIdx.x / YT, tid = threadIdx.x % YT;
+  unsigned char* gbase = smem_raw + (size_t)g * L::group_bytes;
+  double2* buf = reinterpret_cast<double2*>(gbase);                    // [2048 + 128]
+  double* S = reinterpret_cast<double*>(buf);                          // [PAD16(2048) + 1] prefix sums of squares (before the FFTs)
+  double* yin = reinterpret_cast<double*>(buf + L::BUF);               // [PAD8(1024)]
+  double* scratch = yin + L::YIN;                                      // [8] scans / argmin
+  double* level = scratch + 8;                                         // [2] sum of squares of the frame / of the hop
+  int* iscr = reinterpret_cast<int*>(scratch + 12);                    // [8] argmin / first dip
+  volatile int* claim = reinterpret_cast<int*>(scratch + 20);          // [2] claimed chunk (double buffered)
+  double2* s_t2 = reinterpret_cast<double2*>(smem_raw + L::o_t2);
+  double2* s_t3 = reinterpret_cast<double2*>(smem_raw + L::o_t3);
+  for (int i = threadIdx.x; i < 240; i += YT * NG) s_t2[i] = __ldg(P.t.fft_t2 + i);
+  for (int i = threadIdx.x; i < 7 * 256; i += YT * NG) s_t3[i] = __ldg(P.t.fft_t3_2048 + i);
   __syncthreads();
-  // ---- prefix sums of squares: 16 consecutive samples per thread (padded -> conflict free) -----------------
-  {
-    double q2[16]; double loc = 0.0;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { q2[q] = S[PAD16(16 * tid + q)]; loc += q2[q]; }
-    double pre = block_scan_excl(loc, scratch, nullptr);      // its first barrier: every square has been read
-    if (tid == 0) S[0] = 0.0;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { pre += q2[q]; S[PAD16(16 * tid + q + 1)] = pre; }
-  }
-  const FftTw ftw = { P.t.fft_t2, P.t.fft_t3_2048 };
-  fft16_run<YN>(v, buf, ftw, tid, sync);
-  // split into A (transform of a) and B (of b), O = conj(conj(A) B); every thread builds its own 16 inputs
-#pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int k = tid + YT * r;
-    const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((YN - k) & (YN - 1))];
-    const double2 zn = make_double2(zc.x, -zc.y);
-    const double2 A = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y + zn.y));
-    const double2 D = make_double2(0.5 * (zk.x - zn.x), 0.5 * (zk.y - zn.y));
-    const double2 Bc = make_double2(D.y, -D.x);                  // D / i
-    const double2 Pk = f_mul(make_double2(A.x, -A.y), Bc);
-    v[r] = make_double2(Pk.x, -Pk.y);
-  }
-  __syncthreads();                                               // all reads of buf done before it is rewritten
-  fft16_run<YN>(v, buf, ftw, tid, sync);
+  FftSyncNamed<YT> sync{ 1 + g };
+  const FftTw ftw = { s_t2, s_t3 };
+  const size_t TF = (size_t)B.TF;
 
-  // ---- difference function (elementwise, tau = tid + 128 c) ------------------------------------------
-  const double sW = S[PAD16(YW)];
+  // metadata + samples of frame slot `rel` (relative to the launch group) into nx
+  auto fetch = [&](int rel, PitchNext& nx) {
+    nx.slot = -1; nx.live = false; nx.fs = 0.0;
+    if (rel < 0 || rel >= B.g_slots) return;
+    const int slot = B.slot0 + rel;
+    nx.slot = slot;
+    const int fi = B.slot_file[slot];
+    const AfxFile* __restrict__ fp = B.files + fi;
+    const AfxState* __restrict__ sp = B.state + fi;
+    const int t = slot - fp->frame_off;
+    if (fp->status != 0 || t >= sp->F) return;
+    nx.live = true; nx.fs = sp->fs;
+    const int j0 = t * P.H - sp->start_off, audible = sp->audible;
+    const float* __restrict__ src = B.mono + fp->mono_off + sp->lead + j0;
 #pragma unroll
-  for (int c = 0; c < YW / YT; ++c) {
-    const int tau = tid + YT * c;
-    const double sq = (S[PAD16(tau + YW)] - S[PAD16(tau)]) + sW;
-    yin[PAD8(tau)] = sq - buf[FFT_PHYS(tau)].x * (1.0 / YN);
-  }
-  __syncthreads();
-  // ---- cumulative-mean normalisation: 8 consecutive tau per thread ---------------------------------------
-  double y[8]; double ysum = 0.0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) { y[q] = yin[PAD8(8 * tid + q)]; if (8 * tid + q >= 1) ysum += y[q]; }
-  double run = block_scan_excl(ysum, scratch, nullptr);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int tau = 8 * tid + q;
-    double vv;
-    if (tau == 0) vv = 1.0;
-    else { run += y[q]; vv = (run != 0.0) ? y[q] * ((double)tau / run) : 1.0; }
-    y[q] = vv;
-    yin[PAD8(tau)] = vv;
-  }
-  __syncthreads();
+    for (int r = 0; r < 16; ++r) {
+      const int m = tid + YT * r, j = j0 + m;
+      nx.x[r] = (j >= 0 && j < audible) ? __ldg(src + m) : 0.0f;
+    }
+  };
 
-  // ---- first dip below the tolerance, else the last global minimum ---------------------------------
-  int cand = 0x7fffffff;
+  int it = 0;
+  if (tid == 0) claim[0] = (int)atomicAdd(work_ctr, (unsigned)YCH);
+  sync();
+  int rel = claim[0], rel_end = rel + YCH;
+  PitchNext cur;
 #pragma unroll
-  for (int q = 7; q >= 0; --q) {
-    const int p = 8 * tid + q;
-    const double nxt = (q < 7) ? y[q + 1] : yin[PAD8(min(p + 1, YW - 1))];
-    if (p >= 2 && p <= YW - 4 && y[q] < 0.75 && y[q] < nxt) cand = p;
-  }
-  cand = block_min_i(cand, iscr);
-  int pos;
-  if (cand != 0x7fffffff) pos = cand;
-  else {
-    // argmin with ties -> last index (mathutils.c:250-258)
+  for (int r = 0; r < 16; ++r) cur.x[r] = 0.0f;
+  fetch(rel, cur);
+  while (rel < B.g_slots) {
+    // the slot after this one: next in the chunk, else the head of a freshly claimed chunk
+    int nrel = rel + 1, nrel_end = rel_end;
+    if (nrel >= rel_end) {
+      ++it;
+      if (tid == 0) claim[it & 1] = (int)atomicAdd(work_ctr, (unsigned)YCH);
+      sync();
+      nrel = claim[it & 1]; nrel_end = nrel + YCH;
+    }
+    if (!cur.live) {                                 // group-uniform
+      fetch(nrel, cur); rel = nrel; rel_end = nrel_end;
+      continue;
+    }
+    const int slot = cur.slot;
+
+    // ---- z = a + i b in the FFT's strided order, squares to shared memory --------------------------------
+    double2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int m = tid + YT * r;
+      const double xv = (double)cur.x[r] * cur.fs;              // mdata(): SA.cpp:712-718
+      v[r] = make_double2(m < YW ? xv : 0.0, xv);
+      S[PAD16(m)] = xv * xv;
+    }
+    sync();
+    // ---- prefix sums of squares: 16 consecutive samples per thread (padded -> conflict free) -----------------
+    {
+      double q2[16]; double loc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { q2[q] = S[PAD16(16 * tid + q)]; loc += q2[q]; }
+      double pre = group_scan_excl(loc, scratch, tid, sync);     // its first barrier: every square has been read
+      if (tid == 0) S[0] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { pre += q2[q]; S[PAD16(16 * tid + q + 1)] = pre; }
+    }
+    sync();
+    // windowed square sums sq[tau] = sum_{j<W} x[j+tau]^2 + sum_{j<W} x[j]^2 -> yin[] (the difference function subtracts r later)
+    {
+      const double sW = S[PAD16(YW)];
+#pragma unroll
+      for (int c = 0; c < YW / YT; ++c) {
+        const int tau = tid + YT * c;
+        yin[PAD8(tau)] = (S[PAD16(tau + YW)] - S[PAD16(tau)]) + sW;
+      }
+      if (tid == 0) { level[0] = S[PAD16(YN)]; level[1] = S[PAD16(P.H)]; }
+    }
+    sync();                                                      // S is dead: the FFT buffer takes its place
+    fft16_run<YN, FftSyncNamed<YT>, true>(v, buf, ftw, tid, sync);
+    // split into A (transform of a) and B (of b), O = conj(conj(A) B); every thread builds its own 16 inputs
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int k = tid + YT * r;
+      const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((YN - k) & (YN - 1))];
+      const double2 zn = make_double2(zc.x, -zc.y);
+      const double2 A = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y + zn.y));
+      const double2 D = make_double2(0.5 * (zk.x - zn.x), 0.5 * (zk.y - zn.y));
+      const double2 Bc = make_double2(D.y, -D.x);                  // D / i
+      const double2 Pk = f_mul(make_double2(A.x, -A.y), Bc);
+      v[r] = make_double2(Pk.x, -Pk.y);
+    }
+    sync();                                                        // all reads of buf done before it is rewritten
+    fft16_run<YN, FftSyncNamed<YT>, true>(v, buf, ftw, tid, sync);
+
+    // ---- the next frame's loads go out now and land while this frame's search runs -------------------------
+    PitchNext nxt;
+    fetch(nrel, nxt);
+
+    // ---- difference function (elementwise, tau = tid + 128 c) ------------------------------------------
+#pragma unroll
+    for (int c = 0; c < YW / YT; ++c) {
+      const int tau = tid + YT * c;
+      yin[PAD8(tau)] = yin[PAD8(tau)] - buf[FFT_PHYS(tau)].x * (1.0 / YN);
+    }
+    sync();
+    // ---- cumulative-mean normalisation: 8 consecutive tau per thread ---------------------------------------
+    double y[8]; double ysum = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { y[q] = yin[PAD8(8 * tid + q)]; if (8 * tid + q >= 1) ysum += y[q]; }
+    double run = group_scan_excl(ysum, scratch, tid, sync);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int tau = 8 * tid + q;
+      double vv;
+      if (tau == 0) vv = 1.0;
+      else { run += y[q]; vv = (run != 0.0) ? y[q] * ((double)tau / run) : 1.0; }
+      y[q] = vv;
+      yin[PAD8(tau)] = vv;
+    }
+    sync();
+
+    // ---- first dip below the tolerance, else the last global minimum ---------------------------------
+    int cand = 0x7fffffff;
+#pragma unroll
+    for (int q = 7; q >= 0; --q) {
+      const int p = 8 * tid + q;
+      const double nx1 = (q < 7) ? y[q + 1] : yin[PAD8(min(p + 1, YW - 1))];
+      if (p >= 2 && p <= YW - 4 && y[q] < 0.75 && y[q] < nx1) cand = p;
+    }
+    // argmin with ties -> last index (mathutils.c:250-258), evaluated alongside: one exchange serves both
     double mv = y[0]; int mi = 8 * tid;
 #pragma unroll
     for (int q = 1; q < 8; ++q) if (!(mv < y[q])) { mv = y[q]; mi = 8 * tid + q; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
+      cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
       const double ov = __shfl_xor_sync(0xffffffffu, mv, o); const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
       if (ov < mv || (ov == mv && oi > mi)) { mv = ov; mi = oi; }
     }
-    __syncthreads();
-    if ((tid & 31) == 0) { scratch[tid >> 5] = mv; iscr[tid >> 5] = mi; }
-    __syncthreads();
-    mv = scratch[0]; mi = iscr[0];
-    for (int w = 1; w < (YT >> 5); ++w) { const double ov = scratch[w]; const int oi = iscr[w]; if (ov < mv || (ov == mv && oi > mi)) { mv = ov; mi = oi; } }
-    pos = mi;
-  }
-  if (tid == 0) {
-    double period;
-    if (pos == 0 || pos == YW - 1) period = (double)pos;          // mathutils.c:494-506
-    else { const double s0 = yin[PAD8(pos - 1)], s1 = yin[PAD8(pos)], s2 = yin[PAD8(pos + 1)]; period = pos + .5 * (s0 - s2) / (s0 - 2. * s1 + s2); }
-    unsigned peak_pos = 0;
-    if (period == period && period >= 0.0 && period < (double)YW) peak_pos = (unsigned)period;
-    double pitch = (period > 0.0) ? (double)P.sr / (period + 0.) : 0.0;                  // pitch.c:450-462
-    const bool silent_frame = (S[PAD16(YN)] / (double)YN) < AFX_SILENCE_LEVEL;         // pitch.c:399-407
-    if (silent_frame) pitch = 0.0;
-    double conf = (1.0 - yin[PAD8(peak_pos)]) / 0.25;                                    // SA.cpp:887-889
-    conf = conf < 0.0 ? 0.0 : (conf > 1.0 ? 1.0 : conf);
-    double fsafe = 0.0;                                                                  // SA.cpp:897-916
-    if (pitch > 0.0 && conf > 0.2) fsafe = pitch;
-    else {
-      const bool silent_hop = (S[PAD16(P.H)] / (double)P.H) < AFX_SILENCE_LEVEL;
-      if (!silent_hop) { const double c = B.cent_full[slot]; fsafe = (double)P.sr / (double)P.N * (c > 0.0 ? c : 0.0); }
+    if ((tid & 31) == 0) { scratch[4 + (tid >> 5)] = mv; iscr[tid >> 5] = mi; iscr[4 + (tid >> 5)] = cand; }
+    sync();
+    if (tid == 0) {
+      int pos;
+      cand = min(min(iscr[4], iscr[5]), min(iscr[6], iscr[7]));
+      if (cand != 0x7fffffff) pos = cand;
+      else {
+        mv = scratch[4]; mi = iscr[0];
+        for (int w = 1; w < (YT >> 5); ++w) { const double ov = scratch[4 + w]; const int oi = iscr[w]; if (ov < mv || (ov == mv && oi > mi)) { mv = ov; mi = oi; } }
+        pos = mi;
+      }
+      double period;
+      if (pos == 0 || pos == YW - 1) period = (double)pos;          // mathutils.c:494-506
+      else { const double s0 = yin[PAD8(pos - 1)], s1 = yin[PAD8(pos)], s2 = yin[PAD8(pos + 1)]; period = pos + .5 * (s0 - s2) / (s0 - 2. * s1 + s2); }
+      unsigned peak_pos = 0;
+      if (period == period && period >= 0.0 && period < (double)YW) peak_pos = (unsigned)period;
+      double pitch = (period > 0.0) ? (double)P.sr / (period + 0.) : 0.0;                  // pitch.c:450-462
+      const bool silent_frame = (level[0] / (double)YN) < AFX_SILENCE_LEVEL;             // pitch.c:399-407
+      if (silent_frame) pitch = 0.0;
+      double conf = (1.0 - yin[PAD8(peak_pos)]) / 0.25;                                    // SA.cpp:887-889
+      conf = conf < 0.0 ? 0.0 : (conf > 1.0 ? 1.0 : conf);
+      double fsafe = 0.0;                                                                  // SA.cpp:897-916
+      if (pitch > 0.0 && conf > 0.2) fsafe = pitch;
+      else {
+        const bool silent_hop = (level[1] / (double)P.H) < AFX_SILENCE_LEVEL;
+        if (!silent_hop) { const double c = B.cent_full[slot]; fsafe = (double)P.sr / (double)P.N * (c > 0.0 ? c : 0.0); }
+      }
+      B.fs[(size_t)FS_F0 * TF + slot] = pitch;
+      B.fs[(size_t)FS_F0_CONF * TF + slot] = conf;
+      B.fs[(size_t)FS_F0_FAILSAFE * TF + slot] = fsafe;
     }
-    const size_t TF = (size_t)B.TF;
-    B.fs[(size_t)FS_F0 * TF + slot] = pitch;
-    B.fs[(size_t)FS_F0_CONF * TF + slot] = conf;
-    B.fs[(size_t)FS_F0_FAILSAFE * TF + slot] = fsafe;
+    sync();                                          // thread 0 is done with yin / level / scratch before the next frame
+    cur = nxt; rel = nrel; rel_end = nrel_end;
   }
+}
+
+template <int NG>
+static void launch_pitch_t(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s)
+{
+  const int smem = (int)PitchSmem<NG>::bytes;
+  // per launch: function attributes are per device, and one process may drive several devices
+  cudaFuncSetAttribute(k_pitch<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int chunks = (B.g_slots + YCH - 1) / YCH;
+  const int grid = std::max(1, std::min(sms, (chunks + NG - 1) / NG));
+  unsigned int* ctr = P.t.work_ctr + 1;
+  cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s);
+  k_pitch<NG><<<grid, YT * NG, smem, s>>>(B, P, ctr);
 }
 
 void afx_launch_pitch(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  const int smem = (YN + YN / 16) * (int)sizeof(double2) + (YN + YN / 16 + 8) * (int)sizeof(double) + (YW + YW / 8 + 8) * (int)sizeof(double);
-  // per launch: function attributes are per device, and one process may drive several devices
-  cudaFuncSetAttribute(k_pitch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_pitch, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  k_pitch<<<B.g_slots, YT, smem, s>>>(B, P); ++*launches;
+  static const int ng = getenv("AFX_PITCH_NG") ? atoi(getenv("AFX_PITCH_NG")) : 3;
+  if (ng == 4) launch_pitch_t<4>(P, B, s); else launch_pitch_t<3>(P, B, s);
+  ++*launches;
 }
