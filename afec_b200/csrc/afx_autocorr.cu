@@ -11,40 +11,57 @@
 // straight from global memory in 32-sample steps (they nearly always stop in the first step); only the
 // 529-sample window goes to shared memory.  The 140k multiply-adds per frame are register tiled: a lane
 // owns 9 consecutive lags and slides a 9-sample window along j, so every pair of shared-memory loads
-// feeds 9 DFMAs (the FP64 pipe, not shared memory, is the limit); lag groups g and G-1-g are paired so
-// that all lanes carry the same number of products.
+// feeds 9 DFMAs (the FP64 pipe, not shared memory, is the limit); see ac_rounds for how the triangle of
+// lag x sample work is spread over the lanes.
 #include "afx_common.cuh"
 
 #define AW 8                // warps (frames) per CTA
 #define AL 9                // lags per lane task
 #define AC_MAXW 544         // >= ac_width (529) + AL, multiple of 8
+#define AC_XS 696           // window + zero padding: a round reads up to width + 75; idle lanes read zeros from AC_ZERO on
+#define AC_ZERO 544
 
-// returns max(R[i]) over the group's lags i with lo <= i < width; the group holding lag 0 also reports R[0]
-__device__ __forceinline__ double ac_group(const double* __restrict__ x, int width, int g, int lo, double& r0)
+// The lag groups g (lags 9g .. 9g+8, width - 9g products each) form a triangle of work.  Four lanes share a group
+// (each takes a quarter of its j range and slides its own 9-sample window) and the warp walks the groups 8 at a
+// time: inside a round every lane runs the same number of steps -- a quarter of the round's longest group, the
+// shorter ones run into the zero padding -- so the warp never waits for one long lane.  88 % of the lane-steps carry
+// products (62 % when a lane owned whole groups).  Returns max(R[i]) over lags lo <= i < width; r0 = R[0].
+__device__ __forceinline__ double ac_rounds(const double* __restrict__ x, int width, int G, int lane, int lo, double& r0)
 {
-  const int i0 = g * AL;
-  const int nj = width - i0;            // products of the group's first lag; later lags read the zero padding
-  double acc[AL], w[AL];
-#pragma unroll
-  for (int q = 0; q < AL; ++q) { acc[q] = 0.0; w[q] = x[i0 + q]; }
-  for (int j = 0; j < nj; ++j) {
-    const double a = x[j];
-#pragma unroll
-    for (int q = 0; q < AL; ++q) acc[q] = fma(a, w[q], acc[q]);
-#pragma unroll
-    for (int q = 0; q < AL - 1; ++q) w[q] = w[q + 1];
-    w[AL - 1] = x[j + i0 + AL];
-  }
-  if (g == 0) r0 = acc[0];
+  const int sub = lane & 3, gl = lane >> 2;
   double best = 0.0;
+  for (int gbase = 0; gbase < G; gbase += 8) {
+    const int g = gbase + gl, i0 = AL * g;
+    const bool act = g < G;
+    const int len = (width - AL * gbase + 3) >> 2;   // uniform across the warp
+    const int j0 = sub * len;
+    const double* __restrict__ xa = x + j0;
+    const double* __restrict__ xw = x + (act ? j0 + i0 : AC_ZERO);
+    double acc[AL], w[AL];
 #pragma unroll
-  for (int q = 0; q < AL; ++q) if (i0 + q < width && i0 + q >= lo) best = fmax(best, acc[q]);
+    for (int q = 0; q < AL; ++q) { acc[q] = 0.0; w[q] = xw[q]; }
+    for (int jj = 0; jj < len; ++jj) {
+      const double a = xa[jj];
+#pragma unroll
+      for (int q = 0; q < AL; ++q) acc[q] = fma(a, w[q], acc[q]);
+#pragma unroll
+      for (int q = 0; q < AL - 1; ++q) w[q] = w[q + 1];
+      w[AL - 1] = xw[jj + AL];
+    }
+#pragma unroll
+    for (int q = 0; q < AL; ++q) {
+      acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 1);
+      acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], 2);
+      if (act && i0 + q < width && i0 + q >= lo) best = fmax(best, acc[q]);
+    }
+    if (gbase == 0) r0 = acc[0];                     // lanes 0..3 hold R[0]
+  }
   return best;
 }
 
 __global__ void __launch_bounds__(AW * 32) k_autocorr(AfxBatchDev B, AfxParams P)
 {
-  __shared__ double xs[AW][AC_MAXW + 2 * AL + 8];
+  __shared__ double xs[AW][AC_XS];
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int rel = blockIdx.x * AW + wid;
@@ -89,17 +106,13 @@ __global__ void __launch_bounds__(AW * 32) k_autocorr(AfxBatchDev B, AfxParams P
 
   const int width = min(remaining, P.ac_width);
   double* x = xs[wid];
-  for (int k = lane; k < AC_MAXW + 2 * AL + 8; k += 32) x[k] = (k < width) ? mdata(mono, st, n0 + start + k) : 0.0;
+  for (int k = lane; k < AC_XS; k += 32) x[k] = (k < width) ? mdata(mono, st, n0 + start + k) : 0.0;
   __syncwarp();
 
   const int G = (width + AL - 1) / AL;             // lag groups; the last one may be partial (zero padded)
   const int lo = period / 2;
-  double r0 = 0.0, best = 0.0;                     // the result is floored at 0 (Autocorrelation.cpp:96-103)
-  for (int g = lane; g < (G + 1) / 2; g += 32) {
-    best = fmax(best, ac_group(x, width, g, lo, r0));
-    const int g2 = G - 1 - g;
-    if (g2 != g) best = fmax(best, ac_group(x, width, g2, lo, r0));
-  }
+  double r0 = 0.0;                                 // the result is floored at 0 (Autocorrelation.cpp:96-103)
+  double best = ac_rounds(x, width, G, lane, lo, r0);
   best = warp_max(best);
   r0 = __shfl_sync(0xffffffffu, r0, 0);            // lane 0 owns group 0
   // normalisation by R[0] > 0 is monotonic, so max_i (R[i] / R[0]) == (max_i R[i]) / R[0] exactly
