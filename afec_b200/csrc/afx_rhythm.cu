@@ -15,8 +15,9 @@
 //                                      [mag 0..254 | dc | phase 0..254] (bins 0..254 + Re[0]; quirk: the
 //                                      "Nyquist" slot of the reference is Im[0] == 0)
 //   k_rhythm_whiten  (thread per file x bin, sequential over frames) adaptive-max whitening, in place
-//   k_rhythm_odf     (warp per frame)  rectified complex-domain and power onset functions from rows
-//                                      t, t-1, t-2; float32 operation order of the reference
+//   k_rhythm_odf     (warp per 8 frames) rectified complex-domain onset function from rows t, t-1, t-2 (carried in
+//                                      registers); k_rhythm_power (thread per frame) the power onset function;
+//                                      float32 operation order of the reference
 //   k_rhythm_median  (warp per frame)  running median of the last 69 ODF values -> post = odf - median
 //   k_rhythm_back    (CTA per file)    min-gap peak picker -> onset series, onset count, Canny
 //                                      sharpening + z-score, peak strength / frequency / contrast, beat
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(PF * 16, 5) k_rhythm_polar(AfxBatchDev B, AfxP
   fft16_run<256>(v, buf, FftTw{ P.t.fft_t2, nullptr }, ht, FftSyncWarp());
   if (!live) return;
   float* row = B.rpolar + (size_t)rel * AFX_RROW;
-#pragma unroll
+#pragma unroll 2                                             // the body holds two inlined atan2 + sqrt: keep the code small
   for (int c = 0; c < 8; ++c) {
     const int k = ht + 16 * c;                               // 0..127, mirror 256 - k
     const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((256 - k) & 255)];
@@ -188,51 +189,82 @@ __global__ void __launch_bounds__(256) k_rhythm_whiten(AfxBatchDev B, AfxParams 
 }
 
 // -------------------------------------------------------------------------------------------------
-// onset functions (OnsetDetector.cpp:371-547): kFunctionRComplex and kFunctionPower
-__global__ void __launch_bounds__(RPW * 32) k_rhythm_odf(AfxBatchDev B, AfxParams P)
+// onset functions (OnsetDetector.cpp:371-547): kFunctionRComplex (k_rhythm_odf) and kFunctionPower (k_rhythm_power).
+// A warp walks OB consecutive rhythm frame slots.  The complex-domain function of frame t needs |mag| of t-1 and the
+// phases of t-1 and t-2: they stay in registers from the previous steps (two warm-up rows in front of the run), so
+// every polar row is read once, unconditionally -- loads of the next rows are in flight while a frame is evaluated.
+#define OB 8                // frames per warp
+#define OW 8                // warps per CTA
+__global__ void __launch_bounds__(OW * 32) k_rhythm_odf(AfxBatchDev B, AfxParams P)
 {
-  __shared__ __align__(16) float smag[RPW][256];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int rel = blockIdx.x * RPW + wid;
+  const int rel0 = (blockIdx.x * OW + wid) * OB;
+  if (rel0 >= B.g_rslots) return;
+  float pm[8], ph1[8], ph2[8];                   // |mag| of the previous row, phases of the previous two rows
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int i = lane + 32 * c;
+    const float* r1 = B.rpolar + (size_t)(rel0 - 1) * AFX_RROW;
+    const float* r2 = B.rpolar + (size_t)(rel0 - 2) * AFX_RROW;
+    pm[c] = (rel0 >= 1) ? fabsf(r1[i]) : 0.0f;
+    ph1[c] = (rel0 >= 1) ? r1[256 + i] : 0.0f;
+    ph2[c] = (rel0 >= 2) ? r2[256 + i] : 0.0f;
+  }
+#pragma unroll 1                                 // one copy of the body: eight were an instruction-cache problem
+  for (int k = 0; k < OB; ++k) {
+    const int rel = rel0 + k;
+    if (rel >= B.g_rslots) break;                // warp-uniform
+    const int slot = B.rslot0 + rel;
+    const int fi = B.rslot_file[slot];
+    const int t = slot - B.files[fi].rframe_off;
+    if (B.files[fi].status != 0 || t >= B.state[fi].Fr) continue;     // warp-uniform; the next live frame has t == 0
+    const float* r0 = B.rpolar + (size_t)rel * AFX_RROW;
+    float m[8], ph[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { m[c] = r0[lane + 32 * c]; ph[c] = r0[256 + lane + 32 * c]; }
+    double total = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int i = lane + 32 * c;
+      const float cur = fabsf(m[c]);
+      const float pmv = (t >= 1) ? pm[c] : 0.0f;
+      if (i < AFX_RBINS && cur > 0.01f && !(cur < pmv)) {
+        const float yp = (t >= 1) ? ph1[c] : 0.0f;
+        const float yp2 = (t >= 2) ? ph2[c] : 0.0f;
+        const float ypd = (t >= 1) ? phase_rewrap(__fsub_rn(yp, yp2)) : 0.0f;
+        const float pred = __fadd_rn(yp, ypd);
+        const float dev = __fsub_rn(pred, ph[c]);
+        const float cs = cosf(phase_rewrap(dev));
+        const float q = __fsub_rn(__fadd_rn(__fmul_rn(pmv, pmv), __fmul_rn(cur, cur)), __fmul_rn(__fmul_rn(pmv, cur), cs));
+        total += (double)sqrtf(q);
+      }
+      pm[c] = cur; ph2[c] = ph1[c]; ph1[c] = ph[c];
+    }
+    total = warp_sum(total);
+    if (lane == 0) B.rodf[slot] = __fmul_rn((float)total, P.r_norm_complex);
+  }
+}
+
+// The power function is a float32 sum of the squared bins in bin order (the reference's rounding, :388-396): one
+// thread per frame adds its row; a warp's 16-byte loads touch 32 rows, both halves of every sector get used (L1).
+__global__ void __launch_bounds__(128) k_rhythm_power(AfxBatchDev B, AfxParams P)
+{
+  const int rel = blockIdx.x * 128 + threadIdx.x;
   if (rel >= B.g_rslots) return;
   const int slot = B.rslot0 + rel;
   const int fi = B.rslot_file[slot];
-  const AfxFile f = B.files[fi];
-  const int t = slot - f.rframe_off;
-  if (f.status != 0 || t >= B.state[fi].Fr) return;
-  const float* r0 = B.rpolar + (size_t)rel * AFX_RROW;
-  const float* r1 = r0 - AFX_RROW;      // valid when t >= 1
-  const float* r2 = r0 - 2 * AFX_RROW;  // valid when t >= 2
-  double total = 0.0;
-  for (int i = lane; i < 256; i += 32) {
-    const float m = r0[i];
-    smag[wid][i] = (i < AFX_RBINS) ? __fmul_rn(m, m) : m;       // squares for the power function; [255] keeps dc
-    if (i >= AFX_RBINS) continue;
-    const float cur = fabsf(m);
-    const float pm = (t >= 1) ? fabsf(r1[i]) : 0.0f;
-    if (cur > 0.01f && !(cur < pm)) {
-      const float yp = (t >= 1) ? r1[256 + i] : 0.0f;
-      const float yp2 = (t >= 2) ? r2[256 + i] : 0.0f;
-      const float ypd = (t >= 1) ? phase_rewrap(__fsub_rn(yp, yp2)) : 0.0f;
-      const float pred = __fadd_rn(yp, ypd);
-      const float dev = __fsub_rn(pred, r0[256 + i]);
-      const float c = cosf(phase_rewrap(dev));
-      const float q = __fsub_rn(__fadd_rn(__fmul_rn(pm, pm), __fmul_rn(cur, cur)), __fmul_rn(__fmul_rn(pm, cur), c));
-      total += (double)sqrtf(q);
-    }
+  const int t = slot - B.files[fi].rframe_off;
+  if (B.files[fi].status != 0 || t >= B.state[fi].Fr) return;
+  const float4* row = reinterpret_cast<const float4*>(B.rpolar + (size_t)rel * AFX_RROW);
+  const float dc = B.rpolar[(size_t)rel * AFX_RROW + 255];
+  float v = __fadd_rn(__fmul_rn(0.0f, 0.0f), __fmul_rn(dc, dc));            // nyq^2 + dc^2
+#pragma unroll 8
+  for (int i = 0; i < 63; ++i) {
+    const float4 q = row[i];
+    v = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(v, __fmul_rn(q.x, q.x)), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)), __fmul_rn(q.w, q.w));
   }
-  total = warp_sum(total);
-  __syncwarp();
-  if (lane == 0) {
-    const float dc = smag[wid][255];
-    float v = __fadd_rn(__fmul_rn(0.0f, 0.0f), __fmul_rn(dc, dc));          // nyq^2 + dc^2, :388-396
-    const float4* sq4 = reinterpret_cast<const float4*>(smag[wid]);        // the reference adds bin by bin, in order
-#pragma unroll 4
-    for (int i = 0; i < 63; ++i) { const float4 q = sq4[i]; v = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(v, q.x), q.y), q.z), q.w); }
-    { const float4 q = sq4[63]; v = __fadd_rn(__fadd_rn(__fadd_rn(v, q.x), q.y), q.z); }
-    B.rodf[slot] = __fmul_rn((float)total, P.r_norm_complex);
-    B.rodf[(size_t)B.TFr + slot] = __fmul_rn(v, P.r_norm_power);
-  }
+  { const float4 q = row[63]; v = __fadd_rn(__fadd_rn(__fadd_rn(v, __fmul_rn(q.x, q.x)), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)); }
+  B.rodf[(size_t)B.TFr + slot] = __fmul_rn(v, P.r_norm_power);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -637,10 +669,11 @@ void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s,
   const int cap = B.max_fr;
   const int smem_back = (cap + 32) * 8 + ((cap + 15) & ~15) + ((cap + 31) / 32) * 4 + 16;
   cudaFuncSetAttribute(k_rhythm_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);   // per device, see afx_pitch.cu
-  const int fb = (B.g_rslots + RPW - 1) / RPW;
+  const int fb = (B.g_rslots + OW * OB - 1) / (OW * OB);
   k_rhythm_polar<<<(B.g_rslots + PF - 1) / PF, PF * 16, 0, s>>>(B, P); ++*launches;
   k_rhythm_whiten<<<B.g_files, 256, 0, s>>>(B, P); ++*launches;
-  k_rhythm_odf<<<fb, RPW * 32, 0, s>>>(B, P); ++*launches;
+  k_rhythm_odf<<<fb, OW * 32, 0, s>>>(B, P); ++*launches;
+  k_rhythm_power<<<(B.g_rslots + 127) / 128, 128, 0, s>>>(B, P); ++*launches;
   { const int nchunks = (B.g_rslots + ML - 1) / ML; k_rhythm_median<<<(2 * nchunks + 63) / 64, 64, 0, s>>>(B); ++*launches; }
   k_rhythm_back<<<B.g_files, BT_THREADS, smem_back, s>>>(B, P); ++*launches;
 }
