@@ -189,38 +189,65 @@ __device__ __forceinline__ void bands28(AfxBatchDev& B, const AfxParams& P, size
   }
 }
 
-// Phase A: grid (frames / 8, 8 roles).  All warps of a CTA run the SAME role (same code, same duration) on 8
+// Phase A: grid (frames / 8, roles).  All warps of a CTA run the SAME role (same code, same duration) on 8
 // different frames and never synchronise; the raw sums go to a per-frame scratch record in global memory.
-__global__ void __launch_bounds__(BT) k_bands_a(AfxBatchDev B, AfxParams P)
+// Roles 4..7 own the large sub-bands: their loads are issued in one batch at the top of subband().  Roles 0..3 run
+// many short loops over the row (nine small sub-bands, mel filters, the 28 bands): there every warp first copies its
+// frame's magnitude row to shared memory with all loads in flight at once -- as dependent global loads those loops
+// were 44 % long-scoreboard stalls.
+__global__ void __launch_bounds__(BT) k_bands_a_big(AfxBatchDev B, AfxParams P)
 {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int rel = blockIdx.x * 8 + wid;
   if (rel >= B.g_slots) return;
   const int slot = B.slot0 + rel;
   const int fi = B.slot_file[slot];
-  const AfxFile f = B.files[fi];
-  const int t = slot - f.frame_off;
-  if (f.status != 0 || t >= B.state[fi].F) return;
-  const size_t TF = (size_t)B.TF;
+  const int t = slot - B.files[fi].frame_off;
+  if (B.files[fi].status != 0 || t >= B.state[fi].F) return;
   const double* __restrict__ g = B.mag + (size_t)rel * AFX_NBIN;
   const double* __restrict__ gp = (t > 0) ? g - AFX_NBIN : g;              // SampleAnalyser.cpp:936-940
   BandRaw* raw = reinterpret_cast<BandRaw*>(B.bandraw + (size_t)rel * BR_STRIDE);
   double* lg = B.bandraw + (size_t)rel * BR_STRIDE + 140;
-  const int role = blockIdx.y;
-  switch (role) {
-    case 7: subband<9>(P, 13, g, gp, lane, raw); break;
-    case 6: subband<5>(P, 12, g, gp, lane, raw); break;
-    case 5: subband<3>(P, 11, g, gp, lane, raw); mel_energy(P, 12, g, lane, lg); mel_energy(P, 13, g, lane, lg); break;
-    case 4: subband<2>(P, 10, g, gp, lane, raw); subband<2>(P, 9, g, gp, lane, raw); break;
-    default: {
-      // roles 0..3: the nine bands of <= 32 bins (one code instance, looped), the mel energies and the 28 bands
-      const int first = (role == 3) ? 7 : (role == 2) ? 5 : (role == 1) ? 2 : 0;
-      const int last = (role == 3) ? 8 : (role == 2) ? 6 : (role == 1) ? 4 : 1;
-      for (int b = last; b >= first; --b) subband<1>(P, b, g, gp, lane, raw);
-      if (role >= 2) { for (int q = (role == 3 ? 8 : 0); q < (role == 3 ? 12 : 8); ++q) mel_energy(P, q, g, lane, lg); }
-      else bands28(B, P, TF, slot, role == 1 ? 14 : 0, role == 1 ? 28 : 14, g, lane);
-    } break;
+  switch (blockIdx.y) {
+    case 3: subband<9>(P, 13, g, gp, lane, raw); break;
+    case 2: subband<5>(P, 12, g, gp, lane, raw); break;
+    case 1: subband<3>(P, 11, g, gp, lane, raw); mel_energy(P, 12, g, lane, lg); mel_energy(P, 13, g, lane, lg); break;
+    default: subband<2>(P, 10, g, gp, lane, raw); subband<2>(P, 9, g, gp, lane, raw); break;
   }
+}
+
+__global__ void __launch_bounds__(BT) k_bands_a_small(AfxBatchDev B, AfxParams P)
+{
+  extern __shared__ __align__(16) double srow[];            // [8][1024]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rel = blockIdx.x * 8 + wid;
+  if (rel >= B.g_slots) return;
+  const int slot = B.slot0 + rel;
+  const int fi = B.slot_file[slot];
+  const int t = slot - B.files[fi].frame_off;
+  if (B.files[fi].status != 0 || t >= B.state[fi].F) return;
+  const size_t TF = (size_t)B.TF;
+  const double* __restrict__ gg = B.mag + (size_t)rel * AFX_NBIN;
+  const double* __restrict__ gp = (t > 0) ? gg - AFX_NBIN : gg;            // SampleAnalyser.cpp:936-940
+  double* g = srow + wid * AFX_NBIN;
+  {
+    const double2* src = reinterpret_cast<const double2*>(gg);
+    double2 tmp[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) tmp[q] = src[lane + 32 * q];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) reinterpret_cast<double2*>(g)[lane + 32 * q] = tmp[q];
+  }
+  __syncwarp();
+  BandRaw* raw = reinterpret_cast<BandRaw*>(B.bandraw + (size_t)rel * BR_STRIDE);
+  double* lg = B.bandraw + (size_t)rel * BR_STRIDE + 140;
+  const int role = blockIdx.y;
+  // roles 0..3: the nine bands of <= 32 bins (one code instance, looped), the mel energies and the 28 bands
+  const int first = (role == 3) ? 7 : (role == 2) ? 5 : (role == 1) ? 2 : 0;
+  const int last = (role == 3) ? 8 : (role == 2) ? 6 : (role == 1) ? 4 : 1;
+  for (int b = last; b >= first; --b) subband<1>(P, b, g, gp, lane, raw);
+  if (role >= 2) { for (int q = (role == 3 ? 8 : 0); q < (role == 3 ? 12 : 8); ++q) mel_energy(P, q, g, lane, lg); }
+  else bands28(B, P, TF, slot, role == 1 ? 14 : 0, role == 1 ? 28 : 14, g, lane);
 }
 
 // Phase B: 16 lanes per frame; lane j < 14 finishes sub-band j (the pow / log / exp chains run on full warps)
@@ -260,6 +287,9 @@ __global__ void __launch_bounds__(BT) k_bands_b(AfxBatchDev B, AfxParams P)
 void afx_launch_bands(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  k_bands_a<<<dim3((B.g_slots + 7) / 8, 8), BT, 0, s>>>(B, P); ++*launches;
+  const int smem = 8 * AFX_NBIN * (int)sizeof(double);
+  cudaFuncSetAttribute(k_bands_a_small, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device, see afx_pitch.cu
+  k_bands_a_big<<<dim3((B.g_slots + 7) / 8, 4), BT, 0, s>>>(B, P); ++*launches;
+  k_bands_a_small<<<dim3((B.g_slots + 7) / 8, 4), BT, smem, s>>>(B, P); ++*launches;
   k_bands_b<<<(B.g_slots * 16 + BT - 1) / BT, BT, 0, s>>>(B, P); ++*launches;
 }

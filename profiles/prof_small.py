@@ -11,6 +11,8 @@ if os.environ.get("PROF_LONG"):          # one 10-minute 96 kHz stereo file: the
     rate = 96000
     clip = synth.one_shot(7, 30.0, rate=rate, channels=2)
     pcms = [np.ascontiguousarray(np.tile(clip, (20, 1)))]
+elif os.environ.get("PROF_MIXED"):       # the mixed-length (0.5-30 s) corpus of BASELINE configs[3], as in bench.py --workload full
+    pcms = synth.tiled_corpus(int(os.environ.get("PROF_FILES", "128")), 64, seconds=30.0, seed0=0, min_seconds=0.5)
 else:
     pcms = synth.tiled_corpus(int(os.environ.get("PROF_FILES", "400")), 16, seconds=3.0, seed0=0)
 an = api.SampleAnalyser(44100, 2048, hop, features=feats)
