@@ -6,17 +6,15 @@
 // kurtosis, rolloff, flatness, flux) with TStatistics (Statistics.cpp:459-638) and LibXtract
 // (scalar.c:472-493, 624-636).
 //
-// 64 threads per frame, 4 frames per CTA; a frame group synchronises on its own named barrier.  The real
-// frame is packed as 1024 complex points (even samples -> re, odd -> im) and goes through the register-blocked
-// radix 16 x 16 x 4 transform of afx_fft16.cuh; every thread then owns bins tid, tid + 64, ... for the
-// magnitude and the order-free sums, and 12 consecutive analysis bins for the rolloff prefix sums.
+// 64 threads per frame; a frame group synchronises on its own named barrier.  The real frame is packed as 1024
+// complex points (even samples -> re, odd -> im) and goes through the register-blocked radix 16 x 16 x 4 transform
+// of afx_fft16.cuh; see k_spectrum below for the persistent layout, the bin-pair unpack and the fused statistics.
 #include "afx_fft16.cuh"
 #include "../../include/afec_b200.h"
 #include <algorithm>
 #include <cstdlib>
 
 #define SG 64               // threads per frame
-#define SF 4                // frames per CTA
 
 // sqrt of a squared magnitude to ~2^-44 relative: MUFU.RSQ64H seed (2^-22) + one Newton step.  The full IEEE sqrt
 // costs twice the FP64 instructions and its last 8 bits are far below what the FFT's own rounding leaves intact.
@@ -68,174 +66,70 @@ __device__ __forceinline__ double group_max(double v, double* xch, int gt, Sync 
   return v;
 }
 
-__global__ void __launch_bounds__(SG * SF, 3) k_spectrum_old(AfxBatchDev B, AfxParams P, unsigned features)
+// Amplitude features of the hop slice x[n0 .. n0 + H) (SA.cpp:865-873, 1760-1804; mathutils.c:345-357, 606-615;
+// Envelopes.inl:14-18): silence flag, peak, rms, and the maximum of a one-pole envelope follower that starts from 0
+// at every frame.  PER = H / 64 consecutive samples per thread, loaded once and kept in registers; the follower
+// s -> a + c (s - a) is an affine map per sample, so the 64 threads compose their maps with a scan and then replay
+// their own samples from the incoming state.
+template <int PER, class Sync>
+__device__ __forceinline__ void amp_features(const AfxBatchDev& B, const AfxParams& P, const float* __restrict__ mono, const AfxState& st,
+                                             int n0, int slot, int gt, double* xch, Sync sync)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int g = threadIdx.x / SG, gt = threadIdx.x % SG, lane = gt & 31, gw = gt >> 5;
-  double2* buf = reinterpret_cast<double2*>(smem_raw) + g * (AFX_NBIN + AFX_NBIN / 16);   // FFT buffer, later mag[1024]
-  double* xch = reinterpret_cast<double*>(reinterpret_cast<double2*>(smem_raw) + SF * (AFX_NBIN + AFX_NBIN / 16)) + g * 16;
-
-  const int rel = blockIdx.x * SF + g;
-  if (rel >= B.g_slots) return;                      // group-uniform; only the group's named barrier is used below
-  const int slot = B.slot0 + rel;
-  const int fi = B.slot_file[slot];
-  const AfxFile f = B.files[fi];
-  const AfxState st = B.state[fi];
-  const int t = slot - f.frame_off;
-  if (f.status != 0 || t >= st.F) return;
-  const int n0 = t * P.H;
-  const float* __restrict__ mono = B.mono + f.mono_off;
-  const double2* __restrict__ win2 = reinterpret_cast<const double2*>(P.t.window);
-  const int TF = B.TF;
-  FftSyncNamed<SG> sync{ 1 + g };
-
-  // ---- amplitude features of the hop slice (SA.cpp:865-873): H / 64 consecutive samples per thread --------
-  if (features & AFX_FEAT_AMPLITUDE) {
-    const int per = P.H / SG;                         // 4, 8, 16 or 32 (hop is a multiple of 256)
-    const double c = P.env_coef;
-    // one-pole envelope (Envelopes.inl:14-18) as a scan of affine maps s -> A s + Bv
-    double A = 1.0, Bv = 0.0, e_hop = 0.0, pk_hop = 0.0;
-    for (int q = 0; q < per; ++q) {
-      const double xv = mdata(mono, st, n0 + gt * per + q), a = fabs(xv);
-      e_hop += xv * xv; pk_hop = fmax(pk_hop, a);
-      Bv = a + c * (Bv - a);
-      A *= c;
-    }
-    double sA = A, sB = Bv;                           // inclusive scan inside the warp
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double pA = __shfl_up_sync(0xffffffffu, sA, o), pB = __shfl_up_sync(0xffffffffu, sB, o);
-      if (lane >= o) { sB = sA * pB + sB; sA = sA * pA; }
-    }
-    if (lane == 31 && gw == 0) { xch[4] = sA; xch[5] = sB; }
-    double ev[1] = { e_hop };
-    group_sum<1>(ev, xch, gt, sync);                  // also publishes xch[4..5] (first barrier inside)
-    double s_in = (gw == 1) ? xch[5] : 0.0;           // state entering the second warp = first warp's map applied to 0
-    const double pA = __shfl_up_sync(0xffffffffu, sA, 1), pB = __shfl_up_sync(0xffffffffu, sB, 1);
-    if (lane > 0) s_in = pA * s_in + pB;
-    double env = s_in, emax = 0.0;
-    for (int q = 0; q < per; ++q) { const double a = fabs(mdata(mono, st, n0 + gt * per + q)); env = a + c * (env - a); emax = fmax(emax, env); }
-    const double pk = group_max(pk_hop, xch, gt, sync);
-    emax = group_max(emax, xch, gt, sync);
-    if (gt == 0) {
-      const double level = ev[0] / (double)P.H;
-      B.fs[(size_t)FS_AMP_SILENCE * TF + slot] = (level < AFX_SILENCE_LEVEL) ? 1.0 : 0.0;   // mathutils.c:606-615
-      B.fs[(size_t)FS_AMP_PEAK * TF + slot] = pk;
-      const double r = sqrt(level);
-      B.fs[(size_t)FS_AMP_RMS * TF + slot] = (r != r) ? 0.0 : r;
-      B.fs[(size_t)FS_AMP_ENV * TF + slot] = emax;
-    }
-  }
-
-  // ---- load, window, pack (even -> re, odd -> im) in the FFT's strided order; transform ---------------------
-  double2 v[16];
-#pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int m = gt + SG * r;
-    const double2 w = __ldg(win2 + m);
-    v[r] = make_double2(mdata(mono, st, n0 + 2 * m) * w.x, mdata(mono, st, n0 + 2 * m + 1) * w.y);
-  }
-  fft16_run<AFX_NBIN>(v, buf, FftTw{ P.t.fft_t2, P.t.fft_t3_1024 }, gt, sync);
-
-  // ---- real unpack + magnitude / N for bins gt + 64 c (Fourier.cpp:266-271, AudioMath.cpp:497-504) ---------
-  double m16[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const int k = gt + SG * c;
-    const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((AFX_NBIN - k) & (AFX_NBIN - 1))];
-    const double2 zm = make_double2(zc.x, -zc.y);
-    const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y + zm.y));
-    const double2 D = make_double2(0.5 * (zk.x - zm.x), 0.5 * (zk.y - zm.y));
-    const double2 O = make_double2(D.y, -D.x);                 // D / i
-    const double2 X = f_add(E, f_mul(__ldg(P.t.tw2048 + k), O));
-    m16[c] = sqrt(X.x * X.x + X.y * X.y) * (1.0 / AFX_NFFT);
-  }
-  double* gmag = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
-  sync();                                            // everyone has read Z before buf becomes the magnitude array
-  double* mag = reinterpret_cast<double*>(buf);
-#pragma unroll
-  for (int c = 0; c < 16; ++c) { const int k = gt + SG * c; mag[k] = m16[c]; gmag[k] = m16[c]; }
-
-  // ---- order-free sums over the analysis window (bins first_bin .. first_bin + nbins - 1) and all bins -----
-  const int nb = P.nbins, fb = P.first_bin;
-  double acc[6] = { 0, 0, 0, 0, 0, 0 };        // S1, S2, SJ, log-sum, full S, full SJ
-  double mant = 1.0; int ex = 0;
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const int k = gt + SG * c, j = k - fb;
-    const double m = m16[c];
-    acc[4] += m; acc[5] += (double)k * m;
-    if (j >= 0 && j < nb) {
-      acc[0] += m; acc[1] += m * m; acc[2] += (double)j * m;
-      mul_frexp_pos(mant, ex, fabs(m) + 1e-20);               // Statistics.cpp:417-455
-    }
-  }
-  acc[3] = log(mant) + (double)ex * 0.693147180559945309417;
-  group_sum<6>(acc, xch, gt, sync);                  // (its first barrier also publishes mag[])
-  const double S1 = acc[0];
-  const double cen = (S1 == 0.0) ? 0.0 : acc[2] / S1;                          // Statistics.cpp:459-477
-  double sp[1] = { 0.0 };
-#pragma unroll
-  for (int c = 0; c < 16; ++c) { const int j = gt + SG * c - fb; if (j >= 0 && j < nb) { const double d = (double)j - cen; sp[0] += d * d * m16[c]; } }
-  group_sum<1>(sp, xch, gt, sync);
-  const double spread = (S1 == 0.0) ? 0.0 : sp[0] / S1;                        // Statistics.cpp:486-506
-  double sk[2] = { 0.0, 0.0 };
-  const bool have_sk = fabs(spread) > (double)1e-12f;                          // Statistics.cpp:510-554
-  if (have_sk) {
-#pragma unroll
-    for (int c = 0; c < 16; ++c) { const int j = gt + SG * c - fb; if (j >= 0 && j < nb) { const double d = (m16[c] - cen) / spread; const double d2 = d * d; sk[0] += d2 * d; sk[1] += d2 * d2; } }
-  }
-  group_sum<2>(sk, xch, gt, sync);
-
-  // ---- rolloff (LibXtract scalar.c:472-493): count of prefixes below 85 % of the total; 12 bins per thread ---
+  const int lane = gt & 31, gw = gt >> 5;
+  const double c = P.env_coef;
+  float xf[PER];
   {
-    const double pivot = S1 * (85.0 / 100.0);
-    const int j0 = 12 * gt;
-    double m12[12], loc = 0.0;
+    const int j0 = n0 + gt * PER - st.start_off;
+    const float* __restrict__ src = mono + st.lead + j0;
+    if (j0 >= 0 && j0 + PER <= st.audible) {
 #pragma unroll
-    for (int q = 0; q < 12; ++q) { m12[q] = (j0 + q < nb) ? mag[fb + j0 + q] : 0.0; loc += m12[q]; }
-    double inc = loc;
+      for (int q = 0; q < PER; ++q) xf[q] = __ldg(src + q);
+    } else {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double pv = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += pv; }
-    if (lane == 31 && gw == 0) xch[0] = inc;
-    sync();
-    double pre = ((gw == 1) ? xch[0] : 0.0) + inc - loc;      // exclusive prefix = sum of bins before j0
-    int cnt = 0;
-#pragma unroll
-    for (int q = 0; q < 12; ++q) if (j0 + q < nb) { cnt += (pre < pivot) ? 1 : 0; pre += m12[q]; }
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    int* ix = reinterpret_cast<int*>(xch + 2);
-    if (lane == 0) ix[gw] = cnt;
-    sync();
-    if (gt == 0) {
-      const double r = (double)(ix[0] + ix[1]) * (double)(P.sr / (P.N / 2));   // SA.cpp:1892: 44100 / 1024 = 43
-      B.fs[(size_t)FS_SPEC_ROLLOFF * TF + slot] = r;
+      for (int q = 0; q < PER; ++q) xf[q] = (j0 + q >= 0 && j0 + q < st.audible) ? __ldg(src + q) : 0.0f;
     }
   }
-
+  double A = 1.0, Bv = 0.0, e_hop = 0.0, pk_hop = 0.0;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const double xv = (double)xf[q] * st.fs, a = fabs(xv);     // mdata()
+    e_hop += xv * xv; pk_hop = fmax(pk_hop, a);
+    Bv = a + c * (Bv - a);
+    A *= c;
+  }
+  double sA = A, sB = Bv;                           // inclusive scan inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double pA = __shfl_up_sync(0xffffffffu, sA, o), pB = __shfl_up_sync(0xffffffffu, sB, o);
+    if (lane >= o) { sB = sA * pB + sB; sA = sA * pA; }
+  }
+  if (lane == 31 && gw == 0) { xch[4] = sA; xch[5] = sB; }
+  double ev[1] = { e_hop };
+  group_sum<1>(ev, xch, gt, sync);                  // also publishes xch[4..5] (first barrier inside)
+  double s_in = (gw == 1) ? xch[5] : 0.0;           // state entering the second warp = first warp's map applied to 0
+  const double pA = __shfl_up_sync(0xffffffffu, sA, 1), pB = __shfl_up_sync(0xffffffffu, sB, 1);
+  if (lane > 0) s_in = pA * s_in + pB;
+  double env = s_in, emax = 0.0;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) { const double a = fabs((double)xf[q] * st.fs); env = a + c * (env - a); emax = fmax(emax, env); }
+  // one exchange for both maxima
+  pk_hop = warp_max(pk_hop); emax = warp_max(emax);
+  if (lane == 0) { xch[8 + gw] = pk_hop; xch[10 + gw] = emax; }
+  sync();
   if (gt == 0) {
-    const double n = (double)nb;
-    const double rms = sqrt(acc[1] / n);
-    B.fs[(size_t)FS_SPEC_RMS * TF + slot] = (rms != rms) ? 0.0 : rms;
-    B.fs[(size_t)FS_SPEC_CENTROID * TF + slot] = cen;
-    B.fs[(size_t)FS_SPEC_SPREAD * TF + slot] = spread;
-    B.fs[(size_t)FS_SPEC_SKEW * TF + slot] = have_sk ? sk[0] / n : 0.0;
-    B.fs[(size_t)FS_SPEC_KURT * TF + slot] = have_sk ? sk[1] / n - 3.0 : 0.0;
-    const double mean = S1 / n, gmean = exp(acc[3] / n);
-    const double fl = flatness_db(mean, gmean);
-    B.fs[(size_t)FS_SPEC_FLATNESS * TF + slot] = (fl != fl) ? 0.0 : fl;
-    B.cent_full[slot] = (acc[4] == 0.0) ? 0.0 : acc[5] / acc[4];
-    // degenerate in the reference (see oracle/afec_oracle.c, "harmonic spectrum"): always 0
-    B.fs[(size_t)FS_SPEC_INHARM * TF + slot] = 0.0;
-    B.fs[(size_t)FS_TRISTIM1 * TF + slot] = 0.0;
-    B.fs[(size_t)FS_TRISTIM2 * TF + slot] = 0.0;
-    B.fs[(size_t)FS_TRISTIM3 * TF + slot] = 0.0;
+    const size_t TF = (size_t)B.TF;
+    const double level = ev[0] / (double)P.H;
+    B.fs[(size_t)FS_AMP_SILENCE * TF + slot] = (level < AFX_SILENCE_LEVEL) ? 1.0 : 0.0;   // mathutils.c:606-615
+    B.fs[(size_t)FS_AMP_PEAK * TF + slot] = fmax(xch[8], xch[9]);
+    const double r = sqrt(level);
+    B.fs[(size_t)FS_AMP_RMS * TF + slot] = (r != r) ? 0.0 : r;
+    B.fs[(size_t)FS_AMP_ENV * TF + slot] = fmax(xch[10], xch[11]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Persistent form: one CTA per SM, NG frame groups of 64 threads, every group walks frame slots it claims from a
-// global counter (SCH at a time).  What this buys over one-CTA-per-4-frames:
+// Persistent kernel: one CTA per SM, NG frame groups of 64 threads, every group walks frame slots it claims from a
+// global counter (SCH at a time).  What this buys over one CTA per 4 frames (the first form of this kernel):
 //   * the window, the two FFT twiddle tables and the real-unpack twiddles (40 KB) live in shared memory for the
 //     whole kernel -- with 3 x 70 KB of FFT buffers per SM only 28 KB of L1 are left and the tables used to miss
 //     half the time (ncu: 53 % L1 hit rate on global loads, long-scoreboard the top stall);
@@ -301,39 +195,10 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
   // ---- amplitude features of the hop slice (SA.cpp:865-873): H / 64 consecutive samples per thread --------
   if (features & AFX_FEAT_AMPLITUDE) {
     const int per = P.H / SG;                         // 4, 8, 16 or 32 (hop is a multiple of 256)
-    const double c = P.env_coef;
-    // one-pole envelope (Envelopes.inl:14-18) as a scan of affine maps s -> A s + Bv
-    double A = 1.0, Bv = 0.0, e_hop = 0.0, pk_hop = 0.0;
-    for (int q = 0; q < per; ++q) {
-      const double xv = mdata(mono, st, n0 + gt * per + q), a = fabs(xv);
-      e_hop += xv * xv; pk_hop = fmax(pk_hop, a);
-      Bv = a + c * (Bv - a);
-      A *= c;
-    }
-    double sA = A, sB = Bv;                           // inclusive scan inside the warp
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double pA = __shfl_up_sync(0xffffffffu, sA, o), pB = __shfl_up_sync(0xffffffffu, sB, o);
-      if (lane >= o) { sB = sA * pB + sB; sA = sA * pA; }
-    }
-    if (lane == 31 && gw == 0) { xch[4] = sA; xch[5] = sB; }
-    double ev[1] = { e_hop };
-    group_sum<1>(ev, xch, gt, sync);                  // also publishes xch[4..5] (first barrier inside)
-    double s_in = (gw == 1) ? xch[5] : 0.0;           // state entering the second warp = first warp's map applied to 0
-    const double pA = __shfl_up_sync(0xffffffffu, sA, 1), pB = __shfl_up_sync(0xffffffffu, sB, 1);
-    if (lane > 0) s_in = pA * s_in + pB;
-    double env = s_in, emax = 0.0;
-    for (int q = 0; q < per; ++q) { const double a = fabs(mdata(mono, st, n0 + gt * per + q)); env = a + c * (env - a); emax = fmax(emax, env); }
-    const double pk = group_max(pk_hop, xch, gt, sync);
-    emax = group_max(emax, xch, gt, sync);
-    if (gt == 0) {
-      const double level = ev[0] / (double)P.H;
-      B.fs[(size_t)FS_AMP_SILENCE * TF + slot] = (level < AFX_SILENCE_LEVEL) ? 1.0 : 0.0;   // mathutils.c:606-615
-      B.fs[(size_t)FS_AMP_PEAK * TF + slot] = pk;
-      const double r = sqrt(level);
-      B.fs[(size_t)FS_AMP_RMS * TF + slot] = (r != r) ? 0.0 : r;
-      B.fs[(size_t)FS_AMP_ENV * TF + slot] = emax;
-    }
+    if (per == 16) amp_features<16>(B, P, mono, st, n0, slot, gt, xch, sync);
+    else if (per == 8) amp_features<8>(B, P, mono, st, n0, slot, gt, xch, sync);
+    else if (per == 4) amp_features<4>(B, P, mono, st, n0, slot, gt, xch, sync);
+    else amp_features<32>(B, P, mono, st, n0, slot, gt, xch, sync);
   }
 
   // ---- load, window, pack (even -> re, odd -> im) in the FFT's strided order; transform ---------------------
@@ -537,21 +402,10 @@ static void launch_spectrum_p(const AfxParams& P, const AfxBatchDev& B, unsigned
 void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  static const int variant = getenv("AFX_SPEC_VARIANT") ? atoi(getenv("AFX_SPEC_VARIANT")) : 10;
-  if (variant == 0) {
-    const int smem = SF * (AFX_NBIN + AFX_NBIN / 16) * (int)sizeof(double2) + SF * 16 * (int)sizeof(double);
-    cudaFuncSetAttribute(k_spectrum_old, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_spectrum_old, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    k_spectrum_old<<<(B.g_slots + SF - 1) / SF, SG * SF, smem, s>>>(B, P, features); ++*launches;
-  } else {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (variant == 8) launch_spectrum_p<8>(P, B, features, s, sms);
-    else if (variant == 9) launch_spectrum_p<9>(P, B, features, s, sms);
-    else launch_spectrum_p<10>(P, B, features, s, sms);
-    ++*launches;
-  }
-  const int stride = (variant == 0) ? 1 : SCH, nflux = (B.g_slots + stride - 1) / stride;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  launch_spectrum_p<10>(P, B, features, s, sms); ++*launches;
+  const int stride = SCH, nflux = (B.g_slots + stride - 1) / stride;
   k_flux<<<(nflux + 3) / 4, 256, 0, s>>>(B, P, stride); ++*launches;
 }
