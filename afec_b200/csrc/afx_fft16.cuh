@@ -99,7 +99,9 @@ struct FftTw {
 template <bool TW_SMEM>
 __device__ __forceinline__ double2 fft_tw_load(const double2* p) { return TW_SMEM ? *p : __ldg(p); }
 
-template <int N, class Sync, bool TW_SMEM = false>
+// T3STEP: the N = 1024 third pass may read its twiddles from the N = 2048 table (exp(-2 pi i r j / 1024) is row 2r of
+// exp(-2 pi i r j / 2048)): T3STEP = 2 with tw.t3 pointing at the 2048 table
+template <int N, class Sync, bool TW_SMEM = false, int T3STEP = 1>
 __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict__ buf, const FftTw tw, int tid, Sync sync)
 {
   constexpr int NT = N / 16;
@@ -135,7 +137,7 @@ __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict_
     for (int b = 0; b < 4; ++b) {
       const int i = tid + NT * b;          // k = i (i < p = 256)
 #pragma unroll
-      for (int r = 1; r < 4; ++r) v[4 * b + r] = f_mul(v[4 * b + r], fft_tw_load<TW_SMEM>(tw.t3 + (r - 1) * 256 + i));
+      for (int r = 1; r < 4; ++r) v[4 * b + r] = f_mul(v[4 * b + r], fft_tw_load<TW_SMEM>(tw.t3 + (r * T3STEP - 1) * 256 + i));
       f_r4(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) buf[FFT_PHYS(i + q * 256)] = v[4 * b + q];

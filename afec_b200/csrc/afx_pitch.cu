@@ -14,7 +14,7 @@
 //
 // 128 threads per frame.  The zero-padded first half a and the full frame b are transformed
 // together as z = a + i b by ONE 2048-point complex FFT (register-blocked radix 16 x 16 x 8, afx_fft16.cuh),
-// split into A and B, and conj(conj(A) B) goes through the same forward transform (r = Re FFT(conj(P)) / N).
+// split into A and B; the real correlation r = IFFT(conj(A) B) comes back through a HALF-size (1024-point) transform.
 // Shared memory: one padded 2048-point FFT buffer (34 KB) and yin' (9 KB).  The prefix sums of squares live in the FFT
 // buffer before the first transform: the windowed square sums sq[tau] they are needed for go to the yin array up front.
 #include "afx_fft16.cuh"
@@ -36,7 +36,8 @@ template <int NG>
 struct PitchSmem {
   static constexpr int BUF = YN + YN / 16;                             // double2 per group
   static constexpr int YIN = YW + YW / 8 + 8;                          // doubles per group
-  static constexpr size_t group_bytes = (size_t)BUF * sizeof(double2) + (size_t)YIN * sizeof(double) + 40 * sizeof(double);
+  static constexpr int HBUF = YW + YW / 16;                            // double2 per group: the half-size inverse transform
+  static constexpr size_t group_bytes = (size_t)(BUF + HBUF) * sizeof(double2) + (size_t)YIN * sizeof(double) + 40 * sizeof(double);
   static constexpr size_t o_t2 = (size_t)NG * group_bytes;            // [15][16]
   static constexpr size_t o_t3 = o_t2 + 240 * sizeof(double2);        // [7][256]
   static constexpr size_t bytes = o_t3 + 7 * 256 * sizeof(double2);
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(YT * NG, 1) k_pitch(AfxBatchDev B, AfxParams P
   unsigned char* gbase = smem_raw + (size_t)g * L::group_bytes;
   double2* buf = reinterpret_cast<double2*>(gbase);                    // [2048 + 128]
   double* S = reinterpret_cast<double*>(buf);                          // [PAD16(2048) + 1] prefix sums of squares (before the FFTs)
-  double* yin = reinterpret_cast<double*>(buf + L::BUF);               // [PAD8(1024)]
+  double2* hbuf = buf + L::BUF;                                        // [1024 + 64]
+  double* yin = reinterpret_cast<double*>(hbuf + L::HBUF);             // [PAD8(1024)]
   double* scratch = yin + L::YIN;                                      // [8] scans / argmin
   double* level = scratch + 8;                                         // [2] sum of squares of the frame / of the hop
   int* iscr = reinterpret_cast<int*>(scratch + 12);                    // [8] argmin / first dip
@@ -166,20 +168,47 @@ __global__ void __launch_bounds__(YT * NG, 1) k_pitch(AfxBatchDev B, AfxParams P
     }
     sync();                                                      // S is dead: the FFT buffer takes its place
     fft16_run<YN, FftSyncNamed<YT>, true>(v, buf, ftw, tid, sync);
-    // split into A (transform of a) and B (of b), O = conj(conj(A) B); every thread builds its own 16 inputs
+    // ---- r = IFFT_2048(P), P[k] = conj(A[k]) B[k] with A, B the transforms of a and b split out of Z.  r is real, so
+    // the inverse runs at HALF size (Hermitian P): with z[m] = r[2m] + i r[2m+1],
+    //   z = IFFT_1024(Zc),  Zc[k] = (P[k] + conj(P[1024-k])) / 2 + i W^-k (P[k] - conj(P[1024-k])) / 2,  W = exp(-2 pi i / 2048).
+    // All 128 threads build Zc pairwise (k, 1024 - k share P[k] and P[1024-k]) into hbuf; 64 threads then run the
+    // 1024-point transform (as conj(FFT(conj(Zc))) / 1024) -- a quarter of the shared-memory traffic of the full-size
+    // inverse, which is what bounds this kernel.
+    {
+      auto pk = [&](int k, int kc) {                              // P[k] from Z[k] and Z[kc], kc = (2048 - k) mod 2048
+        const double2 z1 = buf[FFT_PHYS(k)], z2 = buf[FFT_PHYS(kc)];
+        const double2 A = make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y));
+        const double2 Bc = make_double2(0.5 * (z1.y + z2.y), 0.5 * (z2.x - z1.x));            // (z1 - conj(z2)) / (2 i)
+        return f_mul(make_double2(A.x, -A.y), Bc);
+      };
+      auto pair = [&](int k) {                                    // 0 <= k <= 512
+        const double2 p1 = pk(k, (YN - k) & (YN - 1)), p2 = pk(YW - k, YW + k);
+        const double2 w = __ldg(P.t.tw2048 + k);                  // W^k; W^-k = conj
+        const double2 e1 = make_double2(0.5 * (p1.x + p2.x), 0.5 * (p1.y - p2.y));           // (P[k] + conj(P[k'])) / 2
+        const double2 d1 = make_double2(0.5 * (p1.x - p2.x), 0.5 * (p1.y + p2.y));           // (P[k] - conj(P[k'])) / 2
+        const double2 o1 = f_mul(make_double2(w.x, -w.y), d1);                                 // W^-k d1
+        const double2 zc1 = make_double2(e1.x - o1.y, e1.y + o1.x);                            // e1 + i o1
+        hbuf[FFT_PHYS(k)] = make_double2(zc1.x, -zc1.y);                                       // conj(Zc[k])
+        if (k > 0) {
+          // Zc[k'] = conj(e1) + i (-W^k) (-conj(d1)) = conj(e1) + i W^k conj(d1)
+          const double2 o2 = f_mul(w, make_double2(d1.x, -d1.y));
+          const double2 zc2 = make_double2(e1.x - o2.y, -e1.y + o2.x);
+          hbuf[FFT_PHYS(YW - k)] = make_double2(zc2.x, -zc2.y);
+        }
+      };
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const int k = tid + YT * r;
-      const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((YN - k) & (YN - 1))];
-      const double2 zn = make_double2(zc.x, -zc.y);
-      const double2 A = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y + zn.y));
-      const double2 D = make_double2(0.5 * (zk.x - zn.x), 0.5 * (zk.y - zn.y));
-      const double2 Bc = make_double2(D.y, -D.x);                  // D / i
-      const double2 Pk = f_mul(make_double2(A.x, -A.y), Bc);
-      v[r] = make_double2(Pk.x, -Pk.y);
+      for (int c = 0; c < 4; ++c) pair(tid + YT * c);
+      if (tid == 0) pair(YW / 2);
     }
-    sync();                                                        // all reads of buf done before it is rewritten
-    fft16_run<YN, FftSyncNamed<YT>, true>(v, buf, ftw, tid, sync);
+    sync();
+    if (tid < 64) {
+      FftSyncNamed<64> hsync{ 8 + g };
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = hbuf[FFT_PHYS(tid + 64 * r)];
+      hsync();                                                     // every input is in registers before hbuf is rewritten
+      fft16_run<YW, FftSyncNamed<64>, true, 2>(v, hbuf, ftw, tid, hsync);
+    }
+    sync();
 
     // ---- the next frame's loads go out now and land while this frame's search runs -------------------------
     PitchNext nxt;
@@ -189,7 +218,8 @@ __global__ void __launch_bounds__(YT * NG, 1) k_pitch(AfxBatchDev B, AfxParams P
 #pragma unroll
     for (int c = 0; c < YW / YT; ++c) {
       const int tau = tid + YT * c;
-      yin[PAD8(tau)] = yin[PAD8(tau)] - buf[FFT_PHYS(tau)].x * (1.0 / YN);
+      const double2 f = hbuf[FFT_PHYS(tau >> 1)];                // z[m] = conj(F[m]) / 1024: r[2m] = Re, r[2m+1] = Im
+      yin[PAD8(tau)] = yin[PAD8(tau)] - ((tau & 1) ? -f.y : f.x) * (1.0 / YW);
     }
     sync();
     // ---- cumulative-mean normalisation: 8 consecutive tau per thread ---------------------------------------
