@@ -7,6 +7,7 @@
 #include "sqlite3_min.h"
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <sys/stat.h>
@@ -20,7 +21,8 @@ struct TSqliteSampleDescriptorPool::Impl {
   sqlite3_stmt* insert_failed = nullptr;
   std::string file;
   int bulk = 0;
-  std::vector<unsigned char> blob;
+  std::vector<unsigned char> blob;    // one row's msgpack blobs, back to back (bound SQLITE_STATIC until the step)
+  std::vector<std::pair<int, std::pair<size_t, size_t>>> blob_binds;   // parameter index -> (offset, size) in blob
 };
 
 static void check(sqlite3* db, int rc, const char* what)
@@ -91,6 +93,10 @@ static bool open_db(sqlite3** db, const std::string& name, bool ro)
     exec(*db, "PRAGMA encoding = utf8;");
     exec(*db, "PRAGMA journal_mode = WAL;");
     exec(*db, "PRAGMA synchronous = NORMAL;");
+    // connection-local tuning (nothing of it is stored in the file): a row is 0.2-1 MB of BLOBs, so the default 2 MB
+    // page cache and the 1000-page auto-checkpoint make every few inserts spill and checkpoint
+    exec(*db, "PRAGMA cache_size = -262144;");
+    exec(*db, "PRAGMA wal_autocheckpoint = 65536;");
   }
   return true;
 }
@@ -166,12 +172,31 @@ std::vector<std::pair<std::string, int>> TSqliteSampleDescriptorPool::SampleModi
 void TSqliteSampleDescriptorPool::BeginBulk() { if (mImpl->bulk++ == 0) exec(mImpl->db, "BEGIN"); }
 void TSqliteSampleDescriptorPool::EndBulk() { if (mImpl->bulk > 0 && --mImpl->bulk == 0) exec(mImpl->db, "COMMIT"); }
 
+// append helpers: msgpack straight into the row buffer (same bytes as PackVR / PackVVR)
+static inline void put_array_header(std::vector<unsigned char>& out, size_t n)
+{
+  if (n < 16) out.push_back((unsigned char)(0x90u | n));
+  else if (n < 65536) { out.push_back(0xdc); out.push_back((unsigned char)(n >> 8)); out.push_back((unsigned char)n); }
+  else { out.push_back(0xdd); out.push_back((unsigned char)(n >> 24)); out.push_back((unsigned char)(n >> 16)); out.push_back((unsigned char)(n >> 8)); out.push_back((unsigned char)n); }
+}
+static inline void put_doubles(std::vector<unsigned char>& out, const double* v, size_t n)
+{
+  const size_t o = out.size();
+  out.resize(o + 9 * n);
+  unsigned char* p = out.data() + o;
+  for (size_t i = 0; i < n; ++i) {
+    uint64_t u; memcpy(&u, v + i, 8);
+    u = __builtin_bswap64(u);
+    *p++ = 0xcb; memcpy(p, &u, 8); p += 8;
+  }
+}
+
 void TSqliteSampleDescriptorPool::InsertSample(const std::string& FileName, const TSampleDescriptors& R)
 {
   Impl& I = *mImpl;
   if (!I.db) throw TReadableException("Database is not open");
-  const std::vector<std::string> cols = ColumnNamesAndTypes();
   if (!I.insert) {
+    const std::vector<std::string> cols = ColumnNamesAndTypes();
     std::string sql = "INSERT OR REPLACE into assets(", q;
     for (size_t i = 0; i < cols.size(); ++i) {
       if (i) { sql += ","; q += ","; }
@@ -185,6 +210,15 @@ void TSqliteSampleDescriptorPool::InsertSample(const std::string& FileName, cons
   const bool own_txn = (I.bulk == 0);
   if (own_txn) exec(I.db, "BEGIN");
   try {
+    // All BLOBs of the row are packed back to back into one buffer and bound without a copy (SQLITE_STATIC is
+    // valid until the statement is stepped); the buffer may move while it grows, so the binds happen at the end.
+    I.blob.clear(); I.blob_binds.clear();
+    size_t want = 64;
+    for (int s = 0; s < AFX_N_FS; ++s) want += 5 + 9 * R.mFramedScalars[s].size();
+    for (int v = 0; v < AFX_N_FV; ++v) want += 5 + (size_t)R.mFrames * (3 + 9 * (size_t)kFramedVectorBands[v]) + AFX_N_STATS * (5 + 9 * (size_t)kFramedVectorBands[v]);
+    I.blob.reserve(want);
+    auto blob_begin = [&]() { return I.blob.size(); };
+    auto blob_end = [&](int param, size_t o) { I.blob_binds.push_back({ param, { o, I.blob.size() - o } }); };
     int p = 1;
     sqlite3_bind_text(st, p++, rel.c_str(), -1, SQLITE_TRANSIENT);
     sqlite3_bind_int(st, p++, ModificationStatTime(FileName));
@@ -197,8 +231,10 @@ void TSqliteSampleDescriptorPool::InsertSample(const std::string& FileName, cons
     sqlite3_bind_int(st, p++, (int)R.mHeader[4]);
     for (int k = 5; k < 9; ++k) sqlite3_bind_double(st, p++, R.mHeader[k]);
     auto framed = [&](int s) {
-      PackVR(I.blob, R.mFramedScalars[s].data(), R.mFramedScalars[s].size());
-      sqlite3_bind_blob(st, p++, I.blob.data(), (int)I.blob.size(), SQLITE_TRANSIENT);
+      const size_t o = blob_begin();
+      put_array_header(I.blob, R.mFramedScalars[s].size());
+      put_doubles(I.blob, R.mFramedScalars[s].data(), R.mFramedScalars[s].size());
+      blob_end(p++, o);
       for (int k = 0; k < AFX_N_STATS; ++k) sqlite3_bind_double(st, p++, R.mStats[s][k]);
     };
     for (int s = 0; s < AFX_N_FS_MAIN; ++s) framed(s);
@@ -210,16 +246,24 @@ void TSqliteSampleDescriptorPool::InsertSample(const std::string& FileName, cons
     int series = AFX_N_FS;
     for (int v = 0; v < AFX_N_FV; ++v) {
       const int nb = kFramedVectorBands[v];
-      PackVVR(I.blob, R.mFramedVectors[v].data(), (size_t)R.mFrames, (size_t)nb);
-      sqlite3_bind_blob(st, p++, I.blob.data(), (int)I.blob.size(), SQLITE_TRANSIENT);
+      {
+        const size_t o = blob_begin();
+        put_array_header(I.blob, (size_t)R.mFrames);
+        for (size_t f = 0; f < (size_t)R.mFrames; ++f) { put_array_header(I.blob, (size_t)nb); put_doubles(I.blob, R.mFramedVectors[v].data() + f * nb, (size_t)nb); }
+        blob_end(p++, o);
+      }
       double col[28];
       for (int k = 0; k < AFX_N_STATS; ++k) {
         for (int b = 0; b < nb; ++b) col[b] = R.mStats[series + b][k];
-        PackVR(I.blob, col, (size_t)nb);
-        sqlite3_bind_blob(st, p++, I.blob.data(), (int)I.blob.size(), SQLITE_TRANSIENT);
+        const size_t o = blob_begin();
+        put_array_header(I.blob, (size_t)nb);
+        put_doubles(I.blob, col, (size_t)nb);
+        blob_end(p++, o);
       }
       series += nb;
     }
+    for (const auto& bb : I.blob_binds)
+      sqlite3_bind_blob(st, bb.first, I.blob.data() + bb.second.first, (int)bb.second.second, SQLITE_STATIC);
     const int rc = sqlite3_step(st);
     sqlite3_reset(st); sqlite3_clear_bindings(st);
     check(I.db, rc, "insert");

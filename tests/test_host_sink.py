@@ -109,3 +109,21 @@ def test_old_database_versions_are_rebuilt_and_newer_refused(host, tmp_path):
     assert [r[0] for r in c.execute("select filename from assets")] == ["/nonexistent/f.wav"]
     c.execute("pragma user_version = 3"); c.commit(); c.close()
     assert host.afxh_write_row(db.encode(), b"", b"/nonexistent/g.wav", None, 0, 0, None, None, None, None, b"x") == -2
+
+
+def test_sink_throughput_hook_writes_readable_rows(host, tmp_path):
+    """afxh_sink_bench (how fast can rows go into afec-ll.db) inserts synthetic rows through the same
+    InsertSample path; the rows must read back with every BLOB a well-formed msgpack array of the declared length."""
+    host.afxh_sink_bench.restype = C.c_double
+    host.afxh_sink_bench.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    db = str(tmp_path / "sink.db")
+    secs = host.afxh_sink_bench(db.encode(), 12, 128, 1030, 5)
+    assert secs > 0.0
+    con = sqlite3.connect(db)
+    assert con.execute("SELECT count(*) FROM assets WHERE status = 'succeeded'").fetchone()[0] == 12
+    row = con.execute("SELECT spectral_centroid_VR, rhythm_complex_onsets_VR, cepstrum_bands_VVR, frequency_bands_mean_VR "
+                      "FROM assets LIMIT 1").fetchone()
+    cen, ons, cep, fbm = (msgpack.unpackb(b) for b in row)
+    assert len(cen) == 128 and len(ons) == 1030 and len(cep) == 128 and len(cep[0]) == 14 and len(fbm) == 28
+    assert con.execute("PRAGMA user_version").fetchone()[0] == 2
+    con.close()
