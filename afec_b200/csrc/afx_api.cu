@@ -501,6 +501,13 @@ int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, 
     if (tf > 0x7fffffffLL || tfr > 0x7fffffffLL) { delete b; return fail(ctx, AFX_ERR_ARG, "afx_batch_create: batch too large (frame slots overflow int32)"); }
   }
   close_group();
+  // per-file kernels (whitening recurrences, rhythm back end) take a group's files longest first: their run time grows
+  // with the file's frame count (the beat tracker's with its square), and a long file started last is the launch's tail
+  b->file_order.resize(n_files);
+  for (int i = 0; i < n_files; ++i) b->file_order[i] = i;
+  for (const auto& gg : b->groups)
+    std::stable_sort(b->file_order.begin() + gg.file0, b->file_order.begin() + gg.file0 + gg.nfiles,
+                     [&](int x, int y) { return b->files[x].rframe_cap > b->files[y].rframe_cap; });
   b->pcm_bytes = pcm_off; b->mono_samples = mono_off; b->mono_src_samples = src_off;
   b->TF = (int)tf; b->TFr = (int)tfr;
 
@@ -574,6 +581,7 @@ extern "C" int afx_batch_upload(afx_batch* b)
   const size_t nrb = b->rs_blocks.size(), nck = b->rs_chk.size();
   const size_t p_rb = place(nrb * sizeof(RsBlock)), p_rbf = place(nrb * 4), p_chk = place(nck * 8);
   const size_t p_inj = place(b->inject.size() * sizeof(AfxInject));
+  const size_t p_order = place((size_t)n * 4);
   take_cached(b->h_plan, ctx->h_plan_cache, po);
   CK(b->h_plan.reserve(po + 256), "cudaHostAlloc(plan)");
   CK(ctx->d_plan.reserve(po + 256), "cudaMalloc(plan)");
@@ -585,6 +593,7 @@ extern "C" int afx_batch_upload(afx_batch* b)
   if (nrb) { memcpy(hp + p_rb, b->rs_blocks.data(), nrb * sizeof(RsBlock)); memcpy(hp + p_rbf, b->rs_blk_file.data(), nrb * 4); }
   if (nck) memcpy(hp + p_chk, b->rs_chk.data(), nck * 8);
   if (!b->inject.empty()) memcpy(hp + p_inj, b->inject.data(), b->inject.size() * sizeof(AfxInject));
+  if (n) memcpy(hp + p_order, b->file_order.data(), (size_t)n * 4);
 
   CK(cudaEventRecord(b->ev[0], ctx->stream), "cudaEventRecord");
   CK(cudaMemcpyAsync(ctx->d_plan.p, hp, po, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(plan)");
@@ -603,6 +612,7 @@ extern "C" int afx_batch_upload(afx_batch* b)
   D.pcm = (const unsigned char*)ctx->d_pcm.p; D.mono = (float*)ctx->d_mono.p; D.mono_src = (float*)ctx->d_mono_src.p;
   D.files = (const AfxFile*)(dp + p_files); D.state = (AfxState*)ctx->d_state.p;
   D.inject = b->inject.empty() ? nullptr : (const AfxInject*)(dp + p_inj);
+  D.file_order = (const int*)(dp + p_order);
   D.mag = (double*)ctx->d_mag.p; D.cent_full = (double*)ctx->d_cent.p; D.fs = (double*)ctx->d_fs.p; D.fsr = (double*)ctx->d_fsr.p;
   D.fv = (double*)ctx->d_fv.p; D.rpolar = (float*)ctx->d_rpolar.p; D.rodf = (float*)ctx->d_rodf.p; D.rpost = (float*)ctx->d_rpost.p; D.bandraw = (double*)ctx->d_bandraw.p;
   D.slot_file = (const int*)ctx->d_slotmap.p; D.rslot_file = (const int*)ctx->d_slotmap.p + TF + 1;

@@ -263,6 +263,7 @@ struct AfxBatchDev {
   const AfxFile* files;
   const AfxInject* inject;  // null unless a file of the batch was conditioned in parts
   AfxState* state;
+  const int* file_order;  // [n_files] per launch group [file0, file0 + g_files): the group's files, longest first -- CTA i of a per-file kernel takes file_order[file0 + i]
   const int* slot_file;   // [TF]  main frame slot -> file index (built on the device by k_slotmap)
   const int* rslot_file;  // [TFr] rhythm frame slot -> file index
   double* mag;        // [g_slots][1024]   (group scratch, indexed by slot - slot0)

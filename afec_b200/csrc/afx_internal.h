@@ -93,6 +93,7 @@ struct afx_batch {
   struct Tail { long long off; long long count; }; std::vector<Tail> rs_tails;   // mono samples libresample never writes
   struct Group { int file0, nfiles, slot0, nslots, rslot0, nrslots; };
   std::vector<Group> groups;
+  std::vector<int> file_order;        // per launch group: its file indices, longest first (per-file kernels start the long ones early)
   int max_gslots = 0, max_grslots = 0, max_fr = 0, rs_smem = 0;
   struct CopyRun { const unsigned char* host; size_t dev_off; size_t bytes; bool to_mono; };
   std::vector<AfxInject> inject;      // conditioning reductions made elsewhere (files conditioned in parts)

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(PF * 16, 5) k_rhythm_polar(AfxBatchDev B, AfxP
 // adaptive-max whitening (OnsetDetector.cpp:193-243): psp is a per-bin recurrence over the file's frames
 __global__ void __launch_bounds__(256) k_rhythm_whiten(AfxBatchDev B, AfxParams P)
 {
-  const int fi = B.file0 + blockIdx.x;
+  const int fi = B.file_order[B.file0 + blockIdx.x];
   const AfxFile f = B.files[fi];
   if (f.status != 0) return;
   const int Fr = B.state[fi].Fr;
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(BT_THREADS) k_rhythm_back(AfxBatchDev B, AfxPa
   __shared__ double res[2][2];      // [type][tempo, confidence]
 
   const int tid = threadIdx.x;
-  const int fi = B.file0 + blockIdx.x;
+  const int fi = B.file_order[B.file0 + blockIdx.x];
   const AfxFile f = B.files[fi];
   if (f.status != 0) return;
   const int n = B.state[fi].Fr;
