@@ -260,7 +260,9 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
   sync();                                            // mag[] is complete
 
   // ---- one pass over the analysis window (bins first_bin .. first_bin + nbins - 1, nbins <= 768): thread gt owns
-  // window bins j = gt + 64 c for the power sums and the 12 consecutive bins 12 gt .. 12 gt + 11 for the rolloff --------
+  // window bins j = gt + 64 c for the power sums and the RB consecutive bins RB gt .. RB gt + RB - 1 for the rolloff.
+  // RB = 13 (not 12): an odd count of doubles between the lanes' runs spreads them over 16 bank pairs (2-way, the
+  // minimum for 64-bit loads); 12 put all 32 lanes on 4 (8-way) ------------------------------------------------------
   const int nb = P.nbins, fb = P.first_bin;
   const double dj0 = (double)gt;
   // spectral flux (Statistics.cpp:578-638, SA.cpp:936-940, 1919-1933) = Pearson correlation with the previous
@@ -269,7 +271,8 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
   // k_flux, which runs after this kernel over those slots only.
   const bool flux_here = rel > rel0 || t == 0;
   const bool flux_prev = rel > rel0 && t > 0;
-  double mj[12], pj[12], m12[12], loc = 0.0;
+  constexpr int RB = 13;
+  double mj[12], pj[12], m12[RB], loc = 0.0;
 #pragma unroll
   for (int c = 0; c < 12; ++c) pj[c] = (flux_prev && gt + SG * c < nb) ? __ldcg(gmag - AFX_NBIN + fb + gt + SG * c) : 0.0;
 #pragma unroll
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
     acc[5] = log(mant) + (double)ex * 0.693147180559945309417;
   }
 #pragma unroll
-  for (int q = 0; q < 12; ++q) { m12[q] = (12 * gt + q < nb) ? mag[fb + 12 * gt + q] : 0.0; loc += m12[q]; }
+  for (int q = 0; q < RB; ++q) { m12[q] = (RB * gt + q < nb) ? mag[fb + RB * gt + q] : 0.0; loc += m12[q]; }
   double inc = loc;                                  // rolloff: inclusive scan of the 12-bin sums inside the warp
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const double pv = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += pv; }
@@ -300,10 +303,10 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
   {
     // rolloff (LibXtract scalar.c:472-493): count of prefixes below 85 % of the total
     const double pivot = S1 * (85.0 / 100.0);
-    double pre = ((gw == 1) ? xch[18] : 0.0) + inc - loc;     // exclusive prefix = sum of the window bins before 12 gt
+    double pre = ((gw == 1) ? xch[18] : 0.0) + inc - loc;     // exclusive prefix = sum of the window bins before RB gt
     int cnt = 0;
 #pragma unroll
-    for (int q = 0; q < 12; ++q) if (12 * gt + q < nb) { cnt += (pre < pivot) ? 1 : 0; pre += m12[q]; }
+    for (int q = 0; q < RB; ++q) if (RB * gt + q < nb) { cnt += (pre < pivot) ? 1 : 0; pre += m12[q]; }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0) reinterpret_cast<int*>(xch + 19)[gw] = cnt;                // published by the next group_sum
   }
@@ -348,16 +351,17 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
 }
 
 // spectral flux = Pearson correlation with the previous frame's spectrum (first frame: itself),
-// Statistics.cpp:578-638, SA.cpp:936-940, 1919-1933.  64 threads per frame, 4 frames per CTA, with the summation
-// order of k_spectrum's fused flux (window bin j = gt + 64 c in c order, xor butterfly, warp 0 + warp 1), so a frame's
-// flux does not depend on which of the two kernels produced it.
-// `stride`: 1 = every slot; SCH = only the first slot of every chunk of the persistent k_spectrum (the others got
-// their flux there).
+// Statistics.cpp:578-638, SA.cpp:936-940, 1919-1933.  TPF = 64 threads per frame (two warps, as k_spectrum's frame
+// groups), 256 / TPF frames per CTA, with the summation order of k_spectrum's fused flux (window bin j = gt + TPF c in
+// c order, xor butterfly, warp 0 + warp 1), so a frame's flux does not depend on which of the two kernels produced it.
+// `stride`: the persistent spectrum kernels leave the first slot of every chunk of `stride` slots to this kernel.
+template <int TPF>
 __global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P, int stride)
 {
-  __shared__ double xs[4][5][2];
-  const int g = threadIdx.x >> 6, gt = threadIdx.x & 63, lane = gt & 31, gw = gt >> 5;
-  const int slot = B.slot0 + (blockIdx.x * 4 + g) * stride;
+  constexpr int FPC = 256 / TPF, NC = 768 / TPF;
+  __shared__ double xs[FPC][5][2];
+  const int g = threadIdx.x / TPF, gt = threadIdx.x % TPF, lane = gt & 31, gw = gt >> 5;
+  const int slot = B.slot0 + (blockIdx.x * FPC + g) * stride;
   bool live = slot < B.slot0 + B.g_slots;
   int t = 0;
   if (live) {
@@ -370,22 +374,24 @@ __global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P, int st
     const double* a = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN + P.first_bin;
     const double* b = (t > 0) ? a - AFX_NBIN : a;
 #pragma unroll
-    for (int c = 0; c < 12; ++c) {
-      const int j = gt + 64 * c;
+    for (int c = 0; c < NC; ++c) {
+      const int j = gt + TPF * c;
       const double x = (j < P.nbins) ? a[j] : 0.0, y = (j < P.nbins) ? b[j] : 0.0;
       v[0] += x; v[1] = fma(x, x, v[1]); v[2] += y; v[3] = fma(y, y, v[3]); v[4] = fma(x, y, v[4]);
     }
   }
 #pragma unroll
   for (int k = 0; k < 5; ++k) v[k] = warp_sum(v[k]);
-  if (lane == 0) {
+  if (TPF == 64) {
+    if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) xs[g][k][gw] = v[k];
+      for (int k = 0; k < 5; ++k) xs[g][k][gw] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v[k] = xs[g][k][0] + xs[g][k][1];
   }
-  __syncthreads();
-  if (live && gt == 0)
-    B.fs[(size_t)FS_SPEC_FLUX * B.TF + slot] = flux_from_sums(xs[g][0][0] + xs[g][0][1], xs[g][1][0] + xs[g][1][1], xs[g][2][0] + xs[g][2][1],
-                                                              xs[g][3][0] + xs[g][3][1], xs[g][4][0] + xs[g][4][1], (double)P.nbins);
+  if (live && gt == 0) B.fs[(size_t)FS_SPEC_FLUX * B.TF + slot] = flux_from_sums(v[0], v[1], v[2], v[3], v[4], (double)P.nbins);
 }
 
 template <int NG>
@@ -407,5 +413,5 @@ void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned feat
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   launch_spectrum_p<10>(P, B, features, s, sms); ++*launches;
   const int stride = SCH, nflux = (B.g_slots + stride - 1) / stride;
-  k_flux<<<(nflux + 3) / 4, 256, 0, s>>>(B, P, stride); ++*launches;
+  k_flux<64><<<(nflux + 3) / 4, 256, 0, s>>>(B, P, stride); ++*launches;
 }
