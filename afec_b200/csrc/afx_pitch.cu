@@ -36,8 +36,7 @@ template <int NG>
 struct PitchSmem {
   static constexpr int BUF = YN + YN / 16;                             // double2 per group
   static constexpr int YIN = YW + YW / 8 + 8;                          // doubles per group
-  static constexpr int HBUF = YW + YW / 16;                            // double2 per group: the half-size inverse transform
-  static constexpr size_t group_bytes = (size_t)(BUF + HBUF) * sizeof(double2) + (size_t)YIN * sizeof(double) + 40 * sizeof(double);
+  static constexpr size_t group_bytes = (size_t)BUF * sizeof(double2) + (size_t)YIN * sizeof(double) + 40 * sizeof(double);
   static constexpr size_t o_t2 = (size_t)NG * group_bytes;            // [15][16]
   static constexpr size_t o_t3 = o_t2 + 240 * sizeof(double2);        // [7][256]
   static constexpr size_t bytes = o_t3 + 7 * 256 * sizeof(double2);
@@ -76,8 +75,8 @@ __global__ void __launch_bounds__(YT * NG, 1) k_pitch(AfxBatchDev B, AfxParams P
   unsigned char* gbase = smem_raw + (size_t)g * L::group_bytes;
   double2* buf = reinterpret_cast<double2*>(gbase);                    // [2048 + 128]
   double* S = reinterpret_cast<double*>(buf);                          // [PAD16(2048) + 1] prefix sums of squares (before the FFTs)
-  double2* hbuf = buf + L::BUF;                                        // [1024 + 64]
-  double* yin = reinterpret_cast<double*>(hbuf + L::HBUF);             // [PAD8(1024)]
+  double2* hbuf = buf;                                                 // the half-size inverse runs in the first half of buf
+  double* yin = reinterpret_cast<double*>(buf + L::BUF);               // [PAD8(1024)]
   double* scratch = yin + L::YIN;                                      // [8] scans / argmin
   double* level = scratch + 8;                                         // [2] sum of squares of the frame / of the hop
   int* iscr = reinterpret_cast<int*>(scratch + 12);                    // [8] argmin / first dip
@@ -171,9 +170,10 @@ __global__ void __launch_bounds__(YT * NG, 1) k_pitch(AfxBatchDev B, AfxParams P
     // ---- r = IFFT_2048(P), P[k] = conj(A[k]) B[k] with A, B the transforms of a and b split out of Z.  r is real, so
     // the inverse runs at HALF size (Hermitian P): with z[m] = r[2m] + i r[2m+1],
     //   z = IFFT_1024(Zc),  Zc[k] = (P[k] + conj(P[1024-k])) / 2 + i W^-k (P[k] - conj(P[1024-k])) / 2,  W = exp(-2 pi i / 2048).
-    // All 128 threads build Zc pairwise (k, 1024 - k share P[k] and P[1024-k]) into hbuf; 64 threads then run the
-    // 1024-point transform (as conj(FFT(conj(Zc))) / 1024) -- a quarter of the shared-memory traffic of the full-size
-    // inverse, which is what bounds this kernel.
+    // All 128 threads build Zc pairwise (k, 1024 - k share P[k] and P[1024-k]) IN PLACE: a pair reads Z at
+    // {k, 1024-k, 1024+k, 2048-k} -- no other pair touches these -- and overwrites slots k and 1024-k.  64 threads then
+    // run the 1024-point transform (as conj(FFT(conj(Zc))) / 1024) in the first half of the buffer -- a quarter of the
+    // shared-memory traffic of the full-size inverse, which is what bounds this kernel.
     {
       auto pk = [&](int k, int kc) {                              // P[k] from Z[k] and Z[kc], kc = (2048 - k) mod 2048
         const double2 z1 = buf[FFT_PHYS(k)], z2 = buf[FFT_PHYS(kc)];
@@ -311,6 +311,6 @@ static void launch_pitch_t(const AfxParams& P, const AfxBatchDev& B, cudaStream_
 void afx_launch_pitch(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  launch_pitch_t<3>(P, B, s);      // 3 groups: 164 registers per thread, no spills (4 groups at 128 registers measured 6 % slower)
+  launch_pitch_t<3>(P, B, s);      // 3 groups: 168 registers per thread, no spills (4 groups at 128 registers measured 6 % slower)
   ++*launches;
 }
