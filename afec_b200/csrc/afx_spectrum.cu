@@ -73,29 +73,32 @@ __device__ __forceinline__ double group_max(double v, double* xch, int gt, Sync 
 // their own samples from the incoming state.
 template <int PER, class Sync>
 __device__ __forceinline__ void amp_features(const AfxBatchDev& B, const AfxParams& P, const float* __restrict__ mono, const AfxState& st,
-                                             int n0, int slot, int gt, double* xch, Sync sync)
+                                             int n0, int slot, int gt, int per, double* xch, Sync sync)
 {
+  const int np = (PER == 32) ? per : PER;             // PER = 32 also serves the other hop sizes (12, 20, 24, 28 samples per thread)
   const int lane = gt & 31, gw = gt >> 5;
   const double c = P.env_coef;
   float xf[PER];
   {
-    const int j0 = n0 + gt * PER - st.start_off;
+    const int j0 = n0 + gt * np - st.start_off;
     const float* __restrict__ src = mono + st.lead + j0;
-    if (j0 >= 0 && j0 + PER <= st.audible) {
+    if (j0 >= 0 && j0 + np <= st.audible) {
 #pragma unroll
-      for (int q = 0; q < PER; ++q) xf[q] = __ldg(src + q);
+      for (int q = 0; q < PER; ++q) xf[q] = (q < np) ? __ldg(src + q) : 0.0f;
     } else {
 #pragma unroll
-      for (int q = 0; q < PER; ++q) xf[q] = (j0 + q >= 0 && j0 + q < st.audible) ? __ldg(src + q) : 0.0f;
+      for (int q = 0; q < PER; ++q) xf[q] = (q < np && j0 + q >= 0 && j0 + q < st.audible) ? __ldg(src + q) : 0.0f;
     }
   }
   double A = 1.0, Bv = 0.0, e_hop = 0.0, pk_hop = 0.0;
 #pragma unroll
   for (int q = 0; q < PER; ++q) {
-    const double xv = (double)xf[q] * st.fs, a = fabs(xv);     // mdata()
-    e_hop += xv * xv; pk_hop = fmax(pk_hop, a);
-    Bv = a + c * (Bv - a);
-    A *= c;
+    if (q < np) {
+      const double xv = (double)xf[q] * st.fs, a = fabs(xv);     // mdata()
+      e_hop += xv * xv; pk_hop = fmax(pk_hop, a);
+      Bv = a + c * (Bv - a);
+      A *= c;
+    }
   }
   double sA = A, sB = Bv;                           // inclusive scan inside the warp
 #pragma unroll
@@ -111,7 +114,7 @@ __device__ __forceinline__ void amp_features(const AfxBatchDev& B, const AfxPara
   if (lane > 0) s_in = pA * s_in + pB;
   double env = s_in, emax = 0.0;
 #pragma unroll
-  for (int q = 0; q < PER; ++q) { const double a = fabs((double)xf[q] * st.fs); env = a + c * (env - a); emax = fmax(emax, env); }
+  for (int q = 0; q < PER; ++q) if (q < np) { const double a = fabs((double)xf[q] * st.fs); env = a + c * (env - a); emax = fmax(emax, env); }
   // one exchange for both maxima
   pk_hop = warp_max(pk_hop); emax = warp_max(emax);
   if (lane == 0) { xch[8 + gw] = pk_hop; xch[10 + gw] = emax; }
@@ -194,11 +197,10 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
 
   // ---- amplitude features of the hop slice (SA.cpp:865-873): H / 64 consecutive samples per thread --------
   if (features & AFX_FEAT_AMPLITUDE) {
-    const int per = P.H / SG;                         // 4, 8, 16 or 32 (hop is a multiple of 256)
-    if (per == 16) amp_features<16>(B, P, mono, st, n0, slot, gt, xch, sync);
-    else if (per == 8) amp_features<8>(B, P, mono, st, n0, slot, gt, xch, sync);
-    else if (per == 4) amp_features<4>(B, P, mono, st, n0, slot, gt, xch, sync);
-    else amp_features<32>(B, P, mono, st, n0, slot, gt, xch, sync);
+    const int per = P.H / SG;                         // 4, 8, ..., 32 (hop is a multiple of 256)
+    if (per == 16) amp_features<16>(B, P, mono, st, n0, slot, gt, per, xch, sync);
+    else if (per == 8) amp_features<8>(B, P, mono, st, n0, slot, gt, per, xch, sync);
+    else amp_features<32>(B, P, mono, st, n0, slot, gt, per, xch, sync);         // 4, 12, 20, 24, 28 or 32 samples per thread
   }
 
   // ---- load, window, pack (even -> re, odd -> im) in the FFT's strided order; transform ---------------------

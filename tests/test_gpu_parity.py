@@ -82,7 +82,7 @@ def test_golden_reference_vectors(analysers, feats, case):
     check(got, case["ref"], feats)
 
 
-@pytest.mark.parametrize("hop", [1024, 512])
+@pytest.mark.parametrize("hop", [1024, 512, 768, 256, 2048])      # every samples-per-thread class of the amplitude features
 def test_batch_vs_oracle(analysers, feats, oracle_lib, hop):
     """A mixed batch (ragged lengths, stereo, tiny, silent) in ONE call vs the oracle file by file."""
     pcms = [synth.one_shot(400 + i, 0.3 + 0.4 * i) for i in range(6)]
