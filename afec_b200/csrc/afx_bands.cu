@@ -16,6 +16,8 @@
 // magnitudes with 32-bit integer compares and warp vote/reduce -- the FP64 pipe is left to the arithmetic.
 // Bands of <= 32 bins rank their elements against each other with shuffles instead.
 #include "afx_common.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 #define BT 256
 
@@ -195,7 +197,8 @@ __device__ __forceinline__ void bands28(AfxBatchDev& B, const AfxParams& P, size
 // many short loops over the row (nine small sub-bands, mel filters, the 28 bands): there every warp first copies its
 // frame's magnitude row to shared memory with all loads in flight at once -- as dependent global loads those loops
 // were 44 % long-scoreboard stalls.
-__global__ void __launch_bounds__(BT) k_bands_a_big(AfxBatchDev B, AfxParams P)
+template <int MINB>
+__global__ void __launch_bounds__(BT, MINB) k_bands_a_big(AfxBatchDev B, AfxParams P)
 {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int rel = blockIdx.x * 8 + wid;
@@ -216,9 +219,13 @@ __global__ void __launch_bounds__(BT) k_bands_a_big(AfxBatchDev B, AfxParams P)
   }
 }
 
-__global__ void __launch_bounds__(BT) k_bands_a_small(AfxBatchDev B, AfxParams P)
+// One launch per role; NSTAGE = how much of the row the role reads (role 0: sub-bands 0..1 + the lower 14 of the 28
+// bands end below bin 128; roles 2 / 3: sub-bands 5..8 and the mel filters end below 384; role 1 takes the upper 14 bands
+// up to bin 1024).  A short stage leaves room for more CTAs per SM -- these roles are latency bound.
+template <int NSTAGE>
+__global__ void __launch_bounds__(BT) k_bands_a_small(AfxBatchDev B, AfxParams P, int role)
 {
-  extern __shared__ __align__(16) double srow[];            // [8][1024]
+  extern __shared__ __align__(16) double srow[];            // [8][NSTAGE]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int rel = blockIdx.x * 8 + wid;
   if (rel >= B.g_slots) return;
@@ -229,19 +236,18 @@ __global__ void __launch_bounds__(BT) k_bands_a_small(AfxBatchDev B, AfxParams P
   const size_t TF = (size_t)B.TF;
   const double* __restrict__ gg = B.mag + (size_t)rel * AFX_NBIN;
   const double* __restrict__ gp = (t > 0) ? gg - AFX_NBIN : gg;            // SampleAnalyser.cpp:936-940
-  double* g = srow + wid * AFX_NBIN;
+  double* g = srow + wid * NSTAGE;
   {
     const double2* src = reinterpret_cast<const double2*>(gg);
-    double2 tmp[16];
+    double2 tmp[NSTAGE / 64];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) tmp[q] = src[lane + 32 * q];
+    for (int q = 0; q < NSTAGE / 64; ++q) tmp[q] = src[lane + 32 * q];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) reinterpret_cast<double2*>(g)[lane + 32 * q] = tmp[q];
+    for (int q = 0; q < NSTAGE / 64; ++q) reinterpret_cast<double2*>(g)[lane + 32 * q] = tmp[q];
   }
   __syncwarp();
   BandRaw* raw = reinterpret_cast<BandRaw*>(B.bandraw + (size_t)rel * BR_STRIDE);
   double* lg = B.bandraw + (size_t)rel * BR_STRIDE + 140;
-  const int role = blockIdx.y;
   // roles 0..3: the nine bands of <= 32 bins (one code instance, looped), the mel energies and the 28 bands
   const int first = (role == 3) ? 7 : (role == 2) ? 5 : (role == 1) ? 2 : 0;
   const int last = (role == 3) ? 8 : (role == 2) ? 6 : (role == 1) ? 4 : 1;
@@ -287,9 +293,24 @@ __global__ void __launch_bounds__(BT) k_bands_b(AfxBatchDev B, AfxParams P)
 void afx_launch_bands(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  const int smem = 8 * AFX_NBIN * (int)sizeof(double);
-  cudaFuncSetAttribute(k_bands_a_small, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device, see afx_pitch.cu
-  k_bands_a_big<<<dim3((B.g_slots + 7) / 8, 4), BT, 0, s>>>(B, P); ++*launches;
-  k_bands_a_small<<<dim3((B.g_slots + 7) / 8, 4), BT, smem, s>>>(B, P); ++*launches;
+  static const int minb = getenv("AFX_BANDS_MINB") ? atoi(getenv("AFX_BANDS_MINB")) : 6;
+  if (minb == 4) k_bands_a_big<4><<<dim3((B.g_slots + 7) / 8, 4), BT, 0, s>>>(B, P);
+  else if (minb == 5) k_bands_a_big<5><<<dim3((B.g_slots + 7) / 8, 4), BT, 0, s>>>(B, P);
+  else k_bands_a_big<6><<<dim3((B.g_slots + 7) / 8, 4), BT, 0, s>>>(B, P);
+  ++*launches;
+  cudaFuncSetAttribute(k_bands_a_small<AFX_NBIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * AFX_NBIN * (int)sizeof(double));   // per device, see afx_pitch.cu
+  for (int role = 0; role < 4; ++role) {
+    // highest bin the role reads (+1: the complexity test looks at a bin's neighbours)
+    const int first = (role == 3) ? 7 : (role == 2) ? 5 : (role == 1) ? 2 : 0, last = (role == 3) ? 8 : (role == 2) ? 6 : (role == 1) ? 4 : 1;
+    int need = 0;
+    for (int b = first; b <= last; ++b) need = std::max(need, P.band14_start[b] + P.band14_n[b] + 2);
+    if (role >= 2) { for (int q = (role == 3 ? 8 : 0); q < (role == 3 ? 12 : 8); ++q) need = std::max(need, P.mel_hi[q] + 1); }
+    else for (int b = (role == 1 ? 14 : 0); b < (role == 1 ? 28 : 14); ++b) need = std::max(need, P.band28_e[b]);
+    const dim3 grid((B.g_slots + 7) / 8);
+    if (need <= 128) k_bands_a_small<128><<<grid, BT, 8 * 128 * sizeof(double), s>>>(B, P, role);
+    else if (need <= 384) k_bands_a_small<384><<<grid, BT, 8 * 384 * sizeof(double), s>>>(B, P, role);
+    else k_bands_a_small<AFX_NBIN><<<grid, BT, 8 * AFX_NBIN * sizeof(double), s>>>(B, P, role);
+    ++*launches;
+  }
   k_bands_b<<<(B.g_slots * 16 + BT - 1) / BT, BT, 0, s>>>(B, P); ++*launches;
 }
