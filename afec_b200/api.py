@@ -21,7 +21,7 @@ FEAT_ALL = 0xFF
 HAVE_RESAMPLE = True   # k_resample + host block plan (libresample HQ restatement)
 
 EXPORTS = [
-    "afx_abi_version", "afx_create", "afx_destroy", "afx_last_error", "afx_host_alloc", "afx_host_free",
+    "afx_abi_version", "afx_create", "afx_destroy", "afx_last_error", "afx_trim", "afx_host_alloc", "afx_host_free",
     "afx_batch_create", "afx_batch_upload", "afx_batch_compute", "afx_batch_download", "afx_batch_sync",
     "afx_analyze", "afx_batch_result", "afx_batch_free", "afx_batch_timings", "afx_batch_counters",
     "afx_batch_kernel_times", "afx_batch_conditioned", "afx_measure_fp64_peak", "afx_debug_fft",
@@ -77,6 +77,7 @@ def load_library():
     L.afx_destroy.argtypes = [C.c_void_p]
     L.afx_destroy.restype = None
     L.afx_last_error.argtypes = [C.c_void_p]
+    L.afx_trim.argtypes = [C.c_void_p]
     L.afx_last_error.restype = C.c_char_p
     L.afx_host_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     L.afx_host_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -295,6 +296,10 @@ class SampleAnalyser:
 
     def pinned(self, nbytes: int) -> PinnedArena:
         return PinnedArena(self, nbytes)
+
+    def trim(self):
+        """Release the context's device buffers (they grow again on demand)."""
+        self._check(self._L.afx_trim(self._ctx))
 
     def close(self):
         if self._ctx:

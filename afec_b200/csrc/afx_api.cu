@@ -370,6 +370,23 @@ extern "C" void afx_destroy(afx_ctx* ctx)
   delete ctx;
 }
 
+extern "C" int afx_trim(afx_ctx* ctx)
+{
+  if (!ctx) return AFX_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamSynchronize(ctx->side[i]);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
+  if (e != cudaSuccess) return fail(ctx, AFX_ERR_CUDA, "afx_trim", e);
+  DevBuf* bufs[] = { &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
+    &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch };
+  for (DevBuf* b : bufs) b->release();
+  for (auto& pb : ctx->part_pool) pb.release();
+  ctx->part_pool.clear();
+  return AFX_OK;
+}
+
 extern "C" int afx_host_alloc(afx_ctx* ctx, uint64_t bytes, void** out)
 {
   if (!ctx || !out) return AFX_ERR_ARG;

@@ -69,7 +69,7 @@ struct afx_ctx {
   DevBuf tables;                      // all constant tables in one allocation
   DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf, d_rpost, d_bandraw, d_slotmap,
          d_stats, d_header, d_plan, d_scratch;
-  long long group_frames = 393216, group_rframes = 3145728;   // per-launch scratch bound: 3 GB mag, 6 GB rpolar
+  long long group_frames = 1572864, group_rframes = 12582912;   // per-launch scratch bound: 12 GB mag, 24 GB rpolar (allocated by need). Large groups matter to the per-file kernels: 4x the files in flight took 17 % off the rhythm chain
   PinBuf h_results_cache, h_plan_cache;   // recycled between batches
   std::vector<PartBufs> part_pool;        // recycled between part jobs
   std::vector<double> zeros;          // backing store of the all-zero series

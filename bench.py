@@ -473,6 +473,7 @@ def main():
     e2e_value = total_audio_hours * args.steps / e2e_s
     for sl in slots[1:]:
         sl.close()
+    an.trim()          # the roofline leg below runs the same batch on a second context: give this one's device buffers back
 
     # ---- roofline of the dominant kernel (k_spectrum), timed live with CUDA events ---------------
     roof = None

@@ -108,6 +108,11 @@ int afx_abi_version(void);
 int afx_create(const afx_config* cfg, afx_ctx** out);
 void afx_destroy(afx_ctx* ctx);
 const char* afx_last_error(const afx_ctx* ctx);   /* ctx may be NULL: last afx_create failure */
+/* Give the context's device buffers back to the driver (they grow again on demand; constant tables, streams and
+ * pinned host memory stay).  The reference has no counterpart: TSampleAnalyser::Extract frees its temporaries per
+ * file (SampleAnalyser.cpp:372-408); here buffers are kept across batches and this is the explicit release between
+ * crawls.  Waits for the context's streams; no batch of the context may be alive. */
+int afx_trim(afx_ctx* ctx);
 
 /* pinned host memory for decode threads (ring slots); H2D copies from it are asynchronous */
 int afx_host_alloc(afx_ctx* ctx, uint64_t bytes, void** out);

@@ -131,6 +131,23 @@ def test_empty_batch(analysers):
     assert analysers(1024).analyze_pcm([], []) == []
 
 
+def test_trim_releases_and_regrows(feats):
+    """afx_trim gives the device buffers back; the next batch grows them again and computes the same bits."""
+    import torch
+    an = api.SampleAnalyser(44100, 2048, 1024, features=feats)
+    pcms = [synth.one_shot(600 + i, 1.0 + i) for i in range(4)]
+    first = an.analyze_pcm(pcms, [44100] * 4)
+    used = torch.cuda.mem_get_info()[0]
+    an.trim()
+    assert torch.cuda.mem_get_info()[0] > used          # free memory went up
+    again = an.analyze_pcm(pcms, [44100] * 4)
+    for a, b in zip(first, again):
+        assert (a.F, a.Fr) == (b.F, b.Fr)
+        for x, y in zip(a.fs, b.fs):
+            assert np.array_equal(x, y)
+    an.close()
+
+
 def test_large_batch_properties(analysers, feats):
     """Size-independent properties at bench scale: identical files give identical rows; results do not
     depend on batch composition or order."""
