@@ -131,6 +131,19 @@ def test_empty_batch(analysers):
     assert analysers(1024).analyze_pcm([], []) == []
 
 
+def test_impulse_tail_frames(analysers, feats, oracle_lib):
+    """A decayed tail whose frames hold a single LSB tick: flat spectra, peak counts decided by FFT rounding (parity.py
+    rule, found by profiles/parity_sweep.py with this very file); everything else of the file must still agree."""
+    rate = 44100                                               # file 85 of the sweep's seed-5000 corpus: a quiet stereo one-shot
+    x = synth.one_shot(5085, 3.041115350932388, rate=rate, channels=2)
+    pcm = np.ascontiguousarray((x.astype(np.float64) * 0.03786796017229539).astype(np.int16))
+    data = oracle_lib.condition(pcm, src_rate=rate)[0]
+    assert parity.impulse_frames(data, 1024, (len(data) - 2048) // 1024 + 1).any()
+    got = analysers(1024).analyze_pcm([pcm], [rate])[0]
+    want = oracle_lib.analyze(pcm, src_rate=rate, file_size=44 + pcm.size * 2)
+    check(got, want, feats, mdata=data)
+
+
 def test_trim_releases_and_regrows(feats):
     """afx_trim gives the device buffers back; the next batch grows them again and computes the same bits."""
     import torch
