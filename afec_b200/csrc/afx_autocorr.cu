@@ -15,7 +15,7 @@
 // lag x sample work is spread over the lanes.
 #include "afx_common.cuh"
 
-#define AW 8                // warps (frames) per CTA
+#define AW 4                // warps (frames) per CTA
 #define AL 9                // lags per lane task
 #define AC_MAXW 544         // >= ac_width (529) + AL, multiple of 8
 #define AC_XS 696           // window + zero padding: a round reads up to width + 75; idle lanes read zeros from AC_ZERO on

@@ -17,7 +17,6 @@
 // Bands of <= 32 bins rank their elements against each other with shuffles instead.
 #include "afx_common.cuh"
 #include <algorithm>
-#include <cstdlib>
 
 #define BT 256
 
@@ -293,11 +292,9 @@ __global__ void __launch_bounds__(BT) k_bands_b(AfxBatchDev B, AfxParams P)
 void afx_launch_bands(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  static const int minb = getenv("AFX_BANDS_MINB") ? atoi(getenv("AFX_BANDS_MINB")) : 6;
-  if (minb == 4) k_bands_a_big<4><<<dim3((B.g_slots + 7) / 8, 4), BT, 0, s>>>(B, P);
-  else if (minb == 5) k_bands_a_big<5><<<dim3((B.g_slots + 7) / 8, 4), BT, 0, s>>>(B, P);
-  else k_bands_a_big<6><<<dim3((B.g_slots + 7) / 8, 4), BT, 0, s>>>(B, P);
-  ++*launches;
+  // 6 CTAs per SM (40 registers, a few spilled words): these roles wait on global loads, residency beats registers
+  // (measured 4 / 5 / 6 CTAs: 4.98 / 4.82 / 4.74 ms per 248k frames)
+  k_bands_a_big<6><<<dim3((B.g_slots + 7) / 8, 4), BT, 0, s>>>(B, P); ++*launches;
   cudaFuncSetAttribute(k_bands_a_small<AFX_NBIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * AFX_NBIN * (int)sizeof(double));   // per device, see afx_pitch.cu
   for (int role = 0; role < 4; ++role) {
     // highest bin the role reads (+1: the complexity test looks at a bin's neighbours)
