@@ -1,0 +1,34 @@
+"""The frame classifiers behind the documented parity exclusions (tests/parity.py), on hand-made signals."""
+import numpy as np
+
+import parity
+
+
+def test_impulse_frames_are_exactly_the_single_sample_frames():
+    hop, N = 1024, 2048
+    x = np.zeros(hop * 6 + N)
+    x[:N] = 0.1                       # frame 0 (and the first half of frame 1) full of signal
+    x[hop * 4 + 7] = 3.0e-5           # one LSB tick: frames 3 and 4 see it alone
+    F = (len(x) - N) // hop + 1
+    got = parity.impulse_frames(x, hop, F)
+    want = np.zeros(F, dtype=bool)
+    want[[3, 4]] = True
+    assert np.array_equal(got, want)
+    # two ticks in the same frame are not an impulse frame
+    x[hop * 4 + 900] = -3.0e-5
+    assert not parity.impulse_frames(x, hop, F)[3:5].any()
+
+
+def test_half_silent_pitch_frames():
+    hop, N = 1024, 2048
+    x = np.zeros(hop * 4 + N)
+    x[hop * 2 + N // 2:] = 0.2        # frame 2: first half silent, second half not
+    F = (len(x) - N) // hop + 1
+    got = parity.ill_conditioned_pitch_frames(x, hop, F)
+    assert got[2] and not got[0] and not got[3]
+
+
+def test_close_uses_the_stated_tolerance():
+    assert parity.close(1.0 + 0.9e-4, 1.0) and not parity.close(1.0 + 1.2e-4, 1.0)
+    assert parity.close(5e-7, 0.0) and not parity.close(2e-6, 0.0)
+    assert parity.close(np.nan, np.nan)
