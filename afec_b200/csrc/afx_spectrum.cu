@@ -18,12 +18,13 @@
 
 // sqrt of a squared magnitude to ~2^-44 relative: MUFU.RSQ64H seed (2^-22) + one Newton step.  The full IEEE sqrt
 // costs twice the FP64 instructions and its last 8 bits are far below what the FFT's own rounding leaves intact.
-__device__ __noinline__ double sqrt_slow(double s) { return sqrt(s); }
+// s is exactly 0 or far above the subnormals the seed instruction flushes (squares of sums of float32 samples times
+// the window: >= 1e-112), so a select on s > 0 replaces the range branch.
 __device__ __forceinline__ double sqrt_mag(double s)
 {
-  if (!(s > 0x1p-900)) return sqrt_slow(s);          // zeros / subnormal squares: the seed instruction flushes them
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+  y = (s > 0.0) ? y : 0.0;
   const double r = s * y;
   return fma(fma(-r, r, s), 0.5 * y, r);
 }
