@@ -287,9 +287,20 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
       const double m = mj[c], m2 = m * m, jm = (dj0 + (double)(SG * c)) * m;
       acc[0] += m; acc[1] = fma(m, m, acc[1]); acc[2] = fma(m2, m, acc[2]); acc[3] = fma(m2, m2, acc[3]); acc[4] += jm;
       acc[8] = fma(m, pj[c], acc[8]);
-      if (gt + SG * c < nb) mul_frexp_pos(mant, ex, fabs(m) + 1e-20);         // Statistics.cpp:417-455
+      if (gt + SG * c < nb) {                                                  // Statistics.cpp:417-455: product with the exponents peeled off
+        const double v = fabs(m) + 1e-20;
+        const int hi = __double2hiint(v);
+        ex += ((hi >> 20) & 0x7ff) - 1022;
+        mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(v));
+      }
     }
-    acc[5] = log(mant) + (double)ex * 0.693147180559945309417;
+    // log of the product = log(product of the 64 threads' mantissas) + ln 2 x (sum of their exponents): the mantissa
+    // product cannot underflow (12 factors >= 1/2 per thread: >= 2^-768 over the group), so ONE log per frame (thread 0)
+    // replaces one per thread; the exponent sum rides in the FP64 reduction (exact)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mant *= __shfl_xor_sync(0xffffffffu, mant, o);
+    if (lane == 0) xch[20 + gw] = mant;              // published by group_sum's first barrier
+    acc[5] = (double)ex;
   }
 #pragma unroll
   for (int q = 0; q < RB; ++q) { m12[q] = (RB * gt + q < nb) ? mag[fb + RB * gt + q] : 0.0; loc += m12[q]; }
@@ -334,7 +345,8 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
     B.fs[(size_t)FS_SPEC_SPREAD * TF + slot] = spread;
     B.fs[(size_t)FS_SPEC_SKEW * TF + slot] = have_sk ? mu3 / (s2 * spread) / n : 0.0;
     B.fs[(size_t)FS_SPEC_KURT * TF + slot] = have_sk ? mu4 / (s2 * s2) / n - 3.0 : 0.0;
-    const double mean = S1 / n, gmean = exp(acc[5] / n);
+    const double lsum = log(xch[20] * xch[21]) + acc[5] * 0.693147180559945309417;
+    const double mean = S1 / n, gmean = exp(lsum / n);
     const double fl = flatness_db(mean, gmean);
     B.fs[(size_t)FS_SPEC_FLATNESS * TF + slot] = (fl != fl) ? 0.0 : fl;
     B.cent_full[slot] = (acc[6] == 0.0) ? 0.0 : acc[7] / acc[6];
