@@ -24,6 +24,8 @@ __device__ __forceinline__ double warp_sum_d(double v) { return warp_sum(v); }
 
 // raw per-band sums handed from the band's warp to the epilogue lane
 struct BandRaw { double s1, s2, s11, s12, s22, ls, x0, lo_sum, hi_sum, cplx; };   // 10 doubles
+// ls / x0: for n >= 2 the band's log-sum travels as (product of the mantissas, sum of the exponents) and the ONE log per
+// band is taken by the epilogue lane; for n == 1 x0 is the band's only value (TStatistics::GeometricMean returns it)
 #define BR_STRIDE 154      // doubles per frame: 14 x BandRaw + 14 mel energies
 
 // per-band epilogue (one lane per band, all 14 in lock step so the pow / log / exp chains run once)
@@ -31,7 +33,7 @@ __device__ __forceinline__ double band_write(AfxBatchDev& B, size_t TF, int slot
 {
   const double dn = (double)n;
   const double mean = (n >= 2) ? r.s1 / dn : r.s1;          // TStatistics::Mean, Statistics.cpp:249-266
-  const double gmean = (n >= 2) ? exp(r.ls / dn) : r.x0;    // TStatistics::GeometricMean :417-455
+  const double gmean = (n >= 2) ? exp((log(r.ls) + r.x0 * 0.693147180559945309417) / dn) : r.x0;    // TStatistics::GeometricMean :417-455
   const size_t o = (size_t)slot * 14 + b;
   B.fv[(size_t)FV_RMS * TF + o] = sqrt(r.s11 / dn);
   B.fv[(size_t)FV_FLATNESS * TF + o] = flatness_db(mean, gmean);
@@ -65,12 +67,17 @@ __device__ __forceinline__ void subband(const AfxParams& P, int b, const double*
     if (valid) {
       s12 += xv * yv; s1 += xv; s11 += xv * xv; s2 += yv; s22 += yv * yv;
       mx = fmax(mx, xv);
-      mul_frexp_pos(mant, ex, fabs(xv) + 1e-20);
+      const double v = fabs(xv) + 1e-20;               // Statistics.cpp:417-455: product with the exponents peeled off
+      const int hw = __double2hiint(v);                // (C <= 9 factors >= 1/2 per lane, >= 2^-288 per warp: no rescue needed)
+      ex += ((hw >> 20) & 0x7ff) - 1022;
+      mant *= __hiloint2double((hw & 0x800fffff) | 0x3fe00000, __double2loint(v));
     }
   }
-  double ls = log(mant) + (double)ex * 0.693147180559945309417;
   s1 = warp_sum(s1); s2 = warp_sum(s2); s11 = warp_sum(s11); s12 = warp_sum(s12); s22 = warp_sum(s22);
-  ls = warp_sum(ls); mx = warp_max(mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mant *= __shfl_xor_sync(0xffffffffu, mant, o);
+  ex = __reduce_add_sync(0xffffffffu, ex);
+  mx = warp_max(mx);
   const double thr = mx * 0.25;
   int cplx = 0;
   if (thr > 0.0) {
@@ -166,7 +173,7 @@ __device__ __forceinline__ void subband(const AfxParams& P, int b, const double*
   const double x0 = __shfl_sync(0xffffffffu, x[0], 0);
   if (lane == 0) {
     BandRaw& r = raw[b];
-    r.s1 = s1; r.s2 = s2; r.s11 = s11; r.s12 = s12; r.s22 = s22; r.ls = ls; r.x0 = x0; r.lo_sum = lo_sum; r.hi_sum = hi_sum; r.cplx = (double)cplx;
+    r.s1 = s1; r.s2 = s2; r.s11 = s11; r.s12 = s12; r.s22 = s22; r.ls = mant; r.x0 = (n >= 2) ? (double)ex : x0; r.lo_sum = lo_sum; r.hi_sum = hi_sum; r.cplx = (double)cplx;
   }
 }
 
