@@ -262,6 +262,7 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   P.first_bin = d2i_round(20.0 / fpb);
   const int last_bin = d2i_round(15500.0 / fpb);
   P.nbins = last_bin - P.first_bin + 1;
+  if (P.first_bin != AFX_WIN_FIRST || P.nbins != AFX_WIN_BINS) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_ARG, "afx_create: analysis window differs from the compiled-in one"); }
   static const double b14[14] = { 50.0, 100.0, 200.0, 400.0, 630.0, 920.0, 1270.0, 1720.0, 2320.0, 3150.0, 4400.0, 6400.0, 9500.0, 15500.0 };
   static const double b28[28] = { 50.0, 100.0, 150.0, 200.0, 300.0, 400.0, 510.0, 630.0, 770.0, 920.0, 1080.0, 1270.0, 1480.0, 1720.0,
     2000.0, 2320.0, 2700.0, 3150.0, 3700.0, 4400.0, 5300.0, 6400.0, 7700.0, 9500.0, 12000.0, 15500.0, 19000.0, 22050.0 };

@@ -25,6 +25,11 @@
 #define AFX_RBINS 255
 #define AFX_RROW 512        // floats per rhythm frame row: mag[0..255], dc, nyq, pad | phase[256..511]
 #define AFX_FV_STRIDE 112
+// the analysis window of the spectral statistics: bins round(20 / 21) .. round(15500 / 21) with the reference's integer
+// FrequenciesPerBin = 44100 / 2048 = 21 (SampleAnalyser.cpp:171-175).  afx_create only accepts that rate / size and checks
+// that its table agrees, so the frame kernels may treat the bounds as compile-time constants.
+#define AFX_WIN_FIRST 1
+#define AFX_WIN_BINS 738
 
 // fs series ids (order of afec_b200/layout.py FRAMED_SCALARS)
 enum {

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
   // window bins j = gt + 64 c for the power sums and the RB consecutive bins RB gt .. RB gt + RB - 1 for the rolloff.
   // RB = 13 (not 12): an odd count of doubles between the lanes' runs spreads them over 16 bank pairs (2-way, the
   // minimum for 64-bit loads); 12 put all 32 lanes on 4 (8-way) ------------------------------------------------------
-  const int nb = P.nbins, fb = P.first_bin;
+  constexpr int nb = AFX_WIN_BINS, fb = AFX_WIN_FIRST;      // == P.nbins, P.first_bin (checked by afx_create)
   const double dj0 = (double)gt;
   // spectral flux (Statistics.cpp:578-638, SA.cpp:936-940, 1919-1933) = Pearson correlation with the previous
   // frame's window.  Inside a chunk the previous row is the one this group wrote last iteration (read back through
