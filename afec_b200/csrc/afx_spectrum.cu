@@ -157,7 +157,9 @@ struct SpecSmem {
   static constexpr size_t bytes = o_claim + (size_t)NG * 2 * sizeof(int);
 };
 
-template <int NG>
+// FULLC: also reduce the full-band sums (centroid of mag[0..1023], the pitch kernel's fail-safe f0); without the pitch
+// feature they are not computed
+template <int NG, bool FULLC>
 __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParams P, unsigned features, unsigned int* __restrict__ work_ctr)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
   double* gmag = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
   sync();                                            // everyone has read Z before buf becomes the magnitude array
   double* mag = reinterpret_cast<double*>(buf);
-  double acc[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };     // S1, S2, S3, S4, SJ, log-sum over the analysis window; full-band S, SJ; sum m * m_prev
+  double acc[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };     // S1, S2, S3, S4, SJ, log-sum over the analysis window; sum m * m_prev; full-band S, SJ
   {
     const double dgt = (double)gt;
 #pragma unroll
@@ -256,8 +258,10 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
       const double dk = dgt + (double)(SG * c), dkm = (c == 0) ? (double)kmir0 : (double)AFX_NBIN - dk;
       mag[k] = m16[c]; gmag[k] = m16[c];
       mag[km] = m16[8 + c]; gmag[km] = m16[8 + c];
-      acc[6] += m16[c] + m16[8 + c];
-      acc[7] = fma(dk, m16[c], fma(dkm, m16[8 + c], acc[7]));
+      if (FULLC) {
+        acc[7] += m16[c] + m16[8 + c];
+        acc[8] = fma(dk, m16[c], fma(dkm, m16[8 + c], acc[8]));
+      }
     }
   }
   sync();                                            // mag[] is complete
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
     for (int c = 0; c < 12; ++c) {
       const double m = mj[c], m2 = m * m, jm = (dj0 + (double)(SG * c)) * m;
       acc[0] += m; acc[1] = fma(m, m, acc[1]); acc[2] = fma(m2, m, acc[2]); acc[3] = fma(m2, m2, acc[3]); acc[4] += jm;
-      acc[8] = fma(m, pj[c], acc[8]);
+      acc[6] = fma(m, pj[c], acc[6]);
       if (gt + SG * c < nb) {                                                  // Statistics.cpp:417-455: product with the exponents peeled off
         const double v = fabs(m) + 1e-20;
         const int hi = __double2hiint(v);
@@ -308,7 +312,8 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const double pv = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += pv; }
   if (lane == 31 && gw == 0) xch[18] = inc;          // published by group_sum's first barrier
-  group_sum<9>(acc, xch, gt, sync);
+  if (FULLC) group_sum<9>(acc, xch, gt, sync);
+  else group_sum<7>(reinterpret_cast<double (&)[7]>(acc), xch, gt, sync);
   const double S1 = acc[0];
   const double cen = (S1 == 0.0) ? 0.0 : acc[4] / S1;                          // Statistics.cpp:459-477
   double sp[1] = { 0.0 };
@@ -349,9 +354,9 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
     const double mean = S1 / n, gmean = exp(lsum / n);
     const double fl = flatness_db(mean, gmean);
     B.fs[(size_t)FS_SPEC_FLATNESS * TF + slot] = (fl != fl) ? 0.0 : fl;
-    B.cent_full[slot] = (acc[6] == 0.0) ? 0.0 : acc[7] / acc[6];
+    if (FULLC) B.cent_full[slot] = (acc[7] == 0.0) ? 0.0 : acc[8] / acc[7];
     if (flux_here)
-      B.fs[(size_t)FS_SPEC_FLUX * TF + slot] = flux_from_sums(S1, S2, flux_prev ? S1p : S1, flux_prev ? S2p : S2, flux_prev ? acc[8] : S2, n);
+      B.fs[(size_t)FS_SPEC_FLUX * TF + slot] = flux_from_sums(S1, S2, flux_prev ? S1p : S1, flux_prev ? S2p : S2, flux_prev ? acc[6] : S2, n);
     // degenerate in the reference (see oracle/afec_oracle.c, "harmonic spectrum"): always 0
     B.fs[(size_t)FS_SPEC_INHARM * TF + slot] = 0.0;
     B.fs[(size_t)FS_TRISTIM1 * TF + slot] = 0.0;
@@ -409,15 +414,15 @@ __global__ void __launch_bounds__(256) k_flux(AfxBatchDev B, AfxParams P, int st
   if (live && gt == 0) B.fs[(size_t)FS_SPEC_FLUX * B.TF + slot] = flux_from_sums(v[0], v[1], v[2], v[3], v[4], (double)P.nbins);
 }
 
-template <int NG>
+template <int NG, bool FULLC>
 static void launch_spectrum_p(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, int sms)
 {
   const int smem = (int)SpecSmem<NG>::bytes;
-  cudaFuncSetAttribute(k_spectrum<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device, see afx_pitch.cu
+  cudaFuncSetAttribute(k_spectrum<NG, FULLC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device, see afx_pitch.cu
   const int groups_needed = (B.g_slots + SCH - 1) / SCH;
   const int grid = std::max(1, std::min(sms, (groups_needed + NG - 1) / NG));
   cudaMemsetAsync(P.t.work_ctr, 0, sizeof(unsigned int), s);
-  k_spectrum<NG><<<grid, SG * NG, smem, s>>>(B, P, features, P.t.work_ctr);
+  k_spectrum<NG, FULLC><<<grid, SG * NG, smem, s>>>(B, P, features, P.t.work_ctr);
 }
 
 void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, long long* launches)
@@ -426,7 +431,9 @@ void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned feat
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  launch_spectrum_p<10>(P, B, features, s, sms); ++*launches;
+  if (features & AFX_FEAT_PITCH) launch_spectrum_p<10, true>(P, B, features, s, sms);
+  else launch_spectrum_p<10, false>(P, B, features, s, sms);
+  ++*launches;
   const int stride = SCH, nflux = (B.g_slots + stride - 1) / stride;
   k_flux<64><<<(nflux + 3) / 4, 256, 0, s>>>(B, P, stride); ++*launches;
 }
