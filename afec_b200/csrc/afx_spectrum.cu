@@ -157,8 +157,8 @@ struct SpecSmem {
   static constexpr size_t bytes = o_claim + (size_t)NG * 2 * sizeof(int);
 };
 
-// FULLC: also reduce the full-band sums (centroid of mag[0..1023], the pitch kernel's fail-safe f0); without the pitch
-// feature they are not computed
+// FULLC: also reduce the full-band sums (centroid of mag[0..1023], the pitch kernel's fail-safe f0) and carry the
+// amplitude features' code; the instantiation without it serves contexts that ask for neither (BASELINE config 2)
 template <int NG, bool FULLC>
 __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParams P, unsigned features, unsigned int* __restrict__ work_ctr)
 {
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
   const float* __restrict__ mono = B.mono + fp->mono_off;
 
   // ---- amplitude features of the hop slice (SA.cpp:865-873): H / 64 consecutive samples per thread --------
-  if (features & AFX_FEAT_AMPLITUDE) {
+  if (FULLC && (features & AFX_FEAT_AMPLITUDE)) {
     const int per = P.H / SG;                         // 4, 8, ..., 32 (hop is a multiple of 256)
     if (per == 16) amp_features<16>(B, P, mono, st, n0, slot, gt, per, xch, sync);
     else if (per == 8) amp_features<8>(B, P, mono, st, n0, slot, gt, per, xch, sync);
@@ -431,7 +431,7 @@ void afx_launch_spectrum(const AfxParams& P, const AfxBatchDev& B, unsigned feat
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (features & AFX_FEAT_PITCH) launch_spectrum_p<10, true>(P, B, features, s, sms);
+  if (features & (AFX_FEAT_PITCH | AFX_FEAT_AMPLITUDE)) launch_spectrum_p<10, true>(P, B, features, s, sms);
   else launch_spectrum_p<10, false>(P, B, features, s, sms);
   ++*launches;
   const int stride = SCH, nflux = (B.g_slots + stride - 1) / stride;
