@@ -143,7 +143,7 @@ __device__ __forceinline__ void amp_features(const AfxBatchDev& B, const AfxPara
 //     T = W^k O, which halves the unpack arithmetic and the twiddle table (k <= 512).
 // A thread owns bins gt + 64 c (c = 0..7) and their mirrors 1024 - (gt + 64 c); the mirror of bin 0 would be the
 // Nyquist bin, which the magnitude spectrum does not hold (AudioMath.cpp:497-504), so that slot takes bin 512.
-#define SCH 8               // frame slots per claim
+#define SCH 16              // frame slots per claim
 
 template <int NG>
 struct SpecSmem {
