@@ -315,7 +315,13 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
   if (FULLC) group_sum<9>(acc, xch, gt, sync);
   else group_sum<7>(reinterpret_cast<double (&)[7]>(acc), xch, gt, sync);
   const double S1 = acc[0];
-  const double cen = (S1 == 0.0) ? 0.0 : acc[4] / S1;                          // Statistics.cpp:459-477
+  // 1 / S1 by reciprocal seed + two Newton steps (every thread needs the centroid; S1 is 0 or >= 1e-56: sums of
+  // magnitudes of float32-derived spectra), good to an ulp or two -- the IEEE division costs five times the instructions
+  double rS1;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rS1) : "d"(S1));
+  rS1 = fma(fma(-S1, rS1, 1.0), rS1, rS1);
+  rS1 = fma(fma(-S1, rS1, 1.0), rS1, rS1);
+  const double cen = (S1 == 0.0) ? 0.0 : acc[4] * rS1;                          // Statistics.cpp:459-477
   double sp[1] = { 0.0 };
 #pragma unroll
   for (int c = 0; c < 12; ++c) { const double d = (dj0 + (double)(SG * c)) - cen; sp[0] = fma(d * d, mj[c], sp[0]); }
@@ -334,7 +340,7 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
     const int* ix = reinterpret_cast<const int*>(xch + 19);
     const double n = (double)nb;
     B.fs[(size_t)FS_SPEC_ROLLOFF * TF + slot] = (double)(ix[0] + ix[1]) * (double)(P.sr / (P.N / 2));   // SA.cpp:1892: 44100 / 1024 = 43
-    const double spread = (S1 == 0.0) ? 0.0 : sp[0] / S1;                      // Statistics.cpp:486-506
+    const double spread = (S1 == 0.0) ? 0.0 : sp[0] * rS1;                     // Statistics.cpp:486-506
     // skewness / kurtosis (Statistics.cpp:510-554): (1/n) sum ((m_j - cen) / spread)^p from the power sums S1..S4
     // (binomial expansion; the terms cannot cancel to nothing because cen >= 1 > m_j except for spectra
     // concentrated in the first two window bins, where all other bins contribute -cen each)
@@ -343,16 +349,24 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
     const double c2 = cen * cen, c3 = c2 * cen, c4 = c2 * c2;
     const double mu3 = ((S3 - 3.0 * cen * S2) + 3.0 * c2 * S1) - n * c3;
     const double mu4 = (((S4 - 4.0 * cen * S3) + 6.0 * c2 * S2) - 4.0 * c3 * S1) + n * c4;
-    const double s2 = spread * spread;
-    const double rms = sqrt(S2 / n);
+    const double inv3 = 1.0 / (spread * spread * spread * n);                  // two divisions for both moments
+    const double rms = sqrt(S2 * (1.0 / AFX_WIN_BINS));
     B.fs[(size_t)FS_SPEC_RMS * TF + slot] = (rms != rms) ? 0.0 : rms;
     B.fs[(size_t)FS_SPEC_CENTROID * TF + slot] = cen;
     B.fs[(size_t)FS_SPEC_SPREAD * TF + slot] = spread;
-    B.fs[(size_t)FS_SPEC_SKEW * TF + slot] = have_sk ? mu3 / (s2 * spread) / n : 0.0;
-    B.fs[(size_t)FS_SPEC_KURT * TF + slot] = have_sk ? mu4 / (s2 * s2) / n - 3.0 : 0.0;
+    B.fs[(size_t)FS_SPEC_SKEW * TF + slot] = have_sk ? mu3 * inv3 : 0.0;
+    B.fs[(size_t)FS_SPEC_KURT * TF + slot] = have_sk ? (mu4 * inv3) / spread - 3.0 : 0.0;
+    // flatness (SA.cpp:129-133, 1898-1913): min(LinToDb(gmean / mean) / -60, 1) with gmean = exp(log-sum / n), taken in
+    // the log domain: log(gmean / mean) = log-sum / n - log(mean) (one log instead of exp + division + log).
+    // LinToDb's branches: ratio <= 1e-12f -> -200 dB; an all-zero window has ratio 0 (Statistics.cpp:568-571) -> 1.0
     const double lsum = log(xch[20] * xch[21]) + acc[5] * 0.693147180559945309417;
-    const double mean = S1 / n, gmean = exp(lsum / n);
-    const double fl = flatness_db(mean, gmean);
+    const double mean = S1 * (1.0 / AFX_WIN_BINS);
+    double fl = 1.0;
+    if (mean != 0.0) {
+      const double lg = lsum * (1.0 / AFX_WIN_BINS) - log(mean);
+      const double db = (lg > -27.631021119924352) ? lg * (20.0 / 2.302585092994045684) : -200.0;   // log((double)1e-12f)
+      fl = fmin(db / -60.0, 1.0);
+    }
     B.fs[(size_t)FS_SPEC_FLATNESS * TF + slot] = (fl != fl) ? 0.0 : fl;
     if (FULLC) B.cent_full[slot] = (acc[7] == 0.0) ? 0.0 : acc[8] / acc[7];
     if (flux_here)
