@@ -176,7 +176,12 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
   for (int i = threadIdx.x; i < 240; i += SG * NG) s_t2[i] = __ldg(P.t.fft_t2 + i);
   for (int i = threadIdx.x; i < 768; i += SG * NG) s_t3[i] = __ldg(P.t.fft_t3_1024 + i);
   for (int i = threadIdx.x; i <= 512; i += SG * NG) s_tw[i] = __ldg(P.t.tw2048 + i);
-  for (int i = threadIdx.x; i < AFX_NBIN; i += SG * NG) s_win2[i] = __ldg(reinterpret_cast<const double2*>(P.t.window) + i);
+  // the shared-memory copy of the window carries the magnitude scale 0.5 / N = 2^-12 of the pair unpack (a power of
+  // two: the spectrum is the same to the bit, one multiply per bin less)
+  for (int i = threadIdx.x; i < AFX_NBIN; i += SG * NG) {
+    const double2 w = __ldg(reinterpret_cast<const double2*>(P.t.window) + i);
+    s_win2[i] = make_double2(w.x * (0.5 / AFX_NFFT), w.y * (0.5 / AFX_NFFT));
+  }
   __syncthreads();
 
   const int TF = B.TF;
@@ -241,10 +246,10 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
     const double2 O = make_double2(zk.y + zc.y, zc.x - zk.x);
     const double2 T = f_mul(s_tw[k], O);
     const double2 Xa = f_add(E, T), Xb = f_sub(E, T);
-    m16[c] = sqrt_mag(Xa.x * Xa.x + Xa.y * Xa.y) * (0.5 / AFX_NFFT);
-    m16[8 + c] = sqrt_mag(Xb.x * Xb.x + Xb.y * Xb.y) * (0.5 / AFX_NFFT);
+    m16[c] = sqrt_mag(Xa.x * Xa.x + Xa.y * Xa.y);
+    m16[8 + c] = sqrt_mag(Xb.x * Xb.x + Xb.y * Xb.y);
   }
-  if (gt == 0) { const double2 z = buf[FFT_PHYS(AFX_NBIN / 2)]; m16[8] = sqrt(z.x * z.x + z.y * z.y) * (1.0 / AFX_NFFT); }
+  if (gt == 0) { const double2 z = buf[FFT_PHYS(AFX_NBIN / 2)]; m16[8] = 2.0 * sqrt(z.x * z.x + z.y * z.y); }
   const int kmir0 = (gt == 0) ? AFX_NBIN / 2 : AFX_NBIN - gt;          // bin held by m16[8]
   double* gmag = B.mag + (size_t)(slot - B.slot0) * AFX_NBIN;
   sync();                                            // everyone has read Z before buf becomes the magnitude array
