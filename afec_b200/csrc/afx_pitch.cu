@@ -177,15 +177,16 @@ __global__ void __launch_bounds__(YT * NG, 1) k_pitch(AfxBatchDev B, AfxParams P
     {
       auto pk = [&](int k, int kc) {                              // P[k] from Z[k] and Z[kc], kc = (2048 - k) mod 2048
         const double2 z1 = buf[FFT_PHYS(k)], z2 = buf[FFT_PHYS(kc)];
-        const double2 A = make_double2(0.5 * (z1.x + z2.x), 0.5 * (z1.y - z2.y));
-        const double2 Bc = make_double2(0.5 * (z1.y + z2.y), 0.5 * (z2.x - z1.x));            // (z1 - conj(z2)) / (2 i)
+        // 2 A and 2 B: the halves (and those of e1 / d1 below) are powers of two and go into the final scale 1 / (8 W)
+        const double2 A = make_double2(z1.x + z2.x, z1.y - z2.y);
+        const double2 Bc = make_double2(z1.y + z2.y, z2.x - z1.x);                            // (z1 - conj(z2)) / i
         return f_mul(make_double2(A.x, -A.y), Bc);
       };
       auto pair = [&](int k) {                                    // 0 <= k <= 512
         const double2 p1 = pk(k, (YN - k) & (YN - 1)), p2 = pk(YW - k, YW + k);
         const double2 w = __ldg(P.t.tw2048 + k);                  // W^k; W^-k = conj
-        const double2 e1 = make_double2(0.5 * (p1.x + p2.x), 0.5 * (p1.y - p2.y));           // (P[k] + conj(P[k'])) / 2
-        const double2 d1 = make_double2(0.5 * (p1.x - p2.x), 0.5 * (p1.y + p2.y));           // (P[k] - conj(P[k'])) / 2
+        const double2 e1 = make_double2(p1.x + p2.x, p1.y - p2.y);                           // P[k] + conj(P[k'])   (x 8: see pk)
+        const double2 d1 = make_double2(p1.x - p2.x, p1.y + p2.y);                           // P[k] - conj(P[k'])
         const double2 o1 = f_mul(make_double2(w.x, -w.y), d1);                                 // W^-k d1
         const double2 zc1 = make_double2(e1.x - o1.y, e1.y + o1.x);                            // e1 + i o1
         hbuf[FFT_PHYS(k)] = make_double2(zc1.x, -zc1.y);                                       // conj(Zc[k])
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(YT * NG, 1) k_pitch(AfxBatchDev B, AfxParams P
     for (int c = 0; c < YW / YT; ++c) {
       const int tau = tid + YT * c;
       const double2 f = hbuf[FFT_PHYS(tau >> 1)];                // z[m] = conj(F[m]) / 1024: r[2m] = Re, r[2m+1] = Im
-      yin[PAD8(tau)] = yin[PAD8(tau)] - ((tau & 1) ? -f.y : f.x) * (1.0 / YW);
+      yin[PAD8(tau)] = yin[PAD8(tau)] - ((tau & 1) ? -f.y : f.x) * (0.125 / YW);
     }
     sync();
     // ---- cumulative-mean normalisation: 8 consecutive tau per thread ---------------------------------------
