@@ -16,7 +16,8 @@ instead of Ooura would disagree with itself):
     (pitchyinfast.c:110-137); there sq[tau] is exactly 0 for small tau and r[tau] is FFT rounding noise, so the
     cumulative-mean normalised function, the first-dip search and the confidence are functions of that noise
     (callers pass the conditioned signal so those frames can be found).
-  * peak counts of a frame that holds exactly ONE non-zero sample (the last LSB tick of a decayed tail): its magnitude
+  * peak counts of a frame whose windowed signal holds exactly ONE non-zero sample (the last LSB tick of a decayed tail;
+    the window's end points are zero): its magnitude
     spectrum is |x w[n]| / N in every bin, so which bins are "strict local maxima above 0.25 max" (spectral_complexity,
     spectral_complexity_bands; Statistics.cpp:140-232, SampleAnalyser.cpp:2150-2187) is decided by the last bit of the
     FFT's rounding; the frame's flatness is then 1e-16-sized noise around 0, which the geometric-mean statistics of the
@@ -66,13 +67,14 @@ FLAT_GMEAN_SERIES = ("spectral_flatness", "spectral_flatness_bands")
 
 
 def impulse_frames(mdata, hop, F, N=2048):
-    """Frames that hold exactly one non-zero sample (see the module docstring)."""
+    """Frames whose WINDOWED signal holds exactly one non-zero sample (see the module docstring).  The Hann window
+    (SampleAnalyser.cpp:178-181) is zero at both ends, so a tick on the frame's first or last sample does not count."""
     x = np.asarray(mdata, dtype=np.float64)
-    nz = np.concatenate([[0], np.cumsum(x != 0.0)])
+    w = 1.0 - np.cos(2.0 * np.pi * np.arange(N) / (N - 1))
     out = np.zeros(F, dtype=bool)
     for t in range(F):
-        a, e = t * hop, min(t * hop + N, len(x))
-        out[t] = e > a and (nz[e] - nz[a]) == 1
+        seg = x[t * hop:t * hop + N]
+        out[t] = np.count_nonzero(seg * w[:len(seg)]) == 1
     return out
 
 

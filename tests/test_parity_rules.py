@@ -14,9 +14,13 @@ def test_impulse_frames_are_exactly_the_single_sample_frames():
     want = np.zeros(F, dtype=bool)
     want[[3, 4]] = True
     assert np.array_equal(got, want)
-    # two ticks in the same frame are not an impulse frame
+    # two ticks in the same frame are not an impulse frame ...
     x[hop * 4 + 900] = -3.0e-5
     assert not parity.impulse_frames(x, hop, F)[3:5].any()
+    # ... unless one of them sits on the window's zero end point
+    y = np.zeros(hop * 3 + N)
+    y[hop + 100] = 1.0e-4; y[hop + N - 1] = -2.0e-4           # frame 1: sample 100 and the last sample
+    assert parity.impulse_frames(y, hop, (len(y) - N) // hop + 1)[1]
 
 
 def test_half_silent_pitch_frames():
