@@ -380,6 +380,7 @@ extern "C" int afx_trim(afx_ctx* ctx)
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamSynchronize(ctx->side[i]);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
   if (e != cudaSuccess) return fail(ctx, AFX_ERR_CUDA, "afx_trim", e);
+  if (ctx->live) return fail(ctx, AFX_ERR_STATE, "afx_trim: a batch of this context is still alive");
   DevBuf* bufs[] = { &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
     &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch };
   for (DevBuf* b : bufs) b->release();
@@ -406,16 +407,29 @@ extern "C" int afx_host_free(afx_ctx* ctx, void* p)
 // process-wide cache of the data-independent libresample replays, keyed by (analysis rate, source rate, length)
 std::shared_ptr<RsShape> afx_rs_shape(int sr, int in_len, int src_rate, int out_len)
 {
+  // least-recently-used eviction; a batch keeps the shapes it uses alive itself (afx_batch::rs_shapes), so an entry
+  // dropped here mid-batch is only dropped from the cache
+  struct Entry { std::shared_ptr<RsShape> shape; unsigned long long used; };
   static std::mutex mu;
-  static std::map<std::tuple<int, int, int>, std::shared_ptr<RsShape>> cache;
-  std::lock_guard<std::mutex> lk(mu);
-  auto key = std::make_tuple(sr, src_rate, in_len);
-  auto it = cache.find(key);
-  if (it == cache.end()) {
-    if (cache.size() > 256) cache.clear();
-    it = cache.emplace(key, rs_plan(in_len, src_rate, sr, out_len)).first;
+  static std::map<std::tuple<int, int, int>, Entry> cache;
+  static unsigned long long tick = 0;
+  const auto key = std::make_tuple(sr, src_rate, in_len);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { it->second.used = ++tick; return it->second.shape; }
   }
-  return it->second;
+  std::shared_ptr<RsShape> made = rs_plan(in_len, src_rate, sr, out_len);   // planned outside the lock: slot threads plan in parallel
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { it->second.used = ++tick; return it->second.shape; }
+  if (cache.size() >= 512) {
+    auto victim = cache.begin();
+    for (auto c = cache.begin(); c != cache.end(); ++c) if (c->second.used < victim->second.used) victim = c;
+    cache.erase(victim);
+  }
+  cache.emplace(key, Entry{ made, ++tick });
+  return made;
 }
 
 extern "C" int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_files, afx_batch** out)
@@ -434,7 +448,7 @@ int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, 
   b->files.resize(n_files);
   size_t pcm_off = 0; long long mono_off = 0, src_off = 0; long long tf = 0, tfr = 0;
   const unsigned char* run_end = nullptr;
-  std::map<const RsShape*, long long> shape_pool;     // shape -> offset of its checkpoints in rs_chk
+  std::map<std::pair<int, int>, long long> shape_pool;   // (source rate, source length) -> offset of that shape's checkpoints in rs_chk
   afx_batch::Group g = { 0, 0, 0, 0, 0, 0 };
   auto close_group = [&]() {
     if (g.nfiles > 0) {
@@ -450,9 +464,8 @@ int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, 
     d.status = AFX_FILE_OK;
     if (f.channels < 1 || f.channels > 8) d.status = AFX_FILE_BAD_CHANNELS;          // SA.cpp:472-477
     else if (f.nframes <= 0 || (!f.pcm && !cond)) d.status = AFX_FILE_EMPTY;          // SA.cpp:479-482
-    else if (f.nframes * f.channels > 0x7fffffffLL || f.src_rate <= 0 || (f.format != AFX_PCM_I16 && f.format != AFX_PCM_F32)) {
-      delete b; return fail(ctx, AFX_ERR_ARG, "afx_batch_create: unsupported file description");
-    }
+    // a description the kernels cannot take fails that file only (the reference fails files one by one, SA.cpp:372-408)
+    else if (f.nframes * f.channels > 0x7fffffffLL || f.src_rate <= 0 || (f.format != AFX_PCM_I16 && f.format != AFX_PCM_F32)) d.status = AFX_FILE_UNSUPPORTED;
     d.frame_off = (int)tf; d.rframe_off = (int)tfr; d.mono_off = mono_off; d.src_off = src_off; d.pcm_off = (long long)pcm_off;
     if (d.status != AFX_FILE_OK) { if (g.nfiles > 0) ++g.nfiles; else { g.file0 = i; g.nfiles = 1; g.slot0 = (int)tf; g.rslot0 = (int)tfr; } continue; }
     d.nframes_src = (int)f.nframes;
@@ -502,10 +515,12 @@ int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, 
     if (speed != 1.0) {
       d.src_off = src_off; src_off += ((long long)d.nframes_src + 3) & ~3LL;
       std::shared_ptr<RsShape> sh = afx_rs_shape(P.sr, d.nframes_src, f.src_rate, d.n);
-      auto pit = shape_pool.find(sh.get());
+      const auto skey = std::make_pair(f.src_rate, d.nframes_src);
+      auto pit = shape_pool.find(skey);
       if (pit == shape_pool.end()) {
-        pit = shape_pool.emplace(sh.get(), (long long)b->rs_chk.size()).first;
+        pit = shape_pool.emplace(skey, (long long)b->rs_chk.size()).first;
         b->rs_chk.insert(b->rs_chk.end(), sh->chk.begin(), sh->chk.end());
+        b->rs_shapes.push_back(sh);
       }
       for (RsBlock rb : sh->blocks) { rb.chk_off += pit->second; b->rs_blocks.push_back(rb); b->rs_blk_file.push_back(i); }
       if (!sh->blocks.empty()) b->rs_smem = std::max(b->rs_smem, afx_rs_smem_need(P.sr, f.src_rate, sh->max_span));
@@ -558,6 +573,11 @@ extern "C" int afx_batch_upload(afx_batch* b)
   if (!b) return AFX_ERR_ARG;
   afx_ctx* ctx = b->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  // the device buffers belong to the context: a second batch uploaded while another one's results still live in them
+  // would overwrite (or reallocate) what the first one downloads -- one uploaded batch per context at a time
+  if (ctx->live && ctx->live != b)
+    return fail(ctx, AFX_ERR_STATE, "afx_batch_upload: another batch of this context is still alive (afx_batch_free it first, or use one context per batch in flight)");
+  ctx->live = b;
   cudaSetDevice(ctx->device);
   const int n = b->n_files;
   if (!b->ev[0]) for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&b->ev[i]), "cudaEventCreate");
@@ -832,6 +852,7 @@ extern "C" void afx_batch_free(afx_batch* b)
     std::lock_guard<std::mutex> lk(ctx->mu);
     give_back(b->h_results, ctx->h_results_cache);
     give_back(b->h_plan, ctx->h_plan_cache);
+    if (ctx->live == b) ctx->live = nullptr;
   }
   for (int i = 0; i < 6; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   for (auto& k : b->ktimes) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }

@@ -77,6 +77,7 @@ struct afx_ctx {
   bool debug_times = false;
   std::mutex mu;
   int max_frame_cap = 0;
+  struct afx_batch* live = nullptr;   // the one batch whose data occupies the device buffers (afx_batch_upload .. afx_batch_free)
 };
 
 struct KernelTime { const char* name; cudaEvent_t a, b; };
@@ -90,6 +91,7 @@ struct afx_batch {
   // plan
   std::vector<int> src_chunk_file, src_chunk_start, dst_chunk_file, dst_chunk_start, rs_chunk_file, rs_chunk_start;
   std::vector<RsBlock> rs_blocks; std::vector<int> rs_blk_file; std::vector<double> rs_chk;
+  std::vector<std::shared_ptr<RsShape>> rs_shapes;   // the batch's distinct resampler shapes (kept alive whatever the process-wide cache evicts)
   struct Tail { long long off; long long count; }; std::vector<Tail> rs_tails;   // mono samples libresample never writes
   struct Group { int file0, nfiles, slot0, nslots, rslot0, nrslots; };
   std::vector<Group> groups;

@@ -124,12 +124,12 @@ extern "C" int afx_part_open(afx_ctx* ctx, const afx_file* whole, const afx_part
   const int n = analysis_len(P.sr, whole->nframes, whole->src_rate);
   std::shared_ptr<RsShape> sh;
   if (whole->src_rate != P.sr) sh = afx_rs_shape(P.sr, (int)whole->nframes, whole->src_rate, n);
+  if (part->out_end > n) return afx_fail(ctx, AFX_ERR_ARG, "afx_part_open: part exceeds the file");
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   afx_partjob* j = new afx_partjob();
   j->ctx = ctx; j->part = *part;
   if (!ctx->part_pool.empty()) { j->bufs = ctx->part_pool.back(); ctx->part_pool.pop_back(); }
-  if (part->out_end > n) { delete j; return afx_fail(ctx, AFX_ERR_ARG, "afx_part_open: part exceeds the file"); }
   j->resampled = whole->src_rate != P.sr;
   const size_t bps = (whole->format == AFX_PCM_I16) ? 2 : 4;
   const long long ns = part->src_end - part->src_begin, no = part->out_end - part->out_begin;

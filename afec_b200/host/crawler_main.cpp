@@ -12,6 +12,7 @@
 #include <cstring>
 #include <dirent.h>
 #include <map>
+#include <set>
 #include <sys/stat.h>
 
 using namespace afec;
@@ -83,12 +84,21 @@ int main(int argc, char** argv)
       for (const auto& f : files) if (f.compare(0, dir.size(), dir) != 0) { all_below = false; break; }
       if (all_below) pool.SetBasePath(dir);
     }
-    // change list: new or modified files are (re)analysed, vanished ones removed
-    std::map<std::string, int> known;
-    for (const auto& e : pool.SampleModificationDates()) known[e.first] = e.second;
+    // change list as SBuildChangeList (Crawler.cpp:933-998): a row is removed only when its file no longer exists on
+    // disk, refreshed when the file's mtime is newer than the stored one -- whether or not this run's inputs name it --
+    // and every input the database does not know is added
     std::vector<std::string> todo, gone;
-    for (const auto& f : files) { auto it = known.find(f); if (it == known.end() || it->second < ModificationStatTime(f)) todo.push_back(f); if (it != known.end()) known.erase(it); }
-    for (const auto& e : known) gone.push_back(e.first);
+    if (pool.IsEmpty()) todo = files;
+    else {
+      std::set<std::string> known;
+      for (const auto& e : pool.SampleModificationDates()) {
+        known.insert(e.first);
+        struct stat st;
+        if (stat(e.first.c_str(), &st) != 0) gone.push_back(e.first);
+        else if (ModificationStatTime(e.first) > e.second) todo.push_back(e.first);
+      }
+      for (const auto& f : files) if (known.find(f) == known.end()) todo.push_back(f);
+    }
     if (!gone.empty()) pool.RemoveSamples(gone);
     if (!quiet) printf("%zu files found, %zu to analyse, %zu removed\n", files.size(), todo.size(), gone.size());
     if (todo.empty()) return 0;

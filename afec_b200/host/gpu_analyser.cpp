@@ -63,6 +63,7 @@ static const char* file_status_message(int status)
   switch (status) {                            // SampleAnalyser.cpp:472-482
     case AFX_FILE_BAD_CHANNELS: return "Unsupported audio file channel layout: Supporting mono, stereo, 3.0, 5.0, 5.1 and 7.1 audio files only.";
     case AFX_FILE_EMPTY: return "Sample file is empty, probably failed to read.";
+    case AFX_FILE_UNSUPPORTED: return "Unsupported sample rate, sample format or file length.";
     default: return "Unknown error";
   }
 }

@@ -60,7 +60,7 @@ void ReadWaveFile(const std::string& FileName, TDecodedAudio& Out)
   }
   if (!have_fmt || !have_data) throw TReadableException("Not a valid WAV file.");
   const bool pcm = (tag == 1), flt = (tag == 3);
-  if ((!pcm && !flt) || channels == 0 || rate == 0 || (pcm && bits != 8 && bits != 16 && bits != 24 && bits != 32) ||
+  if ((!pcm && !flt) || channels == 0 || rate == 0 || rate > 0x7fffffffu || (pcm && bits != 8 && bits != 16 && bits != 24 && bits != 32) ||
       (flt && bits != 32 && bits != 64))
     throw TReadableException("Unsupported file format.");
   (void)block;

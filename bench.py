@@ -5,10 +5,11 @@
 
 One "step" is one pass of the hot path over one batch of synthetic decoded PCM per GPU.
 Workloads (BASELINE.json `configs`):
-  config2  (default at N=1, configs[1]): 10 000 x 3-s 44.1 kHz mono int16 one-shots per GPU,
-           2048-pt STFT hop 512 Hann + spectral stats (features = SPECTRAL)
-  full     configs[3] per-GPU shard: 12 500 mixed-length (0.5-30 s) files per GPU, hop 1024, the
-           full low-level descriptor set (100k files over 8 GPUs)
+  full     (default, configs[3] -- the north-star workload): ONE corpus of 12 500 x N mixed-length (0.5-30 s)
+           44.1 kHz mono int16 files (100k files at 8 GPUs), sharded over the ranks by cost (afec_b200/shard.py),
+           hop 1024, the full low-level descriptor set -- the same work `--impl reference` times on the host cores
+  config2  configs[1]: 10 000 x 3-s one-shots per GPU, 2048-pt STFT hop 512 Hann + spectral stats
+           (features = SPECTRAL); the reference has no such subset switch, so this line carries no cpu_baseline
 Multi-GPU: files are independent units, each rank owns its own shard and its own context; there is
 no data-path collective.  torch.distributed (NCCL) is used only for the barrier and the max-over-ranks
 reduction of the timings.  `value` = audio-hours of all ranks / max-over-ranks device time.
@@ -113,6 +114,26 @@ def build_corpus(wl, rank):
                               min_seconds=wl["min_seconds"])
 
 
+def build_sharded_corpus(wl, rank, world):
+    """ONE corpus of files_per_gpu x world files (every rank derives the same list from the same seeds); this rank's
+    shard is chosen by cost = decoded length, longest-processing-time first (afec_b200/shard.py).
+    -> (list of int16 arrays of this rank's shard, their indices in the global list)."""
+    from afec_b200 import shard
+    base = synth.corpus(N_UNIQUE, wl["seconds"], seed0=1000, min_seconds=wl["min_seconds"])
+    n_total = wl["files_per_gpu"] * world
+    costs = [len(base[i % N_UNIQUE]) for i in range(n_total)]
+    mine = shard.my_shard(costs, rank, world) if world > 1 else list(range(n_total))
+    return [base[i % N_UNIQUE] for i in mine], mine
+
+
+def workload_config(wl, world):
+    """The `config` object both arms print (identical by construction, so the two lines describe the same work)."""
+    return {"workload": wl["desc"], "files_per_gpu": wl["files_per_gpu"], "files_total": wl["files_per_gpu"] * world,
+            "hop": wl["hop"], "fft": 2048, "features": wl["features"], "unique_files": N_UNIQUE,
+            "parallelism": "one corpus sharded by cost over the ranks (file batches), no collective",
+            "l2": "every step's inputs (GBs of PCM, spectra) exceed the 126 MB L2; no flush needed"}
+
+
 # ------------------------------------------------------------------------------------------------------
 def cpu_reference_run(files_pcm, hop, threads, reps=1, rate=44100):
     """Times the reference (or the port) on host cores over the given files.  Returns dict."""
@@ -153,14 +174,24 @@ def reference_sample_files(wl, cores):
     return int(max(2 * cores, min(2048, target_audio_s / avg_s)))
 
 
+def reference_sample(wl, cores):
+    """The CPU legs' bounded sample of the workload: the first files of the global corpus (rank 0's view)."""
+    n_sample = reference_sample_files(wl, cores)
+    if wl["seconds"] >= 600:
+        return build_corpus(dict(wl, files_per_gpu=min(n_sample, wl["files_per_gpu"])), 0)     # hour-long files: minutes of CPU time each
+    if wl["features"] != "all":
+        return build_corpus(dict(wl, files_per_gpu=n_sample), 0)
+    return build_sharded_corpus(dict(wl, files_per_gpu=n_sample), 0, 1)[0]
+
+
 def run_reference_arm(args, wl, rank, world):
+    """The reference's own CPU implementation of the path (TSampleAnalyser::Extract into a TSqliteSampleDescriptorPool,
+    Crawler.cpp:706-728) on every host thread, each step a bounded sample of the SAME workload (same corpus, hop and
+    descriptor set as the GPU arm's `config`)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = reference_sample_files(wl, cores)
-    if wl["seconds"] >= 600:
-        n_sample = min(n_sample, wl["files_per_gpu"])          # hour-long files: minutes of CPU time each
-    pcms = build_corpus(dict(wl, files_per_gpu=n_sample), 0)
+    pcms = reference_sample(wl, cores)
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_reference_run(pcms[: max(4, cores // 2)], wl["hop"], cores, rate=wl.get("rate", 44100))
     secs, audio = 0.0, 0.0
@@ -173,11 +204,11 @@ def run_reference_arm(args, wl, rank, world):
         "impl": "reference", "metric": "low-level descriptor throughput (audio-hours/sec)", "value": value,
         "unit": "audio-hours/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "hop": wl["hop"], "note": "reference CPU path computes the FULL low-level set "
-                   "(TSampleAnalyser::Extract into a sqlite pool, as Crawler.cpp:706-728) whatever the workload's subset"},
+        "dtype": "f64", "data": "synthetic", "config": workload_config(wl, max(1, args.gpus)),
+        "same_feature_set": wl["features"] == "all",
         "cpu_baseline": {"value": value, "unit": "audio-hours/s", "cores": used, "kind": kind,
-                         "sample": "%d files (%.1f s audio) per step, %d host threads" % (len(pcms), audio / args.steps, used)},
+                         "sample": "%d files of the workload's corpus (%.1f s audio) per step, %d host threads, hop %d, full low-level "
+                                   "set into a sqlite pool" % (len(pcms), audio / args.steps, used, wl["hop"])},
         "e2e": {"value": value, "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -303,17 +334,59 @@ def run_long_sharded(args, wl, rank, local_rank, world):
 
 
 # ------------------------------------------------------------------------------------------------------
+# algorithmic flops per frame and kernel group (rFFT counted 2.5 n log2 n); "rhythm" is per RHYTHM frame
+GROUP_FLOPS = {"spectrum": 56320 + 6144 + 23600 + 8000, "peaks": 4000, "bands": 30000 + 2000 + 28672 + 392, "pitch": 184000,
+               "autocorr": 280370, "rhythm": 29000, "stats": 0, "condition": 0}
+GROUP_FLOPS_SPECTRAL_SUBSET = 78e3
+FP32_NOMINAL_TFLOPS = 74.5      # the FP32 roofline the north_star target is stated against (2 x the FP64 pipe)
+
+
+def parity_check_sample(b, pcms, wl, n_check=32, seed=7):
+    """After the timed region: `n_check` files of the batch that was just timed, compared with the oracle under the rules
+    of tests/parity.py (the checker -- it never produces a result).  Returns (n_checked, mismatch strings)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity
+    from afec_b200 import api
+    from oracle import oracle
+    oracle.build()
+    rng = np.random.default_rng(seed)
+    seen, errs, n = {}, [], 0
+    order = rng.permutation(len(pcms)).tolist()
+    only = None
+    if wl["features"] == "spectral":
+        only = ["spectral_rms", "spectral_centroid", "spectral_rolloff", "spectral_spread", "spectral_skewness",
+                "spectral_kurtosis", "spectral_flatness", "spectral_flux"]
+    for i in order:
+        key = (pcms[i].ctypes.data, len(pcms[i]))
+        if key in seen:
+            continue                                  # tiled corpus: take distinct files
+        seen[key] = True
+        p = pcms[i]
+        want = oracle.analyze(p, hop=wl["hop"], file_size=44 + 2 * p.size)
+        data = oracle.condition(p)[0]
+        e = parity.compare(b.result(i), want, only_series=only, check_stats=only is None, check_header=only is None,
+                           mdata=data, hop=wl["hop"])
+        errs += ["file %d: %s" % (i, x) for x in e[:3]]
+        n += 1
+        if n >= n_check:
+            break
+    return n, errs
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="full", choices=sorted(WORKLOADS))
     ap.add_argument("--seconds", type=float, default=0.0, help="override file duration (debug)")
     ap.add_argument("--files", type=int, default=0, help="override files per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--parts", type=int, default=0, help="long workload at N = 1: condition every file in this many parts")
+    ap.add_argument("--e2e-slots", type=int, default=3)
+    ap.add_argument("--e2e-chunks", type=int, default=12)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -332,6 +405,8 @@ def main():
         run_long_sharded(args, wl, rank, local_rank, world)
         return
 
+    import ctypes as C
+    import itertools
     import torch
     from afec_b200 import api
 
@@ -348,25 +423,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce(x: float, op) -> float:
         if dist is None:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def max_over_ranks(x):
+        return reduce(x, dist.ReduceOp.MAX) if dist is not None else x
+
+    def sum_over_ranks(x):
+        return reduce(x, dist.ReduceOp.SUM) if dist is not None else x
 
     feats = api.FEAT_SPECTRAL if wl["features"] == "spectral" else api.FEAT_ALL
     an = api.SampleAnalyser(44100, 2048, wl["hop"], device=local_rank, features=feats)
 
     # ---- synthetic decoded PCM in ONE pinned arena (what per-GPU decode threads would fill) ----
-    pcms = build_corpus(wl, rank)
+    if wl["features"] == "all" and wl["seconds"] < 600:
+        pcms, _ = build_sharded_corpus(wl, rank, world)
+    else:
+        pcms = build_corpus(wl, rank)
     rate, nch = wl.get("rate", 44100), wl.get("channels", 1)
     total = sum(p.size for p in pcms)
     arena = an.pinned(total * 2)
@@ -379,16 +456,15 @@ def main():
     audio_hours = total / float(nch) / float(rate) / 3600.0
     files_arr = (api.AfxFile * len(files))(*files)
 
-    def make_batch():
-        import ctypes as C
+    def wrap(sl, arr, n):
         h = C.c_void_p()
-        an._check(an._L.afx_batch_create(an._ctx, files_arr, len(files), C.byref(h)))
+        sl._check(sl._L.afx_batch_create(sl._ctx, arr, n, C.byref(h)))
         b = api.Batch.__new__(api.Batch)
-        b._an, b._L, b._keep, b.n_files, b._files, b._h = an, an._L, None, len(files), files_arr, h
+        b._an, b._L, b._keep, b.n_files, b._files, b._h = sl, sl._L, None, n, arr, h
         return b
 
     # ---- device-resident timing: inputs already in HBM, K passes of the kernels -------------------
-    b = make_batch()
+    b = wrap(an, files_arr, len(files))
     b.upload(); b.sync()
     for _ in range(max(3, args.warmup)):
         b.compute()
@@ -411,27 +487,33 @@ def main():
     clocks = sampler.stop()
     b.download(); b.sync()
     cnt = b.counters()
-    ktimes = b.kernel_times()
     dev_ms_max = max_over_ranks(dev_ms)
     total_audio_hours = sum_over_ranks(audio_hours)
     total_frames = sum_over_ranks(float(cnt["main_frames"]))
+    total_rframes = sum_over_ranks(float(cnt["rhythm_frames"]))
     value = total_audio_hours * args.steps / (dev_ms_max / 1000.0)
     frames_per_s = total_frames * args.steps / (dev_ms_max / 1000.0)
+
+    # ---- what was timed is what the reference computes: sampled files of THIS batch against the oracle ----
+    parity_n, parity_errs = 0, []
+    if rank == 0 and not args.no_parity_check:
+        try:
+            parity_n, parity_errs = parity_check_sample(b, pcms, wl)
+        except Exception as e:
+            parity_errs = ["parity check failed to run: %r" % (e,)]
     b.free()
 
     # ---- end to end through the C ABI: host PCM -> H2D -> kernels -> D2H results, every step ------
-    # Host pipeline as in afec_b200/host/gpu_analyser.cpp: E2E_SLOTS contexts (stream + device buffers each), one
+    # Host pipeline as in afec_b200/host/gpu_analyser.cpp: slots = contexts (stream + device buffers each), one
     # host thread per slot; a step's files are cut into chunks that the slot threads claim in turn, so the H2D /
     # D2H copies of one chunk overlap the kernels of another.  ctypes releases the GIL inside the C calls.
-    E2E_SLOTS, E2E_CHUNKS = 3, min(12, len(files))
+    E2E_SLOTS, E2E_CHUNKS = max(1, args.e2e_slots), max(1, min(args.e2e_chunks, len(files)))
     slots = [an] + [api.SampleAnalyser(44100, 2048, wl["hop"], device=local_rank, features=feats) for _ in range(E2E_SLOTS - 1)]
     bounds = [len(files) * i // E2E_CHUNKS for i in range(E2E_CHUNKS + 1)]
     chunk_arrs = [(api.AfxFile * (bounds[i + 1] - bounds[i]))(*files[bounds[i]:bounds[i + 1]]) for i in range(E2E_CHUNKS)]
-    import ctypes as C
-    import itertools
     e2e_bytes = [0, 0]
 
-    def e2e_step():
+    def pipeline_step(copy_only: bool):
         counter = itertools.count()
         lock = threading.Lock()
         tot = [0, 0, 0.0]
@@ -443,15 +525,18 @@ def main():
                 if ci >= E2E_CHUNKS:
                     return
                 arr = chunk_arrs[ci]
-                h = C.c_void_p()
-                sl._check(sl._L.afx_batch_create(sl._ctx, arr, len(arr), C.byref(h)))
-                bb = api.Batch.__new__(api.Batch)
-                bb._an, bb._L, bb._keep, bb.n_files, bb._files, bb._h = sl, sl._L, None, len(arr), arr, h
-                bb.run()
-                r = bb.raw_result(len(arr) - 1)            # the step's result is read on the host
-                c = bb.counters()
-                with lock:
-                    tot[0] += c["h2d_bytes"]; tot[1] += c["d2h_bytes"]; tot[2] += r.header[1]
+                bb = wrap(sl, arr, len(arr))
+                if copy_only:
+                    bb.upload(); bb.sync()
+                    c = bb.counters()
+                    with lock:
+                        tot[0] += c["h2d_bytes"]
+                else:
+                    bb.run()
+                    r = bb.raw_result(len(arr) - 1)            # the step's result is read on the host
+                    c = bb.counters()
+                    with lock:
+                        tot[0] += c["h2d_bytes"]; tot[1] += c["d2h_bytes"]; tot[2] += r.header[1]
                 bb.free()
         ths = [threading.Thread(target=work, args=(sl,)) for sl in slots]
         for t in ths:
@@ -461,71 +546,87 @@ def main():
         e2e_bytes[0], e2e_bytes[1] = tot[0], tot[1]
 
     for _ in range(2):
-        e2e_step()
+        pipeline_step(False)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e2e_step()
+        pipeline_step(False)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     h2d, d2h = e2e_bytes
     e2e_value = total_audio_hours * args.steps / e2e_s
+    # copy-only leg: the same arena, chunks, slots and threads, uploads only -- what the host -> device fabric gives
+    # every rank while all ranks copy at once (separates a PCIe / host-memory ceiling from the kernels)
+    pipeline_step(True)
+    barrier()
+    t0 = time.perf_counter()
+    n_copy = max(2, args.steps // 2)
+    for _ in range(n_copy):
+        pipeline_step(True)
+    torch.cuda.synchronize()
+    copy_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    h2d_gbs = e2e_bytes[0] * n_copy / copy_s / 1e9
     for sl in slots[1:]:
         sl.close()
     an.trim()          # the roofline leg below runs the same batch on a second context: give this one's device buffers back
 
-    # ---- roofline of the dominant kernel (k_spectrum), timed live with CUDA events ---------------
+    # ---- roofline: per-kernel-group device times (CUDA events around each group, one stream), timed live -----------
     roof = None
     peaks, peak_src = measured_peaks()
     try:
         os.environ["AFX_DEBUG_KERNEL_TIMES"] = "1"
         an2 = api.SampleAnalyser(44100, 2048, wl["hop"], device=local_rank, features=feats)
-        import ctypes as C
-        h = C.c_void_p()
-        an2._check(an2._L.afx_batch_create(an2._ctx, files_arr, len(files), C.byref(h)))
-        b2 = api.Batch.__new__(api.Batch)
-        b2._an, b2._L, b2._keep, b2.n_files, b2._files, b2._h = an2, an2._L, None, len(files), files_arr, h
+        del os.environ["AFX_DEBUG_KERNEL_TIMES"]
+        b2 = wrap(an2, files_arr, len(files))
         b2.upload()
         for _ in range(3):
             b2.compute()
         b2.sync()
         acc = {}
-        for _ in range(args.steps):
+        n_roof = max(2, min(args.steps, 5))
+        for _ in range(n_roof):
             b2.compute(); b2.sync()
             for name, ms in b2.kernel_times():
                 acc[name] = acc.get(name, 0.0) + ms
         b2.download(); b2.sync()
-        frames = b2.counters()["main_frames"]
+        c2 = b2.counters()
+        frames, rframes = c2["main_frames"], c2["rhythm_frames"]
         fp64_peak = an2.fp64_peak_tflops()
         b2.free(); an2.close()
-        del os.environ["AFX_DEBUG_KERNEL_TIMES"]
-        groups = {k: v / args.steps for k, v in acc.items()}
+        groups = {k: v / n_roof for k, v in acc.items()}
         top = max(groups, key=groups.get)
         top_ms = groups[top]
-        # algorithmic bytes / flops per main frame (DESIGN.md "Kernels")
         H = wl["hop"]
         if wl["features"] == "spectral":
             bytes_per_frame = 2 * H + 8 * 8          # int16 hop in, 8 float64 descriptors out
-            flops_per_frame = 78e3
+            gflops = {"spectrum": GROUP_FLOPS_SPECTRAL_SUBSET * frames}
         else:
             bytes_per_frame = 2 * H + 136 * 8 + 2 * 8 * (H // 128)
-            flops_per_frame = 0.855e6
-        share = top_ms / sum(groups.values())
-        hbm_achieved = bytes_per_frame * frames / (top_ms * 1e-3) / 1e9
-        fl_achieved = flops_per_frame * frames * share / (top_ms * 1e-3) / 1e12 if wl["features"] != "spectral" else \
-            flops_per_frame * frames / (top_ms * 1e-3) / 1e12
+            gflops = {g: (f * rframes if g == "rhythm" else f * frames) for g, f in GROUP_FLOPS.items()}
+        step_flops = sum(gflops.values())
+        table = {g: {"ms": ms, "share": ms / sum(groups.values()), "algorithmic_gflop": gflops.get(g, 0.0) / 1e9,
+                     "tflops": gflops.get(g, 0.0) / (ms * 1e-3) / 1e12 if ms > 0 else None,
+                     "frac_fp64": gflops.get(g, 0.0) / (ms * 1e-3) / 1e12 / fp64_peak if ms > 0 and fp64_peak else None}
+                 for g, ms in groups.items()}
+        top_tf = gflops.get(top, 0.0) / (top_ms * 1e-3) / 1e12
+        step_ms = dev_ms / args.steps                     # this rank's multi-stream step (the `value` timing)
+        step_tf = step_flops / (step_ms * 1e-3) / 1e12
         roof = {
-            "bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json)",
-            "kernel": top, "kernel_ms": top_ms, "kernel_share_of_step": share,
-            "algorithmic_bytes_per_frame": bytes_per_frame, "frames_per_launch": frames,
-            "fp64": {"bound": "fp64 fma pipe (the path is compute-bound: ~%d flop/B)" % int(flops_per_frame / bytes_per_frame),
-                     "achieved": fl_achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": fl_achieved / fp64_peak if fp64_peak else None,
-                     "peak_source": "measured live: dependent-free DFMA loop (afx_measure_fp64_peak)",
-                     "algorithmic_flops_per_frame": flops_per_frame},
-            "groups_ms": groups,
+            "bound": "fp64", "achieved": top_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": top_tf / fp64_peak if fp64_peak else None,
+            "traffic": None, "kernel": top, "kernel_ms": top_ms, "kernel_share_of_step": top_ms / sum(groups.values()),
+            "peak_source": "measured live: dependent-free DFMA loop (afx_measure_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure",
+            "algorithmic_flops": gflops.get(top, 0.0), "frames_per_launch": frames, "rhythm_frames_per_launch": rframes,
+            "note": "every frame kernel computes in FP64 (bit-for-bit decisions of the reference: peak counts, onset thresholds); "
+                    "achieved = SURVEY.md 8(d) algorithmic flops of the group / its CUDA-event time",
+            "step": {"algorithmic_flops": step_flops, "ms": step_ms, "achieved": step_tf, "unit": "TFLOP/s",
+                     "frac_fp64": step_tf / fp64_peak if fp64_peak else None, "frac_fp32_nominal": step_tf / FP32_NOMINAL_TFLOPS,
+                     "flops_per_main_frame": step_flops / max(1, frames)},
+            "hbm": {"achieved": bytes_per_frame * frames / (step_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": bytes_per_frame * frames / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "algorithmic_bytes_per_frame": bytes_per_frame, "peak_source": peak_src + " (MEASURED_PEAKS.json)"},
+            "groups": table,
         }
         # DRAM traffic of the dominant kernel group from the committed `ncu --set full` capture (bytes per main frame
         # there x the frames of this launch); the capture is of the same kernels on a smaller batch of the same files
@@ -538,18 +639,18 @@ def main():
                 roof["traffic"] = per_frame * frames
                 roof["traffic_source"] = tr.get("source")
     except Exception as e:  # the roofline leg must not take the headline number down
-        roof = {"bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
+        roof = {"bound": "fp64", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None,
                 "traffic": None, "error": repr(e)}
 
-    # ---- reported CPU baseline (rank 0, N = 1 only, bounded sample) -----------------------------
+    # ---- reported CPU baseline (rank 0, N = 1 only, bounded sample of the same workload) -----------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and wl["features"] == "all":
         try:
             cores = os.cpu_count() or 1
-            sample = pcms[: reference_sample_files(wl, cores)]
+            sample = reference_sample(wl, cores)
             r = cpu_reference_run(sample, wl["hop"], cores, rate=wl.get("rate", 44100))
             cpu = {"value": r["audio_hours_per_s"], "unit": "audio-hours/s", "cores": r["cores"], "kind": r["kind"],
-                   "sample": "%d files (%.1f s audio), hop %d, %d host threads, FULL low-level set into a sqlite pool"
+                   "sample": "%d files of the workload's corpus (%.1f s audio), hop %d, %d host threads, full low-level set into a sqlite pool"
                              % (len(sample), r["audio_s"], wl["hop"], r["cores"]), "seconds": r["seconds"]}
         except Exception as e:
             cpu = {"value": None, "unit": "audio-hours/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
@@ -559,17 +660,17 @@ def main():
             "metric": "low-level descriptor throughput (audio-hours/sec)", "value": value, "unit": "audio-hours/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "files_per_gpu": wl["files_per_gpu"], "hop": wl["hop"], "fft": 2048,
-                       "features": wl["features"], "parallelism": "file-batch shard per GPU, no collective",
-                       "l2": "inputs (%.2f GB PCM + spectra per step) exceed the 126 MB L2; no flush needed" % (total * 2 / 1e9),
-                       "unique_files": N_UNIQUE},
-            "frames_per_s": frames_per_s, "main_frames_per_step": total_frames,
+            "config": workload_config(wl, world),
+            "frames_per_s": frames_per_s, "rhythm_frames_per_s": total_rframes * args.steps / (dev_ms_max / 1000.0),
+            "main_frames_per_step": total_frames,
             "e2e": {"value": e2e_value, "unit": "audio-hours/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "ms_per_step": 1000.0 * e2e_s / args.steps,
-                    "path": "afx_batch_create -> upload (pinned H2D) -> compute -> download (D2H) -> sync per chunk; 12 chunks per step over 3 contexts / host threads (copies overlap kernels)"},
+                    "ms_per_step": 1000.0 * e2e_s / args.steps, "h2d_gbs_per_gpu": h2d_gbs,
+                    "h2d_note": "copy-only leg: same pinned arena / chunks / slot threads with no kernels, all ranks at once, max over ranks",
+                    "path": "afx_batch_create -> upload (pinned H2D) -> compute -> download (D2H) -> sync per chunk; %d chunks per step over "
+                            "%d contexts / host threads (copies overlap kernels)" % (E2E_CHUNKS, E2E_SLOTS)},
             "gpu_launches": int(cnt["kernel_launches"]) * args.steps * world,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "kernel_group_ms": dict(ktimes) if ktimes else None,
+            "parity_checked": parity_n, "parity_mismatches": parity_errs[:8],
         }
         print(json.dumps(line), flush=True)
     arena.free()

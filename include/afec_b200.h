@@ -41,6 +41,8 @@ extern "C" {
 #define AFX_FILE_OK 0
 #define AFX_FILE_BAD_CHANNELS 1 /* "Unsupported audio file channel layout" (channels outside 1..8) */
 #define AFX_FILE_EMPTY 2        /* "Sample file is empty, probably failed to read." */
+#define AFX_FILE_UNSUPPORTED 3  /* src_rate <= 0, unknown format, or more than INT32_MAX samples (the reference counts samples in
+                                   an int, SampleAnalyser.cpp:484): this file fails, the rest of the batch is analysed */
 
 /* ---- PCM formats -------------------------------------------------------------------------- */
 /* Both are INTERLEAVED frames.  I16 is converted as (float)value, F32 is taken as is: the
@@ -121,7 +123,10 @@ int afx_host_free(afx_ctx* ctx, void* p);
 /* ---- batches ------------------------------------------------------------------------------ */
 /* The stages may be called one by one (upload / compute / download are asynchronous on the
  * context's stream), or all at once through afx_analyze().  PCM memory must stay valid until
- * afx_batch_upload() has been followed by afx_batch_sync() (or afx_analyze() returned). */
+ * afx_batch_upload() has been followed by afx_batch_sync() (or afx_analyze() returned).
+ * The device buffers belong to the context: ONE batch per context may be between afx_batch_upload() and
+ * afx_batch_free() at a time (a second upload returns AFX_ERR_STATE); batches in flight side by side need one
+ * context each, which is how the host adapter's slots overlap copies with kernels. */
 int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_files, afx_batch** out);
 int afx_batch_upload(afx_batch* b);     /* host -> device copies of the PCM + file table */
 int afx_batch_compute(afx_batch* b);    /* all kernels of the configured feature set */

@@ -69,9 +69,43 @@ static double db_to_lin(double v)
 /* TFftTransformComplex::ForwardInplace (AudioTypes/Source/Fourier.cpp:219-274):                */
 /*   X[k] = sum_j x[j] exp(+2 pi i j k / n)                                                    */
 
+/* A second, mathematically identical transform (decimation in frequency: butterflies first, bit reversal last), so   */
+/* that tests can show which outputs of the PATH are decided by the FFT's last-bit rounding -- the situation of the     */
+/* reference itself built with another FFT back end (Fourier.cpp selects IPP / vDSP / Ooura per platform).              */
+static int g_fft_variant = 0;
+void afxo_set_fft_variant(int v) { g_fft_variant = v; }
+
+static void fft_c2c_dif(double* re, double* im, int n, int sign)
+{
+  int i, j, len;
+  for (len = n; len >= 2; len >>= 1) {
+    const int half = len >> 1;
+    for (i = 0; i < n; i += len) {
+      for (j = 0; j < half; ++j) {
+        const double ang = sign * 2.0 * kPi * (double)j / (double)len;
+        const double wr = cos(ang), wi = sin(ang);
+        const double ar = re[i + j], ai = im[i + j], br = re[i + j + half], bi = im[i + j + half];
+        const double dr = ar - br, di = ai - bi;
+        re[i + j] = ar + br; im[i + j] = ai + bi;
+        re[i + j + half] = dr * wr - di * wi; im[i + j + half] = dr * wi + di * wr;
+      }
+    }
+  }
+  for (i = 1, j = 0; i < n; ++i) {
+    int bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) {
+      double t = re[i]; re[i] = re[j]; re[j] = t;
+      t = im[i]; im[i] = im[j]; im[j] = t;
+    }
+  }
+}
+
 static void fft_c2c(double* re, double* im, int n, int sign)
 {
   int i, j, len;
+  if (g_fft_variant) { fft_c2c_dif(re, im, n, sign); return; }
   for (i = 1, j = 0; i < n; ++i) {
     int bit = n >> 1;
     for (; j & bit; bit >>= 1) j ^= bit;

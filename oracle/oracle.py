@@ -47,6 +47,8 @@ def lib():
         L.afxo_flux.restype = C.c_double
         L.afxo_flux.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.afxo_fft.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.afxo_set_fft_variant.argtypes = [C.c_int]
+        L.afxo_set_fft_variant.restype = None
         L.afxo_tables.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.afxo_condition.restype = C.c_int
         L.afxo_condition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -96,6 +98,12 @@ def condition(pcm: np.ndarray, src_rate: int = 44100, sample_rate: int = 44100, 
     ln = L.afxo_condition(planar.ctypes.data, ch, n, src_rate, sample_rate, fft_size, data.ctypes.data,
                           cap, C.byref(off), C.byref(pk), C.byref(rms))
     return data[:ln].copy(), off.value, pk.value, rms.value
+
+
+def set_fft_variant(v: int) -> None:
+    """0: the restatement's decimation-in-time FFT; 1: an identical transform with another rounding order (tests that
+    show which outputs are decided by FFT rounding noise)."""
+    lib().afxo_set_fft_variant(int(v))
 
 
 def scalar_stat(name: str, x) -> float:

@@ -1,15 +1,14 @@
-"""Column-by-column comparison of two afec-ll.db rows (tests only): types and integers exact, REALs and
-msgpack BLOBs within the parity tolerance (1e-4 relative / 1e-6 absolute), BLOB byte lengths equal."""
+"""Comparison of two afec-ll.db rows (tests only).  Column types, TEXT / INTEGER values and BLOB byte lengths must be
+equal; the numeric content is rebuilt into layout.FileResult records and compared by parity.compare -- the same rules
+(1e-4 relative / 1e-6 absolute, integer series exact, the documented ill-conditioned statistics) as every other
+parity test, nothing looser."""
 import sqlite3
 
 import msgpack
 import numpy as np
 
 import parity
-
-# index-weighted / ill-conditioned statistics are compared with parity.compare's exclusions on the arrays
-# themselves (tests/test_gpu_parity.py); here they get the plain tolerance unless listed
-LOOSE_SUFFIXES = ("_centroid", "_spread", "_skewness", "_kurtosis", "_flatness")
+from afec_b200 import layout
 
 
 def rows(path):
@@ -24,6 +23,35 @@ def rows(path):
     return out, sql, pragmas
 
 
+def _unpack(blob):
+    return np.array(msgpack.unpackb(blob), dtype=np.float64)
+
+
+def row_to_result(row: dict) -> layout.FileResult:
+    """The numeric columns of a succeeded row as a FileResult (header scalars that are DB columns, every series, every statistic)."""
+    r = layout.FileResult()
+    for i, n in enumerate(layout.HEADER_NAMES[:23]):
+        r.header[i] = float(row[n + "_R"])
+    for n in layout.FRAMED_SCALARS:
+        r.fs.append(_unpack(row[n + "_VR"]).reshape(-1))
+    for n, nb in layout.FRAMED_VECTORS:
+        v = _unpack(row[n + "_VVR"])
+        r.fv.append(v.reshape(-1, nb) if v.size else np.zeros((0, nb)))
+    r.F = len(r.fs[0]); r.Fr = len(r.fs[layout.N_FS_MAIN])
+    si = 0
+    for n in layout.FRAMED_SCALARS:
+        for k, st in enumerate(layout.STAT_NAMES):
+            r.stats[si, k] = float(row["%s_%s_R" % (n, st)])
+        si += 1
+    for n, nb in layout.FRAMED_VECTORS:
+        for k, st in enumerate(layout.STAT_NAMES):
+            v = _unpack(row["%s_%s_VR" % (n, st)])
+            assert v.shape == (nb,), (n, st, v.shape)
+            r.stats[si:si + nb, k] = v
+        si += nb
+    return r
+
+
 def compare_row(got: dict, want: dict, skip=("filename", "modtime")):
     errs = []
     for k, w in want.items():
@@ -32,24 +60,11 @@ def compare_row(got: dict, want: dict, skip=("filename", "modtime")):
         g = got[k]
         if type(g) is not type(w):
             errs.append("%s: type %s != %s" % (k, type(g).__name__, type(w).__name__))
-            continue
-        if w is None or isinstance(w, (str, int)):
+        elif w is None or isinstance(w, (str, int)):
             if g != w:
                 errs.append("%s: %r != %r" % (k, g, w))
-        elif isinstance(w, float):
-            loose = any(k.endswith(s + "_R") for s in LOOSE_SUFFIXES)
-            if not parity.close(g, w) and not (loose and abs(g - w) <= 1e-3 * max(1.0, abs(w))):
-                errs.append("%s: %r != %r" % (k, g, w))
-        else:
-            if len(g) != len(w):
-                errs.append("%s: blob length %d != %d" % (k, len(g), len(w)))
-                continue
-            a = np.array(msgpack.unpackb(g), dtype=np.float64)
-            b = np.array(msgpack.unpackb(w), dtype=np.float64)
-            ok = parity.close(a, b)
-            if any(k.endswith(s + "_VR") for s in LOOSE_SUFFIXES):
-                ok |= np.abs(a - b) <= 1e-3 * np.maximum(1.0, np.abs(b))
-            if not ok.all():
-                i = np.argwhere(~ok)[0]
-                errs.append("%s: %d values differ, first at %s: %r != %r" % (k, int((~ok).sum()), i.tolist(), a[tuple(i)], b[tuple(i)]))
-    return errs
+        elif isinstance(w, bytes) and len(g) != len(w):
+            errs.append("%s: blob length %d != %d" % (k, len(g), len(w)))
+    if errs or want["status"] != "succeeded":
+        return errs
+    return parity.compare(row_to_result(got), row_to_result(want))

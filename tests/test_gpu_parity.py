@@ -98,6 +98,87 @@ def test_batch_vs_oracle(analysers, feats, oracle_lib, hop):
         check(g, want, feats)
 
 
+# every k_spectrum instantiation the launcher can pick (afx_spectrum.cu: <10, false> without the pitch / amplitude code
+# for the spectral-only subset of BASELINE configs[1], <10, true> otherwise) meets the oracle
+SUBSETS = [api.FEAT_SPECTRAL, api.FEAT_SPECTRAL | api.FEAT_STATS, api.FEAT_SPECTRAL | api.FEAT_AMPLITUDE | api.FEAT_STATS,
+           api.FEAT_SPECTRAL | api.FEAT_PEAKS | api.FEAT_BANDS | api.FEAT_STATS]
+
+
+@pytest.mark.parametrize("features", SUBSETS, ids=["spectral", "spectral+stats", "spectral+amplitude+stats", "spectral+peaks+bands+stats"])
+@pytest.mark.parametrize("hop", [512, 1024])
+def test_feature_subsets_vs_oracle(oracle_lib, hop, features):
+    """The feature-mask subsets (include/afec_b200.h AFX_FEAT_*) against the oracle: BASELINE configs[1] runs
+    FEAT_SPECTRAL alone at hop 512."""
+    pcms = [synth.one_shot(400 + i, 0.3 + 0.4 * i) for i in range(6)]
+    pcms.append(synth.one_shot(410, 0.9, channels=2))
+    pcms.append(synth.one_shot(411, 0.02))
+    pcms.append(np.zeros(30000, dtype=np.int16))
+    pcms.append(synth.one_shot(412, 21.5))
+    an = api.SampleAnalyser(44100, 2048, hop, features=features)
+    got = an.analyze_pcm(pcms, [44100] * len(pcms))
+    an.close()
+    for g, p in zip(got, pcms):
+        want = oracle_lib.analyze(p, hop=hop, file_size=44 + p.size * p.itemsize)
+        errs = parity.compare(g, want, only_series=series_for(features), check_stats=bool(features & api.FEAT_STATS),
+                              check_header=False, mdata=oracle_lib.condition(p)[0], hop=hop)
+        assert not errs, "\n".join(errs[:25])
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["rate"] == 44100], ids=[c["name"] for c in CASES if c["rate"] == 44100])
+def test_golden_reference_vectors_spectral_subset(case):
+    """The reference's own vectors against the spectral-only instantiation (the kernel BASELINE configs[1] times)."""
+    an = api.SampleAnalyser(44100, 2048, case["hop"], features=api.FEAT_SPECTRAL)
+    got = an.analyze_pcm([case["pcm"]], [case["rate"]])[0]
+    an.close()
+    errs = parity.compare(got, case["ref"], only_series=SPECTRAL, check_stats=False, check_header=False)
+    assert not errs, "\n".join(errs[:25])
+
+
+def test_unsupported_description_fails_that_file_only(analysers, feats, oracle_lib):
+    """A file description the kernels cannot take (rate <= 0, unknown format) gets AFX_FILE_UNSUPPORTED; its
+    neighbours are analysed (the reference fails files one by one, SampleAnalyser.cpp:372-408)."""
+    good = synth.one_shot(601, 0.5)
+    an = analysers(1024)
+    f_good, keep = an.describe(good, 44100)
+    f_rate, _ = an.describe(good, 44100); f_rate.src_rate = -5
+    f_fmt, _ = an.describe(good, 44100); f_fmt.format = 7
+    b = an.batch_from_descriptors([f_good, f_rate, f_fmt, f_good], keep).run()
+    got = [b.result(i) for i in range(4)]
+    b.free()
+    assert [g.status for g in got] == [0, 3, 3, 0]
+    want = oracle_lib.analyze(good, file_size=44 + good.size * 2)
+    check(got[0], want, feats)
+    check(got[3], want, feats)
+
+
+def test_many_resampler_shapes_in_one_batch(analysers, oracle_lib):
+    """More distinct (rate, length) resampler shapes in ONE batch than the process-wide shape cache holds: every file
+    must still get its own libresample time stamps (a stale cache entry once gave a file another file's)."""
+    rng = np.random.default_rng(5)
+    base = synth.one_shot(950, 0.4, rate=48000)
+    pcms = [np.ascontiguousarray(base[: 6000 + 17 * i]) for i in range(600)]
+    an = analysers(1024)
+    b = an.batch(pcms, [48000] * len(pcms)).run()
+    for i in rng.choice(len(pcms), 24, replace=False).tolist() + [0, 1, 255, 256, 257, 511, 512, 513, 599]:
+        data = oracle_lib.condition(pcms[i], src_rate=48000)[0]
+        got = b.conditioned(i)
+        assert got.shape == data.shape and np.array_equal(got, data), "file %d" % i
+    b.free()
+
+
+def test_one_live_batch_per_context(analysers):
+    """include/afec_b200.h: a second batch may not be uploaded on a context while another one is alive."""
+    an = analysers(1024)
+    p = synth.one_shot(602, 0.3)
+    b1 = an.batch([p], [44100]).run()
+    b2 = an.batch([p], [44100])
+    with pytest.raises(api.AfxError):
+        b2.upload()
+    b1.free()
+    b2.run()
+    b2.free()
+
+
 def test_conditioning_bit_exact(analysers, oracle_lib):
     """mData (SampleAnalyser.cpp:698-718) must be bit-identical: integer trim / pad + one multiply."""
     pcms = [synth.one_shot(500 + i, 0.2 + 0.3 * i, channels=1 + (i % 3)) for i in range(5)]
