@@ -298,6 +298,7 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   for (int i = -12; i < 13; ++i) P.canny[i + 12] = (double)i / (16.0 * 16.0) * std::exp(-1.0 * (i * i) / (2.0 * 16.0 * 16.0));
   if (getenv("AFX_GROUP_FRAMES")) ctx->group_frames = std::max(1LL, atoll(getenv("AFX_GROUP_FRAMES")));
   if (getenv("AFX_GROUP_RFRAMES")) ctx->group_rframes = std::max(1LL, atoll(getenv("AFX_GROUP_RFRAMES")));
+  if (getenv("AFX_RHYTHM_FUSED")) ctx->rhythm_fused_min = atoi(getenv("AFX_RHYTHM_FUSED")) != 0 ? 0 : 0x7fffffff;
 
   // ---- constant tables ----
   std::vector<double> window(N), rwindow(AFX_RFFT), mel, dct(14 * 14);
@@ -601,7 +602,9 @@ extern "C" int afx_batch_upload(afx_batch* b)
     CK(ctx->d_bandraw.reserve((GS + 1) * 154 * 8), "cudaMalloc(bandraw)");
   }
   if (feat & AFX_FEAT_RHYTHM) {
-    CK(ctx->d_rpolar.reserve((GR + 1) * AFX_RROW * 4), "cudaMalloc(rpolar)");
+    size_t GRs = 0;                                  // polar rows only exist for the groups that take the split rhythm kernels
+    for (const auto& g : b->groups) if (!ctx->rhythm_fused(g.nfiles)) GRs = std::max(GRs, (size_t)g.nrslots);
+    if (GRs) CK(ctx->d_rpolar.reserve((GRs + 1) * AFX_RROW * 4), "cudaMalloc(rpolar)");
     CK(ctx->d_rodf.reserve((TFr + 1) * 2 * 4), "cudaMalloc(rodf)");
     CK(ctx->d_rpost.reserve((TFr + 1) * 2 * 4), "cudaMalloc(rpost)");
     CK(ctx->d_scratch.reserve((GR + 1) * 4 * 8 + 1024), "cudaMalloc(scratch)");
@@ -706,6 +709,7 @@ extern "C" int afx_batch_compute(afx_batch* b)
   for (const auto& g : b->groups) {
     AfxBatchDev D = b->dev;
     D.file0 = g.file0; D.g_files = g.nfiles; D.slot0 = g.slot0; D.g_slots = g.nslots; D.rslot0 = g.rslot0; D.g_rslots = g.nrslots;
+    D.rhythm_fused = ctx->rhythm_fused(g.nfiles) ? 1 : 0;
     // every chain keeps to its own stream across groups, so the reuse of a chain's group scratch stays ordered
 #ifdef AFX_HAVE_AUTOCORR
     if (feat & AFX_FEAT_AUTOCORR) { ktime_begin(b, "autocorr"); afx_launch_autocorr(ctx->P, D, s_ac, &b->launches); ktime_end(b); }

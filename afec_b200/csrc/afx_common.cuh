@@ -284,6 +284,7 @@ struct AfxBatchDev {
   double* header;     // [n_files][32]
   double* scratch;    // [g_rslots][4] rhythm back-end workspace (group scratch)
   int max_fr;         // largest rhythm frame capacity of any file in the batch
+  int rhythm_fused;   // this launch group's rhythm front end runs as ONE kernel with a CTA per file (k_rhythm_front); else the split kernels over rpolar
 };
 
 struct RsBlock { int out0; int nout; long long in0; long long chk_off; int span; int pad; };   // in0: source index of X[0] (may be negative); chk_off: first time checkpoint; span: X[0 .. span) covers every sample the block's filter sums read

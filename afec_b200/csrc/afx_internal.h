@@ -77,6 +77,10 @@ struct afx_ctx {
   bool debug_times = false;
   std::mutex mu;
   int max_frame_cap = 0;
+  // launch groups with at least this many files run the fused rhythm front end (one CTA per file); smaller groups cannot
+  // fill the GPU that way and take the split kernels.  AFX_RHYTHM_FUSED=0 / 1 forces never / always (parity tests compare the two)
+  int rhythm_fused_min = 96;
+  bool rhythm_fused(int g_files) const { return g_files >= rhythm_fused_min; }
   struct afx_batch* live = nullptr;   // the one batch whose data occupies the device buffers (afx_batch_upload .. afx_batch_free)
 };
 

@@ -95,6 +95,51 @@ __device__ __forceinline__ void polar_store(float* __restrict__ row, int k, doub
   row[k] = (float)sqrt_mag_r(fma(X.x, X.x, X.y * X.y));                           // OnsetDetector.cpp:136-155
   row[256 + k] = (float)atan2_phase(X.y, X.x);
 }
+// windowed frame of one 16-thread group: v[r] = packed samples (2m, 2m + 1), m = ht + 16 r   (OnsetDetector.cpp:119-120)
+__device__ __forceinline__ void polar_load(double2 (&v)[16], const float* __restrict__ mono, const AfxState& st, int n0, bool live, int ht,
+                                           const double2* __restrict__ win2)
+{
+  const int j0 = n0 - st.start_off;                 // frame start relative to the first audible sample
+  const float* __restrict__ src = mono + st.lead + j0;
+  if (live && j0 >= 0 && j0 + AFX_RFFT <= st.audible) {     // whole frame inside the audible span (the common case)
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int m = ht + 16 * r;
+      const double2 w = __ldg(win2 + m);
+      v[r] = make_double2(w.x * ((double)__ldg(src + 2 * m) * st.fs), w.y * ((double)__ldg(src + 2 * m + 1) * st.fs));
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int m = ht + 16 * r;
+      const double2 w = __ldg(win2 + m);
+      const double x0 = live ? mdata(mono, st, n0 + 2 * m) : 0.0, x1 = live ? mdata(mono, st, n0 + 2 * m + 1) : 0.0;
+      v[r] = make_double2(w.x * x0, w.y * x1);
+    }
+  }
+}
+// real unpack of the packed transform in buf + polar conversion into row[0..254] (mag) | row[255] (dc) | row[256..510] (phase)
+__device__ __forceinline__ void polar_unpack(float* __restrict__ row, const double2* __restrict__ buf, int ht, const double2* __restrict__ tw512)
+{
+#pragma unroll 2                                             // the body holds two inlined atan2 + sqrt: keep the code small
+  for (int c = 0; c < 8; ++c) {
+    const int k = ht + 16 * c;                               // 0..127, mirror 256 - k
+    const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((256 - k) & 255)];
+    const double2 E = make_double2(zk.x + zc.x, zk.y - zc.y);
+    const double2 O = make_double2(zk.y + zc.y, zc.x - zk.x);
+    const double2 T = f_mul(__ldg(tw512 + k), O);
+    double2 Xa = f_add(E, T);
+    double2 Xb = make_double2(E.x - T.x, T.y - E.y);        // conj(E - T)
+    int kb = 256 - k;
+    if (c == 0 && ht == 0) {
+      Xa.y = 0.0; row[255] = (float)Xa.x;                    // mDC, OnsetDetector.cpp:146
+      const double2 z = buf[FFT_PHYS(128)];
+      Xb = make_double2(2.0 * z.x, -2.0 * z.y); kb = 128;
+    }
+    if (kb < AFX_RBINS) polar_store(row, kb, Xb);
+    polar_store(row, k, Xa);
+  }
+}
 __global__ void __launch_bounds__(PF * 16, 5) k_rhythm_polar(AfxBatchDev B, AfxParams P)
 {
   __shared__ double2 sbuf[PF][256 + 16];
@@ -108,51 +153,11 @@ __global__ void __launch_bounds__(PF * 16, 5) k_rhythm_polar(AfxBatchDev B, AfxP
   const int t = slot - fp->rframe_off;
   const AfxState st = B.state[fi];
   const bool live = in_range && fp->status == 0 && t < st.Fr;   // both halves of a warp run the transform (warp-wide sync)
-  const float* __restrict__ mono = B.mono + fp->mono_off;
-  const double2* __restrict__ win2 = reinterpret_cast<const double2*>(P.t.rwindow);
-  const int n0 = t * AFX_RHOP;
   double2 v[16];
-  {
-    const int j0 = n0 - st.start_off;                 // frame start relative to the first audible sample
-    const float* __restrict__ src = mono + st.lead + j0;
-    if (live && j0 >= 0 && j0 + AFX_RFFT <= st.audible) {     // whole frame inside the audible span (the common case)
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const int m = ht + 16 * r;
-        const double2 w = __ldg(win2 + m);
-        v[r] = make_double2(w.x * ((double)__ldg(src + 2 * m) * st.fs), w.y * ((double)__ldg(src + 2 * m + 1) * st.fs));   // OnsetDetector.cpp:119-120
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const int m = ht + 16 * r;
-        const double2 w = __ldg(win2 + m);
-        const double x0 = live ? mdata(mono, st, n0 + 2 * m) : 0.0, x1 = live ? mdata(mono, st, n0 + 2 * m + 1) : 0.0;
-        v[r] = make_double2(w.x * x0, w.y * x1);
-      }
-    }
-  }
+  polar_load(v, B.mono + fp->mono_off, st, t * AFX_RHOP, live, ht, reinterpret_cast<const double2*>(P.t.rwindow));
   fft16_run<256>(v, buf, FftTw{ P.t.fft_t2, nullptr }, ht, FftSyncWarp());
   if (!live) return;
-  float* row = B.rpolar + (size_t)rel * AFX_RROW;
-#pragma unroll 2                                             // the body holds two inlined atan2 + sqrt: keep the code small
-  for (int c = 0; c < 8; ++c) {
-    const int k = ht + 16 * c;                               // 0..127, mirror 256 - k
-    const double2 zk = buf[FFT_PHYS(k)], zc = buf[FFT_PHYS((256 - k) & 255)];
-    const double2 E = make_double2(zk.x + zc.x, zk.y - zc.y);
-    const double2 O = make_double2(zk.y + zc.y, zc.x - zk.x);
-    const double2 T = f_mul(__ldg(P.t.tw512 + k), O);
-    double2 Xa = f_add(E, T);
-    double2 Xb = make_double2(E.x - T.x, T.y - E.y);        // conj(E - T)
-    int kb = 256 - k;
-    if (c == 0 && ht == 0) {
-      Xa.y = 0.0; row[255] = (float)Xa.x;                    // mDC, OnsetDetector.cpp:146
-      const double2 z = buf[FFT_PHYS(128)];
-      Xb = make_double2(2.0 * z.x, -2.0 * z.y); kb = 128;
-    }
-    if (kb < AFX_RBINS) polar_store(row, kb, Xb);
-    polar_store(row, k, Xa);
-  }
+  polar_unpack(B.rpolar + (size_t)rel * AFX_RROW, buf, ht, P.t.tw512);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -195,6 +200,29 @@ __global__ void __launch_bounds__(256) k_rhythm_whiten(AfxBatchDev B, AfxParams 
 // every polar row is read once, unconditionally -- loads of the next rows are in flight while a frame is evaluated.
 #define OB 8                // frames per warp
 #define OW 8                // warps per CTA
+// one bin of the rectified complex-domain function (OnsetDetector.cpp:440-470): cur / pmv = whitened |mag| of this and the
+// previous frame, ph / yp / yp2 = phases of this and the previous two frames
+__device__ __forceinline__ float odf_complex_bin(float cur, float pmv, float ph, float yp, float yp2, bool has_prev)
+{
+  const float ypd = has_prev ? phase_rewrap(__fsub_rn(yp, yp2)) : 0.0f;
+  const float pred = __fadd_rn(yp, ypd);
+  const float dev = __fsub_rn(pred, ph);
+  const float cs = cosf(phase_rewrap(dev));
+  const float q = __fsub_rn(__fadd_rn(__fmul_rn(pmv, pmv), __fmul_rn(cur, cur)), __fmul_rn(__fmul_rn(pmv, cur), cs));
+  return sqrtf(q);
+}
+// the power function of one whitened row: float32 sum of the squared bins in bin order (the reference's rounding, :388-396)
+__device__ __forceinline__ float odf_power_row(const float4* __restrict__ row, float dc)
+{
+  float v = __fadd_rn(__fmul_rn(0.0f, 0.0f), __fmul_rn(dc, dc));            // nyq^2 + dc^2
+#pragma unroll 8
+  for (int i = 0; i < 63; ++i) {
+    const float4 q = row[i];
+    v = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(v, __fmul_rn(q.x, q.x)), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)), __fmul_rn(q.w, q.w));
+  }
+  { const float4 q = row[63]; v = __fadd_rn(__fadd_rn(__fadd_rn(v, __fmul_rn(q.x, q.x)), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)); }
+  return v;
+}
 __global__ void __launch_bounds__(OW * 32) k_rhythm_odf(AfxBatchDev B, AfxParams P)
 {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -228,16 +256,8 @@ __global__ void __launch_bounds__(OW * 32) k_rhythm_odf(AfxBatchDev B, AfxParams
       const int i = lane + 32 * c;
       const float cur = fabsf(m[c]);
       const float pmv = (t >= 1) ? pm[c] : 0.0f;
-      if (i < AFX_RBINS && cur > 0.01f && !(cur < pmv)) {
-        const float yp = (t >= 1) ? ph1[c] : 0.0f;
-        const float yp2 = (t >= 2) ? ph2[c] : 0.0f;
-        const float ypd = (t >= 1) ? phase_rewrap(__fsub_rn(yp, yp2)) : 0.0f;
-        const float pred = __fadd_rn(yp, ypd);
-        const float dev = __fsub_rn(pred, ph[c]);
-        const float cs = cosf(phase_rewrap(dev));
-        const float q = __fsub_rn(__fadd_rn(__fmul_rn(pmv, pmv), __fmul_rn(cur, cur)), __fmul_rn(__fmul_rn(pmv, cur), cs));
-        total += (double)sqrtf(q);
-      }
+      if (i < AFX_RBINS && cur > 0.01f && !(cur < pmv))
+        total += (double)odf_complex_bin(cur, pmv, ph[c], (t >= 1) ? ph1[c] : 0.0f, (t >= 2) ? ph2[c] : 0.0f, t >= 1);
       pm[c] = cur; ph2[c] = ph1[c]; ph1[c] = ph[c];
     }
     total = warp_sum(total);
@@ -245,8 +265,7 @@ __global__ void __launch_bounds__(OW * 32) k_rhythm_odf(AfxBatchDev B, AfxParams
   }
 }
 
-// The power function is a float32 sum of the squared bins in bin order (the reference's rounding, :388-396): one
-// thread per frame adds its row; a warp's 16-byte loads touch 32 rows, both halves of every sector get used (L1).
+// One thread per frame adds its row; a warp's 16-byte loads touch 32 rows, both halves of every sector get used (L1).
 __global__ void __launch_bounds__(128) k_rhythm_power(AfxBatchDev B, AfxParams P)
 {
   const int rel = blockIdx.x * 128 + threadIdx.x;
@@ -255,16 +274,95 @@ __global__ void __launch_bounds__(128) k_rhythm_power(AfxBatchDev B, AfxParams P
   const int fi = B.rslot_file[slot];
   const int t = slot - B.files[fi].rframe_off;
   if (B.files[fi].status != 0 || t >= B.state[fi].Fr) return;
-  const float4* row = reinterpret_cast<const float4*>(B.rpolar + (size_t)rel * AFX_RROW);
-  const float dc = B.rpolar[(size_t)rel * AFX_RROW + 255];
-  float v = __fadd_rn(__fmul_rn(0.0f, 0.0f), __fmul_rn(dc, dc));            // nyq^2 + dc^2
-#pragma unroll 8
-  for (int i = 0; i < 63; ++i) {
-    const float4 q = row[i];
-    v = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(v, __fmul_rn(q.x, q.x)), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)), __fmul_rn(q.w, q.w));
-  }
-  { const float4 q = row[63]; v = __fadd_rn(__fadd_rn(__fadd_rn(v, __fmul_rn(q.x, q.x)), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)); }
+  const float v = odf_power_row(reinterpret_cast<const float4*>(B.rpolar + (size_t)rel * AFX_RROW), B.rpolar[(size_t)rel * AFX_RROW + 255]);
   B.rodf[(size_t)B.TFr + slot] = __fmul_rn(v, P.r_norm_power);
+}
+
+// -------------------------------------------------------------------------------------------------
+// The fused front end: ONE kernel, one CTA per file (longest first), the polar rows never leave shared memory.
+// A CTA walks its file in spans of RF_S rhythm frames:
+//   1. 16 threads per frame: window, 256-point packed FFT, real unpack, polar conversion -> float32 row in the ring
+//   2. whitening (OnsetDetector.cpp:193-243): every thread owns two of the 256 columns and walks the span's rows in
+//      frame order; the per-bin peak memories live in registers for the whole file
+//   3. onset functions: warps 0..2 evaluate the complex-domain function of the span's frames (one frame per warp and
+//      turn), warp 3 runs the in-order float32 power sums, one lane per frame
+// The row ring holds RF_S + 2 rows (frame t at position t mod (RF_S + 2)): the two frames before a span stay where the
+// previous span left them.  Values are those of the split kernels above bit for bit (same device functions, same order
+// of every sum); the split path remains for launch groups with too few files to fill the GPU with one CTA per file.
+#define RF_S 8
+#define RF_THREADS (RF_S * 16)
+#define RF_RING (RF_S + 2)
+#define RF_ROW 516          // floats per ring row: 512 + 4 (rows start on different banks for the lane-per-row power sums)
+#define RF_SMEM (RF_S * (256 + 16) * 16 + RF_RING * RF_ROW * 4)
+__global__ void __launch_bounds__(RF_THREADS, 4) k_rhythm_front(AfxBatchDev B, AfxParams P)
+{
+  extern __shared__ __align__(16) unsigned char rf_smem[];
+  double2* sbuf = reinterpret_cast<double2*>(rf_smem);
+  float* ring = reinterpret_cast<float*>(rf_smem + RF_S * (256 + 16) * 16);
+  const int tid = threadIdx.x, h = tid >> 4, ht = tid & 15, lane = tid & 31, wid = tid >> 5;
+  const int fi = B.file_order[B.file0 + blockIdx.x];
+  const AfxFile* __restrict__ fp = B.files + fi;
+  if (fp->status != 0) return;
+  const AfxState st = B.state[fi];
+  const int Fr = st.Fr;
+  if (Fr <= 0) return;
+  const float* __restrict__ mono = B.mono + fp->mono_off;
+  const double2* __restrict__ win2 = reinterpret_cast<const double2*>(P.t.rwindow);
+  double2* buf = sbuf + h * (256 + 16);
+  float* __restrict__ odf_c = B.rodf + fp->rframe_off;
+  float* __restrict__ odf_p = B.rodf + (size_t)B.TFr + fp->rframe_off;
+  const double relax = (double)P.r_relax, wfloor = (double)0.1f;
+  double psp0 = 0.0, psp1 = 0.0;                            // peak memories of columns tid and tid + 128 (255 = dc)
+  for (int t0 = 0; t0 < Fr; t0 += RF_S) {
+    const int nlive = min(RF_S, Fr - t0);
+    // ---- 1. transform (both halves of a warp run it: warp-wide sync inside)
+    {
+      const bool live = h < nlive;
+      double2 v[16];
+      polar_load(v, mono, st, (t0 + h) * AFX_RHOP, live, ht, win2);
+      fft16_run<256>(v, buf, FftTw{ P.t.fft_t2, nullptr }, ht, FftSyncWarp());
+      __syncthreads();                                       // the previous span's onset functions are done with the ring
+      if (live) polar_unpack(ring + ((t0 + h) % RF_RING) * RF_ROW, buf, ht, P.t.tw512);
+    }
+    __syncthreads();
+    // ---- 2. whitening, in place
+    for (int k = 0; k < nlive; ++k) {
+      float* row = ring + ((t0 + k) % RF_RING) * RF_ROW;
+      const float v0 = row[tid], v1 = row[tid + 128];
+      double a0 = (double)fabsf(v0), a1 = (double)fabsf(v1);
+      if (a0 < psp0) a0 = __dadd_rn(a0, __dmul_rn(__dsub_rn(psp0, a0), relax));
+      if (a1 < psp1) a1 = __dadd_rn(a1, __dmul_rn(__dsub_rn(psp1, a1), relax));
+      psp0 = a0; psp1 = a1;
+      row[tid] = __fdiv_rn(v0, (float)(wfloor > psp0 ? wfloor : psp0));
+      row[tid + 128] = __fdiv_rn(v1, (float)(wfloor > psp1 ? wfloor : psp1));
+    }
+    __syncthreads();
+    // ---- 3. onset functions
+    if (wid < 3) {
+#pragma unroll 1
+      for (int k = wid; k < nlive; k += 3) {
+        const int t = t0 + k;
+        const float* r0 = ring + (t % RF_RING) * RF_ROW;
+        const float* r1 = ring + ((t + RF_RING - 1) % RF_RING) * RF_ROW;
+        const float* r2 = ring + ((t + RF_RING - 2) % RF_RING) * RF_ROW;
+        double total = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int i = lane + 32 * c;
+          const float cur = fabsf(r0[i]);
+          const float pmv = (t >= 1) ? fabsf(r1[i]) : 0.0f;
+          if (i < AFX_RBINS && cur > 0.01f && !(cur < pmv))
+            total += (double)odf_complex_bin(cur, pmv, r0[256 + i], (t >= 1) ? r1[256 + i] : 0.0f, (t >= 2) ? r2[256 + i] : 0.0f, t >= 1);
+        }
+        total = warp_sum(total);
+        if (lane == 0) odf_c[t] = __fmul_rn((float)total, P.r_norm_complex);
+      }
+    } else if (lane < nlive) {
+      const int t = t0 + lane;
+      const float* r0 = ring + (t % RF_RING) * RF_ROW;
+      odf_p[t] = __fmul_rn(odf_power_row(reinterpret_cast<const float4*>(r0), r0[255]), P.r_norm_power);
+    }
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -669,11 +767,16 @@ void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s,
   const int cap = B.max_fr;
   const int smem_back = (cap + 32) * 8 + ((cap + 15) & ~15) + ((cap + 31) / 32) * 4 + 16;
   cudaFuncSetAttribute(k_rhythm_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);   // per device, see afx_pitch.cu
-  const int fb = (B.g_rslots + OW * OB - 1) / (OW * OB);
-  k_rhythm_polar<<<(B.g_rslots + PF - 1) / PF, PF * 16, 0, s>>>(B, P); ++*launches;
-  k_rhythm_whiten<<<B.g_files, 256, 0, s>>>(B, P); ++*launches;
-  k_rhythm_odf<<<fb, OW * 32, 0, s>>>(B, P); ++*launches;
-  k_rhythm_power<<<(B.g_rslots + 127) / 128, 128, 0, s>>>(B, P); ++*launches;
+  if (B.rhythm_fused) {     // one CTA per file: chosen per launch group by afx_batch_compute (enough files to fill the GPU that way)
+    cudaFuncSetAttribute(k_rhythm_front, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SMEM);
+    k_rhythm_front<<<B.g_files, RF_THREADS, RF_SMEM, s>>>(B, P); ++*launches;
+  } else {
+    const int fb = (B.g_rslots + OW * OB - 1) / (OW * OB);
+    k_rhythm_polar<<<(B.g_rslots + PF - 1) / PF, PF * 16, 0, s>>>(B, P); ++*launches;
+    k_rhythm_whiten<<<B.g_files, 256, 0, s>>>(B, P); ++*launches;
+    k_rhythm_odf<<<fb, OW * 32, 0, s>>>(B, P); ++*launches;
+    k_rhythm_power<<<(B.g_rslots + 127) / 128, 128, 0, s>>>(B, P); ++*launches;
+  }
   { const int nchunks = (B.g_rslots + ML - 1) / ML; k_rhythm_median<<<(2 * nchunks + 63) / 64, 64, 0, s>>>(B); ++*launches; }
   k_rhythm_back<<<B.g_files, BT_THREADS, smem_back, s>>>(B, P); ++*launches;
 }

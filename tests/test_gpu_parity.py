@@ -281,6 +281,30 @@ def test_launch_groups_do_not_change_results(feats, monkeypatch):
         assert np.array_equal(g.stats, w.stats)
 
 
+def test_rhythm_front_end_fused_equals_split(feats, monkeypatch, oracle_lib):
+    """The rhythm front end has two schedules (afx_rhythm.cu): ONE fused kernel with a CTA per file (launch groups with
+    many files) and the split polar / whiten / odf / power kernels (few files).  Both must give the same bits, and both
+    must meet the oracle."""
+    pcms = [synth.one_shot(820 + i, 0.3 + 0.45 * i) for i in range(7)]
+    pcms += [synth.one_shot(830, 21.5), synth.one_shot(831, 0.02), np.zeros(30000, dtype=np.int16),
+             synth.one_shot(832, 0.9, channels=2), np.zeros((0,), dtype=np.int16), synth.one_shot(833, 0.1)]
+    rates = [44100] * len(pcms)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("AFX_RHYTHM_FUSED", mode)
+        an = api.SampleAnalyser(44100, 2048, 1024, features=feats)
+        out[mode] = an.analyze_pcm(pcms, rates)
+        an.close()
+    for g, w, p in zip(out["1"], out["0"], pcms):
+        assert g.status == w.status and (g.F, g.Fr) == (w.F, w.Fr)
+        assert np.array_equal(g.header, w.header)
+        for a, b in zip(g.fs + g.fv, w.fs + w.fv):
+            assert np.array_equal(a, b)
+        assert np.array_equal(g.stats, w.stats)
+        if g.status == 0:
+            check(g, oracle_lib.analyze(p, file_size=44 + p.size * p.itemsize), feats, mdata=oracle_lib.condition(p)[0])
+
+
 def test_resampled_batch_vs_oracle(analysers, feats, oracle_lib):
     """Files at other rates go through the libresample restatement (SampleAnalyser.cpp:563-607)."""
     cases = [(synth.one_shot(900, 0.5, rate=96000, channels=2), 96000), (synth.one_shot(901, 0.6, rate=22050), 22050),
