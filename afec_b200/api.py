@@ -18,6 +18,7 @@ AFX_PCM_I16, AFX_PCM_F32 = 0, 1
 FEAT_SPECTRAL, FEAT_AMPLITUDE, FEAT_PEAKS, FEAT_BANDS = 1, 2, 4, 8
 FEAT_PITCH, FEAT_AUTOCORR, FEAT_RHYTHM, FEAT_STATS = 16, 32, 64, 128
 FEAT_ALL = 0xFF
+FEAT_HIGHLEVEL = 0x100   # on top of FEAT_ALL: model-free high-level descriptors + the classification feature vector
 HAVE_RESAMPLE = True   # k_resample + host block plan (libresample HQ restatement)
 
 EXPORTS = [
@@ -42,9 +43,10 @@ class AfxFile(C.Structure):
 
 class AfxFileResult(C.Structure):
     _fields_ = [("status", C.c_int32), ("n_frames", C.c_int32), ("n_rhythm_frames", C.c_int32),
-                ("reserved", C.c_int32), ("header", C.POINTER(C.c_double)),
+                ("hl_status", C.c_int32), ("header", C.POINTER(C.c_double)),
                 ("fs", C.POINTER(C.c_double) * layout.N_FS), ("fv", C.POINTER(C.c_double) * layout.N_FV),
-                ("stats", C.POINTER(C.c_double))]
+                ("stats", C.POINTER(C.c_double)), ("highlevel", C.POINTER(C.c_double)), ("hl_pitch", C.POINTER(C.c_double)),
+                ("hl_signature", C.POINTER(C.c_double)), ("hl_features", C.POINTER(C.c_double))]
 
 
 class AfxPart(C.Structure):
@@ -212,6 +214,23 @@ class Batch:
         if r.stats:
             out.stats = np.ctypeslib.as_array(r.stats, (layout.N_SERIES * layout.N_STATS,)).copy().reshape(
                 layout.N_SERIES, layout.N_STATS)
+        return out
+
+    def highlevel(self, i: int) -> layout.HighLevelResult:
+        """File i's high-level derivations + classification features (contexts created with FEAT_HIGHLEVEL)."""
+        r = self.raw_result(i)
+        out = layout.HighLevelResult(status=r.status if r.status else (100 if r.hl_status else 0), F=r.n_frames)
+        if r.status != 0:
+            return out
+        if not r.highlevel:
+            raise AfxError("the context was not created with FEAT_HIGHLEVEL")
+        F = r.n_frames
+        out.scalars = np.ctypeslib.as_array(r.highlevel, (layout.N_HL,)).copy()
+        out.pitch = np.ctypeslib.as_array(r.hl_pitch, (F,)).copy() if F > 0 else np.zeros(0)
+        out.peak = np.ctypeslib.as_array(r.fs[1], (F,)).copy() if F > 0 else np.zeros(0)
+        out.signature = np.ctypeslib.as_array(r.hl_signature, (layout.HL_SIGNATURE_FRAMES * layout.HL_SIGNATURE_BANDS,)).copy().reshape(
+            layout.HL_SIGNATURE_FRAMES, layout.HL_SIGNATURE_BANDS)
+        out.features = np.ctypeslib.as_array(r.hl_features, (layout.HL_N_FEATURES,)).copy()
         return out
 
     def free(self):

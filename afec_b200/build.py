@@ -21,7 +21,7 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--prec-div=tr
          "--ftz=false", "-Xptxas", "-v" if os.environ.get("AFX_PTXAS_V") else "-O3"]
 
 SOURCES = ["afx_api.cu", "afx_condition.cu", "afx_spectrum.cu", "afx_peaks.cu", "afx_bands.cu",
-           "afx_pitch.cu", "afx_autocorr.cu", "afx_rhythm.cu", "afx_stats.cu", "afx_debug.cu", "afx_part.cu"]
+           "afx_pitch.cu", "afx_autocorr.cu", "afx_rhythm.cu", "afx_stats.cu", "afx_debug.cu", "afx_part.cu", "afx_highlevel.cu"]
 DEFINES = {"afx_peaks.cu": "AFX_HAVE_PEAKS", "afx_bands.cu": "AFX_HAVE_BANDS", "afx_pitch.cu": "AFX_HAVE_PITCH",
            "afx_autocorr.cu": "AFX_HAVE_AUTOCORR", "afx_rhythm.cu": "AFX_HAVE_RHYTHM", "afx_stats.cu": "AFX_HAVE_STATS"}
 
@@ -64,7 +64,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
-        run([NVCC] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs + ["-cudart", "static"])
+        # link under a temporary name and rename: a gpurun snapshot taken meanwhile never sees a half-written library
+        run([NVCC] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB + ".tmp"] + objs + ["-cudart", "static"])
+        os.replace(LIB + ".tmp", LIB)
     build_host(force=force or bool(jobs), verbose=verbose)
     return LIB
 
@@ -93,10 +95,12 @@ def build_host(force: bool = False, verbose: bool = False):
             raise RuntimeError("host build failed: " + cmd[-1])
 
     if force or _stale(HOST_LIB, deps):
-        run([cxx] + common + ["-shared", "-o", HOST_LIB] + srcs + ["-L" + CSRC, "-lafec_b200", SQLITE] + rpath)
+        run([cxx] + common + ["-shared", "-o", HOST_LIB + ".tmp"] + srcs + ["-L" + CSRC, "-lafec_b200", SQLITE] + rpath)
+        os.replace(HOST_LIB + ".tmp", HOST_LIB)
     if force or _stale(CRAWLER, deps + [os.path.join(HOST, "crawler_main.cpp"), HOST_LIB]):
-        run([cxx] + common + ["-o", CRAWLER, os.path.join(HOST, "crawler_main.cpp"), "-L" + HOST, "-lafec_b200_host",
+        run([cxx] + common + ["-o", CRAWLER + ".tmp", os.path.join(HOST, "crawler_main.cpp"), "-L" + HOST, "-lafec_b200_host",
                               "-L" + CSRC, "-lafec_b200", SQLITE] + rpath)
+        os.replace(CRAWLER + ".tmp", CRAWLER)
     return HOST_LIB
 
 

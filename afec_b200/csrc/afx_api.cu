@@ -234,6 +234,8 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
     return fail(nullptr, AFX_ERR_ARG, "afx_create: only sample_rate 44100 / fft_size 2048 are supported (Crawler.cpp:41-43)");
   if (cfg->hop_size < 256 || cfg->hop_size > 2048 || (cfg->hop_size % 256) != 0)
     return fail(nullptr, AFX_ERR_ARG, "afx_create: hop_size must be a multiple of 256 in [256, 2048]");
+  if ((cfg->features & AFX_FEAT_HIGHLEVEL) && (cfg->features & AFX_FEAT_ALL) != AFX_FEAT_ALL)
+    return fail(nullptr, AFX_ERR_ARG, "afx_create: AFX_FEAT_HIGHLEVEL derives from the full low-level set (AFX_FEAT_ALL | AFX_FEAT_HIGHLEVEL)");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0) return fail(nullptr, AFX_ERR_CUDA, "afx_create: no CUDA device (no CPU fallback exists)", e);
@@ -327,7 +329,8 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_win = place(window.size() * 8), o_rwin = place(rwindow.size() * 8), o_mel = place(mel.size() * 8),
     o_dct = place(dct.size() * 8), o_tw = place(tw2048.size() * 8), o_tw5 = place(tw512.size() * 8), o_imp = place(imp.size() * 4),
-    o_ft2 = place(ft2.size() * 8), o_ft3a = place(ft3a.size() * 8), o_ft3b = place(ft3b.size() * 8), o_ctr = place(64 * 4);
+    o_ft2 = place(ft2.size() * 8), o_ft3a = place(ft3a.size() * 8), o_ft3b = place(ft3b.size() * 8), o_ctr = place(64 * 4),
+    o_pad = place(32 * 8);
   e = ctx->tables.reserve(off);
   if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMalloc(tables)", e); }
   unsigned char* base = (unsigned char*)ctx->tables.p;
@@ -349,8 +352,33 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   P.t.work_ctr = (unsigned int*)(base + o_ctr);
   P.t.fft_t2 = (const double2*)(base + o_ft2); P.t.fft_t3_1024 = (const double2*)(base + o_ft3a); P.t.fft_t3_2048 = (const double2*)(base + o_ft3b);
 
+  P.t.hl_pad = (double*)(base + o_pad);
   ctx->max_frame_cap = (P.analysis_cap - AFX_RFFT) / AFX_RHOP + 2;
   ctx->zeros.assign(ctx->max_frame_cap, 0.0);
+  if (cfg->features & AFX_FEAT_HIGHLEVEL) {
+    // The classification features pad short files with the LAST frame of a silent 0.5-s sample
+    // (SampleClassificationDescriptors.cpp:330-368 analyses one at start-up; so does this context, through its own kernels)
+    std::vector<int16_t> silence(sr / 2, 0);
+    afx_file f; memset(&f, 0, sizeof(f));
+    f.pcm = silence.data(); f.nframes = (int64_t)silence.size(); f.channels = 1; f.src_rate = sr; f.format = AFX_PCM_I16; f.bit_depth = 16;
+    afx_batch* b = nullptr;
+    afx_file_result r;
+    if (afx_analyze(ctx, &f, 1, &b) != AFX_OK || afx_batch_result(b, 0, &r) != AFX_OK || r.status != AFX_FILE_OK || r.n_frames < 1) {
+      g_create_error = "afx_create: the silent reference sample failed to analyse: " + ctx->error;
+      if (b) afx_batch_free(b);
+      afx_destroy(ctx);
+      return AFX_ERR_CUDA;
+    }
+    const int last = r.n_frames - 1;
+    double pad[21];
+    for (int k = 0; k < 14; ++k) pad[k] = r.fv[5][(size_t)last * 28 + k];
+    static const int series[7] = { FS_SPEC_RMS, FS_SPEC_FLATNESS, FS_SPEC_FLUX, FS_SPEC_CONTRAST, FS_SPEC_COMPLEXITY, FS_F0_CONF, FS_AMP_RMS };
+    for (int k = 0; k < 7; ++k) pad[14 + k] = r.fs[series[k]][last];
+    afx_batch_free(b);
+    e = cudaMemcpy(P.t.hl_pad, pad, sizeof(pad), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMemcpy(hl_pad)", e); }
+    ctx->hl_pad_ready = true;
+  }
   *out = ctx;
   return AFX_OK;
 }
@@ -365,7 +393,8 @@ extern "C" void afx_destroy(afx_ctx* ctx)
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_spec) cudaEventDestroy(ctx->ev_spec);
   DevBuf* bufs[] = { &ctx->tables, &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
-    &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch };
+    &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch,
+    &ctx->d_hl, &ctx->d_hl_pitch, &ctx->d_hl_sig, &ctx->d_hl_feat, &ctx->d_hl_status };
   for (DevBuf* b : bufs) b->release();
   ctx->h_results_cache.release(); ctx->h_plan_cache.release();
   for (auto& pb : ctx->part_pool) pb.release();
@@ -383,7 +412,8 @@ extern "C" int afx_trim(afx_ctx* ctx)
   if (e != cudaSuccess) return fail(ctx, AFX_ERR_CUDA, "afx_trim", e);
   if (ctx->live) return fail(ctx, AFX_ERR_STATE, "afx_trim: a batch of this context is still alive");
   DevBuf* bufs[] = { &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
-    &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch };
+    &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch,
+    &ctx->d_hl, &ctx->d_hl_pitch, &ctx->d_hl_sig, &ctx->d_hl_feat, &ctx->d_hl_status };
   for (DevBuf* b : bufs) b->release();
   for (auto& pb : ctx->part_pool) pb.release();
   ctx->part_pool.clear();
@@ -553,6 +583,13 @@ int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, 
   b->o_fsr = o; o += (size_t)2 * b->TFr;
   b->o_fv = o; o += (size_t)AFX_FV_STRIDE * b->TF;
   b->o_state = o; o += ((size_t)n_files * sizeof(AfxState) + 7) / 8;
+  if (ctx->cfg.features & AFX_FEAT_HIGHLEVEL) {
+    b->o_hl = o; o += (size_t)n_files * AFX_N_HL;
+    b->o_hl_sig = o; o += (size_t)n_files * AFX_HL_SIGNATURE;
+    b->o_hl_feat = o; o += (size_t)n_files * AFX_HL_FEATURES;
+    b->o_hl_pitch = o; o += (size_t)b->TF;
+    b->o_hl_status = o; o += ((size_t)n_files * sizeof(int) + 7) / 8;
+  }
   b->total_doubles = o;
   *out = b;
   return AFX_OK;
@@ -609,6 +646,13 @@ extern "C" int afx_batch_upload(afx_batch* b)
     CK(ctx->d_rpost.reserve((TFr + 1) * 2 * 4), "cudaMalloc(rpost)");
     CK(ctx->d_scratch.reserve((GR + 1) * 4 * 8 + 1024), "cudaMalloc(scratch)");
   }
+  if (feat & AFX_FEAT_HIGHLEVEL) {
+    CK(ctx->d_hl.reserve((size_t)(n + 1) * AFX_N_HL * 8), "cudaMalloc(hl)");
+    CK(ctx->d_hl_sig.reserve((size_t)(n + 1) * AFX_HL_SIGNATURE * 8), "cudaMalloc(hl signature)");
+    CK(ctx->d_hl_feat.reserve((size_t)(n + 1) * AFX_HL_FEATURES * 8), "cudaMalloc(hl features)");
+    CK(ctx->d_hl_pitch.reserve((TF + 1) * 8), "cudaMalloc(hl pitch)");
+    CK(ctx->d_hl_status.reserve((size_t)(n + 1) * 4), "cudaMalloc(hl status)");
+  }
   CK(ctx->d_stats.reserve((size_t)(n + 1) * AFX_N_SERIES * AFX_N_STATS * 8), "cudaMalloc(stats)");
   CK(ctx->d_header.reserve((size_t)(n + 1) * AFX_N_HEADER * 8), "cudaMalloc(header)");
 
@@ -659,6 +703,8 @@ extern "C" int afx_batch_upload(afx_batch* b)
   D.slot_file = (const int*)ctx->d_slotmap.p; D.rslot_file = (const int*)ctx->d_slotmap.p + TF + 1;
   D.max_fr = b->max_fr;
   D.stats = (double*)ctx->d_stats.p; D.header = (double*)ctx->d_header.p; D.scratch = (double*)ctx->d_scratch.p;
+  b->hl.scalars = (double*)ctx->d_hl.p; b->hl.pitch = (double*)ctx->d_hl_pitch.p; b->hl.signature = (double*)ctx->d_hl_sig.p;
+  b->hl.features = (double*)ctx->d_hl_feat.p; b->hl.status = (int*)ctx->d_hl_status.p; b->hl.silence_pad = ctx->P.t.hl_pad;
   AfxCondPlan& C = b->cond;
   memset(&C, 0, sizeof(C));
   C.src_chunk_file = (const int*)(dp + p_scf); C.src_chunk_start = (const int*)(dp + p_scs); C.n_src_chunks = (int)nsc;
@@ -740,6 +786,8 @@ extern "C" int afx_batch_compute(afx_batch* b)
 #ifdef AFX_HAVE_STATS
   if (feat & AFX_FEAT_STATS) { ktime_begin(b, "stats"); afx_launch_stats(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
 #endif
+  // the high-level stage reads the finished series and statistics (skipped while afx_create computes the silence pad)
+  if ((feat & AFX_FEAT_HIGHLEVEL) && ctx->hl_pad_ready) { ktime_begin(b, "highlevel"); afx_launch_highlevel(ctx->P, b->dev, b->hl, ctx->stream, &b->launches); ktime_end(b); }
   CK(cudaEventRecord(b->ev[3], ctx->stream), "cudaEventRecord");
   CK(cudaGetLastError(), "kernel launch");
   b->computed = true;
@@ -791,6 +839,13 @@ extern "C" int afx_batch_download(afx_batch* b)
   for (auto& r : rr) CK(cp(H + b->o_fs + (size_t)r.first * TF, b->dev.fs + (size_t)r.first * TF, (size_t)(r.second - r.first) * TF * 8), "D2H fs");
   if (feat & AFX_FEAT_RHYTHM) CK(cp(H + b->o_fsr, b->dev.fsr, 2 * TFr * 8), "D2H fsr");
   if (feat & AFX_FEAT_BANDS) CK(cp(H + b->o_fv, b->dev.fv, TF * AFX_FV_STRIDE * 8), "D2H fv");
+  if ((feat & AFX_FEAT_HIGHLEVEL) && ctx->hl_pad_ready) {
+    CK(cp(H + b->o_hl, b->hl.scalars, (size_t)n * AFX_N_HL * 8), "D2H hl");
+    CK(cp(H + b->o_hl_sig, b->hl.signature, (size_t)n * AFX_HL_SIGNATURE * 8), "D2H hl signature");
+    CK(cp(H + b->o_hl_feat, b->hl.features, (size_t)n * AFX_HL_FEATURES * 8), "D2H hl features");
+    CK(cp(H + b->o_hl_pitch, b->hl.pitch, TF * 8), "D2H hl pitch");
+    CK(cp(H + b->o_hl_status, b->hl.status, (size_t)n * sizeof(int)), "D2H hl status");
+  }
   CK(cudaEventRecord(b->ev[5], ctx->stream), "cudaEventRecord");
   b->downloaded = true;
   return AFX_OK;
@@ -843,6 +898,13 @@ extern "C" int afx_batch_result(const afx_batch* b, int32_t i, afx_file_result* 
     for (int v = 0; v < AFX_N_FV; ++v) out->fv[v] = H + b->o_fv + (size_t)offs[v] * TF + (size_t)f.frame_off * nbv[v];
   }
   if (feat & AFX_FEAT_STATS) out->stats = H + b->o_stats + (size_t)i * AFX_N_SERIES * AFX_N_STATS;
+  if ((feat & AFX_FEAT_HIGHLEVEL) && b->ctx->hl_pad_ready) {
+    out->highlevel = H + b->o_hl + (size_t)i * AFX_N_HL;
+    out->hl_signature = H + b->o_hl_sig + (size_t)i * AFX_HL_SIGNATURE;
+    out->hl_features = H + b->o_hl_feat + (size_t)i * AFX_HL_FEATURES;
+    out->hl_pitch = H + b->o_hl_pitch + f.frame_off;
+    out->hl_status = reinterpret_cast<const int*>(H + b->o_hl_status)[i];
+  }
   return AFX_OK;
 }
 

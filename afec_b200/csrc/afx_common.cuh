@@ -25,6 +25,9 @@
 #define AFX_RBINS 255
 #define AFX_RROW 512        // floats per rhythm frame row: mag[0..255], dc, nyq, pad | phase[256..511]
 #define AFX_FV_STRIDE 112
+#define AFX_N_HL 16
+#define AFX_HL_SIGNATURE (64 * 14)
+#define AFX_HL_FEATURES 1680
 // the analysis window of the spectral statistics: bins round(20 / 21) .. round(15500 / 21) with the reference's integer
 // FrequenciesPerBin = 44100 / 2048 = 21 (SampleAnalyser.cpp:171-175).  afx_create only accepts that rate / size and checks
 // that its table agrees, so the frame kernels may treat the bounds as compile-time constants.
@@ -97,6 +100,7 @@ struct AfxTables {          // per-context constant tables in device memory
   const double* dct;        // [14][14] cos(pi n/14 (m+0.5)), row n
   const float* rs_imp;      // [69632] resampler wing
   unsigned int* work_ctr;   // [64] work-claim counters of the persistent kernels (zeroed on the launching stream)
+  double* hl_pad;           // [21] last-frame values of a silent sample, written by afx_create (AFX_FEAT_HIGHLEVEL)
 };
 
 struct AfxParams {
@@ -287,6 +291,15 @@ struct AfxBatchDev {
   int rhythm_fused;   // this launch group's rhythm front end runs as ONE kernel with a CTA per file (k_rhythm_front); else the split kernels over rpolar
 };
 
+struct AfxHighLevelDev {   // outputs of k_highlevel (afx_highlevel.cu), batch-wide
+  double* scalars;          // [n_files][AFX_N_HL]
+  double* pitch;            // [TF] MIDI notes on the main frame grid (frame_off / F segments)
+  double* signature;        // [n_files][64][14]
+  double* features;         // [n_files][AFX_HL_FEATURES]
+  int* status;              // [n_files] 1: a classification feature is NaN / Inf (the reference fails the file)
+  const double* silence_pad;// [21] last-frame values of a silent sample (SampleClassificationDescriptors.cpp:330-368)
+};
+
 struct RsBlock { int out0; int nout; long long in0; long long chk_off; int span; int pad; };   // in0: source index of X[0] (may be negative); chk_off: first time checkpoint; span: X[0 .. span) covers every sample the block's filter sums read
 struct AfxCondPlan {       // device arrays built by the host for one batch
   const int* src_chunk_file; const int* src_chunk_start; int n_src_chunks;   // chunks over source frames
@@ -307,3 +320,4 @@ void afx_launch_pitch(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, 
 void afx_launch_autocorr(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
 void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
 void afx_launch_stats(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
+void afx_launch_highlevel(const AfxParams& P, const AfxBatchDev& B, const AfxHighLevelDev& O, cudaStream_t s, long long* launches);

@@ -140,3 +140,70 @@ def parse_dump(data: bytes) -> list:
 def load_dump(path: str) -> list:
     with open(path, "rb") as f:
         return parse_dump(f.read())
+
+
+# ---- high-level derivations that need no classification model (SampleAnalyser.cpp:1232-1606) and the
+# classification feature vector (SampleClassificationDescriptors.cpp:330-560) --------------------------------
+HL_SCALARS = ["base_note", "base_note_confidence", "peak_db", "rms_db", "bpm", "bpm_confidence", "brightness",
+              "noisiness", "harmonicity", "spectral_flatness", "spectral_flux", "spectral_complexity",
+              "spectral_contrast", "spectral_inharmonicity", "pitch_confidence"]
+N_HL = 16                   # 15 scalars + 1 reserved
+HL_SIGNATURE_FRAMES, HL_SIGNATURE_BANDS = 64, 14
+HL_N_FEATURES = 1680        # 35 rows of 48 (SampleClassificationDescriptors.cpp:536-547 pads to the time-series width)
+
+
+@dataclass
+class HighLevelResult:
+    status: int = 0
+    F: int = 0
+    scalars: np.ndarray = field(default_factory=lambda: np.zeros(N_HL))
+    pitch: np.ndarray = field(default_factory=lambda: np.zeros(0))          # [F] MIDI notes
+    peak: np.ndarray = field(default_factory=lambda: np.zeros(0))           # [F] == amplitude_peak
+    signature: np.ndarray = field(default_factory=lambda: np.zeros((HL_SIGNATURE_FRAMES, HL_SIGNATURE_BANDS)))
+    features: np.ndarray = field(default_factory=lambda: np.zeros(HL_N_FEATURES))
+
+    def scalar(self, name: str) -> float:
+        return float(self.scalars[HL_SCALARS.index(name)])
+
+
+def record_body(r: "FileResult") -> np.ndarray:
+    """The flat float64 body of an AFXD record (what oracle.afxo_highlevel takes)."""
+    return np.ascontiguousarray(np.concatenate([r.header] + [np.ravel(a) for a in r.fs] + [np.ravel(a) for a in r.fv]
+                                               + [np.ravel(r.stats)]), dtype=np.float64)
+
+
+def parse_highlevel(buf: memoryview, pos: int):
+    """Parse one AFXH record at byte offset pos -> (HighLevelResult, new_pos)."""
+    if bytes(buf[pos:pos + 4]) != b"AFXH":
+        raise ValueError("bad AFXH magic at %d" % pos)
+    status, = struct.unpack_from("<i", buf, pos + 4)
+    pos += 8
+    r = HighLevelResult(status=status)
+    if status != 0:
+        return r, pos
+    F, nf = struct.unpack_from("<ii", buf, pos)
+    pos += 8
+    n = N_HL + 2 * F + HL_SIGNATURE_FRAMES * HL_SIGNATURE_BANDS + nf
+    d = np.frombuffer(buf, dtype="<f8", count=n, offset=pos).copy()
+    pos += 8 * n
+    r.F = F
+    o = 0
+    r.scalars = d[o:o + N_HL]; o += N_HL
+    r.pitch = d[o:o + F]; o += F
+    r.peak = d[o:o + F]; o += F
+    r.signature = d[o:o + HL_SIGNATURE_FRAMES * HL_SIGNATURE_BANDS].reshape(HL_SIGNATURE_FRAMES, HL_SIGNATURE_BANDS)
+    o += HL_SIGNATURE_FRAMES * HL_SIGNATURE_BANDS
+    r.features = d[o:o + nf]
+    return r, pos
+
+
+def load_dump_highlevel(path: str) -> list:
+    """A `afec_ref dumphl` file: per input file an AFXD record followed by an AFXH record -> [(FileResult, HighLevelResult)]."""
+    with open(path, "rb") as f:
+        buf = memoryview(f.read())
+    pos, out = 0, []
+    while pos < len(buf):
+        ll, pos = parse_record(buf, pos)
+        hl, pos = parse_highlevel(buf, pos)
+        out.append((ll, hl))
+    return out

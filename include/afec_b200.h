@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AFX_ABI_VERSION 2
+#define AFX_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------------------------ */
 #define AFX_OK 0
@@ -61,6 +61,11 @@ extern "C" {
 #define AFX_FEAT_RHYTHM (1u << 6)    /* onset functions + rhythm scalars */
 #define AFX_FEAT_STATS (1u << 7)     /* 13 statistics per series */
 #define AFX_FEAT_ALL 0xFFu           /* the full low-level set (`Crawler --level low`) */
+/* On top of AFX_FEAT_ALL: the high-level derivations that need no classification model (base note, loudness, bpm,
+ * brightness / noisiness / harmonicity, spectrum signature, audible-frame spectral means, pitch series;
+ * SampleAnalyser.cpp:1232-1606) and the classification feature vector the LightGBM models take
+ * (SampleClassificationDescriptors.cpp:404-560).  Model evaluation itself stays on the host. */
+#define AFX_FEAT_HIGHLEVEL (1u << 8)
 
 typedef struct afx_ctx afx_ctx;
 typedef struct afx_batch afx_batch;
@@ -93,16 +98,28 @@ typedef struct afx_file {
 #define AFX_N_FV 7           /* framed vectors: 5 x 14 sub-bands, 28 frequency bands, 14 cepstrum bands */
 #define AFX_N_STATS 13
 #define AFX_N_SERIES 136     /* 24 + 5*14 + 28 + 14 */
+#define AFX_N_HL 16          /* base_note, base_note_confidence, peak_db, rms_db, bpm, bpm_confidence, brightness, noisiness,
+                                harmonicity, spectral_flatness, spectral_flux, spectral_complexity, spectral_contrast,
+                                spectral_inharmonicity, pitch_confidence, reserved (names: afec_b200/layout.py HL_SCALARS) */
+#define AFX_HL_SIGNATURE_FRAMES 64   /* TSampleDescriptors::kNumberOfHighLevelSpectrumBandFrames, SampleDescriptors.h:503 */
+#define AFX_HL_SIGNATURE_BANDS 14
+#define AFX_HL_FEATURES 1680         /* 35 rows of the 48-entry time series (SampleClassificationDescriptors.cpp:39-43, 536-547) */
 
 typedef struct afx_file_result {
   int32_t status;            /* AFX_FILE_* */
   int32_t n_frames;          /* F : main frames (fft_size / hop_size grid) */
   int32_t n_rhythm_frames;   /* Fr: 512 / 128 grid */
-  int32_t reserved;
+  int32_t hl_status;         /* AFX_FEAT_HIGHLEVEL: 1 when a classification feature is NaN / Inf ("Invalid Descriptor array
+                                value", SampleClassificationDescriptors.cpp:88-91: the file fails to analyse at --level high) */
   const double* header;      /* [AFX_N_HEADER] scalars */
   const double* fs[AFX_N_FS];/* fs[s][frame]; s < 22 -> n_frames values, s = 22, 23 -> n_rhythm_frames */
   const double* fv[AFX_N_FV];/* fv[v][frame * nbands(v) + band] */
   const double* stats;       /* [AFX_N_SERIES][AFX_N_STATS] */
+  /* AFX_FEAT_HIGHLEVEL only (NULL otherwise) */
+  const double* highlevel;   /* [AFX_N_HL] */
+  const double* hl_pitch;    /* [n_frames] MIDI notes ("pitch"); "peak" is fs[1] (amplitude_peak), SampleAnalyser.cpp:1609 */
+  const double* hl_signature;/* [AFX_HL_SIGNATURE_FRAMES][AFX_HL_SIGNATURE_BANDS] */
+  const double* hl_features; /* [AFX_HL_FEATURES] */
 } afx_file_result;
 
 /* ---- context ------------------------------------------------------------------------------- */

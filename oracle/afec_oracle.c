@@ -1177,3 +1177,185 @@ double afxo_median(const double* x, int n) { return st_median(x, n); }
 double afxo_gmean(const double* x, int n) { return st_gmean(x, n); }
 double afxo_min(const double* x, int n) { double m = n > 0 ? x[0] : 0.0; for (int i = 1; i < n; ++i) m = x[i] < m ? x[i] : m; return m; }
 double afxo_max(const double* x, int n) { double m = n > 0 ? x[0] : 0.0; for (int i = 1; i < n; ++i) m = x[i] > m ? x[i] : m; return m; }
+
+/* =========================================================================================== */
+/* High-level derivations that need no classification model (SampleAnalyser.cpp:1232-1606) and   */
+/* the classification feature vector (SampleClassificationDescriptors.cpp:330-560), from one     */
+/* low-level record laid out as afxo_analyze writes it (header[32], 22 x fs[F], 2 x fs[Fr],      */
+/* 7 x fv[F][nb], stats[136][13]).                                                               */
+/*   hl[16]: base_note, base_note_confidence, peak_db, rms_db, bpm, bpm_confidence, brightness,  */
+/*           noisiness, harmonicity, spectral_flatness, spectral_flux, spectral_complexity,      */
+/*           spectral_contrast, spectral_inharmonicity, pitch_confidence, 0                      */
+/*   pitch[F] (MIDI notes), signature[64][14], features[AFXO_NFEAT]                              */
+/*   pad[21]: the reference pads short files with the LAST frame of a silent 0.5-s sample        */
+/*           analysed at hop 1024 (SampleClassificationDescriptors.cpp:330-368): frequency_bands */
+/*           [0..13] of that frame, then spectral_rms, spectral_flatness, spectral_flux,         */
+/*           spectral_contrast, spectral_complexity, f0_confidence, amplitude_rms                */
+/* Returns 0, or -1 when a feature is NaN / Inf (the reference throws: the file fails to analyse) */
+
+#define HL_NSIG_FRAMES 64
+#define HL_NSIG_BANDS 14
+#define HL_NTIME 48
+#define AFXO_NFEAT 1680
+
+static const int kHlBands[HL_NSIG_BANDS] = { 0, 1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 23, 25 };   /* SampleAnalyser.cpp:1462-1465 */
+static const int kHlTimeSeries[HL_NTIME] = { 0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,
+  25,26,27,28,29,30,31,32,33,34,35,36,37,38,39,40,41,42,43, 64,128,256,512 };                    /* SampleClassificationDescriptors.cpp:39-43 */
+
+static double hl_freqtomidi(double freq)      /* aubio mathutils.c:535-546 (smpl_t = double) */
+{
+  if (freq < 2. || freq > 100000.) return 0.;
+  double midi = freq / 6.875;
+  midi = log(midi) / 0.69314718055995;
+  midi *= 12;
+  midi -= 3;
+  return midi;
+}
+static double hl_lin_to_db_f(float v)          /* TAudioMath::LinToDb(float), AudioMath.inl:38-54 */
+{
+  if (v == 1.0f) return 0.0f;
+  if (v > 1e-12f) return (float)(log((double)v) * (20.0 / log(10.0)));
+  return -200.0f;
+}
+static double hl_cubic(double ym1, double y0, double y1, double y2, double pos)   /* SampleAnalyser.cpp:139-155 */
+{
+  const double x = pos - floor(pos), xx = x * x, xxx = xx * x;
+  const double a = -0.5 * xxx + xx - 0.5 * x, b = 1.5 * xxx - 2.5 * xx + 1.0, c = -1.5 * xxx + 2.0 * xx + 0.5 * x, d = 0.5 * xxx - 0.5 * xx;
+  return a * ym1 + b * y0 + c * y1 + d * y2;
+}
+static double hl_merged_band(const double* bands28_frame, int b)                 /* SampleAnalyser.cpp:1476-1489 */
+{
+  const int s = (b - 1) >= 0 ? kHlBands[b - 1] + 1 : 0, e = kHlBands[b];
+  double m = 0.0;
+  for (int sb = s; sb <= e; ++sb) m += bands28_frame[sb];
+  m /= (double)(e - s + 1);
+  return pow(m * 1.25, 1.0 / 6.0);
+}
+static int hl_push(double* f, int* n, double v) { f[(*n)++] = v; return (isnan(v) || isinf(v)) ? 1 : 0; }
+
+int afxo_highlevel(const double* rec, int F, int Fr, int sample_rate, float peak_value, float rms_value, const double* pad,
+                   double* hl, double* pitch, double* signature, double* features)
+{
+  const double* header = rec;
+  const double* fs[24];
+  const double* p = rec + 32;
+  for (int s = 0; s < 24; ++s) { fs[s] = p; p += (s < 22) ? F : Fr; }
+  static const int nbv[7] = { 14, 14, 14, 14, 14, 28, 14 };
+  const double* fv[7];
+  for (int v = 0; v < 7; ++v) { fv[v] = p; p += (size_t)F * nbv[v]; }
+  const double* stats = p;
+  enum { S_SIL = 0, S_PEAK = 1, S_ARMS = 2, S_RMS = 4, S_CENT = 5, S_ROLL = 6, S_FLAT = 10, S_INH = 11, S_CPLX = 12, S_CONTR = 13, S_FLUX = 14,
+         S_F0 = 15, S_CONF = 16, S_AC = 21 };
+  double* tmp = (double*)malloc(sizeof(double) * (F + 1) * 2);
+  double* tmp2 = tmp + F + 1;
+  memset(hl, 0, sizeof(double) * 16);
+
+  /* audible frames = !IsSilentFrame (SampleAnalyser.cpp:867) */
+  int na = 0;
+  #define AUDIBLE(i) (fs[S_SIL][i] == 0.0)
+  #define GATHER(series, out, n) do { n = 0; for (int i_ = 0; i_ < F; ++i_) if (AUDIBLE(i_)) out[n++] = fs[series][i_]; } while (0)
+  GATHER(S_CONF, tmp, na);
+  const double apcm = na ? st_mean(tmp, na) : 0.0;                              /* :1256-1260 */
+  const double thr = (apcm >= 0.8) ? 0.8 : (apcm >= 0.5) ? 0.5 : 0.2;           /* :1262-1277 */
+  const double fmax = (double)(sample_rate / 4);
+  #define CONFIDENT(i) (fs[S_CONF][i] > thr && fs[S_F0][i] > 20 && fs[S_F0][i] < fmax)
+
+  /* base note (:1279-1330) */
+  double base_note = -1.0;
+  int nc = 0;
+  for (int i = 0; i < F; ++i) if (CONFIDENT(i)) tmp[nc++] = fs[S_F0][i];
+  if (nc) { const double hz = st_median(tmp, nc); if (hz > 20 && hz < fmax) base_note = hl_freqtomidi(hz); }
+  hl[0] = base_note;
+  if (base_note > 0.0) {
+    for (int i = 0; i < nc; ++i) tmp2[i] = fabs(base_note - hl_freqtomidi(tmp[i]));
+    const double sd = sqrt(st_variance(tmp2, nc, st_mean(tmp2, nc)));
+    const double q = sd / 6.0;
+    hl[1] = apcm * (1.0 - (q < 1.0 ? q : 1.0));
+  }
+  hl[2] = hl_lin_to_db_f(peak_value); hl[3] = hl_lin_to_db_f(rms_value);        /* :1336-1339 */
+  { double v = header[21];                                                      /* bpm: :1345-1349, TMath::Quantize(0.5, kRoundToNearest) */
+    if (v > 0.0) v += 0.25; else v -= 0.25;
+    v = (double)((double)(int)(v / 0.5) * 0.5);
+    hl[4] = v; hl[5] = header[22]; }
+  /* brightness (:1355-1383) */
+  { int n1, n2; GATHER(S_ROLL, tmp, n1); GATHER(S_CENT, tmp2, n2);
+    if (n1 && n2) {
+      const double rm = st_mean(tmp, n1); double cm = tmp2[0]; for (int i = 1; i < n2; ++i) cm = tmp2[i] > cm ? tmp2[i] : cm;
+      double w = hl_freqtomidi(rm) / 128.0 * 0.7 + hl_freqtomidi(cm) / 128.0 * 0.3;
+      w = w < 1.0 ? w : 1.0; w = w > 0.0 ? w : 0.0;
+      hl[6] = pow(w, 4.0);
+    } }
+  /* noisiness (:1387-1414), harmonicity (:1419-1446) */
+  { int n; GATHER(S_FLAT, tmp, n);
+    double flat_mean = 0.0;
+    if (n) {
+      double mn = tmp[0], mx = tmp[0]; for (int i = 1; i < n; ++i) { mn = tmp[i] < mn ? tmp[i] : mn; mx = tmp[i] > mx ? tmp[i] : mx; }
+      flat_mean = st_mean(tmp, n);
+      double w = (1.0 - mn) * 0.2 + (1.0 - flat_mean) * 0.6 + (1.0 - mx) * 0.2;
+      w = w < 1.0 ? w : 1.0; w = w > 0.0 ? w : 0.0;
+      hl[7] = pow(w, 2.0);
+    }
+    hl[9] = n ? flat_mean : 0.0;                                                /* :1538-1539 */
+    int m; GATHER(S_AC, tmp, m);
+    if (m) {
+      const double acm = st_mean(tmp, m);
+      const double a = 1.5 * acm, b = 2.0 * apcm;
+      double w = (a < 1.0 ? a : 1.0) * 0.4 + (b < 1.0 ? b : 1.0) * 0.3 + flat_mean * 0.3;
+      w = w < 1.0 ? w : 1.0; w = w > 0.0 ? w : 0.0;
+      hl[8] = pow(w, 2.0);
+    } }
+  { int n;                                                                      /* :1527-1554 */
+    GATHER(S_FLUX, tmp, n); hl[10] = n ? st_mean(tmp, n) : 0.0;
+    GATHER(S_CPLX, tmp, n); hl[11] = n ? st_mean(tmp, n) : 0.0;
+    GATHER(S_CONTR, tmp, n); hl[12] = n ? st_mean(tmp, n) : 0.0;
+    GATHER(S_INH, tmp, n); hl[13] = n ? st_mean(tmp, n) : 0.0; }
+  hl[14] = apcm;                                                                /* :1604 */
+
+  /* spectrum signature (:1449-1521) */
+  { double* scaled = (double*)malloc(sizeof(double) * (size_t)F * HL_NSIG_BANDS);
+    for (int f = 0; f < F; ++f) for (int b = 0; b < HL_NSIG_BANDS; ++b) scaled[f * HL_NSIG_BANDS + b] = hl_merged_band(fv[5] + (size_t)f * 28, b);
+    const double step = (double)F / HL_NSIG_FRAMES;
+    double pos = 0;
+    for (int i = 0; i < HL_NSIG_FRAMES; ++i) {
+      const int ipos = (int)pos, im1 = ipos - 1 > 0 ? ipos - 1 : 0, i1 = ipos + 1 < F - 1 ? ipos + 1 : F - 1, i2 = ipos + 2 < F - 1 ? ipos + 2 : F - 1;
+      for (int j = 0; j < HL_NSIG_BANDS; ++j)
+        signature[i * HL_NSIG_BANDS + j] = hl_cubic(scaled[im1 * HL_NSIG_BANDS + j], scaled[ipos * HL_NSIG_BANDS + j],
+                                                   scaled[i1 * HL_NSIG_BANDS + j], scaled[i2 * HL_NSIG_BANDS + j], pos);
+      pos += step;
+    }
+    free(scaled); }
+
+  /* pitch (:1558-1598) */
+  { double last = 0.0;
+    if (F > 1) { const int lim = (F / 4 > 1) ? F / 4 : 1; for (int i = 0; i <= lim; ++i) if (AUDIBLE(i) && CONFIDENT(i)) { last = fs[S_F0][i]; break; } }
+    for (int i = 0; i < F; ++i) {
+      if (AUDIBLE(i) && CONFIDENT(i)) last = fs[S_F0][i];
+      pitch[i] = hl_freqtomidi(last);
+    } }
+
+  /* classification features (SampleClassificationDescriptors.cpp:404-560) */
+  int n = 0, bad = 0;
+  for (int b = 0; b < HL_NSIG_BANDS; ++b) for (int i = 0; i < HL_NTIME; ++i) {
+    const int tf = kHlTimeSeries[i];
+    bad |= hl_push(features, &n, tf < F ? hl_merged_band(fv[5] + (size_t)tf * 28, b) : pad[b]);
+  }
+  static const int tser[6] = { S_RMS, S_FLAT, S_FLUX, S_CONTR, S_CPLX, S_CONF };
+  static const int pick[7] = { 0, 1, 3, 5, 10, 11, 12 };     /* min, max, mean, variance, flatness, dmean, dvariance */
+  for (int k = 0; k < 6; ++k) for (int i = 0; i < HL_NTIME; ++i) { const int tf = kHlTimeSeries[i]; bad |= hl_push(features, &n, tf < F ? fs[tser[k]][tf] : pad[14 + k]); }
+  for (int k = 0; k < 6; ++k) for (int q = 0; q < 7; ++q) bad |= hl_push(features, &n, stats[tser[k] * 13 + pick[q]]);
+  static const int vbase[6] = { 24, 38, 52, 66, 80, 122 };   /* rms, flatness, flux, complexity, contrast sub-bands; cepstrum */
+  for (int k = 0; k < 6; ++k) for (int b = 0; b < 14; ++b) for (int q = 0; q < 7; ++q) bad |= hl_push(features, &n, stats[(vbase[k] + b) * 13 + pick[q]]);
+  for (int i = 0; i < HL_NTIME; ++i) { const int tf = kHlTimeSeries[i]; bad |= hl_push(features, &n, tf < F ? fs[S_ARMS][tf] : pad[20]); }
+  for (int q = 0; q < 7; ++q) bad |= hl_push(features, &n, stats[S_ARMS * 13 + pick[q]]);
+  for (int q = 0; q < 7; ++q) bad |= hl_push(features, &n, stats[S_SIL * 13 + pick[q]]);
+  bad |= hl_push(features, &n, header[14]); bad |= hl_push(features, &n, header[20]);   /* tempo confidences */
+  bad |= hl_push(features, &n, header[10]); bad |= hl_push(features, &n, header[16]);   /* onset contrasts */
+  bad |= hl_push(features, &n, header[12]); bad |= hl_push(features, &n, header[18]);   /* onset strengths */
+  bad |= hl_push(features, &n, header[7]);                                              /* effectve_length_12dB */
+  while (n % HL_NTIME) bad |= hl_push(features, &n, stats[S_RMS * 13 + 3]);             /* padding: spectral_rms mean */
+  free(tmp);
+  return (n != AFXO_NFEAT) ? -2 : (bad ? -1 : 0);
+  #undef AUDIBLE
+  #undef GATHER
+  #undef CONFIDENT
+}

@@ -54,6 +54,9 @@ def lib():
         L.afxo_condition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                      C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.afxo_highlevel.restype = C.c_int
+        L.afxo_highlevel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -104,6 +107,56 @@ def set_fft_variant(v: int) -> None:
     """0: the restatement's decimation-in-time FFT; 1: an identical transform with another rounding order (tests that
     show which outputs are decided by FFT rounding noise)."""
     lib().afxo_set_fft_variant(int(v))
+
+
+_silence_pad = None
+
+
+def silence_pad() -> np.ndarray:
+    """The values the reference pads short files with in the classification features: the last frame of a silent
+    0.5-s sample analysed at hop 1024 (SampleClassificationDescriptors.cpp:330-368) -- 14 frequency bands, then
+    spectral_rms, spectral_flatness, spectral_flux, spectral_contrast, spectral_complexity, f0_confidence, amplitude_rms."""
+    global _silence_pad
+    if _silence_pad is None:
+        r = analyze(np.zeros(22050, dtype=np.int16), hop=1024)
+        last = r.F - 1
+        _silence_pad = np.array(list(r.series("frequency_bands")[last][:14]) +
+                                [r.series(n)[last] for n in ("spectral_rms", "spectral_flatness", "spectral_flux", "spectral_contrast",
+                                                             "spectral_complexity", "f0_confidence", "amplitude_rms")], dtype=np.float64)
+    return _silence_pad
+
+
+def highlevel(r: layout.FileResult, peak_value: float, rms_value: float, sample_rate: int = 44100) -> layout.HighLevelResult:
+    """High-level derivations + classification features of one low-level result (afxo_highlevel)."""
+    out = layout.HighLevelResult(F=r.F)
+    if r.status != 0:
+        out.status = r.status
+        return out
+    body = layout.record_body(r)
+    pad = silence_pad()
+    out.pitch = np.zeros(r.F)
+    out.signature = np.zeros((layout.HL_SIGNATURE_FRAMES, layout.HL_SIGNATURE_BANDS))
+    out.features = np.zeros(layout.HL_N_FEATURES)
+    rc = lib().afxo_highlevel(body.ctypes.data, r.F, r.Fr, sample_rate, float(peak_value), float(rms_value), pad.ctypes.data,
+                              out.scalars.ctypes.data, out.pitch.ctypes.data, out.signature.ctypes.data, out.features.ctypes.data)
+    out.peak = np.array(r.series("amplitude_peak"), dtype=np.float64)
+    out.status = 0 if rc == 0 else 100 - rc
+    return out
+
+
+def reference_analyze_highlevel(pcms, rates, hop: int = 1024, tmpdir: str | None = None) -> list:
+    """Run the real reference with kHighLevelDescriptors (no classification models) -> [(FileResult, HighLevelResult)]."""
+    assert have_reference()
+    with tempfile.TemporaryDirectory(dir=tmpdir) as d:
+        paths = []
+        for i, (p, r) in enumerate(zip(pcms, rates)):
+            path = os.path.join(d, "f%05d.wav" % i)
+            write_wav(path, p, r)
+            paths.append(path)
+        out = os.path.join(d, "dump.bin")
+        subprocess.run([REF_BIN, "dumphl", str(hop), out] + paths, check=True, env=dict(os.environ, HOME=d),
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return layout.load_dump_highlevel(out)
 
 
 def scalar_stat(name: str, x) -> float:

@@ -9,6 +9,9 @@
 //
 //   afec_ref dump  <hop> <out.bin> <wav>...       flat binary dump ("AFXD" layout, see
 //                                                  afec_b200/layout.py) of every low-level value
+//   afec_ref dumphl <hop> <out.bin> <wav>...      per file the "AFXD" record followed by an "AFXH" record: the high-level
+//                                                  descriptors that need no classification model (SampleAnalyser.cpp:1232-1606)
+//                                                  and the classification feature vector (SampleClassificationDescriptors.cpp)
 //   afec_ref db    <hop> <out.db>  <wav>...       golden afec-ll.db through the reference sink
 //   afec_ref bench <hop> <threads> <reps> <out.db|-> <wav>...
 //                                                  times Extract() like the Crawler's thread pool
@@ -25,6 +28,7 @@
 #include "FeatureExtraction/Export/SampleAnalyser.h"
 #include "FeatureExtraction/Export/SampleDescriptors.h"
 #include "FeatureExtraction/Export/SqliteSampleDescriptorPool.h"
+#include "FeatureExtraction/Export/SampleClassificationDescriptors.h"
 
 #include <atomic>
 #include <chrono>
@@ -142,11 +146,35 @@ static void dump_one(FILE* f, const TSampleDescriptors& R, int status)
   put_stats_vec(f, R.mCepstrumBands);
 }
 
+// High-level record (layout documented in afec_b200/layout.py, AFXH v1)
+static void dump_highlevel(FILE* f, const TSampleDescriptors& R, int status)
+{
+  fwrite("AFXH", 1, 4, f);
+  put_i32(f, status);
+  if (status != 0) return;
+  const TSampleClassificationDescriptors Features(R);
+  const int F = R.mHighLevelPitch.mValues.Size();
+  put_i32(f, F);
+  put_i32(f, (int)Features.mFeatures.size());
+  const double S[16] = { R.mHighLevelBaseNote.mValue, R.mHighLevelBaseNoteConfidence.mValue, R.mHighLevelPeakDb.mValue,
+    R.mHighLevelRmsDb.mValue, R.mHighLevelBpm.mValue, R.mHighLevelBpmConfidence.mValue, R.mHighLevelBrightness.mValue,
+    R.mHighLevelNoisiness.mValue, R.mHighLevelHarmonicity.mValue, R.mHighLevelSpectralFlatness.mValue,
+    R.mHighLevelSpectralFlux.mValue, R.mHighLevelSpectralComplexity.mValue, R.mHighLevelSpectralContrast.mValue,
+    R.mHighLevelSpectralInharmonicity.mValue, R.mHighLevelPitchConfidence.mValue, 0.0 };
+  fwrite(S, 8, 16, f);
+  for (int i = 0; i < F; ++i) put_f64(f, R.mHighLevelPitch.mValues[i]);
+  for (int i = 0; i < F; ++i) put_f64(f, R.mHighLevelPeak.mValues[i]);
+  for (int i = 0; i < R.mHighLevelSpectrumSignature.mValues.Size(); ++i)
+    for (int b = 0; b < R.mHighLevelSpectrumSignature.mValues[i].Size(); ++b) put_f64(f, R.mHighLevelSpectrumSignature.mValues[i][b]);
+  for (size_t i = 0; i < Features.mFeatures.size(); ++i) put_f64(f, Features.mFeatures[i]);
+}
+
 // -------------------------------------------------------------------------------------------------
 
 static int usage()
 {
   fprintf(stderr, "usage: afec_ref dump <hop> <out.bin> <wav>...\n"
+                  "       afec_ref dumphl <hop> <out.bin> <wav>...\n"
                   "       afec_ref db <hop> <out.db> <wav>...\n"
                   "       afec_ref bench <hop> <threads> <reps> <out.db|-> <wav>...\n");
   return 2;
@@ -159,7 +187,7 @@ int gMain(const TList<TString>& Args)
   std::vector<std::string> A;
   for (int i = 0; i < Args.Size(); ++i) A.push_back(Args[i].StdCString());
   // Args may or may not hold argv[0]; normalise so that A[0] is the mode
-  if (!A.empty() && A[0] != "dump" && A[0] != "db" && A[0] != "bench") A.erase(A.begin());
+  if (!A.empty() && A[0] != "dump" && A[0] != "dumphl" && A[0] != "db" && A[0] != "bench") A.erase(A.begin());
   if (A.size() < 4) return usage();
 
   AudioTypesInit();
@@ -185,6 +213,28 @@ int gMain(const TList<TString>& Args)
         fprintf(stderr, "analyze failed for %s: %s\n", A[i].c_str(), e.what());
         TSampleDescriptors Empty;
         dump_one(f, Empty, 1);
+      }
+    }
+    fclose(f);
+    return 0;
+  }
+  else if (Mode == "dumphl")
+  {
+    FILE* f = fopen(A[2].c_str(), "wb");
+    if (!f) { perror("fopen"); return 1; }
+    for (size_t i = 3; i < A.size(); ++i)
+    {
+      try {
+        TSampleDescriptors R = Analyser.Analyze(
+          TString(A[i].c_str(), TString::kFileSystemEncoding), TSampleDescriptors::kHighLevelDescriptors);
+        dump_one(f, R, 0);
+        dump_highlevel(f, R, 0);
+      }
+      catch (const std::exception& e) {
+        fprintf(stderr, "analyze failed for %s: %s\n", A[i].c_str(), e.what());
+        TSampleDescriptors Empty;
+        dump_one(f, Empty, 1);
+        dump_highlevel(f, Empty, 1);
       }
     }
     fclose(f);

@@ -32,7 +32,7 @@ def test_header_symbols_exported(lib_path):
 
 def test_abi_version(lib_path):
     lib = ctypes.CDLL(lib_path)
-    assert lib.afx_abi_version() == 2
+    assert lib.afx_abi_version() == 3
 
 
 def test_create_fails_loudly_without_gpu(lib_path):
