@@ -14,7 +14,8 @@ from . import layout
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libafec_b200.so")
 
-AFX_PCM_I16, AFX_PCM_F32 = 0, 1
+AFX_PCM_I16, AFX_PCM_F32, AFX_PCM_U8, AFX_PCM_I24, AFX_PCM_I32, AFX_PCM_F32U = 0, 1, 2, 3, 4, 5
+AFX_PCM_I8, AFX_PCM_I16BE, AFX_PCM_I24BE, AFX_PCM_I32BE, AFX_PCM_F32UBE = 6, 7, 8, 9, 10
 FEAT_SPECTRAL, FEAT_AMPLITUDE, FEAT_PEAKS, FEAT_BANDS = 1, 2, 4, 8
 FEAT_PITCH, FEAT_AUTOCORR, FEAT_RHYTHM, FEAT_STATS = 16, 32, 64, 128
 FEAT_ALL = 0xFF
@@ -22,7 +23,7 @@ FEAT_HIGHLEVEL = 0x100   # on top of FEAT_ALL: model-free high-level descriptors
 HAVE_RESAMPLE = True   # k_resample + host block plan (libresample HQ restatement)
 
 EXPORTS = [
-    "afx_abi_version", "afx_create", "afx_destroy", "afx_last_error", "afx_trim", "afx_host_alloc", "afx_host_free",
+    "afx_abi_version", "afx_pcm_bytes", "afx_create", "afx_destroy", "afx_last_error", "afx_trim", "afx_host_alloc", "afx_host_free",
     "afx_batch_create", "afx_batch_upload", "afx_batch_compute", "afx_batch_download", "afx_batch_sync",
     "afx_analyze", "afx_batch_result", "afx_batch_free", "afx_batch_timings", "afx_batch_counters",
     "afx_batch_kernel_times", "afx_batch_conditioned", "afx_measure_fp64_peak", "afx_debug_fft",
@@ -75,6 +76,7 @@ def load_library():
                        "there is no CPU fallback for the descriptor path")
     L = C.CDLL(LIB_PATH)
     L.afx_abi_version.restype = C.c_int
+    L.afx_pcm_bytes.argtypes = [C.c_int32]
     L.afx_create.argtypes = [C.POINTER(AfxConfig), C.POINTER(C.c_void_p)]
     L.afx_destroy.argtypes = [C.c_void_p]
     L.afx_destroy.restype = None

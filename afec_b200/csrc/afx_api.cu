@@ -223,6 +223,17 @@ extern "C" int afx_debug_rs_plan_check(int32_t sample_rate, int64_t nframes, int
 
 extern "C" int afx_abi_version(void) { return AFX_ABI_VERSION; }
 
+extern "C" int afx_pcm_bytes(int32_t format)
+{
+  switch (format) {
+    case AFX_PCM_U8: case AFX_PCM_I8: return 1;
+    case AFX_PCM_I16: case AFX_PCM_I16BE: return 2;
+    case AFX_PCM_I24: case AFX_PCM_I24BE: return 3;
+    case AFX_PCM_F32: case AFX_PCM_I32: case AFX_PCM_I32BE: case AFX_PCM_F32U: case AFX_PCM_F32UBE: return 4;
+    default: return 0;
+  }
+}
+
 extern "C" const char* afx_last_error(const afx_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
 extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
@@ -496,7 +507,7 @@ int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, 
     if (f.channels < 1 || f.channels > 8) d.status = AFX_FILE_BAD_CHANNELS;          // SA.cpp:472-477
     else if (f.nframes <= 0 || (!f.pcm && !cond)) d.status = AFX_FILE_EMPTY;          // SA.cpp:479-482
     // a description the kernels cannot take fails that file only (the reference fails files one by one, SA.cpp:372-408)
-    else if (f.nframes * f.channels > 0x7fffffffLL || f.src_rate <= 0 || (f.format != AFX_PCM_I16 && f.format != AFX_PCM_F32)) d.status = AFX_FILE_UNSUPPORTED;
+    else if (f.nframes * f.channels > 0x7fffffffLL || f.src_rate <= 0 || afx_pcm_bytes(f.format) == 0) d.status = AFX_FILE_UNSUPPORTED;
     d.frame_off = (int)tf; d.rframe_off = (int)tfr; d.mono_off = mono_off; d.src_off = src_off; d.pcm_off = (long long)pcm_off;
     if (d.status != AFX_FILE_OK) { if (g.nfiles > 0) ++g.nfiles; else { g.file0 = i; g.nfiles = 1; g.slot0 = (int)tf; g.rslot0 = (int)tfr; } continue; }
     d.nframes_src = (int)f.nframes;
@@ -530,10 +541,11 @@ int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, 
       continue;
     }
     // PCM packing: keep host-contiguous files contiguous on the device so they move in one copy
-    const size_t bps = (f.format == AFX_PCM_I16) ? 2 : 4;
+    const size_t bps = (size_t)afx_pcm_bytes(f.format);
+    const size_t align = (bps == 3) ? 1 : bps;             // the kernels read 2- and 4-byte samples with aligned loads, 3-byte ones bytewise
     const size_t bytes = (size_t)f.nframes * f.channels * bps;
     const unsigned char* hp = (const unsigned char*)f.pcm;
-    if (run_end == hp && (pcm_off % bps) == 0 && !b->runs.empty()) {
+    if (run_end == hp && (pcm_off % align) == 0 && !b->runs.empty()) {
       b->runs.back().bytes += bytes;
     } else {
       pcm_off = (pcm_off + 15) & ~(size_t)15;

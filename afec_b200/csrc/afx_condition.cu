@@ -1,7 +1,8 @@
 // K1: PCM conditioning -- the tail of TSampleAnalyser::LoadSample
 // (Source/Crawler/FeatureExtraction/Source/SampleAnalyser.cpp:531-719) for a whole batch.
 //
-//   k_downmix   : interleaved int16 / float32 -> float32 mono, (sum of channels) * (1/C) in float32
+//   k_downmix   : interleaved raw PCM (8 / 16 / 24 / 32-bit integer, float32; either byte order) -> float32 mono: the
+//                 decoders' sample conversion (SampleConverter.h:392-518), then (sum of channels) * (1/C) in float32
 //                 exactly as SA.cpp:535-548, fused with the peak / sum-of-squares reduction
 //                 (SA.cpp:612-631) for files that need no resampling
 //   k_resample  : libresample HQ restatement for files with src_rate != 44100 (SA.cpp:563-607)
@@ -19,20 +20,45 @@
 #define CHUNK 8192          // samples per CTA
 #define CT 256
 
+// one sample of a raw interleaved PCM stream as the float32 in 16-bit range the reference's decoders produce
+// (CoreFileFormats/Export/SampleConverter.h:392-518); idx counts samples (frame * channels + channel)
+__device__ __forceinline__ float pcm_sample(const unsigned char* __restrict__ base, long long idx, int format)
+{
+  switch (format) {
+    case AFX_PCM_I16: return (float)reinterpret_cast<const short*>(base)[idx];
+    case AFX_PCM_F32: return reinterpret_cast<const float*>(base)[idx];
+    case AFX_PCM_U8: return (float)(((int)base[idx] - 128) << 8);
+    case AFX_PCM_I8: return (float)((int)(signed char)base[idx] << 8);
+    case AFX_PCM_I16BE: { const unsigned char* p = base + 2 * idx; return (float)(short)((p[0] << 8) | p[1]); }
+    case AFX_PCM_I24: case AFX_PCM_I24BE: {
+      const unsigned char* p = base + 3 * idx;
+      const unsigned u = (format == AFX_PCM_I24) ? ((unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16))
+                                                 : ((unsigned)p[2] | ((unsigned)p[1] << 8) | ((unsigned)p[0] << 16));
+      return (float)((double)(int)(u << 8) * 32768.0 / 2147483648.0);
+    }
+    case AFX_PCM_I32: case AFX_PCM_I32BE: {
+      unsigned u = reinterpret_cast<const unsigned*>(base)[idx];
+      if (format == AFX_PCM_I32BE) u = __byte_perm(u, 0, 0x0123);
+      const float v = (float)((double)(int)u * 32768.0 / 2147483648.0);
+      return fmaxf(-32768.0f, fminf(32767.0f, v));
+    }
+    default: {   // AFX_PCM_F32U / AFX_PCM_F32UBE
+      unsigned u = reinterpret_cast<const unsigned*>(base)[idx];
+      if (format == AFX_PCM_F32UBE) u = __byte_perm(u, 0, 0x0123);
+      const double d = (double)__uint_as_float(u) * 32768.0;
+      return (float)(d < -32768.0 ? -32768.0 : (d > 32767.0 ? 32767.0 : d));
+    }
+  }
+}
+
 __device__ __forceinline__ float load_mono(const unsigned char* __restrict__ pcm, const AfxFile& f, int i)
 {
   // SA.cpp:535-548: dst = ch0; dst += ch[c] (c = 1..C-1); dst *= 1.0f / C    -- all float32
   const int C = f.channels;
-  float acc;
-  if (f.format == AFX_PCM_I16) {
-    const short* p = reinterpret_cast<const short*>(pcm + f.pcm_off) + (long long)i * C;
-    acc = (float)p[0];
-    for (int c = 1; c < C; ++c) acc = __fadd_rn(acc, (float)p[c]);
-  } else {
-    const float* p = reinterpret_cast<const float*>(pcm + f.pcm_off) + (long long)i * C;
-    acc = p[0];
-    for (int c = 1; c < C; ++c) acc = __fadd_rn(acc, p[c]);
-  }
+  const unsigned char* base = pcm + f.pcm_off;
+  const long long i0 = (long long)i * C;
+  float acc = pcm_sample(base, i0, f.format);
+  for (int c = 1; c < C; ++c) acc = __fadd_rn(acc, pcm_sample(base, i0 + c, f.format));
   if (C > 1) acc = __fmul_rn(acc, __fdiv_rn(1.0f, (float)C));
   return acc;
 }

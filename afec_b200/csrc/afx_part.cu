@@ -115,7 +115,7 @@ extern "C" int afx_part_open(afx_ctx* ctx, const afx_file* whole, const afx_part
   if (!ctx || !whole || !part || !out) return afx_fail(ctx, AFX_ERR_ARG, "afx_part_open: null argument");
   *out = nullptr;
   if (whole->channels < 1 || whole->channels > 8 || whole->nframes <= 0 || whole->nframes * whole->channels > 0x7fffffffLL || whole->src_rate <= 0 ||
-      (whole->format != AFX_PCM_I16 && whole->format != AFX_PCM_F32))
+      afx_pcm_bytes(whole->format) == 0)
     return afx_fail(ctx, AFX_ERR_ARG, "afx_part_open: unsupported file description");
   if (part->src_begin < 0 || part->src_end < part->src_begin || part->src_end > whole->nframes || part->out_begin < 0 || part->out_end < part->out_begin ||
       (part->src_begin & 3) || (part->src_end > part->src_begin && !pcm_slice))
@@ -131,7 +131,7 @@ extern "C" int afx_part_open(afx_ctx* ctx, const afx_file* whole, const afx_part
   j->ctx = ctx; j->part = *part;
   if (!ctx->part_pool.empty()) { j->bufs = ctx->part_pool.back(); ctx->part_pool.pop_back(); }
   j->resampled = whole->src_rate != P.sr;
-  const size_t bps = (whole->format == AFX_PCM_I16) ? 2 : 4;
+  const size_t bps = (size_t)afx_pcm_bytes(whole->format);
   const long long ns = part->src_end - part->src_begin, no = part->out_end - part->out_begin;
   const size_t pcm_bytes = (size_t)ns * whole->channels * bps;
 

@@ -93,16 +93,31 @@ void PackVR(std::vector<unsigned char>& out, const double* values, size_t n);
 void PackVVR(std::vector<unsigned char>& out, const double* values, size_t frames, size_t bands);
 
 // ---- decoded audio --------------------------------------------------------------------------------
+// Where a file's samples are and what they look like.  The bytes go to the GPU as they sit in the file (AFX_PCM_* raw
+// formats, converted on the device); only 64-bit float data is converted on the host (mHostConvert).
+struct TAudioInfo {
+  std::string mFileName;
+  int64_t mFrames = 0;
+  int mChannels = 0, mSampleRate = 0, mBitDepth = 0, mFormat = AFX_PCM_I16;
+  int64_t mFileSize = 0, mDataOffset = 0;
+  int mFileBytesPerSample = 0, mHostConvert = 0;
+  size_t mDataBytes = 0;                 // bytes ReadAudioData() writes: frames x channels x afx_pcm_bytes(mFormat)
+};
 struct TDecodedAudio {
-  std::vector<unsigned char> mBytes;     // interleaved frames: int16 (16-bit files) or float32 in 16-bit range
+  std::vector<unsigned char> mBytes;     // interleaved frames in format mFormat
   int64_t mFrames = 0;
   int mChannels = 0, mSampleRate = 0, mBitDepth = 0, mFormat = AFX_PCM_I16;
   int64_t mFileSize = 0;
 };
-// RIFF / WAVE reader (PCM 8/16/24/32, IEEE float 32/64, WAVE_FORMAT_EXTENSIBLE); sample conversion as
-// CoreFileFormats/Export/SampleConverter.h:392-518.  Throws TReadableException with the reference's
-// messages (WaveFile.cpp:387-407).  `dst` may point into pinned memory (capacity in bytes) to decode in place.
-void ReadWaveFile(const std::string& FileName, TDecodedAudio& Out);
+// RIFF / WAVE (PCM 8 / 16 / 24 / 32, IEEE float 32 / 64, WAVE_FORMAT_EXTENSIBLE; WaveFile.cpp:372-407) and AIFF / AIFC
+// (PCM 8 / 16 / 24 / 32 big endian, "sowt" little endian, "fl32" / "fl64"; AifFile.cpp:150-372, 436-480) by file extension.
+// Throw TReadableException with the reference's messages.  ProbeAudioFile reads headers only; ReadAudioData reads the
+// samples into caller memory (mDataBytes bytes -- e.g. a pinned ring slot), zero-filling what the file does not deliver.
+void ProbeAudioFile(const std::string& FileName, TAudioInfo& Out);
+void ReadAudioData(const TAudioInfo& Info, unsigned char* Dst);
+void ReadAudioFile(const std::string& FileName, TDecodedAudio& Out);
+void ReadWaveFile(const std::string& FileName, TDecodedAudio& Out);     // == ReadAudioFile (kept for callers of the first version)
+bool IsSupportedAudioFileExtension(const std::string& FileName);
 int ModificationStatTime(const std::string& FileName);
 std::string ExtractFileExtension(const std::string& FileName);
 
@@ -111,7 +126,7 @@ class TGpuSampleAnalyser {
 public:
   // TSampleAnalyser(SampleRate, FftFrameSize, HopFrameSize), Export/SampleAnalyser.h:33-36 (+ device list)
   TGpuSampleAnalyser(int SampleRate, int FftFrameSize, int HopFrameSize,
-                     const std::vector<int>& Devices = std::vector<int>(1, 0), int SlotsPerDevice = 2);
+                     const std::vector<int>& Devices = std::vector<int>(1, 0), int SlotsPerDevice = 3);
   ~TGpuSampleAnalyser();
 
   // Export/SampleAnalyser.h:54-56: analyse one file; throws TReadableException on load / analysis failure
@@ -140,12 +155,15 @@ public:
   int HopFrameSize() const { return mHopFrameSize; }
   void SetMaxBatchBytes(size_t Bytes) { mMaxBatchBytes = Bytes; }
   void SetMaxBatchFiles(int Files) { mMaxBatchFiles = Files; }
+  // decode threads of ExtractBatch (0 = one per slot); the reference decodes on hardware_concurrency threads (Crawler.cpp:680-681)
+  void SetDecodeThreads(int Threads) { mDecodeThreads = Threads; }
 
 private:
   struct Slot;
   int mSampleRate, mFftFrameSize, mHopFrameSize;
   size_t mMaxBatchBytes = (size_t)256 << 20;
   int mMaxBatchFiles = 2048;
+  int mDecodeThreads = 0;
   size_t mLongFileBytes = (size_t)512 << 20;
   int mNumDevices = 1;
   TSampleDescriptors AnalyzeDecodedInParts(const std::string& FileName, const TDecodedAudio& Audio, int NumParts) const;

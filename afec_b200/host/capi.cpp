@@ -3,6 +3,8 @@
 
 #include <chrono>
 #include <cstdio>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 using namespace afec;
@@ -44,6 +46,38 @@ int afxh_write_row(const char* db, const char* base_path, const char* filename, 
   } catch (const std::exception&) { return -2; }
 }
 
+// header probe of a WAV / AIFF file (no GPU): 0, or -1 with the loader's message in err
+int afxh_probe_audio(const char* filename, long long* frames, int* channels, int* rate, int* bits, int* format, long long* data_bytes,
+                     char* err, int errcap)
+{
+  try {
+    TAudioInfo I;
+    ProbeAudioFile(filename, I);
+    if (frames) *frames = I.mFrames;
+    if (channels) *channels = I.mChannels;
+    if (rate) *rate = I.mSampleRate;
+    if (bits) *bits = I.mBitDepth;
+    if (format) *format = I.mFormat;
+    if (data_bytes) *data_bytes = (long long)I.mDataBytes;
+    return 0;
+  } catch (const std::exception& e) {
+    if (err && errcap > 0) { strncpy(err, e.what(), (size_t)errcap - 1); err[errcap - 1] = 0; }
+    return -1;
+  }
+}
+
+// the sample bytes of a WAV / AIFF file as the extractor uploads them (raw, format as probed); returns bytes written or < 0
+long long afxh_read_audio(const char* filename, unsigned char* dst, long long cap)
+{
+  try {
+    TAudioInfo I;
+    ProbeAudioFile(filename, I);
+    if ((long long)I.mDataBytes > cap) return -2;
+    ReadAudioData(I, dst);
+    return (long long)I.mDataBytes;
+  } catch (const std::exception&) { return -1; }
+}
+
 // run the batched extractor over a list of files; returns failed count or < 0
 int afxh_extract_files(const char* db, const char* base_path, const char* const* files, int n_files, int hop,
                        const int* devices, int n_devices, int slots_per_device, double* audio_seconds, double* seconds,
@@ -56,6 +90,7 @@ int afxh_extract_files(const char* db, const char* base_path, const char* const*
     std::vector<int> dev(devices, devices + n_devices);
     TGpuSampleAnalyser an(44100, 2048, hop, dev, slots_per_device);
     std::vector<std::string> names(files, files + n_files);
+    if (getenv("AFXH_MAX_BATCH_FILES")) an.SetMaxBatchFiles(std::max(1, atoi(getenv("AFXH_MAX_BATCH_FILES"))));   // tests: many small chunks
     std::mutex lock; TGpuSampleAnalyser::TProgress pr;
     const int failed = an.ExtractBatch(names, &pool, lock, &pr);
     if (audio_seconds) *audio_seconds = pr.mAudioSeconds;

@@ -1,8 +1,8 @@
 // afec-b200-crawler: a minimal stand-in for `Crawler -l low -o afec-ll.db <paths...>` (Crawler.cpp:136-386,
 // 566-760) that drives the GPU path: collect files, build the change list against the database's modtimes
 // (Crawler.cpp:934-998), analyse in batches on the listed devices, write afec-ll.db.
-// Only the low-level set is produced (classification stays with the reference's host tools) and only WAV is
-// decoded here (FLAC / Ogg / MP3 decoding is the reference's CoreFileFormats, outside this path).
+// Only the low-level set is produced (classification stays with the reference's host tools) and only WAV and
+// AIFF are decoded here (FLAC / Ogg / MP3 decoding is the reference's CoreFileFormats, outside this path).
 #include "afx_host.h"
 
 #include <algorithm>
@@ -21,12 +21,7 @@ static volatile bool sAbort = false;
 static void on_sigint(int) { sAbort = true; }
 
 static bool is_dir(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode); }
-static bool has_audio_ext(const std::string& p)
-{
-  std::string e = ExtractFileExtension(p);
-  std::transform(e.begin(), e.end(), e.begin(), ::tolower);
-  return e == "wav";
-}
+static bool has_audio_ext(const std::string& p) { return IsSupportedAudioFileExtension(p); }
 static void collect(const std::string& path, std::vector<std::string>& out)
 {
   if (!is_dir(path)) { if (has_audio_ext(path)) out.push_back(path); return; }

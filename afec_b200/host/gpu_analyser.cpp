@@ -1,15 +1,17 @@
 // TGpuSampleAnalyser: the reference's TSampleAnalyser entry points (Export/SampleAnalyser.h:33-63;
 // SampleAnalyser.cpp:345-416) over the C ABI of libafec_b200.so.
 //
-// Each "slot" owns one afx context (stream + device buffers) and one pinned PCM ring slot.  ExtractBatch
-// starts one thread per slot; a thread repeatedly claims the next chunk of files, decodes it into its
-// pinned slot, runs upload -> compute -> download on its own stream and hands the results to the pool.
-// With two or more slots per device the decode / H2D of one chunk overlaps the kernels of another.
+// Each "slot" owns one afx context (stream + device buffers) and one pinned PCM ring slot.  ExtractBatch runs a
+// three-stage pipeline over the slots: decode threads fill pinned slots, one GPU thread per slot analyses them, one
+// sink thread inserts the rows (see ExtractBatch).
 #include "afx_host.h"
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <sys/stat.h>
 #include <thread>
 
 namespace afec {
@@ -71,7 +73,7 @@ static const char* file_status_message(int status)
 TSampleDescriptors TGpuSampleAnalyser::AnalyzeInParts(const std::string& FileName, int NumParts) const
 {
   TDecodedAudio audio;
-  ReadWaveFile(FileName, audio);
+  ReadAudioFile(FileName, audio);
   return AnalyzeDecodedInParts(FileName, audio, NumParts);
 }
 
@@ -89,7 +91,7 @@ TSampleDescriptors TGpuSampleAnalyser::AnalyzeDecodedInParts(const std::string& 
   if (afx_part_plan(mSampleRate, audio.mFrames, audio.mSampleRate, n_parts, parts.data()) != AFX_OK)
     throw TReadableException("afx_part_plan failed");
   afx_file whole; describe(audio, nullptr, whole);
-  const size_t frame_bytes = (size_t)audio.mChannels * (audio.mFormat == AFX_PCM_I16 ? 2 : 4);
+  const size_t frame_bytes = (size_t)audio.mChannels * (size_t)afx_pcm_bytes(audio.mFormat);
   std::vector<afx_partjob*> jobs((size_t)n_parts, nullptr);
   std::vector<afx_part_sums> sums((size_t)n_parts);
   std::vector<std::string> errors((size_t)n_parts);
@@ -135,7 +137,7 @@ TSampleDescriptors TGpuSampleAnalyser::AnalyzeDecodedInParts(const std::string& 
 TSampleDescriptors TGpuSampleAnalyser::Analyze(const std::string& FileName) const
 {
   TDecodedAudio audio;
-  ReadWaveFile(FileName, audio);               // throws with the loader's message
+  ReadAudioFile(FileName, audio);               // throws with the loader's message
   if (mNumDevices > 1 && mLongFileBytes && audio.mBytes.size() >= mLongFileBytes) return AnalyzeDecodedInParts(FileName, audio, 0);
   std::lock_guard<std::mutex> lock(mSingleLock);
   Slot& S = *mSlots[0];
@@ -155,7 +157,7 @@ TSampleDescriptors TGpuSampleAnalyser::Analyze(const std::string& FileName) cons
 void TGpuSampleAnalyser::Extract(const std::string& FileName, TSampleDescriptorPool* pPool, std::mutex& PoolLock) const
 {
   TDecodedAudio audio;
-  try { ReadWaveFile(FileName, audio); }
+  try { ReadAudioFile(FileName, audio); }
   catch (const std::exception& e) {
     const std::lock_guard<std::mutex> lock(PoolLock);
     pPool->InsertFailedSample(FileName, std::string("Sample failed to load: ") + e.what());
@@ -194,96 +196,170 @@ void TGpuSampleAnalyser::Extract(const std::string& FileName, TSampleDescriptorP
   pPool->InsertSample(FileName, results);
 }
 
+// The batched extractor as a three-stage pipeline over a ring of slots (one afx context + one pinned buffer each):
+//
+//   decode threads  claim the next chunk of files, take a FREE slot, probe the headers (sizes, formats) and read every
+//                   file's sample bytes straight into the slot's pinned buffer, back to back      -> READY
+//   GPU threads     one per slot: afx_analyze (one H2D copy of the chunk, the kernels, one D2H block)   -> DONE
+//   sink thread     rows of finished chunks go to the pool one by one (PoolLock is held per ROW, a bulk
+//                   transaction per chunk), then the slot's batch is freed                               -> FREE
+//
+// The decode threads never wait for the GPU (only for a free slot), the GPU never waits for sqlite: with the reference's
+// one-file-at-a-time loop (Crawler.cpp:706-728) decode, analysis and insert of a file are serial on one thread.
 int TGpuSampleAnalyser::ExtractBatch(const std::vector<std::string>& FileNames, TSampleDescriptorPool* pPool,
                                      std::mutex& PoolLock, TProgress* pProgress, const volatile bool* pAbort) const
 {
   const auto t0 = std::chrono::steady_clock::now();
-  // chunks by file size on disk (a cheap upper bound of the decoded PCM for 16-bit files)
+  // chunks by file size on disk (an upper bound of the raw PCM bytes)
   struct Chunk { size_t first, count; };
   std::vector<Chunk> chunks;
   {
     size_t first = 0, bytes = 0;
     for (size_t i = 0; i < FileNames.size(); ++i) {
-      struct { int64_t size; } s; TDecodedAudio probe; (void)probe;
-      FILE* f = fopen(FileNames[i].c_str(), "rb"); s.size = 0;
-      if (f) { fseek(f, 0, SEEK_END); s.size = ftell(f); fclose(f); }
-      if (i > first && (bytes + (size_t)s.size > mMaxBatchBytes || (int)(i - first) >= mMaxBatchFiles)) {
+      struct stat st; const size_t size = (stat(FileNames[i].c_str(), &st) == 0) ? (size_t)st.st_size : 0;
+      if (i > first && (bytes + size > mMaxBatchBytes || (int)(i - first) >= mMaxBatchFiles)) {
         chunks.push_back({ first, i - first }); first = i; bytes = 0;
       }
-      bytes += (size_t)s.size;
+      bytes += size;
     }
     if (first < FileNames.size()) chunks.push_back({ first, FileNames.size() - first });
   }
-  std::atomic<size_t> next(0);
-  std::atomic<long long> failed(0), frames(0), rframes(0), files(0);
-  std::mutex stat_lock; double audio_s = 0.0;
 
-  auto worker = [&](Slot* S) {
-    std::vector<TDecodedAudio> audio;
+  enum { kFree = 0, kFilling, kReady, kDone };
+  struct Work {                               // per slot
+    int state = kFree;
+    Chunk chunk{ 0, 0 };
+    std::vector<TAudioInfo> info;
     std::vector<std::string> load_error;
     std::vector<afx_file> descr;
     std::vector<int> index;                   // batch position -> file position inside the chunk
+    std::string batch_error;
+    afx_batch* batch = nullptr;
+  };
+  const size_t S = mSlots.size();
+  std::vector<Work> work(S);
+  std::mutex mu; std::condition_variable cv;  // guards every Work::state, `done_order`, `decoders_left`, `workers_left`
+  std::deque<size_t> done_order;
+  std::atomic<size_t> next(0);
+  int decoders_left = 0, workers_left = (int)S;
+  std::atomic<long long> failed(0), frames(0), rframes(0), files(0);
+  double audio_s = 0.0;
+  auto aborted = [&]() { return pAbort && *pAbort; };
+
+  auto decoder = [&]() {
     for (;;) {
-      if (pAbort && *pAbort) return;
-      const size_t ci = next.fetch_add(1);
-      if (ci >= chunks.size()) return;
-      const Chunk c = chunks[ci];
-      audio.assign(c.count, TDecodedAudio()); load_error.assign(c.count, std::string());
+      const size_t ci = aborted() ? chunks.size() : next.fetch_add(1);
+      if (ci >= chunks.size()) break;
+      size_t si = S;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { for (size_t k = 0; k < S; ++k) if (work[k].state == kFree) { si = k; return true; } return false; });
+        work[si].state = kFilling;
+      }
+      Work& W = work[si]; Slot* Sl = mSlots[si].get();
+      W.chunk = chunks[ci];
+      const size_t n = W.chunk.count;
+      W.info.assign(n, TAudioInfo()); W.load_error.assign(n, std::string()); W.descr.clear(); W.index.clear(); W.batch_error.clear(); W.batch = nullptr;
       size_t total = 0;
-      for (size_t k = 0; k < c.count; ++k) {
+      for (size_t k = 0; k < n; ++k) {
         try {
-          ReadWaveFile(FileNames[c.first + k], audio[k]);
-          if (audio[k].mChannels > 8) load_error[k] = file_status_message(AFX_FILE_BAD_CHANNELS);
-        } catch (const std::exception& e) { load_error[k] = e.what(); if (load_error[k].empty()) load_error[k] = "Audio file failed to load: Unknown error"; }
-        if (load_error[k].empty()) total += (audio[k].mBytes.size() + 15) & ~(size_t)15;
+          ProbeAudioFile(FileNames[W.chunk.first + k], W.info[k]);
+          if (W.info[k].mChannels > 8) W.load_error[k] = file_status_message(AFX_FILE_BAD_CHANNELS);
+          else if (W.info[k].mFrames == 0) W.load_error[k] = file_status_message(AFX_FILE_EMPTY);
+        } catch (const std::exception& e) { W.load_error[k] = e.what(); if (W.load_error[k].empty()) W.load_error[k] = "Audio file failed to load: Unknown error"; }
+        if (W.load_error[k].empty()) total += (W.info[k].mDataBytes + 15) & ~(size_t)15;
       }
-      // stage the chunk's PCM contiguously in the pinned slot: one H2D copy for the whole chunk
-      descr.clear(); index.clear();
-      std::string batch_error;
-      afx_batch* b = nullptr;
-      if (!S->reserve(total + 16)) batch_error = "out of pinned host memory";
+      if (!Sl->reserve(total + 16)) W.batch_error = "out of pinned host memory";
       else {
+        // files back to back in the pinned slot: one H2D copy for the whole chunk (the library merges host-contiguous
+        // files; every file starts on a 4-byte boundary so 16- and 32-bit samples stay aligned)
         size_t off = 0;
-        for (size_t k = 0; k < c.count; ++k) {
-          if (!load_error[k].empty()) continue;
-          memcpy(S->pinned + off, audio[k].mBytes.data(), audio[k].mBytes.size());
-          afx_file f; describe(audio[k], S->pinned + off, f);
-          descr.push_back(f); index.push_back((int)k);
-          off += audio[k].mBytes.size();
-          // keep files back to back (the library merges host-contiguous files into one copy); int16 / float32
-          // alignment is preserved because every file's byte count is a multiple of its sample size
-          std::vector<unsigned char>().swap(audio[k].mBytes);
+        for (size_t k = 0; k < n; ++k) {
+          if (!W.load_error[k].empty()) continue;
+          try { ReadAudioData(W.info[k], Sl->pinned + off); }
+          catch (const std::exception& e) { W.load_error[k] = e.what(); continue; }
+          afx_file f; memset(&f, 0, sizeof(f));
+          f.pcm = Sl->pinned + off; f.nframes = W.info[k].mFrames; f.channels = W.info[k].mChannels; f.src_rate = W.info[k].mSampleRate;
+          f.format = W.info[k].mFormat; f.bit_depth = W.info[k].mBitDepth; f.file_size = W.info[k].mFileSize;
+          W.descr.push_back(f); W.index.push_back((int)k);
+          off += (W.info[k].mDataBytes + 3) & ~(size_t)3;
         }
-        if (!descr.empty() && afx_analyze(S->ctx, descr.data(), (int32_t)descr.size(), &b) != AFX_OK)
-          batch_error = afx_last_error(S->ctx);      // a CUDA failure fails this batch's files only
       }
-      // hand the chunk to the pool in file order
-      TSampleDescriptors results;
-      const std::lock_guard<std::mutex> lock(PoolLock);
-      pPool->BeginBulk();
+      { std::lock_guard<std::mutex> lk(mu); W.state = kReady; }
+      cv.notify_all();
+    }
+    { std::lock_guard<std::mutex> lk(mu); --decoders_left; }
+    cv.notify_all();
+  };
+
+  auto gpu_worker = [&](size_t si) {
+    Work& W = work[si]; Slot* Sl = mSlots[si].get();
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return W.state == kReady || (decoders_left == 0 && W.state == kFree); });
+        if (W.state != kReady) break;
+      }
+      if (W.batch_error.empty() && !W.descr.empty() &&
+          afx_analyze(Sl->ctx, W.descr.data(), (int32_t)W.descr.size(), &W.batch) != AFX_OK)
+        W.batch_error = afx_last_error(Sl->ctx);      // a CUDA failure fails this chunk's files only
+      { std::lock_guard<std::mutex> lk(mu); W.state = kDone; done_order.push_back(si); }
+      cv.notify_all();
+    }
+    { std::lock_guard<std::mutex> lk(mu); --workers_left; }
+    cv.notify_all();
+  };
+
+  auto sink = [&]() {
+    TSampleDescriptors results;
+    for (;;) {
+      size_t si;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return !done_order.empty() || workers_left == 0; });
+        if (done_order.empty()) break;
+        si = done_order.front(); done_order.pop_front();
+      }
+      Work& W = work[si];
+      { const std::lock_guard<std::mutex> lock(PoolLock); pPool->BeginBulk(); }
       size_t bi = 0; double chunk_audio = 0.0;
-      for (size_t k = 0; k < c.count; ++k) {
-        const std::string& name = FileNames[c.first + k];
+      for (size_t k = 0; k < W.chunk.count; ++k) {
+        const std::string& name = FileNames[W.chunk.first + k];
         try {
-          if (!load_error[k].empty()) { pPool->InsertFailedSample(name, "Sample failed to load: " + load_error[k]); ++failed; continue; }
-          if (!batch_error.empty() || !b) { pPool->InsertFailedSample(name, "Sample failed to analyse: " + batch_error); ++failed; ++bi; continue; }
-          afx_file_result r; afx_batch_result(b, (int32_t)bi, &r); ++bi;
-          if (r.status != AFX_FILE_OK) { pPool->InsertFailedSample(name, std::string("Sample failed to load: ") + file_status_message(r.status)); ++failed; continue; }
+          if (!W.load_error[k].empty()) {
+            const std::lock_guard<std::mutex> lock(PoolLock);
+            pPool->InsertFailedSample(name, "Sample failed to load: " + W.load_error[k]); ++failed; continue;
+          }
+          if (!W.batch_error.empty() || !W.batch) {
+            const std::lock_guard<std::mutex> lock(PoolLock);
+            pPool->InsertFailedSample(name, "Sample failed to analyse: " + W.batch_error); ++failed; ++bi; continue;
+          }
+          afx_file_result r; afx_batch_result(W.batch, (int32_t)bi, &r); ++bi;
+          if (r.status != AFX_FILE_OK) {
+            const std::lock_guard<std::mutex> lock(PoolLock);
+            pPool->InsertFailedSample(name, std::string("Sample failed to load: ") + file_status_message(r.status)); ++failed; continue;
+          }
           results.mFileName = name; results.mFileType = ExtractFileExtension(name);
-          results.Assign(r);
-          pPool->InsertSample(name, results);
+          results.Assign(r);                   // outside the lock: only the insert itself is serialised
+          { const std::lock_guard<std::mutex> lock(PoolLock); pPool->InsertSample(name, results); }
           frames += r.n_frames; rframes += r.n_rhythm_frames; ++files;
           chunk_audio += results.mHeader[1];
         } catch (const std::exception&) { ++failed; }
       }
-      pPool->EndBulk();
-      if (b) afx_batch_free(b);
-      { std::lock_guard<std::mutex> sl(stat_lock); audio_s += chunk_audio; }
+      { const std::lock_guard<std::mutex> lock(PoolLock); pPool->EndBulk(); }
+      if (W.batch) { afx_batch_free(W.batch); W.batch = nullptr; }
+      audio_s += chunk_audio;
+      { std::lock_guard<std::mutex> lk(mu); W.state = kFree; }
+      cv.notify_all();
     }
   };
 
+  const int n_dec = std::max(1, std::min<int>(mDecodeThreads > 0 ? mDecodeThreads : (int)S, (int)std::max<size_t>(1, chunks.size())));
+  decoders_left = n_dec;
   std::vector<std::thread> threads;
-  for (auto& s : mSlots) threads.emplace_back(worker, s.get());
+  for (int d = 0; d < n_dec; ++d) threads.emplace_back(decoder);
+  for (size_t si = 0; si < S; ++si) threads.emplace_back(gpu_worker, si);
+  threads.emplace_back(sink);
   for (auto& t : threads) t.join();
   if (pProgress) {
     pProgress->mFiles = files; pProgress->mFailed = failed; pProgress->mMainFrames = frames; pProgress->mRhythmFrames = rframes;

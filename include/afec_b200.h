@@ -45,11 +45,23 @@ extern "C" {
                                    an int, SampleAnalyser.cpp:484): this file fails, the rest of the batch is analysed */
 
 /* ---- PCM formats -------------------------------------------------------------------------- */
-/* Both are INTERLEAVED frames.  I16 is converted as (float)value, F32 is taken as is: the
- * reference's decoders hand LoadSample float32 in 16-bit range (+-32768),
- * Source/Core/CoreFileFormats/Export/SampleConverter.h:446-449. */
-#define AFX_PCM_I16 0
-#define AFX_PCM_F32 1
+/* All are INTERLEAVED frames, uploaded as they sit in the file and converted ON THE DEVICE to the float32 in 16-bit
+ * range (+-32768) the reference's decoders hand LoadSample (Source/Core/CoreFileFormats/Export/SampleConverter.h:392-518
+ * -- the conversions below restate those, value for value): raw bytes cross PCIe, no host conversion pass. */
+#define AFX_PCM_I16 0     /* little-endian int16: (float)v                                   SampleConverter.h:446-449 */
+#define AFX_PCM_F32 1     /* float32 already in 16-bit range, taken as is */
+#define AFX_PCM_U8 2      /* unsigned 8-bit (WAV): (float)((v - 128) << 8)                    :392-395 */
+#define AFX_PCM_I24 3     /* packed 3-byte little-endian: (float)((v24 << 8) * 32768.0 / 2^31) :473-487 */
+#define AFX_PCM_I32 4     /* little-endian int32: clamp((float)(v * 32768.0 / 2^31))          :514-518 */
+#define AFX_PCM_F32U 5    /* little-endian float32 in unit range (WAV IEEE float): (float)clamp(v * 32768.0), WaveFile.cpp */
+#define AFX_PCM_I8 6      /* signed 8-bit (AIFF): (float)(v << 8)                             :410-413 */
+#define AFX_PCM_I16BE 7   /* big-endian forms of the above (AIFF) */
+#define AFX_PCM_I24BE 8
+#define AFX_PCM_I32BE 9
+#define AFX_PCM_F32UBE 10
+#define AFX_PCM_FORMATS 11
+/* bytes per sample of a format (0: unknown format) */
+int afx_pcm_bytes(int32_t format);
 
 /* ---- feature groups (afx_config.features) --------------------------------------------- */
 #define AFX_FEAT_SPECTRAL (1u << 0)  /* window+FFT+magnitude, spectral rms/centroid/spread/skew/kurt/rolloff/flatness/flux */

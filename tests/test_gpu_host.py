@@ -102,3 +102,71 @@ def test_long_file_in_parts_writes_the_same_row(tmp_path):
         if k == "modtime":
             continue
         assert g[k] == w[k], k
+
+
+def test_sample_formats_through_the_crawler_vs_the_reference(tmp_path):
+    """WAV (8 / 16 / 24 / 32-bit, float 32 / 64, extensible) and AIFF / AIFC files: afec-b200-crawler (raw bytes to the GPU,
+    sample conversion on the device) against the database the unmodified reference writes for the same files."""
+    from oracle import oracle
+    if not oracle.have_reference():
+        pytest.skip("oracle/_ref not built")
+    import audio_files
+    from afec_b200 import synth
+    d = str(tmp_path / "lib")
+    os.makedirs(d)
+    pcm = synth.one_shot(64, 0.5, rate=48000, channels=2)
+    paths = []
+    for name, (writer, kind, kw, _) in sorted(audio_files.format_cases().items()):
+        p = os.path.join(d, name)
+        writer(p, audio_files.quantise(pcm, kind), kind, 48000, **kw)
+        paths.append(p)
+    bad = os.path.join(d, "in24.aifc")
+    audio_files.write_aiff(bad, audio_files.quantise(pcm, "i24"), "i24", 48000, compression="in24")
+    ref_db = str(tmp_path / "ref.db")
+    subprocess.run([oracle.REF_BIN, "db", "1024", ref_db] + paths + [bad], check=True, env=dict(os.environ, HOME=str(tmp_path)),
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    db = os.path.join(d, "afec-ll.db")
+    run_crawler(["-o", db, d])
+    got, _, _ = dbcompare.rows(db)
+    want, _, _ = dbcompare.rows(ref_db)
+    assert set(got) == set(want)
+    for name in want:
+        errs = dbcompare.compare_row(got[name], want[name])
+        assert not errs, name + ":\n" + "\n".join(errs[:20])
+    assert want["in24.aifc"]["status"].startswith("error: Sample failed to load")
+
+
+def test_extract_batch_on_two_devices(tmp_path):
+    """TGpuSampleAnalyser over devices {0, 1}: the decode -> GPU -> sink pipeline with slots on both GPUs writes the same
+    rows as one device (needs two visible GPUs)."""
+    import ctypes as C
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from afec_b200 import synth
+    from oracle import oracle
+    L = C.CDLL(afx_build.HOST_LIB)
+    L.afxh_extract_files.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int,
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    d = str(tmp_path)
+    names = []
+    for i in range(48):
+        p = os.path.join(d, "f%03d.wav" % i)
+        oracle.write_wav(p, synth.one_shot(2000 + i, 0.2 + 0.05 * i, channels=1 + i % 2), 44100)
+        names.append(p.encode())
+    arr = (C.c_char_p * len(names))(*names)
+    out = {}
+    for tag, devs in (("one", [0]), ("two", [0, 1])):
+        db = os.path.join(d, tag + ".db")
+        dv = (C.c_int * len(devs))(*devs)
+        os.environ["AFXH_MAX_BATCH_FILES"] = "5"                      # many chunks: both devices get work
+        failed = L.afxh_extract_files(db.encode(), b"", arr, len(names), 1024, dv, len(devs), 2, None, None, None)
+        del os.environ["AFXH_MAX_BATCH_FILES"]
+        assert failed == 0
+        out[tag] = dbcompare.rows(db)[0]
+    assert set(out["one"]) == set(out["two"]) and len(out["one"]) == 48
+    for name, w in out["one"].items():
+        g = out["two"][name]
+        for k in w:
+            if k != "modtime":
+                assert g[k] == w[k], (name, k)

@@ -281,6 +281,35 @@ def test_launch_groups_do_not_change_results(feats, monkeypatch):
         assert np.array_equal(g.stats, w.stats)
 
 
+def test_raw_sample_formats_convert_on_the_device(analysers, feats, oracle_lib):
+    """Every AFX_PCM_* raw format (include/afec_b200.h): the bytes as they sit in a WAV / AIFF file go up unconverted and
+    k_downmix applies the decoders' sample conversion (SampleConverter.h:392-518) -- the conditioned signal must equal the
+    oracle's on the float32 samples the reference's decoders produce for those bytes (pinned against the live reference
+    in tests/test_oracle_vs_reference.py), bit for bit."""
+    import audio_files
+    pcm = synth.one_shot(62, 0.4, rate=48000, channels=2)
+    mono = synth.one_shot(63, 0.3)
+    an = analysers(1024)
+    files, keep, want = [], [], []
+    codes = {("u8", False): api.AFX_PCM_U8, ("i8", True): api.AFX_PCM_I8, ("i16", False): api.AFX_PCM_I16, ("i16", True): api.AFX_PCM_I16BE,
+             ("i24", False): api.AFX_PCM_I24, ("i24", True): api.AFX_PCM_I24BE, ("i32", False): api.AFX_PCM_I32, ("i32", True): api.AFX_PCM_I32BE,
+             ("f32", False): api.AFX_PCM_F32U, ("f32", True): api.AFX_PCM_F32UBE}
+    for src, rate in ((pcm, 48000), (mono, 44100)):
+        for (kind, big), code in codes.items():
+            values = audio_files.quantise(src, kind)
+            raw = np.frombuffer(audio_files._sample_bytes(values, kind, big), dtype=np.uint8).copy()
+            keep.append(raw)
+            files.append(api.AfxFile(raw.ctypes.data, values.shape[0], values.shape[1], rate, code, 16, 1234))
+            want.append((audio_files.to_float16range(values, kind), rate))
+    b = an.batch_from_descriptors(files, keep).run()
+    for i, (x, rate) in enumerate(want):
+        data = oracle_lib.condition(x, src_rate=rate)[0]
+        got = b.conditioned(i)
+        assert got.shape == data.shape and np.array_equal(got, data), "format case %d" % i
+        check(b.result(i), oracle_lib.analyze(x, src_rate=rate, file_size=1234), feats, mdata=data)
+    b.free()
+
+
 def test_rhythm_front_end_fused_equals_split(feats, monkeypatch, oracle_lib):
     """The rhythm front end has two schedules (afx_rhythm.cu): ONE fused kernel with a CTA per file (launch groups with
     many files) and the split polar / whiten / odf / power kernels (few files).  Both must give the same bits, and both
