@@ -20,11 +20,13 @@ FEAT_SPECTRAL, FEAT_AMPLITUDE, FEAT_PEAKS, FEAT_BANDS = 1, 2, 4, 8
 FEAT_PITCH, FEAT_AUTOCORR, FEAT_RHYTHM, FEAT_STATS = 16, 32, 64, 128
 FEAT_ALL = 0xFF
 FEAT_HIGHLEVEL = 0x100   # on top of FEAT_ALL: model-free high-level descriptors + the classification feature vector
+FEAT_PACK = 0x200        # on top of FEAT_ALL: the row's msgpack BLOB images packed on the GPU
+N_BLOBS = 122
 HAVE_RESAMPLE = True   # k_resample + host block plan (libresample HQ restatement)
 
 EXPORTS = [
     "afx_abi_version", "afx_pcm_bytes", "afx_create", "afx_destroy", "afx_last_error", "afx_trim", "afx_host_alloc", "afx_host_free",
-    "afx_batch_create", "afx_batch_upload", "afx_batch_compute", "afx_batch_download", "afx_batch_sync",
+    "afx_batch_create", "afx_batch_upload", "afx_batch_compute", "afx_batch_download", "afx_batch_download_rows", "afx_batch_sync",
     "afx_analyze", "afx_batch_result", "afx_batch_free", "afx_batch_timings", "afx_batch_counters",
     "afx_batch_kernel_times", "afx_batch_conditioned", "afx_measure_fp64_peak", "afx_debug_fft",
     "afx_part_plan", "afx_part_sums_init", "afx_part_sums_merge", "afx_part_open", "afx_part_peak", "afx_part_trim",
@@ -47,7 +49,8 @@ class AfxFileResult(C.Structure):
                 ("hl_status", C.c_int32), ("header", C.POINTER(C.c_double)),
                 ("fs", C.POINTER(C.c_double) * layout.N_FS), ("fv", C.POINTER(C.c_double) * layout.N_FV),
                 ("stats", C.POINTER(C.c_double)), ("highlevel", C.POINTER(C.c_double)), ("hl_pitch", C.POINTER(C.c_double)),
-                ("hl_signature", C.POINTER(C.c_double)), ("hl_features", C.POINTER(C.c_double))]
+                ("hl_signature", C.POINTER(C.c_double)), ("hl_features", C.POINTER(C.c_double)),
+                ("packed", C.POINTER(C.c_ubyte)), ("packed_off", C.POINTER(C.c_uint32))]
 
 
 class AfxPart(C.Structure):
@@ -86,7 +89,7 @@ def load_library():
     L.afx_host_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     L.afx_host_free.argtypes = [C.c_void_p, C.c_void_p]
     L.afx_batch_create.argtypes = [C.c_void_p, C.POINTER(AfxFile), C.c_int32, C.POINTER(C.c_void_p)]
-    for name in ("afx_batch_upload", "afx_batch_compute", "afx_batch_download", "afx_batch_sync"):
+    for name in ("afx_batch_upload", "afx_batch_compute", "afx_batch_download", "afx_batch_download_rows", "afx_batch_sync"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.afx_analyze.argtypes = [C.c_void_p, C.POINTER(AfxFile), C.c_int32, C.POINTER(C.c_void_p)]
     L.afx_batch_result.argtypes = [C.c_void_p, C.c_int32, C.POINTER(AfxFileResult)]
@@ -158,8 +161,22 @@ class Batch:
     def download(self):
         self._an._check(self._L.afx_batch_download(self._h))
 
+    def download_rows(self):
+        self._an._check(self._L.afx_batch_download_rows(self._h))
+
     def sync(self):
         self._an._check(self._L.afx_batch_sync(self._h))
+
+    def packed_blobs(self, i: int) -> list:
+        """File i's AFX_N_BLOBS msgpack BLOB images (contexts created with FEAT_PACK), in afec-ll.db column order."""
+        r = self.raw_result(i)
+        if r.status != 0:
+            return []
+        if not r.packed:
+            raise AfxError("the context was not created with FEAT_PACK")
+        off = np.ctypeslib.as_array(r.packed_off, (N_BLOBS + 1,))
+        raw = np.ctypeslib.as_array(r.packed, (int(off[-1]),))
+        return [raw[int(off[k]):int(off[k + 1])].tobytes() for k in range(N_BLOBS)]
 
     def run(self):
         self.upload(); self.compute(); self.download(); self.sync()

@@ -245,6 +245,8 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
     return fail(nullptr, AFX_ERR_ARG, "afx_create: only sample_rate 44100 / fft_size 2048 are supported (Crawler.cpp:41-43)");
   if (cfg->hop_size < 256 || cfg->hop_size > 2048 || (cfg->hop_size % 256) != 0)
     return fail(nullptr, AFX_ERR_ARG, "afx_create: hop_size must be a multiple of 256 in [256, 2048]");
+  if ((cfg->features & AFX_FEAT_PACK) && (cfg->features & AFX_FEAT_ALL) != AFX_FEAT_ALL)
+    return fail(nullptr, AFX_ERR_ARG, "afx_create: AFX_FEAT_PACK packs the rows of the full low-level set (AFX_FEAT_ALL | AFX_FEAT_PACK)");
   if ((cfg->features & AFX_FEAT_HIGHLEVEL) && (cfg->features & AFX_FEAT_ALL) != AFX_FEAT_ALL)
     return fail(nullptr, AFX_ERR_ARG, "afx_create: AFX_FEAT_HIGHLEVEL derives from the full low-level set (AFX_FEAT_ALL | AFX_FEAT_HIGHLEVEL)");
   int ndev = 0;
@@ -405,9 +407,9 @@ extern "C" void afx_destroy(afx_ctx* ctx)
   if (ctx->ev_spec) cudaEventDestroy(ctx->ev_spec);
   DevBuf* bufs[] = { &ctx->tables, &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
     &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch,
-    &ctx->d_hl, &ctx->d_hl_pitch, &ctx->d_hl_sig, &ctx->d_hl_feat, &ctx->d_hl_status };
+    &ctx->d_hl, &ctx->d_hl_pitch, &ctx->d_hl_sig, &ctx->d_hl_feat, &ctx->d_hl_status, &ctx->d_pack, &ctx->d_pack_off, &ctx->d_pack_file_off };
   for (DevBuf* b : bufs) b->release();
-  ctx->h_results_cache.release(); ctx->h_plan_cache.release();
+  ctx->h_results_cache.release(); ctx->h_plan_cache.release(); ctx->h_pack_cache.release();
   for (auto& pb : ctx->part_pool) pb.release();
   delete ctx;
 }
@@ -424,7 +426,7 @@ extern "C" int afx_trim(afx_ctx* ctx)
   if (ctx->live) return fail(ctx, AFX_ERR_STATE, "afx_trim: a batch of this context is still alive");
   DevBuf* bufs[] = { &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
     &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch,
-    &ctx->d_hl, &ctx->d_hl_pitch, &ctx->d_hl_sig, &ctx->d_hl_feat, &ctx->d_hl_status };
+    &ctx->d_hl, &ctx->d_hl_pitch, &ctx->d_hl_sig, &ctx->d_hl_feat, &ctx->d_hl_status, &ctx->d_pack, &ctx->d_pack_off, &ctx->d_pack_file_off };
   for (DevBuf* b : bufs) b->release();
   for (auto& pb : ctx->part_pool) pb.release();
   ctx->part_pool.clear();
@@ -603,6 +605,15 @@ int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, 
     b->o_hl_status = o; o += ((size_t)n_files * sizeof(int) + 7) / 8;
   }
   b->total_doubles = o;
+  if (ctx->cfg.features & AFX_FEAT_PACK) {
+    b->pack_file_off.resize(n_files);
+    size_t po = 0;
+    for (int i = 0; i < n_files; ++i) {
+      b->pack_file_off[i] = po;
+      if (b->files[i].status == AFX_FILE_OK) po += (afx_pack_region_bytes(b->files[i].frame_cap, b->files[i].rframe_cap) + 15) & ~(size_t)15;
+    }
+    b->pack_bytes = po;
+  }
   *out = b;
   return AFX_OK;
 }
@@ -665,6 +676,11 @@ extern "C" int afx_batch_upload(afx_batch* b)
     CK(ctx->d_hl_pitch.reserve((TF + 1) * 8), "cudaMalloc(hl pitch)");
     CK(ctx->d_hl_status.reserve((size_t)(n + 1) * 4), "cudaMalloc(hl status)");
   }
+  if (feat & AFX_FEAT_PACK) {
+    CK(ctx->d_pack.reserve(b->pack_bytes + 64), "cudaMalloc(pack)");
+    CK(ctx->d_pack_off.reserve((size_t)(n + 1) * (AFX_N_BLOBS + 1) * 4), "cudaMalloc(pack offsets)");
+    CK(ctx->d_pack_file_off.reserve((size_t)(n + 1) * 8), "cudaMalloc(pack file offsets)");
+  }
   CK(ctx->d_stats.reserve((size_t)(n + 1) * AFX_N_SERIES * AFX_N_STATS * 8), "cudaMalloc(stats)");
   CK(ctx->d_header.reserve((size_t)(n + 1) * AFX_N_HEADER * 8), "cudaMalloc(header)");
 
@@ -679,6 +695,7 @@ extern "C" int afx_batch_upload(afx_batch* b)
   const size_t p_rb = place(nrb * sizeof(RsBlock)), p_rbf = place(nrb * 4), p_chk = place(nck * 8);
   const size_t p_inj = place(b->inject.size() * sizeof(AfxInject));
   const size_t p_order = place((size_t)n * 4);
+  const size_t p_pack = place(b->pack_file_off.size() * 8);
   take_cached(b->h_plan, ctx->h_plan_cache, po);
   CK(b->h_plan.reserve(po + 256), "cudaHostAlloc(plan)");
   CK(ctx->d_plan.reserve(po + 256), "cudaMalloc(plan)");
@@ -691,6 +708,7 @@ extern "C" int afx_batch_upload(afx_batch* b)
   if (nck) memcpy(hp + p_chk, b->rs_chk.data(), nck * 8);
   if (!b->inject.empty()) memcpy(hp + p_inj, b->inject.data(), b->inject.size() * sizeof(AfxInject));
   if (n) memcpy(hp + p_order, b->file_order.data(), (size_t)n * 4);
+  if (!b->pack_file_off.empty()) memcpy(hp + p_pack, b->pack_file_off.data(), b->pack_file_off.size() * 8);
 
   CK(cudaEventRecord(b->ev[0], ctx->stream), "cudaEventRecord");
   CK(cudaMemcpyAsync(ctx->d_plan.p, hp, po, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(plan)");
@@ -715,6 +733,8 @@ extern "C" int afx_batch_upload(afx_batch* b)
   D.slot_file = (const int*)ctx->d_slotmap.p; D.rslot_file = (const int*)ctx->d_slotmap.p + TF + 1;
   D.max_fr = b->max_fr;
   D.stats = (double*)ctx->d_stats.p; D.header = (double*)ctx->d_header.p; D.scratch = (double*)ctx->d_scratch.p;
+  b->pack.packed = (unsigned char*)ctx->d_pack.p; b->pack.blob_off = (unsigned*)ctx->d_pack_off.p;
+  b->pack.file_off = (const unsigned long long*)(dp + p_pack);
   b->hl.scalars = (double*)ctx->d_hl.p; b->hl.pitch = (double*)ctx->d_hl_pitch.p; b->hl.signature = (double*)ctx->d_hl_sig.p;
   b->hl.features = (double*)ctx->d_hl_feat.p; b->hl.status = (int*)ctx->d_hl_status.p; b->hl.silence_pad = ctx->P.t.hl_pad;
   AfxCondPlan& C = b->cond;
@@ -800,6 +820,7 @@ extern "C" int afx_batch_compute(afx_batch* b)
 #endif
   // the high-level stage reads the finished series and statistics (skipped while afx_create computes the silence pad)
   if ((feat & AFX_FEAT_HIGHLEVEL) && ctx->hl_pad_ready) { ktime_begin(b, "highlevel"); afx_launch_highlevel(ctx->P, b->dev, b->hl, ctx->stream, &b->launches); ktime_end(b); }
+  if ((feat & AFX_FEAT_PACK) && b->n_files > 0) { ktime_begin(b, "pack"); afx_launch_pack(b->dev, b->pack, ctx->stream, &b->launches); ktime_end(b); }
   CK(cudaEventRecord(b->ev[3], ctx->stream), "cudaEventRecord");
   CK(cudaGetLastError(), "kernel launch");
   b->computed = true;
@@ -824,7 +845,15 @@ static void fs_row_ranges(unsigned feat, std::vector<std::pair<int, int>>& out)
   }
 }
 
-extern "C" int afx_batch_download(afx_batch* b)
+static int batch_download(afx_batch* b, bool arrays);
+extern "C" int afx_batch_download(afx_batch* b) { return batch_download(b, true); }
+extern "C" int afx_batch_download_rows(afx_batch* b)
+{
+  if (b && !(b->ctx->cfg.features & AFX_FEAT_PACK)) return fail(b->ctx, AFX_ERR_STATE, "afx_batch_download_rows: the context was not created with AFX_FEAT_PACK");
+  return batch_download(b, false);
+}
+
+static int batch_download(afx_batch* b, bool arrays)
 {
   if (!b) return AFX_ERR_ARG;
   afx_ctx* ctx = b->ctx;
@@ -847,10 +876,18 @@ extern "C" int afx_batch_download(afx_batch* b)
   CK(cp(H + b->o_header, b->dev.header, (size_t)n * AFX_N_HEADER * 8), "D2H header");
   CK(cp(H + b->o_state, b->dev.state, (size_t)n * sizeof(AfxState)), "D2H state");
   if (feat & AFX_FEAT_STATS) CK(cp(H + b->o_stats, b->dev.stats, (size_t)n * AFX_N_SERIES * AFX_N_STATS * 8), "D2H stats");
+  b->arrays_downloaded = arrays;
   std::vector<std::pair<int, int>> rr; fs_row_ranges(feat, rr);
-  for (auto& r : rr) CK(cp(H + b->o_fs + (size_t)r.first * TF, b->dev.fs + (size_t)r.first * TF, (size_t)(r.second - r.first) * TF * 8), "D2H fs");
-  if (feat & AFX_FEAT_RHYTHM) CK(cp(H + b->o_fsr, b->dev.fsr, 2 * TFr * 8), "D2H fsr");
-  if (feat & AFX_FEAT_BANDS) CK(cp(H + b->o_fv, b->dev.fv, TF * AFX_FV_STRIDE * 8), "D2H fv");
+  if (arrays) for (auto& r : rr) CK(cp(H + b->o_fs + (size_t)r.first * TF, b->dev.fs + (size_t)r.first * TF, (size_t)(r.second - r.first) * TF * 8), "D2H fs");
+  if (arrays && (feat & AFX_FEAT_RHYTHM)) CK(cp(H + b->o_fsr, b->dev.fsr, 2 * TFr * 8), "D2H fsr");
+  if (arrays && (feat & AFX_FEAT_BANDS)) CK(cp(H + b->o_fv, b->dev.fv, TF * AFX_FV_STRIDE * 8), "D2H fv");
+  if ((feat & AFX_FEAT_PACK) && n > 0) {
+    const size_t tab = (size_t)n * (AFX_N_BLOBS + 1) * 4;
+    if (!b->h_pack.p) take_cached(b->h_pack, ctx->h_pack_cache, b->pack_bytes + tab + 64);
+    CK(b->h_pack.reserve(b->pack_bytes + tab + 64), "cudaHostAlloc(pack)");
+    CK(cp(b->h_pack.p, b->pack.packed, b->pack_bytes), "D2H pack");
+    CK(cp((unsigned char*)b->h_pack.p + b->pack_bytes, b->pack.blob_off, tab), "D2H pack offsets");
+  }
   if ((feat & AFX_FEAT_HIGHLEVEL) && ctx->hl_pad_ready) {
     CK(cp(H + b->o_hl, b->hl.scalars, (size_t)n * AFX_N_HL * 8), "D2H hl");
     CK(cp(H + b->o_hl_sig, b->hl.signature, (size_t)n * AFX_HL_SIGNATURE * 8), "D2H hl signature");
@@ -897,19 +934,25 @@ extern "C" int afx_batch_result(const afx_batch* b, int32_t i, afx_file_result* 
   const AfxState* st = reinterpret_cast<const AfxState*>(H + b->o_state) + i;
   out->n_frames = st->F; out->n_rhythm_frames = st->Fr;
   const unsigned feat = b->ctx->cfg.features;
-  std::vector<std::pair<int, int>> rr; fs_row_ranges(feat, rr);
-  const size_t TF = (size_t)b->TF, TFr = (size_t)b->TFr;
-  for (auto& r : rr) for (int s = r.first; s < r.second; ++s) out->fs[s] = H + b->o_fs + (size_t)s * TF + f.frame_off;
-  if (feat & AFX_FEAT_SPECTRAL) {   // constant-zero series (degenerate in the reference)
-    out->fs[FS_SPEC_INHARM] = out->fs[FS_TRISTIM1] = out->fs[FS_TRISTIM2] = out->fs[FS_TRISTIM3] = b->ctx->zeros.data();
-  }
-  if (feat & AFX_FEAT_RHYTHM) for (int s = 0; s < 2; ++s) out->fs[AFX_N_FS_MAIN + s] = H + b->o_fsr + (size_t)s * TFr + f.rframe_off;
-  if (feat & AFX_FEAT_BANDS) {
-    static const int offs[AFX_N_FV] = { FV_RMS, FV_FLATNESS, FV_FLUX, FV_COMPLEXITY, FV_CONTRAST, FV_BANDS28, FV_CEPSTRUM };
-    static const int nbv[AFX_N_FV] = { 14, 14, 14, 14, 14, 28, 14 };
-    for (int v = 0; v < AFX_N_FV; ++v) out->fv[v] = H + b->o_fv + (size_t)offs[v] * TF + (size_t)f.frame_off * nbv[v];
+  if ((feat & AFX_FEAT_PACK) && b->h_pack.p) {
+    out->packed = (const unsigned char*)b->h_pack.p + b->pack_file_off[i];
+    out->packed_off = reinterpret_cast<const uint32_t*>((const unsigned char*)b->h_pack.p + b->pack_bytes) + (size_t)i * (AFX_N_BLOBS + 1);
   }
   if (feat & AFX_FEAT_STATS) out->stats = H + b->o_stats + (size_t)i * AFX_N_SERIES * AFX_N_STATS;
+  if (b->arrays_downloaded) {
+    std::vector<std::pair<int, int>> rr; fs_row_ranges(feat, rr);
+    const size_t TF = (size_t)b->TF, TFr = (size_t)b->TFr;
+    for (auto& r : rr) for (int s = r.first; s < r.second; ++s) out->fs[s] = H + b->o_fs + (size_t)s * TF + f.frame_off;
+    if (feat & AFX_FEAT_SPECTRAL) {   // constant-zero series (degenerate in the reference)
+      out->fs[FS_SPEC_INHARM] = out->fs[FS_TRISTIM1] = out->fs[FS_TRISTIM2] = out->fs[FS_TRISTIM3] = b->ctx->zeros.data();
+    }
+    if (feat & AFX_FEAT_RHYTHM) for (int s = 0; s < 2; ++s) out->fs[AFX_N_FS_MAIN + s] = H + b->o_fsr + (size_t)s * TFr + f.rframe_off;
+    if (feat & AFX_FEAT_BANDS) {
+      static const int offs[AFX_N_FV] = { FV_RMS, FV_FLATNESS, FV_FLUX, FV_COMPLEXITY, FV_CONTRAST, FV_BANDS28, FV_CEPSTRUM };
+      static const int nbv[AFX_N_FV] = { 14, 14, 14, 14, 14, 28, 14 };
+      for (int v = 0; v < AFX_N_FV; ++v) out->fv[v] = H + b->o_fv + (size_t)offs[v] * TF + (size_t)f.frame_off * nbv[v];
+    }
+  }
   if ((feat & AFX_FEAT_HIGHLEVEL) && b->ctx->hl_pad_ready) {
     out->highlevel = H + b->o_hl + (size_t)i * AFX_N_HL;
     out->hl_signature = H + b->o_hl_sig + (size_t)i * AFX_HL_SIGNATURE;
@@ -930,6 +973,7 @@ extern "C" void afx_batch_free(afx_batch* b)
     std::lock_guard<std::mutex> lk(ctx->mu);
     give_back(b->h_results, ctx->h_results_cache);
     give_back(b->h_plan, ctx->h_plan_cache);
+    give_back(b->h_pack, ctx->h_pack_cache);
     if (ctx->live == b) ctx->live = nullptr;
   }
   for (int i = 0; i < 6; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);

@@ -25,6 +25,7 @@
 #define AFX_RBINS 255
 #define AFX_RROW 512        // floats per rhythm frame row: mag[0..255], dc, nyq, pad | phase[256..511]
 #define AFX_FV_STRIDE 112
+#define AFX_N_BLOBS 122      // BLOB columns of an afec-ll.db row: 24 VR + 7 x (1 VVR + 13 VR)
 #define AFX_N_HL 16
 #define AFX_HL_SIGNATURE (64 * 14)
 #define AFX_HL_FEATURES 1680
@@ -299,6 +300,14 @@ struct AfxHighLevelDev {   // outputs of k_highlevel (afx_highlevel.cu), batch-w
   int* status;              // [n_files] 1: a classification feature is NaN / Inf (the reference fails the file)
   const double* silence_pad;// [21] last-frame values of a silent sample (SampleClassificationDescriptors.cpp:330-368)
 };
+
+struct AfxPackDev {         // outputs of k_pack (afx_pack.cu)
+  unsigned char* packed;    // every file's msgpack BLOB images, file i at file_off[i]
+  const unsigned long long* file_off;   // [n_files] host-built from the frame-slot capacities
+  unsigned* blob_off;       // [n_files][AFX_N_BLOBS + 1] offsets of the blobs inside a file's region
+};
+size_t afx_pack_region_bytes(int F, int Fr);
+void afx_launch_pack(const AfxBatchDev& B, const AfxPackDev& O, cudaStream_t s, long long* launches);
 
 struct RsBlock { int out0; int nout; long long in0; long long chk_off; int span; int pad; };   // in0: source index of X[0] (may be negative); chk_off: first time checkpoint; span: X[0 .. span) covers every sample the block's filter sums read
 struct AfxCondPlan {       // device arrays built by the host for one batch

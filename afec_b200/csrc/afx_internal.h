@@ -68,10 +68,10 @@ struct afx_ctx {
   AfxParams P;
   DevBuf tables;                      // all constant tables in one allocation
   DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf, d_rpost, d_bandraw, d_slotmap,
-         d_stats, d_header, d_plan, d_scratch, d_hl, d_hl_pitch, d_hl_sig, d_hl_feat, d_hl_status;
+         d_stats, d_header, d_plan, d_scratch, d_hl, d_hl_pitch, d_hl_sig, d_hl_feat, d_hl_status, d_pack, d_pack_off, d_pack_file_off;
   bool hl_pad_ready = false;          // the silence pad table (tables: hl_pad) has been computed by afx_create
   long long group_frames = 1572864, group_rframes = 12582912;   // per-launch scratch bound: 12 GB mag, 24 GB rpolar (allocated by need). Large groups matter to the per-file kernels: 4x the files in flight took 17 % off the rhythm chain
-  PinBuf h_results_cache, h_plan_cache;   // recycled between batches
+  PinBuf h_results_cache, h_plan_cache, h_pack_cache;   // recycled between batches
   std::vector<PartBufs> part_pool;        // recycled between part jobs
   std::vector<double> zeros;          // backing store of the all-zero series
   std::string error;
@@ -113,10 +113,14 @@ struct afx_batch {
   size_t o_header = 0, o_state = 0, o_fs = 0, o_fsr = 0, o_fv = 0, o_stats = 0, total_doubles = 0;
   size_t o_hl = 0, o_hl_pitch = 0, o_hl_sig = 0, o_hl_feat = 0, o_hl_status = 0;
   AfxHighLevelDev hl;
+  // packed sink rows (AFX_FEAT_PACK): a separate pinned block; file i's region starts at pack_file_off[i]
+  std::vector<unsigned long long> pack_file_off; size_t pack_bytes = 0;
+  PinBuf h_pack;                      // [pack_bytes] blobs, then [n][AFX_N_BLOBS + 1] uint32 offsets
+  AfxPackDev pack;
   AfxBatchDev dev;
   AfxCondPlan cond;
   cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-  bool uploaded = false, computed = false, downloaded = false;
+  bool uploaded = false, computed = false, downloaded = false, arrays_downloaded = false;
   long long launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   std::vector<KernelTime> ktimes;
 };

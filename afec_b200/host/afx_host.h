@@ -57,6 +57,11 @@ public:
   // optional: group the following inserts into one transaction (content identical to one per file)
   virtual void BeginBulk() {}
   virtual void EndBulk() {}
+  // optional: rows whose BLOBs were packed on the GPU (afx_file_result.packed, AFX_FEAT_PACK): a pool that accepts them
+  // binds the bytes as they are; the default unpacks nothing and is never called
+  virtual bool AcceptsPackedSamples() const { return false; }
+  virtual void InsertPackedSample(const std::string& FileName, const std::string& FileType, const afx_file_result& Result)
+  { (void)FileName; (void)FileType; (void)Result; throw TReadableException("this pool takes no packed rows"); }
 };
 
 // afec-ll.db: schema, pragmas, msgpack BLOB encoding and status strings of the reference
@@ -79,8 +84,19 @@ public:
   void RemoveSamples(const std::vector<std::string>& FileNames);
   void BeginBulk() override;
   void EndBulk() override;
+  bool AcceptsPackedSamples() const override { return true; }
+  void InsertPackedSample(const std::string& FileName, const std::string& FileType, const afx_file_result& Result) override;
+  // journal-less filling of an EMPTY database (returns false and changes nothing otherwise); EndBulkLoad / Close restore
+  // the reference's WAL / NORMAL pragmas
+  bool BeginBulkLoad();
+  void EndBulkLoad();
+  // append the rows of other afec-ll.db files (shards written side by side); returns the number of rows taken
+  int MergeFrom(const std::vector<std::string>& ShardFiles, bool DeleteShards);
   static std::vector<std::string> ColumnNamesAndTypes();   // "name TYPE" in table order (461 entries)
 private:
+  void PrepareInsert();
+  void InsertRow(const std::string& FileName, const std::string& FileType, const double* Header, const double (*Stats)[AFX_N_STATS],
+                 const unsigned char* const* BlobPtr, const int* BlobLen);
   struct Impl;
   std::unique_ptr<Impl> mImpl;
   std::string mBasePath;
@@ -126,7 +142,7 @@ class TGpuSampleAnalyser {
 public:
   // TSampleAnalyser(SampleRate, FftFrameSize, HopFrameSize), Export/SampleAnalyser.h:33-36 (+ device list)
   TGpuSampleAnalyser(int SampleRate, int FftFrameSize, int HopFrameSize,
-                     const std::vector<int>& Devices = std::vector<int>(1, 0), int SlotsPerDevice = 3);
+                     const std::vector<int>& Devices = std::vector<int>(1, 0), int SlotsPerDevice = 3, bool PackRowsOnDevice = true);
   ~TGpuSampleAnalyser();
 
   // Export/SampleAnalyser.h:54-56: analyse one file; throws TReadableException on load / analysis failure
@@ -140,6 +156,9 @@ public:
   struct TProgress { int64_t mFiles = 0, mFailed = 0, mMainFrames = 0, mRhythmFrames = 0; double mAudioSeconds = 0, mSeconds = 0; };
   int ExtractBatch(const std::vector<std::string>& FileNames, TSampleDescriptorPool* pPool, std::mutex& PoolLock,
                    TProgress* pProgress = nullptr, const volatile bool* pAbort = nullptr) const;
+  // the same with several pools written side by side (one sink thread per pool; a chunk's rows all go to one pool)
+  int ExtractBatchSharded(const std::vector<std::string>& FileNames, const std::vector<TSampleDescriptorPool*>& Pools,
+                          const std::vector<std::mutex*>& PoolLocks, TProgress* pProgress = nullptr, const volatile bool* pAbort = nullptr) const;
 
   // Long files (BASELINE config 5): the decoded file is cut into NumParts sample-range parts (0 = one per device),
   // part p is conditioned on slot p % slots -- its own GPU when the analyser was built over several devices --
@@ -158,9 +177,13 @@ public:
   // decode threads of ExtractBatch (0 = one per slot); the reference decodes on hardware_concurrency threads (Crawler.cpp:680-681)
   void SetDecodeThreads(int Threads) { mDecodeThreads = Threads; }
 
-private:
   struct Slot;
+private:
   int mSampleRate, mFftFrameSize, mHopFrameSize;
+  bool mPackRows = true;
+  std::vector<int> mDevices;
+  mutable std::unique_ptr<Slot> mSingle;
+  Slot& SingleSlot() const;
   size_t mMaxBatchBytes = (size_t)256 << 20;
   int mMaxBatchFiles = 2048;
   int mDecodeThreads = 0;

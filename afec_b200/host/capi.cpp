@@ -4,6 +4,9 @@
 #include <chrono>
 #include <cstdio>
 #include <algorithm>
+#include <memory>
+#include <thread>
+#include <sys/stat.h>
 #include <cstdlib>
 #include <cstring>
 
@@ -137,6 +140,78 @@ double afxh_sink_bench(const char* db, int n_rows, int frames, int rframes, int 
     pool.Close();
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   } catch (const std::exception&) { return -2.0; }
+}
+
+// sink throughput with the round-2 paths: `mode` bit 0 = journal-less bulk load of the fresh database, bit 1 = rows arrive
+// packed (as afx_file_result.packed delivers them from the GPU; packed once here, outside the timed region), `shards` pools
+// written by as many threads.  Returns seconds (< 0 on error); *bytes = database bytes written.
+double afxh_sink_bench2(const char* db, int n_rows, int frames, int rframes, int bulk, int mode, int shards, long long* bytes)
+{
+  try {
+    TSampleDescriptors d;
+    d.mFileType = "wav"; d.mFrames = frames; d.mRhythmFrames = rframes;
+    for (int s = 0; s < AFX_N_FS; ++s) { const int n = s < AFX_N_FS_MAIN ? frames : rframes; d.mFramedScalars[s].resize(n); for (int i = 0; i < n; ++i) d.mFramedScalars[s][i] = 0.001 * i + s; }
+    for (int v = 0; v < AFX_N_FV; ++v) { const size_t n = (size_t)frames * kFramedVectorBands[v]; d.mFramedVectors[v].resize(n); for (size_t i = 0; i < n; ++i) d.mFramedVectors[v][i] = 1e-3 * (double)i; }
+    for (int s = 0; s < AFX_N_SERIES; ++s) for (int k = 0; k < AFX_N_STATS; ++k) d.mStats[s][k] = s + 0.01 * k;
+    // the packed image of that row
+    std::vector<unsigned char> packed, one; std::vector<uint32_t> off;
+    for (int s = 0; s < AFX_N_FS; ++s) { off.push_back((uint32_t)packed.size()); PackVR(one, d.mFramedScalars[s].data(), d.mFramedScalars[s].size()); packed.insert(packed.end(), one.begin(), one.end()); }
+    int series = AFX_N_FS;
+    for (int v = 0; v < AFX_N_FV; ++v) {
+      const int nb = kFramedVectorBands[v];
+      off.push_back((uint32_t)packed.size()); PackVVR(one, d.mFramedVectors[v].data(), (size_t)frames, (size_t)nb); packed.insert(packed.end(), one.begin(), one.end());
+      for (int k = 0; k < AFX_N_STATS; ++k) {
+        double col[28]; for (int b = 0; b < nb; ++b) col[b] = d.mStats[series + b][k];
+        off.push_back((uint32_t)packed.size()); PackVR(one, col, (size_t)nb); packed.insert(packed.end(), one.begin(), one.end());
+      }
+      series += nb;
+    }
+    off.push_back((uint32_t)packed.size());
+    afx_file_result r; memset(&r, 0, sizeof(r));
+    r.n_frames = frames; r.n_rhythm_frames = rframes; r.header = d.mHeader; r.stats = &d.mStats[0][0];
+    r.packed = packed.data(); r.packed_off = off.data();
+
+    std::vector<std::unique_ptr<TSqliteSampleDescriptorPool>> pools;
+    std::vector<std::string> names;
+    for (int k = 0; k < std::max(1, shards); ++k) {
+      names.push_back(k == 0 ? std::string(db) : std::string(db) + "." + std::to_string(k));
+      pools.emplace_back(new TSqliteSampleDescriptorPool());
+      if (!pools.back()->Open(names.back())) return -1.0;
+      if (mode & 1) pools.back()->BeginBulkLoad();
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < pools.size(); ++k) th.emplace_back([&, k]() {
+      TSqliteSampleDescriptorPool& pool = *pools[k];
+      TSampleDescriptors mine = d;
+      char name[64];
+      int in_txn = 0;
+      for (int i = (int)k; i < n_rows; i += (int)pools.size()) {
+        if (bulk > 1 && in_txn == 0) pool.BeginBulk();
+        snprintf(name, sizeof(name), "/nonexistent/f%07d.wav", i);
+        if (mode & 2) pool.InsertPackedSample(name, "wav", r);
+        else { mine.mFileName = name; pool.InsertSample(name, mine); }
+        if (bulk > 1 && ++in_txn == bulk) { pool.EndBulk(); in_txn = 0; }
+      }
+      if (in_txn) pool.EndBulk();
+      if (mode & 1) pool.EndBulkLoad();
+      pool.Close();
+    });
+    for (auto& t : th) t.join();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (bytes) { *bytes = 0; for (const auto& n : names) { struct stat st; if (stat(n.c_str(), &st) == 0) *bytes += (long long)st.st_size; } }
+    return secs;
+  } catch (const std::exception&) { return -2.0; }
+}
+
+// append shard databases to `db` (TSqliteSampleDescriptorPool::MergeFrom); returns rows merged or < 0
+int afxh_merge_shards(const char* db, const char* const* shards, int n_shards, int delete_shards)
+{
+  try {
+    TSqliteSampleDescriptorPool pool;
+    if (!pool.Open(db)) return -1;
+    return pool.MergeFrom(std::vector<std::string>(shards, shards + n_shards), delete_shards != 0);
+  } catch (const std::exception&) { return -2; }
 }
 
 // one long file through the part path (TGpuSampleAnalyser::AnalyzeInParts) into the pool

@@ -11,8 +11,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <dirent.h>
+#include <chrono>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <set>
+#include <unistd.h>
 #include <sys/stat.h>
 
 using namespace afec;
@@ -42,8 +46,8 @@ static std::string abs_path(const std::string& p)
 int main(int argc, char** argv)
 {
   std::string out_db = "afec-ll.db", level = "low";
-  int hop = 1024, slots = 2; std::vector<int> devices(1, 0); std::vector<std::string> paths;
-  bool quiet = false;
+  int hop = 1024, slots = 3, shards = 1, decode_threads = 0; std::vector<int> devices(1, 0); std::vector<std::string> paths;
+  bool quiet = false, merge = false, host_pack = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(1); } return argv[++i]; };
@@ -52,9 +56,17 @@ int main(int argc, char** argv)
     else if (a == "-j" || a == "--jobs") slots = std::max(1, atoi(next().c_str()));
     else if (a == "--hop") hop = atoi(next().c_str());
     else if (a == "--devices") { devices.clear(); std::string s = next(); size_t p = 0; while (p <= s.size()) { size_t q = s.find(',', p); if (q == std::string::npos) q = s.size(); if (q > p) devices.push_back(atoi(s.substr(p, q - p).c_str())); p = q + 1; } }
+    else if (a == "--shards") shards = std::max(1, atoi(next().c_str()));
+    else if (a == "--merge") merge = true;
+    else if (a == "--decode-threads") decode_threads = std::max(1, atoi(next().c_str()));
+    else if (a == "--host-pack") host_pack = true;
     else if (a == "-q") quiet = true;
     else if (a == "-h" || a == "--help") {
-      printf("usage: %s [-l low] [-o afec-ll.db] [-j slots-per-gpu] [--hop 1024] [--devices 0,1,..] <file-or-dir>...\n", argv[0]);
+      printf("usage: %s [-l low] [-o afec-ll.db] [-j slots-per-gpu] [--hop 1024] [--devices 0,1,..] [--decode-threads N]\n"
+             "          [--shards N [--merge]] [--host-pack] <file-or-dir>...\n"
+             "  --shards N   N sqlite writers side by side: afec-ll.db, afec-ll.db.1 .. .N-1 (each a valid afec-ll.db holding a\n"
+             "               disjoint part of the rows); --merge appends the shards to afec-ll.db afterwards and deletes them\n"
+             "  --host-pack  pack the msgpack BLOBs on the host instead of the GPU\n", argv[0]);
       return 0;
     } else if (!a.empty() && a[0] == '-') { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
     else paths.push_back(a);
@@ -97,12 +109,38 @@ int main(int argc, char** argv)
     if (!gone.empty()) pool.RemoveSamples(gone);
     if (!quiet) printf("%zu files found, %zu to analyse, %zu removed\n", files.size(), todo.size(), gone.size());
     if (todo.empty()) return 0;
-    TGpuSampleAnalyser analyser(44100, 2048, hop, devices, slots);
-    std::mutex lock; TGpuSampleAnalyser::TProgress pr;
-    const int failed = analyser.ExtractBatch(todo, &pool, lock, &pr, &sAbort);
-    if (!quiet) printf("{\"files\": %lld, \"failed\": %d, \"main_frames\": %lld, \"rhythm_frames\": %lld, \"audio_seconds\": %.3f, \"seconds\": %.4f, \"audio_hours_per_s\": %.4f}\n",
-                       (long long)pr.mFiles, failed, (long long)pr.mMainFrames, (long long)pr.mRhythmFrames, pr.mAudioSeconds, pr.mSeconds,
-                       pr.mSeconds > 0 ? pr.mAudioSeconds / 3600.0 / pr.mSeconds : 0.0);
+    TGpuSampleAnalyser analyser(44100, 2048, hop, devices, slots, !host_pack);
+    if (decode_threads) analyser.SetDecodeThreads(decode_threads);
+    // a fresh database is filled without a journal (TSqliteSampleDescriptorPool::BeginBulkLoad), shards always are fresh
+    const bool bulk_main = pool.BeginBulkLoad();
+    std::vector<std::unique_ptr<TSqliteSampleDescriptorPool>> shard_pools;
+    std::vector<std::string> shard_files;
+    std::vector<TSampleDescriptorPool*> pools(1, &pool);
+    std::vector<std::unique_ptr<std::mutex>> lock_store; std::vector<std::mutex*> locks;
+    for (int k = 1; k < shards; ++k) {
+      const std::string name = db_abs + "." + std::to_string(k);
+      unlink(name.c_str()); unlink((name + "-wal").c_str()); unlink((name + "-shm").c_str());
+      std::unique_ptr<TSqliteSampleDescriptorPool> sp(new TSqliteSampleDescriptorPool());
+      if (!sp->Open(name)) { fprintf(stderr, "failed to open shard %s\n", name.c_str()); return 1; }
+      sp->SetBasePath(pool.BasePath());
+      sp->BeginBulkLoad();
+      pools.push_back(sp.get()); shard_files.push_back(name); shard_pools.push_back(std::move(sp));
+    }
+    for (size_t k = 0; k < pools.size(); ++k) { lock_store.emplace_back(new std::mutex()); locks.push_back(lock_store.back().get()); }
+    TGpuSampleAnalyser::TProgress pr;
+    const int failed = analyser.ExtractBatchSharded(todo, pools, locks, &pr, &sAbort);
+    if (bulk_main) pool.EndBulkLoad();
+    for (auto& sp : shard_pools) sp->Close();
+    double merge_s = 0.0;
+    if (merge && !shard_files.empty()) {
+      const auto m0 = std::chrono::steady_clock::now();
+      pool.MergeFrom(shard_files, true);
+      merge_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - m0).count();
+      if (!quiet) printf("merged %zu shards in %.3f s\n", shard_files.size(), merge_s);
+    }
+    if (!quiet) printf("{\"files\": %lld, \"failed\": %d, \"main_frames\": %lld, \"rhythm_frames\": %lld, \"audio_seconds\": %.3f, \"seconds\": %.4f, \"merge_seconds\": %.4f, \"shards\": %d, \"audio_hours_per_s\": %.4f}\n",
+                       (long long)pr.mFiles, failed, (long long)pr.mMainFrames, (long long)pr.mRhythmFrames, pr.mAudioSeconds, pr.mSeconds, merge_s, shards,
+                       pr.mSeconds + merge_s > 0 ? pr.mAudioSeconds / 3600.0 / (pr.mSeconds + merge_s) : 0.0);
     return sAbort ? 2 : 0;
   } catch (const std::exception& e) {
     fprintf(stderr, "error: %s\n", e.what());

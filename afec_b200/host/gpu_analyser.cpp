@@ -33,22 +33,39 @@ struct TGpuSampleAnalyser::Slot {
   }
 };
 
+static std::unique_ptr<TGpuSampleAnalyser::Slot> make_slot(int Device, int SampleRate, int FftFrameSize, int HopFrameSize, unsigned Features);
+
 TGpuSampleAnalyser::TGpuSampleAnalyser(int SampleRate, int FftFrameSize, int HopFrameSize,
-                                       const std::vector<int>& Devices, int SlotsPerDevice)
-  : mSampleRate(SampleRate), mFftFrameSize(FftFrameSize), mHopFrameSize(HopFrameSize)
+                                       const std::vector<int>& Devices, int SlotsPerDevice, bool PackRowsOnDevice)
+  : mSampleRate(SampleRate), mFftFrameSize(FftFrameSize), mHopFrameSize(HopFrameSize), mPackRows(PackRowsOnDevice)
 {
   if (Devices.empty() || SlotsPerDevice < 1) throw TReadableException("TGpuSampleAnalyser: no devices");
-  for (int d : Devices) for (int s = 0; s < SlotsPerDevice; ++s) {
-    std::unique_ptr<Slot> slot(new Slot());
-    afx_config cfg; memset(&cfg, 0, sizeof(cfg));
-    cfg.device = d; cfg.sample_rate = SampleRate; cfg.fft_size = FftFrameSize; cfg.hop_size = HopFrameSize;
-    cfg.features = AFX_FEAT_ALL;
-    slot->device = d;
-    if (afx_create(&cfg, &slot->ctx) != AFX_OK)
-      throw TReadableException(std::string("TGpuSampleAnalyser: ") + afx_last_error(nullptr));
-    mSlots.push_back(std::move(slot));
-  }
+  // ring slots: with PackRowsOnDevice their contexts also pack every row's msgpack BLOBs on the GPU (the batched
+  // extractor then downloads rows, not arrays); slot order is device-major
+  for (int d : Devices) for (int s = 0; s < SlotsPerDevice; ++s)
+    mSlots.push_back(make_slot(d, SampleRate, FftFrameSize, HopFrameSize, AFX_FEAT_ALL | (PackRowsOnDevice ? AFX_FEAT_PACK : 0u)));
   mNumDevices = (int)Devices.size();
+  mDevices = Devices;
+}
+
+std::unique_ptr<TGpuSampleAnalyser::Slot> make_slot(int Device, int SampleRate, int FftFrameSize, int HopFrameSize, unsigned Features)
+{
+  std::unique_ptr<TGpuSampleAnalyser::Slot> slot(new TGpuSampleAnalyser::Slot());
+  afx_config cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.device = Device; cfg.sample_rate = SampleRate; cfg.fft_size = FftFrameSize; cfg.hop_size = HopFrameSize;
+  cfg.features = Features;
+  slot->device = Device;
+  if (afx_create(&cfg, &slot->ctx) != AFX_OK)
+    throw TReadableException(std::string("TGpuSampleAnalyser: ") + afx_last_error(nullptr));
+  return slot;
+}
+
+// the single-file entry points (Analyze / Extract / the last step of AnalyzeInParts) return descriptor ARRAYS: they run
+// on their own context, created on first use
+TGpuSampleAnalyser::Slot& TGpuSampleAnalyser::SingleSlot() const
+{
+  if (!mSingle) mSingle = make_slot(mDevices[0], mSampleRate, mFftFrameSize, mHopFrameSize, AFX_FEAT_ALL);
+  return *mSingle;
 }
 
 TGpuSampleAnalyser::~TGpuSampleAnalyser() {}
@@ -116,7 +133,7 @@ TSampleDescriptors TGpuSampleAnalyser::AnalyzeDecodedInParts(const std::string& 
   for (int p = 0; p < n_parts; ++p)
     if (afx_part_effective(jobs[p], &g, &sums[p]) != AFX_OK) throw TReadableException(afx_last_error(slots[(size_t)p % slots.size()]->ctx));
   g = combine();
-  Slot& S0 = *slots[0];
+  Slot& S0 = SingleSlot();
   int64_t begin = 0, count = 0;
   afx_part_window(S0.ctx, &whole, &g, &begin, &count);
   std::vector<float> window((size_t)std::max<int64_t>(count, 1), 0.0f);
@@ -140,7 +157,7 @@ TSampleDescriptors TGpuSampleAnalyser::Analyze(const std::string& FileName) cons
   ReadAudioFile(FileName, audio);               // throws with the loader's message
   if (mNumDevices > 1 && mLongFileBytes && audio.mBytes.size() >= mLongFileBytes) return AnalyzeDecodedInParts(FileName, audio, 0);
   std::lock_guard<std::mutex> lock(mSingleLock);
-  Slot& S = *mSlots[0];
+  Slot& S = SingleSlot();
   afx_file f; describe(audio, audio.mBytes.data(), f);
   afx_batch* b = nullptr;
   if (afx_analyze(S.ctx, &f, 1, &b) != AFX_OK) throw TReadableException(afx_last_error(S.ctx));
@@ -178,7 +195,7 @@ void TGpuSampleAnalyser::Extract(const std::string& FileName, TSampleDescriptorP
       return;
     }
     std::lock_guard<std::mutex> lock(mSingleLock);
-    Slot& S = *mSlots[0];
+    Slot& S = SingleSlot();
     afx_file f; describe(audio, audio.mBytes.data(), f);
     afx_batch* b = nullptr;
     if (afx_analyze(S.ctx, &f, 1, &b) != AFX_OK) throw TReadableException(afx_last_error(S.ctx));
@@ -209,6 +226,17 @@ void TGpuSampleAnalyser::Extract(const std::string& FileName, TSampleDescriptorP
 int TGpuSampleAnalyser::ExtractBatch(const std::vector<std::string>& FileNames, TSampleDescriptorPool* pPool,
                                      std::mutex& PoolLock, TProgress* pProgress, const volatile bool* pAbort) const
 {
+  std::vector<TSampleDescriptorPool*> pools(1, pPool);
+  std::vector<std::mutex*> locks(1, &PoolLock);
+  return ExtractBatchSharded(FileNames, pools, locks, pProgress, pAbort);
+}
+
+// One sink thread per pool: every finished chunk goes to the pool whose sink thread takes it first, so N pools (N
+// afec-ll.db shard files, merged or attached afterwards) are written side by side -- one sqlite writer moves 0.3-0.7 GB/s.
+int TGpuSampleAnalyser::ExtractBatchSharded(const std::vector<std::string>& FileNames, const std::vector<TSampleDescriptorPool*>& Pools,
+                                            const std::vector<std::mutex*>& PoolLocks, TProgress* pProgress, const volatile bool* pAbort) const
+{
+  if (Pools.empty() || Pools.size() != PoolLocks.size()) throw TReadableException("ExtractBatchSharded: one lock per pool");
   const auto t0 = std::chrono::steady_clock::now();
   // chunks by file size on disk (an upper bound of the raw PCM bytes)
   struct Chunk { size_t first, count; };
@@ -243,7 +271,8 @@ int TGpuSampleAnalyser::ExtractBatch(const std::vector<std::string>& FileNames, 
   std::atomic<size_t> next(0);
   int decoders_left = 0, workers_left = (int)S;
   std::atomic<long long> failed(0), frames(0), rframes(0), files(0);
-  double audio_s = 0.0;
+  std::mutex stat_mu; double audio_s = 0.0;
+  int sinks_left = (int)Pools.size(); (void)sinks_left;
   auto aborted = [&]() { return pAbort && *pAbort; };
 
   auto decoder = [&]() {
@@ -300,9 +329,16 @@ int TGpuSampleAnalyser::ExtractBatch(const std::vector<std::string>& FileNames, 
         cv.wait(lk, [&]() { return W.state == kReady || (decoders_left == 0 && W.state == kFree); });
         if (W.state != kReady) break;
       }
-      if (W.batch_error.empty() && !W.descr.empty() &&
-          afx_analyze(Sl->ctx, W.descr.data(), (int32_t)W.descr.size(), &W.batch) != AFX_OK)
-        W.batch_error = afx_last_error(Sl->ctx);      // a CUDA failure fails this chunk's files only
+      if (W.batch_error.empty() && !W.descr.empty()) {
+        // rows packed on the device come back without the framed arrays (afx_batch_download_rows)
+        bool ok = afx_batch_create(Sl->ctx, W.descr.data(), (int32_t)W.descr.size(), &W.batch) == AFX_OK;
+        ok = ok && afx_batch_upload(W.batch) == AFX_OK && afx_batch_compute(W.batch) == AFX_OK &&
+             (mPackRows ? afx_batch_download_rows(W.batch) : afx_batch_download(W.batch)) == AFX_OK && afx_batch_sync(W.batch) == AFX_OK;
+        if (!ok) {                                    // a CUDA failure fails this chunk's files only
+          W.batch_error = afx_last_error(Sl->ctx);
+          if (W.batch) { afx_batch_free(W.batch); W.batch = nullptr; }
+        }
+      }
       { std::lock_guard<std::mutex> lk(mu); W.state = kDone; done_order.push_back(si); }
       cv.notify_all();
     }
@@ -310,7 +346,10 @@ int TGpuSampleAnalyser::ExtractBatch(const std::vector<std::string>& FileNames, 
     cv.notify_all();
   };
 
-  auto sink = [&]() {
+  auto sink = [&](size_t pi) {
+    TSampleDescriptorPool* pPool = Pools[pi];
+    std::mutex& PoolLock = *PoolLocks[pi];
+    const bool packed = mPackRows && pPool->AcceptsPackedSamples();
     TSampleDescriptors results;
     for (;;) {
       size_t si;
@@ -339,16 +378,22 @@ int TGpuSampleAnalyser::ExtractBatch(const std::vector<std::string>& FileNames, 
             const std::lock_guard<std::mutex> lock(PoolLock);
             pPool->InsertFailedSample(name, std::string("Sample failed to load: ") + file_status_message(r.status)); ++failed; continue;
           }
-          results.mFileName = name; results.mFileType = ExtractFileExtension(name);
-          results.Assign(r);                   // outside the lock: only the insert itself is serialised
-          { const std::lock_guard<std::mutex> lock(PoolLock); pPool->InsertSample(name, results); }
+          if (packed) {                        // the BLOBs were packed on the GPU: bind them as they are
+            const std::lock_guard<std::mutex> lock(PoolLock); pPool->InsertPackedSample(name, ExtractFileExtension(name), r);
+          } else if (!r.fs[0]) {
+            throw TReadableException("the pool takes no packed rows: build the analyser with PackRowsOnDevice = false");
+          } else {
+            results.mFileName = name; results.mFileType = ExtractFileExtension(name);
+            results.Assign(r);                 // outside the lock: only the insert itself is serialised
+            const std::lock_guard<std::mutex> lock(PoolLock); pPool->InsertSample(name, results);
+          }
           frames += r.n_frames; rframes += r.n_rhythm_frames; ++files;
-          chunk_audio += results.mHeader[1];
+          chunk_audio += r.header[1];
         } catch (const std::exception&) { ++failed; }
       }
       { const std::lock_guard<std::mutex> lock(PoolLock); pPool->EndBulk(); }
       if (W.batch) { afx_batch_free(W.batch); W.batch = nullptr; }
-      audio_s += chunk_audio;
+      { std::lock_guard<std::mutex> sl(stat_mu); audio_s += chunk_audio; }
       { std::lock_guard<std::mutex> lk(mu); W.state = kFree; }
       cv.notify_all();
     }
@@ -359,7 +404,7 @@ int TGpuSampleAnalyser::ExtractBatch(const std::vector<std::string>& FileNames, 
   std::vector<std::thread> threads;
   for (int d = 0; d < n_dec; ++d) threads.emplace_back(decoder);
   for (size_t si = 0; si < S; ++si) threads.emplace_back(gpu_worker, si);
-  threads.emplace_back(sink);
+  for (size_t pi = 0; pi < Pools.size(); ++pi) threads.emplace_back(sink, pi);
   for (auto& t : threads) t.join();
   if (pProgress) {
     pProgress->mFiles = files; pProgress->mFailed = failed; pProgress->mMainFrames = frames; pProgress->mRhythmFrames = rframes;

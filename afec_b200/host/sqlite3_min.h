@@ -20,6 +20,7 @@ typedef void (*sqlite3_destructor_type)(void*);
 #define SQLITE_TRANSIENT ((sqlite3_destructor_type)-1)
 int sqlite3_open_v2(const char* filename, sqlite3** db, int flags, const char* vfs);
 int sqlite3_close(sqlite3*);
+int sqlite3_changes(sqlite3*);
 int sqlite3_busy_timeout(sqlite3*, int ms);
 int sqlite3_exec(sqlite3*, const char* sql, int (*cb)(void*, int, char**, char**), void*, char** errmsg);
 void sqlite3_free(void*);

@@ -21,8 +21,8 @@ struct TSqliteSampleDescriptorPool::Impl {
   sqlite3_stmt* insert_failed = nullptr;
   std::string file;
   int bulk = 0;
+  bool bulk_load = false;
   std::vector<unsigned char> blob;    // one row's msgpack blobs, back to back (bound SQLITE_STATIC until the step)
-  std::vector<std::pair<int, std::pair<size_t, size_t>>> blob_binds;   // parameter index -> (offset, size) in blob
 };
 
 static void check(sqlite3* db, int rc, const char* what)
@@ -77,6 +77,7 @@ void TSqliteSampleDescriptorPool::Close()
   Impl& I = *mImpl;
   if (!I.db) return;
   if (I.bulk) { try { exec(I.db, "COMMIT"); } catch (...) {} I.bulk = 0; }
+  if (I.bulk_load) { try { EndBulkLoad(); } catch (...) {} }
   if (I.insert) sqlite3_finalize(I.insert);
   if (I.insert_failed) sqlite3_finalize(I.insert_failed);
   I.insert = I.insert_failed = nullptr;
@@ -191,88 +192,158 @@ static inline void put_doubles(std::vector<unsigned char>& out, const double* v,
   }
 }
 
-void TSqliteSampleDescriptorPool::InsertSample(const std::string& FileName, const TSampleDescriptors& R)
+// One row.  `blobs` (AFX_N_BLOBS pointers + sizes, column order) stay valid until the statement has been stepped: they are
+// bound SQLITE_STATIC, so a row packed on the GPU goes from the pinned download buffer into sqlite's pages with no copy
+// in between.
+static void insert_row(sqlite3* db, sqlite3_stmt* st, const std::string& rel, int modtime, const std::string& file_type,
+                       const double* header, const double (*stats)[AFX_N_STATS], const unsigned char* const* blob_ptr, const int* blob_len)
+{
+  int p = 1, blob = 0;
+  sqlite3_bind_text(st, p++, rel.c_str(), -1, SQLITE_TRANSIENT);
+  sqlite3_bind_int(st, p++, modtime);
+  sqlite3_bind_text(st, p++, "succeeded", -1, SQLITE_STATIC);
+  sqlite3_bind_text(st, p++, file_type.c_str(), -1, SQLITE_TRANSIENT);
+  sqlite3_bind_int(st, p++, (int)header[0]);        // file_size
+  sqlite3_bind_double(st, p++, header[1]);          // file_length
+  sqlite3_bind_int(st, p++, (int)header[2]);
+  sqlite3_bind_int(st, p++, (int)header[3]);
+  sqlite3_bind_int(st, p++, (int)header[4]);
+  for (int k = 5; k < 9; ++k) sqlite3_bind_double(st, p++, header[k]);
+  auto framed = [&](int s) {
+    sqlite3_bind_blob(st, p++, blob_ptr[blob], blob_len[blob], SQLITE_STATIC); ++blob;
+    for (int k = 0; k < AFX_N_STATS; ++k) sqlite3_bind_double(st, p++, stats[s][k]);
+  };
+  for (int s = 0; s < AFX_N_FS_MAIN; ++s) framed(s);
+  for (int t = 0; t < 2; ++t) {
+    framed(AFX_N_FS_MAIN + t);
+    for (int k = 0; k < 6; ++k) sqlite3_bind_double(st, p++, header[9 + 6 * t + k]);
+  }
+  sqlite3_bind_double(st, p++, header[21]); sqlite3_bind_double(st, p++, header[22]);
+  for (int v = 0; v < AFX_N_FV; ++v)
+    for (int k = 0; k < 1 + AFX_N_STATS; ++k) { sqlite3_bind_blob(st, p++, blob_ptr[blob], blob_len[blob], SQLITE_STATIC); ++blob; }
+  const int rc = sqlite3_step(st);
+  sqlite3_reset(st); sqlite3_clear_bindings(st);
+  check(db, rc, "insert");
+}
+
+void TSqliteSampleDescriptorPool::PrepareInsert()
 {
   Impl& I = *mImpl;
   if (!I.db) throw TReadableException("Database is not open");
-  if (!I.insert) {
-    const std::vector<std::string> cols = ColumnNamesAndTypes();
-    std::string sql = "INSERT OR REPLACE into assets(", q;
-    for (size_t i = 0; i < cols.size(); ++i) {
-      if (i) { sql += ","; q += ","; }
-      sql += cols[i].substr(0, cols[i].find(' ')); q += "?";
-    }
-    sql += ") values(" + q + ")";
-    check(I.db, sqlite3_prepare_v2(I.db, sql.c_str(), -1, &I.insert, nullptr), "prepare insert");
+  if (I.insert) return;
+  const std::vector<std::string> cols = ColumnNamesAndTypes();
+  std::string sql = "INSERT OR REPLACE into assets(", q;
+  for (size_t i = 0; i < cols.size(); ++i) {
+    if (i) { sql += ","; q += ","; }
+    sql += cols[i].substr(0, cols[i].find(' ')); q += "?";
   }
-  sqlite3_stmt* st = I.insert;
-  const std::string rel = RelativeFilenamePath(FileName);
+  sql += ") values(" + q + ")";
+  check(I.db, sqlite3_prepare_v2(I.db, sql.c_str(), -1, &I.insert, nullptr), "prepare insert");
+}
+
+void TSqliteSampleDescriptorPool::InsertRow(const std::string& FileName, const std::string& FileType, const double* Header,
+                                            const double (*Stats)[AFX_N_STATS], const unsigned char* const* BlobPtr, const int* BlobLen)
+{
+  Impl& I = *mImpl;
+  PrepareInsert();
   const bool own_txn = (I.bulk == 0);
   if (own_txn) exec(I.db, "BEGIN");
   try {
-    // All BLOBs of the row are packed back to back into one buffer and bound without a copy (SQLITE_STATIC is
-    // valid until the statement is stepped); the buffer may move while it grows, so the binds happen at the end.
-    I.blob.clear(); I.blob_binds.clear();
-    size_t want = 64;
-    for (int s = 0; s < AFX_N_FS; ++s) want += 5 + 9 * R.mFramedScalars[s].size();
-    for (int v = 0; v < AFX_N_FV; ++v) want += 5 + (size_t)R.mFrames * (3 + 9 * (size_t)kFramedVectorBands[v]) + AFX_N_STATS * (5 + 9 * (size_t)kFramedVectorBands[v]);
-    I.blob.reserve(want);
-    auto blob_begin = [&]() { return I.blob.size(); };
-    auto blob_end = [&](int param, size_t o) { I.blob_binds.push_back({ param, { o, I.blob.size() - o } }); };
-    int p = 1;
-    sqlite3_bind_text(st, p++, rel.c_str(), -1, SQLITE_TRANSIENT);
-    sqlite3_bind_int(st, p++, ModificationStatTime(FileName));
-    sqlite3_bind_text(st, p++, "succeeded", -1, SQLITE_STATIC);
-    sqlite3_bind_text(st, p++, R.mFileType.c_str(), -1, SQLITE_TRANSIENT);
-    sqlite3_bind_int(st, p++, (int)R.mHeader[0]);        // file_size
-    sqlite3_bind_double(st, p++, R.mHeader[1]);          // file_length
-    sqlite3_bind_int(st, p++, (int)R.mHeader[2]);
-    sqlite3_bind_int(st, p++, (int)R.mHeader[3]);
-    sqlite3_bind_int(st, p++, (int)R.mHeader[4]);
-    for (int k = 5; k < 9; ++k) sqlite3_bind_double(st, p++, R.mHeader[k]);
-    auto framed = [&](int s) {
-      const size_t o = blob_begin();
-      put_array_header(I.blob, R.mFramedScalars[s].size());
-      put_doubles(I.blob, R.mFramedScalars[s].data(), R.mFramedScalars[s].size());
-      blob_end(p++, o);
-      for (int k = 0; k < AFX_N_STATS; ++k) sqlite3_bind_double(st, p++, R.mStats[s][k]);
-    };
-    for (int s = 0; s < AFX_N_FS_MAIN; ++s) framed(s);
-    for (int t = 0; t < 2; ++t) {
-      framed(AFX_N_FS_MAIN + t);
-      for (int k = 0; k < 6; ++k) sqlite3_bind_double(st, p++, R.mHeader[9 + 6 * t + k]);
-    }
-    sqlite3_bind_double(st, p++, R.mHeader[21]); sqlite3_bind_double(st, p++, R.mHeader[22]);
-    int series = AFX_N_FS;
-    for (int v = 0; v < AFX_N_FV; ++v) {
-      const int nb = kFramedVectorBands[v];
-      {
-        const size_t o = blob_begin();
-        put_array_header(I.blob, (size_t)R.mFrames);
-        for (size_t f = 0; f < (size_t)R.mFrames; ++f) { put_array_header(I.blob, (size_t)nb); put_doubles(I.blob, R.mFramedVectors[v].data() + f * nb, (size_t)nb); }
-        blob_end(p++, o);
-      }
-      double col[28];
-      for (int k = 0; k < AFX_N_STATS; ++k) {
-        for (int b = 0; b < nb; ++b) col[b] = R.mStats[series + b][k];
-        const size_t o = blob_begin();
-        put_array_header(I.blob, (size_t)nb);
-        put_doubles(I.blob, col, (size_t)nb);
-        blob_end(p++, o);
-      }
-      series += nb;
-    }
-    for (const auto& bb : I.blob_binds)
-      sqlite3_bind_blob(st, bb.first, I.blob.data() + bb.second.first, (int)bb.second.second, SQLITE_STATIC);
-    const int rc = sqlite3_step(st);
-    sqlite3_reset(st); sqlite3_clear_bindings(st);
-    check(I.db, rc, "insert");
+    insert_row(I.db, I.insert, RelativeFilenamePath(FileName), ModificationStatTime(FileName), FileType, Header, Stats, BlobPtr, BlobLen);
     if (own_txn) exec(I.db, "COMMIT");
   } catch (...) {
-    sqlite3_reset(st); sqlite3_clear_bindings(st);
+    sqlite3_reset(I.insert); sqlite3_clear_bindings(I.insert);
     if (own_txn) { try { exec(I.db, "ROLLBACK"); } catch (...) {} }
     throw;
   }
+}
+
+void TSqliteSampleDescriptorPool::InsertSample(const std::string& FileName, const TSampleDescriptors& R)
+{
+  Impl& I = *mImpl;
+  // All BLOBs of the row are packed back to back into one buffer (the buffer may move while it grows, so the pointers
+  // are taken at the end); column order as ColumnNamesAndTypes()
+  I.blob.clear();
+  size_t want = 64;
+  for (int s = 0; s < AFX_N_FS; ++s) want += 5 + 9 * R.mFramedScalars[s].size();
+  for (int v = 0; v < AFX_N_FV; ++v) want += 5 + (size_t)R.mFrames * (3 + 9 * (size_t)kFramedVectorBands[v]) + AFX_N_STATS * (5 + 9 * (size_t)kFramedVectorBands[v]);
+  I.blob.reserve(want);
+  size_t off[AFX_N_BLOBS + 1]; int nb_ = 0;
+  for (int s = 0; s < AFX_N_FS; ++s) {
+    off[nb_++] = I.blob.size();
+    put_array_header(I.blob, R.mFramedScalars[s].size());
+    put_doubles(I.blob, R.mFramedScalars[s].data(), R.mFramedScalars[s].size());
+  }
+  int series = AFX_N_FS;
+  for (int v = 0; v < AFX_N_FV; ++v) {
+    const int nb = kFramedVectorBands[v];
+    off[nb_++] = I.blob.size();
+    put_array_header(I.blob, (size_t)R.mFrames);
+    for (size_t f = 0; f < (size_t)R.mFrames; ++f) { put_array_header(I.blob, (size_t)nb); put_doubles(I.blob, R.mFramedVectors[v].data() + f * nb, (size_t)nb); }
+    double col[28];
+    for (int k = 0; k < AFX_N_STATS; ++k) {
+      for (int b = 0; b < nb; ++b) col[b] = R.mStats[series + b][k];
+      off[nb_++] = I.blob.size();
+      put_array_header(I.blob, (size_t)nb);
+      put_doubles(I.blob, col, (size_t)nb);
+    }
+    series += nb;
+  }
+  off[nb_] = I.blob.size();
+  const unsigned char* ptr[AFX_N_BLOBS]; int len[AFX_N_BLOBS];
+  for (int k = 0; k < AFX_N_BLOBS; ++k) { ptr[k] = I.blob.data() + off[k]; len[k] = (int)(off[k + 1] - off[k]); }
+  InsertRow(FileName, R.mFileType, R.mHeader, R.mStats, ptr, len);
+}
+
+void TSqliteSampleDescriptorPool::InsertPackedSample(const std::string& FileName, const std::string& FileType, const afx_file_result& R)
+{
+  if (!R.packed || !R.packed_off || !R.header || !R.stats) throw TReadableException("InsertPackedSample: the result holds no packed row (AFX_FEAT_PACK)");
+  const unsigned char* ptr[AFX_N_BLOBS]; int len[AFX_N_BLOBS];
+  for (int k = 0; k < AFX_N_BLOBS; ++k) { ptr[k] = R.packed + R.packed_off[k]; len[k] = (int)(R.packed_off[k + 1] - R.packed_off[k]); }
+  InsertRow(FileName, FileType, R.header, reinterpret_cast<const double (*)[AFX_N_STATS]>(R.stats), ptr, len);
+}
+
+// A fresh database can be filled without a journal: nothing exists that a crash could damage (the crawl starts over), and
+// sqlite then writes every page once instead of twice (WAL frame + checkpoint).  The file is switched to the reference's
+// journal_mode = WAL / synchronous = NORMAL again when the load ends, so the finished afec-ll.db has the same header
+// pragmas as one written row by row.
+bool TSqliteSampleDescriptorPool::BeginBulkLoad()
+{
+  Impl& I = *mImpl;
+  if (!I.db || I.bulk_load || I.bulk || NumberOfSamples() != 0) return false;
+  exec(I.db, "PRAGMA journal_mode = OFF;");
+  exec(I.db, "PRAGMA synchronous = OFF;");
+  I.bulk_load = true;
+  return true;
+}
+void TSqliteSampleDescriptorPool::EndBulkLoad()
+{
+  Impl& I = *mImpl;
+  if (!I.db || !I.bulk_load) return;
+  if (I.bulk) { exec(I.db, "COMMIT"); I.bulk = 0; }
+  exec(I.db, "PRAGMA journal_mode = WAL;");
+  exec(I.db, "PRAGMA synchronous = NORMAL;");
+  I.bulk_load = false;
+}
+
+// Rows of other afec-ll.db files (written side by side by several sink threads) are appended to this one
+int TSqliteSampleDescriptorPool::MergeFrom(const std::vector<std::string>& ShardFiles, bool DeleteShards)
+{
+  Impl& I = *mImpl;
+  if (!I.db) throw TReadableException("Database is not open");
+  int merged = 0;
+  for (size_t k = 0; k < ShardFiles.size(); ++k) {
+    const std::string alias = "shard" + std::to_string(k);
+    std::string quoted = ShardFiles[k]; for (size_t q = 0; (q = quoted.find('\'', q)) != std::string::npos; q += 2) quoted.insert(q, "'");
+    exec(I.db, "ATTACH DATABASE '" + quoted + "' AS " + alias);
+    exec(I.db, "BEGIN");
+    exec(I.db, "INSERT OR REPLACE INTO main.assets SELECT * FROM " + alias + ".assets");
+    merged += sqlite3_changes(I.db);
+    exec(I.db, "COMMIT");
+    exec(I.db, "DETACH DATABASE " + alias);
+    if (DeleteShards) { unlink(ShardFiles[k].c_str()); unlink((ShardFiles[k] + "-wal").c_str()); unlink((ShardFiles[k] + "-shm").c_str()); }
+  }
+  return merged;
 }
 
 void TSqliteSampleDescriptorPool::InsertFailedSample(const std::string& FileName, const std::string& Reason)

@@ -78,6 +78,11 @@ int afx_pcm_bytes(int32_t format);
  * SampleAnalyser.cpp:1232-1606) and the classification feature vector the LightGBM models take
  * (SampleClassificationDescriptors.cpp:404-560).  Model evaluation itself stays on the host. */
 #define AFX_FEAT_HIGHLEVEL (1u << 8)
+/* The sink's BLOB images packed on the GPU: every VR / VVR column of an afec-ll.db row as the msgpack bytes the reference
+ * stores (SqliteSampleDescriptorPool.cpp:601-713, 890-954), in column order, ready to bind (afx_file_result.packed).
+ * afx_batch_download_rows() then copies back only what a sink needs -- the packed rows, headers and statistics -- and
+ * leaves the framed arrays on the device (fs / fv stay NULL). */
+#define AFX_FEAT_PACK (1u << 9)
 
 typedef struct afx_ctx afx_ctx;
 typedef struct afx_batch afx_batch;
@@ -110,6 +115,8 @@ typedef struct afx_file {
 #define AFX_N_FV 7           /* framed vectors: 5 x 14 sub-bands, 28 frequency bands, 14 cepstrum bands */
 #define AFX_N_STATS 13
 #define AFX_N_SERIES 136     /* 24 + 5*14 + 28 + 14 */
+#define AFX_N_BLOBS 122      /* BLOB columns of a row: 22 framed scalars + 2 onset series (VR), then per framed vector its VVR and its
+                                13 per-band statistic VRs -- the order of the table's columns (SqliteSampleDescriptorPool.cpp:1313-1350) */
 #define AFX_N_HL 16          /* base_note, base_note_confidence, peak_db, rms_db, bpm, bpm_confidence, brightness, noisiness,
                                 harmonicity, spectral_flatness, spectral_flux, spectral_complexity, spectral_contrast,
                                 spectral_inharmonicity, pitch_confidence, reserved (names: afec_b200/layout.py HL_SCALARS) */
@@ -132,6 +139,9 @@ typedef struct afx_file_result {
   const double* hl_pitch;    /* [n_frames] MIDI notes ("pitch"); "peak" is fs[1] (amplitude_peak), SampleAnalyser.cpp:1609 */
   const double* hl_signature;/* [AFX_HL_SIGNATURE_FRAMES][AFX_HL_SIGNATURE_BANDS] */
   const double* hl_features; /* [AFX_HL_FEATURES] */
+  /* AFX_FEAT_PACK only (NULL otherwise) */
+  const unsigned char* packed;   /* the row's AFX_N_BLOBS msgpack blobs back to back */
+  const uint32_t* packed_off;    /* [AFX_N_BLOBS + 1] byte offsets into packed: blob k = [packed_off[k], packed_off[k + 1]) */
 } afx_file_result;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -160,6 +170,7 @@ int afx_batch_create(afx_ctx* ctx, const afx_file* files, int32_t n_files, afx_b
 int afx_batch_upload(afx_batch* b);     /* host -> device copies of the PCM + file table */
 int afx_batch_compute(afx_batch* b);    /* all kernels of the configured feature set */
 int afx_batch_download(afx_batch* b);   /* device -> pinned host copies of every result array */
+int afx_batch_download_rows(afx_batch* b);  /* AFX_FEAT_PACK: packed rows + headers + statistics only (instead of afx_batch_download) */
 int afx_batch_sync(afx_batch* b);       /* wait for everything issued so far */
 int afx_analyze(afx_ctx* ctx, const afx_file* files, int32_t n_files, afx_batch** out); /* all of the above */
 int afx_batch_result(const afx_batch* b, int32_t file_index, afx_file_result* out);

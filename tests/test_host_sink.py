@@ -127,3 +127,48 @@ def test_sink_throughput_hook_writes_readable_rows(host, tmp_path):
     assert len(cen) == 128 and len(ons) == 1030 and len(cep) == 128 and len(cep[0]) == 14 and len(fbm) == 28
     assert con.execute("PRAGMA user_version").fetchone()[0] == 2
     con.close()
+
+
+def _dump_table(path):
+    con = sqlite3.connect(path)
+    rows = {r[0]: r for r in con.execute("SELECT * FROM assets")}
+    pragmas = {k: con.execute("pragma " + k).fetchone()[0] for k in ("user_version", "encoding", "journal_mode")}
+    con.close()
+    return rows, pragmas
+
+
+def test_packed_rows_bulk_load_and_shards_write_the_same_bytes(host, tmp_path):
+    """The round-2 sink paths -- rows whose BLOBs arrive packed (as the GPU delivers them), journal-less bulk load of a
+    fresh database, several shard writers + merge -- all end in a database whose every column of every row equals the
+    row-by-row WAL path byte for byte, with the reference's pragmas in the file header."""
+    host.afxh_sink_bench2.restype = C.c_double
+    host.afxh_sink_bench2.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    host.afxh_merge_shards.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int]
+    n, F, Fr = 23, 40, 330
+    base = str(tmp_path / "plain.db")
+    assert host.afxh_sink_bench2(base.encode(), n, F, Fr, 1, 0, 1, None) > 0          # one transaction per row, WAL, host packing
+    want, pragmas = _dump_table(base)
+    assert len(want) == n and pragmas == {"user_version": 2, "encoding": "UTF-8", "journal_mode": "wal"}
+    for tag, mode, shards in (("packed", 2, 1), ("bulk", 1, 1), ("packed_bulk", 3, 1), ("sharded", 3, 3)):
+        db = str(tmp_path / (tag + ".db"))
+        assert host.afxh_sink_bench2(db.encode(), n, F, Fr, 7, mode, shards, None) > 0
+        if shards > 1:
+            names = [(db + ".%d" % k).encode() for k in range(1, shards)]
+            parts = [len(_dump_table(x.decode())[0]) for x in names] + [len(_dump_table(db)[0])]
+            assert sum(parts) == n and min(parts) > 0                                 # disjoint shards, each a valid afec-ll.db
+            assert host.afxh_merge_shards(db.encode(), (C.c_char_p * len(names))(*names), len(names), 1) == n - parts[-1]
+            assert not any(os.path.exists(x.decode()) for x in names)
+        got, pr = _dump_table(db)
+        assert pr == pragmas, tag
+        assert got == want, tag
+
+
+def test_bulk_load_only_touches_an_empty_database(host, tmp_path):
+    host.afxh_sink_bench2.restype = C.c_double
+    host.afxh_sink_bench2.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    db = str(tmp_path / "twice.db")
+    assert host.afxh_sink_bench2(db.encode(), 5, 10, 80, 2, 3, 1, None) > 0
+    # a second run into the now non-empty database: BeginBulkLoad declines, rows are replaced through the WAL path
+    assert host.afxh_sink_bench2(db.encode(), 5, 10, 80, 2, 3, 1, None) > 0
+    rows, pragmas = _dump_table(db)
+    assert len(rows) == 5 and pragmas["journal_mode"] == "wal"
