@@ -816,7 +816,7 @@ extern "C" int afx_batch_compute(afx_batch* b)
     for (int i = 0; i < 3; ++i) { CK(cudaEventRecord(ctx->ev_join[i], ctx->side[i]), "cudaEventRecord"); CK(cudaStreamWaitEvent(s_main, ctx->ev_join[i], 0), "cudaStreamWaitEvent"); }
   }
 #ifdef AFX_HAVE_STATS
-  if (feat & AFX_FEAT_STATS) { ktime_begin(b, "stats"); afx_launch_stats(ctx->P, b->dev, ctx->stream, &b->launches); ktime_end(b); }
+  if (feat & AFX_FEAT_STATS) { ktime_begin(b, "stats"); afx_launch_stats(ctx->P, b->dev, feat, ctx->stream, &b->launches); ktime_end(b); }
 #endif
   // the high-level stage reads the finished series and statistics (skipped while afx_create computes the silence pad)
   if ((feat & AFX_FEAT_HIGHLEVEL) && ctx->hl_pad_ready) { ktime_begin(b, "highlevel"); afx_launch_highlevel(ctx->P, b->dev, b->hl, ctx->stream, &b->launches); ktime_end(b); }

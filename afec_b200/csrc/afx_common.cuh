@@ -328,5 +328,5 @@ void afx_launch_bands(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, 
 void afx_launch_pitch(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
 void afx_launch_autocorr(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
 void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
-void afx_launch_stats(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches);
+void afx_launch_stats(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, long long* launches);
 void afx_launch_highlevel(const AfxParams& P, const AfxBatchDev& B, const AfxHighLevelDev& O, cudaStream_t s, long long* launches);

@@ -78,9 +78,11 @@ struct afx_ctx {
   bool debug_times = false;
   std::mutex mu;
   int max_frame_cap = 0;
-  // launch groups with at least this many files run the fused rhythm front end (one CTA per file); smaller groups cannot
-  // fill the GPU that way and take the split kernels.  AFX_RHYTHM_FUSED=0 / 1 forces never / always (parity tests compare the two)
-  int rhythm_fused_min = 96;
+  // launch groups with at least this many files run the fused rhythm front end (one CTA per file).  MEASURED SLOWER than
+  // the split kernels on the full workload (158 vs 135 ms per 50.7 M rhythm frames, profiles/README.md: with 16 warps per
+  // SM every phase of the fused kernel is latency bound on its own), so it is off unless AFX_RHYTHM_FUSED=1 asks for it
+  // (AFX_RHYTHM_FUSED=0 / 1 forces never / always: the parity test compares the two schedules)
+  int rhythm_fused_min = 0x7fffffff;
   bool rhythm_fused(int g_files) const { return g_files >= rhythm_fused_min; }
   struct afx_batch* live = nullptr;   // the one batch whose data occupies the device buffers (afx_batch_upload .. afx_batch_free)
 };

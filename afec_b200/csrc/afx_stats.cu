@@ -24,7 +24,21 @@ __device__ __forceinline__ double key_to_double(unsigned long long k)
   return __longlong_as_double((long long)u);
 }
 
-__global__ void __launch_bounds__(SW * 32) k_stats(AfxBatchDev B, AfxParams P)
+// series the configured feature groups produce (the others hold no data -- their arrays may not even be allocated -- and
+// get all-zero statistics)
+__device__ __forceinline__ bool series_enabled(int s, unsigned feat)
+{
+  if (s < 4) return feat & AFX_FEAT_AMPLITUDE;
+  if (s <= FS_SPEC_FLATNESS || s == FS_SPEC_INHARM || s == FS_SPEC_FLUX || (s >= FS_TRISTIM1 && s <= FS_TRISTIM3)) return feat & AFX_FEAT_SPECTRAL;
+  if (s == FS_SPEC_COMPLEXITY) return feat & AFX_FEAT_PEAKS;
+  if (s == FS_SPEC_CONTRAST) return feat & AFX_FEAT_BANDS;
+  if (s >= FS_F0 && s <= FS_F0_FAILSAFE) return feat & AFX_FEAT_PITCH;
+  if (s == FS_AUTOCORR) return feat & AFX_FEAT_AUTOCORR;
+  if (s < AFX_N_FS) return feat & AFX_FEAT_RHYTHM;
+  return feat & AFX_FEAT_BANDS;
+}
+
+__global__ void __launch_bounds__(SW * 32) k_stats(AfxBatchDev B, AfxParams P, unsigned features)
 {
   __shared__ int hist[SW][256];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -33,7 +47,7 @@ __global__ void __launch_bounds__(SW * 32) k_stats(AfxBatchDev B, AfxParams P)
   if (fi >= B.n_files) return;
   const AfxFile f = B.files[fi];
   double* out = B.stats + ((size_t)fi * AFX_N_SERIES + s) * AFX_N_STATS;
-  if (f.status != 0) { if (lane < AFX_N_STATS) out[lane] = 0.0; return; }
+  if (f.status != 0 || !series_enabled(s, features)) { if (lane < AFX_N_STATS) out[lane] = 0.0; return; }
   const AfxState* st = B.state + fi;
   const size_t TF = (size_t)B.TF;
   const double* x; int n, stride;
@@ -129,9 +143,9 @@ __global__ void __launch_bounds__(SW * 32) k_stats(AfxBatchDev B, AfxParams P)
   }
 }
 
-void afx_launch_stats(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
+void afx_launch_stats(const AfxParams& P, const AfxBatchDev& B, unsigned features, cudaStream_t s, long long* launches)
 {
   if (B.n_files <= 0) return;
   const long long warps = (long long)B.n_files * AFX_N_SERIES;
-  k_stats<<<(unsigned)((warps + SW - 1) / SW), SW * 32, 0, s>>>(B, P); ++*launches;
+  k_stats<<<(unsigned)((warps + SW - 1) / SW), SW * 32, 0, s>>>(B, P, features); ++*launches;
 }
