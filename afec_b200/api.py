@@ -21,6 +21,7 @@ FEAT_PITCH, FEAT_AUTOCORR, FEAT_RHYTHM, FEAT_STATS = 16, 32, 64, 128
 FEAT_ALL = 0xFF
 FEAT_HIGHLEVEL = 0x100   # on top of FEAT_ALL: model-free high-level descriptors + the classification feature vector
 FEAT_PACK = 0x200        # on top of FEAT_ALL: the row's msgpack BLOB images packed on the GPU
+FEAT_EXT_MELCHROMA = 0x400   # extension: MFCC-13 over 40 mel filters + chroma-12 (needs FEAT_SPECTRAL)
 N_BLOBS = 122
 HAVE_RESAMPLE = True   # k_resample + host block plan (libresample HQ restatement)
 
@@ -50,6 +51,7 @@ class AfxFileResult(C.Structure):
                 ("fs", C.POINTER(C.c_double) * layout.N_FS), ("fv", C.POINTER(C.c_double) * layout.N_FV),
                 ("stats", C.POINTER(C.c_double)), ("highlevel", C.POINTER(C.c_double)), ("hl_pitch", C.POINTER(C.c_double)),
                 ("hl_signature", C.POINTER(C.c_double)), ("hl_features", C.POINTER(C.c_double)),
+                ("ext_mfcc", C.POINTER(C.c_double)), ("ext_chroma", C.POINTER(C.c_double)), ("ext_chroma_index", C.POINTER(C.c_double)),
                 ("packed", C.POINTER(C.c_ubyte)), ("packed_off", C.POINTER(C.c_uint32))]
 
 
@@ -234,6 +236,20 @@ class Batch:
             out.stats = np.ctypeslib.as_array(r.stats, (layout.N_SERIES * layout.N_STATS,)).copy().reshape(
                 layout.N_SERIES, layout.N_STATS)
         return out
+
+    def extension(self, i: int):
+        """File i's extension outputs (contexts created with FEAT_EXT_MELCHROMA): (mfcc [F, 13], chroma [F, 12], chroma_index [F])."""
+        r = self.raw_result(i)
+        if r.status != 0:
+            return None
+        if not r.ext_mfcc:
+            raise AfxError("the context was not created with FEAT_EXT_MELCHROMA")
+        F = r.n_frames
+        if F <= 0:
+            return np.zeros((0, 13)), np.zeros((0, 12)), np.zeros(0)
+        return (np.ctypeslib.as_array(r.ext_mfcc, (F * 13,)).copy().reshape(F, 13),
+                np.ctypeslib.as_array(r.ext_chroma, (F * 12,)).copy().reshape(F, 12),
+                np.ctypeslib.as_array(r.ext_chroma_index, (F,)).copy())
 
     def highlevel(self, i: int) -> layout.HighLevelResult:
         """File i's high-level derivations + classification features (contexts created with FEAT_HIGHLEVEL)."""

@@ -21,7 +21,7 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--prec-div=tr
          "--ftz=false", "-Xptxas", "-v" if os.environ.get("AFX_PTXAS_V") else "-O3"]
 
 SOURCES = ["afx_api.cu", "afx_condition.cu", "afx_spectrum.cu", "afx_peaks.cu", "afx_bands.cu",
-           "afx_pitch.cu", "afx_autocorr.cu", "afx_rhythm.cu", "afx_stats.cu", "afx_debug.cu", "afx_part.cu", "afx_highlevel.cu", "afx_pack.cu"]
+           "afx_pitch.cu", "afx_autocorr.cu", "afx_rhythm.cu", "afx_stats.cu", "afx_debug.cu", "afx_part.cu", "afx_highlevel.cu", "afx_pack.cu", "afx_ext.cu"]
 DEFINES = {"afx_peaks.cu": "AFX_HAVE_PEAKS", "afx_bands.cu": "AFX_HAVE_BANDS", "afx_pitch.cu": "AFX_HAVE_PITCH",
            "afx_autocorr.cu": "AFX_HAVE_AUTOCORR", "afx_rhythm.cu": "AFX_HAVE_RHYTHM", "afx_stats.cu": "AFX_HAVE_STATS"}
 

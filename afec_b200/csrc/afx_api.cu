@@ -64,6 +64,36 @@ static void build_mel(std::vector<double>& tab, int nbins, double nyquist, doubl
   }
 }
 
+// extension tables (afx_ext.cu): 40 equal-gain triangular mel filters over ALL `nbins` bins (LibXtract's construction,
+// init.c:237-378, without its halving of the bin range) and the 12 chroma classes
+static void build_ext_weights(std::vector<float>& w, int nbins, double sr, int nfft)
+{
+  const int nmel = 40, nchr = 12, nout = nmel + nchr;
+  w.assign((size_t)nout * nbins, 0.0f);
+  const double nyquist = sr / 2.0, fmin = 20.0, fmax = 15500.0;
+  std::vector<double> lin(nmel + 2); std::vector<int> peak(nmel + 2);
+  const double mel_max = 1127 * std::log(1 + fmax / 700), mel_min = 1127 * std::log(1 + fmin / 700), bw = (mel_max - mel_min) / nmel;
+  for (int n = 0; n < nmel + 2; ++n) {
+    const double mel = mel_min + bw * n;
+    lin[n] = (n == 0) ? fmin : 700 * (std::exp(mel / 1127) - 1);
+    peak[n] = (int)(lin[n] / nyquist * nbins);
+  }
+  for (int n = 0; n < nmel; ++n) {              // filter n: rises peak[n] .. peak[n + 1], falls to peak[n + 2]
+    float* row = w.data() + (size_t)n * nbins;
+    const int p0 = peak[n], p1 = peak[n + 1], p2 = peak[n + 2];
+    for (int k = p0; k <= p1 && k < nbins; ++k) row[k] = (p1 > p0) ? (float)((double)(k - p0) / (p1 - p0)) : 1.0f;
+    for (int k = p1 + 1; k <= p2 && k < nbins; ++k) row[k] = (p2 > p1) ? (float)((double)(p2 - k) / (p2 - p1)) : 0.0f;
+  }
+  for (int k = 1; k < nbins; ++k) {             // chroma: a bin is shared linearly between its two nearest semitones
+    const double f = (double)k * sr / nfft;
+    if (f < 65.40639132514966 || f > 8372.018089619156) continue;
+    const double pitch = 69.0 + 12.0 * std::log2(f / 440.0), lower = std::floor(pitch), frac = pitch - lower;
+    const int c0 = (((int)lower % 12) + 12) % 12, c1 = (c0 + 1) % 12;
+    w[(size_t)(nmel + c0) * nbins + k] += (float)(1.0 - frac);
+    w[(size_t)(nmel + c1) * nbins + k] += (float)frac;
+  }
+}
+
 // libresample filterkit.c:67-113 + resample.c:113-116 (float copy of one Kaiser-windowed sinc wing)
 static double rs_izero(double x)
 {
@@ -247,6 +277,8 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
     return fail(nullptr, AFX_ERR_ARG, "afx_create: hop_size must be a multiple of 256 in [256, 2048]");
   if ((cfg->features & AFX_FEAT_PACK) && (cfg->features & AFX_FEAT_ALL) != AFX_FEAT_ALL)
     return fail(nullptr, AFX_ERR_ARG, "afx_create: AFX_FEAT_PACK packs the rows of the full low-level set (AFX_FEAT_ALL | AFX_FEAT_PACK)");
+  if ((cfg->features & AFX_FEAT_EXT_MELCHROMA) && !(cfg->features & AFX_FEAT_SPECTRAL))
+    return fail(nullptr, AFX_ERR_ARG, "afx_create: AFX_FEAT_EXT_MELCHROMA contracts the magnitude spectra (needs AFX_FEAT_SPECTRAL)");
   if ((cfg->features & AFX_FEAT_HIGHLEVEL) && (cfg->features & AFX_FEAT_ALL) != AFX_FEAT_ALL)
     return fail(nullptr, AFX_ERR_ARG, "afx_create: AFX_FEAT_HIGHLEVEL derives from the full low-level set (AFX_FEAT_ALL | AFX_FEAT_HIGHLEVEL)");
   int ndev = 0;
@@ -344,6 +376,12 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
     o_dct = place(dct.size() * 8), o_tw = place(tw2048.size() * 8), o_tw5 = place(tw512.size() * 8), o_imp = place(imp.size() * 4),
     o_ft2 = place(ft2.size() * 8), o_ft3a = place(ft3a.size() * 8), o_ft3b = place(ft3b.size() * 8), o_ctr = place(64 * 4),
     o_pad = place(32 * 8);
+  std::vector<float> extw, extw_k; std::vector<double> extdct(13 * 40);
+  build_ext_weights(extw, N / 2, (double)sr, N);
+  extw_k.resize(extw.size());
+  for (int o = 0; o < 52; ++o) for (int k = 0; k < N / 2; ++k) extw_k[(size_t)k * 52 + o] = extw[(size_t)o * (N / 2) + k];
+  for (int n = 0; n < 13; ++n) for (int m = 0; m < 40; ++m) extdct[n * 40 + m] = std::cos(pi * n * (m + 0.5) / 40.0);
+  const size_t o_extw = place(extw.size() * 4), o_extwk = place(extw_k.size() * 4), o_extdct = place(extdct.size() * 8);
   e = ctx->tables.reserve(off);
   if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMalloc(tables)", e); }
   unsigned char* base = (unsigned char*)ctx->tables.p;
@@ -366,6 +404,14 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   P.t.fft_t2 = (const double2*)(base + o_ft2); P.t.fft_t3_1024 = (const double2*)(base + o_ft3a); P.t.fft_t3_2048 = (const double2*)(base + o_ft3b);
 
   P.t.hl_pad = (double*)(base + o_pad);
+  cudaMemcpy(base + o_extw, extw.data(), extw.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_extwk, extw_k.data(), extw_k.size() * 4, cudaMemcpyHostToDevice);
+  e = cudaMemcpy(base + o_extdct, extdct.data(), extdct.size() * 8, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMemcpy(ext tables)", e); }
+  memset(&ctx->ext_tables, 0, sizeof(ctx->ext_tables));
+  ctx->ext_tables.w_nmajor = (const float*)(base + o_extw); ctx->ext_tables.w_kmajor = (const float*)(base + o_extwk);
+  ctx->ext_tables.dct = (const double*)(base + o_extdct);
+  ctx->ext_tensor = getenv("AFX_EXT_TENSOR") && atoi(getenv("AFX_EXT_TENSOR")) != 0;
   ctx->max_frame_cap = (P.analysis_cap - AFX_RFFT) / AFX_RHOP + 2;
   ctx->zeros.assign(ctx->max_frame_cap, 0.0);
   if (cfg->features & AFX_FEAT_HIGHLEVEL) {
@@ -407,7 +453,7 @@ extern "C" void afx_destroy(afx_ctx* ctx)
   if (ctx->ev_spec) cudaEventDestroy(ctx->ev_spec);
   DevBuf* bufs[] = { &ctx->tables, &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
     &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch,
-    &ctx->d_hl, &ctx->d_hl_pitch, &ctx->d_hl_sig, &ctx->d_hl_feat, &ctx->d_hl_status, &ctx->d_pack, &ctx->d_pack_off, &ctx->d_pack_file_off };
+    &ctx->d_hl, &ctx->d_hl_pitch, &ctx->d_hl_sig, &ctx->d_hl_feat, &ctx->d_hl_status, &ctx->d_pack, &ctx->d_pack_off, &ctx->d_pack_file_off, &ctx->d_ext_mfcc, &ctx->d_ext_chroma, &ctx->d_ext_idx };
   for (DevBuf* b : bufs) b->release();
   ctx->h_results_cache.release(); ctx->h_plan_cache.release(); ctx->h_pack_cache.release();
   for (auto& pb : ctx->part_pool) pb.release();
@@ -426,7 +472,7 @@ extern "C" int afx_trim(afx_ctx* ctx)
   if (ctx->live) return fail(ctx, AFX_ERR_STATE, "afx_trim: a batch of this context is still alive");
   DevBuf* bufs[] = { &ctx->d_pcm, &ctx->d_mono, &ctx->d_mono_src, &ctx->d_files, &ctx->d_state, &ctx->d_mag, &ctx->d_cent,
     &ctx->d_fs, &ctx->d_fsr, &ctx->d_fv, &ctx->d_rpolar, &ctx->d_rodf, &ctx->d_rpost, &ctx->d_bandraw, &ctx->d_slotmap, &ctx->d_stats, &ctx->d_header, &ctx->d_plan, &ctx->d_scratch,
-    &ctx->d_hl, &ctx->d_hl_pitch, &ctx->d_hl_sig, &ctx->d_hl_feat, &ctx->d_hl_status, &ctx->d_pack, &ctx->d_pack_off, &ctx->d_pack_file_off };
+    &ctx->d_hl, &ctx->d_hl_pitch, &ctx->d_hl_sig, &ctx->d_hl_feat, &ctx->d_hl_status, &ctx->d_pack, &ctx->d_pack_off, &ctx->d_pack_file_off, &ctx->d_ext_mfcc, &ctx->d_ext_chroma, &ctx->d_ext_idx };
   for (DevBuf* b : bufs) b->release();
   for (auto& pb : ctx->part_pool) pb.release();
   ctx->part_pool.clear();
@@ -597,6 +643,11 @@ int afx_batch_create_impl(afx_ctx* ctx, const afx_file* files, int32_t n_files, 
   b->o_fsr = o; o += (size_t)2 * b->TFr;
   b->o_fv = o; o += (size_t)AFX_FV_STRIDE * b->TF;
   b->o_state = o; o += ((size_t)n_files * sizeof(AfxState) + 7) / 8;
+  if (ctx->cfg.features & AFX_FEAT_EXT_MELCHROMA) {
+    b->o_ext_mfcc = o; o += (size_t)b->TF * 13;
+    b->o_ext_chroma = o; o += (size_t)b->TF * 12;
+    b->o_ext_idx = o; o += (size_t)b->TF;
+  }
   if (ctx->cfg.features & AFX_FEAT_HIGHLEVEL) {
     b->o_hl = o; o += (size_t)n_files * AFX_N_HL;
     b->o_hl_sig = o; o += (size_t)n_files * AFX_HL_SIGNATURE;
@@ -659,7 +710,7 @@ extern "C" int afx_batch_upload(afx_batch* b)
   CK(ctx->d_fsr.reserve((TFr + 1) * 2 * 8), "cudaMalloc(fsr)");
   if (feat & AFX_FEAT_BANDS) {
     CK(ctx->d_fv.reserve((TF + 1) * AFX_FV_STRIDE * 8), "cudaMalloc(fv)");
-    CK(ctx->d_bandraw.reserve((GS + 1) * 154 * 8), "cudaMalloc(bandraw)");
+    CK(ctx->d_bandraw.reserve((GS + 1) * 16 * 8), "cudaMalloc(bandraw)");   // afx_bands.cu BR2_STRIDE
   }
   if (feat & AFX_FEAT_RHYTHM) {
     size_t GRs = 0;                                  // polar rows only exist for the groups that take the split rhythm kernels
@@ -675,6 +726,11 @@ extern "C" int afx_batch_upload(afx_batch* b)
     CK(ctx->d_hl_feat.reserve((size_t)(n + 1) * AFX_HL_FEATURES * 8), "cudaMalloc(hl features)");
     CK(ctx->d_hl_pitch.reserve((TF + 1) * 8), "cudaMalloc(hl pitch)");
     CK(ctx->d_hl_status.reserve((size_t)(n + 1) * 4), "cudaMalloc(hl status)");
+  }
+  if (feat & AFX_FEAT_EXT_MELCHROMA) {
+    CK(ctx->d_ext_mfcc.reserve((TF + 1) * 13 * 8), "cudaMalloc(ext mfcc)");
+    CK(ctx->d_ext_chroma.reserve((TF + 1) * 12 * 8), "cudaMalloc(ext chroma)");
+    CK(ctx->d_ext_idx.reserve((TF + 1) * 8), "cudaMalloc(ext chroma index)");
   }
   if (feat & AFX_FEAT_PACK) {
     CK(ctx->d_pack.reserve(b->pack_bytes + 64), "cudaMalloc(pack)");
@@ -733,6 +789,8 @@ extern "C" int afx_batch_upload(afx_batch* b)
   D.slot_file = (const int*)ctx->d_slotmap.p; D.rslot_file = (const int*)ctx->d_slotmap.p + TF + 1;
   D.max_fr = b->max_fr;
   D.stats = (double*)ctx->d_stats.p; D.header = (double*)ctx->d_header.p; D.scratch = (double*)ctx->d_scratch.p;
+  b->ext = ctx->ext_tables;
+  b->ext.mfcc = (double*)ctx->d_ext_mfcc.p; b->ext.chroma = (double*)ctx->d_ext_chroma.p; b->ext.chroma_index = (double*)ctx->d_ext_idx.p;
   b->pack.packed = (unsigned char*)ctx->d_pack.p; b->pack.blob_off = (unsigned*)ctx->d_pack_off.p;
   b->pack.file_off = (const unsigned long long*)(dp + p_pack);
   b->hl.scalars = (double*)ctx->d_hl.p; b->hl.pitch = (double*)ctx->d_hl_pitch.p; b->hl.signature = (double*)ctx->d_hl_sig.p;
@@ -798,6 +856,7 @@ extern "C" int afx_batch_compute(afx_batch* b)
     if (feat & (AFX_FEAT_SPECTRAL | AFX_FEAT_AMPLITUDE | AFX_FEAT_PEAKS | AFX_FEAT_BANDS | AFX_FEAT_PITCH)) {
       ktime_begin(b, "spectrum"); afx_launch_spectrum(ctx->P, D, feat, s_main, &b->launches); ktime_end(b);
     }
+    if (feat & AFX_FEAT_EXT_MELCHROMA) { ktime_begin(b, "ext"); afx_launch_ext(D, b->ext, ctx->ext_tensor, s_main, &b->launches); ktime_end(b); }
 #ifdef AFX_HAVE_PITCH
     if (feat & AFX_FEAT_PITCH) {            // needs the spectrum's full-band centroid (fail-safe f0)
       if (ms) { CK(cudaEventRecord(ctx->ev_spec, s_main), "cudaEventRecord"); CK(cudaStreamWaitEvent(s_pitch, ctx->ev_spec, 0), "cudaStreamWaitEvent"); }
@@ -881,6 +940,11 @@ static int batch_download(afx_batch* b, bool arrays)
   if (arrays) for (auto& r : rr) CK(cp(H + b->o_fs + (size_t)r.first * TF, b->dev.fs + (size_t)r.first * TF, (size_t)(r.second - r.first) * TF * 8), "D2H fs");
   if (arrays && (feat & AFX_FEAT_RHYTHM)) CK(cp(H + b->o_fsr, b->dev.fsr, 2 * TFr * 8), "D2H fsr");
   if (arrays && (feat & AFX_FEAT_BANDS)) CK(cp(H + b->o_fv, b->dev.fv, TF * AFX_FV_STRIDE * 8), "D2H fv");
+  if (feat & AFX_FEAT_EXT_MELCHROMA) {
+    CK(cp(H + b->o_ext_mfcc, b->ext.mfcc, TF * 13 * 8), "D2H ext mfcc");
+    CK(cp(H + b->o_ext_chroma, b->ext.chroma, TF * 12 * 8), "D2H ext chroma");
+    CK(cp(H + b->o_ext_idx, b->ext.chroma_index, TF * 8), "D2H ext chroma index");
+  }
   if ((feat & AFX_FEAT_PACK) && n > 0) {
     const size_t tab = (size_t)n * (AFX_N_BLOBS + 1) * 4;
     if (!b->h_pack.p) take_cached(b->h_pack, ctx->h_pack_cache, b->pack_bytes + tab + 64);
@@ -952,6 +1016,11 @@ extern "C" int afx_batch_result(const afx_batch* b, int32_t i, afx_file_result* 
       static const int nbv[AFX_N_FV] = { 14, 14, 14, 14, 14, 28, 14 };
       for (int v = 0; v < AFX_N_FV; ++v) out->fv[v] = H + b->o_fv + (size_t)offs[v] * TF + (size_t)f.frame_off * nbv[v];
     }
+  }
+  if (feat & AFX_FEAT_EXT_MELCHROMA) {
+    out->ext_mfcc = H + b->o_ext_mfcc + (size_t)f.frame_off * 13;
+    out->ext_chroma = H + b->o_ext_chroma + (size_t)f.frame_off * 12;
+    out->ext_chroma_index = H + b->o_ext_idx + f.frame_off;
   }
   if ((feat & AFX_FEAT_HIGHLEVEL) && b->ctx->hl_pad_ready) {
     out->highlevel = H + b->o_hl + (size_t)i * AFX_N_HL;

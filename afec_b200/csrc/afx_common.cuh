@@ -278,7 +278,7 @@ struct AfxBatchDev {
   const int* rslot_file;  // [TFr] rhythm frame slot -> file index
   double* mag;        // [g_slots][1024]   (group scratch, indexed by slot - slot0)
   double* cent_full;  // [TF] centroid of mag[0..1023] (failsafe f0)
-  double* bandraw;    // [g_slots][154] raw sub-band sums (14 x 10) + mel energies (14)   (group scratch)
+  double* bandraw;    // [g_slots][16] order statistics + peak counts of the five large sub-bands (group scratch)
   double* fs;         // [22][TF]
   double* fsr;        // [2][TFr]
   double* fv;         // 7 arrays [TF][nb], array v at fv + FV_x * TF
@@ -300,6 +300,16 @@ struct AfxHighLevelDev {   // outputs of k_highlevel (afx_highlevel.cu), batch-w
   int* status;              // [n_files] 1: a classification feature is NaN / Inf (the reference fails the file)
   const double* silence_pad;// [21] last-frame values of a silent sample (SampleClassificationDescriptors.cpp:330-368)
 };
+
+struct AfxExtDev {          // the mel-40 / MFCC-13 / chroma-12 extension (afx_ext.cu)
+  const float* w_kmajor;    // [1024][52] weights, bin-major: 40 mel filters then 12 chroma classes
+  const float* w_nmajor;    // [52][1024] the same, output-major (K-major rows for the tensor-core operands)
+  const double* dct;        // [13][40] cos(pi n (m + 1/2) / 40)
+  double* mfcc;             // [TF][13]
+  double* chroma;           // [TF][12]
+  double* chroma_index;     // [TF]
+};
+void afx_launch_ext(const AfxBatchDev& B, const AfxExtDev& X, bool tensor, cudaStream_t s, long long* launches);
 
 struct AfxPackDev {         // outputs of k_pack (afx_pack.cu)
   unsigned char* packed;    // every file's msgpack BLOB images, file i at file_off[i]

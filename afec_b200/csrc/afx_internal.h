@@ -68,7 +68,9 @@ struct afx_ctx {
   AfxParams P;
   DevBuf tables;                      // all constant tables in one allocation
   DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf, d_rpost, d_bandraw, d_slotmap,
-         d_stats, d_header, d_plan, d_scratch, d_hl, d_hl_pitch, d_hl_sig, d_hl_feat, d_hl_status, d_pack, d_pack_off, d_pack_file_off;
+         d_stats, d_header, d_plan, d_scratch, d_hl, d_hl_pitch, d_hl_sig, d_hl_feat, d_hl_status, d_pack, d_pack_off, d_pack_file_off, d_ext_mfcc, d_ext_chroma, d_ext_idx;
+  bool ext_tensor = false;            // the extension's contraction runs on the tensor cores (AFX_EXT_TENSOR=1)
+  AfxExtDev ext_tables;               // weight / DCT tables of the extension (inside `tables`)
   bool hl_pad_ready = false;          // the silence pad table (tables: hl_pad) has been computed by afx_create
   long long group_frames = 1572864, group_rframes = 12582912;   // per-launch scratch bound: 12 GB mag, 24 GB rpolar (allocated by need). Large groups matter to the per-file kernels: 4x the files in flight took 17 % off the rhythm chain
   PinBuf h_results_cache, h_plan_cache, h_pack_cache;   // recycled between batches
@@ -115,6 +117,8 @@ struct afx_batch {
   size_t o_header = 0, o_state = 0, o_fs = 0, o_fsr = 0, o_fv = 0, o_stats = 0, total_doubles = 0;
   size_t o_hl = 0, o_hl_pitch = 0, o_hl_sig = 0, o_hl_feat = 0, o_hl_status = 0;
   AfxHighLevelDev hl;
+  size_t o_ext_mfcc = 0, o_ext_chroma = 0, o_ext_idx = 0;
+  AfxExtDev ext;
   // packed sink rows (AFX_FEAT_PACK): a separate pinned block; file i's region starts at pack_file_off[i]
   std::vector<unsigned long long> pack_file_off; size_t pack_bytes = 0;
   PinBuf h_pack;                      // [pack_bytes] blobs, then [n][AFX_N_BLOBS + 1] uint32 offsets

@@ -83,6 +83,12 @@ int afx_pcm_bytes(int32_t format);
  * afx_batch_download_rows() then copies back only what a sink needs -- the packed rows, headers and statistics -- and
  * leaves the framed arrays on the device (fs / fv stay NULL). */
 #define AFX_FEAT_PACK (1u << 9)
+/* Extension (BASELINE configs[2]; the reference has no counterpart): per main frame MFCC-13 over 40 mel
+ * filters and a 12-class chroma vector with its arg-max, as one [frames x 1024] x [1024 x 52] contraction of the
+ * magnitude spectra (afec_b200/csrc/afx_ext.cu; definition and CPU restatement: tests/ext_reference.py).  Needs
+ * AFX_FEAT_SPECTRAL.  The contraction runs as an FP32 FMA tile, or -- AFX_EXT_TENSOR=1 in the environment when the
+ * context is created -- as 3xTF32 on the tensor cores (tcgen05). */
+#define AFX_FEAT_EXT_MELCHROMA (1u << 10)
 
 typedef struct afx_ctx afx_ctx;
 typedef struct afx_batch afx_batch;
@@ -139,6 +145,10 @@ typedef struct afx_file_result {
   const double* hl_pitch;    /* [n_frames] MIDI notes ("pitch"); "peak" is fs[1] (amplitude_peak), SampleAnalyser.cpp:1609 */
   const double* hl_signature;/* [AFX_HL_SIGNATURE_FRAMES][AFX_HL_SIGNATURE_BANDS] */
   const double* hl_features; /* [AFX_HL_FEATURES] */
+  /* AFX_FEAT_EXT_MELCHROMA only (NULL otherwise) */
+  const double* ext_mfcc;        /* [n_frames][13] */
+  const double* ext_chroma;      /* [n_frames][12], max-normalised */
+  const double* ext_chroma_index;/* [n_frames] arg-max class 0..11 (C = 0), integer-valued */
   /* AFX_FEAT_PACK only (NULL otherwise) */
   const unsigned char* packed;   /* the row's AFX_N_BLOBS msgpack blobs back to back */
   const uint32_t* packed_off;    /* [AFX_N_BLOBS + 1] byte offsets into packed: blob k = [packed_off[k], packed_off[k + 1]) */

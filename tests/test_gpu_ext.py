@@ -1,0 +1,79 @@
+"""The mel-40 / MFCC-13 / chroma-12 extension (AFX_FEAT_EXT_MELCHROMA, afx_ext.cu) against its FP64 CPU restatement
+(tests/ext_reference.py), for BOTH implementations of the contraction: the FP32 FMA tile and 3xTF32 on the tensor cores
+(tcgen05).  north_star item (4): tensor cores only if the split-precision scheme stays inside 1e-4 relative / 1e-6
+absolute -- this test is that measurement; it also shows that plain (1x) TF32 rounding of the operands would not."""
+import numpy as np
+import pytest
+
+import ext_reference as ext
+import parity
+from afec_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def corpus():
+    pcms = [synth.one_shot(1600 + i, 0.3 + 0.8 * i) for i in range(6)]
+    pcms += [synth.one_shot(1610, 1.0, channels=2), np.zeros(30000, dtype=np.int16), synth.one_shot(1611, 0.02), synth.one_shot(1612, 9.0)]
+    t = np.arange(44100 * 2) / 44100.0
+    pcms.append(np.round(9000 * np.sin(2 * np.pi * 523.25 * t)).astype(np.int16))        # C5
+    return pcms
+
+
+def run(monkeypatch, tensor: bool, hop: int):
+    monkeypatch.setenv("AFX_EXT_TENSOR", "1" if tensor else "0")
+    an = api.SampleAnalyser(44100, 2048, hop, features=api.FEAT_SPECTRAL | api.FEAT_EXT_MELCHROMA)
+    pcms = corpus()
+    b = an.batch(pcms, [44100] * len(pcms)).run()
+    out = [(b.result(i), b.extension(i)) for i in range(len(pcms))]
+    b.free()
+    an.close()
+    return pcms, out
+
+
+@pytest.mark.parametrize("tensor", [False, True], ids=["fp32_tile", "tcgen05_3xtf32"])
+@pytest.mark.parametrize("hop", [1024, 512])
+def test_extension_vs_restatement(monkeypatch, oracle_lib, tensor, hop):
+    pcms, out = run(monkeypatch, tensor, hop)
+    worst = 0.0
+    for p, (r, e) in zip(pcms, out):
+        mdata = oracle_lib.condition(p)[0]
+        mfcc, chroma, idx, E, C = ext.analyze(mdata, hop)
+        g_mfcc, g_chroma, g_idx = e
+        assert g_mfcc.shape == mfcc.shape and g_chroma.shape == chroma.shape
+        assert parity.close(g_mfcc, mfcc).all(), ("mfcc", np.abs(g_mfcc - mfcc).max())
+        assert parity.close(g_chroma, chroma).all(), ("chroma", np.abs(g_chroma - chroma).max())
+        # integer output: exact, except where the two largest classes are closer than the contraction's own rounding
+        top2 = np.sort(C, axis=1)[:, -2:]
+        tie = (top2[:, 1] - top2[:, 0]) <= 1e-5 * np.maximum(top2[:, 1], 1e-300)
+        assert np.array_equal(g_idx[~tie], idx[~tie])
+        if len(mfcc):
+            worst = max(worst, float(np.max(np.abs(g_mfcc - mfcc) / (parity.ATOL + parity.RTOL * np.abs(mfcc)))))
+    assert worst < 1.0
+
+
+def test_both_implementations_agree_closely(monkeypatch):
+    _, a = run(monkeypatch, False, 1024)
+    _, b = run(monkeypatch, True, 1024)
+    for (_, x), (_, y) in zip(a, b):
+        if x is None:
+            continue
+        assert np.allclose(x[0], y[0], rtol=2e-5, atol=2e-6) and np.allclose(x[1], y[1], rtol=2e-5, atol=2e-6)
+
+
+def test_plain_tf32_would_not_meet_the_tolerance(oracle_lib):
+    """Why the split is needed: rounding the operands to TF32 once (10-bit mantissa) moves the mel energies by ~1e-3."""
+    p = synth.one_shot(1600, 1.5)
+    mag = ext.magnitude_spectra(oracle_lib.condition(p)[0], 1024)
+    wm, _ = ext.weights()
+
+    def tf32(x):
+        v = np.asarray(x, dtype=np.float32).view(np.uint32)
+        return ((v + 0x1000) & 0xFFFFE000).view(np.float32).astype(np.float64)
+    exact = mag @ wm.T
+    once = tf32(mag) @ tf32(wm).T
+    hi_a, hi_w = tf32(mag), tf32(wm)
+    lo_a, lo_w = tf32(mag.astype(np.float32).astype(np.float64) - hi_a), tf32(wm - hi_w)
+    split = hi_a @ hi_w.T + lo_a @ hi_w.T + hi_a @ lo_w.T
+    rel = lambda x: np.max(np.abs(x - exact) / np.maximum(exact, 1e-300))
+    assert rel(once) > 1e-4 > 1e-5 > rel(split)

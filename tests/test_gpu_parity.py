@@ -141,7 +141,7 @@ def test_unsupported_description_fails_that_file_only(analysers, feats, oracle_l
     an = analysers(1024)
     f_good, keep = an.describe(good, 44100)
     f_rate, _ = an.describe(good, 44100); f_rate.src_rate = -5
-    f_fmt, _ = an.describe(good, 44100); f_fmt.format = 7
+    f_fmt, _ = an.describe(good, 44100); f_fmt.format = 99
     b = an.batch_from_descriptors([f_good, f_rate, f_fmt, f_good], keep).run()
     got = [b.result(i) for i in range(4)]
     b.free()
