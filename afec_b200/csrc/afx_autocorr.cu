@@ -14,6 +14,7 @@
 // feeds 9 DFMAs (the FP64 pipe, not shared memory, is the limit); see ac_rounds for how the triangle of
 // lag x sample work is spread over the lanes.
 #include "afx_common.cuh"
+#include <cstdlib>
 
 #define AW 4                // warps (frames) per CTA
 #define AL 9                // lags per lane task
@@ -59,9 +60,55 @@ __device__ __forceinline__ double ac_rounds(const double* __restrict__ x, int wi
   return best;
 }
 
+// FP32 form of the same tiling (round 2, "precision demotion"): R[i] / R[0] does not depend on the file's scale, so the
+// window is taken as the RAW float32 mono samples (exact), a lane owns 16 lags (two shared-memory loads feed 16 FFMAs on
+// the pipe that is twice as wide as the FP64 one) and a round's partial sums -- at most 133 products each -- stay in FP32;
+// they are widened to FP64 before the four lanes of a group and the rounds are combined.  Rounding analysis: the error of
+// a partial sum is ~ eps sqrt(n) |s| / 3 ~ 2e-7 |s| with |s| <= R[0] / 4, i.e. <= 1e-7 of R[0], against a tolerance of
+// 1e-6 + 1e-4 |v| on v = R[i] / R[0] in [0, 1]; nothing downstream of this value is a threshold (it is a maximum over lags,
+// then temporal statistics).  Measured against the FP64 kernel: profiles/README.md.  AFX_AUTOCORR_FP64=1 keeps the FP64 form.
+#define ALF 16              // lags per lane task
+#define ACF_XS 768          // floats: window + zero padding
+#define ACF_ZERO 592        // idle lanes read zeros from here (a round reads at most 133 + 16 samples)
+__device__ __forceinline__ double ac_rounds_f32(const float* __restrict__ x, int width, int G, int lane, int lo, double& r0)
+{
+  const int sub = lane & 3, gl = lane >> 2;
+  double best = 0.0;
+  for (int gbase = 0; gbase < G; gbase += 8) {
+    const int g = gbase + gl, i0 = ALF * g;
+    const bool act = g < G;
+    const int len = (width - ALF * gbase + 3) >> 2;  // uniform across the warp
+    const int j0 = sub * len;
+    const float* __restrict__ xa = x + j0;
+    const float* __restrict__ xw = x + (act ? j0 + i0 : ACF_ZERO);
+    float acc[ALF], w[ALF];
+#pragma unroll
+    for (int q = 0; q < ALF; ++q) { acc[q] = 0.0f; w[q] = xw[q]; }
+    for (int jj = 0; jj < len; ++jj) {
+      const float a = xa[jj];
+#pragma unroll
+      for (int q = 0; q < ALF; ++q) acc[q] = fmaf(a, w[q], acc[q]);
+#pragma unroll
+      for (int q = 0; q < ALF - 1; ++q) w[q] = w[q + 1];
+      w[ALF - 1] = xw[jj + ALF];
+    }
+#pragma unroll
+    for (int q = 0; q < ALF; ++q) {
+      double d = (double)acc[q];
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      if (act && i0 + q < width && i0 + q >= lo) best = fmax(best, d);
+      if (gbase == 0 && q == 0) r0 = d;              // lanes 0..3 hold R[0]
+    }
+  }
+  return best;
+}
+
+template <bool F32>
 __global__ void __launch_bounds__(AW * 32) k_autocorr(AfxBatchDev B, AfxParams P)
 {
-  __shared__ double xs[AW][AC_XS];
+  __shared__ double xs[F32 ? 1 : AW][AC_XS];
+  __shared__ float xf[F32 ? AW : 1][ACF_XS];
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int rel = blockIdx.x * AW + wid;
@@ -105,14 +152,23 @@ __global__ void __launch_bounds__(AW * 32) k_autocorr(AfxBatchDev B, AfxParams P
   if (!remaining || period >= remaining) { if (lane == 0) *out = 0.0; return; }   // :2361-2365
 
   const int width = min(remaining, P.ac_width);
-  double* x = xs[wid];
-  for (int k = lane; k < AC_XS; k += 32) x[k] = (k < width) ? mdata(mono, st, n0 + start + k) : 0.0;
-  __syncwarp();
-
-  const int G = (width + AL - 1) / AL;             // lag groups; the last one may be partial (zero padded)
   const int lo = period / 2;
-  double r0 = 0.0;                                 // the result is floored at 0 (Autocorrelation.cpp:96-103)
-  double best = ac_rounds(x, width, G, lane, lo, r0);
+  double r0 = 0.0, best;                           // the result is floored at 0 (Autocorrelation.cpp:96-103)
+  if (F32) {
+    // raw mono samples of the conditioned window: mdata() without its scale (trim and padding as there)
+    float* x = xf[wid];
+    for (int k = lane; k < ACF_XS; k += 32) {
+      const int j = n0 + start + k - st.start_off;
+      x[k] = (k < width && j >= 0 && j < st.audible) ? __ldg(mono + st.lead + j) : 0.0f;
+    }
+    __syncwarp();
+    best = ac_rounds_f32(x, width, (width + ALF - 1) / ALF, lane, lo, r0);
+  } else {
+    double* x = xs[wid];
+    for (int k = lane; k < AC_XS; k += 32) x[k] = (k < width) ? mdata(mono, st, n0 + start + k) : 0.0;
+    __syncwarp();
+    best = ac_rounds(x, width, (width + AL - 1) / AL, lane, lo, r0);   // lag groups; the last one may be partial (zero padded)
+  }
   best = warp_max(best);
   r0 = __shfl_sync(0xffffffffu, r0, 0);            // lane 0 owns group 0
   // normalisation by R[0] > 0 is monotonic, so max_i (R[i] / R[0]) == (max_i R[i]) / R[0] exactly
@@ -122,5 +178,8 @@ __global__ void __launch_bounds__(AW * 32) k_autocorr(AfxBatchDev B, AfxParams P
 void afx_launch_autocorr(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  k_autocorr<<<(B.g_slots + AW - 1) / AW, AW * 32, 0, s>>>(B, P); ++*launches;
+  static const bool fp64 = [] { const char* e = getenv("AFX_AUTOCORR_FP64"); return e && atoi(e) != 0; }();
+  if (fp64) k_autocorr<false><<<(B.g_slots + AW - 1) / AW, AW * 32, 0, s>>>(B, P);
+  else k_autocorr<true><<<(B.g_slots + AW - 1) / AW, AW * 32, 0, s>>>(B, P);
+  ++*launches;
 }

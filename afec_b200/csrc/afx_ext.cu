@@ -157,6 +157,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 #define TC_WC_ROWS 16
 #define TC_STAGE_BYTES (4 * TC_A_BYTES + 2 * TC_WM_ROWS * 128 + 2 * TC_WC_ROWS * 128)
 #define TC_STAGES 2
+#define TC_NACC 8           // TMEM accumulator sets (x 64 columns = the SM's 512)
 #define TC_SMEM (TC_STAGES * TC_STAGE_BYTES + 1024)
 
 // byte offset of element (row, col) of a K-major SWIZZLE_128B tile whose rows hold 32 x 4 bytes: 8-row atoms of 1024 B,
@@ -182,8 +183,12 @@ __global__ void __launch_bounds__(EX_T) k_ext_tc(AfxBatchDev B, AfxExtDev X)
   const int last_row = B.g_slots - 1;
 
   if (tid == 0) { for (int s = 0; s < TC_STAGES; ++s) mbar_init(&bar_mma[s], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  if (wid == 0) {                              // 64 TMEM columns: mel accumulator at column 0 (48), chroma at column 48 (16)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" :: "r"(smem_u32(&tmem_base_s)) : "memory");
+  // TMEM: TC_NACC accumulator sets of 64 columns (mel at column 0 (48 wide), chroma at column 48 (16 wide) of a set).  The
+  // tensor core adds into its FP32 accumulators with truncation, so the error of ONE accumulator grows linearly with the
+  // number of MMAs chained into it (measured: 3e-6 relative after the 384 of a whole row); K step `it` therefore goes to
+  // set it % TC_NACC (48 MMAs per set) and the sets are added in FP64 by the epilogue.
+  if (wid == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&tmem_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -234,13 +239,15 @@ __global__ void __launch_bounds__(EX_T) k_ext_tc(AfxBatchDev B, AfxExtDev X)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t ko = (uint32_t)k * 32u;                     // 8 tf32 = 32 bytes along K inside the swizzle row
-        const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-        umma_tf32(tmem, umma_desc_sw128(a_mh + ko), umma_desc_sw128(w_mh + ko), idesc_mel, first);
-        umma_tf32(tmem, umma_desc_sw128(a_ml + ko), umma_desc_sw128(w_mh + ko), idesc_mel, 1u);
-        umma_tf32(tmem, umma_desc_sw128(a_mh + ko), umma_desc_sw128(w_ml + ko), idesc_mel, 1u);
-        umma_tf32(tmem + 48, umma_desc_sw128(a_ph + ko), umma_desc_sw128(w_ch + ko), idesc_chr, first);
-        umma_tf32(tmem + 48, umma_desc_sw128(a_pl + ko), umma_desc_sw128(w_ch + ko), idesc_chr, 1u);
-        umma_tf32(tmem + 48, umma_desc_sw128(a_ph + ko), umma_desc_sw128(w_cl + ko), idesc_chr, 1u);
+        const uint32_t first = (it >= TC_NACC || k > 0) ? 1u : 0u;   // 0: overwrite (the set's first MMA), 1: accumulate
+        const uint32_t d = tmem + 64u * (uint32_t)(it % TC_NACC);
+        // small terms first: lo.hi and hi.lo are ~2^-11 of hi.hi
+        umma_tf32(d, umma_desc_sw128(a_ml + ko), umma_desc_sw128(w_mh + ko), idesc_mel, first);
+        umma_tf32(d, umma_desc_sw128(a_mh + ko), umma_desc_sw128(w_ml + ko), idesc_mel, 1u);
+        umma_tf32(d, umma_desc_sw128(a_mh + ko), umma_desc_sw128(w_mh + ko), idesc_mel, 1u);
+        umma_tf32(d + 48, umma_desc_sw128(a_pl + ko), umma_desc_sw128(w_ch + ko), idesc_chr, first);
+        umma_tf32(d + 48, umma_desc_sw128(a_ph + ko), umma_desc_sw128(w_cl + ko), idesc_chr, 1u);
+        umma_tf32(d + 48, umma_desc_sw128(a_ph + ko), umma_desc_sw128(w_ch + ko), idesc_chr, 1u);
       }
       // arrives on the barrier when every MMA issued so far has completed (implies tcgen05.fence::before_thread_sync)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar_mma[s])) : "memory");
@@ -255,26 +262,34 @@ __global__ void __launch_bounds__(EX_T) k_ext_tc(AfxBatchDev B, AfxExtDev X)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   float acc[EX_NOUT];
   {
-    const uint32_t taddr = tmem + ((uint32_t)(wid * 32) << 16);   // lane field in bits 31:16: warp w owns TMEM lanes 32 w .. 32 w + 31
-    uint32_t v[64];
+    double sum[EX_NOUT];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                   : "=r"(v[16 * c]), "=r"(v[16 * c + 1]), "=r"(v[16 * c + 2]), "=r"(v[16 * c + 3]), "=r"(v[16 * c + 4]), "=r"(v[16 * c + 5]),
-                     "=r"(v[16 * c + 6]), "=r"(v[16 * c + 7]), "=r"(v[16 * c + 8]), "=r"(v[16 * c + 9]), "=r"(v[16 * c + 10]), "=r"(v[16 * c + 11]),
-                     "=r"(v[16 * c + 12]), "=r"(v[16 * c + 13]), "=r"(v[16 * c + 14]), "=r"(v[16 * c + 15])
-                   : "r"(taddr + 16u * c));
+    for (int q = 0; q < EX_NOUT; ++q) sum[q] = 0.0;
+#pragma unroll 1
+    for (int a = 0; a < TC_NACC; ++a) {
+      const uint32_t taddr = tmem + ((uint32_t)(wid * 32) << 16) + 64u * (uint32_t)a;   // lane field in bits 31:16: warp w owns TMEM lanes 32 w .. 32 w + 31
+      uint32_t v[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(v[16 * c]), "=r"(v[16 * c + 1]), "=r"(v[16 * c + 2]), "=r"(v[16 * c + 3]), "=r"(v[16 * c + 4]), "=r"(v[16 * c + 5]),
+                       "=r"(v[16 * c + 6]), "=r"(v[16 * c + 7]), "=r"(v[16 * c + 8]), "=r"(v[16 * c + 9]), "=r"(v[16 * c + 10]), "=r"(v[16 * c + 11]),
+                       "=r"(v[16 * c + 12]), "=r"(v[16 * c + 13]), "=r"(v[16 * c + 14]), "=r"(v[16 * c + 15])
+                     : "r"(taddr + 16u * c));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < EX_NMEL; ++q) sum[q] += (double)__uint_as_float(v[q]);
+#pragma unroll
+      for (int q = 0; q < EX_NCHR; ++q) sum[EX_NMEL + q] += (double)__uint_as_float(v[48 + q]);
     }
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int q = 0; q < EX_NMEL; ++q) acc[q] = __uint_as_float(v[q]);
-#pragma unroll
-    for (int q = 0; q < EX_NCHR; ++q) acc[EX_NMEL + q] = __uint_as_float(v[48 + q]);
+    for (int q = 0; q < EX_NOUT; ++q) acc[q] = (float)sum[q];
   }
   if (live) ext_epilogue(B, X, slot, acc);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" :: "r"(tmem) : "memory");
+  if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
 void afx_launch_ext(const AfxBatchDev& B, const AfxExtDev& X, bool tensor, cudaStream_t s, long long* launches)

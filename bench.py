@@ -373,6 +373,39 @@ def parity_check_sample(b, pcms, wl, n_check=32, seed=7):
     return n, errs
 
 
+def crawl_with_sink(pcms, wl, device, n_files=600):
+    """The whole crawler on a bounded sample of the workload: WAV files on a RAM disk -> afec-b200-crawler (host decode
+    ring, GPU, rows packed on the device, sqlite sink) -> afec-ll.db.  This is what a user's `Crawler -l low` run sees;
+    the database writer, not the GPU, bounds it."""
+    import shutil
+    from afec_b200 import build as afx_build
+    from oracle import oracle
+    root = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    d = tempfile.mkdtemp(prefix="afx_crawl_", dir=root)
+    try:
+        audio_s = 0.0
+        for i in range(min(n_files, len(pcms))):
+            oracle.write_wav(os.path.join(d, "f%05d.wav" % i), pcms[i], wl.get("rate", 44100))
+            audio_s += len(pcms[i]) / float(wl.get("rate", 44100))
+        out = {}
+        for tag, extra in (("one_writer", []), ("four_shards", ["--shards", "4"])):
+            db = os.path.join(d, tag + ".db")
+            t0 = time.perf_counter()
+            r = subprocess.run([afx_build.CRAWLER, "-o", db, "--hop", str(wl["hop"]), "--devices", str(device), "-j", "3"] + extra + [d],
+                               capture_output=True, text=True, timeout=600)
+            wall = time.perf_counter() - t0
+            js = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            size = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d) if f.startswith(tag + ".db"))
+            out[tag] = {"value": js["audio_seconds"] / 3600.0 / js["seconds"], "unit": "audio-hours/s", "files": js["files"],
+                        "seconds": js["seconds"], "wall_seconds": wall, "rows_per_s": js["files"] / js["seconds"],
+                        "db_mb_per_s": size / js["seconds"] / 1e6}
+        best = max(out, key=lambda k: out[k]["value"])
+        return dict(out[best], writer=best, variants=out, sample="%d WAV files of the workload's corpus (%.0f s audio) on %s" % (min(n_files, len(pcms)), audio_s, root),
+                    path="afec-b200-crawler: decode threads -> pinned ring -> GPU (rows packed on the device) -> sqlite sink (journal-less bulk load)")
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -384,6 +417,7 @@ def main():
     ap.add_argument("--files", type=int, default=0, help="override files per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-sink", action="store_true", help="skip the crawler-with-sqlite-sink leg")
     ap.add_argument("--parts", type=int, default=0, help="long workload at N = 1: condition every file in this many parts")
     ap.add_argument("--e2e-slots", type=int, default=3)
     ap.add_argument("--e2e-chunks", type=int, default=12)
@@ -655,6 +689,13 @@ def main():
         except Exception as e:
             cpu = {"value": None, "unit": "audio-hours/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
 
+    sink = None
+    if rank == 0 and world == 1 and wl["features"] == "all" and not args.no_sink:
+        try:
+            sink = crawl_with_sink(pcms, wl, local_rank)
+        except Exception as e:
+            sink = {"value": None, "error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": "low-level descriptor throughput (audio-hours/sec)", "value": value, "unit": "audio-hours/s",
@@ -670,7 +711,7 @@ def main():
                             "%d contexts / host threads (copies overlap kernels)" % (E2E_CHUNKS, E2E_SLOTS)},
             "gpu_launches": int(cnt["kernel_launches"]) * args.steps * world,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "parity_checked": parity_n, "parity_mismatches": parity_errs[:8],
+            "parity_checked": parity_n, "parity_mismatches": parity_errs[:8], "e2e_with_sink": sink,
         }
         print(json.dumps(line), flush=True)
     arena.free()
