@@ -376,11 +376,38 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
     o_dct = place(dct.size() * 8), o_tw = place(tw2048.size() * 8), o_tw5 = place(tw512.size() * 8), o_imp = place(imp.size() * 4),
     o_ft2 = place(ft2.size() * 8), o_ft3a = place(ft3a.size() * 8), o_ft3b = place(ft3b.size() * 8), o_ctr = place(64 * 4),
     o_pad = place(32 * 8);
+  // the walk of k_bands_lane: cut the bin axis at every sub-band / frequency-band / mel-support edge and every 32 bins
+  std::vector<AfxBandSeg> segs;
+  {
+    std::vector<int> cuts;
+    for (int k = 0; k <= N / 2; k += 32) cuts.push_back(k);
+    for (int b = 0; b < 14; ++b) { cuts.push_back(P.band14_start[b]); cuts.push_back(P.band14_start[b] + P.band14_n[b]); }
+    for (int b = 0; b < 28; ++b) { cuts.push_back(P.band28_s[b]); cuts.push_back(P.band28_e[b]); }
+    for (int q = 0; q < 14; ++q) if (P.mel_hi[q] >= P.mel_lo[q]) { cuts.push_back(P.mel_lo[q]); cuts.push_back(P.mel_hi[q] + 1); }
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    for (size_t i = 0; i + 1 < cuts.size(); ++i) {
+      const int k0 = cuts[i], k1 = cuts[i + 1];
+      if (k0 < 0 || k1 > N / 2 || k0 >= k1) continue;
+      AfxBandSeg sg; memset(&sg, 0, sizeof(sg));
+      sg.k0 = (short)k0; sg.k1 = (short)k1; sg.b14 = sg.b28 = sg.q0 = -1;
+      for (int b = 0; b < 14; ++b) if (k0 >= P.band14_start[b] && k0 < P.band14_start[b] + P.band14_n[b]) {
+        sg.b14 = (signed char)b; sg.start14 = (k0 == P.band14_start[b]); sg.end14 = (k1 == P.band14_start[b] + P.band14_n[b]);
+      }
+      for (int b = 0; b < 28; ++b) if (k0 >= P.band28_s[b] && k0 < P.band28_e[b]) { sg.b28 = (signed char)b; sg.end28 = (k1 == P.band28_e[b]); }
+      for (int q = 0; q < 14; ++q) if (P.mel_hi[q] >= P.mel_lo[q] && k0 >= P.mel_lo[q] && k0 <= P.mel_hi[q]) { if (sg.q0 < 0) sg.q0 = (signed char)q; ++sg.nq; }
+      if (sg.nq > 2 || (sg.nq == 2 && !(k0 >= P.mel_lo[sg.q0 + 1] && k0 <= P.mel_hi[sg.q0 + 1]))) {
+        afx_destroy(ctx); return fail(nullptr, AFX_ERR_ARG, "afx_create: more than two mel filters overlap (unexpected filter table)");
+      }
+      segs.push_back(sg);
+    }
+  }
   std::vector<float> extw, extw_k; std::vector<double> extdct(13 * 40);
   build_ext_weights(extw, N / 2, (double)sr, N);
   extw_k.resize(extw.size());
   for (int o = 0; o < 52; ++o) for (int k = 0; k < N / 2; ++k) extw_k[(size_t)k * 52 + o] = extw[(size_t)o * (N / 2) + k];
   for (int n = 0; n < 13; ++n) for (int m = 0; m < 40; ++m) extdct[n * 40 + m] = std::cos(pi * n * (m + 0.5) / 40.0);
+  const size_t o_segs = place(segs.size() * sizeof(AfxBandSeg));
   const size_t o_extw = place(extw.size() * 4), o_extwk = place(extw_k.size() * 4), o_extdct = place(extdct.size() * 8);
   e = ctx->tables.reserve(off);
   if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMalloc(tables)", e); }
@@ -404,6 +431,8 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   P.t.fft_t2 = (const double2*)(base + o_ft2); P.t.fft_t3_1024 = (const double2*)(base + o_ft3a); P.t.fft_t3_2048 = (const double2*)(base + o_ft3b);
 
   P.t.hl_pad = (double*)(base + o_pad);
+  cudaMemcpy(base + o_segs, segs.data(), segs.size() * sizeof(AfxBandSeg), cudaMemcpyHostToDevice);
+  P.t.band_segs = (const AfxBandSeg*)(base + o_segs); P.t.n_band_segs = (int)segs.size();
   cudaMemcpy(base + o_extw, extw.data(), extw.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(base + o_extwk, extw_k.data(), extw_k.size() * 4, cudaMemcpyHostToDevice);
   e = cudaMemcpy(base + o_extdct, extdct.data(), extdct.size() * 8, cudaMemcpyHostToDevice);

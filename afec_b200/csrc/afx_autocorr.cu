@@ -77,20 +77,25 @@ __device__ __forceinline__ double ac_rounds_f32(const float* __restrict__ x, int
   for (int gbase = 0; gbase < G; gbase += 8) {
     const int g = gbase + gl, i0 = ALF * g;
     const bool act = g < G;
-    const int len = (width - ALF * gbase + 3) >> 2;  // uniform across the warp
+    // a quarter of the round's longest group, rounded up to the unroll depth: steps past a group's last product read the
+    // zero padding behind the window (x[j + i] = 0 for j + i >= width), so a longer walk adds nothing
+    const int len = ((((width - ALF * gbase + 3) >> 2) + ALF - 1) / ALF) * ALF;    // uniform across the warp
     const int j0 = sub * len;
     const float* __restrict__ xa = x + j0;
     const float* __restrict__ xw = x + (act ? j0 + i0 : ACF_ZERO);
     float acc[ALF], w[ALF];
 #pragma unroll
     for (int q = 0; q < ALF; ++q) { acc[q] = 0.0f; w[q] = xw[q]; }
-    for (int jj = 0; jj < len; ++jj) {
-      const float a = xa[jj];
+    // sixteen steps per trip with the window registers addressed modulo 16: register u holds x[.. + u] until step u has
+    // used it, then takes the sample 16 further on -- the window slides without a single register move
+    for (int jj = 0; jj < len; jj += ALF) {
 #pragma unroll
-      for (int q = 0; q < ALF; ++q) acc[q] = fmaf(a, w[q], acc[q]);
+      for (int u = 0; u < ALF; ++u) {
+        const float a = xa[jj + u];
 #pragma unroll
-      for (int q = 0; q < ALF - 1; ++q) w[q] = w[q + 1];
-      w[ALF - 1] = xw[jj + ALF];
+        for (int q = 0; q < ALF; ++q) acc[q] = fmaf(a, w[(q + u) & (ALF - 1)], acc[q]);
+        w[u] = xw[jj + u + ALF];
+      }
     }
 #pragma unroll
     for (int q = 0; q < ALF; ++q) {

@@ -61,21 +61,28 @@ __device__ __forceinline__ double band_write(AfxBatchDev& B, size_t TF, int slot
 #define BR2_STRIDE 16       // doubles per frame: 5 large bands x (lo_sum, hi_sum, complexity) + pad
 #define BIG0 9              // first large sub-band (41, 61, 96, 148, 287 bins)
 
-// order statistics + complexity of one large sub-band on one warp (C = ceil(n / 32) elements per lane)
+// order statistics + complexity of one large sub-band on one warp (C = ceil(n / 32) elements per lane).
+//
+// Selection is an exact most-significant-digit radix select on the 64-bit patterns of the (non-negative) magnitudes,
+// 8 bits per pass, histograms in shared memory: the bits common to the whole band are skipped, the first pass is shared
+// by the two selections (the nei smallest / the nei largest), and a selection stops as soon as a bucket boundary splits
+// the band exactly -- after one or two passes for almost every frame (the bisection this replaces took ~14 passes of
+// one bit each).  `hist` = 2 x 256 ints of the warp.
 template <int C>
-__device__ __forceinline__ void subband_select(const AfxParams& P, int b, const double* __restrict__ g, int lane, double* __restrict__ out3)
+__device__ __forceinline__ void subband_select(const AfxParams& P, int b, const double* __restrict__ g, int lane, int* hist, double* __restrict__ out3)
 {
   const int s0 = P.band14_start[b], n = P.band14_n[b], nei = P.band14_nei[b];
-  double x[C]; unsigned hi[C], lo[C];
+  double x[C]; unsigned long long u[C];
   double mx = 0.0;
+  unsigned long long kmin = 0xffffffffffffffffull, kmax = 0ull;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     const int k = lane + 32 * c;
     const bool valid = k < n;
     const double xv = valid ? g[s0 + k] : 0.0;
     x[c] = xv;
-    const unsigned long long u = valid ? (unsigned long long)__double_as_longlong(xv) : 0xffffffffffffffffull;
-    hi[c] = (unsigned)(u >> 32); lo[c] = (unsigned)u;
+    u[c] = valid ? (unsigned long long)__double_as_longlong(xv) : 0xffffffffffffffffull;   // invalid slots sort last and are never counted
+    if (valid) { kmin = min(kmin, u[c]); kmax = max(kmax, u[c]); }
     mx = fmax(mx, xv);
   }
   mx = warp_max(mx);
@@ -89,67 +96,99 @@ __device__ __forceinline__ void subband_select(const AfxParams& P, int b, const 
     }
   }
   cplx = __reduce_add_sync(0xffffffffu, cplx);
-  // exact MSB-first bisection on the 64-bit patterns (see subband<C>)
-  const int r1 = nei - 1, r2 = n - nei;
-  unsigned mnh = 0xffffffffu, mxh = 0;
-#pragma unroll
-  for (int c = 0; c < C; ++c) if (lane + 32 * c < n) { mnh = min(mnh, hi[c]); mxh = max(mxh, hi[c]); }
-  mnh = __reduce_min_sync(0xffffffffu, mnh); mxh = __reduce_max_sync(0xffffffffu, mxh);
-  const int top = 31 - __clz((mnh ^ mxh) | 1u);
-  const unsigned common = (top >= 31) ? 0u : (mxh & ~((2u << top) - 1u));
-  unsigned p1h = common, p2h = common, p1l = 0, p2l = 0;
-  bool done1 = false, done2 = false;
-  unsigned t1h = 0, t1l = 0, t2h = 0, t2l = 0;
-  for (int bit = top; bit >= 0 && !(done1 && done2); --bit) {
-    const unsigned a1 = p1h | (1u << bit), a2 = p2h | (1u << bit);
-    int c1 = 0, c2 = 0;
-#pragma unroll
-    for (int c = 0; c < C; ++c) { c1 += (hi[c] < a1) ? 1 : 0; c2 += (hi[c] < a2) ? 1 : 0; }
-    c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2);
-    if (!done1) { if (c1 == nei) { done1 = true; t1h = a1; t1l = 0; } else if (c1 <= r1) p1h = a1; }
-    if (!done2) { if (c2 == r2) { done2 = true; t2h = a2; t2l = 0; } else if (c2 <= r2) p2h = a2; }
+  {
+    unsigned lo32 = (unsigned)kmin, hi32 = (unsigned)(kmin >> 32);
+    hi32 = __reduce_min_sync(0xffffffffu, hi32);
+    lo32 = __reduce_min_sync(0xffffffffu, ((unsigned)(kmin >> 32) == hi32) ? lo32 : 0xffffffffu);
+    kmin = ((unsigned long long)hi32 << 32) | lo32;
+    lo32 = (unsigned)kmax; hi32 = (unsigned)(kmax >> 32);
+    hi32 = __reduce_max_sync(0xffffffffu, hi32);
+    lo32 = __reduce_max_sync(0xffffffffu, ((unsigned)(kmax >> 32) == hi32) ? lo32 : 0u);
+    kmax = ((unsigned long long)hi32 << 32) | lo32;
   }
-  if (!(done1 && done2)) {
-    int b1 = 0, b2 = 0;
+  // Two selections run side by side: s = 0 takes the need[0] = nei smallest, s = 1 separates the need[1] = n - nei smallest
+  // from the nei largest.  State per selection: the digits fixed so far (prefix under pmask) and `below` = how many elements
+  // are smaller than every remaining candidate.  A selection ends either on a key boundary with exactly need[s] elements
+  // under it (exact), or -- equal values straddle the split -- on the order statistic itself after the last digit.
+  unsigned long long prefix[2], pmask[2], bound[2] = { 0ull, 0ull };
+  int below[2] = { 0, 0 };
+  const int need[2] = { nei, n - nei };
+  bool done[2] = { false, false }, exact[2] = { false, false };
+  const unsigned long long diff = kmin ^ kmax;
+  int lo = 0, w = 0;                                  // current digit: bits [lo, lo + w)
+  if (diff == 0ull) { done[0] = done[1] = true; bound[0] = bound[1] = kmin; prefix[0] = prefix[1] = pmask[0] = pmask[1] = 0ull; }
+  else {
+    const int top = 63 - __clzll((long long)diff);    // highest bit in which the band's keys differ
+    lo = max(0, top - 7); w = top - lo + 1;
+    const unsigned long long hm = (top >= 63) ? 0ull : (~0ull << (top + 1));
+    prefix[0] = prefix[1] = kmin & hm; pmask[0] = pmask[1] = hm;
+  }
+  while (!(done[0] && done[1])) {
+    const bool shared = !done[0] && !done[1] && prefix[0] == prefix[1];     // same candidates: one histogram serves both
+    for (int q = lane; q < 512; q += 32) hist[q] = 0;
+    __syncwarp();
+    const unsigned dm = (1u << w) - 1u;
 #pragma unroll
-    for (int c = 0; c < C; ++c) { b1 += (hi[c] < p1h) ? 1 : 0; b2 += (hi[c] < p2h) ? 1 : 0; }
-    b1 = __reduce_add_sync(0xffffffffu, b1); b2 = __reduce_add_sync(0xffffffffu, b2);
-    for (int bit = 31; bit >= 0 && !(done1 && done2); --bit) {
-      const unsigned a1 = p1l | (1u << bit), a2 = p2l | (1u << bit);
-      int c1 = 0, c2 = 0;
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        c1 += (hi[c] == p1h && lo[c] < a1) ? 1 : 0;
-        c2 += (hi[c] == p2h && lo[c] < a2) ? 1 : 0;
+    for (int c = 0; c < C; ++c) {
+      if (lane + 32 * c < n) {
+        const int d = (int)((unsigned)(u[c] >> lo) & dm);
+        if (!done[0] && (u[c] & pmask[0]) == prefix[0]) atomicAdd(&hist[d], 1);
+        if (!shared && !done[1] && (u[c] & pmask[1]) == prefix[1]) atomicAdd(&hist[256 + d], 1);
       }
-      c1 = b1 + __reduce_add_sync(0xffffffffu, c1); c2 = b2 + __reduce_add_sync(0xffffffffu, c2);
-      if (!done1) { if (c1 == nei) { done1 = true; t1h = p1h; t1l = a1; } else if (c1 <= r1) p1l = a1; }
-      if (!done2) { if (c2 == r2) { done2 = true; t2h = p2h; t2l = a2; } else if (c2 <= r2) p2l = a2; }
     }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (done[s]) continue;                            // warp-uniform
+      const int* h = hist + ((s == 1 && !shared) ? 256 : 0);
+      int cnt[8]; int tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { cnt[q] = h[lane * 8 + q]; tot += cnt[q]; }
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int pv = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += pv; }
+      const int k = need[s] - below[s];                 // the k smallest candidates are taken, 1 <= k <= candidates
+      int run = inc - tot, digit = -1, under = 0, inb = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { if (digit < 0 && cnt[q] > 0 && k > run && k <= run + cnt[q]) { digit = lane * 8 + q; under = run; inb = cnt[q]; } run += cnt[q]; }
+      const int src = __ffs(__ballot_sync(0xffffffffu, digit >= 0)) - 1;
+      digit = __shfl_sync(0xffffffffu, digit, src); under = __shfl_sync(0xffffffffu, under, src); inb = __shfl_sync(0xffffffffu, inb, src);
+      const unsigned long long dk = prefix[s] | ((unsigned long long)digit << lo);
+      if (under + inb == k) {                           // the bucket ends exactly at the split: everything up to it is taken
+        done[s] = true; exact[s] = true; bound[s] = dk + (1ull << lo);      // keys < bound: exactly need[s] elements (finite keys: no wrap)
+      } else if (lo == 0) {                             // last digit: dk is the order statistic, equal values straddle the split
+        done[s] = true; bound[s] = dk;
+      } else {
+        below[s] += under; prefix[s] = dk; pmask[s] |= (unsigned long long)dm << lo;
+      }
+    }
+    const int nlo = max(0, lo - 8);
+    w = lo - nlo; lo = nlo;
   }
-  const unsigned long long T1 = done1 ? (((unsigned long long)t1h << 32) | t1l) : (((unsigned long long)p1h << 32) | p1l);
-  const unsigned long long T2 = done2 ? (((unsigned long long)t2h << 32) | t2l) : (((unsigned long long)p2h << 32) | p2l);
-  int nl = 0, ngt = 0; double sl = 0.0, sge = 0.0, sgt = 0.0;
+  // sums over the band with the two bounds
+  int nlt0 = 0, ngt1 = 0; double slt0 = 0.0, sge1 = 0.0, sgt1 = 0.0;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    const unsigned long long u = ((unsigned long long)hi[c] << 32) | lo[c];
-    const bool valid = (lane + 32 * c) < n;
-    if (valid && u < T1) { ++nl; sl += x[c]; }
-    if (valid && u >= T2) sge += x[c];
-    if (valid && u > T2) { ++ngt; sgt += x[c]; }
+    if (lane + 32 * c < n) {
+      if (u[c] < bound[0]) { ++nlt0; slt0 += x[c]; }
+      if (u[c] >= bound[1]) sge1 += x[c];
+      if (u[c] > bound[1]) { ++ngt1; sgt1 += x[c]; }
+    }
   }
-  nl = __reduce_add_sync(0xffffffffu, nl); ngt = __reduce_add_sync(0xffffffffu, ngt);
-  sl = warp_sum(sl); sge = warp_sum(sge); sgt = warp_sum(sgt);
+  nlt0 = __reduce_add_sync(0xffffffffu, nlt0); ngt1 = __reduce_add_sync(0xffffffffu, ngt1);
+  slt0 = warp_sum(slt0); sge1 = warp_sum(sge1); sgt1 = warp_sum(sgt1);
   if (lane == 0) {
-    out3[0] = done1 ? sl : sl + (double)(nei - nl) * __longlong_as_double((long long)T1);
-    out3[1] = done2 ? sge : sgt + (double)(nei - ngt) * __longlong_as_double((long long)T2);
+    out3[0] = exact[0] ? slt0 : slt0 + (double)(nei - nlt0) * __longlong_as_double((long long)bound[0]);
+    out3[1] = exact[1] ? sge1 : sgt1 + (double)(nei - ngt1) * __longlong_as_double((long long)bound[1]);
     out3[2] = (double)cplx;
   }
 }
 
 __global__ void __launch_bounds__(BT, 6) k_bands_select(AfxBatchDev B, AfxParams P)
 {
+  __shared__ int hists[BT / 32][512];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int* hist = hists[wid];
   const int rel = blockIdx.x * 8 + wid;
   if (rel >= B.g_slots) return;
   const int slot = B.slot0 + rel;
@@ -159,14 +198,42 @@ __global__ void __launch_bounds__(BT, 6) k_bands_select(AfxBatchDev B, AfxParams
   const double* __restrict__ g = B.mag + (size_t)rel * AFX_NBIN;
   double* out = B.bandraw + (size_t)rel * BR2_STRIDE;
   switch (blockIdx.y) {                         // heaviest band first in launch order (grid y is the slow index)
-    case 0: subband_select<9>(P, 13, g, lane, out + 12); break;
-    case 1: subband_select<5>(P, 12, g, lane, out + 9); break;
-    case 2: subband_select<3>(P, 11, g, lane, out + 6); break;
-    default: subband_select<2>(P, 10, g, lane, out + 3); subband_select<2>(P, 9, g, lane, out); break;
+    case 0: subband_select<9>(P, 13, g, lane, hist, out + 12); break;
+    case 1: subband_select<5>(P, 12, g, lane, hist, out + 9); break;
+    case 2: subband_select<3>(P, 11, g, lane, hist, out + 6); break;
+    default: subband_select<2>(P, 10, g, lane, hist, out + 3); subband_select<2>(P, 9, g, lane, hist, out); break;
   }
 }
 
 #define BLW 4               // warps per CTA of k_bands_lane (128 frame slots)
+
+// finish sub-band b of one frame (lane-local): order statistics / peak count of a small band from the lane's value array
+// (vals[0] and vals[n + 1] are the band's neighbours), of a large band from k_bands_select's record; epilogue; returns the contrast
+__device__ __forceinline__ double lane_finish_band(AfxBatchDev& B, const AfxParams& P, size_t TF, int slot, int rel, int b, bool live,
+                                                   const double* vals, BandRaw& r, double mx)
+{
+  const int n = P.band14_n[b], nei = P.band14_nei[b];
+  if (n <= 32) {
+    const double thr = 0.25 * mx;
+    int cplx = 0;
+    double lo_sum = 0.0, hi_sum = 0.0;
+    for (int i = 1; i <= n; ++i) {
+      const double vi = vals[i];
+      if (thr > 0.0 && vi > thr && vi > vals[i - 1] && vi > vals[i + 1]) ++cplx;
+      int rank = 0;                             // position of vals[i] in the sorted band (ties in index order)
+      for (int m = 1; m <= n; ++m) { const double vm = vals[m]; rank += (vm < vi || (vm == vi && m < i)) ? 1 : 0; }
+      if (rank < nei) lo_sum += vi;
+      if (rank >= n - nei) hi_sum += vi;
+    }
+    r.lo_sum = lo_sum; r.hi_sum = hi_sum; r.cplx = (double)cplx;
+  } else {
+    const double* br = B.bandraw + (size_t)rel * BR2_STRIDE + (b - BIG0) * 3;
+    r.lo_sum = br[0]; r.hi_sum = br[1]; r.cplx = br[2];
+  }
+  r.x0 = (n >= 2) ? r.x0 : vals[1];
+  return live ? band_write(B, TF, slot, b, n, nei, r) : 0.0;
+}
+
 __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParams P)
 {
   __shared__ double tiles[BLW][32][33];
@@ -174,9 +241,10 @@ __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParam
   const int rel0 = (blockIdx.x * BLW + wid) * 32;
   if (rel0 >= B.g_slots) return;                // warp-uniform
   double (*tile)[33] = tiles[wid];
-  const int rel = rel0 + lane;
-  const bool in_range = rel < B.g_slots;
-  const int slot = B.slot0 + (in_range ? rel : rel0);
+  const int rel_raw = rel0 + lane;
+  const bool in_range = rel_raw < B.g_slots;
+  const int rel = in_range ? rel_raw : rel0;
+  const int slot = B.slot0 + rel;
   const int fi = B.slot_file[slot];
   const int t = slot - B.files[fi].frame_off;
   const bool live = in_range && B.files[fi].status == 0 && t < B.state[fi].F;
@@ -185,88 +253,76 @@ __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParam
   const double* __restrict__ mag = B.mag;
   const int last_row = B.g_slots - 1;
 
-  // running state of the walk over the bins
-  int b = 0, bs = P.band14_start[0], be = bs + P.band14_n[0];
-  double s1 = 0, s2 = 0, s11 = 0, s12 = 0, s22 = 0, mx = 0, mant = 1.0; int ex = 0;
-  double vals[34];                              // a small band with its two neighbours: vals[0] = x[bs - 1], vals[1 + i] = x[bs + i]
-  double xprev = 0.0;
-  int b28 = 0; double acc28 = 0.0;
+  // state of the walk.  Everything that changes along the bin axis is constant inside a segment (AfxBandSeg, built by
+  // afx_create), so the per-bin loop below is straight arithmetic.
+  double s1 = 0, s2 = 0, s11 = 0, s12 = 0, s22 = 0, mx = 0, mant = 1.0; int ex = 0, nv = 0;
+  double vals[34];                              // a small band with its two neighbours: vals[0] = x[start - 1], vals[1 + i] = x[start + i]
+  double xprev = 0.0, a28 = 0.0, csum = 0.0;
   double mel[14];
 #pragma unroll
   for (int q = 0; q < 14; ++q) mel[q] = 0.0;
-  int qlo = 0;                                  // first mel filter whose support has not ended
-  double csum = 0.0;
+  int pending = -1;                             // sub-band waiting for its right neighbour
+  BandRaw pend; double pend_mx = 0.0;
+  pend.s1 = pend.s2 = pend.s11 = pend.s12 = pend.s22 = pend.ls = pend.x0 = pend.lo_sum = pend.hi_sum = pend.cplx = 0.0;
 
-  for (int kb = 0; kb < AFX_NBIN; kb += 32) {
-    // the tile: rows rel0 - 1 .. rel0 + 31, bins kb .. kb + 31; lane = bin on the way in, lane = frame on the way out
-#pragma unroll 11
-    for (int c = 0; c < 33; ++c) {
-      const int rc = min(max(rel0 - 1 + c, 0), last_row);
-      tile[lane][c] = mag[(size_t)rc * AFX_NBIN + kb + lane];
-    }
-    __syncwarp();
+  const AfxBandSeg* __restrict__ segs = P.t.band_segs;
+  const int nseg = P.t.n_band_segs;
 #pragma unroll 1
-    for (int j = 0; j < 32; ++j) {
-      const int k = kb + j;                     // uniform
-      const double x = tile[j][lane + 1];
-      const double y = has_prev ? tile[j][lane] : x;
-      // ---- 28 frequency bands (SampleAnalyser.cpp:2007-2048) ----
-      while (b28 < 28 && k >= P.band28_e[b28]) {
-        if (live) B.fv[(size_t)FV_BANDS28 * TF + (size_t)slot * 28 + b28] = acc28;
-        acc28 = 0.0; ++b28;
+  for (int si = 0; si < nseg; ++si) {
+    const AfxBandSeg sg = segs[si];             // uniform
+    const int k0 = sg.k0, k1 = sg.k1;
+    if ((k0 & 31) == 0) {
+      // the tile: rows rel0 - 1 .. rel0 + 31, bins k0 .. k0 + 31; lane = bin on the way in, lane = frame on the way out
+      __syncwarp();
+#pragma unroll 11
+      for (int c = 0; c < 33; ++c) {
+        const int rc = min(max(rel0 - 1 + c, 0), last_row);
+        tile[lane][c] = mag[(size_t)rc * AFX_NBIN + k0 + lane];
       }
-      if (b28 < 28 && k >= P.band28_s[b28]) acc28 = fma(x, x, acc28);
-      // ---- mel energies on the filters' supports (vector.c:350-391) ----
-      while (qlo < 14 && k > P.mel_hi[qlo]) ++qlo;
-      for (int q = qlo; q < 14 && P.mel_lo[q] <= k; ++q) mel[q] = fma(x, __ldg(P.t.mel + (size_t)q * AFX_NBIN + k), mel[q]);
-      // ---- 14 sub-bands (SampleAnalyser.cpp:2067-2260) ----
-      if (b < 14 && k == be) {
-        // band b is complete and x is its right neighbour
-        const int n = be - bs, nei = P.band14_nei[b];
-        BandRaw r;
-        r.s1 = s1; r.s2 = s2; r.s11 = s11; r.s12 = s12; r.s22 = s22; r.ls = mant; r.x0 = (n >= 2) ? (double)ex : vals[1];
-        if (n <= 32) {
-          vals[n + 1] = x;
-          const double thr = 0.25 * mx;
-          int cplx = 0;
-          double lo_sum = 0.0, hi_sum = 0.0;
-          for (int i = 1; i <= n; ++i) {
-            const double vi = vals[i];
-            if (thr > 0.0 && vi > thr && vi > vals[i - 1] && vi > vals[i + 1]) ++cplx;
-            int rank = 0;                         // position of vals[i] in the sorted band (ties in index order)
-            for (int m = 1; m <= n; ++m) { const double vm = vals[m]; rank += (vm < vi || (vm == vi && m < i)) ? 1 : 0; }
-            if (rank < nei) lo_sum += vi;
-            if (rank >= n - nei) hi_sum += vi;
-          }
-          r.lo_sum = lo_sum; r.hi_sum = hi_sum; r.cplx = (double)cplx;
-        } else {
-          const double* br = B.bandraw + (size_t)(in_range ? rel : rel0) * BR2_STRIDE + (b - BIG0) * 3;
-          r.lo_sum = br[0]; r.hi_sum = br[1]; r.cplx = br[2];
-        }
-        if (live) csum += band_write(B, TF, slot, b, n, nei, r);
-        ++b;
-        if (b < 14) { bs = P.band14_start[b]; be = bs + P.band14_n[b]; }
-        s1 = s2 = s11 = s12 = s22 = 0.0; mx = 0.0; mant = 1.0; ex = 0;
-      }
-      if (b < 14 && k >= bs) {
-        if (k == bs) vals[0] = xprev;
+      __syncwarp();
+    }
+    const bool in14 = sg.b14 >= 0, in28 = sg.b28 >= 0;
+    const bool small14 = in14 && P.band14_n[sg.b14] <= 32;
+    double e0 = 0.0, e1 = 0.0;
+    const double* __restrict__ w0 = P.t.mel + (size_t)(sg.q0 < 0 ? 0 : sg.q0) * AFX_NBIN;
+    const double* __restrict__ w1 = w0 + AFX_NBIN;
+    if (pending >= 0) {                         // the first bin of this segment is the right neighbour of the band that just ended
+      vals[nv + 1] = tile[k0 & 31][lane + 1];
+      csum += lane_finish_band(B, P, TF, slot, rel, pending, live, vals, pend, pend_mx);
+      pending = -1;
+    }
+    if (sg.start14) { s1 = s2 = s11 = s12 = s22 = 0.0; mx = 0.0; mant = 1.0; ex = 0; nv = 0; vals[0] = xprev; }
+    double x = xprev;
+#pragma unroll 2
+    for (int k = k0; k < k1; ++k) {
+      x = tile[k & 31][lane + 1];
+      const double y = has_prev ? tile[k & 31][lane] : x;
+      if (in14) {                               // SampleAnalyser.cpp:2067-2260
         s12 = fma(x, y, s12); s1 += x; s11 = fma(x, x, s11); s2 += y; s22 = fma(y, y, s22);
         mx = fmax(mx, x);
         const double v = fabs(x) + 1e-20;            // Statistics.cpp:417-455: product with the exponents peeled off
         const int hw = __double2hiint(v);            // (<= 287 factors >= 1/2: the mantissa product cannot underflow)
         ex += ((hw >> 20) & 0x7ff) - 1022;
         mant *= __hiloint2double((hw & 0x800fffff) | 0x3fe00000, __double2loint(v));
-        if (k - bs < 32) vals[k - bs + 1] = x;
+        if (small14) vals[++nv] = x;
       }
-      xprev = x;
+      if (in28) a28 = fma(x, x, a28);           // SampleAnalyser.cpp:2007-2048
+      if (sg.nq > 0) e0 = fma(x, __ldg(w0 + k), e0);      // vector.c:350-391, on the filters' supports
+      if (sg.nq > 1) e1 = fma(x, __ldg(w1 + k), e1);
     }
-    __syncwarp();
+    xprev = x;
+    if (sg.nq > 0) mel[sg.q0] += e0;
+    if (sg.nq > 1) mel[sg.q0 + 1] += e1;
+    if (sg.end28) { if (live) B.fv[(size_t)FV_BANDS28 * TF + (size_t)slot * 28 + sg.b28] = a28; a28 = 0.0; }
+    if (sg.end14) {
+      pend.s1 = s1; pend.s2 = s2; pend.s11 = s11; pend.s12 = s12; pend.s22 = s22; pend.ls = mant; pend.x0 = (double)ex; pend_mx = mx;
+      pending = sg.b14;
+    }
   }
-  while (b28 < 28) {                             // bands that run to the end of the row
-    if (live) B.fv[(size_t)FV_BANDS28 * TF + (size_t)slot * 28 + b28] = acc28;
-    acc28 = 0.0; ++b28;
-  }
+  if (pending >= 0) { vals[nv + 1] = 0.0; csum += lane_finish_band(B, P, TF, slot, rel, pending, live, vals, pend, pend_mx); }
   if (!live) return;
+  for (int b = 0; b < 28; ++b)                   // bands that lie beyond the spectrum hold no bins (SampleAnalyser.cpp:2026-2045)
+    if (P.band28_e[b] <= P.band28_s[b]) B.fv[(size_t)FV_BANDS28 * TF + (size_t)slot * 28 + b] = 0.0;
   // ---- cepstrum: log of the mel energies, unnormalised DCT-II in the reference's order (vector.c:372-391) ----
   double lg[14];
 #pragma unroll

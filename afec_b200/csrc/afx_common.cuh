@@ -88,6 +88,15 @@ struct AfxState {           // device-computed, one per file (SampleAnalyser.cpp
   int L, F, Fr, data_offset;
 };
 
+// One run of consecutive bins inside which nothing changes for k_bands_lane (afx_bands.cu): the sub-band, the frequency
+// band and the (at most two) mel filters that cover it are constant, and the run does not cross a 32-bin tile.
+struct AfxBandSeg {
+  short k0, k1;             // bins [k0, k1)
+  signed char b14, b28;     // sub-band / frequency band of the run, -1 = none
+  signed char q0, nq;       // first mel filter covering the run and how many (0..2)
+  unsigned char start14, end14, end28, pad;   // the run starts / ends its sub-band, ends its frequency band
+};
+
 struct AfxTables {          // per-context constant tables in device memory
   const double* window;     // [2048] Hann * 2
   const double2* tw2048;    // [2048] exp(-2 pi i k / 2048)
@@ -102,6 +111,8 @@ struct AfxTables {          // per-context constant tables in device memory
   const float* rs_imp;      // [69632] resampler wing
   unsigned int* work_ctr;   // [64] work-claim counters of the persistent kernels (zeroed on the launching stream)
   double* hl_pad;           // [21] last-frame values of a silent sample, written by afx_create (AFX_FEAT_HIGHLEVEL)
+  const AfxBandSeg* band_segs;   // [n_band_segs] the walk of k_bands_lane over the 1024 bins
+  int n_band_segs;
 };
 
 struct AfxParams {

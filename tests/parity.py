@@ -23,6 +23,13 @@ instead of Ooura would disagree with itself):
     FFT's rounding; the frame's flatness is then 1e-16-sized noise around 0, which the geometric-mean statistics of the
     flatness series (gmean, flatness = gmean / mean) amplify.  Found by profiles/parity_sweep.py; the reference built
     with another FFT disagrees with itself on these frames in the same way.
+  * the geometric mean (and flatness = gmean / mean) of a series that holds values at the FP-noise level: TStatistics::
+    GeometricMean sums log(|x| + 1e-20) (Statistics.cpp:417-455), so a frame value of 0 against 1e-17 -- both "zero" to
+    eleven orders below the absolute tolerance, e.g. f0_confidence = (1 - yin') / 0.25 where yin' rounds to 1, or the flatness
+    of a two-bin band whose bins are equal -- moves the log sum by 7 / n.  When the two series differ at an element below
+    1e-9, these two statistics of the CUDA path are checked against the oracle's TStatistics restatement applied to the
+    series the CUDA path itself produced (as for the noise-determined frames above), not against the reference's.
+    Found by profiles/parity_sweep.py (round 2, seeds 7114 and 8030).
 Derived tolerance: the statistic flatness = gmean / mean (Statistics.cpp:69-72) is compared with the tolerance
 its two inputs carry, |fl| * (tol(gmean) / |gmean| + tol(mean) / |mean|), on top of its own -- a gmean that
 agrees to the absolute tolerance (series with many FP-noise values around 0, e.g. DCT rows of silent frames)
@@ -136,6 +143,13 @@ def stat_rules(ok, x, b):
     return ok
 
 
+def log_domain_noise(got_series, want_series) -> bool:
+    """True when the two series differ at an element that is below 1e-9 in either of them (see the module docstring)."""
+    a, b = np.asarray(got_series, dtype=np.float64), np.asarray(want_series, dtype=np.float64)
+    tiny = (np.abs(a) < 1e-9) | (np.abs(b) < 1e-9)
+    return bool(np.any(tiny & (a != b)))
+
+
 def flatness_tol(a, b, ok):
     if b[3] != 0.0 and b[4] != 0.0:          # flatness = gmean / mean with its inputs' tolerances
         tol = ATOL + RTOL * abs(b[10]) + abs(b[10]) * ((ATOL + RTOL * abs(b[4])) / abs(b[4]) +
@@ -166,6 +180,11 @@ def compare_stats(got, want, skip_series=(), only_series=None, ill_pitch=None, i
         ok = close(a, b)
         ok = flatness_tol(a, b, ok)
         ok = stat_rules(ok, x, b)
+        if not noise and not (ok[4] and ok[10]) and log_domain_noise(gs[n], x):
+            from oracle import oracle
+            own = oracle.stats13(np.ascontiguousarray(gs[n], dtype=np.float64))
+            ok2 = flatness_tol(a, own, close(a, own))
+            ok[4], ok[10] = ok2[4], ok2[10]
         if not ok.all():
             k = int(np.argwhere(~ok)[0][0])
             errs.append("stat %s_%s%s: %r != %r" % (n, layout.STAT_NAMES[k], " (of the produced series)" if noise else "", a[k], b[k]))

@@ -36,3 +36,17 @@ def test_close_uses_the_stated_tolerance():
     assert parity.close(1.0 + 0.9e-4, 1.0) and not parity.close(1.0 + 1.2e-4, 1.0)
     assert parity.close(5e-7, 0.0) and not parity.close(2e-6, 0.0)
     assert parity.close(np.nan, np.nan)
+
+
+def test_log_domain_noise_rule_only_fires_on_sub_tolerance_differences():
+    a = np.array([0.5, 0.25, 0.0, 0.75])
+    assert not parity.log_domain_noise(a, a.copy())                       # identical, zeros included
+    b = a.copy(); b[2] = 1e-17
+    assert parity.log_domain_noise(a, b) and parity.log_domain_noise(b, a)
+    c = a.copy(); c[1] = 0.2500001                                         # an ordinary difference is not "noise"
+    assert not parity.log_domain_noise(a, c)
+    # and the geometric mean really is that sensitive: 0 against 1e-17 in one of 200 frames moves it by percents
+    from oracle import oracle
+    x = np.full(200, 0.5); y = x.copy(); x[7] = 0.0; y[7] = 1e-17
+    gx, gy = oracle.stats13(x)[4], oracle.stats13(y)[4]
+    assert abs(gx - gy) > 1e-2 * gx and parity.close(x, y).all()
