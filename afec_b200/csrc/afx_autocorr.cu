@@ -61,15 +61,15 @@ __device__ __forceinline__ double ac_rounds(const double* __restrict__ x, int wi
 }
 
 // FP32 form of the same tiling (round 2, "precision demotion"): R[i] / R[0] does not depend on the file's scale, so the
-// window is taken as the RAW float32 mono samples (exact), a lane owns 16 lags (two shared-memory loads feed 16 FFMAs on
+// window is taken as the RAW float32 mono samples (exact), a lane owns 17 lags (two shared-memory loads feed 17 FFMAs on
 // the pipe that is twice as wide as the FP64 one) and a round's partial sums -- at most 133 products each -- stay in FP32;
 // they are widened to FP64 before the four lanes of a group and the rounds are combined.  Rounding analysis: the error of
 // a partial sum is ~ eps sqrt(n) |s| / 3 ~ 2e-7 |s| with |s| <= R[0] / 4, i.e. <= 1e-7 of R[0], against a tolerance of
 // 1e-6 + 1e-4 |v| on v = R[i] / R[0] in [0, 1]; nothing downstream of this value is a threshold (it is a maximum over lags,
 // then temporal statistics).  Measured against the FP64 kernel: profiles/README.md.  AFX_AUTOCORR_FP64=1 keeps the FP64 form.
-#define ALF 16              // lags per lane task
+#define ALF 17              // lags per lane task (odd: the lag groups and the quarters of a group then start on different banks)
 #define ACF_XS 768          // floats: window + zero padding
-#define ACF_ZERO 592        // idle lanes read zeros from here (a round reads at most 133 + 16 samples)
+#define ACF_ZERO 592        // idle lanes read zeros from here (a round reads at most 136 + 34 samples)
 __device__ __forceinline__ double ac_rounds_f32(const float* __restrict__ x, int width, int G, int lane, int lo, double& r0)
 {
   const int sub = lane & 3, gl = lane >> 2;
@@ -86,14 +86,15 @@ __device__ __forceinline__ double ac_rounds_f32(const float* __restrict__ x, int
     float acc[ALF], w[ALF];
 #pragma unroll
     for (int q = 0; q < ALF; ++q) { acc[q] = 0.0f; w[q] = xw[q]; }
-    // sixteen steps per trip with the window registers addressed modulo 16: register u holds x[.. + u] until step u has
-    // used it, then takes the sample 16 further on -- the window slides without a single register move
+    // ALF steps per trip with the window registers addressed modulo ALF: register u holds x[.. + u] until step u has
+    // used it, then takes the sample ALF further on -- the window slides without a single register move.  (With 16 lags
+    // per lane every group started on bank 0 or 16: 24 ns per frame instead of 12.)
     for (int jj = 0; jj < len; jj += ALF) {
 #pragma unroll
       for (int u = 0; u < ALF; ++u) {
         const float a = xa[jj + u];
 #pragma unroll
-        for (int q = 0; q < ALF; ++q) acc[q] = fmaf(a, w[(q + u) & (ALF - 1)], acc[q]);
+        for (int q = 0; q < ALF; ++q) acc[q] = fmaf(a, w[(q + u) % ALF], acc[q]);
         w[u] = xw[jj + u + ALF];
       }
     }
