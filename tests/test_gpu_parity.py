@@ -334,6 +334,22 @@ def test_rhythm_front_end_fused_equals_split(feats, monkeypatch, oracle_lib):
             check(g, oracle_lib.analyze(p, file_size=44 + p.size * p.itemsize), feats, mdata=oracle_lib.condition(p)[0])
 
 
+def test_peaks_fused_equals_split(feats):
+    """The whitening + peak count has a fused per-file form (AFX_PEAKS_FUSED=1, afx_peaks.cu); it must give the same counts."""
+    import subprocess
+    import sys
+    code = ("import sys, numpy as np; sys.path.insert(0, '.'); from afec_b200 import api, synth\n"
+            "pcms = [synth.one_shot(840 + i, 0.3 + 0.9 * i) for i in range(6)] + [np.zeros(30000, dtype=np.int16), synth.one_shot(850, 0.02)]\n"
+            "an = api.SampleAnalyser(44100, 2048, 1024, features=%d)\n"
+            "r = an.analyze_pcm(pcms, [44100] * len(pcms))\n"
+            "print(';'.join(','.join('%%d' %% v for v in x.series('spectral_complexity')) for x in r))" % feats)
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = [subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, AFX_PEAKS_FUSED=m), capture_output=True, text=True,
+                           check=True).stdout for m in ("0", "1")]
+    assert outs[0] == outs[1] and outs[0].count(",") > 100
+
+
 def test_resampled_batch_vs_oracle(analysers, feats, oracle_lib):
     """Files at other rates go through the libresample restatement (SampleAnalyser.cpp:563-607)."""
     cases = [(synth.one_shot(900, 0.5, rate=96000, channels=2), 96000), (synth.one_shot(901, 0.6, rate=22050), 22050),
