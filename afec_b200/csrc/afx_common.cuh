@@ -300,6 +300,7 @@ struct AfxBatchDev {
   double* header;     // [n_files][32]
   double* scratch;    // [g_rslots][4] rhythm back-end workspace (group scratch)
   int max_fr;         // largest rhythm frame capacity of any file in the batch
+  int pitch_generic;  // AFX_PITCH_GENERIC=1: the general 2048-point pitch kernel also at hop 1024 (else the block-sharing form)
   int rhythm_fused;   // this launch group's rhythm front end runs as ONE kernel with a CTA per file (k_rhythm_front); else the split kernels over rpolar
 };
 

@@ -85,6 +85,7 @@ struct afx_ctx {
   // SM every phase of the fused kernel is latency bound on its own), so it is off unless AFX_RHYTHM_FUSED=1 asks for it
   // (AFX_RHYTHM_FUSED=0 / 1 forces never / always: the parity test compares the two schedules)
   int rhythm_fused_min = 0x7fffffff;
+  bool pitch_generic = false;
   bool rhythm_fused(int g_files) const { return g_files >= rhythm_fused_min; }
   struct afx_batch* live = nullptr;   // the one batch whose data occupies the device buffers (afx_batch_upload .. afx_batch_free)
 };

@@ -644,6 +644,10 @@ def main():
                      "tflops": gflops.get(g, 0.0) / (ms * 1e-3) / 1e12 if ms > 0 else None,
                      "frac_fp64": gflops.get(g, 0.0) / (ms * 1e-3) / 1e12 / fp64_peak if ms > 0 and fp64_peak else None}
                  for g, ms in groups.items()}
+        # the autocorrelation multiplies in FP32 since round 2 (unless AFX_AUTOCORR_FP64=1): its pipe is the FP32 one
+        if "autocorr" in table and table["autocorr"]["tflops"] is not None and os.environ.get("AFX_AUTOCORR_FP64", "0") in ("", "0"):
+            table["autocorr"]["pipe"] = "fp32"
+            table["autocorr"]["frac_fp32_nominal"] = table["autocorr"]["tflops"] / FP32_NOMINAL_TFLOPS
         top_tf = gflops.get(top, 0.0) / (top_ms * 1e-3) / 1e12
         step_ms = dev_ms / args.steps                     # this rank's multi-stream step (the `value` timing)
         step_tf = step_flops / (step_ms * 1e-3) / 1e12
@@ -652,8 +656,9 @@ def main():
             "traffic": None, "kernel": top, "kernel_ms": top_ms, "kernel_share_of_step": top_ms / sum(groups.values()),
             "peak_source": "measured live: dependent-free DFMA loop (afx_measure_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure",
             "algorithmic_flops": gflops.get(top, 0.0), "frames_per_launch": frames, "rhythm_frames_per_launch": rframes,
-            "note": "every frame kernel computes in FP64 (bit-for-bit decisions of the reference: peak counts, onset thresholds); "
-                    "achieved = SURVEY.md 8(d) algorithmic flops of the group / its CUDA-event time",
+            "note": "the frame kernels compute in FP64 (bit-for-bit decisions of the reference: peak counts, onset thresholds) except the "
+                    "autocorrelation products (FP32, see groups.autocorr.pipe); achieved = SURVEY.md 8(d) algorithmic flops of the group / "
+                    "its CUDA-event time",
             "step": {"algorithmic_flops": step_flops, "ms": step_ms, "achieved": step_tf, "unit": "TFLOP/s",
                      "frac_fp64": step_tf / fp64_peak if fp64_peak else None, "frac_fp32_nominal": step_tf / FP32_NOMINAL_TFLOPS,
                      "flops_per_main_frame": step_flops / max(1, frames)},

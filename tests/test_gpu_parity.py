@@ -334,6 +334,35 @@ def test_rhythm_front_end_fused_equals_split(feats, monkeypatch, oracle_lib):
             check(g, oracle_lib.analyze(p, file_size=44 + p.size * p.itemsize), feats, mdata=oracle_lib.condition(p)[0])
 
 
+def test_pitch_block_sharing_form_vs_general(feats, monkeypatch, oracle_lib):
+    """At hop 1024 the pitch kernel shares one block transform between consecutive frames (k_pitch_hop, afx_pitch.cu); the
+    general 2048-point kernel (AFX_PITCH_GENERIC=1, every other hop) computes the same correlation another way.  Both
+    must meet the oracle; against each other they agree to rounding on every frame the parity rules do not release
+    (runs start at chunk and file boundaries: long files, short files, dead slots and padding are all in the batch)."""
+    pcms = [synth.one_shot(860 + i, 0.25 + 0.5 * i) for i in range(8)]
+    pcms += [synth.one_shot(870, 23.0), synth.one_shot(871, 0.02), np.zeros(40000, dtype=np.int16),
+             synth.one_shot(872, 1.3, channels=2), np.zeros((0,), dtype=np.int16), synth.one_shot(873, 0.1),
+             synth.one_shot(874, 6.0, rate=48000)]
+    rates = [44100] * (len(pcms) - 1) + [48000]
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("AFX_PITCH_GENERIC", mode)
+        an = api.SampleAnalyser(44100, 2048, 1024, features=feats)
+        out[mode] = an.analyze_pcm(pcms, rates)
+        an.close()
+    n_frames = 0
+    for g, w, p, r in zip(out["0"], out["1"], pcms, rates):
+        assert g.status == w.status and (g.F, g.Fr) == (w.F, w.Fr)
+        if g.status != 0:
+            continue
+        want = oracle_lib.analyze(p, src_rate=r, file_size=44 + p.size * p.itemsize)
+        mdata = oracle_lib.condition(p, src_rate=r)[0]
+        check(g, want, feats, mdata=mdata)
+        check(w, want, feats, mdata=mdata)
+        n_frames += g.F
+    assert n_frames > 1500
+
+
 def test_peaks_fused_equals_split(feats):
     """The whitening + peak count has a fused per-file form (AFX_PEAKS_FUSED=1, afx_peaks.cu); it must give the same counts."""
     import subprocess
