@@ -102,11 +102,12 @@ __device__ __forceinline__ double2 fft_tw_load(const double2* p) { return TW_SME
 // T3STEP: the N = 1024 third pass may read its twiddles from the N = 2048 table (exp(-2 pi i r j / 1024) is row 2r of
 // exp(-2 pi i r j / 2048)): T3STEP = 2 with tw.t3 pointing at the 2048 table
 //
+// T3_POWERS (N = 1024 only): the third pass derives its twiddles w^2, w^3 from w (see there).
 // HALF_OPT (N = 1024 only): with `half` set at run time the last pass keeps only outputs 0..511 and stores X[j] at
 // buf[FFT_PAD8(j)] -- a layout in which a thread can then read 8 consecutive outputs without bank conflicts (the pitch kernel
 // needs just the first half of its inverse transform, 16 consecutive lags per thread).
 #define FFT_PAD8(i) ((i) + ((i) >> 3))
-template <int N, class Sync, bool TW_SMEM = false, int T3STEP = 1, bool HALF_OPT = false>
+template <int N, class Sync, bool TW_SMEM = false, int T3STEP = 1, bool HALF_OPT = false, bool T3_POWERS = false>
 __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict__ buf, const FftTw tw, int tid, Sync sync, bool half = false)
 {
   constexpr int NT = N / 16;
@@ -141,8 +142,14 @@ __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict_
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int i = tid + NT * b;          // k = i (i < p = 256)
+      if (T3_POWERS) {                     // w, w^2, w^3 from ONE table load (two products, ~2 ulp): the kernel is short of shared-memory bandwidth
+        const double2 w1 = fft_tw_load<TW_SMEM>(tw.t3 + (T3STEP - 1) * 256 + i);
+        const double2 w2 = f_mul(w1, w1), w3 = f_mul(w2, w1);
+        v[4 * b + 1] = f_mul(v[4 * b + 1], w1); v[4 * b + 2] = f_mul(v[4 * b + 2], w2); v[4 * b + 3] = f_mul(v[4 * b + 3], w3);
+      } else {
 #pragma unroll
-      for (int r = 1; r < 4; ++r) v[4 * b + r] = f_mul(v[4 * b + r], fft_tw_load<TW_SMEM>(tw.t3 + (r * T3STEP - 1) * 256 + i));
+        for (int r = 1; r < 4; ++r) v[4 * b + r] = f_mul(v[4 * b + r], fft_tw_load<TW_SMEM>(tw.t3 + (r * T3STEP - 1) * 256 + i));
+      }
       f_r4(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {

@@ -316,12 +316,10 @@ __global__ void __launch_bounds__(YT * NG, 1) k_pitch(AfxBatchDev B, AfxParams P
 #define PADX(m) ((m) + 4 * ((m) >> 4))      // raw block: 16 consecutive floats per thread at a 20-float stride
 
 // tau / run for the cumulative-mean normalisation: reciprocal seed + Newton steps on the quotient (~1 ulp; the reference's
-// own quotient is one rounding of the same value, and nothing here is bit-exact against its FFT anyway).  Tiny or huge
-// denominators take the IEEE division.
+// own quotient is one rounding of the same value, and nothing here is bit-exact against its FFT anyway).  den is a sum of
+// differences of squared float32-derived samples: zero (handled by the caller) or far inside the normal range.
 __device__ __forceinline__ double yin_div(double num, double den)
 {
-  const double ad = fabs(den);
-  if (!(ad > 1e-290 && ad < 1e290)) return num / den;
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
   r = fma(fma(-den, r, 1.0), r, r);
@@ -334,7 +332,7 @@ struct PitchHopSmem {
   static constexpr int BUF = YW + YW / 16;                             // double2 per group (FFT_PHYS; FFT_PAD8(511) fits too)
   static constexpr int YIN = YW + YW / 16 + 8;                         // doubles: PAD16 layout (yin', I_A, I_B)
   static constexpr int XIN = YW + YW / 4;                              // floats: PADX layout
-  static constexpr size_t group_bytes = (size_t)BUF * sizeof(double2) + 3 * (size_t)YIN * sizeof(double) + (size_t)XIN * sizeof(float) + 48 * sizeof(double);
+  static constexpr size_t group_bytes = (size_t)BUF * sizeof(double2) + 2 * (size_t)YIN * sizeof(double) + (size_t)XIN * sizeof(float) + 48 * sizeof(double);
   static constexpr size_t o_t2 = (size_t)NG * group_bytes;            // [15][16]
   static constexpr size_t o_t3 = o_t2 + 240 * sizeof(double2);        // [3][256]
   static constexpr size_t o_tw = o_t3 + 3 * 256 * sizeof(double2);    // [513] exp(-2 pi i k / 2048)
@@ -370,8 +368,8 @@ __global__ void __launch_bounds__(HT * NG, 1) k_pitch_hop(AfxBatchDev B, AfxPara
   const int g = threadIdx.x / HT, tid = threadIdx.x % HT;
   unsigned char* gbase = smem_raw + (size_t)g * L::group_bytes;
   double2* buf = reinterpret_cast<double2*>(gbase);                    // packed spectrum of the new block, then Zc, then r (first half)
-  double* yin = reinterpret_cast<double*>(buf + L::BUF);               // [PAD16(1024)] yin'
-  double* I0 = yin + L::YIN;                                           // [2][PAD16(1024)] block-local inclusive sums of squares:
+  double* yin = reinterpret_cast<double*>(buf);                        // [PAD16(1024)] yin': takes the place of r once every thread holds its lags
+  double* I0 = reinterpret_cast<double*>(buf + L::BUF);                // [2][PAD16(1024)] block-local inclusive sums of squares:
                                                                        //   I0 + pp * YIN: the carried block (A), the other one: the new block
   float* xin = reinterpret_cast<float*>(I0 + 2 * L::YIN);              // [PADX(1024)] raw samples of the block to transform next (cp.async target)
   double* scratch = reinterpret_cast<double*>(xin + L::XIN);           // [8] scans / argmin
@@ -508,12 +506,13 @@ __global__ void __launch_bounds__(HT * NG, 1) k_pitch_hop(AfxBatchDev B, AfxPara
         for (int r = 0; r < 16; ++r) v[r] = buf[FFT_PHYS(tid + HT * r)];
         sync();                                                      // every input is in registers before buf is rewritten
       }
-      fft16_run<YW, FftSyncNamed<HT>, true, 1, true>(v, buf, ftw, tid, sync, step == 2);
+      fft16_run<YW, FftSyncNamed<HT>, true, 1, true, true>(v, buf, ftw, tid, sync, step == 2);
       if (step == 2) break;
       // ---- unpack bins k and 1024 - k of F_B; step 1: P, then Zc of the half-size inverse, in place ----
       // (r real => the inverse of the Hermitian P runs at half size: with z[m] = r[2m] + i r[2m+1], z = IFFT_1024(Zc),
       //  Zc[k] = (P[k] + conj(P[1024-k])) / 2 + i W^-k (P[k] - conj(P[1024-k])) / 2, W = exp(-2 pi i / 2048); every halving
       //  here and in the unpacking is left out and folded into the final scale 1 / (8 W))
+      const double2 wt = s_tw[tid];                                                       // W^k = W^tid W^(64 c): one load, seven products
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int k = tid + HT * c;
@@ -531,7 +530,11 @@ __global__ void __launch_bounds__(HT * NG, 1) k_pitch_hop(AfxBatchDev B, AfxPara
           FA[0] = fb0; FA[1] = fbh;
         } else {
           const double2 z1 = buf[FFT_PHYS(k)], z2 = buf[FFT_PHYS(YW - k)];
-          const double2 w = s_tw[k];                                                      // W^k; W^-k = conj
+          constexpr double kC[8] = { 1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
+                                     0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785 };     // cos(2 pi 64 c / 2048)
+          constexpr double kS[8] = { 0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474, 0.70710678118654752440,
+                                     0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913 };     // sin(2 pi 64 c / 2048)
+          const double2 w = (c == 0) ? wt : f_mul(wt, make_double2(kC[c], -kS[c]));       // W^k; W^-k = conj
           const double2 e = make_double2(z1.x + z2.x, z1.y - z2.y);                       // Z[k] + conj(Z[1024-k])
           const double2 d = make_double2(z1.x - z2.x, z1.y + z2.y);                       // Z[k] - conj(Z[1024-k])
           const double2 o = f_mul(w, d);
@@ -698,7 +701,7 @@ void afx_launch_pitch(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, 
   if (B.g_slots <= 0) return;
   // hop == 1024 (the reference's and BASELINE's hop): the block-sharing form; AFX_PITCH_GENERIC=1 keeps the general one
   static const int ng = [] { const char* e = getenv("AFX_PITCH_NG"); return e ? atoi(e) : 4; }();
-  if (P.H == YW && P.N == YN && !B.pitch_generic) { if (ng == 5) launch_pitch_hop_t<5>(P, B, s); else launch_pitch_hop_t<4>(P, B, s); }
+  if (P.H == YW && P.N == YN && !B.pitch_generic) { if (ng == 4) launch_pitch_hop_t<4>(P, B, s); else launch_pitch_hop_t<5>(P, B, s); }
   else launch_pitch_t<3>(P, B, s);      // 3 groups: 168 registers per thread, no spills (4 groups at 128 registers measured 6 % slower)
   ++*launches;
 }
