@@ -296,9 +296,17 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) { e = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming); }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_spec, cudaEventDisableTiming);
   if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaStreamCreate(side)", e); }
-  ctx->multi_stream = !ctx->debug_times && !(getenv("AFX_SINGLE_STREAM") && atoi(getenv("AFX_SINGLE_STREAM")) != 0);
+  // MEASURED (round 2, full workload): the four kernel chains on four streams make a step 5 % SLOWER than one stream (606 vs
+  // 577 ms): every frame kernel fills the GPU on its own, and side by side they only share caches and shared memory.  One
+  // stream is the default; AFX_MULTI_STREAM=1 brings the fork / join back.
+  ctx->multi_stream = !ctx->debug_times && getenv("AFX_MULTI_STREAM") && atoi(getenv("AFX_MULTI_STREAM")) != 0
+                      && !(getenv("AFX_SINGLE_STREAM") && atoi(getenv("AFX_SINGLE_STREAM")) != 0);
+  // ... and for the same reason the computes of the contexts of one device (the adapter's slots) run one after the other, in the
+  // order they were enqueued, while their copies overlap the other contexts' kernels (AFX_COMPUTE_CHAIN=0: independent)
+  ctx->compute_chain = !(getenv("AFX_COMPUTE_CHAIN") && atoi(getenv("AFX_COMPUTE_CHAIN")) == 0);
 
   AfxParams& P = ctx->P;
   memset(&P, 0, sizeof(P));
@@ -377,11 +385,11 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
     o_dct = place(dct.size() * 8), o_tw = place(tw2048.size() * 8), o_tw5 = place(tw512.size() * 8), o_imp = place(imp.size() * 4),
     o_ft2 = place(ft2.size() * 8), o_ft3a = place(ft3a.size() * 8), o_ft3b = place(ft3b.size() * 8), o_ctr = place(64 * 4),
     o_pad = place(32 * 8);
-  // the walk of k_bands_lane: cut the bin axis at every sub-band / frequency-band / mel-support edge and every 32 bins
+  // the walk of k_bands_lane: cut the bin axis at every sub-band / frequency-band / mel-support edge and every 16 bins (its tile)
   std::vector<AfxBandSeg> segs;
   {
     std::vector<int> cuts;
-    for (int k = 0; k <= N / 2; k += 32) cuts.push_back(k);
+    for (int k = 0; k <= N / 2; k += 16) cuts.push_back(k);
     for (int b = 0; b < 14; ++b) { cuts.push_back(P.band14_start[b]); cuts.push_back(P.band14_start[b] + P.band14_n[b]); }
     for (int b = 0; b < 28; ++b) { cuts.push_back(P.band28_s[b]); cuts.push_back(P.band28_e[b]); }
     for (int q = 0; q < 14; ++q) if (P.mel_hi[q] >= P.mel_lo[q]) { cuts.push_back(P.mel_lo[q]); cuts.push_back(P.mel_hi[q] + 1); }
@@ -472,11 +480,20 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   return AFX_OK;
 }
 
+// end of the last compute enqueued on each device, by any context: the next compute on that device waits for it
+static std::mutex g_chain_mu;
+static cudaEvent_t g_chain[64] = { nullptr };
+
 extern "C" void afx_destroy(afx_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  {
+    std::lock_guard<std::mutex> lk(g_chain_mu);
+    if (ctx->device >= 0 && ctx->device < 64 && g_chain[ctx->device] == ctx->ev_chain) g_chain[ctx->device] = nullptr;   // (its work is done: synchronised above)
+  }
+  if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
   for (int i = 0; i < 3; ++i) { if (ctx->side[i]) { cudaStreamSynchronize(ctx->side[i]); cudaStreamDestroy(ctx->side[i]); } if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -861,6 +878,11 @@ extern "C" int afx_batch_compute(afx_batch* b)
   for (auto& k : b->ktimes) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
   b->ktimes.clear();
   b->launches = 0;
+  std::unique_lock<std::mutex> chain_lk;
+  if (ctx->compute_chain && ctx->device >= 0 && ctx->device < 64) {
+    chain_lk = std::unique_lock<std::mutex>(g_chain_mu);            // held while this compute is enqueued: chain order = enqueue order
+    if (g_chain[ctx->device] && g_chain[ctx->device] != ctx->ev_chain) CK(cudaStreamWaitEvent(ctx->stream, g_chain[ctx->device], 0), "cudaStreamWaitEvent(chain)");
+  }
   CK(cudaEventRecord(b->ev[2], ctx->stream), "cudaEventRecord");
   for (const auto& t : b->rs_tails)   // samples past what libresample delivers stay 0 (SA.cpp:579-580: zero-initialised buffer)
     CK(cudaMemsetAsync((float*)ctx->d_mono.p + t.off, 0, (size_t)t.count * 4, ctx->stream), "cudaMemsetAsync(mono tail)");
@@ -912,6 +934,7 @@ extern "C" int afx_batch_compute(afx_batch* b)
   if ((feat & AFX_FEAT_HIGHLEVEL) && ctx->hl_pad_ready) { ktime_begin(b, "highlevel"); afx_launch_highlevel(ctx->P, b->dev, b->hl, ctx->stream, &b->launches); ktime_end(b); }
   if ((feat & AFX_FEAT_PACK) && b->n_files > 0) { ktime_begin(b, "pack"); afx_launch_pack(b->dev, b->pack, ctx->stream, &b->launches); ktime_end(b); }
   CK(cudaEventRecord(b->ev[3], ctx->stream), "cudaEventRecord");
+  if (chain_lk.owns_lock()) { CK(cudaEventRecord(ctx->ev_chain, ctx->stream), "cudaEventRecord(chain)"); g_chain[ctx->device] = ctx->ev_chain; }
   CK(cudaGetLastError(), "kernel launch");
   b->computed = true;
   return AFX_OK;

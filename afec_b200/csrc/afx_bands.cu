@@ -236,11 +236,14 @@ __device__ __forceinline__ double lane_finish_band(AfxBatchDev& B, const AfxPara
 
 __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParams P)
 {
-  __shared__ double tiles[BLW][32][33];
+  // two tiles of 16 bins per warp: the next 16 bins arrive (cp.async, 8 bytes per lane and row, transposed on the way in) while the
+  // warp walks the current ones -- with one tile the walk stood still for a global round trip once per tile
+  // (ncu: 42 % of the stall samples on the loads' scoreboard)
+  __shared__ double tiles[BLW][2][16][33];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int rel0 = (blockIdx.x * BLW + wid) * 32;
   if (rel0 >= B.g_slots) return;                // warp-uniform
-  double (*tile)[33] = tiles[wid];
+  double (*tile)[33] = tiles[wid][0];
   const int rel_raw = rel0 + lane;
   const bool in_range = rel_raw < B.g_slots;
   const int rel = in_range ? rel_raw : rel0;
@@ -252,6 +255,21 @@ __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParam
   const size_t TF = (size_t)B.TF;
   const double* __restrict__ mag = B.mag;
   const int last_row = B.g_slots - 1;
+  // rows rel0 - 1 .. rel0 + 31, bins k0 .. k0 + 15 -> tiles[wid][buf]; half a warp per row on the way in (lane = bin),
+  // lane = frame on the way out
+  auto fetch_tile = [&](int k0, int buf) {
+    const int hb = lane >> 4, b = lane & 15;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(&tiles[wid][buf][b][hb]);
+#pragma unroll
+    for (int c = 0; c < 17; ++c) {
+      const int r = 2 * c + hb;
+      if (r < 33) {
+        const int rc = min(max(rel0 - 1 + r, 0), last_row);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst + 16 * c), "l"(mag + (size_t)rc * AFX_NBIN + k0 + b) : "memory");
+      }
+    }
+  };
+  fetch_tile(0, 0);
 
   // state of the walk.  Everything that changes along the bin axis is constant inside a segment (AfxBandSeg, built by
   // afx_create), so the per-bin loop below is straight arithmetic.
@@ -271,15 +289,11 @@ __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParam
   for (int si = 0; si < nseg; ++si) {
     const AfxBandSeg sg = segs[si];             // uniform
     const int k0 = sg.k0, k1 = sg.k1;
-    if ((k0 & 31) == 0) {
-      // the tile: rows rel0 - 1 .. rel0 + 31, bins k0 .. k0 + 31; lane = bin on the way in, lane = frame on the way out
-      __syncwarp();
-#pragma unroll 11
-      for (int c = 0; c < 33; ++c) {
-        const int rc = min(max(rel0 - 1 + c, 0), last_row);
-        tile[lane][c] = mag[(size_t)rc * AFX_NBIN + k0 + lane];
-      }
-      __syncwarp();
+    if ((k0 & 15) == 0) {                       // the segments are cut at every 16 bins: a new tile starts here
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp();                             // every lane's part has landed, and every lane is done with the tile before
+      tile = tiles[wid][(k0 >> 4) & 1];
+      if (k0 + 16 < AFX_NBIN) fetch_tile(k0 + 16, ((k0 >> 4) + 1) & 1);
     }
     const bool in14 = sg.b14 >= 0, in28 = sg.b28 >= 0;
     const bool small14 = in14 && P.band14_n[sg.b14] <= 32;
@@ -287,7 +301,7 @@ __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParam
     const double* __restrict__ w0 = P.t.mel + (size_t)(sg.q0 < 0 ? 0 : sg.q0) * AFX_NBIN;
     const double* __restrict__ w1 = w0 + AFX_NBIN;
     if (pending >= 0) {                         // the first bin of this segment is the right neighbour of the band that just ended
-      vals[nv + 1] = tile[k0 & 31][lane + 1];
+      vals[nv + 1] = tile[k0 & 15][lane + 1];
       csum += lane_finish_band(B, P, TF, slot, rel, pending, live, vals, pend, pend_mx);
       pending = -1;
     }
@@ -295,8 +309,8 @@ __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParam
     double x = xprev;
 #pragma unroll 2
     for (int k = k0; k < k1; ++k) {
-      x = tile[k & 31][lane + 1];
-      const double y = has_prev ? tile[k & 31][lane] : x;
+      x = tile[k & 15][lane + 1];
+      const double y = has_prev ? tile[k & 15][lane] : x;
       if (in14) {                               // SampleAnalyser.cpp:2067-2260
         s12 = fma(x, y, s12); s1 += x; s11 = fma(x, x, s11); s2 += y; s22 = fma(y, y, s22);
         mx = fmax(mx, x);

@@ -64,7 +64,9 @@ struct afx_ctx {
   cudaStream_t side[3] = { nullptr, nullptr, nullptr };
   cudaStream_t copy_stream = nullptr;   // H2D copies of part jobs: a later part uploads while an earlier one computes
   cudaEvent_t ev_fork = nullptr, ev_spec = nullptr, ev_join[3] = { nullptr, nullptr, nullptr };
-  bool multi_stream = true;
+  cudaEvent_t ev_chain = nullptr;   // end of this context's last compute (see g_chain in afx_api.cu)
+  bool compute_chain = true;
+  bool multi_stream = false;
   AfxParams P;
   DevBuf tables;                      // all constant tables in one allocation
   DevBuf d_pcm, d_mono, d_mono_src, d_files, d_state, d_mag, d_cent, d_fs, d_fsr, d_fv, d_rpolar, d_rodf, d_rpost, d_bandraw, d_slotmap,

@@ -547,7 +547,10 @@ def main():
     chunk_arrs = [(api.AfxFile * (bounds[i + 1] - bounds[i]))(*files[bounds[i]:bounds[i + 1]]) for i in range(E2E_CHUNKS)]
     e2e_bytes = [0, 0]
 
-    def pipeline_step(copy_only: bool):
+    def pipeline_steps(n_steps: int, copy_only: bool):
+        """n_steps passes over the corpus as ONE stream of chunks through the slots (a crawler's file list does not stop
+        between passes either: the pipeline fills once and drains once per call); every chunk is uploaded from pinned host
+        memory and its results are read back on the host."""
         counter = itertools.count()
         lock = threading.Lock()
         tot = [0, 0, 0.0]
@@ -556,9 +559,9 @@ def main():
             while True:
                 with lock:
                     ci = next(counter)
-                if ci >= E2E_CHUNKS:
+                if ci >= E2E_CHUNKS * n_steps:
                     return
-                arr = chunk_arrs[ci]
+                arr = chunk_arrs[ci % E2E_CHUNKS]
                 bb = wrap(sl, arr, len(arr))
                 if copy_only:
                     bb.upload(); bb.sync()
@@ -577,14 +580,12 @@ def main():
             t.start()
         for t in ths:
             t.join()
-        e2e_bytes[0], e2e_bytes[1] = tot[0], tot[1]
+        e2e_bytes[0], e2e_bytes[1] = tot[0] // n_steps, tot[1] // n_steps
 
-    for _ in range(2):
-        pipeline_step(False)
+    pipeline_steps(2, False)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        pipeline_step(False)
+    pipeline_steps(args.steps, False)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
@@ -592,12 +593,11 @@ def main():
     e2e_value = total_audio_hours * args.steps / e2e_s
     # copy-only leg: the same arena, chunks, slots and threads, uploads only -- what the host -> device fabric gives
     # every rank while all ranks copy at once (separates a PCIe / host-memory ceiling from the kernels)
-    pipeline_step(True)
+    pipeline_steps(1, True)
     barrier()
     t0 = time.perf_counter()
     n_copy = max(2, args.steps // 2)
-    for _ in range(n_copy):
-        pipeline_step(True)
+    pipeline_steps(n_copy, True)
     torch.cuda.synchronize()
     copy_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
@@ -649,7 +649,7 @@ def main():
             table["autocorr"]["pipe"] = "fp32"
             table["autocorr"]["frac_fp32_nominal"] = table["autocorr"]["tflops"] / FP32_NOMINAL_TFLOPS
         top_tf = gflops.get(top, 0.0) / (top_ms * 1e-3) / 1e12
-        step_ms = dev_ms / args.steps                     # this rank's multi-stream step (the `value` timing)
+        step_ms = dev_ms / args.steps                     # this rank's step (the `value` timing)
         step_tf = step_flops / (step_ms * 1e-3) / 1e12
         roof = {
             "bound": "fp64", "achieved": top_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": top_tf / fp64_peak if fp64_peak else None,
@@ -713,7 +713,8 @@ def main():
                     "ms_per_step": 1000.0 * e2e_s / args.steps, "h2d_gbs_per_gpu": h2d_gbs,
                     "h2d_note": "copy-only leg: same pinned arena / chunks / slot threads with no kernels, all ranks at once, max over ranks",
                     "path": "afx_batch_create -> upload (pinned H2D) -> compute -> download (D2H) -> sync per chunk; %d chunks per step over "
-                            "%d contexts / host threads (copies overlap kernels)" % (E2E_CHUNKS, E2E_SLOTS)},
+                            "%d contexts / host threads (copies overlap kernels; the K timed steps are one continuous stream of chunks, the "
+                            "computes of the contexts run one after the other on the device)" % (E2E_CHUNKS, E2E_SLOTS)},
             "gpu_launches": int(cnt["kernel_launches"]) * args.steps * world,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "parity_checked": parity_n, "parity_mismatches": parity_errs[:8], "e2e_with_sink": sink,
