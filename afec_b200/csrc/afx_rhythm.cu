@@ -601,14 +601,58 @@ __global__ void __launch_bounds__(BT_THREADS) k_rhythm_back(AfxBatchDev B, AfxPa
 
     // ---- contrast (RhythmTracker.cpp:392-480): 85th percentile threshold, peaks vs preceding valleys ----
     const double pthr = block_select(s, n, (int)(85.0 / 100.0 * (n - 1)), hist, ctl);
-    if (tid == 0) {
-      double ps = 0, vs = 0; int pc = 0, vpos = 0; double vval = pthr;
-      for (int i = 0; i < n; ++i) {
-        const double v = s[i];
-        if (v < vval) { vpos = i; vval = v; }
-        if (v < pthr) continue;
-        if (lm[i]) { ps += v; vs += s[vpos]; ++pc; vval = v; }
+    // The reference walks the function once, tracking the running minimum ("valley") since the last accepted peak:
+    //     if (v < vval) { vpos = i; vval = v; }   if (v >= pthr && local max) { ps += v; vs += s[vpos]; ++pc; vval = v; }
+    // One warp walks it 32 samples at a time instead (a single thread spent half of this kernel here): the samples after a
+    // peak form a segment whose level is that peak's value; a segmented min-scan gives every lane the first position of
+    // the minimum of its segment so far, a valley is "found" where that minimum is below the level, and a peak whose segment
+    // found none inherits the position from the last segment that did.
+    if (tid < 32) {
+      const int lane = tid;
+      double ps = 0, vs = 0; int pc = 0;
+      double vval = pthr; int vpos = 0;                           // carried between the 32-sample steps (uniform)
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const bool valid = i < n;
+        const double v = valid ? s[i] : __longlong_as_double(0x7ff0000000000000ll);
+        const bool pk = valid && !(v < pthr) && lm[i];
+        const unsigned pkm = __ballot_sync(0xffffffffu, pk);
+        const unsigned heads = (pkm << 1) | 1u;                    // a segment starts at lane 0 and after every peak
+        const int h = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));      // head of this lane's segment
+        const double vprev = __shfl_up_sync(0xffffffffu, v, 1);
+        const double lvl_h = (lane == 0) ? vval : vprev;          // level of a segment that starts at this lane
+        const double lvl = __shfl_sync(0xffffffffu, lvl_h, h);
+        double mv = v; int mp = i; bool fl = (heads >> lane) & 1u;   // inclusive segmented (min, first position) scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double ov = __shfl_up_sync(0xffffffffu, mv, o);
+          const int op = __shfl_up_sync(0xffffffffu, mp, o);
+          const bool of = __shfl_up_sync(0xffffffffu, fl, o);
+          if (lane >= o && !fl) { if (ov <= mv) { mv = ov; mp = op; } fl = of; }
+        }
+        const bool found = mv < lvl;
+        const unsigned fm = __ballot_sync(0xffffffffu, pk && found);         // peaks whose segment found a valley of its own
+        // valley position in force at this lane's peak: its own segment's, else the last found one before it, else the carry
+        const unsigned below = fm & (0xffffffffu >> (31 - lane));
+        const int src = below ? 31 - __clz(below) : 0;
+        const int psrc = __shfl_sync(0xffffffffu, mp, src);
+        const int myv = below ? psrc : vpos;
+        if (pk) { ps += v; vs += s[myv]; }
+        pc += __popc(pkm);
+        // carry: after a peak in lane 31 the level is its value and the valley in force stays; else the open segment's state
+        const bool pk31 = (pkm >> 31) & 1u;
+        const double v31 = __shfl_sync(0xffffffffu, v, 31), lvl31 = __shfl_sync(0xffffffffu, lvl, 31), mv31 = __shfl_sync(0xffffffffu, mv, 31);
+        const int mp31 = __shfl_sync(0xffffffffu, mp, 31), myv31 = __shfl_sync(0xffffffffu, myv, 31);
+        const bool found31 = __shfl_sync(0xffffffffu, found, 31);
+        if (pk31) { vval = v31; vpos = myv31; }
+        else {
+          const int lastf = fm ? __shfl_sync(0xffffffffu, mp, 31 - __clz(fm)) : vpos;     // (fm has no bit 31 here)
+          vval = found31 ? mv31 : lvl31;
+          vpos = found31 ? mp31 : lastf;
+        }
       }
+      ps = warp_sum(ps); vs = warp_sum(vs);
+      if (lane == 0) {
       const double pmean = pc ? ps / pc : 0.0, vmean = (pc ? vs / pc : 0.0) + 0.0001;
       double* Hh = H + H_RC_COUNT + 6 * ty;
       Hh[0] = (double)cnt;
@@ -618,6 +662,7 @@ __global__ void __launch_bounds__(BT_THREADS) k_rhythm_back(AfxBatchDev B, AfxPa
       Hh[3] = st < 0.0 ? 0.0 : (st > 1.0 ? 1.0 : st);
       Hh[4] = 0.0; Hh[5] = 0.0;
       res[ty][0] = 0.0; res[ty][1] = 0.0;
+      }
     }
     __syncthreads();
 
