@@ -364,19 +364,23 @@ def test_pitch_block_sharing_form_vs_general(feats, monkeypatch, oracle_lib):
 
 
 def test_peaks_fused_equals_split(feats):
-    """The whitening + peak count has a fused per-file form (AFX_PEAKS_FUSED=1, afx_peaks.cu); it must give the same counts."""
+    """The whitening + peak count has three schedules (afx_peaks.cu): the split pair, a fused per-file kernel
+    (AFX_PEAKS_FUSED=1) and the producer / consumer pipeline that large launch groups get (forced here with
+    AFX_PEAKS_PIPE=1); all must give the same counts."""
     import subprocess
     import sys
     code = ("import sys, numpy as np; sys.path.insert(0, '.'); from afec_b200 import api, synth\n"
-            "pcms = [synth.one_shot(840 + i, 0.3 + 0.9 * i) for i in range(6)] + [np.zeros(30000, dtype=np.int16), synth.one_shot(850, 0.02)]\n"
+            "pcms = [synth.one_shot(840 + i, 0.3 + 0.9 * i) for i in range(6)] + [np.zeros(30000, dtype=np.int16), synth.one_shot(850, 0.02),"
+            " synth.one_shot(851, 19.0), synth.one_shot(852, 0.05)]\n"
             "an = api.SampleAnalyser(44100, 2048, 1024, features=%d)\n"
             "r = an.analyze_pcm(pcms, [44100] * len(pcms))\n"
             "print(';'.join(','.join('%%d' %% v for v in x.series('spectral_complexity')) for x in r))" % feats)
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = [subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, AFX_PEAKS_FUSED=m), capture_output=True, text=True,
-                           check=True).stdout for m in ("0", "1")]
-    assert outs[0] == outs[1] and outs[0].count(",") > 100
+    envs = [dict(AFX_PEAKS_FUSED="0", AFX_PEAKS_PIPE="0"), dict(AFX_PEAKS_FUSED="1", AFX_PEAKS_PIPE="0"), dict(AFX_PEAKS_FUSED="0", AFX_PEAKS_PIPE="1")]
+    outs = [subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **e), capture_output=True, text=True,
+                           check=True).stdout for e in envs]
+    assert outs[0] == outs[1] == outs[2] and outs[0].count(",") > 1000
 
 
 def test_resampled_batch_vs_oracle(analysers, feats, oracle_lib):
