@@ -9,7 +9,10 @@ from afec_b200 import api, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 hop = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 feats = api.FEAT_SPECTRAL if (len(sys.argv) > 3 and sys.argv[3] == "spectral") else api.FEAT_ALL
-if os.environ.get("VT_MIXED"):     # mixed-length (0.5-30 s) corpus, the shape of bench.py --workload full
+if os.environ.get("VT_BENCH"):     # exactly bench.py's default corpus (N = 1)
+    base = synth.corpus(64, 30.0, seed0=1000, min_seconds=0.5)
+    pcms = [base[i % 64] for i in range(n)]
+elif os.environ.get("VT_MIXED"):     # mixed-length (0.5-30 s) corpus, the shape of bench.py --workload full
     pcms = synth.tiled_corpus(n, 64, seconds=30.0, seed0=0, min_seconds=0.5)
 else:
     pcms = synth.tiled_corpus(n, 16, seconds=3.0, seed0=0)
