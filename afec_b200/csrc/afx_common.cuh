@@ -86,6 +86,12 @@ struct AfxState {           // device-computed, one per file (SampleAnalyser.cpp
   double amp;
   int lead, audible, start_off, len;
   int L, F, Fr, data_offset;
+  // batch path: the effective-length scan rides in the trim pass (raw mono indices); k_layout maps them into the conditioned
+  // signal, and asks for an exact rescan of the audible span in the (rounding-boundary) case that one lies outside it
+  int effraw_first[3], effraw_last[3];
+  int eff_rescan, pad_;
+  // smallest float32 magnitudes that pass the trim floor / the three effective-length floors (k_amp): the scans compare floats
+  float thr_trim, thr_eff[3];
 };
 
 // One run of consecutive bins inside which nothing changes for k_bands_lane (afx_bands.cu): the sub-band, the frequency

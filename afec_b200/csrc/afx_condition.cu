@@ -372,7 +372,22 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample(AfxBatchDev B, AfxTable
 }
 
 // ---- Amplification / FinalScaling -------------------------------------------------------------
-__global__ void k_amp(AfxBatchDev B)
+// smallest non-negative float t with |(double)t * scale| > floor: the double-precision test of the reference is monotone in
+// |t|, so the scans over the samples can compare float magnitudes against this instead of converting every sample
+__device__ float first_float_above(double scale, double floor_)
+{
+  if (!(scale > 0.0)) return __int_as_float(0x7f800000);
+  float t = (float)(floor_ / scale);
+  if (!(t >= 0.0f)) t = 0.0f;
+  for (int it = 0; it < 64 && t > 0.0f; ++it) {                       // down while the value below still passes
+    const float below = __int_as_float(__float_as_int(t) - 1);
+    if (fabs((double)below * scale) > floor_) t = below; else break;
+  }
+  for (int it = 0; it < 64 && !(fabs((double)t * scale) > floor_); ++it) t = __int_as_float(__float_as_int(t) + 1);   // up until it passes
+  return t;
+}
+
+__global__ void k_amp(AfxBatchDev B, AfxParams P)
 {
   const int fi = blockIdx.x * blockDim.x + threadIdx.x;
   if (fi >= B.n_files) return;
@@ -381,10 +396,15 @@ __global__ void k_amp(AfxBatchDev B)
   const double amp = (maxamp > (double)1e-12f) ? 32768.0 / maxamp : 1.0;   // SA.cpp:636-637
   st->amp = amp;
   st->fs = amp / 32768.0;                                                  // SA.cpp:712
+  st->thr_trim = first_float_above(amp, P.silence_floor_amp);              // fabs(amp * x) > floor (SA.cpp:648-669)
+  for (int k = 0; k < 3; ++k) st->thr_eff[k] = first_float_above(st->fs, P.eff_floor[k]);   // fabs(x * fs) > floor (SA.cpp:1715-1756)
 }
 
+// EFF: the thresholds of the effective-length scan (SA.cpp:1715-1756) are tested in the same pass over the samples (one
+// read of the mono signal instead of two); indices stay raw here, k_layout maps them
+template <bool EFF>
 __global__ void __launch_bounds__(CT) k_trim(AfxBatchDev B, const int* __restrict__ chunk_file,
-                                            const int* __restrict__ chunk_start, double floor_amp)
+                                            const int* __restrict__ chunk_start, double floor_amp, AfxParams P)
 {
   __shared__ int scratch[32];
   const int fi = chunk_file[blockIdx.x];
@@ -394,20 +414,68 @@ __global__ void __launch_bounds__(CT) k_trim(AfxBatchDev B, const int* __restric
   if (start >= f.n) return;
   const int end = min(start + CHUNK, f.dst_end);
   const float* src = B.mono + f.mono_off;
-  const double amp = B.state[fi].amp;
-  int first = 0x7fffffff, last = -1;
-  for (int i = start + threadIdx.x; i < end; i += CT) {
-    if (fabs(amp * (double)src[i]) > floor_amp) { first = min(first, i); last = max(last, i); }
+  const float tt = B.state[fi].thr_trim;
+  const float t0 = B.state[fi].thr_eff[0], t1 = B.state[fi].thr_eff[1], t2 = B.state[fi].thr_eff[2];
+  // a thread visits samples start + tid + it * CT, it = 0..31, in ascending order: one bit per visit and threshold, first and
+  // last hit from the masks afterwards (two instructions per sample and threshold; the pass stays bound by the one read of
+  // the signal)
+  static_assert(CHUNK / CT == 32, "one mask bit per sample of a thread");
+  // 16-byte loads: a thread visits the 4-sample groups tid + it * CT, it = 0..7 (mono offsets and chunk starts are multiples
+  // of 4; the last group of a file may reach into the padding behind it -- those lanes are masked by i < end)
+  unsigned mt = 0u, me[3] = { 0u, 0u, 0u };
+  const float4* __restrict__ src4 = reinterpret_cast<const float4*>(src + start);
+  const int nrem = end - start;
+  const bool aligned = (reinterpret_cast<size_t>(src4) & 15) == 0;
+#pragma unroll
+  for (int it = 0; it < CHUNK / CT / 4; ++it) {
+    const int g = threadIdx.x + it * CT;
+    if (4 * g < nrem) {
+      float4 v;
+      if (aligned) v = src4[g];
+      else {                                                     // a part's range (afx_part.cu) may start anywhere
+        const float* q = src + start + 4 * g;
+        v.x = q[0]; v.y = (4 * g + 1 < nrem) ? q[1] : 0.0f; v.z = (4 * g + 2 < nrem) ? q[2] : 0.0f; v.w = (4 * g + 3 < nrem) ? q[3] : 0.0f;
+      }
+      const float a4[4] = { fabsf(v.x), fabsf(v.y), fabsf(v.z), fabsf(v.w) };
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = (4 * g + j < nrem) ? a4[j] : -1.0f;      // (thresholds are >= 0: -1 passes none)
+        const unsigned bit = 1u << (4 * it + j);
+        if (a >= tt) mt |= bit;
+        if (EFF) {
+          if (a >= t0) me[0] |= bit;
+          if (a >= t1) me[1] |= bit;
+          if (a >= t2) me[2] |= bit;
+        }
+      }
+    }
   }
+  // bit b of a mask <-> sample start + 4 (tid + (b >> 2) CT) + (b & 3): ascending in b
+  auto pos = [&](int b) { return start + 4 * ((int)threadIdx.x + (b >> 2) * CT) + (b & 3); };
+  int first = mt ? pos(__ffs(mt) - 1) : 0x7fffffff, last = mt ? pos(31 - __clz(mt)) : -1;
+  int ef[3], el[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { ef[k] = me[k] ? pos(__ffs(me[k]) - 1) : 0x7fffffff; el[k] = me[k] ? pos(31 - __clz(me[k])) : -1; }
   first = block_min_i(first, scratch);
   last = -block_min_i(-last, scratch);
   if (threadIdx.x == 0) {
     if (first != 0x7fffffff) atomicMin(&B.state[fi].first, first);
     if (last >= 0) atomicMax(&B.state[fi].last, last);
   }
+  if (EFF) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int a = block_min_i(ef[k], scratch);
+      const int b = -block_min_i(-el[k], scratch);
+      if (threadIdx.x == 0) {
+        if (a != 0x7fffffff) atomicMin(&B.state[fi].effraw_first[k], a);
+        if (b >= 0) atomicMax(&B.state[fi].effraw_last[k], b);
+      }
+    }
+  }
 }
 
-__global__ void k_layout(AfxBatchDev B, AfxParams P)
+__global__ void k_layout(AfxBatchDev B, AfxParams P, int fused_eff)
 {
   const int fi = blockIdx.x * blockDim.x + threadIdx.x;
   if (fi >= B.n_files) return;
@@ -435,6 +503,17 @@ __global__ void k_layout(AfxBatchDev B, AfxParams P)
   if (Fr > f.rframe_cap) Fr = f.rframe_cap;
   st->F = F; st->Fr = Fr;
   for (int k = 0; k < 3; ++k) { st->eff_first[k] = 0x7fffffff; st->eff_last[k] = -1; }
+  if (fused_eff) {
+    // a sample above an effective-length floor is above the trim floor too -- except on a rounding boundary of the two
+    // expressions (the -48 dB floors are the same level); then, and only then, the audible span is scanned again
+    bool inside = true;
+    for (int k = 0; k < 3; ++k)
+      if (st->effraw_last[k] >= 0 && (st->effraw_first[k] < lead || st->effraw_last[k] >= lead + audible)) inside = false;
+    if (inside) {
+      for (int k = 0; k < 3; ++k)
+        if (st->effraw_last[k] >= 0) { st->eff_first[k] = st->effraw_first[k] - lead + start_off; st->eff_last[k] = st->effraw_last[k] - lead + start_off; }
+    } else st->eff_rescan = 1;
+  }
   if (B.inject && f.inject >= 0) {
     const AfxInject in = B.inject[f.inject];
     for (int k = 0; k < 3; ++k) { st->eff_first[k] = in.eff_first[k]; st->eff_last[k] = in.eff_last[k]; }
@@ -479,6 +558,30 @@ __device__ __forceinline__ float samples_to_ms(int sr, int samples)
   return __fdiv_rn((float)samples, __fdiv_rn((float)sr, 1000.0f));
 }
 
+// the exact rescan k_layout may ask for (see there): one CTA per file, a no-op for all but pathological files
+__global__ void __launch_bounds__(CT) k_eff_fix(AfxBatchDev B, AfxParams P)
+{
+  __shared__ int scratch[32];
+  const int fi = blockIdx.x;
+  const AfxFile f = B.files[fi];
+  const AfxState st = B.state[fi];
+  if (f.status != 0 || !st.eff_rescan || (B.inject && f.inject >= 0)) return;
+  const float* src = B.mono + f.mono_off;
+  int first[3] = { 0x7fffffff, 0x7fffffff, 0x7fffffff }, last[3] = { -1, -1, -1 };
+  for (int i = st.lead + threadIdx.x; i < st.lead + st.audible; i += CT) {
+    const double v = fabs((double)src[i] * st.fs);
+    const int idx = i - st.lead + st.start_off;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) if (v > P.eff_floor[k]) { first[k] = min(first[k], idx); last[k] = max(last[k], idx); }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int a = block_min_i(first[k], scratch);
+    const int b = -block_min_i(-last[k], scratch);
+    if (threadIdx.x == 0) { B.state[fi].eff_first[k] = a; B.state[fi].eff_last[k] = b; }
+  }
+}
+
 __global__ void k_header(AfxBatchDev B, AfxParams P)
 {
   const int fi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -521,6 +624,8 @@ __global__ void k_state_init(AfxBatchDev B)
   if (fi >= B.n_files) return;
   AfxState* st = B.state + fi;
   st->maxabs_bits = 0u; st->sumsq = 0.0; st->first = 0x7fffffff; st->last = -1;
+  for (int k = 0; k < 3; ++k) { st->effraw_first[k] = 0x7fffffff; st->effraw_last[k] = -1; }
+  st->eff_rescan = 0;
   const int inj = B.files[fi].inject;
   if (B.inject && inj >= 0) {
     const AfxInject in = B.inject[inj];
@@ -557,12 +662,12 @@ void afx_launch_part_reduce(const AfxParams& P, const AfxBatchDev& B, const AfxC
 }
 void afx_launch_part_trim(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s)
 {
-  k_amp<<<1, 128, 0, s>>>(B);
-  if (C.n_dst_chunks > 0) k_trim<<<C.n_dst_chunks, CT, 0, s>>>(B, C.dst_chunk_file, C.dst_chunk_start, P.silence_floor_amp);
+  k_amp<<<1, 128, 0, s>>>(B, P);
+  if (C.n_dst_chunks > 0) k_trim<false><<<C.n_dst_chunks, CT, 0, s>>>(B, C.dst_chunk_file, C.dst_chunk_start, P.silence_floor_amp, P);
 }
 void afx_launch_part_eff(const AfxParams& P, const AfxBatchDev& B, const AfxCondPlan& C, cudaStream_t s)
 {
-  k_layout<<<1, 128, 0, s>>>(B, P);
+  k_layout<<<1, 128, 0, s>>>(B, P, 0);
   if (C.n_dst_chunks > 0) k_eff<<<C.n_dst_chunks, CT, 0, s>>>(B, C.dst_chunk_file, C.dst_chunk_start, P);
 }
 
@@ -577,9 +682,9 @@ void afx_launch_condition_plan(const AfxParams& P, const AfxBatchDev& B, const A
     launch_resample(P, B, C, s); ++*launches;
     k_reduce<<<C.n_rs_chunks, CT, 0, s>>>(B, C.rs_chunk_file, C.rs_chunk_start); ++*launches;
   }
-  k_amp<<<fb, 128, 0, s>>>(B); ++*launches;
-  if (C.n_dst_chunks > 0) { k_trim<<<C.n_dst_chunks, CT, 0, s>>>(B, C.dst_chunk_file, C.dst_chunk_start, P.silence_floor_amp); ++*launches; }
-  k_layout<<<fb, 128, 0, s>>>(B, P); ++*launches;
-  if (C.n_dst_chunks > 0) { k_eff<<<C.n_dst_chunks, CT, 0, s>>>(B, C.dst_chunk_file, C.dst_chunk_start, P); ++*launches; }
+  k_amp<<<fb, 128, 0, s>>>(B, P); ++*launches;
+  if (C.n_dst_chunks > 0) { k_trim<true><<<C.n_dst_chunks, CT, 0, s>>>(B, C.dst_chunk_file, C.dst_chunk_start, P.silence_floor_amp, P); ++*launches; }
+  k_layout<<<fb, 128, 0, s>>>(B, P, 1); ++*launches;
+  k_eff_fix<<<B.n_files, CT, 0, s>>>(B, P); ++*launches;
   k_header<<<fb, 128, 0, s>>>(B, P); ++*launches;
 }
