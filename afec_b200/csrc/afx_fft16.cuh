@@ -102,12 +102,13 @@ __device__ __forceinline__ double2 fft_tw_load(const double2* p) { return TW_SME
 // T3STEP: the N = 1024 third pass may read its twiddles from the N = 2048 table (exp(-2 pi i r j / 1024) is row 2r of
 // exp(-2 pi i r j / 2048)): T3STEP = 2 with tw.t3 pointing at the 2048 table
 //
+// T2_POWERS: the second pass loads four of its fifteen twiddles and multiplies the rest together.
 // T3_POWERS (N = 1024 only): the third pass derives its twiddles w^2, w^3 from w (see there).
 // HALF_OPT (N = 1024 only): with `half` set at run time the last pass keeps only outputs 0..511 and stores X[j] at
 // buf[FFT_PAD8(j)] -- a layout in which a thread can then read 8 consecutive outputs without bank conflicts (the pitch kernel
 // needs just the first half of its inverse transform, 16 consecutive lags per thread).
 #define FFT_PAD8(i) ((i) + ((i) >> 3))
-template <int N, class Sync, bool TW_SMEM = false, int T3STEP = 1, bool HALF_OPT = false, bool T3_POWERS = false>
+template <int N, class Sync, bool TW_SMEM = false, int T3STEP = 1, bool HALF_OPT = false, bool T3_POWERS = false, bool T2_POWERS = false>
 __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict__ buf, const FftTw tw, int tid, Sync sync, bool half = false)
 {
   constexpr int NT = N / 16;
@@ -123,8 +124,19 @@ __device__ __forceinline__ void fft16_run(double2 (&v)[16], double2* __restrict_
   sync();
   {
     const int k = tid & 15;
+    if (T2_POWERS) {                       // w^1, w^2, w^4, w^8 from the table, the other eleven powers as products (at most three deep)
+      double2 w[16];
+      w[1] = fft_tw_load<TW_SMEM>(tw.t2 + 0 * 16 + k); w[2] = fft_tw_load<TW_SMEM>(tw.t2 + 1 * 16 + k);
+      w[4] = fft_tw_load<TW_SMEM>(tw.t2 + 3 * 16 + k); w[8] = fft_tw_load<TW_SMEM>(tw.t2 + 7 * 16 + k);
+      w[3] = f_mul(w[1], w[2]); w[5] = f_mul(w[1], w[4]); w[6] = f_mul(w[2], w[4]); w[7] = f_mul(w[3], w[4]);
 #pragma unroll
-    for (int r = 1; r < 16; ++r) v[r] = f_mul(v[r], fft_tw_load<TW_SMEM>(tw.t2 + (r - 1) * 16 + k));
+      for (int r = 9; r < 16; ++r) w[r] = f_mul(w[8], w[r - 8]);
+#pragma unroll
+      for (int r = 1; r < 16; ++r) v[r] = f_mul(v[r], w[r]);
+    } else {
+#pragma unroll
+      for (int r = 1; r < 16; ++r) v[r] = f_mul(v[r], fft_tw_load<TW_SMEM>(tw.t2 + (r - 1) * 16 + k));
+    }
     f_dft16(v);
     const int base = (tid - k) * 16 + k;
 #pragma unroll

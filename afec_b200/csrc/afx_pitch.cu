@@ -312,6 +312,9 @@ __global__ void __launch_bounds__(YT * NG, 1) k_pitch(AfxBatchDev B, AfxParams P
 // and the normalisation run in registers on 16 consecutive lags per thread straight from I_A, I_B and the inverse
 // transform's output, which the last FFT pass stores -- first half only -- in a layout made for that read.
 #define HT 64
+#ifndef PITCH_T2P
+#define PITCH_T2P false        // measured: the eleven extra products cost more than the eleven table loads they save (15.2 vs 14.7 ns per frame)
+#endif
 #define HCH 16              // frame slots per claim: one extra transform per claimed run
 #define PADX(m) ((m) + 4 * ((m) >> 4))      // raw block: 16 consecutive floats per thread at a 20-float stride
 
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(HT * NG, 1) k_pitch_hop(AfxBatchDev B, AfxPara
         for (int r = 0; r < 16; ++r) v[r] = buf[FFT_PHYS(tid + HT * r)];
         sync();                                                      // every input is in registers before buf is rewritten
       }
-      fft16_run<YW, FftSyncNamed<HT>, true, 1, true, true>(v, buf, ftw, tid, sync, step == 2);
+      fft16_run<YW, FftSyncNamed<HT>, true, 1, true, true, PITCH_T2P>(v, buf, ftw, tid, sync, step == 2);
       if (step == 2) break;
       // ---- unpack bins k and 1024 - k of F_B; step 1: P, then Zc of the half-size inverse, in place ----
       // (r real => the inverse of the Hermitian P runs at half size: with z[m] = r[2m] + i r[2m+1], z = IFFT_1024(Zc),
