@@ -405,18 +405,27 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
       }
       for (int b = 0; b < 28; ++b) if (k0 >= P.band28_s[b] && k0 < P.band28_e[b]) { sg.b28 = (signed char)b; sg.end28 = (k1 == P.band28_e[b]); }
       for (int q = 0; q < 14; ++q) if (P.mel_hi[q] >= P.mel_lo[q] && k0 >= P.mel_lo[q] && k0 <= P.mel_hi[q]) { if (sg.q0 < 0) sg.q0 = (signed char)q; ++sg.nq; }
+      if (sg.nq > 0 && k1 == P.mel_hi[sg.q0] + 1) sg.fin |= 1;
+      if (sg.nq > 1 && k1 == P.mel_hi[sg.q0 + 1] + 1) sg.fin |= 2;
       if (sg.nq > 2 || (sg.nq == 2 && !(k0 >= P.mel_lo[sg.q0 + 1] && k0 <= P.mel_hi[sg.q0 + 1]))) {
         afx_destroy(ctx); return fail(nullptr, AFX_ERR_ARG, "afx_create: more than two mel filters overlap (unexpected filter table)");
       }
       segs.push_back(sg);
     }
   }
+  std::vector<double> mel_ab(2 * (size_t)(N / 2), 0.0);
+  for (const auto& sg : segs)
+    for (int k = sg.k0; k < sg.k1; ++k) {
+      if (sg.nq > 0) mel_ab[2 * k] = mel[(size_t)sg.q0 * (N / 2) + k];
+      if (sg.nq > 1) mel_ab[2 * k + 1] = mel[(size_t)(sg.q0 + 1) * (N / 2) + k];
+    }
   std::vector<float> extw, extw_k; std::vector<double> extdct(13 * 40);
   build_ext_weights(extw, N / 2, (double)sr, N);
   extw_k.resize(extw.size());
   for (int o = 0; o < 52; ++o) for (int k = 0; k < N / 2; ++k) extw_k[(size_t)k * 52 + o] = extw[(size_t)o * (N / 2) + k];
   for (int n = 0; n < 13; ++n) for (int m = 0; m < 40; ++m) extdct[n * 40 + m] = std::cos(pi * n * (m + 0.5) / 40.0);
   const size_t o_segs = place(segs.size() * sizeof(AfxBandSeg));
+  const size_t o_melab = place(mel_ab.size() * 8);
   const size_t o_extw = place(extw.size() * 4), o_extwk = place(extw_k.size() * 4), o_extdct = place(extdct.size() * 8);
   e = ctx->tables.reserve(off);
   if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMalloc(tables)", e); }
@@ -434,6 +443,8 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMemcpy(tables)", e); }
   P.t.window = (const double*)(base + o_win); P.t.rwindow = (const double*)(base + o_rwin);
   P.t.mel = (const double*)(base + o_mel); P.t.dct = (const double*)(base + o_dct);
+  cudaMemcpy(base + o_melab, mel_ab.data(), mel_ab.size() * 8, cudaMemcpyHostToDevice);
+  P.t.mel_ab = (const double2*)(base + o_melab);
   P.t.tw2048 = (const double2*)(base + o_tw); P.t.tw512 = (const double2*)(base + o_tw5);
   P.t.rs_imp = (const float*)(base + o_imp);
   P.t.work_ctr = (unsigned int*)(base + o_ctr);

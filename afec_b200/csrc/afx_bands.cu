@@ -234,16 +234,18 @@ __device__ __forceinline__ double lane_finish_band(AfxBatchDev& B, const AfxPara
   return live ? band_write(B, TF, slot, b, n, nei, r) : 0.0;
 }
 
-__global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParams P)
+__global__ void __launch_bounds__(BLW * 32, 4) k_bands_lane(AfxBatchDev B, AfxParams P)
 {
   // two tiles of 16 bins per warp: the next 16 bins arrive (cp.async, 8 bytes per lane and row, transposed on the way in) while the
   // warp walks the current ones -- with one tile the walk stood still for a global round trip once per tile
   // (ncu: 42 % of the stall samples on the loads' scoreboard)
   __shared__ double tiles[BLW][2][16][33];
+  __shared__ double2 melw[BLW][2][16];          // the tile's mel weights (per bin: the two filters that can cover it)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int rel0 = (blockIdx.x * BLW + wid) * 32;
   if (rel0 >= B.g_slots) return;                // warp-uniform
   double (*tile)[33] = tiles[wid][0];
+  const double2* mw = melw[wid][0];
   const int rel_raw = rel0 + lane;
   const bool in_range = rel_raw < B.g_slots;
   const int rel = in_range ? rel_raw : rel0;
@@ -268,6 +270,10 @@ __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParam
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst + 16 * c), "l"(mag + (size_t)rc * AFX_NBIN + k0 + b) : "memory");
       }
     }
+    if (lane < 16) {
+      const unsigned wd = (unsigned)__cvta_generic_to_shared(&melw[wid][buf][lane]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(wd), "l"(P.t.mel_ab + k0 + lane) : "memory");
+    }
   };
   fetch_tile(0, 0);
 
@@ -276,9 +282,20 @@ __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParam
   double s1 = 0, s2 = 0, s11 = 0, s12 = 0, s22 = 0, mx = 0, mant = 1.0; int ex = 0, nv = 0;
   double vals[34];                              // a small band with its two neighbours: vals[0] = x[start - 1], vals[1 + i] = x[start + i]
   double xprev = 0.0, a28 = 0.0, csum = 0.0;
-  double mel[14];
+  // mel energies: at most two consecutive filters are open at a time -- they live in two registers by parity; a filter that
+  // ends goes straight into the cepstrum sums (log, then its column of the DCT), in filter order as the reference sums them
+  double melA = 0.0, melB = 0.0, cep[14];
 #pragma unroll
-  for (int q = 0; q < 14; ++q) mel[q] = 0.0;
+  for (int j = 0; j < 14; ++j) cep[j] = 0.0;
+  int next_q = 0;                               // next filter the cepstrum is waiting for (uniform)
+  auto cep_add = [&](int q, double energy) {    // vector.c:372-391; filters without support come in with energy 0
+    for (; next_q <= q; ++next_q) {
+      const double en = (next_q == q) ? energy : 0.0;
+      const double lg = log(en < 2e-42 ? 2e-42 : en);               // XTRACT_LOG_LIMIT
+#pragma unroll
+      for (int j = 0; j < 14; ++j) cep[j] = __dadd_rn(cep[j], __dmul_rn(lg, __ldg(P.t.dct + j * 14 + next_q)));
+    }
+  };
   int pending = -1;                             // sub-band waiting for its right neighbour
   BandRaw pend; double pend_mx = 0.0;
   pend.s1 = pend.s2 = pend.s11 = pend.s12 = pend.s22 = pend.ls = pend.x0 = pend.lo_sum = pend.hi_sum = pend.cplx = 0.0;
@@ -293,13 +310,12 @@ __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParam
       asm volatile("cp.async.wait_all;" ::: "memory");
       __syncwarp();                             // every lane's part has landed, and every lane is done with the tile before
       tile = tiles[wid][(k0 >> 4) & 1];
+      mw = melw[wid][(k0 >> 4) & 1];
       if (k0 + 16 < AFX_NBIN) fetch_tile(k0 + 16, ((k0 >> 4) + 1) & 1);
     }
     const bool in14 = sg.b14 >= 0, in28 = sg.b28 >= 0;
     const bool small14 = in14 && P.band14_n[sg.b14] <= 32;
     double e0 = 0.0, e1 = 0.0;
-    const double* __restrict__ w0 = P.t.mel + (size_t)(sg.q0 < 0 ? 0 : sg.q0) * AFX_NBIN;
-    const double* __restrict__ w1 = w0 + AFX_NBIN;
     if (pending >= 0) {                         // the first bin of this segment is the right neighbour of the band that just ended
       vals[nv + 1] = tile[k0 & 15][lane + 1];
       csum += lane_finish_band(B, P, TF, slot, rel, pending, live, vals, pend, pend_mx);
@@ -321,12 +337,15 @@ __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParam
         if (small14) vals[++nv] = x;
       }
       if (in28) a28 = fma(x, x, a28);           // SampleAnalyser.cpp:2007-2048
-      if (sg.nq > 0) e0 = fma(x, __ldg(w0 + k), e0);      // vector.c:350-391, on the filters' supports
-      if (sg.nq > 1) e1 = fma(x, __ldg(w1 + k), e1);
+      const double2 wab = mw[k & 15];            // vector.c:350-391, on the filters' supports (weights outside are 0 and unused)
+      if (sg.nq > 0) e0 = fma(x, wab.x, e0);
+      if (sg.nq > 1) e1 = fma(x, wab.y, e1);
     }
     xprev = x;
-    if (sg.nq > 0) mel[sg.q0] += e0;
-    if (sg.nq > 1) mel[sg.q0 + 1] += e1;
+    if (sg.nq > 0) { if (sg.q0 & 1) melB += e0; else melA += e0; }
+    if (sg.nq > 1) { if (sg.q0 & 1) melA += e1; else melB += e1; }
+    if (sg.fin & 1) { if (sg.q0 & 1) { cep_add(sg.q0, melB); melB = 0.0; } else { cep_add(sg.q0, melA); melA = 0.0; } }
+    if (sg.fin & 2) { if (sg.q0 & 1) { cep_add(sg.q0 + 1, melA); melA = 0.0; } else { cep_add(sg.q0 + 1, melB); melB = 0.0; } }
     if (sg.end28) { if (live) B.fv[(size_t)FV_BANDS28 * TF + (size_t)slot * 28 + sg.b28] = a28; a28 = 0.0; }
     if (sg.end14) {
       pend.s1 = s1; pend.s2 = s2; pend.s11 = s11; pend.s12 = s12; pend.s22 = s22; pend.ls = mant; pend.x0 = (double)ex; pend_mx = mx;
@@ -337,17 +356,11 @@ __global__ void __launch_bounds__(BLW * 32) k_bands_lane(AfxBatchDev B, AfxParam
   if (!live) return;
   for (int b = 0; b < 28; ++b)                   // bands that lie beyond the spectrum hold no bins (SampleAnalyser.cpp:2026-2045)
     if (P.band28_e[b] <= P.band28_s[b]) B.fv[(size_t)FV_BANDS28 * TF + (size_t)slot * 28 + b] = 0.0;
-  // ---- cepstrum: log of the mel energies, unnormalised DCT-II in the reference's order (vector.c:372-391) ----
-  double lg[14];
+  // ---- cepstrum: log of the mel energies, unnormalised DCT-II in the reference's order (vector.c:372-391); filters that
+  // never ended (no support) enter with the log limit ----
+  cep_add(13, 0.0);
 #pragma unroll
-  for (int q = 0; q < 14; ++q) lg[q] = log(mel[q] < 2e-42 ? 2e-42 : mel[q]);     // XTRACT_LOG_LIMIT
-#pragma unroll 1
-  for (int j = 0; j < 14; ++j) {
-    double a = 0.0;
-#pragma unroll
-    for (int m = 0; m < 14; ++m) a = __dadd_rn(a, __dmul_rn(lg[m], __ldg(P.t.dct + j * 14 + m)));
-    B.fv[(size_t)FV_CEPSTRUM * TF + (size_t)slot * 14 + j] = a;
-  }
+  for (int j = 0; j < 14; ++j) B.fv[(size_t)FV_CEPSTRUM * TF + (size_t)slot * 14 + j] = cep[j];
   B.fs[(size_t)FS_SPEC_CONTRAST * TF + slot] = csum / 14.0;
 }
 

@@ -100,7 +100,7 @@ struct AfxBandSeg {
   short k0, k1;             // bins [k0, k1)
   signed char b14, b28;     // sub-band / frequency band of the run, -1 = none
   signed char q0, nq;       // first mel filter covering the run and how many (0..2)
-  unsigned char start14, end14, end28, pad;   // the run starts / ends its sub-band, ends its frequency band
+  unsigned char start14, end14, end28, fin;   // the run starts / ends its sub-band, ends its frequency band; fin bit 0 / 1: mel filter q0 / q0 + 1 ends with the run
 };
 
 struct AfxTables {          // per-context constant tables in device memory
@@ -113,6 +113,7 @@ struct AfxTables {          // per-context constant tables in device memory
   const double2* fft_t3_2048;   // [7][256]  exp(-2 pi i r j / 2048), r = 1..7
   const double* rwindow;    // [512] rhythm Hann x 0.5 (see k_rhythm_polar)
   const double* mel;        // [14][1024]
+  const double2* mel_ab;    // [1024] per bin: weights of the (at most two) mel filters covering it, in filter order (k_bands_lane)
   const double* dct;        // [14][14] cos(pi n/14 (m+0.5)), row n
   const float* rs_imp;      // [69632] resampler wing
   unsigned int* work_ctr;   // [64] work-claim counters of the persistent kernels (zeroed on the launching stream)

@@ -9,11 +9,12 @@ import csv, json, os, sys
 GROUPS = {
     "spectrum": ["k_spectrum", "k_flux"],
     "rhythm": ["k_rhythm_front", "k_rhythm_polar", "k_rhythm_whiten", "k_rhythm_odf", "k_rhythm_power", "k_rhythm_median", "k_rhythm_back"],
-    "pitch": ["k_pitch"],
+    "pitch": ["k_pitch", "k_pitch_hop"],
     "bands": ["k_bands_a_big", "k_bands_a_small", "k_bands_b", "k_bands_select", "k_bands_lane"],
     "autocorr": ["k_autocorr"],
-    "peaks": ["k_whiten_main", "k_peaks_count", "k_peaks_file"],
+    "peaks": ["k_whiten_main", "k_peaks_count", "k_peaks_file", "k_peaks_pipe"],
     "stats": ["k_stats"],
+    "condition": ["k_downmix", "k_trim", "k_eff"],
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
