@@ -47,17 +47,19 @@ __device__ __forceinline__ double band_write(AfxBatchDev& B, size_t TF, int slot
 // Round-2 schedule: two kernels instead of seven launches.
 //
 //   k_bands_select  warp per (frame, LARGE sub-band: the five with more than 32 bins): only what needs the whole band
-//                   at once -- the order statistics behind the contrast (exact bisection, as subband<C> above) and the
+//                   at once -- the order statistics behind the contrast (exact radix select, subband_select<C> below) and the
 //                   peak count against 0.25 x band max.  3 doubles per band go to the per-frame scratch record.
 //   k_bands_lane    LANE per frame, 32 consecutive frame slots per warp: everything that is a running sum over the bins
 //                   of a frame -- the five correlation sums, log-sum and maximum of all 14 sub-bands, the 28 frequency
 //                   bands, the 14 mel energies -- walks the row once, bin by bin, with NO cross-lane reduction at all
 //                   (the first schedule spent most of its instructions in warp reductions of 7 sums x 14 bands); the
 //                   nine sub-bands of <= 32 bins keep their values in a per-lane array and are ranked there; the
-//                   per-band epilogue (log / exp / pow chains) and the DCT run on all 32 lanes.  The magnitude rows
-//                   reach the lanes through a transposed shared-memory tile (32 bins x 33 frames: the extra column is
-//                   the frame before the warp's first, for the flux of lane 0), loaded with coalesced 256-byte reads.
-//                   Sums run in bin order -- the reference's own order.
+//                   per-band epilogue (log / exp / pow chains) runs on all 32 lanes, and a mel filter that ends goes
+//                   straight into the cepstrum sums.  The bin axis is cut by the host into runs inside which nothing
+//                   changes (AfxBandSeg), so the inner loop has no control flow.  The magnitude rows reach the lanes through
+//                   transposed 16-bin shared-memory tiles (16 bins x 33 frames: the extra column is the frame before the
+//                   warp's first, for the flux of lane 0), double buffered with cp.async: the next tile and its mel
+//                   weights land while the warp walks the current one.  Sums run in bin order -- the reference's own order.
 #define BR2_STRIDE 16       // doubles per frame: 5 large bands x (lo_sum, hi_sum, complexity) + pad
 #define BIG0 9              // first large sub-band (41, 61, 96, 148, 287 bins)
 

@@ -18,7 +18,10 @@
 //   k_ext_tc     3xTF32 on the 5th-generation tensor cores: tcgen05.mma kind::tf32, M = 128 frames per CTA, accumulators
 //                in TMEM.  Every FP32 operand is split x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and
 //                A W ~= A_hi W_hi + A_lo W_hi + A_hi W_lo (the dropped lo x lo term is 2^-22 relative): three MMAs per
-//                K step into the same accumulator.  Operands are staged by the CTA's threads in the canonical K-major
+//                K step.  The tensor core adds into its FP32 accumulator with TRUNCATION, so the error grows with the number
+//                of MMAs chained into one accumulator (1.8e-5 on an MFCC coefficient with a single one): the K steps are dealt
+//                round robin to EIGHT accumulator sets (all 512 TMEM columns) that the epilogue adds in FP64, small terms
+//                first (0.47 x tolerance).  Operands are staged by the CTA's threads in the canonical K-major
 //                SWIZZLE_128B shared-memory layout (8-row x 128-byte atoms); one thread issues the MMAs and commits
 //                them to an mbarrier; the epilogue reads the accumulators back with tcgen05.ld.
 // Both feed the same FP64 epilogue.  tests/test_gpu_ext.py compares both with the FP64 restatement: north_star's rule is
