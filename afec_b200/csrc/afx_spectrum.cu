@@ -361,6 +361,12 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
     B.fs[(size_t)FS_SPEC_SPREAD * TF + slot] = spread;
     B.fs[(size_t)FS_SPEC_SKEW * TF + slot] = have_sk ? mu3 * inv3 : 0.0;
     B.fs[(size_t)FS_SPEC_KURT * TF + slot] = have_sk ? (mu4 * inv3) / spread - 3.0 : 0.0;
+  }
+  // the other half of the frame's scalar tail runs on the first thread of the group's SECOND warp, next to the one above (one
+  // thread doing both was a tenth of this kernel's time)
+  if (gt == 32) {
+    const double n = (double)nb;
+    const double S2 = acc[1];
     // flatness (SA.cpp:129-133, 1898-1913): min(LinToDb(gmean / mean) / -60, 1) with gmean = exp(log-sum / n), taken in
     // the log domain: log(gmean / mean) = log-sum / n - log(mean) (one log instead of exp + division + log).
     // LinToDb's branches: ratio <= 1e-12f -> -200 dB; an all-zero window has ratio 0 (Statistics.cpp:568-571) -> 1.0
@@ -384,7 +390,8 @@ __global__ void __launch_bounds__(SG * NG, 1) k_spectrum(AfxBatchDev B, AfxParam
   }
   S1p = S1; S2p = acc[1];
   // no barrier here: the next frame's first shared-memory writes (xch[0..1, 4..5], the FFT buffer) touch nothing
-  // that is still read after the last group_sum (only xch[19], by thread 0)
+  // that is still read after the last group_sum (only xch[19], by thread 0, and xch[20..21], by thread 32 -- rewritten only
+  // behind the next frame's FFT barriers)
     }
   }
 }
