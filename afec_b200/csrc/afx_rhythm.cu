@@ -141,24 +141,44 @@ __device__ __forceinline__ void polar_unpack(float* __restrict__ row, const doub
     polar_store(row, k, Xa);
   }
 }
+// A CTA walks PI consecutive groups of PF frames: the slot -> file -> state chain of dependent loads in front of a frame's
+// samples (two levels, ~1.5 k cycles: a tenth of a one-group CTA's life, ncu) is fetched for the NEXT group while the
+// current one is transformed.
+#define PI 4
+struct PolarMeta { int fi, t; bool live; int start_off, audible, lead; long long mono_off; double fs; };
+__device__ __forceinline__ PolarMeta polar_meta(const AfxBatchDev& B, int rel)
+{
+  PolarMeta m;
+  const bool in_range = rel < B.g_rslots;
+  const int slot = B.rslot0 + (in_range ? rel : 0);
+  m.fi = B.rslot_file[slot];
+  const AfxFile* __restrict__ fp = B.files + m.fi;
+  const AfxState* __restrict__ sp = B.state + m.fi;
+  m.t = slot - fp->rframe_off;
+  m.live = in_range && fp->status == 0 && m.t < sp->Fr;     // both halves of a warp run the transform (warp-wide sync)
+  m.start_off = sp->start_off; m.audible = sp->audible; m.lead = sp->lead; m.fs = sp->fs; m.mono_off = fp->mono_off;
+  return m;
+}
 __global__ void __launch_bounds__(PF * 16, 5) k_rhythm_polar(AfxBatchDev B, AfxParams P)
 {
   __shared__ double2 sbuf[PF][256 + 16];
   const int h = threadIdx.x >> 4, ht = threadIdx.x & 15;
   double2* buf = sbuf[h];
-  const int rel = blockIdx.x * PF + h;
-  const bool in_range = rel < B.g_rslots;
-  const int slot = B.rslot0 + (in_range ? rel : 0);
-  const int fi = B.rslot_file[slot];
-  const AfxFile* __restrict__ fp = B.files + fi;
-  const int t = slot - fp->rframe_off;
-  const AfxState st = B.state[fi];
-  const bool live = in_range && fp->status == 0 && t < st.Fr;   // both halves of a warp run the transform (warp-wide sync)
-  double2 v[16];
-  polar_load(v, B.mono + fp->mono_off, st, t * AFX_RHOP, live, ht, reinterpret_cast<const double2*>(P.t.rwindow));
-  fft16_run<256>(v, buf, FftTw{ P.t.fft_t2, nullptr }, ht, FftSyncWarp());
-  if (!live) return;
-  polar_unpack(B.rpolar + (size_t)rel * AFX_RROW, buf, ht, P.t.tw512);
+  int rel = blockIdx.x * (PF * PI) + h;
+  PolarMeta nx = polar_meta(B, rel);
+#pragma unroll 1
+  for (int it = 0; it < PI; ++it, rel += PF) {
+    if (rel - h >= B.g_rslots) break;                          // uniform: the whole group lies past the end
+    const PolarMeta m = nx;
+    AfxState st;                                               // the fields polar_load / mdata read
+    st.start_off = m.start_off; st.audible = m.audible; st.lead = m.lead; st.fs = m.fs;
+    double2 v[16];
+    polar_load(v, B.mono + m.mono_off, st, m.t * AFX_RHOP, m.live, ht, reinterpret_cast<const double2*>(P.t.rwindow));
+    if (it + 1 < PI) nx = polar_meta(B, rel + PF);
+    fft16_run<256>(v, buf, FftTw{ P.t.fft_t2, nullptr }, ht, FftSyncWarp());
+    if (m.live) polar_unpack(B.rpolar + (size_t)rel * AFX_RROW, buf, ht, P.t.tw512);
+    __syncwarp();                                              // the warp's two buffers are read before the next transform writes them
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -771,7 +791,7 @@ void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s,
     k_rhythm_front<<<B.g_files, RF_THREADS, RF_SMEM, s>>>(B, P); ++*launches;
   } else {
     const int fb = (B.g_rslots + OW * OB - 1) / (OW * OB);
-    k_rhythm_polar<<<(B.g_rslots + PF - 1) / PF, PF * 16, 0, s>>>(B, P); ++*launches;
+    k_rhythm_polar<<<(B.g_rslots + PF * PI - 1) / (PF * PI), PF * 16, 0, s>>>(B, P); ++*launches;
     k_rhythm_whiten<<<B.g_files, 256, 0, s>>>(B, P); ++*launches;
     k_rhythm_odf<<<fb, OW * 32, 0, s>>>(B, P); ++*launches;
     k_rhythm_power<<<(B.g_rslots + 127) / 128, 128, 0, s>>>(B, P); ++*launches;
