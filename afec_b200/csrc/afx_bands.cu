@@ -166,6 +166,7 @@ __device__ __forceinline__ void subband_select(const AfxParams& P, int b, const 
     }
     const int nlo = max(0, lo - 8);
     w = lo - nlo; lo = nlo;
+    __syncwarp();                                       // histogram reads above are over before the next pass clears it
   }
   // sums over the band with the two bounds
   int nlt0 = 0, ngt1 = 0; double slt0 = 0.0, sge1 = 0.0, sgt1 = 0.0;
