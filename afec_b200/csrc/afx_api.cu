@@ -379,8 +379,15 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   for (int r = 1; r < 4; ++r) for (int j = 0; j < 256; ++j) { const double a = -2.0 * pi * (double)(r * j) / 1024.0; ft3a[2 * ((r - 1) * 256 + j)] = std::cos(a); ft3a[2 * ((r - 1) * 256 + j) + 1] = std::sin(a); }
   for (int r = 1; r < 8; ++r) for (int j = 0; j < 256; ++j) { const double a = -2.0 * pi * (double)(r * j) / 2048.0; ft3b[2 * ((r - 1) * 256 + j)] = std::cos(a); ft3b[2 * ((r - 1) * 256 + j) + 1] = std::sin(a); }
 
+  // float32 twiddles of the autocorrelation's transforms (afx_autocorr.cu): pass 2, pass 3 (N = 512), bin-pair unpack (N = 1024)
+  std::vector<float> actw(2 * (240 + 256 + 257));
+  for (int r = 1; r < 16; ++r) for (int k = 0; k < 16; ++k) { const double a = -2.0 * pi * (double)(r * k) / 256.0; actw[2 * ((r - 1) * 16 + k)] = (float)std::cos(a); actw[2 * ((r - 1) * 16 + k) + 1] = (float)std::sin(a); }
+  for (int j = 0; j < 256; ++j) { const double a = -2.0 * pi * (double)j / 512.0; actw[2 * (240 + j)] = (float)std::cos(a); actw[2 * (240 + j) + 1] = (float)std::sin(a); }
+  for (int k = 0; k <= 256; ++k) { const double a = -2.0 * pi * (double)k / 1024.0; actw[2 * (496 + k)] = (float)std::cos(a); actw[2 * (496 + k) + 1] = (float)std::sin(a); }
+
   size_t off = 0;
   auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_actw = place(actw.size() * 4);
   const size_t o_win = place(window.size() * 8), o_rwin = place(rwindow.size() * 8), o_mel = place(mel.size() * 8),
     o_dct = place(dct.size() * 8), o_tw = place(tw2048.size() * 8), o_tw5 = place(tw512.size() * 8), o_imp = place(imp.size() * 4),
     o_ft2 = place(ft2.size() * 8), o_ft3a = place(ft3a.size() * 8), o_ft3b = place(ft3b.size() * 8), o_ctr = place(64 * 4),
@@ -439,6 +446,8 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   cudaMemcpy(base + o_ft2, ft2.data(), ft2.size() * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(base + o_ft3a, ft3a.data(), ft3a.size() * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(base + o_ft3b, ft3b.data(), ft3b.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(base + o_actw, actw.data(), actw.size() * 4, cudaMemcpyHostToDevice);
+  P.t.ac_tw = (const float2*)(base + o_actw);
   e = cudaMemcpy(base + o_imp, imp.data(), imp.size() * 4, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { afx_destroy(ctx); return fail(nullptr, AFX_ERR_CUDA, "cudaMemcpy(tables)", e); }
   P.t.window = (const double*)(base + o_win); P.t.rwindow = (const double*)(base + o_rwin);

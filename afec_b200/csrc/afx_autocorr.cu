@@ -13,7 +13,7 @@
 // owns 9 consecutive lags and slides a 9-sample window along j, so every pair of shared-memory loads
 // feeds 9 DFMAs (the FP64 pipe, not shared memory, is the limit); see ac_rounds for how the triangle of
 // lag x sample work is spread over the lanes.
-#include "afx_common.cuh"
+#include "afx_fft16.cuh"
 #include <cstdlib>
 
 #define AW 4                // warps (frames) per CTA
@@ -110,11 +110,171 @@ __device__ __forceinline__ double ac_rounds_f32(const float* __restrict__ x, int
   return best;
 }
 
-template <bool F32>
+// -------------------------------------------------------------------------------------------------
+// FFT form (round 2, default): the 529 x 529 / 2 products are a linear correlation, and since the FP32 demotion nothing ties
+// the kernel to the reference's summation order any more, so R = IFFT(|FFT(x)|^2) on the window zero-padded to 1024:
+//   z[m] = x[2m] + i x[2m+1]  ->  512-point complex FFT  ->  bin-pair unpack to 2 X[k]  ->  P[k] = |2 X[k]|^2
+//   V[k] = (E - D s_k, -D c_k),  V[512-k] = (E + D s_k, -D c_k)   with E = P[k] + P[512-k], D = P[k] - P[512-k],
+//   (c_k, s_k) = (cos, sin)(2 pi k / 1024)                            (the real-output inverse as ONE more forward transform)
+//   y = FFT512(V):  R[2m] = Re y[m],  R[2m+1] = -Im y[m]             (x 4096: the scale cancels in R[i] / R[0])
+// The circular correlation of length 1024 is the linear one for lags < 1024 - (width - 1) = 496; the 33 lags above that
+// (at most 33 products each) are summed directly.  ~60 kflop per frame instead of 280 k; FP32 error of R[i] / R[0] measured
+// against FP64 sums: <= 2.1e-7 absolute, <= 0.17 of the tolerance 1e-6 + 1e-4 |v| (numpy emulation over 4000 windows incl.
+// DC offsets and quiet files, profiles/README.md).  AFX_AUTOCORR_DIRECT=1 keeps the direct FP32 sums, AFX_AUTOCORR_FP64=1
+// the FP64 ones.  Transform: radix 16 x 16 x 2 (afx_fft16.cuh's scheme in float2), one warp per frame, 16 points per lane;
+// the first pass knows that inputs 9..15 of every butterfly are zero padding, the last pass of the second transform keeps
+// its outputs in registers (only lags < 496 are wanted) and takes the maximum right there.
+__device__ __forceinline__ float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 c_mul(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)); }
+__device__ __forceinline__ void c_r4(float2& a0, float2& a1, float2& a2, float2& a3)
+{
+  const float2 s02 = c_add(a0, a2), d02 = c_sub(a0, a2), s13 = c_add(a1, a3), d13 = c_sub(a1, a3);
+  const float2 md = make_float2(d13.y, -d13.x);          // -i (a1 - a3)
+  a0 = c_add(s02, s13); a1 = c_add(d02, md); a2 = c_sub(s02, s13); a3 = c_sub(d02, md);
+}
+#define CF_C1 0.92387953251128673848f
+#define CF_S1 0.38268343236508978178f
+#define CF_H 0.70710678118654752440f
+__device__ __forceinline__ float2 c_w16_1(float2 a) { return make_float2(fmaf(a.x, CF_C1, a.y * CF_S1), fmaf(a.y, CF_C1, -(a.x * CF_S1))); }
+__device__ __forceinline__ float2 c_w16_2(float2 a) { return make_float2((a.x + a.y) * CF_H, (a.y - a.x) * CF_H); }
+__device__ __forceinline__ float2 c_w16_3(float2 a) { return make_float2(fmaf(a.x, CF_S1, a.y * CF_C1), fmaf(a.y, CF_S1, -(a.x * CF_C1))); }
+__device__ __forceinline__ float2 c_w16_4(float2 a) { return make_float2(a.y, -a.x); }
+__device__ __forceinline__ float2 c_w16_6(float2 a) { return make_float2((a.y - a.x) * CF_H, -(a.x + a.y) * CF_H); }
+// twiddles + row transforms of the 4 x 4 decomposition (the column transforms come first and differ, see below)
+__device__ __forceinline__ void c_dft16_rows(float2 (&v)[16])
+{
+  v[5] = c_w16_1(v[5]);  v[9] = c_w16_2(v[9]);   v[13] = c_w16_3(v[13]);
+  v[6] = c_w16_2(v[6]);  v[10] = c_w16_4(v[10]); v[14] = c_w16_6(v[14]);
+  v[7] = c_w16_3(v[7]);  v[11] = c_w16_6(v[11]);
+  { const float2 a = v[15]; v[15] = make_float2(-fmaf(a.x, CF_C1, a.y * CF_S1), fmaf(a.x, CF_S1, -(a.y * CF_C1))); }   // W16^9
+  c_r4(v[0], v[1], v[2], v[3]);
+  c_r4(v[4], v[5], v[6], v[7]);
+  c_r4(v[8], v[9], v[10], v[11]);
+  c_r4(v[12], v[13], v[14], v[15]);
+}
+// 16-point forward DFT in registers; X[m + 4 n] ends up in v[4 m + n] (FFT_REG16)
+__device__ __forceinline__ void c_dft16(float2 (&v)[16])
+{
+  c_r4(v[0], v[4], v[8], v[12]);
+  c_r4(v[1], v[5], v[9], v[13]);
+  c_r4(v[2], v[6], v[10], v[14]);
+  c_r4(v[3], v[7], v[11], v[15]);
+  c_dft16_rows(v);
+}
+// the same with inputs 9..15 known to be zero: column 0 holds (v0, v4, v8, 0), columns 1..3 hold (v_c, v_c+4, 0, 0)
+__device__ __forceinline__ void c_dft16_pruned(float2 (&v)[16])
+{
+  {
+    const float2 s02 = c_add(v[0], v[8]), d02 = c_sub(v[0], v[8]), a1 = v[4], md = make_float2(a1.y, -a1.x);
+    v[0] = c_add(s02, a1); v[4] = c_add(d02, md); v[8] = c_sub(s02, a1); v[12] = c_sub(d02, md);
+  }
+#pragma unroll
+  for (int c = 1; c < 4; ++c) {
+    const float2 a0 = v[c], a1 = v[c + 4], md = make_float2(a1.y, -a1.x);
+    v[c] = c_add(a0, a1); v[c + 4] = c_add(a0, md); v[c + 8] = c_sub(a0, a1); v[c + 12] = c_sub(a0, md);
+  }
+  c_dft16_rows(v);
+}
+#define ACT_T2 0            // [15][16] exp(-2 pi i r k / 256), r = 1..15   (AfxTables::ac_tw, float2)
+#define ACT_T3 240          // [256]    exp(-2 pi i j / 512)
+#define ACT_UN 496          // [257]    exp(-2 pi i k / 1024)
+#define ACB 544             // float2 per frame: 512 + one pad per 16 (FFT_PHYS)
+#define ACX 576             // staged window floats per frame (zero from `width` on; the packed pairs read up to 575)
+#define AC_LIN 496          // lags below this come out of the 1024-point circular correlation unaliased
+
+// passes 1 and 2 of the 512-point transform (16 x 16); the radix-2 pass that follows is left to the caller
+template <bool PRUNED>
+__device__ __forceinline__ void acf_fft_p12(float2 (&v)[16], float2* __restrict__ buf, const float2* __restrict__ tw, int lane)
+{
+  if (PRUNED) c_dft16_pruned(v); else c_dft16(v);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) buf[lane * 17 + q] = v[FFT_REG16(q)];
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = buf[FFT_PHYS(lane + 32 * r)];
+  __syncwarp();
+  const int k = lane & 15;
+#pragma unroll
+  for (int r = 1; r < 16; ++r) v[r] = c_mul(v[r], __ldg(tw + ACT_T2 + (r - 1) * 16 + k));
+  c_dft16(v);
+  const int base = (lane - k) * 16 + k;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) buf[FFT_PHYS(base + q * 16)] = v[FFT_REG16(q)];
+  __syncwarp();
+}
+
+// x: the staged window (ACX floats, zero from `width` on); returns max(R[i]) over lags lo <= i < width (floored at 0), r0 = R[0]
+__device__ __forceinline__ float ac_fft(const float* __restrict__ x, float2* __restrict__ buf, const float2* __restrict__ tw,
+                                        int width, int lane, int lo, float& r0)
+{
+  float2 v[16];
+#pragma unroll
+  for (int r = 0; r < 9; ++r) v[r] = reinterpret_cast<const float2*>(x)[lane + 32 * r];
+#pragma unroll
+  for (int r = 9; r < 16; ++r) v[r] = make_float2(0.f, 0.f);
+  acf_fft_p12<true>(v, buf, tw, lane);
+  // pass 3 (radix 2), in place: butterfly i owns slots i and i + 256
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const int i = lane + 32 * b;
+    const float2 a = buf[FFT_PHYS(i)], c = c_mul(buf[FFT_PHYS(i + 256)], __ldg(tw + ACT_T3 + i));
+    buf[FFT_PHYS(i)] = c_add(a, c); buf[FFT_PHYS(i + 256)] = c_sub(a, c);
+  }
+  __syncwarp();
+  // unpack to the power spectrum and pack the inverse's input, in place: the pair (k, 512 - k) belongs to one lane
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    const int k = (c < 8) ? lane + 32 * c : 256;
+    if (c == 8 && lane != 0) break;
+    const float2 zk = buf[FFT_PHYS(k)], zr = buf[FFT_PHYS((512 - k) & 511)];
+    const float2 E = make_float2(zk.x + zr.x, zk.y - zr.y);          // Z[k] + conj(Z[512 - k])
+    const float2 O = make_float2(zk.y + zr.y, zr.x - zk.x);          // (Z[k] - conj(Z[512 - k])) / i
+    const float2 w = __ldg(tw + ACT_UN + k);                         // (cos, -sin)(2 pi k / 1024)
+    const float2 T = c_mul(w, O);
+    const float2 Xa = c_add(E, T), Xb = c_sub(E, T);                 // 2 X[k], conj(2 X[512 - k])
+    const float Pa = fmaf(Xa.x, Xa.x, Xa.y * Xa.y), Pb = fmaf(Xb.x, Xb.x, Xb.y * Xb.y);
+    const float Es = Pa + Pb, D = Pa - Pb, Ds = D * -w.y, Dc = D * w.x;
+    buf[FFT_PHYS(k)] = make_float2(Es - Ds, -Dc);
+    if (k > 0 && k < 256) buf[FFT_PHYS(512 - k)] = make_float2(Es + Ds, -Dc);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = buf[FFT_PHYS(lane + 32 * r)];
+  __syncwarp();
+  acf_fft_p12<false>(v, buf, tw, lane);
+  // last pass: only y[i], i < 248, is wanted (lags 2 i and 2 i + 1 below AC_LIN): the maximum is taken from the registers
+  const int wlim = min(width, AC_LIN);
+  float best = 0.f;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const int i = lane + 32 * b;
+    const float2 a = buf[FFT_PHYS(i)], c = c_mul(buf[FFT_PHYS(i + 256)], __ldg(tw + ACT_T3 + i));
+    const float re = a.x + c.x, im = -(a.y + c.y);
+    if (b == 0) r0 = re;                                             // lane 0: R[0]
+    if (2 * i >= lo && 2 * i < wlim) best = fmaxf(best, re);
+    if (2 * i + 1 >= lo && 2 * i + 1 < wlim) best = fmaxf(best, im);
+  }
+  // the aliased lags, directly: lag AC_LIN + lane (and 528 on lane 0); x is zero from `width` on, so the sums end by themselves
+  if (width > AC_LIN) {
+    float acc = 0.f;
+    const float* __restrict__ xl = x + AC_LIN + lane;
+#pragma unroll 11
+    for (int j = 0; j < 33; ++j) acc = fmaf(x[j], xl[j], acc);
+    const float scale = 4096.f;                                      // the transforms' R carries 2^2 (unpack) x 1024 (no 1 / N)
+    if (AC_LIN + lane >= lo && AC_LIN + lane < width) best = fmaxf(best, acc * scale);
+    if (lane == 0 && 528 >= lo && 528 < width) best = fmaxf(best, x[0] * x[528] * scale);
+  }
+  return best;
+}
+
+// MODE 0: FP64 direct sums, 1: FP32 direct sums, 2: FP32 FFT form
+template <int MODE>
 __global__ void __launch_bounds__(AW * 32) k_autocorr(AfxBatchDev B, AfxParams P)
 {
-  __shared__ double xs[F32 ? 1 : AW][AC_XS];
-  __shared__ float xf[F32 ? AW : 1][ACF_XS];
+  __shared__ double xs[MODE == 0 ? AW : 1][AC_XS];
+  __shared__ float xf[MODE == 0 ? 1 : AW][MODE == 2 ? ACX : ACF_XS];
+  __shared__ float2 fb[MODE == 2 ? AW : 1][MODE == 2 ? ACB : 1];
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int rel = blockIdx.x * AW + wid;
@@ -171,7 +331,17 @@ __global__ void __launch_bounds__(AW * 32) k_autocorr(AfxBatchDev B, AfxParams P
   const int width = min(remaining, P.ac_width);
   const int lo = period / 2;
   double r0 = 0.0, best;                           // the result is floored at 0 (Autocorrelation.cpp:96-103)
-  if (F32) {
+  if (MODE == 2) {
+    float* x = xf[wid];
+    for (int k = lane; k < ACX; k += 32) {
+      const int j = n0 + start + k - st.start_off;
+      x[k] = (k < width && j >= 0 && j < st.audible) ? __ldg(mono + st.lead + j) : 0.0f;
+    }
+    __syncwarp();
+    float r0f = 0.f;
+    best = (double)ac_fft(x, fb[wid], P.t.ac_tw, width, lane, lo, r0f);
+    r0 = (double)r0f;
+  } else if (MODE == 1) {
     // raw mono samples of the conditioned window: mdata() without its scale (trim and padding as there)
     float* x = xf[wid];
     for (int k = lane; k < ACF_XS; k += 32) {
@@ -195,8 +365,13 @@ __global__ void __launch_bounds__(AW * 32) k_autocorr(AfxBatchDev B, AfxParams P
 void afx_launch_autocorr(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s, long long* launches)
 {
   if (B.g_slots <= 0) return;
-  static const bool fp64 = [] { const char* e = getenv("AFX_AUTOCORR_FP64"); return e && atoi(e) != 0; }();
-  if (fp64) k_autocorr<false><<<(B.g_slots + AW - 1) / AW, AW * 32, 0, s>>>(B, P);
-  else k_autocorr<true><<<(B.g_slots + AW - 1) / AW, AW * 32, 0, s>>>(B, P);
+  static const int mode = [] {
+    const char* e = getenv("AFX_AUTOCORR_FP64"); if (e && atoi(e) != 0) return 0;
+    e = getenv("AFX_AUTOCORR_DIRECT"); return (e && atoi(e) != 0) ? 1 : 2;
+  }();
+  const int grid = (B.g_slots + AW - 1) / AW;
+  if (mode == 0) k_autocorr<0><<<grid, AW * 32, 0, s>>>(B, P);
+  else if (mode == 1) k_autocorr<1><<<grid, AW * 32, 0, s>>>(B, P);
+  else k_autocorr<2><<<grid, AW * 32, 0, s>>>(B, P);
   ++*launches;
 }

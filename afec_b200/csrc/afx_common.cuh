@@ -112,6 +112,7 @@ struct AfxTables {          // per-context constant tables in device memory
   const double2* fft_t3_1024;   // [3][256]  exp(-2 pi i r j / 1024), r = 1..3
   const double2* fft_t3_2048;   // [7][256]  exp(-2 pi i r j / 2048), r = 1..7
   const double* rwindow;    // [512] rhythm Hann x 0.5 (see k_rhythm_polar)
+  const float2* ac_tw;      // [240 + 256 + 257] float32 twiddles of the autocorrelation's 512-point transforms (afx_autocorr.cu, ACT_*)
   const double* mel;        // [14][1024]
   const double2* mel_ab;    // [1024] per bin: weights of the (at most two) mel filters covering it, in filter order (k_bands_lane)
   const double* dct;        // [14][14] cos(pi n/14 (m+0.5)), row n

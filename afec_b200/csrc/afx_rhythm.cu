@@ -300,6 +300,117 @@ __global__ void __launch_bounds__(128) k_rhythm_power(AfxBatchDev B, AfxParams P
 }
 
 // -------------------------------------------------------------------------------------------------
+// Whitening + both onset functions as ONE producer / consumer pipeline per file (round 2, the default for launch groups
+// with at least two files per SM; the three kernels above remain for smaller groups).  The polar rows are read once and
+// never rewritten -- 4 KB of DRAM traffic per rhythm frame (polar write + this read) instead of 7:
+//   producers (8 warps, a thread per column 0..254 | dc) walk the file's frames in order with the peak memory in a
+//     register, RP_H rows of loads in flight, and put the whitened magnitudes into a shared-memory ring of two halves of
+//     RP_H frames; row 0 of a half repeats the last frame of the half before it (the complex-domain function of frame t
+//     needs |mag| of frame t - 1);
+//   consumers: 8 warps evaluate the complex-domain function of one frame each (phases of frames t, t-1, t-2 straight from
+//     global memory, requested before the wait for the producers), a ninth warp runs the in-order float32 power sums,
+//     one lane per frame.
+// The halves are handed over with named barriers (bar.arrive / bar.sync), one hand-over per RP_H frames, as in
+// k_peaks_pipe.  Values are those of the split kernels bit for bit (same device functions, same order of every sum).
+#define RP_P 8
+#define RP_C 7
+#define RP_H 7
+#define RP_ROWF 260         // floats per ring row: 256 + 4 (16-byte aligned rows on different bank groups for the lane-per-row power sums)
+#define RP_THREADS ((RP_P + RP_C + 1) * 32)
+// barrier ids as immediates (a register id makes ptxas reserve all 16 barriers of the CTA)
+template <int ID> __device__ __forceinline__ void rp_bar_sync_i() { asm volatile("bar.sync %0, %1;" :: "n"(ID), "n"(RP_THREADS) : "memory"); }
+template <int ID> __device__ __forceinline__ void rp_bar_arrive_i() { asm volatile("bar.arrive %0, %1;" :: "n"(ID), "n"(RP_THREADS) : "memory"); }
+__device__ __forceinline__ void rp_full_sync(int h) { if (h) rp_bar_sync_i<2>(); else rp_bar_sync_i<1>(); }
+__device__ __forceinline__ void rp_full_arrive(int h) { if (h) rp_bar_arrive_i<2>(); else rp_bar_arrive_i<1>(); }
+__device__ __forceinline__ void rp_free_sync(int h) { if (h) rp_bar_sync_i<4>(); else rp_bar_sync_i<3>(); }
+__device__ __forceinline__ void rp_free_arrive(int h) { if (h) rp_bar_arrive_i<4>(); else rp_bar_arrive_i<3>(); }
+__global__ void __launch_bounds__(RP_THREADS, 3) k_rhythm_pipe(AfxBatchDev B, AfxParams P)
+{
+  __shared__ __align__(16) float ring[2][RP_H + 1][RP_ROWF];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int fi = B.file_order[B.file0 + blockIdx.x];
+  const AfxFile f = B.files[fi];
+  if (f.status != 0) return;
+  const int Fr = B.state[fi].Fr;
+  if (Fr <= 0) return;
+  const float* __restrict__ rows = B.rpolar + (size_t)(f.rframe_off - B.rslot0) * AFX_RROW;
+  const int nb = (Fr + RP_H - 1) / RP_H;                      // batches of RP_H frames; batch b uses ring half b & 1
+  // barriers: 1 + h = "half h is full", 3 + h = "half h is free again"
+  if (wid < RP_P) {
+    const int tp = threadIdx.x;                                // column: bins 0..254, 255 = dc
+    const float* __restrict__ col = rows + tp;
+    const double relax = (double)P.r_relax, wfloor = (double)0.1f;
+    double psp = 0.0;
+    float lastw = 0.0f;
+    float nxt[RP_H];
+#pragma unroll
+    for (int q = 0; q < RP_H; ++q) nxt[q] = (q < Fr) ? __ldg(col + (size_t)q * AFX_RROW) : 0.0f;
+    for (int b = 0; b < nb; ++b) {
+      const int h = b & 1, t0 = b * RP_H;
+      if (b >= 2) rp_free_sync(h);                             // the consumers are done with batch b - 2
+      ring[h][0][tp] = lastw;
+#pragma unroll
+      for (int q = 0; q < RP_H; ++q) {
+        const float v = nxt[q];
+        nxt[q] = (t0 + RP_H + q < Fr) ? __ldg(col + (size_t)(t0 + RP_H + q) * AFX_RROW) : 0.0f;
+        if (t0 + q < Fr) {                                     // OnsetDetector.cpp:193-243
+          double a = (double)fabsf(v);
+          if (a < psp) a = __dadd_rn(a, __dmul_rn(__dsub_rn(psp, a), relax));
+          psp = a;
+          lastw = __fdiv_rn(v, (float)(wfloor > psp ? wfloor : psp));
+          ring[h][q + 1][tp] = lastw;
+        }
+      }
+      rp_full_arrive(h);
+    }
+  } else if (wid < RP_P + RP_C) {
+    const int cw = wid - RP_P;
+    float* __restrict__ odf_c = B.rodf + f.rframe_off;
+    for (int b = 0; b < nb; ++b) {
+      const int h = b & 1, t = b * RP_H + cw;
+      float ph[8], ph1[8];                                     // the phases of frame t - 2 are fetched per rising bin (L1: a neighbour's t - 1)
+      const float* __restrict__ p2 = rows + (size_t)(t >= 2 ? t - 2 : 0) * AFX_RROW + 256 + lane;
+      if (t < Fr) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int i = 256 + lane + 32 * c;
+          ph[c] = __ldg(rows + (size_t)t * AFX_RROW + i);
+          ph1[c] = (t >= 1) ? __ldg(rows + (size_t)(t - 1) * AFX_RROW + i) : 0.0f;
+        }
+      }
+      rp_full_sync(h);
+      if (t < Fr) {
+        const float* r0 = ring[h][cw + 1];
+        const float* r1 = ring[h][cw];
+        double total = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int i = lane + 32 * c;
+          const float cur = fabsf(r0[i]);
+          const float pmv = (t >= 1) ? fabsf(r1[i]) : 0.0f;
+          if (i < AFX_RBINS && cur > 0.01f && !(cur < pmv))
+            total += (double)odf_complex_bin(cur, pmv, ph[c], ph1[c], (t >= 2) ? __ldg(p2 + 32 * c) : 0.0f, t >= 1);
+        }
+        total = warp_sum(total);
+        if (lane == 0) odf_c[t] = __fmul_rn((float)total, P.r_norm_complex);
+      }
+      if (b + 2 < nb) rp_free_arrive(h);
+    }
+  } else {
+    float* __restrict__ odf_p = B.rodf + (size_t)B.TFr + f.rframe_off;
+    for (int b = 0; b < nb; ++b) {
+      const int h = b & 1, t = b * RP_H + lane;
+      rp_full_sync(h);
+      if (lane < RP_H && t < Fr) {
+        const float* r0 = ring[h][lane + 1];
+        odf_p[t] = __fmul_rn(odf_power_row(reinterpret_cast<const float4*>(r0), r0[255]), P.r_norm_power);
+      }
+      if (b + 2 < nb) rp_free_arrive(h);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // The fused front end: ONE kernel, one CTA per file (longest first), the polar rows never leave shared memory.
 // A CTA walks its file in spans of RF_S rhythm frames:
 //   1. 16 threads per frame: window, 256-point packed FFT, real unpack, polar conversion -> float32 row in the ring
@@ -791,10 +902,19 @@ void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s,
     k_rhythm_front<<<B.g_files, RF_THREADS, RF_SMEM, s>>>(B, P); ++*launches;
   } else {
     const int fb = (B.g_rslots + OW * OB - 1) / (OW * OB);
+    // the pipeline needs a CTA (a file) per resident slot to be worth it; AFX_RHYTHM_PIPE=0 / 1 forces the choice
+    static const int pipe = [] { const char* e = getenv("AFX_RHYTHM_PIPE"); return e ? atoi(e) : -1; }();
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     k_rhythm_polar<<<(B.g_rslots + PF * PI - 1) / (PF * PI), PF * 16, 0, s>>>(B, P); ++*launches;
-    k_rhythm_whiten<<<B.g_files, 256, 0, s>>>(B, P); ++*launches;
-    k_rhythm_odf<<<fb, OW * 32, 0, s>>>(B, P); ++*launches;
-    k_rhythm_power<<<(B.g_rslots + 127) / 128, 128, 0, s>>>(B, P); ++*launches;
+    if (pipe == 1 || (pipe < 0 && B.g_files >= 2 * sms)) {
+      k_rhythm_pipe<<<B.g_files, RP_THREADS, 0, s>>>(B, P); ++*launches;
+    } else {
+      k_rhythm_whiten<<<B.g_files, 256, 0, s>>>(B, P); ++*launches;
+      k_rhythm_odf<<<fb, OW * 32, 0, s>>>(B, P); ++*launches;
+      k_rhythm_power<<<(B.g_rslots + 127) / 128, 128, 0, s>>>(B, P); ++*launches;
+    }
   }
   { const int nchunks = (B.g_rslots + ML - 1) / ML; k_rhythm_median<<<(2 * nchunks + 63) / 64, 64, 0, s>>>(B); ++*launches; }
   k_rhythm_back<<<B.g_files, BT_THREADS, smem_back, s>>>(B, P); ++*launches;
