@@ -354,6 +354,7 @@ extern "C" int afx_create(const afx_config* cfg, afx_ctx** out)
   if (getenv("AFX_GROUP_FRAMES")) ctx->group_frames = std::max(1LL, atoll(getenv("AFX_GROUP_FRAMES")));
   if (getenv("AFX_GROUP_RFRAMES")) ctx->group_rframes = std::max(1LL, atoll(getenv("AFX_GROUP_RFRAMES")));
   if (getenv("AFX_PITCH_GENERIC")) ctx->pitch_generic = atoi(getenv("AFX_PITCH_GENERIC")) != 0;
+  if (getenv("AFX_RHYTHM_PIPE")) ctx->rhythm_pipe = atoi(getenv("AFX_RHYTHM_PIPE")) != 0 ? 1 : 0;
   if (getenv("AFX_RHYTHM_FUSED")) ctx->rhythm_fused_min = atoi(getenv("AFX_RHYTHM_FUSED")) != 0 ? 0 : 0x7fffffff;
 
   // ---- constant tables ----
@@ -918,6 +919,7 @@ extern "C" int afx_batch_compute(afx_batch* b)
     AfxBatchDev D = b->dev;
     D.file0 = g.file0; D.g_files = g.nfiles; D.slot0 = g.slot0; D.g_slots = g.nslots; D.rslot0 = g.rslot0; D.g_rslots = g.nrslots;
     D.rhythm_fused = ctx->rhythm_fused(g.nfiles) ? 1 : 0;
+    D.rhythm_pipe = ctx->rhythm_pipe;
     D.pitch_generic = ctx->pitch_generic ? 1 : 0;
     // every chain keeps to its own stream across groups, so the reuse of a chain's group scratch stays ordered
 #ifdef AFX_HAVE_AUTOCORR

@@ -309,6 +309,7 @@ struct AfxBatchDev {
   double* scratch;    // [g_rslots][4] rhythm back-end workspace (group scratch)
   int max_fr;         // largest rhythm frame capacity of any file in the batch
   int pitch_generic;  // AFX_PITCH_GENERIC=1: the general 2048-point pitch kernel also at hop 1024 (else the block-sharing form)
+  int rhythm_pipe;    // k_rhythm_pipe for this launch group: -1 = by group size, 0 = no, 1 = yes
   int rhythm_fused;   // this launch group's rhythm front end runs as ONE kernel with a CTA per file (k_rhythm_front); else the split kernels over rpolar
 };
 

@@ -88,6 +88,9 @@ struct afx_ctx {
   // (AFX_RHYTHM_FUSED=0 / 1 forces never / always: the parity test compares the two schedules)
   int rhythm_fused_min = 0x7fffffff;
   bool pitch_generic = false;
+  // whitening + onset functions as one producer / consumer pipeline per file (k_rhythm_pipe): -1 = for launch groups with at
+  // least two files per SM, 0 / 1 = never / always (AFX_RHYTHM_PIPE; the parity test compares the schedules)
+  int rhythm_pipe = -1;
   bool rhythm_fused(int g_files) const { return g_files >= rhythm_fused_min; }
   struct afx_batch* live = nullptr;   // the one batch whose data occupies the device buffers (afx_batch_upload .. afx_batch_free)
 };

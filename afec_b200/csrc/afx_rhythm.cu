@@ -368,14 +368,14 @@ __global__ void __launch_bounds__(RP_THREADS, 3) k_rhythm_pipe(AfxBatchDev B, Af
     float* __restrict__ odf_c = B.rodf + f.rframe_off;
     for (int b = 0; b < nb; ++b) {
       const int h = b & 1, t = b * RP_H + cw;
-      float ph[8], ph1[8];                                     // the phases of frame t - 2 are fetched per rising bin (L1: a neighbour's t - 1)
-      const float* __restrict__ p2 = rows + (size_t)(t >= 2 ? t - 2 : 0) * AFX_RROW + 256 + lane;
+      float ph[8], ph1[8], ph2[8];
       if (t < Fr) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const int i = 256 + lane + 32 * c;
           ph[c] = __ldg(rows + (size_t)t * AFX_RROW + i);
           ph1[c] = (t >= 1) ? __ldg(rows + (size_t)(t - 1) * AFX_RROW + i) : 0.0f;
+          ph2[c] = (t >= 2) ? __ldg(rows + (size_t)(t - 2) * AFX_RROW + i) : 0.0f;
         }
       }
       rp_full_sync(h);
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(RP_THREADS, 3) k_rhythm_pipe(AfxBatchDev B, Af
           const float cur = fabsf(r0[i]);
           const float pmv = (t >= 1) ? fabsf(r1[i]) : 0.0f;
           if (i < AFX_RBINS && cur > 0.01f && !(cur < pmv))
-            total += (double)odf_complex_bin(cur, pmv, ph[c], ph1[c], (t >= 2) ? __ldg(p2 + 32 * c) : 0.0f, t >= 1);
+            total += (double)odf_complex_bin(cur, pmv, ph[c], ph1[c], ph2[c], t >= 1);
         }
         total = warp_sum(total);
         if (lane == 0) odf_c[t] = __fmul_rn((float)total, P.r_norm_complex);
@@ -902,8 +902,8 @@ void afx_launch_rhythm(const AfxParams& P, const AfxBatchDev& B, cudaStream_t s,
     k_rhythm_front<<<B.g_files, RF_THREADS, RF_SMEM, s>>>(B, P); ++*launches;
   } else {
     const int fb = (B.g_rslots + OW * OB - 1) / (OW * OB);
-    // the pipeline needs a CTA (a file) per resident slot to be worth it; AFX_RHYTHM_PIPE=0 / 1 forces the choice
-    static const int pipe = [] { const char* e = getenv("AFX_RHYTHM_PIPE"); return e ? atoi(e) : -1; }();
+    // the pipeline needs a CTA (a file) per resident slot to be worth it; AFX_RHYTHM_PIPE=0 / 1 forces the choice (afx_create)
+    const int pipe = B.rhythm_pipe;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -334,6 +334,30 @@ def test_rhythm_front_end_fused_equals_split(feats, monkeypatch, oracle_lib):
             check(g, oracle_lib.analyze(p, file_size=44 + p.size * p.itemsize), feats, mdata=oracle_lib.condition(p)[0])
 
 
+def test_rhythm_pipeline_equals_split(feats, monkeypatch, oracle_lib):
+    """Whitening + the two onset functions run either as three kernels over the polar rows or as one producer / consumer
+    pipeline per file (k_rhythm_pipe, large launch groups; forced here with AFX_RHYTHM_PIPE=1).  Same bits, both meet the
+    oracle.  File lengths cover 0, 1 .. 3 rhythm frames, one ring half exactly, and many hand-overs."""
+    pcms = [synth.one_shot(1820 + i, 0.2 + 0.41 * i) for i in range(7)]
+    pcms += [synth.one_shot(1830, 17.5), synth.one_shot(1831, 0.02), np.zeros(30000, dtype=np.int16), synth.one_shot(1834, 0.012),
+             synth.one_shot(1832, 0.9, channels=2), np.zeros((0,), dtype=np.int16), synth.one_shot(1833, 0.1), synth.one_shot(1835, 0.031)]
+    rates = [44100] * len(pcms)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("AFX_RHYTHM_PIPE", mode)
+        an = api.SampleAnalyser(44100, 2048, 1024, features=feats)
+        out[mode] = an.analyze_pcm(pcms, rates)
+        an.close()
+    for g, w, p in zip(out["1"], out["0"], pcms):
+        assert g.status == w.status and (g.F, g.Fr) == (w.F, w.Fr)
+        assert np.array_equal(g.header, w.header)
+        for a, b in zip(g.fs + g.fv, w.fs + w.fv):
+            assert np.array_equal(a, b)
+        assert np.array_equal(g.stats, w.stats)
+        if g.status == 0:
+            check(g, oracle_lib.analyze(p, file_size=44 + p.size * p.itemsize), feats, mdata=oracle_lib.condition(p)[0])
+
+
 def test_pitch_block_sharing_form_vs_general(feats, monkeypatch, oracle_lib):
     """At hop 1024 the pitch kernel shares one block transform between consecutive frames (k_pitch_hop, afx_pitch.cu); the
     general 2048-point kernel (AFX_PITCH_GENERIC=1, every other hop) computes the same correlation another way.  Both
