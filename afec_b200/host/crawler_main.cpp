@@ -60,13 +60,15 @@ int main(int argc, char** argv)
     else if (a == "--merge") merge = true;
     else if (a == "--decode-threads") decode_threads = std::max(1, atoi(next().c_str()));
     else if (a == "--host-pack") host_pack = true;
+    else if (a == "--page-size") setenv("AFX_SINK_PAGE_SIZE", next().c_str(), 1);
     else if (a == "-q") quiet = true;
     else if (a == "-h" || a == "--help") {
       printf("usage: %s [-l low] [-o afec-ll.db] [-j slots-per-gpu] [--hop 1024] [--devices 0,1,..] [--decode-threads N]\n"
-             "          [--shards N [--merge]] [--host-pack] <file-or-dir>...\n"
+             "          [--shards N [--merge]] [--host-pack] [--page-size N] <file-or-dir>...\n"
              "  --shards N   N sqlite writers side by side: afec-ll.db, afec-ll.db.1 .. .N-1 (each a valid afec-ll.db holding a\n"
              "               disjoint part of the rows); --merge appends the shards to afec-ll.db afterwards and deletes them\n"
-             "  --host-pack  pack the msgpack BLOBs on the host instead of the GPU\n", argv[0]);
+             "  --host-pack  pack the msgpack BLOBs on the host instead of the GPU\n"
+             "  --page-size N  sqlite page size of a NEW database (power of two, 512 .. 65536; default: sqlite's 4096 as the reference)\n", argv[0]);
       return 0;
     } else if (!a.empty() && a[0] == '-') { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
     else paths.push_back(a);

@@ -391,7 +391,7 @@ def crawl_with_sink(pcms, wl, device, n_files=600):
             oracle.write_wav(os.path.join(d, "f%05d.wav" % i), pcms[i], wl.get("rate", 44100))
             audio_s += len(pcms[i]) / float(wl.get("rate", 44100))
         out = {}
-        for tag, extra in (("one_writer", []), ("four_shards", ["--shards", "4"])):
+        for tag, extra in (("one_writer", []), ("four_shards", ["--shards", "4"]), ("one_writer_32k_pages", ["--page-size", "32768"])):
             db = os.path.join(d, tag + ".db")
             t0 = time.perf_counter()
             r = subprocess.run([afx_build.CRAWLER, "-o", db, "--hop", str(wl["hop"]), "--devices", str(device), "-j", "3"] + extra + [d],

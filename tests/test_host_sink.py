@@ -172,3 +172,26 @@ def test_bulk_load_only_touches_an_empty_database(host, tmp_path):
     assert host.afxh_sink_bench2(db.encode(), 5, 10, 80, 2, 3, 1, None) > 0
     rows, pragmas = _dump_table(db)
     assert len(rows) == 5 and pragmas["journal_mode"] == "wal"
+
+
+def test_page_size_option_changes_the_file_not_the_rows(host, tmp_path, monkeypatch):
+    """AFX_SINK_PAGE_SIZE / `afec-b200-crawler --page-size` (a sink-throughput option, off by default: the reference writes
+    sqlite's 4096-byte pages): a new database takes the page size, every column of every row stays the same bytes, the file
+    passes sqlite's integrity check; a value that is not a power of two in 512 .. 65536 is ignored."""
+    import sqlite3
+    host.afxh_sink_bench2.restype = C.c_double
+    host.afxh_sink_bench2.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    n, F, Fr = 9, 40, 330
+    base = str(tmp_path / "plain.db")
+    assert host.afxh_sink_bench2(base.encode(), n, F, Fr, 4, 3, 1, None) > 0
+    want, pragmas = _dump_table(base)
+    for value, expect in (("32768", 32768), ("65536", 65536), ("5000", 4096), ("junk", 4096)):
+        monkeypatch.setenv("AFX_SINK_PAGE_SIZE", value)
+        db = str(tmp_path / ("p%s.db" % value))
+        assert host.afxh_sink_bench2(db.encode(), n, F, Fr, 4, 3, 1, None) > 0
+        got, pr = _dump_table(db)
+        assert got == want and pr == pragmas, value
+        con = sqlite3.connect(db)
+        assert con.execute("PRAGMA page_size").fetchone()[0] == expect, value
+        assert con.execute("PRAGMA integrity_check").fetchone()[0] == "ok"
+        con.close()
