@@ -42,12 +42,14 @@ __device__ __forceinline__ float phase_rewrap(float p)
 
 // atan2 for the float32 phase column.  The reference computes atan2 in double and rounds to float
 // (OnsetDetector.cpp:136-155); the result only has to be right to well below a float ulp (2.4e-7 at pi), so an
-// octant reduction to |w| <= tan(pi/8), one reciprocal-seeded division (MUFU.RCP64H + two Newton steps on the
-// quotient, ~1e-15) and the Taylor series through w^21 (error < 7e-11) replace libdevice's fully rounded double
-// atan2 -- a quarter of its FP64 work.  The FP64 constants sit in constant memory: as literals every use costs
+// octant reduction to |w| <= tan(pi/8), one reciprocal-seeded division (MUFU.RCP64H + one Newton step: ~1e-13 of the
+// quotient) and atan(w) = w - w^3 Q(w^2) with Q the degree-6 interpolant of (w - atan w) / w^3 at the Chebyshev nodes of
+// [0, tan^2(pi/8)] (error of atan < 1.2e-12; the Taylor series needs w^21 for 6e-11) replace libdevice's fully rounded
+// double atan2 -- a fifth of its FP64 work.  The FP64 constants sit in constant memory: as literals every use costs
 // two UMOVs, and this kernel is issue bound.
-__constant__ double c_at[16] = { -1.0 / 21.0, 1.0 / 19.0, -1.0 / 17.0, 1.0 / 15.0, -1.0 / 13.0, 1.0 / 11.0, -1.0 / 9.0, 1.0 / 7.0,
-                                 -1.0 / 5.0, 1.0 / 3.0, 0.41421356237309503, 0.78539816339744830962, 1.57079632679489661923,
+__constant__ double c_at[16] = { 0.04043224825887161, -0.07135325122330678, 0.09028983500350463, -0.11107495135714474,
+                                 0.14285612511387016, -0.1999999891728858, 0.3333333333144073, 0.0, 0.0, 0.0,
+                                 0.41421356237309503, 0.78539816339744830962, 1.57079632679489661923,
                                  3.14159265358979323846, 1.0, 0.5 };
 __device__ __forceinline__ double atan2_phase(double y, double x)
 {
@@ -61,13 +63,12 @@ __device__ __forceinline__ double atan2_phase(double y, double x)
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));   // den is 0 or far above the subnormals (float32 samples)
   r = fma(fma(-den, r, c_at[14]), r, r);
-  const double q = num * r;
-  const double w = fma(fma(-den, q, num), r, q);
+  const double w = num * r;
   const double w2 = w * w;
   double p = c_at[0];
 #pragma unroll
-  for (int i = 1; i < 10; ++i) p = fma(p, w2, c_at[i]);
-  r = fma(-(p * w2), w, w);                                 // w - w^3 / 3 + ...
+  for (int i = 1; i < 7; ++i) p = fma(p, w2, c_at[i]);
+  r = fma(-(p * w2), w, w);                                 // w - w^3 Q(w^2)
   if (hi) r += c_at[11];
   if (sw) r = c_at[12] - r;
   if (x < 0.0) r = c_at[13] - r;
