@@ -167,10 +167,11 @@ def cpu_reference_run(files_pcm, hop, threads, reps=1, rate=44100):
 
 
 def reference_sample_files(wl, cores):
-    """Bounded sample for the CPU legs: about 10 s of wall time per step on `cores` threads
-    (the reference runs ~25 x real time per core)."""
+    """Bounded sample for the CPU legs: about 10 s of wall time per step on `cores` threads (the reference runs ~100 x real
+    time per core on the GPU boxes' hosts at hop 1024: 4476 s of audio in 2.67 s on 16 threads, profiles/r02f_bench_full_n1.json;
+    BASELINE.md section 2 quotes ~25 x on older hardware)."""
     avg_s = wl["seconds"] if wl["min_seconds"] is None else 0.5 * (wl["seconds"] + wl["min_seconds"])
-    target_audio_s = 10.0 * 25.0 * cores
+    target_audio_s = 10.0 * 100.0 * cores
     return int(max(2 * cores, min(2048, target_audio_s / avg_s)))
 
 

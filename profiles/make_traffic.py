@@ -8,7 +8,7 @@ import csv, json, os, sys
 
 GROUPS = {
     "spectrum": ["k_spectrum", "k_flux"],
-    "rhythm": ["k_rhythm_front", "k_rhythm_polar", "k_rhythm_whiten", "k_rhythm_odf", "k_rhythm_power", "k_rhythm_median", "k_rhythm_back"],
+    "rhythm": ["k_rhythm_front", "k_rhythm_polar", "k_rhythm_pipe", "k_rhythm_whiten", "k_rhythm_odf", "k_rhythm_power", "k_rhythm_median", "k_rhythm_back"],
     "pitch": ["k_pitch", "k_pitch_hop"],
     "bands": ["k_bands_a_big", "k_bands_a_small", "k_bands_b", "k_bands_select", "k_bands_lane"],
     "autocorr": ["k_autocorr"],
