@@ -629,7 +629,7 @@ __device__ __noinline__ void rb_acf_group(const double* __restrict__ x, int n, i
 
 __device__ __forceinline__ double rb_sum(double v, double* scr) { double a[1] = { v }; block_sum<1>(a, scr); return a[0]; }
 
-__global__ void __launch_bounds__(BT_THREADS, 4) k_rhythm_back(AfxBatchDev B, AfxParams P)
+__global__ void __launch_bounds__(BT_THREADS) k_rhythm_back(AfxBatchDev B, AfxParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double scr[64];
