@@ -67,6 +67,31 @@ def test_half_silent_frame_pitch_flips_with_the_fft():
     assert parity.compare(a, b, mdata=data) == []
 
 
+def test_single_tick_half_frame_pitch_flips_with_the_fft():
+    """The same with ONE least-significant-bit tick inside the silent half (the sweep's file of seed 15064, frame 230): r[tau]
+    is that tick times the signal tau samples on -- zero across the gap -- so the normalised function ties at exactly 1 over
+    the small lags and the arg-min fall-back picks among FFT rounding noise."""
+    pcm = synth.one_shot(77, 1.2).copy()
+    g0 = 20000
+    pcm[g0:g0 + 6000] = 0
+    pcm[g0 + 4976] = 1                                         # one LSB tick, 1024 samples before the gap ends: whatever the frame
+                                                               # grid's offset, one frame has it alone in its first half and signal in its second
+    data = oracle.condition(pcm)[0]
+    a, b = both_ffts(pcm)
+    ill = parity.ill_conditioned_pitch_frames(data, 1024, a.F)
+    only_zero_half = np.zeros(a.F, dtype=bool)
+    x = np.asarray(data)
+    for t in range(a.F):
+        only_zero_half[t] = not x[t * 1024:t * 1024 + 1024].any()
+    assert (ill & ~only_zero_half).any(), "expected a frame whose first half holds exactly one tick"
+    d = np.zeros(a.F, dtype=bool)
+    for n in parity.PITCH_SERIES:
+        d |= ~parity.close(a.series(n), b.series(n))
+    assert (d & ill & ~only_zero_half).any(), "expected the two FFTs to disagree on a single-tick frame"
+    assert not (d & ~ill).any()                               # outside the rule's frames the two FFTs agree
+    assert parity.compare(a, b, mdata=data) == []
+
+
 @pytest.mark.parametrize("seed", [11, 12, 13, 14])
 def test_ordinary_files_do_not_depend_on_the_fft(seed):
     """On ordinary material every output agrees between the two FFTs under the rules: the exclusions are not a blanket."""
