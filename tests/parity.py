@@ -11,16 +11,17 @@ instead of Ooura would disagree with itself):
     of a series whose sum cancels (sum|x| / |sum x| > 1e6): Statistics.cpp:459-574 divide by
     that sum;
   * skewness/kurtosis whose spread is within 1e-6 of the 1e-12 cut-off;
-  * the pitch triple (f0, f0_confidence, failsafe_f0) of a frame whose first 1024 samples are digital silence
-    while the rest is not: aubio's yinfast forms yin[tau] = sq[tau] - r[tau] with r from FFTs
-    (pitchyinfast.c:110-137); there sq[tau] is exactly 0 for small tau and r[tau] is FFT rounding noise, so the
-    cumulative-mean normalised function, the first-dip search and the confidence are functions of that noise
-    (callers pass the conditioned signal so those frames can be found).  The same holds when the first half holds ONE
-    non-zero sample x[j] (the last LSB tick of a decayed tail): r[tau] = x[j] x[j + tau] vanishes wherever the signal
-    does, sq[tau] is the same 2 x[j]^2 for every small tau, the normalised function is exactly 1 there and the arg-min
-    fall-back (mathutils.c:250-258) picks among ties that only the FFT's rounding breaks.  Found by
-    profiles/parity_sweep.py (round 2, seed 15064, frame 230: the oracle with its two FFT variants returns 3163.9 and
-    4026.0 Hz, the CUDA path 2845.2); tests/test_fft_rounding_rules.py demonstrates it.
+  * the pitch triple (f0, f0_confidence, failsafe_f0) of a frame whose first 1024 samples are silent next to the rest
+    (digital silence, or the last LSB ticks of a decayed tail: less than 1e-6 of the frame's energy): aubio's yinfast
+    forms yin[tau] = sq[tau] - r[tau] with r from FFTs (pitchyinfast.c:110-137).  With a silent first half sq[tau] is
+    exactly 0 for small tau and r[tau] is FFT rounding noise; with a few ticks x[j] in it r[tau] = sum x[j] x[j + tau]
+    vanishes wherever the signal does, sq[tau] is the same 2 sum x[j]^2 for every small tau, the normalised function is
+    exactly 1 there and the arg-min fall-back (mathutils.c:250-258) picks among ties.  Either way the FFT's rounding
+    (1e-16 of the FRAME's energy, i.e. >= 1e-10 of these values) decides the cumulative-mean normalised function, the
+    first-dip search and the confidence (callers pass the conditioned signal so those frames can be found).  Found by
+    profiles/parity_sweep.py (silent half: round 1; one tick: seed 15064, frame 230 -- the oracle with its two FFT
+    variants returns 3163.9 and 4026.0 Hz, the CUDA path 2845.2; two ticks: seed 16138, frame 350);
+    tests/test_fft_rounding_rules.py demonstrates both.
   * peak counts of a frame whose windowed signal holds exactly ONE non-zero sample (the last LSB tick of a decayed tail;
     the window's end points are zero): its magnitude
     spectrum is |x w[n]| / N in every bin, so which bins are "strict local maxima above 0.25 max" (spectral_complexity,
@@ -62,16 +63,19 @@ def close(a, b):
 PITCH_SERIES = ("f0", "f0_confidence", "failsafe_f0")
 
 
+PITCH_SILENT_HALF = 1e-6      # first-half energy below this fraction of the frame's: -60 dB
+
+
 def ill_conditioned_pitch_frames(mdata, hop, F, N=2048):
-    """Frames whose first N/2 samples hold at most ONE non-zero sample while the second half is not silent (see the module
-    docstring)."""
+    """Frames whose first N/2 samples are silent next to the second half: exactly zero, or a few LSB ticks of a decayed
+    tail -- less than PITCH_SILENT_HALF of the frame's energy (see the module docstring)."""
     x = np.asarray(mdata, dtype=np.float64)
     out = np.zeros(F, dtype=bool)
-    nz = np.concatenate([[0], np.cumsum(x != 0.0)])
     for t in range(F):
         a, m, e = t * hop, t * hop + N // 2, min(t * hop + N, len(x))
         if m <= len(x):
-            out[t] = (nz[m] - nz[a] <= 1) and (nz[e] - nz[m] > 0)
+            s0 = float(np.dot(x[a:m], x[a:m])); s1 = float(np.dot(x[m:e], x[m:e]))
+            out[t] = s1 > 0.0 and s0 <= PITCH_SILENT_HALF * (s0 + s1)
     return out
 
 
