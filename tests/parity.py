@@ -21,7 +21,12 @@ instead of Ooura would disagree with itself):
     first-dip search and the confidence (callers pass the conditioned signal so those frames can be found).  Found by
     profiles/parity_sweep.py (silent half: round 1; one tick: seed 15064, frame 230 -- the oracle with its two FFT
     variants returns 3163.9 and 4026.0 Hz, the CUDA path 2845.2; two ticks: seed 16138, frame 350);
-    tests/test_fft_rounding_rules.py demonstrates both.
+    tests/test_fft_rounding_rules.py demonstrates both.  The same ties arise from one impulse alone in a frame (yin[tau] =
+    x0^2 for every tau) and from a constant frame (yin[tau] = W c^2); instead of one structural rule per shape, a pitch frame
+    that differs is put to the general test pitch_noise_sensitive(): the reference's own decision procedure, restated here,
+    is run on the exact difference function with r[tau] perturbed at the level of an FFT's rounding (1e-15 of the frame's
+    energy); if its f0 or confidence moves beyond the tolerance, the frame has no reference value.  Ordinary frames do not
+    react to it (tests/test_parity_rules.py); profiles/stress_corpus.py holds the material that does.
   * peak counts of a frame whose windowed signal holds exactly ONE non-zero sample (the last LSB tick of a decayed tail;
     the window's end points are zero): its magnitude
     spectrum is |x w[n]| / N in every bin, so which bins are "strict local maxima above 0.25 max" (spectral_complexity,
@@ -79,6 +84,76 @@ def ill_conditioned_pitch_frames(mdata, hop, F, N=2048):
     return out
 
 
+PITCH_FFT_NOISE = 1e-15       # rounding of an FFT-made correlation, as a fraction of the frame's energy (eps x log2 N x a few)
+
+
+def _yin_decision(yin, sr):
+    """aubio's yinfast decision on a difference function (pitchyinfast.c:150-176, mathutils.c:250-258, 494-506;
+    SampleAnalyser.cpp:887-889): cumulative-mean normalisation, first dip below 0.75, arg-min fall-back (the last minimum
+    wins ties), parabolic refinement -> (f0 before the silence gate, confidence)."""
+    W = len(yin)
+    y = np.array(yin, dtype=np.float64)
+    y[0] = 1.0
+    c = np.cumsum(y[1:])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        y[1:] = np.where(c != 0, y[1:] * np.arange(1, W) / c, 1.0)
+    pos = -1
+    # first p >= 2 with y[p] < 0.75 and y[p] < y[p + 1], seen at t = p + 3 <= W - 1
+    cand = np.nonzero((y[2:W - 3] < 0.75) & (y[2:W - 3] < y[3:W - 2]))[0]
+    if cand.size:
+        pos = int(cand[0]) + 2
+    else:
+        m = y.min()
+        pos = int(np.nonzero(y == m)[0][-1])
+    if pos == 0 or pos == W - 1:
+        period = float(pos)
+    else:
+        s0, s1, s2 = y[pos - 1], y[pos], y[pos + 1]
+        den = s0 - 2.0 * s1 + s2
+        period = pos + 0.5 * (s0 - s2) / den if den != 0 else float("nan")
+    peak = int(period) if (period == period and period >= 0) else 0
+    f0 = sr / period if period > 0 else 0.0
+    conf = min(1.0, max(0.0, (1.0 - y[min(peak, W - 1)]) / 0.25))
+    return f0, conf
+
+
+def _yin_exact(frame):
+    """The difference function of one frame in extended precision with the correlation as a direct sum; returns (yin, energy)."""
+    N = 2048
+    x = np.zeros(N, dtype=np.longdouble)
+    f = np.asarray(frame, dtype=np.float64)[:N]
+    x[:len(f)] = f
+    W = N // 2
+    E = float(np.dot(x, x))
+    sq = np.empty(W, dtype=np.longdouble)
+    s0 = np.dot(x[:W], x[:W])
+    x2 = x * x
+    sq[0] = s0
+    sq[1:] = s0 - np.cumsum(x2[:W - 1]) + np.cumsum(x2[W:2 * W - 1])
+    sq += s0
+    r = np.correlate(x[:2 * W - 1], x[:W], mode="valid")           # r[tau] = sum_{m < W} x[m] x[m + tau]
+    return (sq - r).astype(np.float64), E                          # aubio's halved correlation: sq - 2 (r / 2)
+
+
+def pitch_noise_sensitive(frame, sr=44100.0, draws=6, seed=1) -> bool:
+    """The general form of the pitch rule: True when the reference's OWN pitch decision for this frame (see _yin_decision)
+    changes beyond the tolerance once its correlation r[tau] -- which the reference computes with FFTs -- is perturbed at the
+    level of an FFT's rounding, PITCH_FFT_NOISE x the frame's energy.  Such a frame has no reference value to compare with:
+    exact ties of the normalised difference function (a silent or tick-only first half, one impulse, a constant frame) or
+    near-ties far below what double precision resolves."""
+    yin, E = _yin_exact(frame)
+    if E == 0.0:
+        return False
+    W = len(yin)
+    base = _yin_decision(yin, sr)
+    rng = np.random.default_rng(seed)
+    for _ in range(draws):
+        got = _yin_decision(yin + PITCH_FFT_NOISE * E * rng.uniform(-1.0, 1.0, W), sr)
+        if not (close(got[0], base[0]) and close(got[1], base[1])):
+            return True
+    return False
+
+
 FLAT_COUNT_SERIES = ("spectral_complexity", "spectral_complexity_bands")
 FLAT_GMEAN_SERIES = ("spectral_flatness", "spectral_flatness_bands")
 
@@ -120,6 +195,16 @@ def compare(got: layout.FileResult, want: layout.FileResult, skip_series=(), onl
     names = list(layout.FRAMED_SCALARS) + [n for n, _ in layout.FRAMED_VECTORS]
     ill_pitch = ill_conditioned_pitch_frames(mdata, hop, want.F) if mdata is not None else np.zeros(want.F, dtype=bool)
     ill_flat = impulse_frames(mdata, hop, want.F) if mdata is not None else np.zeros(want.F, dtype=bool)
+    if mdata is not None:
+        # pitch frames that differ and that no structural rule names: is the reference's own decision determined there?
+        cand = np.zeros(want.F, dtype=bool)
+        for n in PITCH_SERIES:
+            if not (n in skip_series or (only_series is not None and n not in only_series)):
+                cand |= ~close(got.series(n), want.series(n))
+        x = np.asarray(mdata, dtype=np.float64)
+        for t in np.nonzero(cand & ~ill_pitch)[0]:
+            if pitch_noise_sensitive(x[t * hop:t * hop + 2048]):
+                ill_pitch[t] = True
     for n in names:
         if n in skip_series or (only_series is not None and n not in only_series):
             continue

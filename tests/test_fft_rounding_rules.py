@@ -93,6 +93,29 @@ def test_ticks_in_a_silent_half_pitch_flips_with_the_fft(ticks):
     assert parity.compare(a, b, mdata=data) == []
 
 
+@pytest.mark.parametrize("kind", ["one_impulse", "dc"])
+def test_tie_frames_of_other_shapes_pitch_flips_with_the_fft(kind):
+    """One impulse alone in a frame (yin[tau] = x0^2 for every tau) and a constant signal (yin[tau] = W c^2) tie the
+    normalised difference function exactly as well; no structural rule names them -- the general test of
+    parity.pitch_noise_sensitive() does (profiles/stress_corpus.py found both)."""
+    n = 66150
+    if kind == "one_impulse":
+        pcm = np.zeros(n, dtype=np.int16); pcm[n // 2] = 30000
+    else:
+        pcm = np.full(n, 1000, dtype=np.int16)
+    data = oracle.condition(pcm)[0]
+    a, b = both_ffts(pcm)
+    d = np.zeros(a.F, dtype=bool)
+    for name in parity.PITCH_SERIES:
+        d |= ~parity.close(a.series(name), b.series(name))
+    assert d.any(), "expected the two FFTs to disagree on the pitch of a tie frame"
+    assert not parity.ill_conditioned_pitch_frames(data, 1024, a.F)[d].all()      # not (all) covered by the structural rule
+    x = np.asarray(data, dtype=np.float64)
+    assert all(parity.pitch_noise_sensitive(x[t * 1024:t * 1024 + 2048]) for t in np.nonzero(d)[0])
+    assert parity.compare(a, b), "the plain tolerance must flag the disagreement"
+    assert parity.compare(a, b, mdata=data) == []
+
+
 @pytest.mark.parametrize("seed", [11, 12, 13, 14])
 def test_ordinary_files_do_not_depend_on_the_fft(seed):
     """On ordinary material every output agrees between the two FFTs under the rules: the exclusions are not a blanket."""

@@ -50,3 +50,52 @@ def test_log_domain_noise_rule_only_fires_on_sub_tolerance_differences():
     x = np.full(200, 0.5); y = x.copy(); x[7] = 0.0; y[7] = 1e-17
     gx, gy = oracle.stats13(x)[4], oracle.stats13(y)[4]
     assert abs(gx - gy) > 1e-2 * gx and parity.close(x, y).all()
+
+
+def test_yin_decision_restates_the_oracle():
+    """The decision procedure behind pitch_noise_sensitive() is a restatement of the oracle's (and so of aubio's): on
+    ordinary material, fed the exact difference function, it returns the oracle's f0 and confidence frame for frame."""
+    from afec_b200 import synth
+    from oracle import oracle
+    n_checked = 0
+    for seed in (21, 22, 23):
+        pcm = synth.one_shot(seed, 1.5)
+        want = oracle.analyze(pcm, file_size=44 + pcm.size * 2)
+        data = np.asarray(oracle.condition(pcm)[0], dtype=np.float64)
+        ill = parity.ill_conditioned_pitch_frames(data, 1024, want.F)
+        f0, conf = want.series("f0"), want.series("f0_confidence")
+        for t in range(want.F):
+            if ill[t]:
+                continue
+            yin, E = parity._yin_exact(data[t * 1024:t * 1024 + 2048])
+            g0, gc = parity._yin_decision(yin, 44100.0)
+            assert parity.close(gc, conf[t]), (seed, t, gc, conf[t])
+            if f0[t] != 0.0:                                  # the silence gate (-48 dB) sits outside the decision
+                assert parity.close(g0, f0[t]), (seed, t, g0, f0[t])
+            n_checked += 1
+    assert n_checked > 100
+
+
+def test_pitch_noise_sensitivity_names_the_tie_frames_only():
+    from afec_b200 import synth
+    from oracle import oracle
+    N = 2048
+    impulse = np.zeros(N); impulse[0] = 1.0                   # yin[tau] = x0^2 for every tau
+    assert parity.pitch_noise_sensitive(impulse)
+    assert parity.pitch_noise_sensitive(np.full(N, 0.03))     # constant: yin[tau] = W c^2
+    ticks = np.zeros(N); ticks[370] = ticks[961] = 3.8e-5     # the sweep's seed 16138, frame 350
+    ticks[1256:1286] = 0.4 * np.hanning(30)
+    assert parity.pitch_noise_sensitive(ticks)
+    assert not parity.pitch_noise_sensitive(np.zeros(N))      # silence: nothing to decide
+    # ordinary material does not react to rounding-level noise: the test is not a blanket
+    flagged = total = 0
+    for seed in (31, 32, 33, 34):
+        pcm = synth.one_shot(seed, 1.2)
+        data = np.asarray(oracle.condition(pcm)[0], dtype=np.float64)
+        F = (len(data) - N) // 1024 + 1
+        ill = parity.ill_conditioned_pitch_frames(data, 1024, F)
+        for t in range(F):
+            if not ill[t]:
+                total += 1
+                flagged += bool(parity.pitch_noise_sensitive(data[t * 1024:t * 1024 + N]))
+    assert total > 100 and flagged == 0
