@@ -99,3 +99,19 @@ def test_pitch_noise_sensitivity_names_the_tie_frames_only():
                 total += 1
                 flagged += bool(parity.pitch_noise_sensitive(data[t * 1024:t * 1024 + N]))
     assert total > 100 and flagged == 0
+
+
+def test_sub_tolerance_series_rule():
+    """A series of rounding-level values (one ulp here, zero there) equals its counterpart under the tolerance element by
+    element, but its index-weighted statistics are a function of WHERE the ulps sit (profiles/stress_corpus.py, sine_21000)."""
+    from oracle import oracle
+    a = np.zeros(64); b = np.zeros(64)
+    a[[5, 7, 15, 40]] = 4.44e-16
+    b[[6, 30, 50]] = 4.44e-16
+    assert parity.close(a, b).all()
+    sa, sb = oracle.stats13(a), oracle.stats13(b)
+    assert not parity.close(sa[6], sb[6])                    # the temporal centroids differ by far more than the tolerance
+    assert parity.sub_tolerance_series(a, b)
+    assert not parity.sub_tolerance_series(a, a)             # identical series: nothing to release
+    c = b.copy(); c[3] = 1e-3
+    assert not parity.sub_tolerance_series(a, c)             # one element above the tolerance: the plain rules apply
