@@ -242,6 +242,26 @@ def test_ticks_in_a_silent_half_frame(analysers, feats, oracle_lib, ticks):
     check(got, want, feats, mdata=data)
 
 
+def test_edge_material_corpus(analysers, feats, oracle_lib):
+    """Steady tones on and off bin centres, square / saw / impulse trains, DC, clipped noise, a Nyquist tone, one impulse in
+    silence, phase-inverted stereo, few-LSB material ... (tests/edge_corpus.py) in ONE batch against the oracle, under the
+    rules of tests/parity.py -- the frames of this material whose pitch the reference's own arithmetic does not determine
+    (exact ties: impulse, constant) are the ones tests/test_fft_rounding_rules.py demonstrates."""
+    import edge_corpus
+    files = edge_corpus.build()
+    got = analysers(1024).analyze_pcm([p for _, p, _ in files], [r for _, _, r in files])
+    bad = []
+    for g, (name, p, r) in zip(got, files):
+        want = oracle_lib.analyze(p, src_rate=r, file_size=44 + p.size * 2)
+        data = oracle_lib.condition(p, src_rate=r)[0] if want.status == 0 else None
+        full = (feats & api.FEAT_ALL) == api.FEAT_ALL
+        errs = parity.compare(g, want, only_series=None if full else series_for(feats), check_stats=bool(feats & api.FEAT_STATS),
+                              check_header=full, mdata=data)
+        if errs:
+            bad.append("%s: %s" % (name, errs[:3]))
+    assert not bad, "\n".join(bad)
+
+
 def test_trim_releases_and_regrows(feats):
     """afx_trim gives the device buffers back; the next batch grows them again and computes the same bits."""
     import torch
