@@ -40,7 +40,11 @@ instead of Ooura would disagree with itself):
     of a two-bin band whose bins are equal -- moves the log sum by 7 / n.  When the two series differ at an element below
     1e-9, these two statistics of the CUDA path are checked against the oracle's TStatistics restatement applied to the
     series the CUDA path itself produced (as for the noise-determined frames above), not against the reference's.
-    Found by profiles/parity_sweep.py (round 2, seeds 7114 and 8030).
+    Found by profiles/parity_sweep.py (round 2, seeds 7114 and 8030).  The same FP-noise-level element can carry the
+    index-weighted statistics: an f0_confidence series with ONE frame of 1.4e-5 and, in one of the two results, one ulp
+    (4.4e-16) in two other frames has spread 0 against 2.6e-9 -- on either side of the reference's 1e-12 cut-off -- and so
+    skewness 0 against -1.1e32 (profiles/edge_self_sweep.py, seed 91764: the oracle's two FFT variants).  So every
+    statistic that disagrees under this condition is checked on the produced series.
   * every statistic of a series that lies below the absolute tolerance as a whole in both results (f0_confidence of a tone
     next to Nyquist: one ulp in some frames, 0 in the others -- which frames is rounding): the temporal centroid, spread, ...
     divide by the sum of the values.  The CUDA statistics are checked against the oracle's TStatistics restatement applied to
@@ -289,11 +293,11 @@ def compare_stats(got, want, skip_series=(), only_series=None, ill_pitch=None, i
         ok = close(a, b)
         ok = flatness_tol(a, b, ok)
         ok = stat_rules(ok, x, b)
-        if not noise and not (ok[4] and ok[10]) and log_domain_noise(gs[n], x):
+        if not noise and not ok.all() and log_domain_noise(gs[n], x):
             from oracle import oracle
-            own = oracle.stats13(np.ascontiguousarray(gs[n], dtype=np.float64))
-            ok2 = flatness_tol(a, own, close(a, own))
-            ok[4], ok[10] = ok2[4], ok2[10]
+            mine = np.ascontiguousarray(gs[n], dtype=np.float64)
+            own = oracle.stats13(mine)
+            ok |= stat_rules(flatness_tol(a, own, close(a, own)), mine, own)
         if not ok.all():
             k = int(np.argwhere(~ok)[0][0])
             errs.append("stat %s_%s%s: %r != %r" % (n, layout.STAT_NAMES[k], " (of the produced series)" if noise else "", a[k], b[k]))

@@ -115,3 +115,24 @@ def test_sub_tolerance_series_rule():
     assert not parity.sub_tolerance_series(a, a)             # identical series: nothing to release
     c = b.copy(); c[3] = 1e-3
     assert not parity.sub_tolerance_series(a, c)             # one element above the tolerance: the plain rules apply
+
+
+def test_noise_level_elements_can_carry_the_index_weighted_statistics():
+    """profiles/edge_self_sweep.py, seed 91764: one frame of 1.4e-5 and -- in one result only -- one ulp in two other frames put
+    the spread on either side of the reference's 1e-12 cut-off: skewness 0 against -1e32.  The series agree element by element;
+    the rule checks such statistics on the produced series and still catches a wrong statistic."""
+    from afec_b200 import layout
+    from oracle import oracle
+    a = np.zeros(160); b = np.zeros(160)
+    a[126] = b[126] = 1.377e-5
+    a[[40, 90]] = 4.44e-16
+    sa, sb = oracle.stats13(a), oracle.stats13(b)
+    k = layout.STAT_NAMES.index("skewness")
+    assert sb[k] == 0.0 and abs(sa[k]) > 1e20
+    assert parity.close(a, b).all() and parity.log_domain_noise(a, b)
+    ok = parity.close(sb, sa)
+    assert not ok[k]
+    own = oracle.stats13(b)                                   # what compare_stats does under the rule
+    assert parity.close(sb, own).all()
+    wrong = sb.copy(); wrong[k] = 3.0
+    assert not parity.close(wrong, own)[k]                    # a wrong statistic of the produced series is still caught
