@@ -389,7 +389,12 @@ int TGpuSampleAnalyser::ExtractBatchSharded(const std::vector<std::string>& File
           }
           frames += r.n_frames; rframes += r.n_rhythm_frames; ++files;
           chunk_audio += r.header[1];
-        } catch (const std::exception&) { ++failed; }
+        } catch (const std::exception& e) {
+          // SampleAnalyser.cpp:372-408: whatever goes wrong with a file ends as a failed row, never as a missing one
+          ++failed;
+          try { const std::lock_guard<std::mutex> lock(PoolLock); pPool->InsertFailedSample(name, std::string("Sample failed to analyse: ") + e.what()); }
+          catch (const std::exception&) {}
+        }
       }
       { const std::lock_guard<std::mutex> lock(PoolLock); pPool->EndBulk(); }
       if (W.batch) { afx_batch_free(W.batch); W.batch = nullptr; }
