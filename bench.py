@@ -413,7 +413,7 @@ def crawl_with_sink(pcms, wl, device, n_files=600):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=12)      # 12 x 0.49 s: a timed region above 5 s on the default workload
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="full", choices=sorted(WORKLOADS))
