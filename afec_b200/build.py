@@ -74,7 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 HOST = os.path.join(HERE, "host")
 HOST_LIB = os.path.join(HOST, "libafec_b200_host.so")
 CRAWLER = os.path.join(HOST, "afec-b200-crawler")
-HOST_SOURCES = ["descriptors.cpp", "sqlite_pool.cpp", "audio_reader.cpp", "gpu_analyser.cpp", "capi.cpp"]
+HOST_SOURCES = ["descriptors.cpp", "sqlite_pool.cpp", "direct_db_writer.cpp", "audio_reader.cpp", "gpu_analyser.cpp", "capi.cpp"]
 SQLITE = "/usr/lib/x86_64-linux-gnu/libsqlite3.so.0"
 
 

@@ -90,6 +90,8 @@ public:
   // the reference's WAL / NORMAL pragmas
   bool BeginBulkLoad();
   void EndBulkLoad();
+  // the same without sqlite in the data path (direct_db_writer.h): rows are written into the file in sqlite's format
+  bool BeginDirectLoad();
   // append the rows of other afec-ll.db files (shards written side by side); returns the number of rows taken
   int MergeFrom(const std::vector<std::string>& ShardFiles, bool DeleteShards);
   static std::vector<std::string> ColumnNamesAndTypes();   // "name TYPE" in table order (461 entries)

@@ -1,6 +1,7 @@
 // Small C entry points over the host classes, for language bindings and tests (ctypes).
 #include "afx_host.h"
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <algorithm>
@@ -143,8 +144,9 @@ double afxh_sink_bench(const char* db, int n_rows, int frames, int rframes, int 
 }
 
 // sink throughput with the round-2 paths: `mode` bit 0 = journal-less bulk load of the fresh database, bit 1 = rows arrive
-// packed (as afx_file_result.packed delivers them from the GPU; packed once here, outside the timed region), `shards` pools
-// written by as many threads.  Returns seconds (< 0 on error); *bytes = database bytes written.
+// packed (as afx_file_result.packed delivers them from the GPU; packed once here, outside the timed region), bit 2 = direct load
+// (TSqliteSampleDescriptorPool::BeginDirectLoad: the file is written in sqlite's format without sqlite), bit 3 = a failed row after
+// every third row, bit 4 = the first name once more at the end (-4 when a direct load accepts it); `shards` pools written by as many threads.  Returns seconds (< 0 on error); *bytes = database bytes written.
 double afxh_sink_bench2(const char* db, int n_rows, int frames, int rframes, int bulk, int mode, int shards, long long* bytes)
 {
   try {
@@ -177,9 +179,11 @@ double afxh_sink_bench2(const char* db, int n_rows, int frames, int rframes, int
       names.push_back(k == 0 ? std::string(db) : std::string(db) + "." + std::to_string(k));
       pools.emplace_back(new TSqliteSampleDescriptorPool());
       if (!pools.back()->Open(names.back())) return -1.0;
-      if (mode & 1) pools.back()->BeginBulkLoad();
+      if (mode & 4) { if (!pools.back()->BeginDirectLoad()) return -3.0; }
+      else if (mode & 1) pools.back()->BeginBulkLoad();
     }
     const auto t0 = std::chrono::steady_clock::now();
+    std::atomic<bool> dup_accepted(false);
     std::vector<std::thread> th;
     for (size_t k = 0; k < pools.size(); ++k) th.emplace_back([&, k]() {
       TSqliteSampleDescriptorPool& pool = *pools[k];
@@ -191,15 +195,21 @@ double afxh_sink_bench2(const char* db, int n_rows, int frames, int rframes, int
         snprintf(name, sizeof(name), "/nonexistent/f%07d.wav", i);
         if (mode & 2) pool.InsertPackedSample(name, "wav", r);
         else { mine.mFileName = name; pool.InsertSample(name, mine); }
+        if ((mode & 8) && i % 3 == 0) { snprintf(name, sizeof(name), "/nonexistent/bad%07d.wav", i); pool.InsertFailedSample(name, "Sample failed to load: test"); }
         if (bulk > 1 && ++in_txn == bulk) { pool.EndBulk(); in_txn = 0; }
       }
+      if ((mode & 16) && k == 0 && n_rows > 0) {           // the first row's name once more: a direct load must refuse it, sqlite replaces the row
+        snprintf(name, sizeof(name), "/nonexistent/f%07d.wav", 0);
+        try { pool.InsertFailedSample(name, "again"); dup_accepted = true; } catch (const std::exception&) {}
+      }
       if (in_txn) pool.EndBulk();
-      if (mode & 1) pool.EndBulkLoad();
+      if (mode & 5) pool.EndBulkLoad();
       pool.Close();
     });
     for (auto& t : th) t.join();
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (bytes) { *bytes = 0; for (const auto& n : names) { struct stat st; if (stat(n.c_str(), &st) == 0) *bytes += (long long)st.st_size; } }
+    if ((mode & 16) && (mode & 4) && dup_accepted) return -4.0;
     return secs;
   } catch (const std::exception&) { return -2.0; }
 }

@@ -47,7 +47,7 @@ int main(int argc, char** argv)
 {
   std::string out_db = "afec-ll.db", level = "low";
   int hop = 1024, slots = 3, shards = 1, decode_threads = 0; std::vector<int> devices(1, 0); std::vector<std::string> paths;
-  bool quiet = false, merge = false, host_pack = false;
+  bool quiet = false, merge = false, host_pack = false, direct_load = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto next = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(1); } return argv[++i]; };
@@ -61,13 +61,15 @@ int main(int argc, char** argv)
     else if (a == "--decode-threads") decode_threads = std::max(1, atoi(next().c_str()));
     else if (a == "--host-pack") host_pack = true;
     else if (a == "--page-size") setenv("AFX_SINK_PAGE_SIZE", next().c_str(), 1);
+    else if (a == "--direct-load") direct_load = true;
     else if (a == "-q") quiet = true;
     else if (a == "-h" || a == "--help") {
       printf("usage: %s [-l low] [-o afec-ll.db] [-j slots-per-gpu] [--hop 1024] [--devices 0,1,..] [--decode-threads N]\n"
-             "          [--shards N [--merge]] [--host-pack] [--page-size N] <file-or-dir>...\n"
+             "          [--shards N [--merge]] [--host-pack] [--page-size N] [--direct-load] <file-or-dir>...\n"
              "  --shards N   N sqlite writers side by side: afec-ll.db, afec-ll.db.1 .. .N-1 (each a valid afec-ll.db holding a\n"
              "               disjoint part of the rows); --merge appends the shards to afec-ll.db afterwards and deletes them\n"
              "  --host-pack  pack the msgpack BLOBs on the host instead of the GPU\n"
+             "  --direct-load  a NEW database is written in sqlite's file format directly (no sqlite in the data path of the load)\n"
              "  --page-size N  sqlite page size of a NEW database (power of two, 512 .. 65536; default: sqlite's 4096 as the reference)\n", argv[0]);
       return 0;
     } else if (!a.empty() && a[0] == '-') { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
@@ -114,7 +116,12 @@ int main(int argc, char** argv)
     TGpuSampleAnalyser analyser(44100, 2048, hop, devices, slots, !host_pack);
     if (decode_threads) analyser.SetDecodeThreads(decode_threads);
     // a fresh database is filled without a journal (TSqliteSampleDescriptorPool::BeginBulkLoad), shards always are fresh
-    const bool bulk_main = pool.BeginBulkLoad();
+    if (direct_load) {                                  // a direct load cannot replace a row: every file name once
+      std::set<std::string> seen; std::vector<std::string> uniq;
+      for (const auto& f : todo) if (seen.insert(f).second) uniq.push_back(f);
+      todo.swap(uniq);
+    }
+    const bool bulk_main = (direct_load && pool.BeginDirectLoad()) || pool.BeginBulkLoad();
     std::vector<std::unique_ptr<TSqliteSampleDescriptorPool>> shard_pools;
     std::vector<std::string> shard_files;
     std::vector<TSampleDescriptorPool*> pools(1, &pool);
@@ -125,7 +132,7 @@ int main(int argc, char** argv)
       std::unique_ptr<TSqliteSampleDescriptorPool> sp(new TSqliteSampleDescriptorPool());
       if (!sp->Open(name)) { fprintf(stderr, "failed to open shard %s\n", name.c_str()); return 1; }
       sp->SetBasePath(pool.BasePath());
-      sp->BeginBulkLoad();
+      if (!(direct_load && sp->BeginDirectLoad())) sp->BeginBulkLoad();
       pools.push_back(sp.get()); shard_files.push_back(name); shard_pools.push_back(std::move(sp));
     }
     for (size_t k = 0; k < pools.size(); ++k) { lock_store.emplace_back(new std::mutex()); locks.push_back(lock_store.back().get()); }

@@ -5,12 +5,14 @@
 // one transaction (the reference commits one per file); rows and bytes are identical.
 #include "afx_host.h"
 #include "sqlite3_min.h"
+#include "direct_db_writer.h"
 
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -24,6 +26,8 @@ struct TSqliteSampleDescriptorPool::Impl {
   int bulk = 0;
   bool bulk_load = false;
   std::vector<unsigned char> blob;    // one row's msgpack blobs, back to back (bound SQLITE_STATIC until the step)
+  std::unique_ptr<TDirectDbWriter> direct;   // BeginDirectLoad .. EndBulkLoad: rows go straight into the file (db is closed meanwhile)
+  std::vector<TDbValue> values;
 };
 
 static void check(sqlite3* db, int rc, const char* what)
@@ -76,6 +80,7 @@ TSqliteSampleDescriptorPool::~TSqliteSampleDescriptorPool() { Close(); }
 void TSqliteSampleDescriptorPool::Close()
 {
   Impl& I = *mImpl;
+  if (I.direct) { try { EndBulkLoad(); } catch (...) { I.direct.reset(); I.bulk_load = false; } }
   if (!I.db) return;
   if (I.bulk) { try { exec(I.db, "COMMIT"); } catch (...) {} I.bulk = 0; }
   if (I.bulk_load) { try { EndBulkLoad(); } catch (...) {} }
@@ -178,8 +183,8 @@ std::vector<std::pair<std::string, int>> TSqliteSampleDescriptorPool::SampleModi
   return ret;
 }
 
-void TSqliteSampleDescriptorPool::BeginBulk() { if (mImpl->bulk++ == 0) exec(mImpl->db, "BEGIN"); }
-void TSqliteSampleDescriptorPool::EndBulk() { if (mImpl->bulk > 0 && --mImpl->bulk == 0) exec(mImpl->db, "COMMIT"); }
+void TSqliteSampleDescriptorPool::BeginBulk() { if (mImpl->direct) return; if (mImpl->bulk++ == 0) exec(mImpl->db, "BEGIN"); }
+void TSqliteSampleDescriptorPool::EndBulk() { if (mImpl->direct) return; if (mImpl->bulk > 0 && --mImpl->bulk == 0) exec(mImpl->db, "COMMIT"); }
 
 // append helpers: msgpack straight into the row buffer (same bytes as PackVR / PackVVR)
 static inline void put_array_header(std::vector<unsigned char>& out, size_t n)
@@ -200,35 +205,52 @@ static inline void put_doubles(std::vector<unsigned char>& out, const double* v,
   }
 }
 
-// One row.  `blobs` (AFX_N_BLOBS pointers + sizes, column order) stay valid until the statement has been stepped: they are
-// bound SQLITE_STATIC, so a row packed on the GPU goes from the pinned download buffer into sqlite's pages with no copy
-// in between.
-static void insert_row(sqlite3* db, sqlite3_stmt* st, const std::string& rel, int modtime, const std::string& file_type,
+// One row as values in column order (ColumnNamesAndTypes).  Texts and BLOBs are referenced, not copied: they stay valid until
+// the row has been stepped / written -- a row packed on the GPU goes from the pinned download buffer into sqlite's pages (or,
+// in a direct load, into the file's) with no copy in between.
+static void row_values(std::vector<TDbValue>& v, const std::string& rel, int modtime, const std::string& file_type,
                        const double* header, const double (*stats)[AFX_N_STATS], const unsigned char* const* blob_ptr, const int* blob_len)
 {
-  int p = 1, blob = 0;
-  sqlite3_bind_text(st, p++, rel.c_str(), -1, SQLITE_TRANSIENT);
-  sqlite3_bind_int(st, p++, modtime);
-  sqlite3_bind_text(st, p++, "succeeded", -1, SQLITE_STATIC);
-  sqlite3_bind_text(st, p++, file_type.c_str(), -1, SQLITE_TRANSIENT);
-  sqlite3_bind_int(st, p++, (int)header[0]);        // file_size
-  sqlite3_bind_double(st, p++, header[1]);          // file_length
-  sqlite3_bind_int(st, p++, (int)header[2]);
-  sqlite3_bind_int(st, p++, (int)header[3]);
-  sqlite3_bind_int(st, p++, (int)header[4]);
-  for (int k = 5; k < 9; ++k) sqlite3_bind_double(st, p++, header[k]);
+  static const std::string kSucceeded = "succeeded";
+  v.clear();
+  int blob = 0;
+  v.push_back(TDbValue::Text(rel));
+  v.push_back(TDbValue::Int(modtime));
+  v.push_back(TDbValue::Text(kSucceeded));
+  v.push_back(TDbValue::Text(file_type));
+  v.push_back(TDbValue::Int((int)header[0]));        // file_size
+  v.push_back(TDbValue::Real(header[1]));            // file_length
+  v.push_back(TDbValue::Int((int)header[2]));
+  v.push_back(TDbValue::Int((int)header[3]));
+  v.push_back(TDbValue::Int((int)header[4]));
+  for (int k = 5; k < 9; ++k) v.push_back(TDbValue::Real(header[k]));
   auto framed = [&](int s) {
-    sqlite3_bind_blob(st, p++, blob_ptr[blob], blob_len[blob], SQLITE_STATIC); ++blob;
-    for (int k = 0; k < AFX_N_STATS; ++k) sqlite3_bind_double(st, p++, stats[s][k]);
+    v.push_back(TDbValue::Blob(blob_ptr[blob], (size_t)blob_len[blob])); ++blob;
+    for (int k = 0; k < AFX_N_STATS; ++k) v.push_back(TDbValue::Real(stats[s][k]));
   };
   for (int s = 0; s < AFX_N_FS_MAIN; ++s) framed(s);
   for (int t = 0; t < 2; ++t) {
     framed(AFX_N_FS_MAIN + t);
-    for (int k = 0; k < 6; ++k) sqlite3_bind_double(st, p++, header[9 + 6 * t + k]);
+    for (int k = 0; k < 6; ++k) v.push_back(TDbValue::Real(header[9 + 6 * t + k]));
   }
-  sqlite3_bind_double(st, p++, header[21]); sqlite3_bind_double(st, p++, header[22]);
-  for (int v = 0; v < AFX_N_FV; ++v)
-    for (int k = 0; k < 1 + AFX_N_STATS; ++k) { sqlite3_bind_blob(st, p++, blob_ptr[blob], blob_len[blob], SQLITE_STATIC); ++blob; }
+  v.push_back(TDbValue::Real(header[21])); v.push_back(TDbValue::Real(header[22]));
+  for (int f = 0; f < AFX_N_FV; ++f)
+    for (int k = 0; k < 1 + AFX_N_STATS; ++k) { v.push_back(TDbValue::Blob(blob_ptr[blob], (size_t)blob_len[blob])); ++blob; }
+}
+
+static void step_values(sqlite3* db, sqlite3_stmt* st, const std::vector<TDbValue>& v)
+{
+  int p = 1;
+  for (const TDbValue& x : v) {
+    switch (x.mKind) {
+      case TDbValue::kNull: sqlite3_bind_null(st, p); break;
+      case TDbValue::kInt: sqlite3_bind_int64(st, p, x.mInt); break;
+      case TDbValue::kReal: sqlite3_bind_double(st, p, x.mReal); break;
+      case TDbValue::kText: sqlite3_bind_text(st, p, (const char*)x.mData, (int)x.mSize, SQLITE_STATIC); break;
+      case TDbValue::kBlob: sqlite3_bind_blob(st, p, x.mData, (int)x.mSize, SQLITE_STATIC); break;
+    }
+    ++p;
+  }
   const int rc = sqlite3_step(st);
   sqlite3_reset(st); sqlite3_clear_bindings(st);
   check(db, rc, "insert");
@@ -253,11 +275,14 @@ void TSqliteSampleDescriptorPool::InsertRow(const std::string& FileName, const s
                                             const double (*Stats)[AFX_N_STATS], const unsigned char* const* BlobPtr, const int* BlobLen)
 {
   Impl& I = *mImpl;
+  const std::string rel = RelativeFilenamePath(FileName);
+  row_values(I.values, rel, ModificationStatTime(FileName), FileType, Header, Stats, BlobPtr, BlobLen);
+  if (I.direct) { I.direct->AddRow(I.values); return; }
   PrepareInsert();
   const bool own_txn = (I.bulk == 0);
   if (own_txn) exec(I.db, "BEGIN");
   try {
-    insert_row(I.db, I.insert, RelativeFilenamePath(FileName), ModificationStatTime(FileName), FileType, Header, Stats, BlobPtr, BlobLen);
+    step_values(I.db, I.insert, I.values);
     if (own_txn) exec(I.db, "COMMIT");
   } catch (...) {
     sqlite3_reset(I.insert); sqlite3_clear_bindings(I.insert);
@@ -327,11 +352,42 @@ bool TSqliteSampleDescriptorPool::BeginBulkLoad()
 void TSqliteSampleDescriptorPool::EndBulkLoad()
 {
   Impl& I = *mImpl;
+  if (I.direct) {                                       // the file is complete: back to sqlite (open_db sets WAL / NORMAL)
+    std::unique_ptr<TDirectDbWriter> w = std::move(I.direct);
+    I.bulk_load = false;
+    w->Finish();
+    if (!open_db(&I.db, I.file, false)) throw TReadableException("Failed to reopen the database after the direct load");
+    return;
+  }
   if (!I.db || !I.bulk_load) return;
   if (I.bulk) { exec(I.db, "COMMIT"); I.bulk = 0; }
   exec(I.db, "PRAGMA journal_mode = WAL;");
   exec(I.db, "PRAGMA synchronous = NORMAL;");
   I.bulk_load = false;
+}
+
+// The same for an EMPTY database, without sqlite in the data path: the rows are written into the file in sqlite's format
+// (TDirectDbWriter), sequentially, one copy per row.  Until EndBulkLoad / Close only the Insert* calls and BeginBulk /
+// EndBulk (no-ops) may be used; a file name must not come twice (INSERT OR REPLACE needs the b-tree sqlite keeps).
+bool TSqliteSampleDescriptorPool::BeginDirectLoad()
+{
+  Impl& I = *mImpl;
+  if (!I.db || I.bulk_load || I.bulk || I.direct || NumberOfSamples() != 0) return false;
+  if (scalar_int(I.db, "PRAGMA auto_vacuum") != 0) return false;
+  if (scalar_int(I.db, "SELECT count(*) FROM sqlite_master WHERE tbl_name='assets'") != 2) return false;     // the table and its key index
+  const long long troot = scalar_int(I.db, "SELECT rootpage FROM sqlite_master WHERE type='table' AND name='assets'");
+  const long long iroot = scalar_int(I.db, "SELECT rootpage FROM sqlite_master WHERE type='index' AND tbl_name='assets'");
+  if (troot < 2 || iroot < 2) return false;
+  if (I.insert) sqlite3_finalize(I.insert);
+  if (I.insert_failed) sqlite3_finalize(I.insert_failed);
+  I.insert = I.insert_failed = nullptr;
+  exec(I.db, "PRAGMA wal_checkpoint(TRUNCATE);");
+  exec(I.db, "PRAGMA journal_mode = DELETE;");          // no log beside the file while it is written directly
+  sqlite3_close(I.db); I.db = nullptr;
+  try { I.direct.reset(new TDirectDbWriter(I.file, (uint32_t)troot, (uint32_t)iroot)); }
+  catch (...) { if (!open_db(&I.db, I.file, false)) I.db = nullptr; throw; }
+  I.bulk_load = true;
+  return true;
 }
 
 // Rows of other afec-ll.db files (written side by side by several sink threads) are appended to this one
@@ -357,6 +413,13 @@ int TSqliteSampleDescriptorPool::MergeFrom(const std::vector<std::string>& Shard
 void TSqliteSampleDescriptorPool::InsertFailedSample(const std::string& FileName, const std::string& Reason)
 {
   Impl& I = *mImpl;
+  if (I.direct) {
+    const std::string rel = RelativeFilenamePath(FileName), status = "error: " + Reason;
+    I.values.assign(ColumnNamesAndTypes().size(), TDbValue::Null());
+    I.values[0] = TDbValue::Text(rel); I.values[1] = TDbValue::Int(ModificationStatTime(FileName)); I.values[2] = TDbValue::Text(status);
+    I.direct->AddRow(I.values);
+    return;
+  }
   if (!I.db) throw TReadableException("Database is not open");
   if (!I.insert_failed)
     check(I.db, sqlite3_prepare_v2(I.db, "INSERT OR REPLACE into assets(filename, modtime, status) values (?,?,?)", -1, &I.insert_failed, nullptr), "prepare");

@@ -24,13 +24,17 @@ def run_crawler(args):
     return r.stdout
 
 
-def test_crawler_database_is_a_drop_in(tmp_path):
+@pytest.mark.parametrize("load", ["sqlite", "direct"])
+def test_crawler_database_is_a_drop_in(tmp_path, load):
+    """`direct`: the fresh database is written in sqlite's file format by the repo's own writer (--direct-load,
+    afec_b200/host/direct_db_writer.cpp); everything after that -- the comparison with the reference's database, the
+    incremental crawls that delete and replace rows -- goes through sqlite on that file."""
     d = str(tmp_path)
     os.makedirs(os.path.join(d, "sub"))
     paths = db_cases.write_files(d)
     shutil.move(paths[1], os.path.join(d, "sub", os.path.basename(paths[1])))
     db = os.path.join(d, "afec-ll.db")
-    out = run_crawler(["-l", "low", "-o", db, d])
+    out = run_crawler(["-l", "low", "-o", db] + (["--direct-load"] if load == "direct" else []) + [d])
     assert "4 files found, 4 to analyse" in out
     stats = json.loads(out.strip().splitlines()[-1])
     assert stats["files"] == 3 and stats["failed"] == 1
@@ -45,6 +49,7 @@ def test_crawler_database_is_a_drop_in(tmp_path):
     c = sqlite3.connect(db)
     names = sorted(r[0] for r in c.execute("select filename from assets"))
     assert "sub/pad_stereo.wav" in names and "kick.wav" in names          # relative to the database directory
+    assert c.execute("PRAGMA integrity_check").fetchall() == [("ok",)]
     c.close()
 
     # incremental crawl (Crawler.cpp:934-998): nothing to do, then one modified and one vanished file

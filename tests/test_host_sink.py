@@ -195,3 +195,86 @@ def test_page_size_option_changes_the_file_not_the_rows(host, tmp_path, monkeypa
         assert con.execute("PRAGMA page_size").fetchone()[0] == expect, value
         assert con.execute("PRAGMA integrity_check").fetchone()[0] == "ok"
         con.close()
+
+
+def _sink(host):
+    host.afxh_sink_bench2.restype = C.c_double
+    host.afxh_sink_bench2.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    return host.afxh_sink_bench2
+
+
+@pytest.mark.parametrize("page_size", [None, "32768", "1024"])
+@pytest.mark.parametrize("n,F", [(1, 3), (7, 40), (230, 12), (60, 260), (2500, 1)])
+def test_direct_load_writes_the_database_sqlite_would(host, tmp_path, monkeypatch, n, F, page_size):
+    """TSqliteSampleDescriptorPool::BeginDirectLoad (afec-b200-crawler --direct-load): the rows of a fresh database are written
+    in sqlite's FILE FORMAT by this repo's writer (direct_db_writer.cpp: table leaves + overflow chains, the filename index,
+    interior pages, header) instead of through sqlite.  The result must be the database sqlite would have written: every
+    column of every row (succeeded and failed ones) equal to the WAL path's, the reference's pragmas, sqlite's own integrity
+    check clean (it walks both b-trees, every overflow chain, the free list and the index / table correspondence), look-ups
+    through the index, and sqlite must be able to go on editing the file.  Sizes: one leaf as root, several leaves, an index
+    of more than one level (2500 rows), rows of ~400 KB; three page sizes."""
+    bench = _sink(host)
+    if page_size:
+        monkeypatch.setenv("AFX_SINK_PAGE_SIZE", page_size)
+    want_db, got_db = str(tmp_path / "sqlite.db"), str(tmp_path / "direct.db")
+    assert bench(want_db.encode(), n, F, 8 * F, 16, 8 | 0, 1, None) > 0                 # row by row through sqlite, WAL, host packing
+    assert bench(got_db.encode(), n, F, 8 * F, 16, 8 | 4 | 2, 1, None) > 0              # direct load, rows arrive packed
+    want, pragmas = _dump_table(want_db)
+    got, pr = _dump_table(got_db)
+    assert len(got) == n + (n + 2) // 3 and got == want and pr == pragmas
+    con = sqlite3.connect(got_db)
+    assert con.execute("PRAGMA integrity_check").fetchall() == [("ok",)]
+    assert con.execute("PRAGMA page_size").fetchone()[0] == int(page_size or 4096)
+    for i in (0, n // 2, n - 1):
+        name = "/nonexistent/f%07d.wav" % i
+        plan = " ".join(r[-1] for r in con.execute("EXPLAIN QUERY PLAN SELECT status FROM assets WHERE filename = ?", (name,)))
+        assert "sqlite_autoindex_assets_1" in plan
+        assert con.execute("SELECT status FROM assets WHERE filename = ?", (name,)).fetchall() == [("succeeded",)]
+    assert con.execute("SELECT status FROM assets WHERE filename = '/nonexistent/bad0000000.wav'").fetchall() == [("error: Sample failed to load: test",)]
+    # sqlite goes on with the file: delete, replace, insert
+    con.execute("DELETE FROM assets WHERE filename = '/nonexistent/f0000000.wav'")
+    con.execute("INSERT OR REPLACE INTO assets(filename, modtime, status) VALUES ('/nonexistent/bad0000000.wav', 7, 'error: again')")
+    con.execute("INSERT INTO assets(filename, modtime, status) VALUES ('zzz', 7, 'error: new')")
+    con.commit()
+    assert con.execute("PRAGMA integrity_check").fetchall() == [("ok",)]
+    assert con.execute("SELECT count(*) FROM assets").fetchone()[0] == len(got)
+    con.close()
+
+
+def test_direct_load_needs_an_empty_database_and_unique_names(host, tmp_path):
+    bench = _sink(host)
+    db = str(tmp_path / "twice.db")
+    assert bench(db.encode(), 4, 10, 80, 2, 4 | 2, 1, None) > 0
+    assert bench(db.encode(), 4, 10, 80, 2, 4 | 2, 1, None) == -3.0           # not empty any more: BeginDirectLoad declines
+    rows, _ = _dump_table(db)
+    assert len(rows) == 4
+    # the same file name twice in one load: a direct load has no b-tree to replace the row in and refuses the second one
+    # (the crawler passes every name once); the rows written so far are intact
+    db2 = str(tmp_path / "dup.db")
+    assert bench(db2.encode(), 4, 10, 80, 2, 16 | 4 | 2, 1, None) > 0         # -4 would mean the duplicate was accepted
+    rows, _ = _dump_table(db2)
+    assert len(rows) == 4 and all(r[2] == "succeeded" for r in rows.values())
+    con = sqlite3.connect(db2)
+    assert con.execute("PRAGMA integrity_check").fetchall() == [("ok",)]
+    con.close()
+    db3 = str(tmp_path / "dup_sqlite.db")                                      # through sqlite the second row replaces the first
+    assert bench(db3.encode(), 4, 10, 80, 2, 16 | 2, 1, None) > 0
+    rows, _ = _dump_table(db3)
+    assert len(rows) == 4 and sum(r[2] == "error: again" for r in rows.values()) == 1
+
+
+def test_direct_load_shards_and_merge(host, tmp_path):
+    """Direct loads of several shard files side by side, merged through sqlite afterwards (ATTACH + INSERT ... SELECT reads the
+    directly written files): the rows are those of one WAL-path database."""
+    bench = _sink(host)
+    host.afxh_merge_shards.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int]
+    n, F = 41, 30
+    base = str(tmp_path / "plain.db")
+    assert bench(base.encode(), n, F, 8 * F, 1, 0, 1, None) > 0
+    db = str(tmp_path / "sharded.db")
+    assert bench(db.encode(), n, F, 8 * F, 5, 4 | 2, 3, None) > 0
+    names = [(db + ".%d" % k).encode() for k in (1, 2)]
+    assert host.afxh_merge_shards(db.encode(), (C.c_char_p * 2)(*names), 2, 1) > 0
+    got, pr = _dump_table(db)
+    want, pragmas = _dump_table(base)
+    assert got == want and pr == pragmas
