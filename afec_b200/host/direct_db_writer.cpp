@@ -73,8 +73,10 @@ TDirectDbWriter::TDirectDbWriter(const std::string& FileName, uint32_t TableRoot
   mPageSize = get_be16(mHeaderBuf.data() + 16); if (mPageSize == 1) mPageSize = 65536;
   mUsable = mPageSize - mHeaderBuf[20];
   const uint32_t pages = get_be32(mHeaderBuf.data() + 28);
+  // a file longer than its header says is what a load that was cut off leaves behind (the header is written last): the tail
+  // is not part of the database and is written over
   const bool sane = mPageSize >= 512 && (mPageSize & (mPageSize - 1)) == 0 && mUsable >= 480 && fstat(mFd, &st) == 0 && pages >= 3 &&
-                    (uint64_t)st.st_size == (uint64_t)pages * mPageSize && get_be32(mHeaderBuf.data() + 52) == 0 &&          // no auto-vacuum: no pointer-map pages
+                    (uint64_t)st.st_size >= (uint64_t)pages * mPageSize && get_be32(mHeaderBuf.data() + 52) == 0 &&          // no auto-vacuum: no pointer-map pages
                     get_be32(mHeaderBuf.data() + 56) == 1 && TableRoot >= 2 && IndexRoot >= 2 && TableRoot <= pages && IndexRoot <= pages;
   if (!sane) { close(mFd); mFd = -1; throw TReadableException("direct database load: unexpected database header"); }
   mNextPage = pages + 1;

@@ -385,7 +385,10 @@ bool TSqliteSampleDescriptorPool::BeginDirectLoad()
   exec(I.db, "PRAGMA journal_mode = DELETE;");          // no log beside the file while it is written directly
   sqlite3_close(I.db); I.db = nullptr;
   try { I.direct.reset(new TDirectDbWriter(I.file, (uint32_t)troot, (uint32_t)iroot)); }
-  catch (...) { if (!open_db(&I.db, I.file, false)) I.db = nullptr; throw; }
+  catch (const std::exception&) {                       // not a file this writer takes: back to sqlite, the caller loads through it
+    if (!open_db(&I.db, I.file, false)) { I.db = nullptr; throw; }
+    return false;
+  }
   I.bulk_load = true;
   return true;
 }

@@ -392,20 +392,25 @@ def crawl_with_sink(pcms, wl, device, n_files=600):
             oracle.write_wav(os.path.join(d, "f%05d.wav" % i), pcms[i], wl.get("rate", 44100))
             audio_s += len(pcms[i]) / float(wl.get("rate", 44100))
         out = {}
-        for tag, extra in (("one_writer", []), ("four_shards", ["--shards", "4"]), ("one_writer_32k_pages", ["--page-size", "32768"])):
-            db = os.path.join(d, tag + ".db")
-            t0 = time.perf_counter()
-            r = subprocess.run([afx_build.CRAWLER, "-o", db, "--hop", str(wl["hop"]), "--devices", str(device), "-j", "3"] + extra + [d],
-                               capture_output=True, text=True, timeout=600)
-            wall = time.perf_counter() - t0
-            js = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-            size = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d) if f.startswith(tag + ".db"))
-            out[tag] = {"value": js["audio_seconds"] / 3600.0 / js["seconds"], "unit": "audio-hours/s", "files": js["files"],
-                        "seconds": js["seconds"], "wall_seconds": wall, "rows_per_s": js["files"] / js["seconds"],
-                        "db_mb_per_s": size / js["seconds"] / 1e6}
+        for tag, extra in (("one_writer", []), ("four_shards", ["--shards", "4"]), ("one_writer_32k_pages", ["--page-size", "32768"]),
+                           ("one_writer_direct_load", ["--direct-load"]), ("four_shards_direct_load", ["--shards", "4", "--direct-load"])):
+            try:
+                db = os.path.join(d, tag + ".db")
+                t0 = time.perf_counter()
+                r = subprocess.run([afx_build.CRAWLER, "-o", db, "--hop", str(wl["hop"]), "--devices", str(device), "-j", "3"] + extra + [d],
+                                   capture_output=True, text=True, timeout=600)
+                wall = time.perf_counter() - t0
+                js = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+                size = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d) if f.startswith(tag + ".db"))
+                out[tag] = {"value": js["audio_seconds"] / 3600.0 / js["seconds"], "unit": "audio-hours/s", "files": js["files"],
+                            "seconds": js["seconds"], "wall_seconds": wall, "rows_per_s": js["files"] / js["seconds"],
+                            "db_mb_per_s": size / js["seconds"] / 1e6}
+            except Exception as e:                      # one variant failing must not take the others (or the bench line) with it
+                out[tag] = {"value": 0.0, "unit": "audio-hours/s", "error": repr(e)[:200]}
         best = max(out, key=lambda k: out[k]["value"])
         return dict(out[best], writer=best, variants=out, sample="%d WAV files of the workload's corpus (%.0f s audio) on %s" % (min(n_files, len(pcms)), audio_s, root),
-                    path="afec-b200-crawler: decode threads -> pinned ring -> GPU (rows packed on the device) -> sqlite sink (journal-less bulk load)")
+                    path="afec-b200-crawler: decode threads -> pinned ring -> GPU (rows packed on the device) -> afec-ll.db (variants: journal-less "
+                         "bulk load through sqlite with one / four writers, 32 KB pages, the file written directly in sqlite's format)")
     finally:
         shutil.rmtree(d, ignore_errors=True)
 

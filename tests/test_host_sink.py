@@ -278,3 +278,23 @@ def test_direct_load_shards_and_merge(host, tmp_path):
     got, pr = _dump_table(db)
     want, pragmas = _dump_table(base)
     assert got == want and pr == pragmas
+
+
+def test_direct_load_after_a_load_that_was_cut_off(host, tmp_path):
+    """The header (page count) is written last: a direct load that dies leaves an EMPTY database with a tail of pages that are
+    not part of it.  The next load writes over that tail."""
+    bench = _sink(host)
+    db = str(tmp_path / "cut.db")
+    assert bench(db.encode(), 0, 5, 40, 2, 2, 1, None) >= 0                   # schema only
+    con = sqlite3.connect(db); con.execute("PRAGMA wal_checkpoint(TRUNCATE)"); con.close()
+    with open(db, "ab") as f:
+        f.write(os.urandom(4096 * 37 + 100))
+    con = sqlite3.connect(db)
+    assert con.execute("SELECT count(*) FROM assets").fetchone()[0] == 0 and con.execute("PRAGMA integrity_check").fetchall() == [("ok",)]
+    con.close()
+    assert bench(db.encode(), 9, 20, 160, 2, 4 | 2, 1, None) > 0
+    con = sqlite3.connect(db)
+    assert con.execute("PRAGMA integrity_check").fetchall() == [("ok",)]
+    assert con.execute("SELECT count(*) FROM assets").fetchone()[0] == 9
+    con.close()
+    assert os.path.getsize(db) % 4096 == 0
