@@ -242,3 +242,22 @@ int afxh_extract_one_in_parts(const char* db, const char* filename, int hop, con
 }
 
 }  // extern "C"
+
+// test hook: n failed rows with file names of `name_len` characters through a direct load (long names make the index records
+// spill into overflow pages); returns 0, -1 when the pool declines the direct load, -2 on an exception
+extern "C" int afxh_direct_failed_rows(const char* db, int n, int name_len)
+{
+  try {
+    afec::TSqliteSampleDescriptorPool pool;
+    if (!pool.Open(db)) return -1;
+    if (!pool.BeginDirectLoad()) return -1;
+    for (int i = 0; i < n; ++i) {
+      char tail[32]; snprintf(tail, sizeof(tail), "%07d.wav", (i * 7919) % n);      // not in sorted order
+      std::string name = "/nonexistent/" + std::string((size_t)std::max(0, name_len - 24), (char)('a' + i % 3)) + tail;
+      pool.InsertFailedSample(name, "Sample failed to load: test");
+    }
+    pool.EndBulkLoad();
+    pool.Close();
+    return 0;
+  } catch (const std::exception&) { return -2; }
+}

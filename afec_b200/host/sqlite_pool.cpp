@@ -418,7 +418,8 @@ void TSqliteSampleDescriptorPool::InsertFailedSample(const std::string& FileName
   Impl& I = *mImpl;
   if (I.direct) {
     const std::string rel = RelativeFilenamePath(FileName), status = "error: " + Reason;
-    I.values.assign(ColumnNamesAndTypes().size(), TDbValue::Null());
+    static const size_t kColumns = ColumnNamesAndTypes().size();
+    I.values.assign(kColumns, TDbValue::Null());
     I.values[0] = TDbValue::Text(rel); I.values[1] = TDbValue::Int(ModificationStatTime(FileName)); I.values[2] = TDbValue::Text(status);
     I.direct->AddRow(I.values);
     return;

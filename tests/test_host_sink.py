@@ -298,3 +298,27 @@ def test_direct_load_after_a_load_that_was_cut_off(host, tmp_path):
     assert con.execute("SELECT count(*) FROM assets").fetchone()[0] == 9
     con.close()
     assert os.path.getsize(db) % 4096 == 0
+
+
+@pytest.mark.parametrize("page_size,name_len,n", [(None, 60, 900), (None, 1500, 400), (None, 3900, 60), ("1024", 400, 700), ("512", 200, 1200)])
+def test_direct_load_index_with_long_names(host, tmp_path, monkeypatch, page_size, name_len, n):
+    """File names longer than an index page's local limit (1002 bytes at 4096-byte pages, 230 at 1024, 102 at 512) make the index
+    records spill into overflow pages, in leaves and -- for the keys that move up -- in interior pages; names arrive unsorted.
+    The prime 7919 permutes the numbering, so n must not be a multiple of it."""
+    if page_size:
+        monkeypatch.setenv("AFX_SINK_PAGE_SIZE", page_size)
+    host.afxh_direct_failed_rows.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    db = str(tmp_path / "names.db")
+    assert host.afxh_direct_failed_rows(db.encode(), n, name_len) == 0
+    con = sqlite3.connect(db)
+    assert con.execute("PRAGMA integrity_check").fetchall() == [("ok",)]
+    assert con.execute("SELECT count(*), count(DISTINCT filename), min(length(filename)), max(length(filename)) FROM assets").fetchone() == (n, n, max(24, name_len), max(24, name_len))
+    names = [r[0] for r in con.execute("SELECT filename FROM assets ORDER BY filename")]          # walks the index
+    assert names == sorted(names)
+    for probe in (names[0], names[n // 2], names[-1]):
+        assert con.execute("SELECT status FROM assets WHERE filename = ?", (probe,)).fetchall() == [("error: Sample failed to load: test",)]
+    con.execute("DELETE FROM assets WHERE filename = ?", (names[1],))
+    con.execute("INSERT INTO assets(filename, modtime, status) VALUES (?, 1, 'error: new')", (names[1] + "x",))
+    con.commit()
+    assert con.execute("PRAGMA integrity_check").fetchall() == [("ok",)]
+    con.close()
