@@ -116,11 +116,6 @@ int main(int argc, char** argv)
     TGpuSampleAnalyser analyser(44100, 2048, hop, devices, slots, !host_pack);
     if (decode_threads) analyser.SetDecodeThreads(decode_threads);
     // a fresh database is filled without a journal (TSqliteSampleDescriptorPool::BeginBulkLoad), shards always are fresh
-    if (direct_load) {                                  // a direct load cannot replace a row: every file name once
-      std::set<std::string> seen; std::vector<std::string> uniq;
-      for (const auto& f : todo) if (seen.insert(f).second) uniq.push_back(f);
-      todo.swap(uniq);
-    }
     const bool bulk_main = (direct_load && pool.BeginDirectLoad()) || pool.BeginBulkLoad();
     std::vector<std::unique_ptr<TSqliteSampleDescriptorPool>> shard_pools;
     std::vector<std::string> shard_files;

@@ -39,9 +39,11 @@ public:
   // root page is `TableRoot` and its primary-key index (text key = column 0, then the rowid) with root `IndexRoot`
   TDirectDbWriter(const std::string& FileName, uint32_t TableRoot, uint32_t IndexRoot);
   ~TDirectDbWriter();
-  // one row, all columns in table order; column 0 is the TEXT primary key (a key seen before throws)
+  // one row, all columns in table order; column 0 is the TEXT primary key (a key seen before throws: see HasKey -- the pool
+  // keeps such rows aside and replaces through sqlite afterwards)
   void AddRow(const std::vector<TDbValue>& Values);
   long long Rows() const { return mRowId; }
+  bool HasKey(const std::string& Key) const { return mKeys.count(Key) != 0; }
   // writes the interior pages, both roots and the header; the file is complete and closed afterwards
   void Finish();
 

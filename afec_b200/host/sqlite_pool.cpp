@@ -28,7 +28,23 @@ struct TSqliteSampleDescriptorPool::Impl {
   std::vector<unsigned char> blob;    // one row's msgpack blobs, back to back (bound SQLITE_STATIC until the step)
   std::unique_ptr<TDirectDbWriter> direct;   // BeginDirectLoad .. EndBulkLoad: rows go straight into the file (db is closed meanwhile)
   std::vector<TDbValue> values;
+  // rows of a direct load whose file name came before in the same load: kept (deep copies) and put through sqlite's INSERT OR
+  // REPLACE when the load ends -- the direct writer has no b-tree to replace a row in
+  struct Deferred { std::vector<TDbValue> values; std::vector<std::string> store; };
+  std::vector<Deferred> deferred;
+  void add_direct(const std::string& key);
 };
+
+void TSqliteSampleDescriptorPool::Impl::add_direct(const std::string& key)
+{
+  if (!direct->HasKey(key)) { direct->AddRow(values); return; }
+  deferred.emplace_back();
+  Deferred& d = deferred.back();
+  d.values = values;
+  d.store.reserve(values.size());
+  for (TDbValue& v : d.values)
+    if (v.mKind == TDbValue::kText || v.mKind == TDbValue::kBlob) { d.store.emplace_back((const char*)v.mData, v.mSize); v.mData = d.store.back().data(); }
+}
 
 static void check(sqlite3* db, int rc, const char* what)
 {
@@ -277,7 +293,7 @@ void TSqliteSampleDescriptorPool::InsertRow(const std::string& FileName, const s
   Impl& I = *mImpl;
   const std::string rel = RelativeFilenamePath(FileName);
   row_values(I.values, rel, ModificationStatTime(FileName), FileType, Header, Stats, BlobPtr, BlobLen);
-  if (I.direct) { I.direct->AddRow(I.values); return; }
+  if (I.direct) { I.add_direct(rel); return; }
   PrepareInsert();
   const bool own_txn = (I.bulk == 0);
   if (own_txn) exec(I.db, "BEGIN");
@@ -357,6 +373,14 @@ void TSqliteSampleDescriptorPool::EndBulkLoad()
     I.bulk_load = false;
     w->Finish();
     if (!open_db(&I.db, I.file, false)) throw TReadableException("Failed to reopen the database after the direct load");
+    if (!I.deferred.empty()) {                          // names that came twice: the later row replaces the earlier one, as it would have
+      std::vector<Impl::Deferred> rows;
+      rows.swap(I.deferred);
+      PrepareInsert();
+      exec(I.db, "BEGIN");
+      try { for (const Impl::Deferred& d : rows) step_values(I.db, I.insert, d.values); exec(I.db, "COMMIT"); }
+      catch (...) { try { exec(I.db, "ROLLBACK"); } catch (...) {} throw; }
+    }
     return;
   }
   if (!I.db || !I.bulk_load) return;
@@ -368,7 +392,8 @@ void TSqliteSampleDescriptorPool::EndBulkLoad()
 
 // The same for an EMPTY database, without sqlite in the data path: the rows are written into the file in sqlite's format
 // (TDirectDbWriter), sequentially, one copy per row.  Until EndBulkLoad / Close only the Insert* calls and BeginBulk /
-// EndBulk (no-ops) may be used; a file name must not come twice (INSERT OR REPLACE needs the b-tree sqlite keeps).
+// EndBulk (no-ops) may be used; a row whose file name came before in the same load is kept aside and goes through sqlite's
+// INSERT OR REPLACE when the load ends.
 bool TSqliteSampleDescriptorPool::BeginDirectLoad()
 {
   Impl& I = *mImpl;
@@ -421,7 +446,7 @@ void TSqliteSampleDescriptorPool::InsertFailedSample(const std::string& FileName
     static const size_t kColumns = ColumnNamesAndTypes().size();
     I.values.assign(kColumns, TDbValue::Null());
     I.values[0] = TDbValue::Text(rel); I.values[1] = TDbValue::Int(ModificationStatTime(FileName)); I.values[2] = TDbValue::Text(status);
-    I.direct->AddRow(I.values);
+    I.add_direct(rel);
     return;
   }
   if (!I.db) throw TReadableException("Database is not open");

@@ -241,26 +241,25 @@ def test_direct_load_writes_the_database_sqlite_would(host, tmp_path, monkeypatc
     con.close()
 
 
-def test_direct_load_needs_an_empty_database_and_unique_names(host, tmp_path):
+def test_direct_load_needs_an_empty_database_and_takes_a_name_twice(host, tmp_path):
     bench = _sink(host)
     db = str(tmp_path / "twice.db")
     assert bench(db.encode(), 4, 10, 80, 2, 4 | 2, 1, None) > 0
     assert bench(db.encode(), 4, 10, 80, 2, 4 | 2, 1, None) == -3.0           # not empty any more: BeginDirectLoad declines
     rows, _ = _dump_table(db)
     assert len(rows) == 4
-    # the same file name twice in one load: a direct load has no b-tree to replace the row in and refuses the second one
-    # (the crawler passes every name once); the rows written so far are intact
-    db2 = str(tmp_path / "dup.db")
-    assert bench(db2.encode(), 4, 10, 80, 2, 16 | 4 | 2, 1, None) > 0         # -4 would mean the duplicate was accepted
-    rows, _ = _dump_table(db2)
-    assert len(rows) == 4 and all(r[2] == "succeeded" for r in rows.values())
+    # the same file name twice in one load: the direct writer has no b-tree to replace a row in, so the pool keeps the later row
+    # aside and puts it through sqlite's INSERT OR REPLACE when the load ends -- the database is the one sqlite alone writes
+    db2, db3 = str(tmp_path / "dup.db"), str(tmp_path / "dup_sqlite.db")
+    assert bench(db2.encode(), 4, 10, 80, 2, 16 | 4 | 2, 1, None) > 0
+    assert bench(db3.encode(), 4, 10, 80, 2, 16 | 2, 1, None) > 0
+    rows, pr = _dump_table(db2)
+    want, pragmas = _dump_table(db3)
+    assert rows == want and pr == pragmas
+    assert len(rows) == 4 and sum(r[2] == "error: again" for r in rows.values()) == 1
     con = sqlite3.connect(db2)
     assert con.execute("PRAGMA integrity_check").fetchall() == [("ok",)]
     con.close()
-    db3 = str(tmp_path / "dup_sqlite.db")                                      # through sqlite the second row replaces the first
-    assert bench(db3.encode(), 4, 10, 80, 2, 16 | 2, 1, None) > 0
-    rows, _ = _dump_table(db3)
-    assert len(rows) == 4 and sum(r[2] == "error: again" for r in rows.values()) == 1
 
 
 def test_direct_load_shards_and_merge(host, tmp_path):
