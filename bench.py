@@ -405,6 +405,9 @@ def crawl_with_sink(pcms, wl, device, n_files=600):
                 out[tag] = {"value": js["audio_seconds"] / 3600.0 / js["seconds"], "unit": "audio-hours/s", "files": js["files"],
                             "seconds": js["seconds"], "wall_seconds": wall, "rows_per_s": js["files"] / js["seconds"],
                             "db_mb_per_s": size / js["seconds"] / 1e6}
+                for f in os.listdir(d):                 # the next variant starts with the RAM disk as this one found it
+                    if f.startswith(tag + ".db"):
+                        os.remove(os.path.join(d, f))
             except Exception as e:                      # one variant failing must not take the others (or the bench line) with it
                 out[tag] = {"value": 0.0, "unit": "audio-hours/s", "error": repr(e)[:200]}
         best = max(out, key=lambda k: out[k]["value"])
