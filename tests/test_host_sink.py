@@ -321,3 +321,29 @@ def test_direct_load_index_with_long_names(host, tmp_path, monkeypatch, page_siz
     con.commit()
     assert con.execute("PRAGMA integrity_check").fetchall() == [("ok",)]
     con.close()
+
+
+def test_direct_load_under_sanitizers(tmp_path):
+    """The direct writer handles raw page buffers: the same load (packed-on-host rows, failed rows, a name twice, long names, three
+    page sizes) under AddressSanitizer + UndefinedBehaviorSanitizer must report nothing and leave a database sqlite accepts."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    hostdir = os.path.join(os.path.dirname(here), "afec_b200", "host")
+    exe = str(tmp_path / "harness")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
+           "-I" + hostdir, "-I" + os.path.join(os.path.dirname(here), "include"), os.path.join(here, "direct_load_harness.cpp"),
+           os.path.join(hostdir, "sqlite_pool.cpp"), os.path.join(hostdir, "direct_db_writer.cpp"), os.path.join(hostdir, "descriptors.cpp"),
+           afx_build.SQLITE, "-pthread", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("this g++ has no sanitizer runtime")
+    assert r.returncode == 0, r.stderr[-2000:]
+    for page_size, rows, frames, name_len in (("4096", 300, 40, 60), ("4096", 40, 300, 2000), ("512", 200, 10, 700), ("65536", 150, 30, 24)):
+        db = str(tmp_path / ("s%s_%d.db" % (page_size, rows)))
+        env = dict(os.environ, AFX_SINK_PAGE_SIZE=page_size, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0")
+        r = subprocess.run([exe, db, str(rows), str(frames), str(name_len)], capture_output=True, text=True, env=env)
+        assert r.returncode == 0 and "ERROR" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
+        con = sqlite3.connect(db)
+        assert con.execute("PRAGMA integrity_check").fetchall() == [("ok",)]
+        assert con.execute("SELECT count(*), sum(status = 'error: twice') FROM assets").fetchone() == (rows, 1)
+        con.close()
